@@ -1,0 +1,84 @@
+// backend.h -- the device side of libdemcmc_b200 as seen by the host engine: memory, streams and
+// one launcher per kernel.  kernels.cu implements it with CUDA for sm_100a.  (tests/emu/ holds a
+// host-only test double of the same interface so the engine's host logic can be unit-tested on a
+// machine without a GPU; it is never built into or loaded by the product.)
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "de_types.h"
+
+namespace de {
+namespace be {
+
+const char *name();                       // "cuda-sm100a" or "emu"
+int device_count();
+int set_device(int dev);                  // 0 or error
+const char *last_error();
+
+void *dmalloc(size_t bytes);              // nullptr on failure
+void dfree(void *p);
+void *hmalloc_pinned(size_t bytes);
+void hfree_pinned(void *p);
+int h2d(void *dst, const void *src, size_t bytes);         // on the engine stream, async if src pinned
+int d2h(void *dst, const void *src, size_t bytes);         // synchronous
+int d2d(void *dst, const void *src, size_t bytes);
+int dzero(void *dst, size_t bytes);
+int sync();
+
+void *event_create();
+void event_destroy(void *ev);
+int event_record(void *ev);               // on the engine stream
+int event_wait(void *ev);                 // host waits
+
+// CUDA-event stopwatch on the engine stream
+int timer_start();
+int timer_stop(double *ms);
+
+// ---- kernels ----------------------------------------------------------------------------------
+// transposes MVN / hierarchical data into the k-major padded layout of the SSD kernel
+int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m /* xT allocated */);
+// init_particle: weights of n particles theta[n][d] -> w[n] (also demcmc_eval)
+int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior,
+                double *w, double *scratch_part);
+// select_base preparation on the sweep-start weights: cw[P] running sums, tot[G]; th[P] is scratch
+int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
+// propose -> loglik -> accept for one level of one sweep
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv);
+int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part);
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv);
+// migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
+// [position][d+3] = {theta..., weight, id, accept flag}
+int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);
+int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *theta, const double *w,
+                      const int32_t *id, const uint8_t *acc, double *stage);
+int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
+                       double *w, int32_t *id, uint8_t *acc);
+// history rows [n_rows][P][d] by slot -> reference layout [P][d][n_rows] by id (utilities.jl:34)
+int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
+                         int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,
+                         double *samples, double *lp, uint8_t *accept);
+// particle algebra known-answer ops (single warp each)
+int launch_op_project(const double *p1, const double *p2, int d, double *out);
+int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,
+                      int d, double *out, double *log_adj);
+int launch_op_de(const double *pt, const double *pm, const double *pn, const double *pb, double g1, double g2,
+                 const double *b, int d, double *out);
+int launch_op_reset(const double *prop, const double *pt, const uint8_t *mask, int d, double *out);
+int launch_op_accept(const double *wp, const double *wc, const double *adj, const double *u, int n, uint8_t *out);
+int launch_op_select(const double *w, int n, double u, int32_t *base_idx, int32_t *mig_idx);
+// roofline probes
+int fp64_peak(double *tflops);
+int copy_peak(double *gbs);
+
+int64_t launch_count();                   // kernels launched so far (for demcmc_counters)
+
+// ---- cross-rank migration (NCCL over NVLink) ---------------------------------------------------
+int comm_unique_id(uint8_t id[128]);
+int comm_init(const uint8_t id[128], int rank, int n_ranks, void **comm);
+int comm_destroy(void *comm);
+// grouped send/recv of stage rows: for each position i, src_rank[i] sends row send_pos[i] to dst_rank[i]
+int comm_exchange(void *comm, int rank, int n, const int *src_rank, const int *dst_rank, double *stage_send,
+                  double *stage_recv, int row_len);
+
+} // namespace be
+} // namespace de

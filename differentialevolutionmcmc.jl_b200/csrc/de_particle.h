@@ -1,0 +1,201 @@
+// de_particle.h -- the per-particle parts of the population step (proposal, bounds, prior,
+// Metropolis accept, state write), written once against a "cooperating lanes" policy C:
+//   C::lane(), C::width()      this lane and the number of lanes sharing one particle
+//   C::sum(x)                  sum over lanes, same value returned to every lane, fixed order
+//   C::all(b)                  logical AND over lanes
+//   C::min_int(i)              minimum over lanes
+//   C::sync()                  makes the lanes' global-memory writes visible to each other
+// kernels.cu instantiates it with a 32-lane warp; the host test double with a single lane.
+#pragma once
+#include "de_types.h"
+
+namespace de {
+
+struct SerialLanes {
+    DE_HD int lane() const { return 0; }
+    DE_HD int width() const { return 1; }
+    DE_HD double sum(double x) const { return x; }
+    DE_HD bool all(bool b) const { return b; }
+    DE_HD int min_int(int x) const { return x; }
+    DE_HD void sync() const {}
+};
+
+// log-likelihood from the reduced kernel output `total` (sum of per-observation log densities for
+// the pointwise kernels; sum of squared differences for MVN / hierarchical normal)
+DE_HD double finalize_ll(const ModelDev &m, const double *theta, double total)
+{
+    switch (m.kind) {
+    case M_MVNORMAL: {
+        // Multivariate_Guassian_Example.jl:31-33: per column -(d*log2pi + d*log(s^2))/2 - sqmahal/2
+        const double sig = theta[m.n_dim], s2 = sig * sig, dm = (double)m.n_dim;
+        const double c0 = -(dm * DE_LOG2PI + dm * log(s2)) / 2.0;
+        return (double)m.n_obs * c0 - (total / s2) / 2.0;
+    }
+    case M_HIER: {
+        // Hierarchical_Example.jl:36-44: sum_s sum_j logpdf(Normal(0,sigma), y_sj - (mu + b_s))
+        const double sig = theta[m.n_dim + 2];
+        return -(double)m.n_obs * (DE_LOG2PI / 2.0 + log(sig)) - (total / (sig * sig)) / 2.0;
+    }
+    case M_BINOMIAL: return binomial_ll(m.binom_N, m.binom_k, theta[0]);
+    default: return total;
+    }
+}
+
+// in_bounds (utilities.jl:70-78) + prior_loglike of one parameter vector
+template <class C>
+DE_HD void bounds_and_prior(const C &co, const ConfigDev &cfg, const ModelDev &m, const double *theta, bool &inb, double &prior)
+{
+    bool ok = true;
+    double ps = 0.0;
+    for (int k = co.lane(); k < cfg.d; k += co.width()) {
+        const double v = theta[k];
+        ok = ok && (v >= cfg.lo[k] && v <= cfg.hi[k]);
+        const Prior pr = m.prior[k];
+        ps += prior_elem(pr, v, pr.kind == PRIOR_NORMAL_REF ? theta[pr.ref] : 0.0);
+    }
+    inb = co.all(ok);
+    prior = co.sum(ps);
+}
+
+// crossover!(model,de,group,pt[,block]) / mutation! up to evaluate_fitness!: writes the proposal,
+// its prior, bounds flag and snooker adjustment (crossover.jl:30-99,154-273,301-352; mutation.jl:13-25)
+template <class C>
+DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, int p)
+{
+    const int Np = cfg.Np, d = cfg.d;
+    const int g = p / Np, j = p - g * Np;
+    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
+    const bool mutate = ctx.mutate[g] != 0;
+    const double *tcur = ctx.cur_theta + (size_t)p * d;
+    double *prop = ctx.prop_theta + (size_t)p * d;
+
+    int kind, i0 = -1, i1 = -1, i2 = -1;
+    double g1 = 0.0, g2 = 0.0, u_base = 0.0;
+    if (ctx.replay) {
+        kind = ctx.t_kind[p];
+        i0 = ctx.t_idx[p * 3]; i1 = ctx.t_idx[p * 3 + 1]; i2 = ctx.t_idx[p * 3 + 2];
+        g1 = ctx.t_g1[p]; g2 = ctx.t_g2[p];
+    } else {
+        const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
+        kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; u_base = pl.u_base;
+        if (kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, kind, cfg.proposal, ctx.in_burnin != 0, d); g1 = gg.a; g2 = gg.b; }
+    }
+    // a donor that sits before the target in the sweep already holds this sweep's value
+    const size_t gbase = (size_t)g * Np;
+#define DE_DONOR(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
+
+    const bool is_mut = kind == KIND_MUTATION;
+    double r1 = 0.0, r2 = 0.0;
+    const double *pm = nullptr, *pn = nullptr, *pb = nullptr, *pz = nullptr;
+    bool has_base = false;
+    if (kind == KIND_DE) {
+        pm = DE_DONOR(i1); pn = DE_DONOR(i2);
+        has_base = cfg.proposal == 0 && ctx.in_burnin != 0;
+        if (has_base) {
+            if (ctx.exact_base) pb = DE_DONOR(i0);
+            else {
+                // select_base (crossover.jl:282-289) on the sweep-start weights: first slot whose
+                // running weight sum is not below u*sum (StatsBase cumulative walk)
+                const double *cw = ctx.base_cw + gbase;
+                const double t = u_base * ctx.base_tot[g];
+                int found = Np - 1;
+                for (int q0 = 0; q0 < Np - 1; q0 += co.width()) {
+                    const int q = q0 + co.lane();
+                    const bool hit = q < Np - 1 && !(cw[q] < t);
+                    const int best = co.min_int(hit ? q : 0x7fffffff);
+                    if (best != 0x7fffffff) { found = best; break; }
+                }
+                i0 = found;
+                pb = ctx.cur_theta + (gbase + (size_t)i0) * d;
+            }
+        }
+    } else if (kind == KIND_SNOOKER) {
+        pz = DE_DONOR(i0); pm = DE_DONOR(i1); pn = DE_DONOR(i2);
+        // project (utilities.jl:239-246): v1 = sum(p1.*pd), v2 = sum(pd.^2)
+        double v1m = 0.0, v1n = 0.0, v2 = 0.0;
+        for (int k = co.lane(); k < d; k += co.width()) {
+            const double pd = sub(tcur[k], pz[k]);
+            v1m = add(v1m, mul(pm[k], pd));
+            v1n = add(v1n, mul(pn[k], pd));
+            v2 = add(v2, mul(pd, pd));
+        }
+        v1m = co.sum(v1m); v1n = co.sum(v1n); v2 = co.sum(v2);
+        r1 = v1m / v2; r2 = v1n / v2;
+    }
+#undef DE_DONOR
+
+    const uint8_t *mask = (ctx.block >= 0 && !is_mut) ? cfg.blocks + (size_t)ctx.block * d : nullptr;
+    bool ok = true;
+    double sq1 = 0.0, sq2 = 0.0;
+    for (int k = co.lane(); k < d; k += co.width()) {
+        const double t = tcur[k];
+        const double nz = ctx.replay ? ctx.t_noise[(size_t)p * d + k] : noise_elem(cfg.seed, ctx.sweep, unit, k, is_mut, cfg.eps, cfg.sigma);
+        double v;
+        if (is_mut) v = add(t, nz);                                            // utilities.jl:291-298
+        else if (kind == KIND_DE) v = de_elem(t, pm[k], pn[k], has_base ? pb[k] : t, g1, g2, has_base, nz);
+        else v = snooker_elem(t, pz[k], r1, r2, g1, nz);
+        if (!is_mut) {
+            if (cfg.kappa != 1.0) {                                            // recombination! (crossover.jl:301-321)
+                const bool keep = ctx.replay ? ctx.t_keep[(size_t)p * d + k] != 0 : keep_elem(cfg.seed, ctx.sweep, unit, k, cfg.kappa);
+                if (keep) v = t;
+            }
+            if (mask && !mask[k]) v = t;                                       // reset! (crossover.jl:336-352)
+        }
+        if (kind == KIND_SNOOKER) {                                            // adjust_loglike (crossover.jl:268-273)
+            const double a = sub(v, pz[k]), b = sub(t, pz[k]);
+            sq1 = add(sq1, mul(a, a)); sq2 = add(sq2, mul(b, b));
+        }
+        ok = ok && (v >= cfg.lo[k] && v <= cfg.hi[k]);
+        prop[k] = v;
+        if (ctx.tr_theta) ctx.tr_theta[(size_t)p * d + k] = v;
+    }
+    co.sync();
+    double ps = 0.0;
+    for (int k = co.lane(); k < d; k += co.width()) {
+        const Prior pr = m.prior[k];
+        ps += prior_elem(pr, prop[k], pr.kind == PRIOR_NORMAL_REF ? prop[pr.ref] : 0.0);
+    }
+    const bool inb = co.all(ok);
+    ps = co.sum(ps);
+    double adj = 0.0;
+    if (kind == KIND_SNOOKER) { sq1 = co.sum(sq1); sq2 = co.sum(sq2); adj = adjust_loglike(sq1, sq2, d); }
+    if (co.lane() == 0) {
+        ctx.prop_prior[p] = ps;
+        ctx.prop_inb[p] = inb ? 1 : 0;
+        ctx.prop_adj[p] = adj;
+    }
+}
+
+// compute_posterior! tail + mh_update! (utilities.jl:92-99, 201-210) + the row write that replaces
+// store_samples! (utilities.jl:161-180)
+template <class C>
+DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, int p)
+{
+    const int d = cfg.d, Np = cfg.Np;
+    const int n_split = m.n_osplit * m.n_ksplit;
+    const double *prop = ctx.prop_theta + (size_t)p * d;
+    const double *tcur = ctx.cur_theta + (size_t)p * d;
+    double part = 0.0;
+    if (m.kind != M_BINOMIAL)
+        for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
+    const double total = co.sum(part);
+    const double ll = finalize_ll(m, prop, total);
+    const bool inb = ctx.prop_inb[p] != 0;
+    const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();
+    const double adj = ctx.prop_adj[p];
+    const int g = p / Np, j = p - g * Np;
+    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
+    const double u = ctx.replay ? ctx.t_uacc[p] : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
+    const double wcur = ctx.cur_w[p];
+    const bool acc = accept(wprop, wcur, adj, u);
+    double *dst = ctx.next_theta + (size_t)p * d;
+    for (int k = co.lane(); k < d; k += co.width()) dst[k] = acc ? prop[k] : tcur[k];
+    if (co.lane() == 0) {
+        ctx.next_w[p] = acc ? wprop : wcur;
+        ctx.next_id[p] = ctx.cur_id[p];
+        ctx.next_acc[p] = acc ? 1 : 0;
+        if (ctx.tr_w) { ctx.tr_w[p] = wprop; ctx.tr_adj[p] = adj; ctx.tr_acc[p] = acc ? 1 : 0; }
+    }
+}
+
+} // namespace de

@@ -1,0 +1,83 @@
+// de_types.h -- POD argument blocks passed by value to the kernels of libdemcmc_b200.
+#pragma once
+#include <stdint.h>
+#include "de_math.h"
+
+namespace de {
+
+constexpr int MAX_ACC = 8;        // accumulators of LNR / LBA held in registers
+constexpr int SSD_TP = 64;        // particles per tile of the sum-of-squared-differences kernel
+constexpr int SSD_TN = 64;        // observations per tile
+constexpr int SSD_KC = 32;        // dimensions per shared-memory chunk
+constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
+constexpr int PW_THREADS = 256;
+
+enum ModelKind { M_GAUSSIAN = 0, M_MVNORMAL = 1, M_BINOMIAL = 2, M_LNR = 3, M_LBA = 4, M_HIER = 5 };
+
+// The registered likelihood a handle is bound to (GPULoglike), device-resident.
+struct ModelDev {
+    int32_t kind, d;
+    int64_t n_obs;
+    int32_t n_dim, n_per;
+    const double *x;          // pointwise kernels: x[n_obs] / rt[n_obs]
+    const int32_t *choice;    // LNR/LBA winners (1-based)
+    const double *xT;         // SSD kernels: xT[ssd_k][ssd_ld], observations contiguous, zero padded
+    int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension
+    int32_t ssd_k;            // dimensions (MVN: n_dim; hierarchical: subjects)
+    int32_t has_sigma;
+    double sigma_acc[MAX_ACC];
+    double lba_floor;
+    double binom_N, binom_k;
+    const Prior *prior;       // [d]
+    // partition of the likelihood sum: split s covers observations [s*split_len, ...) x dimension
+    // chunk; fixed by the model alone so the summation order never depends on the GPU count
+    int32_t n_osplit, n_ksplit, split_len, ksplit_len;
+};
+
+struct ConfigDev {
+    int32_t Np, d, G_local, group_begin, proposal, burnin, n_blocks;
+    double eps, sigma, kappa, theta_snooker;
+    const double *lo, *hi;    // [d]
+    const uint8_t *blocks;    // [n_blocks][d]
+    uint64_t seed;
+};
+
+// One sweep (one pass of mutate_or_crossover! over every local group).  State is kept in ROWS:
+// the sweep reads row `cur` (immutable while the sweep runs) and writes row `next`; a donor with
+// a smaller slot than the target is read from `next`, reproducing the reference's sequential,
+// in-place sweep (crossover.jl:12-17, utilities.jl:201-210) level by level.
+struct SweepCtx {
+    uint32_t sweep;           // iter0*B + block, the Philox sweep coordinate
+    int32_t block;            // block index or -1
+    int32_t in_burnin;        // de.iter <= de.burnin (crossover.jl:164)
+    int32_t replay;           // draws come from the tape
+    int32_t exact_base;       // replay: trust idx[.][0] with sequential semantics
+    const double *cur_theta; const double *cur_w; const int32_t *cur_id;
+    double *next_theta; double *next_w; int32_t *next_id; uint8_t *next_acc;
+    const uint8_t *mutate;    // [G_local] this sweep's rand() <= beta (main.jl:200)
+    // select_base on the sweep-start weights (native mode, burn-in, random_gamma): running sums of
+    // the sampling weights per group and their totals (crossover.jl:282-289)
+    const double *base_cw;    // [P_local]
+    const double *base_tot;   // [G_local]
+    // tape slices of this sweep, local shard (replay only)
+    const uint8_t *t_kind; const int32_t *t_idx; const double *t_g1, *t_g2, *t_uacc, *t_noise; const uint8_t *t_keep;
+    // proposal scratch
+    double *prop_theta;       // [P_local][d]
+    double *prop_prior;       // [P_local]
+    double *prop_adj;         // [P_local]
+    uint8_t *prop_inb;        // [P_local]
+    double *ll_part;          // [P_local][n_split]
+    // trace rows of this sweep or NULL
+    double *tr_theta, *tr_w, *tr_adj; uint8_t *tr_acc;
+};
+
+struct Level { const int32_t *order; int32_t n; };   // local positions updated in this level
+
+constexpr int MAX_MIG = 128;      // groups in one migration cycle (kernel-parameter block)
+struct MigArgs {
+    int32_t n;                      // migrating groups
+    int32_t groups[MAX_MIG];        // ordered subset (global group ids)
+    double u_pick[MAX_MIG];         // uniform of select_particle per position
+};
+
+} // namespace de

@@ -1,0 +1,793 @@
+// engine.cpp -- host side of libdemcmc_b200: the handle, the iteration loop of _sample
+// (src/main.jl:33-38) and the C ABI of include/demcmc_b200.h.  All arithmetic on particles happens
+// in the kernels behind backend.h; the host only schedules (planner.h) and moves buffers.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/demcmc_b200.h"
+#include "backend.h"
+#include "de_types.h"
+#include "planner.h"
+
+using namespace de;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define BE(call) do { if ((call) != 0) return fail(DEMCMC_ECUDA, "%s: %s", #call, be::last_error()); } while (0)
+
+namespace {
+
+struct Row { double *theta; double *w; int32_t *id; uint8_t *acc; };
+
+struct Upload {            // pinned staging + device copy of one sweep's schedule
+    int32_t *h_order = nullptr, *d_order = nullptr;
+    uint8_t *h_mut = nullptr, *d_mut = nullptr;
+    void *copied = nullptr;  // event: the H2D copies out of the pinned buffers have run
+    bool armed = false;
+};
+
+} // namespace
+
+struct demcmc_handle {
+    demcmc_config cfg;
+    std::vector<uint8_t> blocks;
+    std::vector<double> lo, hi;
+    int G_local = 0, P = 0, B = 1, d = 0;
+    ConfigDev dcfg;
+    ModelDev dmodel;
+    bool has_model = false, has_state = false;
+    std::vector<void *> model_allocs;
+    // state rows
+    int64_t hist_cap = 0, iters_done = 0;
+    double *hist_theta = nullptr, *hist_w = nullptr;
+    int32_t *hist_id = nullptr;
+    uint8_t *hist_acc = nullptr;
+    double *scr_theta = nullptr, *scr_w = nullptr;      // 3 scratch rows
+    int32_t *scr_id = nullptr;
+    uint8_t *scr_acc = nullptr;
+    int cur_scratch = 0;                                // current state lives in scratch row k, or
+    int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
+    // proposal scratch
+    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *ll_part = nullptr;
+    uint8_t *prop_inb = nullptr;
+    double *base_th = nullptr, *base_cw = nullptr, *base_tot = nullptr;
+    double *d_lo = nullptr, *d_hi = nullptr;
+    uint8_t *d_blocks = nullptr;
+    // schedule ring
+    static constexpr int RING = 8;
+    Upload ring[RING];
+    int64_t ring_use = 0;
+    // migration
+    int32_t *d_picks = nullptr;
+    double *d_stage = nullptr, *d_stage_recv = nullptr;
+    std::vector<int32_t> last_mig_slots;                // [n_iter][G_total] of the last call
+    int32_t *d_mig_log = nullptr;                       // device log of picks of the last call
+    int64_t mig_log_iters = 0;
+    // trace of the last call
+    double *tr_theta = nullptr, *tr_w = nullptr, *tr_adj = nullptr;
+    uint8_t *tr_acc = nullptr;
+    int64_t tr_sweeps = 0;
+    // comm
+    void *comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::vector<int> group_owner;                       // [G_total] rank owning each group
+    demcmc_counters ctr;
+};
+
+static Row row_of(demcmc_handle *h, bool hist, int64_t idx)
+{
+    const size_t P = h->P, d = h->d;
+    Row r;
+    if (hist) { r.theta = h->hist_theta + idx * P * d; r.w = h->hist_w + idx * P; r.id = h->hist_id + idx * P; r.acc = h->hist_acc + idx * P; }
+    else { r.theta = h->scr_theta + idx * P * d; r.w = h->scr_w + idx * P; r.id = h->scr_id + idx * P; r.acc = h->scr_acc + idx * P; }
+    return r;
+}
+static Row cur_row(demcmc_handle *h) { return h->cur_hist >= 0 ? row_of(h, true, h->cur_hist) : row_of(h, false, h->cur_scratch); }
+
+static int grow_history(demcmc_handle *h, int64_t need)
+{
+    if (need <= h->hist_cap) return 0;
+    int64_t cap = std::max<int64_t>(need, h->hist_cap * 2);
+    const size_t P = h->P, d = h->d;
+    double *nt = (double *)be::dmalloc(sizeof(double) * cap * P * d);
+    double *nw = (double *)be::dmalloc(sizeof(double) * cap * P);
+    int32_t *ni = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P);
+    uint8_t *na = (uint8_t *)be::dmalloc(cap * P);
+    if (!nt || !nw || !ni || !na) return fail(DEMCMC_ENOMEM, "history of %lld rows does not fit on the device", (long long)cap);
+    if (h->iters_done > 0) {
+        BE(be::d2d(nt, h->hist_theta, sizeof(double) * h->iters_done * P * d));
+        BE(be::d2d(nw, h->hist_w, sizeof(double) * h->iters_done * P));
+        BE(be::d2d(ni, h->hist_id, sizeof(int32_t) * h->iters_done * P));
+        BE(be::d2d(na, h->hist_acc, h->iters_done * P));
+        BE(be::sync());
+    }
+    be::dfree(h->hist_theta); be::dfree(h->hist_w); be::dfree(h->hist_id); be::dfree(h->hist_acc);
+    h->hist_theta = nt; h->hist_w = nw; h->hist_id = ni; h->hist_acc = na; h->hist_cap = cap;
+    return 0;
+}
+
+// ---- particle algebra ops (known-answer tests) --------------------------------------------------
+namespace {
+struct DevBuf {
+    std::vector<void *> p;
+    ~DevBuf() { for (void *q : p) be::dfree(q); }
+    template <typename T> T *up(const T *src, size_t n)
+    {
+        T *q = (T *)be::dmalloc(std::max<size_t>(8, sizeof(T) * n));
+        if (!q) return nullptr;
+        p.push_back(q);
+        if (src && n && be::h2d(q, src, sizeof(T) * n)) return nullptr;
+        return q;
+    }
+};
+int op_begin(int device)
+{
+    if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback");
+    if (be::set_device(device)) return fail(DEMCMC_ENODEVICE, "cannot select device %d", device);
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+const char *demcmc_last_error(void) { return g_err.c_str(); }
+int demcmc_abi_version(void) { return DEMCMC_ABI_VERSION; }
+int demcmc_device_count(void) { return be::device_count(); }
+const char *demcmc_backend_name(void) { return be::name(); }
+
+int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
+{
+    if (!cfg || !out) return fail(DEMCMC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DEMCMC_ABI_VERSION) return fail(DEMCMC_EINVAL, "abi_version %d != %d", cfg->abi_version, DEMCMC_ABI_VERSION);
+    if (cfg->Np < 3) return fail(DEMCMC_EINVAL, "Np must be >= 3 (two donors besides the target, crossover.jl:158-160)");
+    if (cfg->n_groups < 1 || cfg->d < 1 || !cfg->lo || !cfg->hi) return fail(DEMCMC_EINVAL, "bad n_groups/d/bounds");
+    if (cfg->n_groups > MAX_MIG) return fail(DEMCMC_EUNSUPPORTED, "n_groups > %d", MAX_MIG);
+    if (cfg->n_blocks < 0 || (cfg->n_blocks > 0 && !cfg->blocks)) return fail(DEMCMC_EINVAL, "blocks missing");
+    if (cfg->proposal < 0 || cfg->proposal > 2) return fail(DEMCMC_EINVAL, "unknown generate_proposal %d", cfg->proposal);
+    if (cfg->store_every > 1) return fail(DEMCMC_EUNSUPPORTED, "thinning (store_every > 1) is not built yet");
+    if (cfg->n_initial != 0) return fail(DEMCMC_EUNSUPPORTED, "n_initial > 0 / sample = resample is not built yet");
+    if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
+    if (be::set_device(cfg->device) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
+
+    demcmc_handle *h = new demcmc_handle();
+    h->cfg = *cfg;
+    h->d = cfg->d;
+    h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
+    if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
+    h->P = h->G_local * cfg->Np;
+    h->B = cfg->n_blocks > 0 ? cfg->n_blocks : 1;
+    h->lo.assign(cfg->lo, cfg->lo + cfg->d);
+    h->hi.assign(cfg->hi, cfg->hi + cfg->d);
+    if (cfg->n_blocks > 0) h->blocks.assign(cfg->blocks, cfg->blocks + (size_t)cfg->n_blocks * cfg->d);
+    if (cfg->n_groups == 1) h->cfg.alpha = 0.0;   // structs.jl:102-105
+    memset(&h->ctr, 0, sizeof h->ctr);
+    memset(&h->dmodel, 0, sizeof h->dmodel);
+    h->group_owner.assign(cfg->n_groups, 0);
+
+    const size_t P = h->P, d = h->d;
+    h->d_lo = (double *)be::dmalloc(sizeof(double) * d);
+    h->d_hi = (double *)be::dmalloc(sizeof(double) * d);
+    h->d_blocks = (uint8_t *)be::dmalloc(std::max<size_t>(1, h->blocks.size()));
+    h->scr_theta = (double *)be::dmalloc(sizeof(double) * 3 * P * d);
+    h->scr_w = (double *)be::dmalloc(sizeof(double) * 3 * P);
+    h->scr_id = (int32_t *)be::dmalloc(sizeof(int32_t) * 3 * P);
+    h->scr_acc = (uint8_t *)be::dmalloc(3 * P);
+    h->prop_theta = (double *)be::dmalloc(sizeof(double) * P * d);
+    h->prop_prior = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_inb = (uint8_t *)be::dmalloc(P);
+    h->base_th = (double *)be::dmalloc(sizeof(double) * P);
+    h->base_cw = (double *)be::dmalloc(sizeof(double) * P);
+    h->base_tot = (double *)be::dmalloc(sizeof(double) * std::max(1, h->G_local));
+    h->d_picks = (int32_t *)be::dmalloc(sizeof(int32_t) * MAX_MIG);
+    h->d_stage = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
+    h->d_stage_recv = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
+    bool ok = h->d_lo && h->d_hi && h->d_blocks && h->scr_theta && h->scr_w && h->scr_id && h->scr_acc && h->prop_theta &&
+              h->prop_prior && h->prop_adj && h->prop_inb && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
+    for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
+        Upload &u = h->ring[i];
+        u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P);
+        u.h_mut = (uint8_t *)be::hmalloc_pinned(std::max<size_t>(16, h->G_local));
+        u.d_order = (int32_t *)be::dmalloc(sizeof(int32_t) * P);
+        u.d_mut = (uint8_t *)be::dmalloc(std::max<size_t>(16, h->G_local));
+        u.copied = be::event_create();
+        ok = u.h_order && u.h_mut && u.d_order && u.d_mut && u.copied;
+    }
+    if (!ok) { demcmc_destroy(h); return fail(DEMCMC_ENOMEM, "device allocation failed: %s", be::last_error()); }
+    if (be::h2d(h->d_lo, h->lo.data(), sizeof(double) * d) || be::h2d(h->d_hi, h->hi.data(), sizeof(double) * d) ||
+        (!h->blocks.empty() && be::h2d(h->d_blocks, h->blocks.data(), h->blocks.size())) || be::sync()) {
+        demcmc_destroy(h);
+        return fail(DEMCMC_ECUDA, "upload failed: %s", be::last_error());
+    }
+    ConfigDev &c = h->dcfg;
+    c.Np = cfg->Np; c.d = cfg->d; c.G_local = h->G_local; c.group_begin = cfg->group_begin; c.proposal = cfg->proposal;
+    c.burnin = cfg->burnin; c.n_blocks = cfg->n_blocks; c.eps = cfg->eps; c.sigma = cfg->sigma; c.kappa = cfg->kappa;
+    c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
+    *out = h;
+    return 0;
+}
+
+int demcmc_destroy(demcmc_handle *h)
+{
+    if (!h) return 0;
+    be::set_device(h->cfg.device);
+    be::sync();
+    if (h->comm) be::comm_destroy(h->comm);
+    for (void *p : h->model_allocs) be::dfree(p);
+    void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
+                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
+                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc };
+    for (void *p : ptrs) be::dfree(p);
+    for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::dfree(u.d_order); be::dfree(u.d_mut); be::event_destroy(u.copied); }
+    delete h;
+    return 0;
+}
+
+int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
+{
+    if (!h || !m || !m->prior) return fail(DEMCMC_EINVAL, "null argument");
+    if (m->d != h->d) return fail(DEMCMC_EINVAL, "model.d %d != config.d %d", m->d, h->d);
+    BE(be::set_device(h->cfg.device));
+    for (void *p : h->model_allocs) be::dfree(p);
+    h->model_allocs.clear();
+    be::dfree(h->ll_part); h->ll_part = nullptr;
+    ModelDev &D = h->dmodel;
+    memset(&D, 0, sizeof D);
+    D.kind = m->kind; D.d = m->d; D.n_obs = m->n_obs; D.n_dim = m->n_dim; D.n_per = m->n_per; D.lba_floor = m->lba_floor;
+    auto upload = [&](const void *src, size_t bytes, bool on_dev) -> void * {
+        void *p = be::dmalloc(std::max<size_t>(bytes, 8));
+        if (!p) return nullptr;
+        h->model_allocs.push_back(p);
+        if (bytes && (on_dev ? be::d2d(p, src, bytes) : be::h2d(p, src, bytes))) return nullptr;
+        return p;
+    };
+    // parameter-count contract of each registered kernel
+    int want_d = -1;
+    switch (m->kind) {
+    case DEMCMC_GAUSSIAN: want_d = 2; break;
+    case DEMCMC_MVNORMAL: want_d = m->n_dim + 1; break;
+    case DEMCMC_BINOMIAL: want_d = 1; break;
+    case DEMCMC_LNR: want_d = m->n_dim + 1; break;
+    case DEMCMC_LBA: want_d = m->n_dim + 3; break;
+    case DEMCMC_HIER_NORMAL: want_d = m->n_dim + 3; break;
+    default: return fail(DEMCMC_EUNSUPPORTED, "no registered kernel for model kind %d: arbitrary closures are not supported and there is no CPU fallback", m->kind);
+    }
+    if (m->d != want_d) return fail(DEMCMC_EINVAL, "model kind %d expects d = %d, got %d", m->kind, want_d, m->d);
+    if (!m->x) return fail(DEMCMC_EINVAL, "model data missing");
+    if ((m->kind == DEMCMC_LNR || m->kind == DEMCMC_LBA) && (!m->choice || m->n_dim < 2 || m->n_dim > MAX_ACC))
+        return fail(DEMCMC_EINVAL, "LNR/LBA need choices and 2..%d accumulators", MAX_ACC);
+    if (m->n_obs < 0) return fail(DEMCMC_EINVAL, "negative n_obs");
+
+    std::vector<Prior> pr(m->d);
+    for (int k = 0; k < m->d; ++k) {
+        pr[k].kind = m->prior[k].kind; pr[k].ref = m->prior[k].ref; pr[k].a = m->prior[k].a; pr[k].b = m->prior[k].b;
+        if (pr[k].kind < 0 || pr[k].kind > PRIOR_NORMAL_REF) return fail(DEMCMC_EUNSUPPORTED, "prior kind %d of parameter %d is not registered", pr[k].kind, k);
+        if (pr[k].kind == PRIOR_NORMAL_REF && (pr[k].ref < 0 || pr[k].ref >= m->d)) return fail(DEMCMC_EINVAL, "prior ref out of range");
+    }
+    D.prior = (const Prior *)upload(pr.data(), sizeof(Prior) * pr.size(), false);
+    if (!D.prior) return fail(DEMCMC_ENOMEM, "prior upload failed");
+    const bool dev = m->data_on_device != 0;
+    D.n_osplit = 1; D.n_ksplit = 1; D.split_len = 0; D.ksplit_len = 0;
+    if (m->kind == DEMCMC_BINOMIAL) {
+        double nk[2];
+        if (dev) { BE(be::d2h(nk, m->x, sizeof nk)); } else memcpy(nk, m->x, sizeof nk);
+        D.binom_N = nk[0]; D.binom_k = nk[1]; D.n_obs = 1;
+    } else if (m->kind == DEMCMC_MVNORMAL || m->kind == DEMCMC_HIER_NORMAL) {
+        // SSD layout: xT[k][ld]; MVN: k = dimension, obs = n_obs; hierarchical: k = subject, obs = n_per
+        D.ssd_k = m->n_dim;
+        D.ssd_n = m->kind == DEMCMC_MVNORMAL ? m->n_obs : m->n_per;
+        if (m->kind == DEMCMC_HIER_NORMAL) D.n_obs = (int64_t)m->n_dim * m->n_per;
+        D.ssd_ld = (D.ssd_n + SSD_TN - 1) / SSD_TN * SSD_TN;
+        if (D.ssd_ld == 0) D.ssd_ld = SSD_TN;
+        double *xT = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k * D.ssd_ld);
+        if (!xT) return fail(DEMCMC_ENOMEM, "data do not fit on the device");
+        h->model_allocs.push_back(xT);
+        D.xT = xT;
+        BE(be::launch_pack_ssd(m->x, dev, &D));
+        // observation splits: ~one per SM, whole tiles; dimension splits: chunks of <= 256 dims
+        const int64_t tiles = D.ssd_ld / SSD_TN;
+        const int64_t tiles_per_split = std::max<int64_t>(1, (tiles + 147) / 148);
+        D.split_len = (int32_t)(tiles_per_split * SSD_TN);
+        D.n_osplit = (int32_t)((D.ssd_ld + D.split_len - 1) / D.split_len);
+        D.ksplit_len = D.ssd_k <= 256 ? D.ssd_k : 128;
+        D.n_ksplit = (D.ssd_k + D.ksplit_len - 1) / D.ksplit_len;
+    } else {
+        D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
+        if (!D.x) return fail(DEMCMC_ENOMEM, "data upload failed");
+        if (m->choice) { D.choice = (const int32_t *)upload(m->choice, sizeof(int32_t) * m->n_obs, dev); if (!D.choice) return fail(DEMCMC_ENOMEM, "data upload failed"); }
+        if (m->sigma) { D.has_sigma = 1; for (int r = 0; r < m->n_dim && r < MAX_ACC; ++r) D.sigma_acc[r] = m->sigma[r]; }
+        const int64_t chunk = PW_THREADS;
+        const int64_t chunks = std::max<int64_t>(1, (m->n_obs + chunk - 1) / chunk);
+        const int64_t per = std::max<int64_t>(1, (chunks + 147) / 148);
+        D.split_len = (int32_t)(per * chunk);
+        D.n_osplit = (int32_t)std::max<int64_t>(1, (m->n_obs + D.split_len - 1) / D.split_len);
+    }
+    const size_t n_split = (size_t)D.n_osplit * D.n_ksplit;
+    h->ll_part = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, (size_t)h->P * n_split));
+    if (!h->ll_part) return fail(DEMCMC_ENOMEM, "partial-sum workspace does not fit");
+    BE(be::sync());
+    h->has_model = true;
+    return 0;
+}
+
+int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids)
+{
+    if (!h || !theta) return fail(DEMCMC_EINVAL, "null argument");
+    if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model must come before set_state");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    // the current state moves to scratch row 0 (history rows already written stay as they are)
+    h->cur_hist = -1; h->cur_scratch = 0;
+    Row r = row_of(h, false, 0);
+    std::vector<int32_t> idv(P);
+    for (size_t p = 0; p < P; ++p) idv[p] = ids ? ids[p] : (int32_t)(h->cfg.group_begin * h->cfg.Np + p);
+    BE(be::h2d(r.theta, theta, sizeof(double) * P * d));
+    BE(be::h2d(r.id, idv.data(), sizeof(int32_t) * P));
+    BE(be::dzero(r.acc, P));
+    BE(be::sync());
+    // init_particle (utilities.jl:13-22): weight through evaluate_fitness!
+    BE(be::launch_eval(h->dcfg, h->dmodel, r.theta, (int64_t)P, nullptr, nullptr, r.w, h->ll_part));
+    BE(be::sync());
+    h->has_state = true;
+    return 0;
+}
+
+static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
+{
+    if (!h || n_iter < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (!h->has_model || !h->has_state) return fail(DEMCMC_ESTATE, "set_model and set_state must come before run");
+    BE(be::set_device(h->cfg.device));
+    const demcmc_config &cfg = h->cfg;
+    const int Np = cfg.Np, Gt = cfg.n_groups, G = h->G_local, P = h->P, d = h->d, B = h->B;
+    const int64_t Pt = (int64_t)Gt * Np, S = n_iter * B;
+    const int64_t pbeg = (int64_t)cfg.group_begin * Np;
+    if (int rc = grow_history(h, h->iters_done + n_iter)) return rc;
+
+    // ---- replay: upload the local shard of the tape ------------------------------------------------
+    uint8_t *t_kind = nullptr, *t_keep = nullptr;
+    int32_t *t_idx = nullptr;
+    double *t_g1 = nullptr, *t_g2 = nullptr, *t_uacc = nullptr, *t_noise = nullptr;
+    std::vector<uint8_t> hk;          // host copy of local kinds / idx for the planner
+    std::vector<int32_t> hi;
+    std::vector<void *> tmp;
+    auto cleanup = [&]() { for (void *p : tmp) be::dfree(p); tmp.clear(); };
+    if (tape) {
+        if (!tape->kind || !tape->idx || !tape->gamma1 || !tape->gamma2 || !tape->u_acc || !tape->noise)
+            return fail(DEMCMC_EINVAL, "tape misses a required array");
+        if (cfg.kappa != 1.0 && !tape->keep) return fail(DEMCMC_EINVAL, "kappa != 1 needs tape.keep");
+        if (Gt > 1 && (!tape->mig_n || !tape->mig_groups || !tape->mig_pick_u)) return fail(DEMCMC_EINVAL, "tape misses the migration arrays");
+        auto shard = [&](const void *src, size_t elem, size_t per_particle) -> void * {
+            // [S][Pt][per] -> [S][P][per]
+            const size_t rowb = elem * per_particle;
+            std::vector<uint8_t> buf((size_t)S * P * rowb);
+            for (int64_t s = 0; s < S; ++s)
+                memcpy(buf.data() + (size_t)s * P * rowb, (const uint8_t *)src + ((size_t)s * Pt + pbeg) * rowb, (size_t)P * rowb);
+            void *p = be::dmalloc(std::max<size_t>(8, buf.size()));
+            if (!p) return nullptr;
+            tmp.push_back(p);
+            if (!buf.empty() && (be::h2d(p, buf.data(), buf.size()) || be::sync())) return nullptr;
+            return p;
+        };
+        t_kind = (uint8_t *)shard(tape->kind, 1, 1);
+        t_idx = (int32_t *)shard(tape->idx, 4, 3);
+        t_g1 = (double *)shard(tape->gamma1, 8, 1);
+        t_g2 = (double *)shard(tape->gamma2, 8, 1);
+        t_uacc = (double *)shard(tape->u_acc, 8, 1);
+        t_noise = (double *)shard(tape->noise, 8, d);
+        if (cfg.kappa != 1.0) t_keep = (uint8_t *)shard(tape->keep, 1, d);
+        if (!t_kind || !t_idx || !t_g1 || !t_g2 || !t_uacc || !t_noise || (cfg.kappa != 1.0 && !t_keep)) { cleanup(); return fail(DEMCMC_ENOMEM, "tape upload failed: %s", be::last_error()); }
+        hk.resize((size_t)S * P); hi.resize((size_t)S * P * 3);
+        for (int64_t s = 0; s < S; ++s) {
+            memcpy(hk.data() + (size_t)s * P, tape->kind + (size_t)s * Pt + pbeg, P);
+            memcpy(hi.data() + (size_t)s * P * 3, tape->idx + ((size_t)s * Pt + pbeg) * 3, sizeof(int32_t) * P * 3);
+        }
+        for (size_t i = 0; i < hk.size(); ++i) if (hk[i] > KIND_MUTATION) { cleanup(); return fail(DEMCMC_EINVAL, "tape.kind[%zu] = %d", i, hk[i]); }
+        for (size_t i = 0; i < hi.size(); ++i) if (hk[i / 3] != KIND_MUTATION && !(hk[i / 3] == KIND_DE && i % 3 == 0 && hi[i] < 0) && (hi[i] < 0 || hi[i] >= Np)) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx[%zu] = %d out of range", i, hi[i]); }
+    }
+
+    // ---- trace and migration log of this call ------------------------------------------------------
+    be::dfree(h->tr_theta); be::dfree(h->tr_w); be::dfree(h->tr_adj); be::dfree(h->tr_acc);
+    h->tr_theta = h->tr_w = h->tr_adj = nullptr; h->tr_acc = nullptr; h->tr_sweeps = 0;
+    if (cfg.trace && S > 0) {
+        h->tr_theta = (double *)be::dmalloc(sizeof(double) * S * P * d);
+        h->tr_w = (double *)be::dmalloc(sizeof(double) * S * P);
+        h->tr_adj = (double *)be::dmalloc(sizeof(double) * S * P);
+        h->tr_acc = (uint8_t *)be::dmalloc((size_t)S * P);
+        if (!h->tr_theta || !h->tr_w || !h->tr_adj || !h->tr_acc) { cleanup(); return fail(DEMCMC_ENOMEM, "trace buffers do not fit"); }
+        h->tr_sweeps = S;
+    }
+    be::dfree(h->d_mig_log); h->d_mig_log = nullptr; h->mig_log_iters = n_iter;
+    h->last_mig_slots.assign((size_t)std::max<int64_t>(1, n_iter) * Gt, -1);
+    std::vector<std::pair<int64_t, MigSchedule>> mig_events;      // iterations that migrated
+    if (n_iter > 0) {
+        h->d_mig_log = (int32_t *)be::dmalloc(sizeof(int32_t) * n_iter * MAX_MIG);
+        if (!h->d_mig_log) { cleanup(); return fail(DEMCMC_ENOMEM, "migration log"); }
+    }
+
+    const int64_t launches0 = be::launch_count();
+    int64_t n_levels = 0;
+    BE(be::timer_start());
+    SweepPlan plan;
+    MigSchedule ms;
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t itg = h->iters_done + it;            // 0-based iteration of the whole chain
+        const int64_t de_iter = itg + 1 + cfg.n_initial;   // de.iter (main.jl:34)
+        const bool in_burnin = de_iter <= cfg.burnin;
+        Row cur = cur_row(h);
+
+        // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
+        if (Gt > 1) {
+            if (tape) {
+                ms.migrate = tape->mig_n[it] > 0; ms.n = tape->mig_n[it]; ms.groups.clear(); ms.u_pick.clear();
+                for (int i = 0; i < ms.n; ++i) { ms.groups.push_back(tape->mig_groups[it * Gt + i]); ms.u_pick.push_back(tape->mig_pick_u[it * Gt + i]); }
+            } else {
+                plan_migration(cfg.seed, (uint32_t)itg, Gt, cfg.alpha, ms);
+            }
+            if (ms.migrate) {
+                if (ms.n < 2 || ms.n > Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration with %d groups", ms.n); }
+                MigArgs a;
+                memset(&a, 0, sizeof a);
+                a.n = ms.n;
+                bool cross = false, any_local = false;
+                std::vector<int> src(ms.n), dst(ms.n);
+                for (int i = 0; i < ms.n; ++i) {
+                    a.groups[i] = ms.groups[i]; a.u_pick[i] = ms.u_pick[i];
+                    if (a.groups[i] < 0 || a.groups[i] >= Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration group out of range"); }
+                    dst[i] = h->group_owner[ms.groups[i]];
+                    src[i] = h->group_owner[ms.groups[(i + ms.n - 1) % ms.n]];
+                    cross |= src[i] != dst[i];
+                    any_local |= dst[i] == h->rank;
+                }
+                if (any_local || cross) {
+                    int32_t *picks = h->d_mig_log + it * MAX_MIG;
+                    BE(be::launch_mig_pick(h->dcfg, a, cur.w, picks));
+                    BE(be::launch_mig_gather(h->dcfg, a, picks, cur.theta, cur.w, cur.id, cur.acc, h->d_stage));
+                    const double *incoming = h->d_stage;
+                    if (cross) {
+                        if (!h->comm) { cleanup(); return fail(DEMCMC_ECOMM, "migration crosses ranks but demcmc_comm_init was not called"); }
+                        BE(be::d2d(h->d_stage_recv, h->d_stage, sizeof(double) * ms.n * (d + 3)));
+                        if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
+                        incoming = h->d_stage_recv;
+                    }
+                    BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc));
+                }
+                mig_events.emplace_back(it, ms);
+            }
+        }
+
+        // ---- update! (main.jl:161-167): every block is one sweep ---------------------------------
+        for (int b = 0; b < B; ++b) {
+            const int64_t s_local = it * B + b;
+            const uint32_t sweep = (uint32_t)(itg * B + b);
+            PlanInput pin;
+            pin.seed = cfg.seed; pin.Np = Np; pin.G_local = G; pin.group_begin = cfg.group_begin; pin.G_total = Gt;
+            pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker;
+            pin.t_kind = tape ? hk.data() + (size_t)s_local * P : nullptr;
+            pin.t_idx = tape ? hi.data() + (size_t)s_local * P * 3 : nullptr;
+            pin.base_dependency = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin;
+            plan_sweep(pin, sweep, plan);
+
+            Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
+            if (u.armed) BE(be::event_wait(u.copied));     // the pinned slot is free once its copies ran
+            h->ring_use++;
+            memcpy(u.h_order, plan.order.data(), sizeof(int32_t) * P);
+            memcpy(u.h_mut, plan.mutate.data(), G);
+            BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * P));
+            BE(be::h2d(u.d_mut, u.h_mut, G));
+            BE(be::event_record(u.copied));
+            u.armed = true;
+
+            // destination row: the history row of this iteration on the last block, else scratch
+            Row next;
+            int next_scratch = -1;
+            if (b == B - 1) next = row_of(h, true, itg);
+            else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
+
+            SweepCtx ctx;
+            memset(&ctx, 0, sizeof ctx);
+            ctx.sweep = sweep; ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = in_burnin; ctx.replay = tape != nullptr;
+            ctx.exact_base = tape != nullptr;
+            ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
+            ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
+            ctx.mutate = u.d_mut;
+            if (tape) {
+                ctx.t_kind = t_kind + (size_t)s_local * P; ctx.t_idx = t_idx + (size_t)s_local * P * 3;
+                ctx.t_g1 = t_g1 + (size_t)s_local * P; ctx.t_g2 = t_g2 + (size_t)s_local * P; ctx.t_uacc = t_uacc + (size_t)s_local * P;
+                ctx.t_noise = t_noise + (size_t)s_local * P * d; ctx.t_keep = t_keep ? t_keep + (size_t)s_local * P * d : nullptr;
+            }
+            ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb;
+            ctx.ll_part = h->ll_part;
+            ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
+            bool any_cross = false;
+            for (int g = 0; g < G; ++g) any_cross |= plan.mutate[g] == 0;
+            if (!tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin && any_cross)
+                BE(be::launch_base_prep(h->dcfg, cur.w, h->base_th, h->base_cw, h->base_tot));
+            if (h->tr_sweeps) {
+                ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
+                ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
+            }
+            for (int l = 0; l < plan.n_levels; ++l) {
+                Level lv;
+                lv.order = u.d_order + plan.level_off[l];
+                lv.n = plan.level_off[l + 1] - plan.level_off[l];
+                if (lv.n == 0) continue;
+                BE(be::launch_propose(h->dcfg, h->dmodel, ctx, lv));
+                BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part));
+                BE(be::launch_accept(h->dcfg, h->dmodel, ctx, lv));
+                ++n_levels;
+            }
+            if (b == B - 1) { h->cur_hist = itg; }
+            else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
+            cur = next;
+        }
+    }
+    double ms_dev = 0.0;
+    BE(be::timer_stop(&ms_dev));
+    BE(be::sync());
+    // migration log -> host
+    for (auto &ev : mig_events) {
+        std::vector<int32_t> picks(ev.second.n);
+        BE(be::d2h(picks.data(), h->d_mig_log + ev.first * MAX_MIG, sizeof(int32_t) * ev.second.n));
+        for (int i = 0; i < ev.second.n; ++i) h->last_mig_slots[ev.first * Gt + i] = picks[i];
+    }
+    cleanup();
+    h->iters_done += n_iter;
+    h->ctr.iterations += n_iter; h->ctr.sweeps += S; h->ctr.particle_updates += S * P; h->ctr.loglike_evals += S * P;
+    h->ctr.kernel_launches += be::launch_count() - launches0; h->ctr.levels += n_levels; h->ctr.device_ms = ms_dev;
+    return 0;
+}
+
+int demcmc_run(demcmc_handle *h, int64_t n_iter) { return run_impl(h, nullptr, n_iter); }
+int demcmc_replay(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
+{
+    if (!tape) return fail(DEMCMC_EINVAL, "null tape");
+    return run_impl(h, tape, n_iter);
+}
+
+static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *accept, int64_t n_rows)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (n_rows != h->iters_done + h->cfg.n_initial) return fail(DEMCMC_EINVAL, "n_rows %lld != iterations run %lld + n_initial", (long long)n_rows, (long long)h->iters_done);
+    if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "by-id history of a sharded job: gather demcmc_get_history_by_slot on the host");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    const int64_t n0 = h->cfg.n_initial;
+    double *ds = nullptr, *dl = nullptr; uint8_t *da = nullptr;
+    int rc = 0;
+    if (samples) ds = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P * d));
+    if (lp) dl = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P));
+    if (accept) da = (uint8_t *)be::dmalloc(std::max<size_t>(1, n_rows * P));
+    if ((samples && !ds) || (lp && !dl) || (accept && !da)) rc = fail(DEMCMC_ENOMEM, "output staging does not fit on the device");
+    if (!rc && n_rows > 0) {
+        if (ds && be::dzero(ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
+        if (dl && be::dzero(dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
+        if (da && be::dzero(da, n_rows * P)) rc = DEMCMC_ECUDA;
+        if (!rc && h->iters_done > 0 &&
+            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, h->iters_done, n0, n_rows, (int32_t)P, (int32_t)d,
+                                     h->cfg.group_begin * h->cfg.Np, ds, dl, da)) rc = DEMCMC_ECUDA;
+        if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
+        if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
+        if (!rc && da && be::d2h(accept, da, n_rows * P)) rc = DEMCMC_ECUDA;
+        if (rc == DEMCMC_ECUDA) fail(rc, "history gather: %s", be::last_error());
+    }
+    be::dfree(ds); be::dfree(dl); be::dfree(da);
+    return rc;
+}
+
+int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, out, nullptr, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows) { return out ? history_out(h, nullptr, nullptr, out, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, nullptr, out, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+
+int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, double *theta, double *w, int32_t *ids, uint8_t *acc)
+{
+    if (!h || row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range outside the iterations run");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    if (n_rows == 0) return 0;
+    if (theta) BE(be::d2h(theta, h->hist_theta + row0 * P * d, sizeof(double) * n_rows * P * d));
+    if (w) BE(be::d2h(w, h->hist_w + row0 * P, sizeof(double) * n_rows * P));
+    if (ids) BE(be::d2h(ids, h->hist_id + row0 * P, sizeof(int32_t) * n_rows * P));
+    if (acc) BE(be::d2h(acc, h->hist_acc + row0 * P, n_rows * P));
+    return 0;
+}
+
+int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *ids)
+{
+    if (!h || !h->has_state) return fail(DEMCMC_ESTATE, "no state");
+    BE(be::set_device(h->cfg.device));
+    Row r = cur_row(h);
+    const size_t P = h->P, d = h->d;
+    if (theta) BE(be::d2h(theta, r.theta, sizeof(double) * P * d));
+    if (weight) BE(be::d2h(weight, r.w, sizeof(double) * P));
+    if (ids) BE(be::d2h(ids, r.id, sizeof(int32_t) * P));
+    return 0;
+}
+
+int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, double *log_adj, uint8_t *accepted)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (!h->tr_sweeps) return fail(DEMCMC_ESTATE, "no trace: create the handle with cfg.trace = 1 and run first");
+    BE(be::set_device(h->cfg.device));
+    const size_t n = (size_t)h->tr_sweeps * h->P;
+    if (prop_theta) BE(be::d2h(prop_theta, h->tr_theta, sizeof(double) * n * h->d));
+    if (prop_weight) BE(be::d2h(prop_weight, h->tr_w, sizeof(double) * n));
+    if (log_adj) BE(be::d2h(log_adj, h->tr_adj, sizeof(double) * n));
+    if (accepted) BE(be::d2h(accepted, h->tr_acc, n));
+    return 0;
+}
+
+int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
+{
+    if (!h || !slots) return fail(DEMCMC_EINVAL, "null argument");
+    memcpy(slots, h->last_mig_slots.data(), sizeof(int32_t) * (size_t)h->mig_log_iters * h->cfg.n_groups);
+    return 0;
+}
+
+int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out)
+{
+    if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
+    *out = h->ctr;
+    return 0;
+}
+
+int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior)
+{
+    if (!h || !theta || n < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model first");
+    BE(be::set_device(h->cfg.device));
+    if (n == 0) return 0;
+    const size_t d = h->d, ns = (size_t)h->dmodel.n_osplit * h->dmodel.n_ksplit;
+    double *dt = (double *)be::dmalloc(sizeof(double) * n * d), *dl = (double *)be::dmalloc(sizeof(double) * n),
+           *dp = (double *)be::dmalloc(sizeof(double) * n), *part = (double *)be::dmalloc(sizeof(double) * n * ns);
+    int rc = 0;
+    if (!dt || !dl || !dp || !part) rc = fail(DEMCMC_ENOMEM, "eval staging does not fit");
+    if (!rc && (be::h2d(dt, theta, sizeof(double) * n * d) || be::sync() ||
+                be::launch_eval(h->dcfg, h->dmodel, dt, n, dl, dp, nullptr, part) ||
+                (loglike && be::d2h(loglike, dl, sizeof(double) * n)) || (prior && be::d2h(prior, dp, sizeof(double) * n))))
+        rc = fail(DEMCMC_ECUDA, "eval: %s", be::last_error());
+    be::dfree(dt); be::dfree(dl); be::dfree(dp); be::dfree(part);
+    return rc;
+}
+
+
+int demcmc_op_project(int device, const double *p1, const double *p2, int32_t d, double *out)
+{
+    if (!p1 || !p2 || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(p1, d), *c = b.up(p2, d), *o = b.up<double>(nullptr, d);
+    if (!a || !c || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_project(a, c, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_reset(int device, const double *prop, const double *pt, const uint8_t *mask, int32_t d, double *out)
+{
+    if (!prop || !pt || !mask || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(prop, d), *c = b.up(pt, d), *o = b.up<double>(nullptr, d);
+    uint8_t *m = b.up(mask, d);
+    if (!a || !c || !o || !m) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_reset(a, c, m, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_de_proposal(int device, const double *pt, const double *pm, const double *pn, const double *pb,
+                          double g1, double g2, const double *bn, int32_t d, double *out)
+{
+    if (!pt || !pm || !pn || !bn || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *t = b.up(pt, d), *m = b.up(pm, d), *n = b.up(pn, d), *bb = pb ? b.up(pb, d) : nullptr, *nz = b.up(bn, d), *o = b.up<double>(nullptr, d);
+    if (!t || !m || !n || !nz || !o || (pb && !bb)) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_de(t, m, n, bb, g1, g2, nz, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_snooker(int device, const double *pt, const double *pz, const double *pm, const double *pn,
+                      double g, const double *bn, int32_t d, double *out, double *log_adj)
+{
+    if (!pt || !pz || !pm || !pn || !bn || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *t = b.up(pt, d), *z = b.up(pz, d), *m = b.up(pm, d), *n = b.up(pn, d), *nz = b.up(bn, d), *o = b.up<double>(nullptr, d), *la = b.up<double>(nullptr, 1);
+    if (!t || !z || !m || !n || !nz || !o || !la) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_snooker(t, z, m, n, g, nz, d, o, la));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    if (log_adj) BE(be::d2h(log_adj, la, sizeof(double)));
+    return 0;
+}
+
+int demcmc_op_accept(int device, const double *w_prop, const double *w_cur, const double *log_adj, const double *u, int32_t n, uint8_t *out)
+{
+    if (!w_prop || !w_cur || !log_adj || !u || !out || n < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(w_prop, n), *c = b.up(w_cur, n), *l = b.up(log_adj, n), *uu = b.up(u, n);
+    uint8_t *o = b.up<uint8_t>(nullptr, n);
+    if (!a || !c || !l || !uu || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_accept(a, c, l, uu, n, o));
+    BE(be::d2h(out, o, n));
+    return 0;
+}
+
+int demcmc_op_select(int device, const double *w, int32_t n, double u, int32_t *base_idx, int32_t *migrate_idx)
+{
+    if (!w || n < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(w, n);
+    int32_t *o = b.up<int32_t>(nullptr, 2);
+    if (!a || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_select(a, n, u, o, o + 1));
+    int32_t r[2];
+    BE(be::d2h(r, o, sizeof r));
+    if (base_idx) *base_idx = r[0];
+    if (migrate_idx) *migrate_idx = r[1];
+    return 0;
+}
+
+int demcmc_comm_unique_id(uint8_t id[128])
+{
+    if (!id) return fail(DEMCMC_EINVAL, "null id");
+    if (be::comm_unique_id(id)) return fail(DEMCMC_ECOMM, "%s", be::last_error());
+    return 0;
+}
+
+int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int32_t n_ranks)
+{
+    if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(DEMCMC_EINVAL, "bad argument");
+    const int Gt = h->cfg.n_groups;
+    if (Gt % n_ranks) return fail(DEMCMC_EINVAL, "n_groups %d is not a multiple of the %d ranks", Gt, n_ranks);
+    const int per = Gt / n_ranks;
+    if (h->cfg.group_begin != rank * per || h->G_local != per) return fail(DEMCMC_EINVAL, "handle holds groups [%d,%d) but rank %d of %d must hold [%d,%d)", h->cfg.group_begin, h->cfg.group_begin + h->G_local, rank, n_ranks, rank * per, rank * per + per);
+    BE(be::set_device(h->cfg.device));
+    if (n_ranks > 1 && be::comm_init(id, rank, n_ranks, &h->comm)) return fail(DEMCMC_ECOMM, "%s", be::last_error());
+    h->rank = rank; h->n_ranks = n_ranks;
+    for (int g = 0; g < Gt; ++g) h->group_owner[g] = g / per;
+    return 0;
+}
+
+int demcmc_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::fp64_peak(tflops));
+    return 0;
+}
+
+int demcmc_copy_peak(int device, double *gbs)
+{
+    if (!gbs) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::copy_peak(gbs));
+    return 0;
+}
+
+} // extern "C"

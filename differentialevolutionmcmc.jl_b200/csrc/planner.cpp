@@ -1,0 +1,70 @@
+// planner.cpp -- see planner.h
+#include "planner.h"
+#include <algorithm>
+#include "de_math.h"
+
+namespace de {
+
+void plan_sweep(const PlanInput &in, uint32_t sweep, SweepPlan &out)
+{
+    const int Np = in.Np, G = in.G_local, P = Np * G;
+    out.mutate.assign(G, 0);
+    out.order.resize(P);
+    std::vector<int32_t> level(P, 0);
+    int max_level = 0;
+    for (int g = 0; g < G; ++g) {
+        const int gg = in.group_begin + g;
+        bool mutate;
+        if (in.t_kind) mutate = in.t_kind[g * Np] == KIND_MUTATION;
+        else mutate = uniform2(in.seed, ST_MUT, sweep, (uint32_t)gg, 0).a <= in.beta;   // main.jl:200
+        out.mutate[g] = mutate ? 1 : 0;
+        if (mutate) continue;                                                           // one level
+        int32_t *lv = level.data() + g * Np;
+        for (int j = 0; j < Np; ++j) {
+            int dep[3], nd = 0;
+            if (in.t_kind) {
+                const int32_t *ix = in.t_idx + (size_t)(g * Np + j) * 3;
+                if (in.t_kind[g * Np + j] == KIND_SNOOKER) { dep[nd++] = ix[0]; dep[nd++] = ix[1]; dep[nd++] = ix[2]; }
+                else { dep[nd++] = ix[1]; dep[nd++] = ix[2]; if (in.base_dependency) dep[nd++] = ix[0]; }
+            } else {
+                const Plan p = plan_particle(in.seed, sweep, (uint32_t)(gg * Np + j), j, Np, false, in.theta_snooker);
+                if (p.kind == KIND_SNOOKER) dep[nd++] = p.i0;
+                dep[nd++] = p.i1; dep[nd++] = p.i2;
+            }
+            int l = 0;
+            for (int q = 0; q < nd; ++q)
+                if (dep[q] >= 0 && dep[q] < j) l = std::max(l, lv[dep[q]] + 1);
+            lv[j] = l;
+            max_level = std::max(max_level, l);
+        }
+    }
+    // stable counting sort of all local positions by level
+    out.n_levels = max_level + 1;
+    out.level_off.assign(out.n_levels + 1, 0);
+    for (int p = 0; p < P; ++p) out.level_off[level[p] + 1]++;
+    for (int l = 0; l < out.n_levels; ++l) out.level_off[l + 1] += out.level_off[l];
+    std::vector<int32_t> cursor(out.level_off.begin(), out.level_off.end() - 1);
+    for (int p = 0; p < P; ++p) out.order[cursor[level[p]]++] = p;
+}
+
+void plan_migration(uint64_t seed, uint32_t iter0, int32_t G, double alpha, MigSchedule &out)
+{
+    out.groups.clear(); out.u_pick.clear(); out.n = 0; out.migrate = false;
+    const dbl2 u = uniform2(seed, ST_MIG, iter0, 0, 0);
+    out.u_mig = u.a;
+    if (G < 2 || !(u.a <= alpha)) return;                    // main.jl:85
+    out.migrate = true;
+    const int N = 2 + rand_index(u.b, G - 1);                // rand(2:n_groups), migration.jl:57
+    std::vector<int32_t> arr(G);
+    for (int i = 0; i < G; ++i) arr[i] = i;
+    for (int i = 0; i < N; ++i) {                            // ordered subset without replacement
+        const dbl2 v = uniform2(seed, ST_MIG, iter0, 0, (uint32_t)(1 + i));
+        const int j = i + rand_index(v.a, G - i);
+        std::swap(arr[i], arr[j]);
+        out.groups.push_back(arr[i]);
+        out.u_pick.push_back(v.b);
+    }
+    out.n = N;
+}
+
+} // namespace de

@@ -1,0 +1,193 @@
+/*
+ * demcmc_b200.h -- C ABI of libdemcmc_b200.so, the B200 (sm_100a) implementation of the
+ * population step of itsdfish/DifferentialEvolutionMCMC.jl.
+ *
+ * The reference has no FFI (pure Julia).  Each entry point below names the reference interface
+ * it replaces (file:line under the reference root); INTEGRATION.md shows the Julia `ccall`
+ * binding a maintainer would add, and julia/GPULoglike.jl holds it.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns 0 on success or a
+ * negative DEMCMC_E* code and never throws; demcmc_last_error() returns a thread-local message.
+ * The caller owns every host buffer; the library copies in/out during the call and keeps no host
+ * pointer.  Device memory belongs to the handle.  A handle is not thread-safe.  There is no CPU
+ * fallback: without a CUDA device demcmc_create fails with DEMCMC_ENODEVICE.
+ *
+ * Layout: P = n_groups*Np particles, position p = g*Np + j (group-major, the order of
+ * sample_init, src/main.jl:263-271); d = flattened parameter count in `names` order, column-major
+ * inside array parameters (get_names, src/utilities.jl:131-149).  All indices are 0-based.
+ */
+#ifndef DEMCMC_B200_H
+#define DEMCMC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEMCMC_ABI_VERSION 1
+
+enum { DEMCMC_OK = 0, DEMCMC_EINVAL = -1, DEMCMC_ENODEVICE = -2, DEMCMC_ECUDA = -3, DEMCMC_ENOMEM = -4,
+       DEMCMC_ESTATE = -5, DEMCMC_EUNSUPPORTED = -6, DEMCMC_ECOMM = -7 };
+
+/* GPULoglike kinds: the registered hand-written likelihood kernels (replace the user closures
+ * `loglike(data, theta...)`, e.g. Examples/Gaussian_Example.jl:26-28) */
+enum { DEMCMC_GAUSSIAN = 0, DEMCMC_MVNORMAL = 1, DEMCMC_BINOMIAL = 2, DEMCMC_LNR = 3, DEMCMC_LBA = 4,
+       DEMCMC_HIER_NORMAL = 5 };
+/* registered prior specs (replace `prior_loglike(theta...)`, e.g. Examples/Gaussian_Example.jl:11-16) */
+enum { DEMCMC_PRIOR_FLAT = 0, DEMCMC_PRIOR_NORMAL = 1, DEMCMC_PRIOR_HALFCAUCHY = 2,
+       DEMCMC_PRIOR_UNIFORM = 3, DEMCMC_PRIOR_BETA = 4, DEMCMC_PRIOR_NORMAL_REF = 5 };
+/* DE.generate_proposal (src/structs.jl:71, src/crossover.jl:154-226) */
+enum { DEMCMC_RANDOM_GAMMA = 0, DEMCMC_FIXED_GAMMA = 1, DEMCMC_VARIABLE_GAMMA = 2 };
+/* per-particle update kind on the replay tape */
+enum { DEMCMC_KIND_DE = 0, DEMCMC_KIND_SNOOKER = 1, DEMCMC_KIND_MUTATION = 2 };
+
+typedef struct {
+    int32_t kind;   /* DEMCMC_PRIOR_* */
+    int32_t ref;    /* NORMAL_REF: flattened index of the parameter that is the sd */
+    double a, b;    /* NORMAL(mean a, sd b); HALFCAUCHY = truncated(Cauchy(a,b),0,Inf); UNIFORM(a,b);
+                       BETA(a,b); NORMAL_REF(mean a, sd theta[ref]) */
+} demcmc_prior;
+
+/* Binds a model to a registered kernel: the GPULoglike plugin (replaces DEModel's loglike and
+ * prior_loglike closures, src/structs.jl:176-189). */
+typedef struct {
+    int32_t kind;           /* DEMCMC_GAUSSIAN ... */
+    int32_t d;              /* flattened parameter count */
+    int64_t n_obs;          /* observations / trials */
+    int32_t n_dim;          /* MVNORMAL: data dimension; LNR/LBA: accumulators; HIER: subjects */
+    int32_t n_per;          /* HIER: observations per subject */
+    const double *x;        /* GAUSSIAN x[n_obs]; MVNORMAL x[n_obs][n_dim] (= Julia n_dim x n_obs
+                               column-major); LNR/LBA rt[n_obs]; HIER y[n_dim][n_per];
+                               BINOMIAL {N, k} */
+    const int32_t *choice;  /* LNR/LBA: 1-based winner per trial, else NULL */
+    const double *sigma;    /* LNR: sd per accumulator [n_dim], NULL => 1 */
+    double lba_floor;       /* LBA density floor (1e-10 in SequentialSamplingModels), 0 disables */
+    const demcmc_prior *prior; /* [d], host memory */
+    int32_t data_on_device; /* 1: x / choice are device pointers on the handle's device */
+    int32_t reserved;
+} demcmc_model;
+
+/* Mirrors the DE sampler struct field by field (src/structs.jl:57-131). */
+typedef struct {
+    int32_t abi_version;     /* DEMCMC_ABI_VERSION */
+    int32_t n_groups;        /* de.n_groups: groups in the whole job */
+    int32_t Np;              /* de.Np (>= 3: samplepair needs two donors besides the target) */
+    int32_t d;
+    int32_t burnin;          /* de.burnin */
+    int32_t n_initial;       /* de.n_initial (history rows before iteration 1; resample is not built yet) */
+    double alpha, beta, eps, sigma, kappa, theta_snooker; /* de.α β ϵ σ κ θsnooker */
+    int32_t proposal;        /* DEMCMC_RANDOM_GAMMA ... */
+    int32_t n_blocks;        /* 0: blocking_on(de) == false; else blocking on every iteration */
+    const uint8_t *blocks;   /* [n_blocks][d] 1 = updated in this block (de.blocks flattened) */
+    const double *lo, *hi;   /* [d] de.bounds expanded per element (src/utilities.jl:70-78) */
+    uint64_t seed;           /* Philox key of the native draw map */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t group_begin;     /* first group held by this handle (multi-GPU: groups shard over ranks) */
+    int32_t group_count;     /* groups held by this handle; 0 => all */
+    int32_t reserved0;       /* must be 0 */
+    int32_t trace;           /* 1: keep per-sweep proposals / proposal weights / log_adj for
+                                demcmc_get_trace (parity tests) */
+    int32_t store_every;     /* 1 = keep every iteration (reference behaviour, utilities.jl:161-180) */
+} demcmc_config;
+
+/* Structured replay tape: the reference's own random draws, recorded
+ * after transformation.  Shapes use the WHOLE job's G and P; S = n_iter*max(1,n_blocks);
+ * sweep s = iter0*B + block.  Host memory. */
+typedef struct {
+    const double  *mig_u;       /* [n_iter]     rand() <= alpha       (src/main.jl:85)            */
+    const int32_t *mig_n;       /* [n_iter]     0 = no migration      (src/migration.jl:57)       */
+    const int32_t *mig_groups;  /* [n_iter][G]  ordered subset        (src/migration.jl:58)       */
+    const double  *mig_pick_u;  /* [n_iter][G]  uniform of select_particle (src/migration.jl:93)  */
+    const uint8_t *kind;        /* [S][P]       DEMCMC_KIND_*         (main.jl:200, crossover.jl:31) */
+    const int32_t *idx;         /* [S][P][3]    DE (base,m,n) / snooker (z,m,n) slots in the group */
+    const double  *gamma1;      /* [S][P]       gamma_1 or snooker gamma (crossover.jl:162,249)   */
+    const double  *gamma2;      /* [S][P]       gamma_2, 0 after burn-in (crossover.jl:164)       */
+    const double  *u_acc;       /* [S][P]       rand() in accept      (src/utilities.jl:57)       */
+    const double  *noise;       /* [S][P][d]    b_k or N(0,sigma) draws (crossover.jl:168, mutation.jl:18) */
+    const uint8_t *keep;        /* [S][P][d]    recombination restores theta_t,k; NULL if kappa==1 */
+} demcmc_tape;
+
+typedef struct {
+    int64_t iterations, sweeps, particle_updates, loglike_evals, kernel_launches, levels;
+    double device_ms;        /* CUDA-event time of the last run/replay call */
+    double loglike_ms;       /* of which: likelihood kernels (0 unless timing was requested) */
+} demcmc_counters;
+
+typedef struct demcmc_handle demcmc_handle;
+
+const char *demcmc_last_error(void);
+int demcmc_abi_version(void);
+int demcmc_device_count(void);
+const char *demcmc_backend_name(void);   /* "cuda-sm100a" for the product library */
+
+/* DE(; ...) constructor (src/structs.jl:80-131) */
+int demcmc_create(const demcmc_config *cfg, demcmc_handle **out);
+int demcmc_destroy(demcmc_handle *h);
+/* DEModel(; loglike = GPULoglike(...), prior_loglike = ..., data) (src/structs.jl:176-189) */
+int demcmc_set_model(demcmc_handle *h, const demcmc_model *model);
+/* sample_init / init_particle (src/main.jl:263-271, src/utilities.jl:13-22): theta[P_local][d] by
+ * position, ids[P_local] (NULL: id = global position).  Evaluates the initial weights on the device. */
+int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids);
+/* the `for iter = 1:n_iter ... stepfun(model, de, groups)` loop of _sample (src/main.jl:33-38),
+ * i.e. n_iter x step!/pstep! (src/main.jl:84-107), entirely on the device */
+int demcmc_run(demcmc_handle *h, int64_t n_iter);
+/* same loop, consuming the reference's recorded draws instead of Philox */
+int demcmc_replay(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter);
+
+/* de.samples (src/utilities.jl:29-41,161-180): out[n_rows][d][P_local] in Julia order (row
+ * fastest, then parameter, then particle id - group_begin*Np); n_rows = iterations run so far +
+ * n_initial; rows < n_initial are zero-filled */
+int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows);
+/* Particle.accept / Particle.lp (src/structs.jl:202-208, utilities.jl:207-208): [n_rows][P_local],
+ * row fastest, column = particle id - group_begin*Np */
+int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows);
+int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows);
+/* the same history as the device keeps it, rows [row0, row0+n_rows) of the iterations run, by
+ * POSITION: theta[n_rows][P_local][d], w[n_rows][P_local] (= lp), ids[n_rows][P_local] (particle id
+ * sitting at each position after that iteration), acc[n_rows][P_local]; any pointer may be NULL.
+ * This is what a sharded job gathers on the host (ids migrate across ranks). */
+int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, double *theta, double *w,
+                               int32_t *ids, uint8_t *acc);
+/* final `groups` (src/main.jl:36,40): theta[P_local][d], weight[P_local], ids[P_local] by position */
+int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *ids);
+/* per-sweep trace of the LAST run/replay call (needs cfg.trace): prop_theta[S][P_local][d],
+ * prop_weight[S][P_local], log_adj[S][P_local], accepted[S][P_local]; any pointer may be NULL */
+int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, double *log_adj, uint8_t *accepted);
+/* migration picks of the last call: slots[n_iter][G] (-1 where the group did not migrate) */
+int demcmc_get_migration(demcmc_handle *h, int32_t *slots);
+int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out);
+
+/* compute_posterior! pieces (src/utilities.jl:92-99) for n arbitrary parameter vectors
+ * theta[n][d]: loglike[n], prior[n] (prior is -inf when out of bounds); either may be NULL */
+int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior);
+
+/* Particle algebra on the device, for the reference's known-answer tests (test/utility_tests.jl):
+ * project (utilities.jl:239-246), reset! (crossover.jl:336-352), random_gamma body
+ * (crossover.jl:168; pb NULL => fixed/variable form), snooker_update! (crossover.jl:239-257) with
+ * adjust_loglike (crossover.jl:268-273), accept (utilities.jl:55-58) */
+int demcmc_op_project(int device, const double *p1, const double *p2, int32_t d, double *out);
+int demcmc_op_reset(int device, const double *prop, const double *pt, const uint8_t *mask, int32_t d, double *out);
+int demcmc_op_de_proposal(int device, const double *pt, const double *pm, const double *pn, const double *pb,
+                          double g1, double g2, const double *b, int32_t d, double *out);
+int demcmc_op_snooker(int device, const double *pt, const double *pz, const double *pm, const double *pn,
+                      double g, const double *b, int32_t d, double *out, double *log_adj);
+int demcmc_op_accept(int device, const double *w_prop, const double *w_cur, const double *log_adj,
+                     const double *u, int32_t n, uint8_t *out);
+/* select_base (crossover.jl:282-289) and select_particle (migration.jl:89-95) on n weights */
+int demcmc_op_select(int device, const double *w, int32_t n, double u, int32_t *base_idx, int32_t *migrate_idx);
+
+/* Multi-GPU: groups shard over ranks; the only exchange is migration (src/migration.jl:109-116),
+ * done with NCCL over NVLink when the cycle spans devices.  The host passes the NCCL unique id
+ * (128 bytes) obtained on rank 0 to every rank by its own means. */
+int demcmc_comm_unique_id(uint8_t id[128]);
+int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int32_t n_ranks);
+
+/* fp64 FMA peak of the device in TFLOP/s (DFMA microbenchmark; the roofline denominator that
+ * MEASURED_PEAKS.json does not carry) and a copy-bandwidth probe in GB/s */
+int demcmc_fp64_peak(int device, double *tflops);
+int demcmc_copy_peak(int device, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,327 @@
+// emu_backend.cpp -- HOST-ONLY TEST DOUBLE of csrc/backend.h.
+//
+// This is test infrastructure, not a product path: it is compiled only by tests/emu/Makefile into
+// tests/emu/libdemcmc_emu.so, and nothing in the package ever loads it (the product library
+// fails with DEMCMC_ENODEVICE when there is no CUDA device).  It lets the CPU test-suite exercise
+// the engine's host logic (planner levels, row bookkeeping, tape sharding, migration cycle, ABI
+// error paths) and the shared __host__ __device__ math in de_math.h / de_particle.h against the
+// oracle on a machine without a GPU.  "Device" memory is plain malloc; each "kernel" is a loop
+// that honours the same contract as the CUDA kernel of the same name.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "de_particle.h"
+
+namespace de {
+namespace be {
+
+static std::string g_err;
+static int64_t g_launches = 0;
+// exchange hook so a CPU test can stand in for NCCL (tests/test_multirank_gloo.py)
+typedef int (*exchange_fn)(int rank, int n, const int *src_rank, const int *dst_rank, double *send, double *recv, int row_len, void *user);
+static exchange_fn g_exchange = nullptr;
+static void *g_exchange_user = nullptr;
+
+const char *name() { return "emu"; }
+const char *last_error() { return g_err.c_str(); }
+int device_count() { return 1; }
+int set_device(int) { return 0; }
+void *dmalloc(size_t b) { return calloc(1, b ? b : 8); }
+void dfree(void *p) { free(p); }
+void *hmalloc_pinned(size_t b) { return calloc(1, b ? b : 8); }
+void hfree_pinned(void *p) { free(p); }
+int h2d(void *d, const void *s, size_t b) { if (b) memcpy(d, s, b); return 0; }
+int d2h(void *d, const void *s, size_t b) { if (b) memcpy(d, s, b); return 0; }
+int d2d(void *d, const void *s, size_t b) { if (b) memmove(d, s, b); return 0; }
+int dzero(void *d, size_t b) { if (b) memset(d, 0, b); return 0; }
+int sync() { return 0; }
+void *event_create() { return malloc(8); }
+void event_destroy(void *e) { free(e); }
+int event_record(void *) { return 0; }
+int event_wait(void *) { return 0; }
+int timer_start() { return 0; }
+int timer_stop(double *ms) { *ms = 0.0; return 0; }
+int64_t launch_count() { return g_launches; }
+
+struct ksum_t { double s, c; };
+static void kadd(ksum_t &k, double x)
+{
+    const double t = k.s + x;
+    if (isfinite(t)) { if (fabs(k.s) >= fabs(x)) k.c += (k.s - t) + x; else k.c += (x - t) + k.s; }
+    k.s = t;
+}
+static double kval(const ksum_t &k) { return isfinite(k.s) ? k.s + k.c : k.s; }
+
+int launch_pack_ssd(const double *x, int, ModelDev *m)
+{
+    ++g_launches;
+    double *xT = const_cast<double *>(m->xT);
+    for (int k = 0; k < m->ssd_k; ++k)
+        for (int64_t i = 0; i < m->ssd_ld; ++i) {
+            double v = 0.0;
+            if (i < m->ssd_n) v = m->kind == M_MVNORMAL ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i];
+            xT[(int64_t)k * m->ssd_ld + i] = v;
+        }
+    return 0;
+}
+
+// contract of k_ssd / k_ll_pointwise: part[p][split] for every particle of the level
+int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, const Level &lv, double *part)
+{
+    ++g_launches;
+    if (m.kind == M_BINOMIAL) return 0;
+    const int n_split = m.n_osplit * m.n_ksplit;
+    for (int q = 0; q < lv.n; ++q) {
+        const int p = lv.order ? lv.order[q] : q;
+        const double *th = theta + (size_t)p * m.d;
+        if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+            for (int os = 0; os < m.n_osplit; ++os)
+                for (int ks = 0; ks < m.n_ksplit; ++ks) {
+                    const int k0 = ks * m.ksplit_len, k1 = std::min(m.ssd_k, k0 + m.ksplit_len);
+                    const int64_t o0 = (int64_t)os * m.split_len, o1 = std::min<int64_t>(m.ssd_n, o0 + m.split_len);
+                    double s = 0.0;
+                    for (int k = k0; k < k1; ++k) {
+                        const double mean = m.kind == M_HIER ? th[0] + th[2 + k] : th[k];
+                        for (int64_t i = o0; i < o1; ++i) { const double t = m.xT[(int64_t)k * m.ssd_ld + i] - mean; s += t * t; }
+                    }
+                    part[(size_t)p * n_split + os * m.n_ksplit + ks] = s;
+                }
+        } else {
+            double par[MAX_ACC + 4];
+            if (m.kind == M_GAUSSIAN) { par[0] = th[0]; par[1] = th[1]; par[2] = log(th[1]); }
+            else if (m.kind == M_LNR) { for (int r = 0; r <= m.n_dim; ++r) par[r] = th[r]; }
+            else {
+                double pneg = 1.0;
+                for (int r = 0; r < m.n_dim; ++r) { par[r] = th[r]; pneg *= norm_cdf(-th[r]); }
+                par[m.n_dim] = th[m.n_dim]; par[m.n_dim + 1] = th[m.n_dim + 1]; par[m.n_dim + 2] = th[m.n_dim + 2];
+                par[m.n_dim + 3] = 1.0 / (1.0 - pneg);
+            }
+            const double *sg = m.has_sigma ? m.sigma_acc : nullptr;
+            for (int os = 0; os < m.n_osplit; ++os) {
+                const int64_t i0 = (int64_t)os * m.split_len, i1 = std::min<int64_t>(m.n_obs, i0 + m.split_len);
+                double s = 0.0;
+                for (int64_t i = i0; i < i1; ++i) {
+                    const int c = m.kind == M_GAUSSIAN ? 0 : m.choice[i] - 1;
+                    if (m.kind == M_GAUSSIAN) s += gaussian_obs(par, m.x[i]);
+                    else if (m.kind == M_LNR) s += lnr_obs(par, m.n_dim, sg, m.x[i], c);
+                    else s += lba_obs(par, m.n_dim, par[m.n_dim + 3], m.lba_floor, m.x[i], c);
+                }
+                part[(size_t)p * n_split + os] = s;
+            }
+        }
+    }
+    return 0;
+}
+
+int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior, double *w, double *part)
+{
+    Level lv; lv.order = nullptr; lv.n = (int32_t)n;
+    launch_loglik(cfg, m, theta, lv, part);
+    ++g_launches;
+    const SerialLanes co;
+    const int n_split = m.n_osplit * m.n_ksplit;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *th = theta + (size_t)i * cfg.d;
+        bool inb; double pr;
+        bounds_and_prior(co, cfg, m, th, inb, pr);
+        double s = 0.0;
+        if (m.kind != M_BINOMIAL) for (int q = 0; q < n_split; ++q) s += part[(size_t)i * n_split + q];
+        const double l = finalize_ll(m, th, s);
+        if (ll) ll[i] = l;
+        if (prior) prior[i] = inb ? pr : -inf();
+        if (w) w[i] = inb ? pr + l : -inf();
+    }
+    return 0;
+}
+
+int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot)
+{
+    ++g_launches;
+    const int Np = cfg.Np;
+    for (int g = 0; g < cfg.G_local; ++g) {
+        const double *wg = w + (size_t)g * Np;
+        double *tg = th + (size_t)g * Np, *cg = cw + (size_t)g * Np;
+        ksum_t k = { 0, 0 };
+        for (int i = 0; i < Np; ++i) { tg[i] = exp(wg[i]); kadd(k, tg[i]); }
+        const double t = kval(k);
+        bool bad = false;
+        for (int i = 0; i < Np; ++i) { tg[i] = tg[i] / t; bad |= tg[i] != tg[i]; }
+        const double *src = bad ? wg : tg;
+        ksum_t k2 = { 0, 0 };
+        for (int i = 0; i < Np; ++i) kadd(k2, src[i]);
+        tot[g] = kval(k2);
+        double c = src[0];
+        cg[0] = c;
+        for (int i = 1; i < Np; ++i) { c += src[i]; cg[i] = c; }
+    }
+    return 0;
+}
+
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+{
+    ++g_launches;
+    for (int q = 0; q < lv.n; ++q) propose_particle(SerialLanes(), cfg, m, ctx, lv.order[q]);
+    return 0;
+}
+
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+{
+    ++g_launches;
+    for (int q = 0; q < lv.n; ++q) accept_particle(SerialLanes(), cfg, m, ctx, lv.order[q]);
+    return 0;
+}
+
+static int select_particle(const double *w, int Np, double u)
+{
+    std::vector<double> th(Np);
+    ksum_t k = { 0, 0 };
+    for (int i = 0; i < Np; ++i) { th[i] = exp(-w[i]); kadd(k, th[i]); }
+    const double tot = kval(k);
+    bool bad = false;
+    for (int i = 0; i < Np; ++i) { th[i] /= tot; bad |= th[i] != th[i]; }
+    int r = 0;
+    if (bad) { for (int i = 0; i < Np; ++i) { if (w[i] != w[i]) { r = i; break; } if (w[i] < w[r]) r = i; } return r; }
+    ksum_t k2 = { 0, 0 };
+    for (int i = 0; i < Np; ++i) kadd(k2, th[i]);
+    const double t = u * kval(k2);
+    double cw = th[0];
+    while (cw < t && r < Np - 1) { ++r; cw += th[r]; }
+    return r;
+}
+
+static int select_base(const double *w, int Np, double u)
+{
+    std::vector<double> th(Np);
+    ksum_t k = { 0, 0 };
+    for (int i = 0; i < Np; ++i) { th[i] = exp(w[i]); kadd(k, th[i]); }
+    const double tot = kval(k);
+    bool bad = false;
+    for (int i = 0; i < Np; ++i) { th[i] /= tot; bad |= th[i] != th[i]; }
+    const double *src = bad ? w : th.data();
+    ksum_t k2 = { 0, 0 };
+    for (int i = 0; i < Np; ++i) kadd(k2, src[i]);
+    const double t = u * kval(k2);
+    int r = 0;
+    double cw = src[0];
+    while (cw < t && r < Np - 1) { ++r; cw += src[r]; }
+    return r;
+}
+
+int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks)
+{
+    ++g_launches;
+    for (int i = 0; i < a.n; ++i) {
+        const int gl = a.groups[i] - cfg.group_begin;
+        picks[i] = (gl < 0 || gl >= cfg.G_local) ? -1 : select_particle(w + (size_t)gl * cfg.Np, cfg.Np, a.u_pick[i]);
+    }
+    return 0;
+}
+
+int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *theta, const double *w, const int32_t *id, const uint8_t *acc, double *stage)
+{
+    ++g_launches;
+    for (int i = 0; i < a.n; ++i) {
+        const int gl = a.groups[i] - cfg.group_begin;
+        if (gl < 0 || gl >= cfg.G_local) continue;
+        const size_t p = (size_t)gl * cfg.Np + picks[i];
+        double *row = stage + (size_t)i * (cfg.d + 3);
+        memcpy(row, theta + p * cfg.d, sizeof(double) * cfg.d);
+        row[cfg.d] = w[p]; row[cfg.d + 1] = (double)id[p]; row[cfg.d + 2] = (double)acc[p];
+    }
+    return 0;
+}
+
+int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta, double *w, int32_t *id, uint8_t *acc)
+{
+    ++g_launches;
+    for (int i = 0; i < a.n; ++i) {
+        const int gl = a.groups[i] - cfg.group_begin;
+        if (gl < 0 || gl >= cfg.G_local) continue;
+        const size_t p = (size_t)gl * cfg.Np + picks[i];
+        const double *row = stage + (size_t)((i + a.n - 1) % a.n) * (cfg.d + 3);
+        memcpy(theta + p * cfg.d, row, sizeof(double) * cfg.d);
+        w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2];
+    }
+    return 0;
+}
+
+int launch_history_by_id(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid, int64_t n_rows_dev, int64_t row0,
+                         int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base, double *samples, double *lp, uint8_t *accept)
+{
+    ++g_launches;
+    for (int64_t r = 0; r < n_rows_dev; ++r)
+        for (int slot = 0; slot < P; ++slot) {
+            const int id = rid[r * P + slot] - id_base;
+            if (id < 0 || id >= P) continue;
+            const int64_t ro = row0 + r;
+            if (samples) for (int k = 0; k < d; ++k) samples[((int64_t)id * d + k) * n_rows_out + ro] = rt[(r * P + slot) * d + k];
+            if (lp) lp[(int64_t)id * n_rows_out + ro] = rw[r * P + slot];
+            if (accept) accept[(int64_t)id * n_rows_out + ro] = ra[r * P + slot];
+        }
+    return 0;
+}
+
+int launch_op_project(const double *p1, const double *p2, int d, double *out)
+{
+    double v1 = 0, v2 = 0;
+    for (int k = 0; k < d; ++k) { v1 += p1[k] * p2[k]; v2 += p2[k] * p2[k]; }
+    for (int k = 0; k < d; ++k) out[k] = p2[k] * (v1 / v2);
+    return 0;
+}
+int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b, int d, double *out, double *log_adj)
+{
+    double v1m = 0, v1n = 0, v2 = 0;
+    for (int k = 0; k < d; ++k) { const double pd = pt[k] - pz[k]; v1m += pm[k] * pd; v1n += pn[k] * pd; v2 += pd * pd; }
+    double sq1 = 0, sq2 = 0;
+    for (int k = 0; k < d; ++k) {
+        out[k] = snooker_elem(pt[k], pz[k], v1m / v2, v1n / v2, g, b[k]);
+        sq1 += (out[k] - pz[k]) * (out[k] - pz[k]); sq2 += (pt[k] - pz[k]) * (pt[k] - pz[k]);
+    }
+    *log_adj = adjust_loglike(sq1, sq2, d);
+    return 0;
+}
+int launch_op_de(const double *pt, const double *pm, const double *pn, const double *pb, double g1, double g2, const double *b, int d, double *out)
+{
+    for (int k = 0; k < d; ++k) out[k] = de_elem(pt[k], pm[k], pn[k], pb ? pb[k] : pt[k], g1, g2, pb != nullptr, b[k]);
+    return 0;
+}
+int launch_op_reset(const double *prop, const double *pt, const uint8_t *mask, int d, double *out)
+{
+    for (int k = 0; k < d; ++k) out[k] = mask[k] ? prop[k] : pt[k];
+    return 0;
+}
+int launch_op_accept(const double *wp, const double *wc, const double *adj, const double *u, int n, uint8_t *out)
+{
+    for (int i = 0; i < n; ++i) out[i] = accept(wp[i], wc[i], adj[i], u[i]) ? 1 : 0;
+    return 0;
+}
+int launch_op_select(const double *w, int n, double u, int32_t *base_idx, int32_t *mig_idx)
+{
+    *base_idx = select_base(w, n, u);
+    *mig_idx = select_particle(w, n, u);
+    return 0;
+}
+int fp64_peak(double *t) { *t = 0.0; return 0; }
+int copy_peak(double *g) { *g = 0.0; return 0; }
+
+int comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return 0; }
+int comm_init(const uint8_t *, int, int, void **comm) { *comm = malloc(8); return 0; }
+int comm_destroy(void *comm) { free(comm); return 0; }
+int comm_exchange(void *, int rank, int n, const int *src_rank, const int *dst_rank, double *send, double *recv, int row_len)
+{
+    if (!g_exchange) { g_err = "emu: no exchange hook installed"; return -1; }
+    return g_exchange(rank, n, src_rank, dst_rank, send, recv, row_len, g_exchange_user);
+}
+
+} // namespace be
+} // namespace de
+
+extern "C" void demcmc_emu_set_exchange(de::be::exchange_fn fn, void *user)
+{
+    de::be::g_exchange = fn;
+    de::be::g_exchange_user = user;
+}
