@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the DE-MCMC population step (BASELINE.json metric).
+
+A "step" is one iteration of the sampler: migration (w.p. alpha) + one sweep over every particle
+(proposal, full log-posterior, Metropolis accept, state/sample write).  Workload at N=1 is
+BASELINE.json configs[1]: isotropic multivariate normal d=50, 1e5 observations, 4 groups x 256
+particles, crossover + snooker (theta_snooker = 0.1), synthetic data (seed 50514).
+With N GPUs the groups shard over the ranks (4 groups per GPU, weak scaling) and migration crosses
+NVLink through NCCL send/recv when a cycle spans ranks.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # the CPU restatement of the reference
+                                                           # (the reference is Julia; no Julia here)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec (loglike evals incl.)"
+UNIT = "particle-updates/s"
+N_OBS, N_DIM, GROUPS_PER_GPU, NP = 100_000, 50, 4, 256
+THETA_SNOOKER = 0.1
+L2_FLUSH_BYTES = 256 << 20
+
+
+def workload(n_groups, seed=50514):
+    rng = np.random.default_rng(seed)
+    mu = rng.normal(size=N_DIM)
+    x = rng.normal(mu, 1.0, size=(N_OBS, N_DIM))
+    prior = [("normal", 0.0, 1.0)] * N_DIM + [("halfcauchy", 0.0, 1.0)]
+    lo = [-np.inf] * N_DIM + [0.0]
+    hi = [np.inf] * (N_DIM + 1)
+    # initial states: prior draws as in the example's sample_prior (Multivariate_Guassian_Example.jl:16-20)
+    P = n_groups * NP
+    theta0 = np.column_stack([rng.normal(size=(P, N_DIM)), np.abs(rng.standard_cauchy(P))])
+    return x, prior, lo, hi, theta0
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the C restatement of the reference's algorithm (oracle/), one thread per group as the
+# reference's ThreadsX.map over groups (src/main.jl:135-148)
+# ---------------------------------------------------------------------------------------------
+def cpu_updates_per_s(steps, warmup, budget_s=100.0):
+    from oracle import oracle as O
+    x, prior, lo, hi, _ = workload(GROUPS_PER_GPU)
+    model = O.Model("mvnormal", N_DIM + 1, prior, x=x)
+    cores = min(GROUPS_PER_GPU, os.cpu_count() or 1)
+    rng = np.random.default_rng(1)
+
+    def run(np_sample, n_iter):
+        P = GROUPS_PER_GPU * np_sample
+        theta0 = np.column_stack([rng.normal(size=(P, N_DIM)), np.abs(rng.standard_cauchy(P)) + 0.5])
+        cfg = O.Config(GROUPS_PER_GPU, np_sample, N_DIM + 1, lo, hi, burnin=0, theta_snooker=THETA_SNOOKER, n_threads=cores, seed=3)
+        t0 = time.perf_counter()
+        O.run(cfg, model, theta0, n_iter, record=False, trace=False, history=False)
+        return time.perf_counter() - t0, P * n_iter
+
+    # probe the per-update cost, then size the per-step sample so the whole run fits the budget
+    t, n = run(3, 1)
+    per_update = (t - 0.0) / (n + GROUPS_PER_GPU * 3)      # the run also evaluates the initial weights
+    total = max(1, steps + warmup)
+    np_sample = int(max(3, min(NP, budget_s / (per_update * total * GROUPS_PER_GPU))))
+    if warmup > 0:
+        run(np_sample, min(warmup, 1))
+    t, n = run(np_sample, steps)
+    t_init = per_update * GROUPS_PER_GPU * np_sample        # initial-weight evaluations are not updates
+    ups = n / max(t - t_init, 1e-9)
+    sample = (f"{steps} iterations of the same model/data (d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups) with "
+              f"{np_sample} particles per group instead of {NP} ({n} particle updates)")
+    return ups, cores, sample, t / max(1, steps) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ups, cores, sample, ms = cpu_updates_per_s(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])"},
+            "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference's algorithm (oracle/), one thread per group; the reference itself is Julia and cannot run in this image"},
+            "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import demcmc_b200 as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libdemcmc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D._ffi.use_library(D._ffi.DEFAULT_LIB)
+    assert D._ffi.lib().demcmc_backend_name() == b"cuda-sm100a"
+
+    G = GROUPS_PER_GPU * world
+    x, prior, lo, hi, theta0 = workload(G)
+    P_local = GROUPS_PER_GPU * NP
+    d = N_DIM + 1
+    kw = dict(burnin=0, theta_snooker=THETA_SNOOKER, seed=20261017, device=local, group_begin=rank * GROUPS_PER_GPU,
+              group_count=GROUPS_PER_GPU)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-side number: inputs resident in HBM before the timed region ----------------------
+    xd = torch.from_numpy(x).to(f"cuda:{local}")                      # the data set, already on the device
+    torch.cuda.synchronize()
+    h = D.Handle(G, NP, d, lo, hi, **kw)
+    h.set_model("mvnormal", prior, device_ptrs=(xd.data_ptr(), None), n_obs=N_OBS, n_dim=N_DIM)
+    if world > 1:
+        uid = [D.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+    h.set_state(theta0[rank * P_local:(rank + 1) * P_local])
+    h.set_timing(L2_FLUSH_BYTES, True)
+    h.run(args.warmup)
+    c0 = h.counters()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    t0 = time.time()
+    h.run(args.steps)
+    barrier()
+    t1 = time.time()
+    c1 = h.counters()
+    ck = clocks.stop(t0, t1)
+    wall_timed = t1 - t0
+    ms = torch.tensor([c1["device_ms"]], dtype=torch.float64, device=f"cuda:{local}")
+    ms_ll = torch.tensor([c1["loglike_ms"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)                    # max over ranks, device time
+        dist.all_reduce(ms_ll, op=dist.ReduceOp.MAX)
+    ms, ms_ll = float(ms.item()), float(ms_ll.item())
+    updates = (c1["particle_updates"] - c0["particle_updates"]) * world
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    ll_launches = c1["levels"] - c0["levels"]
+    value = updates / (ms * 1e-3)
+
+    # steady state without the L2 flush (how a real run behaves: the data set stays in L2)
+    h.set_timing(0, False)
+    barrier()
+    h.run(args.steps)
+    barrier()
+    ms_steady = h.counters()["device_ms"]
+    h.close()
+
+    # ---- roofline of the dominant kernel (k_ssd, the likelihood) ----------------------------------
+    peaks = measured_peaks()
+    fp64_peak = D.fp64_peak(local)                                   # DFMA microbenchmark, TFLOP/s (not in MEASURED_PEAKS.json)
+    flops = 3.0 * N_OBS * N_DIM * (updates / world)                  # direct form: DADD + DFMA per (obs, dim, particle)
+    achieved = flops / (ms_ll * 1e-3) / 1e12 if ms_ll > 0 else None
+    roofline = {"bound": "fp64", "kernel": "k_ssd<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak if achieved else None,
+                "pipe_frac": (achieved / fp64_peak) * 4.0 / 3.0 if achieved else None,
+                "traffic": None,
+                "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
+                "avg_launch_ms": ms_ll / max(1, ll_launches), "share_of_step": ms_ll / ms if ms > 0 else None,
+                "peak_source": "measured in this run: DFMA loop, 16 independent chains x 256 threads x 8 CTAs/SM (MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s)",
+                "note": "the kernel issues 2 fp64 instructions (DADD+DFMA) per 3 algorithmic flops, so frac <= 0.75; pipe_frac = issue-slot utilisation of the fp64 pipe",
+                "hbm_gbs_measured": peaks.get("hbm_gbs")}
+
+    # ---- end to end through the public API with HOST buffers -------------------------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        rng = np.random.default_rng(7)
+        model = D.DEModel(sample_prior=lambda: [rng.normal(size=N_DIM), abs(rng.standard_cauchy())],
+                          prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                          loglike=D.GPULoglike("mvnormal", x), names=("μ", "σ"))
+        if world == 1:
+            de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=NP, burnin=0,
+                      θsnooker=THETA_SNOOKER, seed=11)
+            D.sample(model, de, 2, device=local)                     # warm the context and the allocator
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            chains = D.sample(model, de, args.steps, device=local)   # host data in, chains out
+            t_e2e = time.perf_counter() - t0
+            assert len(chains) == args.steps
+            h2d = (x.nbytes + G * NP * d * 8) / args.steps
+            d2h = G * NP * (d * 8 + 8 + 1)
+            e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "call": "sample(model, de, n_iter) with host (pageable numpy) data; includes handle creation, upload, all iterations, download of samples/accept/lp and bundle_samples",
+                   "seconds": t_e2e}
+    if world > 1:
+        # sharded e2e: every rank builds its handle from host buffers, runs, and downloads its by-slot history
+        barrier()
+        t0 = time.perf_counter()
+        h2 = D.Handle(G, NP, d, lo, hi, **kw)
+        h2.set_model("mvnormal", prior, x=x)
+        uid2 =[D.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        h2.comm_init(uid2[0], rank, world)
+        h2.set_state(theta0[rank * P_local:(rank + 1) * P_local])
+        h2.run(args.steps)
+        hist = h2.history_by_slot()
+        h2.close()
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_e2e.item())
+        e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (x.nbytes + P_local * d * 8) / args.steps,
+               "d2h_bytes_per_step": P_local * (d * 8 + 8 + 4 + 1), "seconds": t_e2e,
+               "call": "per rank: Handle + set_model(host data) + set_state + run + history_by_slot (host buffers in and out)"}
+        del hist
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ups, cores, sample, _ = cpu_updates_per_s(2, 0, budget_s=25.0)
+        cpu = {"value": ups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])",
+                           "groups_total": G, "particles_total": G * NP, "parallelism": f"groups sharded over {world} GPU(s); NCCL send/recv migration",
+                           "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten between timed steps, per-step CUDA events, flush excluded",
+                           "timing": "CUDA events on the library's launching stream (demcmc_counters.device_ms), max over ranks"},
+                "value_steady_no_flush": updates / (ms_steady * 1e-3) if world == 1 else None,
+                "gpu_launches": int(launches), "clocks": ck, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "wall_s_timed_region": wall_timed}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

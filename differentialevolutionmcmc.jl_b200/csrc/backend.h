@@ -30,6 +30,11 @@ void event_destroy(void *ev);
 int event_record(void *ev);               // on the engine stream
 int event_wait(void *ev);                 // host waits
 
+void *tevent_create();                    // timing-capable event
+void tevent_destroy(void *ev);
+int tevent_elapsed(void *a, void *b, double *ms);
+int dfill(void *dst, int byte, size_t bytes);
+
 // CUDA-event stopwatch on the engine stream
 int timer_start();
 int timer_stop(double *ms);

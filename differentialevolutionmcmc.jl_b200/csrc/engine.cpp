@@ -87,6 +87,11 @@ struct demcmc_handle {
     int rank = 0, n_ranks = 1;
     std::vector<int> group_owner;                       // [G_total] rank owning each group
     demcmc_counters ctr;
+    // measurement mode (demcmc_set_timing)
+    int64_t flush_bytes = 0;
+    bool time_loglik = false;
+    void *flush_buf = nullptr;
+    std::vector<void *> tev;                            // pool of timing events
 };
 
 static Row row_of(demcmc_handle *h, bool hist, int64_t idx)
@@ -232,7 +237,8 @@ int demcmc_destroy(demcmc_handle *h)
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
                      h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
-                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc };
+                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
+    for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
     for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::dfree(u.d_order); be::dfree(u.d_mut); be::event_destroy(u.copied); }
     delete h;
@@ -422,6 +428,11 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 
     const int64_t launches0 = be::launch_count();
     int64_t n_levels = 0;
+    // timing events: [2*it, 2*it+1] bracket iteration `it` when the L2 flush is on; the likelihood
+    // launches get their own pairs after those
+    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter : 0), tev_ll0 = tev_need, tev_ll = 0;
+    if (h->time_loglik) tev_need += 2 * (size_t)S * 64;
+    while (h->tev.size() < tev_need) { void *e = be::tevent_create(); if (!e) { cleanup(); return fail(DEMCMC_ECUDA, "event pool: %s", be::last_error()); } h->tev.push_back(e); }
     BE(be::timer_start());
     SweepPlan plan;
     MigSchedule ms;
@@ -430,6 +441,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         const int64_t de_iter = itg + 1 + cfg.n_initial;   // de.iter (main.jl:34)
         const bool in_burnin = de_iter <= cfg.burnin;
         Row cur = cur_row(h);
+        if (h->flush_bytes) {                               // evict L2 between timed iterations
+            BE(be::dfill(h->flush_buf, (int)(it & 1), (size_t)h->flush_bytes));
+            BE(be::event_record(h->tev[2 * it]));
+        }
 
         // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
         if (Gt > 1) {
@@ -528,7 +543,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 lv.n = plan.level_off[l + 1] - plan.level_off[l];
                 if (lv.n == 0) continue;
                 BE(be::launch_propose(h->dcfg, h->dmodel, ctx, lv));
+                const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+                if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
                 BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part));
+                if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
                 BE(be::launch_accept(h->dcfg, h->dmodel, ctx, lv));
                 ++n_levels;
             }
@@ -536,10 +554,18 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
+        if (h->flush_bytes) BE(be::event_record(h->tev[2 * it + 1]));
     }
     double ms_dev = 0.0;
     BE(be::timer_stop(&ms_dev));
     BE(be::sync());
+    if (h->flush_bytes) {                                   // sum of the per-iteration times, flushes excluded
+        ms_dev = 0.0;
+        for (int64_t it = 0; it < n_iter; ++it) { double t = 0.0; BE(be::tevent_elapsed(h->tev[2 * it], h->tev[2 * it + 1], &t)); ms_dev += t; }
+    }
+    double ms_ll = 0.0;
+    for (size_t i = 0; i < tev_ll; ++i) { double t = 0.0; BE(be::tevent_elapsed(h->tev[tev_ll0 + 2 * i], h->tev[tev_ll0 + 2 * i + 1], &t)); ms_ll += t; }
+    h->ctr.loglike_ms = ms_ll;
     // migration log -> host
     for (auto &ev : mig_events) {
         std::vector<int32_t> picks(ev.second.n);
@@ -636,6 +662,20 @@ int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
 {
     if (!h || !slots) return fail(DEMCMC_EINVAL, "null argument");
     memcpy(slots, h->last_mig_slots.data(), sizeof(int32_t) * (size_t)h->mig_log_iters * h->cfg.n_groups);
+    return 0;
+}
+
+int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_loglik)
+{
+    if (!h || l2_flush_bytes < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    BE(be::set_device(h->cfg.device));
+    be::dfree(h->flush_buf); h->flush_buf = nullptr; h->flush_bytes = 0;
+    if (l2_flush_bytes > 0) {
+        h->flush_buf = be::dmalloc((size_t)l2_flush_bytes);
+        if (!h->flush_buf) return fail(DEMCMC_ENOMEM, "flush buffer");
+        h->flush_bytes = l2_flush_bytes;
+    }
+    h->time_loglik = time_loglik != 0;
     return 0;
 }
 

@@ -94,6 +94,21 @@ void *event_create()
 void event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
 int event_record(void *ev) { CU(cudaEventRecord((cudaEvent_t)ev, stream())); return 0; }
 int event_wait(void *ev) { CU(cudaEventSynchronize((cudaEvent_t)ev)); return 0; }
+void *tevent_create()
+{
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return (void *)e;
+}
+void tevent_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int tevent_elapsed(void *a, void *b, double *ms)
+{
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, (cudaEvent_t)a, (cudaEvent_t)b));
+    *ms = f;
+    return 0;
+}
+int dfill(void *dst, int byte, size_t bytes) { if (bytes) CU(cudaMemsetAsync(dst, byte, bytes, stream())); return 0; }
 int timer_start()
 {
     if (!g_t0) { CU(cudaEventCreate(&g_t0)); CU(cudaEventCreate(&g_t1)); }

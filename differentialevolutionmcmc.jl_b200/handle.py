@@ -118,7 +118,7 @@ class Handle:
         self._last_iters = n_iter
 
     def replay(self, tape: dict, n_iter):
-        """`tape`: dict of numpy arrays with the oracle's field names and whole-job shapes."""
+        """`tape`: dict of numpy arrays named after the demcmc_tape fields, whole-job shapes."""
         def get(name, dt):
             a = tape.get(name)
             if a is None:
@@ -183,6 +183,9 @@ class Handle:
         c = _ffi.Counters()
         check(_ffi.lib().demcmc_get_counters(self._h, C.byref(c)))
         return {n: getattr(c, n) for n, _ in _ffi.Counters._fields_}
+
+    def set_timing(self, l2_flush_bytes=0, time_loglik=False):
+        check(_ffi.lib().demcmc_set_timing(self._h, int(l2_flush_bytes), int(bool(time_loglik))))
 
     def eval(self, theta):
         th = f8(theta).reshape(-1, self.d)

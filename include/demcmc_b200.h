@@ -156,6 +156,11 @@ int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, 
 /* migration picks of the last call: slots[n_iter][G] (-1 where the group did not migrate) */
 int demcmc_get_migration(demcmc_handle *h, int32_t *slots);
 int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out);
+/* measurement mode for bench.py: l2_flush_bytes > 0 overwrites a buffer of that size between
+ * iterations (evicting L2) and makes counters.device_ms the sum of per-iteration CUDA-event times
+ * with the flushes excluded; time_loglik brackets every likelihood launch with CUDA events on the
+ * launching stream and reports their sum in counters.loglike_ms */
+int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_loglik);
 
 /* compute_posterior! pieces (src/utilities.jl:92-99) for n arbitrary parameter vectors
  * theta[n][d]: loglike[n], prior[n] (prior is -inf when out of bounds); either may be NULL */

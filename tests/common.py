@@ -1,0 +1,168 @@
+"""Shared fixtures: the six registered models as (oracle Model, handle.set_model kwargs) pairs on
+seeded synthetic data, plus matching sampler configurations."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import demcmc_b200 as D  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "libdemcmc_emu.so")
+CUDA_LIB = D._ffi.DEFAULT_LIB
+INF = np.inf
+
+
+def use_emu():
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu"), "-s"], check=True)
+    D._ffi.use_library(EMU_LIB)
+
+
+def use_cuda():
+    D._ffi.use_library(CUDA_LIB)
+    assert D._ffi.lib().demcmc_backend_name() == b"cuda-sm100a"
+
+
+def lba_sim(rng, n, nu=(3.0, 2.0), A=0.8, k=0.2, tau=0.3):
+    """Standard LBA generator: start ~ U(0,A), drift ~ N(nu,1) redrawn until one is positive."""
+    nu = np.asarray(nu)
+    choice = np.zeros(n, dtype=np.int32)
+    rt = np.zeros(n)
+    b = A + k
+    for i in range(n):
+        while True:
+            v = rng.normal(nu, 1.0)
+            if (v > 0).any():
+                break
+        a = rng.uniform(0, A, size=nu.size)
+        t = np.where(v > 0, (b - a) / np.where(v > 0, v, 1.0), np.inf)
+        choice[i] = int(np.argmin(t)) + 1
+        rt[i] = tau + t.min()
+    return choice, rt
+
+
+def lnr_sim(rng, n, nu=(-2.0, -2.0, -3.0, -3.0), tau=0.5):
+    nu = np.asarray(nu)
+    x = np.exp(rng.normal(nu, 1.0, size=(n, nu.size)))
+    return (np.argmin(x, axis=1) + 1).astype(np.int32), tau + x.min(axis=1)
+
+
+class Case:
+    """One model + sampler setup usable with both the oracle and a Handle."""
+
+    def __init__(self, name, kind, d, prior, lo, hi, sample_prior, data):
+        self.name, self.kind, self.d, self.prior = name, kind, d, prior
+        self.lo, self.hi = np.asarray(lo, float), np.asarray(hi, float)
+        self.sample_prior = sample_prior
+        self.data = data      # kwargs: x, choice, sigma...
+
+    def oracle_model(self):
+        return O.Model(self.kind, self.d, self.prior, **self.data)
+
+    def oracle_config(self, G, Np, **kw):
+        return O.Config(G, Np, self.d, self.lo, self.hi, **kw)
+
+    def handle(self, G, Np, **kw):
+        h = D.Handle(G, Np, self.d, self.lo, self.hi, **kw)
+        h.set_model(self.kind, self.prior, **self.data)
+        return h
+
+    def theta0(self, rng, P):
+        return np.array([self.sample_prior(rng) for _ in range(P)])
+
+
+def halfcauchy(rng):
+    return abs(rng.standard_cauchy())
+
+
+def make_case(name, rng, n_obs=None):
+    if name == "gaussian":
+        n = n_obs or 50
+        x = rng.normal(0.0, 1.0, n)
+        return Case(name, "gaussian", 2, [("normal", 0, 1), ("halfcauchy", 0, 1)], [-INF, 0], [INF, INF],
+                    lambda r: [r.normal(), halfcauchy(r)], dict(x=x))
+    if name == "mvnormal":
+        n = n_obs or 200
+        dm = 7
+        mu = rng.normal(size=dm)
+        x = rng.normal(mu, 1.0, size=(n, dm))
+        return Case(name, "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-INF] * dm + [0],
+                    [INF] * (dm + 1), lambda r: list(r.normal(size=dm)) + [halfcauchy(r) + 0.3], dict(x=x))
+    if name == "binomial":
+        return Case(name, "binomial", 1, [("beta", 1, 1)], [0], [1], lambda r: [r.uniform()], dict(x=np.array([10.0, 4.0])))
+    if name == "lnr":
+        n = n_obs or 100
+        choice, rt = lnr_sim(rng, n)
+        mn = rt.min()
+        return Case(name, "lnr", 5, [("normal", 0, 3)] * 4 + [("uniform", 0, mn)], [-INF] * 4 + [0], [INF] * 4 + [mn],
+                    lambda r: list(r.normal(0, 3, 4)) + [r.uniform(0, mn)], dict(x=rt, choice=choice, n_dim=4))
+    if name == "lba":
+        n = n_obs or 100
+        choice, rt = lba_sim(rng, n)
+        mn = rt.min()
+        prior = [("normal", 1, 5), ("normal", 1, 5), ("normal", 0.8, 0.2), ("normal", 0.2, 0.1), ("uniform", 0, mn)]
+        return Case(name, "lba", 5, prior, [0, 0, 0, 0, 0], [INF, INF, INF, INF, mn],
+                    lambda r: [abs(r.normal(1, 5)), abs(r.normal(1, 5)), abs(r.normal(0.8, 0.2)), abs(r.normal(0.2, 0.1)), r.uniform(0, mn)],
+                    dict(x=rt, choice=choice, n_dim=2))
+    if name == "hier_normal":
+        S, n = 9, (n_obs or 12)
+        b0 = rng.normal(0, 1, S)
+        y = rng.normal(1.0 + b0[:, None], 0.5, size=(S, n))
+        prior = [("normal", 1, 1), ("halfcauchy", 0, 1)] + [("normal_ref", 0, 0, 1)] * S + [("halfcauchy", 0, 1)]
+        lo = [-INF, 0] + [-INF] * S + [0]
+        hi = [INF] * (S + 3)
+
+        def sp(r):
+            sb = halfcauchy(r) + 0.2
+            return [r.normal(1, 1), sb] + list(r.normal(0, sb, S)) + [halfcauchy(r) + 0.2]
+        return Case(name, "hier_normal", S + 3, prior, lo, hi, sp, dict(x=y))
+    raise KeyError(name)
+
+
+ALL_MODELS = ["gaussian", "mvnormal", "binomial", "lnr", "lba", "hier_normal"]
+
+
+def hier_blocks(S):
+    return np.array([[1, 1] + [0] * S + [1], [0, 0] + [1] * S + [0]], dtype=np.uint8)
+
+
+def compare_run(case, G, Np, n_iter, mode, seed=5, rng_seed=0, rtol=1e-12, **kw):
+    """Runs the oracle and the bound library on the same inputs and returns the comparison.
+    mode = "replay": the library consumes the oracle's tape (reference semantics);
+    mode = "native": both draw from Philox with the same seed (select_base on sweep-start weights)."""
+    rng = np.random.default_rng(rng_seed)
+    theta0 = case.theta0(rng, G * Np)
+    okw = dict(kw)
+    cfg = case.oracle_config(G, Np, seed=seed, base_snapshot=1 if mode == "native" else 0, **okw)
+    r = O.run(cfg, case.oracle_model(), theta0, n_iter)
+    h = case.handle(G, Np, seed=seed, trace=True, **kw)
+    try:
+        h.set_state(theta0)
+        if mode == "native":
+            h.run(n_iter)
+        else:
+            h.replay(r["tape"], n_iter)
+        out = dict(samples=h.samples(), accept=h.accept(), lp=h.lp(), trace=h.trace(), state=h.get_state(),
+                   mig=h.migration_slots(), counters=h.counters())
+    finally:
+        h.close()
+    return r, out
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1,|b|) over finite entries; non-finite entries must agree exactly."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    fin = np.isfinite(b)
+    same_nonfinite = np.array_equal(np.isnan(a[~fin]), np.isnan(b[~fin])) and np.array_equal(a[~fin][~np.isnan(a[~fin])], b[~fin][~np.isnan(b[~fin])])
+    if not same_nonfinite:
+        return np.inf
+    if not fin.any():
+        return 0.0
+    return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(1.0, np.abs(b[fin]))))

@@ -43,6 +43,10 @@ void *event_create() { return malloc(8); }
 void event_destroy(void *e) { free(e); }
 int event_record(void *) { return 0; }
 int event_wait(void *) { return 0; }
+void *tevent_create() { return malloc(8); }
+void tevent_destroy(void *e) { free(e); }
+int tevent_elapsed(void *, void *, double *ms) { *ms = 0.0; return 0; }
+int dfill(void *d, int v, size_t b) { if (b) memset(d, v, b); return 0; }
 int timer_start() { return 0; }
 int timer_stop(double *ms) { *ms = 0.0; return 0; }
 int64_t launch_count() { return g_launches; }

@@ -1,0 +1,261 @@
+"""GPU parity tests proper (-m gpu): the CUDA kernels, called through the C ABI, against the
+oracle on the same seeded inputs.
+
+(a) replay mode: the library consumes the oracle's recorded draws; accept decisions must be
+    IDENTICAL, proposals and log-densities within 1e-12 relative (fp64).
+(b) native mode: both sides draw from the same Philox map (select_base on sweep-start weights).
+Full BASELINE sizes are covered through size-independent properties (sufficient statistics in
+extended precision, additivity over observation slices)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import ALL_MODELS, D, O, compare_run, hier_blocks, make_case, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cuda")]
+RTOL = 1e-12   # north_star: proposals and log-densities within 1e-12 relative in fp64
+KA = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))
+
+
+def check(r, out, rtol=RTOL):
+    assert np.array_equal(out["trace"]["accepted"], r["trace"]["accepted"]), "accept decisions differ"
+    assert np.array_equal(out["accept"], r["accept"])
+    assert rel_err(out["trace"]["prop_theta"], r["trace"]["prop_theta"]) <= rtol
+    assert rel_err(out["trace"]["prop_weight"], r["trace"]["prop_weight"]) <= rtol
+    assert rel_err(out["trace"]["log_adj"], r["trace"]["log_adj"]) <= 1e-9
+    assert rel_err(out["samples"], r["samples"]) <= rtol
+    assert rel_err(out["lp"], r["lp"]) <= rtol
+    assert np.array_equal(out["state"][2], r["final_id"])
+    assert np.array_equal(out["mig"], r["tape"]["mig_slots"])
+
+
+# ---- the reference's own known-answer vectors, on the device -----------------------------------
+def test_device_projection():          # test/utility_tests.jl:71-93
+    c = KA["projection"]
+    assert np.allclose(D.op_project(c["p1"], c["p2"]), np.array(c["expected_num"]) / c["expected_den"], rtol=1e-15)
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=(2, 1003))
+    assert rel_err(D.op_project(a, b), O.project(a, b)) <= RTOL
+
+
+def test_device_reset():               # test/utility_tests.jl:42-69
+    for key in ("reset_vector", "reset_matrix"):
+        c = KA[key]
+        assert np.array_equal(D.op_reset(c["p1"], c["p2"], c["mask"]), np.array(c["expected"]))
+
+
+def test_device_particle_algebra():    # test/utility_tests.jl:161-199
+    for c in KA["algebra"]["cases"]:
+        assert np.allclose(D.op_de_proposal(c["pt"], c["pm"], c["pn"], None, c["g"], 0.0, c["b"]), c["expected"], rtol=1e-15)
+    rng = np.random.default_rng(1)
+    pt, pm, pn, pb, b = rng.normal(size=(5, 101))
+    assert np.array_equal(D.op_de_proposal(pt, pm, pn, pb, 0.77, 0.61, b), O.de_proposal(pt, pm, pn, pb, 0.77, 0.61, b))
+    assert np.array_equal(D.op_de_proposal(pt, pm, pn, None, 2.38, 0.0, b), O.de_proposal(pt, pm, pn, None, 2.38, 0.0, b))
+
+
+def test_device_snooker_and_accept():
+    rng = np.random.default_rng(2)
+    for d in (2, 6, 51, 1003):
+        pt, pz, pm, pn, b = rng.normal(size=(5, d))
+        out, adj = D.op_snooker(pt, pz, pm, pn, 1.7, b * 1e-3)
+        ref = O.snooker_proposal(pt, pz, pm, pn, 1.7, b * 1e-3)
+        assert rel_err(out, ref) <= RTOL
+        assert np.isclose(adj, O.adjust_loglike(pt, ref, pz), rtol=1e-10, atol=1e-10)
+    wp = np.array([-1.0, -3.0, -3.0, -np.inf, -np.inf, -np.inf, 1.0])
+    wc = np.array([-2.0, -2.0, -2.0, -2.0, -2.0, -np.inf, 2.0])
+    adj = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, np.nan])
+    u = np.array([0.999999, np.exp(-1.0) * (1 - 1e-12), np.exp(-1.0) * (1 + 1e-12), 1e-300, 0.0, 0.0, 0.0])
+    exp = [O.accept(*t) for t in zip(wp, wc, adj, u)]
+    assert list(D.op_accept(wp, wc, adj, u)) == exp == [True, True, False, False, True, False, False]
+
+
+def test_device_select_quirks():       # SURVEY hard part 4 (softmax under/overflow fallbacks)
+    w = np.array([-5000.0, -5100.0, -4900.0, -5050.0])
+    for u in np.linspace(0.01, 0.99, 25):
+        b, m = D.op_select(w, float(u))
+        assert b == O.select_base(w, float(u)) and m == O.select_particle(w, float(u))[0] == 1
+    rng = np.random.default_rng(3)
+    for n in (3, 24, 256, 4096):
+        w = rng.normal(-3, 2, n)
+        for u in rng.uniform(size=6):
+            b, m = D.op_select(w, float(u))
+            assert b == O.select_base(w, float(u)) and m == O.select_particle(w, float(u))[0]
+
+
+# ---- whole population steps --------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_population_step_all_models(mode, model):
+    case = make_case(model, np.random.default_rng(21))
+    r, out = compare_run(case, 3, 8, 30, mode, burnin=15, theta_snooker=0.15, alpha=0.3)
+    check(r, out)
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("kw", [dict(theta_snooker=0.3, kappa=0.8), dict(proposal="fixed_gamma"),
+                                dict(proposal="variable_gamma", theta_snooker=0.1), dict(beta=0.5, alpha=0.5)],
+                         ids=["snooker_kappa", "fixed_gamma", "variable_gamma", "mutation_migration"])
+def test_gaussian_variants(mode, kw):
+    case = make_case("gaussian", np.random.default_rng(22))
+    r, out = compare_run(case, 4, 6, 100, mode, burnin=50, **kw)
+    check(r, out)
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_blocking_hierarchical(mode):   # blocking_on, block masks, last-block-wins (main.jl:174-179)
+    case = make_case("hier_normal", np.random.default_rng(23))
+    r, out = compare_run(case, 2, 8, 30, mode, burnin=15, blocks=hier_blocks(9), theta_snooker=0.2, alpha=0.3)
+    check(r, out)
+
+
+def test_many_particles_per_group_levels():
+    """Np = 256: ~10 dependency levels per sweep must reproduce the sequential in-place sweep."""
+    rng = np.random.default_rng(24)
+    n, dm = 3000, 50
+    x = rng.normal(rng.normal(size=dm), 1.0, size=(n, dm))
+    case = common.Case("mvn50", "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-np.inf] * dm + [0],
+                       [np.inf] * (dm + 1), lambda r: list(r.normal(size=dm)) + [abs(r.standard_cauchy()) + 0.5], dict(x=x))
+    r, out = compare_run(case, 2, 256, 4, "replay", burnin=2, theta_snooker=0.1, alpha=0.5)
+    check(r, out)
+    assert out["counters"]["levels"] >= 4 * 5
+
+
+def test_ragged_and_tiny_inputs():
+    """Observation counts that do not fill a tile, one observation, one dimension."""
+    rng = np.random.default_rng(25)
+    for n, dm in ((1, 1), (63, 3), (65, 33), (130, 70)):
+        x = rng.normal(size=(n, dm))
+        case = common.Case("mvn", "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-np.inf] * dm + [0],
+                           [np.inf] * (dm + 1), lambda r, dm=dm: list(r.normal(size=dm)) + [abs(r.standard_cauchy()) + 0.5], dict(x=x))
+        r, out = compare_run(case, 2, 5, 6, "replay", burnin=3, theta_snooker=0.2)
+        check(r, out)
+    for n in (1, 255, 257, 1000):
+        case = make_case("gaussian", np.random.default_rng(n), n_obs=n)
+        r, out = compare_run(case, 2, 5, 6, "replay", burnin=3)
+        check(r, out)
+    # hierarchical with enough subjects for several dimension splits
+    S, n = 300, 7
+    y = rng.normal(1.0 + rng.normal(0, 1, S)[:, None], 0.5, size=(S, n))
+    prior = [("normal", 1, 1), ("halfcauchy", 0, 1)] + [("normal_ref", 0, 0, 1)] * S + [("halfcauchy", 0, 1)]
+
+    def sp(r):
+        return [r.normal(1, 1), 1.0] + list(r.normal(0, 1, S)) + [0.7]
+    case = common.Case("hier300", "hier_normal", S + 3, prior, [-np.inf, 0] + [-np.inf] * S + [0], [np.inf] * (S + 3), sp, dict(x=y))
+    r, out = compare_run(case, 2, 6, 5, "replay", burnin=2, blocks=hier_blocks(S), theta_snooker=0.1)
+    check(r, out)
+
+
+# ---- BASELINE full sizes through size-independent properties -----------------------------------
+def test_mvn_full_size_sufficient_statistics():
+    """Config 2 shape (d=50, 1e5 obs, 1024 particles): the per-observation kernel must agree with
+    the sufficient-statistics identity evaluated in extended precision, and be additive over
+    observation slices."""
+    rng = np.random.default_rng(50514)
+    n, dm, P = 100_000, 50, 1024
+    mu = rng.normal(size=dm)
+    x = rng.normal(mu, 1.0, size=(n, dm))
+    th = np.column_stack([rng.normal(mu, 0.05, size=(P, dm)), rng.uniform(0.8, 1.3, P)])
+    prior = [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)]
+    lo, hi = [-np.inf] * dm + [0], [np.inf] * (dm + 1)
+    with D.Handle(4, 256, dm + 1, lo, hi) as h:
+        h.set_model("mvnormal", prior, x=x)
+        ll, _ = h.eval(th)
+    xl = x.astype(np.longdouble)
+    sx, sxx = xl.sum(axis=0), (xl * xl).sum()
+    tl = th.astype(np.longdouble)
+    ssd = sxx - 2 * (tl[:, :dm] * sx).sum(axis=1) + n * (tl[:, :dm] ** 2).sum(axis=1)
+    ref = -0.5 * n * dm * np.log(2 * np.pi) - n * dm * np.log(tl[:, dm]) - 0.5 * ssd / tl[:, dm] ** 2
+    assert np.max(np.abs(ll - ref.astype(float)) / np.abs(ref.astype(float))) <= RTOL
+    # additivity over a split of the observations (sizes chosen to leave ragged tiles)
+    parts = []
+    for sl in (slice(0, 33_333), slice(33_333, n)):
+        with D.Handle(4, 256, dm + 1, lo, hi) as h:
+            h.set_model("mvnormal", prior, x=x[sl])
+            parts.append(h.eval(th)[0])
+    assert np.max(np.abs(parts[0] + parts[1] - ll) / np.abs(ll)) <= RTOL
+
+
+def test_lba_full_size_additivity():
+    """Config 3 shape (1e5 trials): additivity over trial slices and agreement with the oracle on
+    a bounded sample of particles."""
+    rng = np.random.default_rng(88484)
+    choice, rt = common.lba_sim(rng, 100_000)
+    mn = rt.min()
+    prior = [("normal", 1, 5), ("normal", 1, 5), ("normal", 0.8, 0.2), ("normal", 0.2, 0.1), ("uniform", 0, mn)]
+    lo, hi = [0] * 5, [np.inf] * 4 + [mn]
+    th = np.column_stack([rng.uniform(2, 4, 64), rng.uniform(1, 3, 64), rng.uniform(0.5, 1.0, 64), rng.uniform(0.1, 0.4, 64), rng.uniform(0, mn, 64)])
+    with D.Handle(4, 16, 5, lo, hi) as h:
+        h.set_model("lba", prior, x=rt, choice=choice, n_dim=2)
+        ll, _ = h.eval(th)
+    m = O.Model("lba", 5, prior, x=rt, choice=choice, n_dim=2)
+    ref = np.array([O.loglike(m, t) for t in th[:8]])
+    assert np.max(np.abs(ll[:8] - ref) / np.abs(ref)) <= RTOL
+    parts = []
+    for sl in (slice(0, 41_111), slice(41_111, 100_000)):
+        with D.Handle(4, 16, 5, lo, hi) as h:
+            h.set_model("lba", prior, x=rt[sl], choice=choice[sl], n_dim=2)
+            parts.append(h.eval(th)[0])
+    assert np.max(np.abs(parts[0] + parts[1] - ll) / np.abs(ll)) <= RTOL
+
+
+def test_hier_full_size_against_oracle():
+    """Config 4 shape (1000 subjects x 50 obs, d = 1003)."""
+    rng = np.random.default_rng(9528)
+    S, n = 1000, 50
+    y = rng.normal(1.0 + rng.normal(0, 1, S)[:, None], 0.5, size=(S, n))
+    prior = [("normal", 1, 1), ("halfcauchy", 0, 1)] + [("normal_ref", 0, 0, 1)] * S + [("halfcauchy", 0, 1)]
+    lo, hi = [-np.inf, 0] + [-np.inf] * S + [0], [np.inf] * (S + 3)
+    th = np.column_stack([rng.normal(1, 0.1, 40), rng.uniform(0.8, 1.2, 40), rng.normal(0, 1, (40, S)), rng.uniform(0.4, 0.7, 40)])
+    with D.Handle(2, 20, S + 3, lo, hi) as h:
+        h.set_model("hier_normal", prior, x=y)
+        ll, pr = h.eval(th)
+    m = O.Model("hier_normal", S + 3, prior, x=y)
+    ref = np.array([O.loglike(m, t) for t in th])
+    pref = np.array([O.prior_loglike(m, t) for t in th])
+    assert np.max(np.abs(ll - ref) / np.abs(ref)) <= RTOL
+    assert np.max(np.abs(pr - pref) / np.abs(pref)) <= RTOL
+
+
+# ---- (b) native RNG: posterior statistics -------------------------------------------------------
+def test_native_binomial_posterior():
+    """test/binomial_tests.jl restated: posterior is Beta(k+1, N-k+1)."""
+    from scipy import stats
+    rng = np.random.default_rng(29542)
+    model = D.DEModel(sample_prior=lambda: [rng.uniform()], prior_loglike=D.GPUPrior(D.Beta(1, 1)),
+                      loglike=D.GPULoglike("binomial", N=10, k=4), names=("θ",))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((0, 1),), burnin=1500, Np=3, seed=7)
+    chains = D.sample(model, de, 3000)
+    sol = stats.beta(5, 7)
+    assert np.isclose(chains.mean()[0], sol.mean(), rtol=0.03)
+    assert np.isclose(chains.std()[0], sol.std(), rtol=0.05)
+    x = chains.value[::5, 0, :].ravel()
+    assert stats.kstest(x, sol.cdf).statistic < 0.03
+
+
+def test_native_mvn_posterior_matches_oracle_chains():
+    """Means, variances and KS statistics of the GPU chains against the oracle's chains (native RNG,
+    different seeds) and against the analytic posterior sd = sigma/sqrt(n)."""
+    from scipy import stats
+    rng = np.random.default_rng(505514)
+    n, dm, G, Np, n_iter, burn = 100, 8, 4, 16, 3000, 1000
+    x = rng.normal(0.0, 1.0, size=(n, dm))
+    case = common.Case("mvn", "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-np.inf] * dm + [0],
+                       [np.inf] * (dm + 1), lambda r: list(r.normal(size=dm)) + [abs(r.standard_cauchy()) + 0.5], dict(x=x))
+    theta0 = case.theta0(rng, G * Np)
+    kw = dict(burnin=burn, theta_snooker=0.1)
+    ref = O.run(case.oracle_config(G, Np, seed=11, **kw), case.oracle_model(), theta0, n_iter, record=False, trace=False)
+    with case.handle(G, Np, seed=12, **kw) as h:
+        h.set_state(theta0)
+        h.run(n_iter)
+        s = h.samples()
+    a, b = s[:, :, burn:], ref["samples"][:, :, burn:]
+    assert np.allclose(a.mean(axis=(0, 2)), b.mean(axis=(0, 2)), atol=0.02)
+    assert np.allclose(a.std(axis=(0, 2)), b.std(axis=(0, 2)), rtol=0.08)
+    assert np.allclose(a[:, :dm].std(axis=(0, 2)), 0.1, atol=0.02)
+    assert np.corrcoef(a[:, :dm].mean(axis=(0, 2)), x.mean(axis=0))[0, 1] > 0.98
+    for k in range(dm + 1):
+        ks = stats.ks_2samp(a[:, k, ::20].ravel(), b[:, k, ::20].ravel()).statistic
+        assert ks < 0.06, (k, ks)

@@ -1,0 +1,194 @@
+"""Host logic of the library (planner levels, row bookkeeping, tape sharding, migration cycle, ABI
+error paths, the Python mirror of DE/DEModel/sample) exercised on CPU through the host-only test
+double of the device backend (tests/emu), and checked against the oracle.  The CUDA kernels
+themselves are checked by the -m gpu tests."""
+import numpy as np
+import pytest
+
+import common
+from common import ALL_MODELS, D, O, compare_run, hier_blocks, make_case, rel_err
+
+pytestmark = pytest.mark.usefixtures("emu")
+
+VARIANTS = {
+    "default": dict(),
+    "snooker_kappa": dict(theta_snooker=0.3, kappa=0.8),
+    "fixed_gamma": dict(proposal="fixed_gamma"),
+    "variable_gamma": dict(proposal="variable_gamma", theta_snooker=0.1),
+    "more_mutation": dict(beta=0.5, alpha=0.4),
+}
+
+
+def check(r, out, rtol=1e-12):
+    assert np.array_equal(out["accept"], r["accept"])
+    assert np.array_equal(out["trace"]["accepted"], r["trace"]["accepted"])
+    assert rel_err(out["trace"]["prop_theta"], r["trace"]["prop_theta"]) <= rtol
+    assert rel_err(out["trace"]["prop_weight"], r["trace"]["prop_weight"]) <= rtol
+    assert rel_err(out["trace"]["log_adj"], r["trace"]["log_adj"]) <= 1e-9
+    assert rel_err(out["samples"], r["samples"]) <= rtol
+    assert rel_err(out["lp"], r["lp"]) <= rtol
+    assert np.array_equal(out["state"][2], r["final_id"])
+    assert rel_err(out["state"][0], r["final_theta"]) <= rtol
+    assert np.array_equal(out["mig"], r["tape"]["mig_slots"])
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_gaussian_variants(mode, variant):
+    case = make_case("gaussian", np.random.default_rng(11))
+    r, out = compare_run(case, 4, 6, 120, mode, burnin=60, **VARIANTS[variant])
+    check(r, out)
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_all_models(mode, model):
+    case = make_case(model, np.random.default_rng(12))
+    r, out = compare_run(case, 3, 5, 40, mode, burnin=20, theta_snooker=0.15, alpha=0.3)
+    check(r, out)
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_blocking(mode):
+    case = make_case("hier_normal", np.random.default_rng(13))
+    r, out = compare_run(case, 2, 8, 40, mode, burnin=20, blocks=hier_blocks(9), theta_snooker=0.2, alpha=0.3)
+    check(r, out)
+    # a mutation sweep ignores the block mask (main.jl:205): some mutation proposal moves a masked element
+    kind = r["tape"]["kind"]
+    assert (kind == O.KIND_MUTATION).any()
+
+
+def test_levels_reproduce_sequential_sweep():
+    """The level schedule must give the in-place sweep's result for many particles per group."""
+    case = make_case("gaussian", np.random.default_rng(14))
+    r, out = compare_run(case, 2, 64, 12, "replay", burnin=6, theta_snooker=0.2)
+    check(r, out)
+    assert out["counters"]["levels"] > 12 * 3      # several levels per sweep
+
+
+def test_sharded_handles_match_single(emu):
+    """Two handles holding half of the groups each, with alpha = 0 (no exchange), reproduce the
+    single-handle run: the draw map is keyed by global positions."""
+    case = make_case("gaussian", np.random.default_rng(15))
+    G, Np, n = 4, 6, 30
+    theta0 = case.theta0(np.random.default_rng(1), G * Np)
+    full = case.handle(G, Np, seed=3, burnin=10, alpha=0.0)
+    full.set_state(theta0); full.run(n)
+    ref = full.history_by_slot()
+    full.close()
+    for half in range(2):
+        h = case.handle(G, Np, seed=3, burnin=10, alpha=0.0, group_begin=2 * half, group_count=2)
+        h.set_state(theta0[half * 12:(half + 1) * 12]); h.run(n)
+        th, w, ids, acc = h.history_by_slot()
+        h.close()
+        assert np.array_equal(th, ref[0][:, half * 12:(half + 1) * 12])
+        assert np.array_equal(acc, ref[3][:, half * 12:(half + 1) * 12])
+        assert np.array_equal(ids, ref[2][:, half * 12:(half + 1) * 12])
+
+
+def test_teacher_forced_stepping():
+    """replay one iteration at a time with set_state in between (how long GPU runs are checked)."""
+    case = make_case("lnr", np.random.default_rng(16))
+    G, Np, n = 3, 5, 10
+    theta0 = case.theta0(np.random.default_rng(2), G * Np)
+    cfg = case.oracle_config(G, Np, seed=9, burnin=5, theta_snooker=0.2)
+    r = O.run(cfg, case.oracle_model(), theta0, n)
+    h = case.handle(G, Np, seed=9, burnin=5, theta_snooker=0.2, trace=True)
+    h.set_state(theta0)
+    tape = r["tape"]
+    for it in range(n):
+        one = {k: (v[it:it + 1] if v is not None else None) for k, v in tape.items()}
+        if it > 0:
+            h.set_state(r["trace"]["state_theta"][it - 1], r["trace"]["state_id"][it - 1])
+        h.replay(one, 1)
+        th, w, ids = h.get_state()
+        assert np.array_equal(ids, r["trace"]["state_id"][it])
+        assert rel_err(th, r["trace"]["state_theta"][it]) <= 1e-12
+        assert rel_err(w, r["trace"]["state_weight"][it]) <= 1e-12
+    h.close()
+
+
+def test_abi_error_paths():
+    case = make_case("gaussian", np.random.default_rng(17))
+    with pytest.raises(D._ffi.DemcmcError, match="Np must be >= 3"):
+        D.Handle(2, 2, 2, case.lo, case.hi)
+    with pytest.raises(D._ffi.DemcmcError, match="resample"):
+        D.Handle(2, 4, 2, case.lo, case.hi, n_initial=12)
+    h = D.Handle(2, 4, 2, case.lo, case.hi)
+    with pytest.raises(D._ffi.DemcmcError, match="set_model"):
+        h.set_state(np.zeros((8, 2)))
+    with pytest.raises(D._ffi.DemcmcError, match="expects d"):
+        h.set_model("mvnormal", case.prior, x=np.zeros((5, 4)))
+    with pytest.raises(D._ffi.DemcmcError, match="no registered kernel"):
+        h.set_model(17, case.prior, x=np.zeros(5))
+    h.set_model("gaussian", case.prior, x=case.data["x"])
+    with pytest.raises(D._ffi.DemcmcError, match="set_state"):
+        h.run(1)
+    h.close()
+
+
+def test_eval_matches_oracle():
+    for model in ALL_MODELS:
+        case = make_case(model, np.random.default_rng(18))
+        th = case.theta0(np.random.default_rng(3), 9)
+        th[0, -1] = -1.0                     # out of bounds for every model's last parameter
+        h = case.handle(3, 3)
+        ll, pr = h.eval(th)
+        h.close()
+        m, cfg = case.oracle_model(), case.oracle_config(3, 3)
+        for i in range(9):
+            post = O.posterior(cfg, m, th[i])
+            if np.isfinite(post):
+                assert np.isclose(ll[i], O.loglike(m, th[i]), rtol=1e-12)
+                assert np.isclose(pr[i], O.prior_loglike(m, th[i]), rtol=1e-12)
+        assert pr[0] == -np.inf
+
+
+# ---- the Python mirror of the reference's API --------------------------------------------------
+def test_sample_api_gaussian_posterior():
+    """test/gaussian_tests.jl restated: Normal(mu,sigma), 50 obs, DE(burnin=1500, Np=6), 3000 it;
+    the NUTS comparison is replaced by 2-D quadrature of the same posterior."""
+    rng = np.random.default_rng(973536)
+    data = rng.normal(0.0, 1.0, 50)
+    model = D.DEModel(sample_prior=lambda: [rng.normal(0, 10), abs(rng.standard_cauchy())],
+                      prior_loglike=D.GPUPrior(D.Normal(0, 10), D.HalfCauchy(0, 1)),
+                      loglike=D.GPULoglike("gaussian", data), names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), burnin=1500, Np=6, seed=1)
+    chains = D.sample(model, de, 3000)
+    assert len(chains) == 1500 and chains.names == ["μ", "σ", "acceptance", "lp"]
+    mu = np.linspace(-1.5, 1.5, 401); sg = np.linspace(0.5, 2.2, 401)
+    M, S = np.meshgrid(mu, sg, indexing="ij")
+    from scipy import stats
+    lp = -50 * np.log(S) - ((data[None, None, :] - M[..., None]) ** 2).sum(-1) / (2 * S ** 2) + stats.norm(0, 10).logpdf(M) + stats.halfcauchy.logpdf(S)
+    w = np.exp(lp - lp.max()); w /= w.sum()
+    mean = np.array([(w * M).sum(), (w * S).sum()])
+    sd = np.sqrt(np.array([(w * M ** 2).sum(), (w * S ** 2).sum()]) - mean ** 2)
+    assert np.allclose(chains.mean(), mean, atol=0.02)
+    assert np.allclose(chains.std(), sd, atol=0.02)
+    assert np.all(np.abs(chains.rhat() - 1.0) < 0.05)
+    # discard_burnin = false keeps every iteration (test/utility_tests.jl:32-39)
+    de2 = D.DE(sample_prior=model.sample_prior, bounds=de.bounds, burnin=100, Np=4, discard_burnin=False, seed=2)
+    assert len(D.sample(model, de2, D.MCMCThreads(), 250)) == 250
+
+
+def test_closure_raises_instead_of_cpu_fallback():
+    model = D.DEModel(sample_prior=lambda: [0.0, 1.0], prior_loglike=D.GPUPrior(D.Normal(), D.HalfCauchy()),
+                      loglike=lambda data, mu, sigma: 0.0, names=("μ", "σ"), data=np.zeros(3))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-1, 1), (0, 1)), Np=4)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        D.sample(model, de, 10)
+    model2 = D.DEModel(sample_prior=lambda: [0.0, 1.0], prior_loglike=lambda mu, sigma: 0.0,
+                       loglike=D.GPULoglike("gaussian", np.zeros(3)), names=("μ", "σ"))
+    with pytest.raises(TypeError, match="GPUPrior"):
+        D.sample(model2, de, 10)
+    with pytest.raises(NotImplementedError):
+        D.DE(sample_prior=model.sample_prior, bounds=((-1, 1),), Np=4, sample="resample")
+
+
+def test_names_blocks_and_bounds_flattening():
+    from demcmc_b200.api import _expand_block, _flat_names, _flatten
+    theta = [np.array([[1.0, 2.0], [3.0, 4.0]]), 5.0, np.array([6.0, 7.0])]
+    assert _flatten(theta) == [1.0, 3.0, 2.0, 4.0, 5.0, 6.0, 7.0]               # column-major (main.jl:236-238)
+    shapes = [np.shape(v) for v in theta]
+    assert _flat_names(("A", "s", "v"), shapes) == ["A[1,1]", "A[2,1]", "A[1,2]", "A[2,2]", "s", "v[1]", "v[2]"]
+    assert _expand_block([[[True, False], [False, True]], False, True], shapes) == [True, False, False, True, False, True, True]
