@@ -156,6 +156,43 @@ def compare_run(case, G, Np, n_iter, mode, seed=5, rng_seed=0, rtol=1e-12, **kw)
     return r, out
 
 
+def forced_run(case, G, Np, n_iter, mode, seed=5, rng_seed=0, **kw):
+    """Teacher-forced comparison (SURVEY.md 7.3 hard part 2): the oracle runs the whole chain; the
+    library runs ONE iteration at a time, each started from the oracle's state after the previous
+    iteration, so rounding differences (different libm, different reduction order) cannot be
+    amplified by the population dynamics (theta' = theta_t + gamma (theta_m - theta_n) has a
+    positive Lyapunov exponent).  Returns the same structure as compare_run."""
+    rng = np.random.default_rng(rng_seed)
+    theta0 = case.theta0(rng, G * Np)
+    cfg = case.oracle_config(G, Np, seed=seed, base_snapshot=1 if mode == "native" else 0, **kw)
+    r = O.run(cfg, case.oracle_model(), theta0, n_iter)
+    h = case.handle(G, Np, seed=seed, trace=True, **kw)
+    traces, migs = [], []
+    try:
+        for it in range(n_iter):
+            if it == 0:
+                h.set_state(theta0)
+            else:
+                h.set_state(r["trace"]["state_theta"][it - 1], r["trace"]["state_id"][it - 1])
+            if mode == "native":
+                h.run(1)
+            else:
+                B = h.B
+                one = {}
+                for k, v in r["tape"].items():
+                    if v is None:
+                        continue
+                    one[k] = v[it:it + 1] if k.startswith("mig_") else v[it * B:(it + 1) * B]
+                h.replay(one, 1)
+            traces.append(h.trace())
+            migs.append(h.migration_slots())
+        out = dict(samples=h.samples(), accept=h.accept(), lp=h.lp(), state=h.get_state(), counters=h.counters(),
+                   trace={k: np.concatenate([t[k] for t in traces]) for k in traces[0]}, mig=np.concatenate(migs))
+    finally:
+        h.close()
+    return r, out
+
+
 def rel_err(a, b):
     """max |a-b| / max(1,|b|) over finite entries; non-finite entries must agree exactly."""
     a, b = np.asarray(a, float), np.asarray(b, float)
