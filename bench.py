@@ -221,16 +221,15 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (k_ssd, the likelihood) ----------------------------------
     peaks = measured_peaks()
     fp64_peak = D.fp64_peak(local)                                   # DFMA microbenchmark, TFLOP/s (not in MEASURED_PEAKS.json)
-    flops = 3.0 * N_OBS * N_DIM * (updates / world)                  # direct form: DADD + DFMA per (obs, dim, particle)
+    flops = 2.0 * N_OBS * N_DIM * (updates / world)                  # contraction form: one DFMA per (obs, dim, particle)
     achieved = flops / (ms_ll * 1e-3) / 1e12 if ms_ll > 0 else None
-    roofline = {"bound": "fp64", "kernel": "k_ssd<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "k_xdot<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
-                "pipe_frac": (achieved / fp64_peak) * 4.0 / 3.0 if achieved else None,
                 "traffic": None,
                 "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
                 "avg_launch_ms": ms_ll / max(1, ll_launches), "share_of_step": ms_ll / ms if ms > 0 else None,
                 "peak_source": "measured in this run: DFMA loop, 16 independent chains x 256 threads x 8 CTAs/SM (MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s)",
-                "note": "the kernel issues 2 fp64 instructions (DADD+DFMA) per 3 algorithmic flops, so frac <= 0.75; pipe_frac = issue-slot utilisation of the fp64 pipe",
+                "note": "bound = fp64 pipe (not hbm/tensor): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one DFMA per observation x dimension x particle, contraction form of the sum of squares)",
                 "hbm_gbs_measured": peaks.get("hbm_gbs")}
 
     # ---- end to end through the public API with HOST buffers -------------------------------------
@@ -287,7 +286,7 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])",
                            "groups_total": G, "particles_total": G * NP, "parallelism": f"groups sharded over {world} GPU(s); NCCL send/recv migration",
-                           "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten between timed steps, per-step CUDA events, flush excluded",
+                           "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten before every chunk of overlapped steps (a chunk ends at each migration, at most 16 steps; steps inside a chunk share launches so there is no per-step boundary), per-chunk CUDA events, flush excluded",
                            "timing": "CUDA events on the library's launching stream (demcmc_counters.device_ms), max over ranks"},
                 "value_steady_no_flush": updates / (ms_steady * 1e-3) if world == 1 else None,
                 "gpu_launches": int(launches), "clocks": ck, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,

@@ -48,9 +48,9 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
 // select_base preparation on the sweep-start weights: cw[P] running sums, tot[G]; th[P] is scratch
 int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
 // propose -> loglik -> accept for one level of one sweep
-int launch_propose(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv);
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part);
-int launch_accept(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv);
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
 // [position][d+3] = {theta..., weight, id, accept flag}
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);

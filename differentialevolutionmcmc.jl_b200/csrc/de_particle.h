@@ -20,21 +20,40 @@ struct SerialLanes {
     DE_HD void sync() const {}
 };
 
-// log-likelihood from the reduced kernel output `total` (sum of per-observation log densities for
-// the pointwise kernels; sum of squared differences for MVN / hierarchical normal)
-DE_HD double finalize_ll(const ModelDev &m, const double *theta, double total)
+// mean of dimension k of the MVN / hierarchical likelihood, relative to the data centre
+DE_HD double centred_mean(const ModelDev &m, const double *theta, int k)
+{
+    return (m.kind == M_HIER ? theta[0] + theta[2 + k] : theta[k]) - m.center[k];
+}
+
+// sum_k mean'_k^2 (the particle-only term of the expanded sum of squares)
+template <class C>
+DE_HD double mean_sq(const C &co, const ModelDev &m, const double *theta)
+{
+    if (m.kind != M_MVNORMAL && m.kind != M_HIER) return 0.0;
+    double s = 0.0;
+    for (int k = co.lane(); k < m.ssd_k; k += co.width()) { const double v = centred_mean(m, theta, k); s += v * v; }
+    return co.sum(s);
+}
+
+// log-likelihood from the reduced kernel output `total`: the sum of per-observation log densities
+// for the pointwise kernels; for MVN / hierarchical normal the cross term B = sum_i sum_k x'_ik m'_k
+// of the expanded sum of squares  SSD = sum x'^2 - 2 B + n sum_k m'_k^2  (x', m' centred)
+DE_HD double finalize_ll(const ModelDev &m, const double *theta, double total, double msq)
 {
     switch (m.kind) {
     case M_MVNORMAL: {
         // Multivariate_Guassian_Example.jl:31-33: per column -(d*log2pi + d*log(s^2))/2 - sqmahal/2
+        const double ssd = (m.ssd_xx - 2.0 * total) + (double)m.ssd_n * msq;
         const double sig = theta[m.n_dim], s2 = sig * sig, dm = (double)m.n_dim;
         const double c0 = -(dm * DE_LOG2PI + dm * log(s2)) / 2.0;
-        return (double)m.n_obs * c0 - (total / s2) / 2.0;
+        return (double)m.n_obs * c0 - (ssd / s2) / 2.0;
     }
     case M_HIER: {
         // Hierarchical_Example.jl:36-44: sum_s sum_j logpdf(Normal(0,sigma), y_sj - (mu + b_s))
+        const double ssd = (m.ssd_xx - 2.0 * total) + (double)m.ssd_n * msq;
         const double sig = theta[m.n_dim + 2];
-        return -(double)m.n_obs * (DE_LOG2PI / 2.0 + log(sig)) - (total / (sig * sig)) / 2.0;
+        return -(double)m.n_obs * (DE_LOG2PI / 2.0 + log(sig)) - (ssd / (sig * sig)) / 2.0;
     }
     case M_BINOMIAL: return binomial_ll(m.binom_N, m.binom_k, theta[0]);
     default: return total;
@@ -179,7 +198,7 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     if (m.kind != M_BINOMIAL)
         for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
     const double total = co.sum(part);
-    const double ll = finalize_ll(m, prop, total);
+    const double ll = finalize_ll(m, prop, total, mean_sq(co, m, prop));
     const bool inb = ctx.prop_inb[p] != 0;
     const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();
     const double adj = ctx.prop_adj[p];

@@ -6,9 +6,11 @@
 namespace de {
 
 constexpr int MAX_ACC = 8;        // accumulators of LNR / LBA held in registers
-constexpr int SSD_TP = 64;        // particles per tile of the sum-of-squared-differences kernel
+constexpr int SSD_TP = 64;        // particles per tile of the MVN / hierarchical likelihood kernel
 constexpr int SSD_TN = 64;        // observations per tile
-constexpr int SSD_KC = 32;        // dimensions per shared-memory chunk
+constexpr int SSD_KC = 32;        // dimensions per shared-memory stage
+constexpr int SSD_KS = 64;        // max dimensions per dimension-split (mean tile resident in smem)
+constexpr int SSD_SLICES = 592;   // target number of observation slices (4 per SM)
 constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
 constexpr int PW_THREADS = 256;
 
@@ -21,16 +23,21 @@ struct ModelDev {
     int32_t n_dim, n_per;
     const double *x;          // pointwise kernels: x[n_obs] / rt[n_obs]
     const int32_t *choice;    // LNR/LBA winners (1-based)
-    const double *xT;         // SSD kernels: xT[ssd_k][ssd_ld], observations contiguous, zero padded
+    const double *xT;         // MVN/hier kernel: CENTRED data xT[ssd_k][ssd_ld] = x - center[k],
+                              // observations contiguous, zero padded
+    const double *center;     // [ssd_k] column means removed from the data
+    double ssd_xx;            // sum of the squared centred data
     int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension
     int32_t ssd_k;            // dimensions (MVN: n_dim; hierarchical: subjects)
+    int32_t ssd_tps;          // observation tiles per slice
     int32_t has_sigma;
     double sigma_acc[MAX_ACC];
     double lba_floor;
     double binom_N, binom_k;
     const Prior *prior;       // [d]
-    // partition of the likelihood sum: split s covers observations [s*split_len, ...) x dimension
-    // chunk; fixed by the model alone so the summation order never depends on the GPU count
+    // partition of the likelihood sum: slice s covers observations [s*split_len, ...) x dimension
+    // split; fixed by the model alone so the summation order never depends on the GPU count or on
+    // how many slices one CTA happens to process
     int32_t n_osplit, n_ksplit, split_len, ksplit_len;
 };
 
@@ -71,7 +78,12 @@ struct SweepCtx {
     double *tr_theta, *tr_w, *tr_adj; uint8_t *tr_acc;
 };
 
-struct Level { const int32_t *order; int32_t n; };   // local positions updated in this level
+// One launch: the (sweep slot, local position) updates of one dependency level.  Entry encoding:
+// (slot << 24) | position; ctxs[slot] is the sweep the update belongs to (nullptr for plain lists
+// of positions, e.g. demcmc_eval).
+struct Level { const int32_t *order; int32_t n; const SweepCtx *ctxs; };
+constexpr int LV_SLOT_SHIFT = 24;
+constexpr uint32_t LV_POS_MASK = (1u << LV_SLOT_SHIFT) - 1;
 
 constexpr int MAX_MIG = 128;      // groups in one migration cycle (kernel-parameter block)
 struct MigArgs {

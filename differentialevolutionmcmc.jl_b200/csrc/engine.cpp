@@ -35,8 +35,9 @@ namespace {
 struct Row { double *theta; double *w; int32_t *id; uint8_t *acc; };
 
 struct Upload {            // pinned staging + device copy of one sweep's schedule
-    int32_t *h_order = nullptr, *d_order = nullptr;
-    uint8_t *h_mut = nullptr, *d_mut = nullptr;
+    int32_t *h_order = nullptr, *d_order = nullptr;   // [MAX_CHUNK][P] level-sorted entries
+    uint8_t *h_mut = nullptr, *d_mut = nullptr;       // [MAX_CHUNK][G]
+    SweepCtx *h_ctx = nullptr, *d_ctx = nullptr;      // [MAX_CHUNK]
     void *copied = nullptr;  // event: the H2D copies out of the pinned buffers have run
     bool armed = false;
 };
@@ -69,7 +70,8 @@ struct demcmc_handle {
     double *d_lo = nullptr, *d_hi = nullptr;
     uint8_t *d_blocks = nullptr;
     // schedule ring
-    static constexpr int RING = 8;
+    static constexpr int RING = 4;
+    int max_chunk = MAX_CHUNK;                          // sweeps overlapped on the device (1 = a barrier per sweep)
     Upload ring[RING];
     int64_t ring_use = 0;
     // migration
@@ -207,12 +209,14 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
               h->prop_prior && h->prop_adj && h->prop_inb && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
     for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
         Upload &u = h->ring[i];
-        u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P);
-        u.h_mut = (uint8_t *)be::hmalloc_pinned(std::max<size_t>(16, h->G_local));
-        u.d_order = (int32_t *)be::dmalloc(sizeof(int32_t) * P);
-        u.d_mut = (uint8_t *)be::dmalloc(std::max<size_t>(16, h->G_local));
+        u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P * MAX_CHUNK);
+        u.h_mut = (uint8_t *)be::hmalloc_pinned(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
+        u.h_ctx = (SweepCtx *)be::hmalloc_pinned(sizeof(SweepCtx) * MAX_CHUNK);
+        u.d_order = (int32_t *)be::dmalloc(sizeof(int32_t) * P * MAX_CHUNK);
+        u.d_mut = (uint8_t *)be::dmalloc(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
+        u.d_ctx = (SweepCtx *)be::dmalloc(sizeof(SweepCtx) * MAX_CHUNK);
         u.copied = be::event_create();
-        ok = u.h_order && u.h_mut && u.d_order && u.d_mut && u.copied;
+        ok = u.h_order && u.h_mut && u.h_ctx && u.d_order && u.d_mut && u.d_ctx && u.copied;
     }
     if (!ok) { demcmc_destroy(h); return fail(DEMCMC_ENOMEM, "device allocation failed: %s", be::last_error()); }
     if (be::h2d(h->d_lo, h->lo.data(), sizeof(double) * d) || be::h2d(h->d_hi, h->hi.data(), sizeof(double) * d) ||
@@ -240,7 +244,7 @@ int demcmc_destroy(demcmc_handle *h)
                      h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
-    for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::dfree(u.d_order); be::dfree(u.d_mut); be::event_destroy(u.copied); }
+    for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::hfree_pinned(u.h_ctx); be::dfree(u.d_order); be::dfree(u.d_mut); be::dfree(u.d_ctx); be::event_destroy(u.copied); }
     delete h;
     return 0;
 }
@@ -302,16 +306,19 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         D.ssd_ld = (D.ssd_n + SSD_TN - 1) / SSD_TN * SSD_TN;
         if (D.ssd_ld == 0) D.ssd_ld = SSD_TN;
         double *xT = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k * D.ssd_ld);
-        if (!xT) return fail(DEMCMC_ENOMEM, "data do not fit on the device");
+        double *center = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k);
+        if (!xT || !center) return fail(DEMCMC_ENOMEM, "data do not fit on the device");
         h->model_allocs.push_back(xT);
+        h->model_allocs.push_back(center);
         D.xT = xT;
-        BE(be::launch_pack_ssd(m->x, dev, &D));
-        // observation splits: ~one per SM, whole tiles; dimension splits: chunks of <= 256 dims
+        D.center = center;
+        BE(be::launch_pack_ssd(m->x, dev, &D));       // centres the data, fills D.ssd_xx
+        // observation slices: ~4 per SM, whole 64-observation tiles; dimension splits of <= SSD_KS dims
         const int64_t tiles = D.ssd_ld / SSD_TN;
-        const int64_t tiles_per_split = std::max<int64_t>(1, (tiles + 147) / 148);
-        D.split_len = (int32_t)(tiles_per_split * SSD_TN);
-        D.n_osplit = (int32_t)((D.ssd_ld + D.split_len - 1) / D.split_len);
-        D.ksplit_len = D.ssd_k <= 256 ? D.ssd_k : 128;
+        D.ssd_tps = (int32_t)std::max<int64_t>(1, (tiles + SSD_SLICES - 1) / SSD_SLICES);
+        D.split_len = D.ssd_tps * SSD_TN;
+        D.n_osplit = (int32_t)((tiles + D.ssd_tps - 1) / D.ssd_tps);
+        D.ksplit_len = std::min<int32_t>(D.ssd_k, SSD_KS);
         D.n_ksplit = (D.ssd_k + D.ksplit_len - 1) / D.ksplit_len;
     } else {
         D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
@@ -428,99 +435,58 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 
     const int64_t launches0 = be::launch_count();
     int64_t n_levels = 0;
-    // timing events: [2*it, 2*it+1] bracket iteration `it` when the L2 flush is on; the likelihood
-    // launches get their own pairs after those
-    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter : 0), tev_ll0 = tev_need, tev_ll = 0;
+    // timing events: one pair per chunk when the L2 flush is on; the likelihood launches get their
+    // own pairs after those
+    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter * B : 0), tev_ll0 = tev_need, tev_ll = 0, tev_chunks = 0;
     if (h->time_loglik) tev_need += 2 * (size_t)S * 64;
     while (h->tev.size() < tev_need) { void *e = be::tevent_create(); if (!e) { cleanup(); return fail(DEMCMC_ECUDA, "event pool: %s", be::last_error()); } h->tev.push_back(e); }
     BE(be::timer_start());
-    SweepPlan plan;
+    ChunkPlan plan;
     MigSchedule ms;
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t itg = h->iters_done + it;            // 0-based iteration of the whole chain
-        const int64_t de_iter = itg + 1 + cfg.n_initial;   // de.iter (main.jl:34)
-        const bool in_burnin = de_iter <= cfg.burnin;
+
+    auto get_mig = [&](int64_t it, MigSchedule &out) {
+        out.migrate = false; out.n = 0; out.groups.clear(); out.u_pick.clear();
+        if (Gt < 2) return;
+        if (tape) {
+            out.n = tape->mig_n[it]; out.migrate = out.n > 0;
+            for (int i = 0; i < out.n; ++i) { out.groups.push_back(tape->mig_groups[it * Gt + i]); out.u_pick.push_back(tape->mig_pick_u[it * Gt + i]); }
+        } else {
+            plan_migration(cfg.seed, (uint32_t)(h->iters_done + it), Gt, cfg.alpha, out);
+        }
+    };
+    auto in_burnin_at = [&](int64_t it) { return h->iters_done + it + 1 + cfg.n_initial <= cfg.burnin; };   // de.iter <= burnin
+    // native select_base reads the sweep-start weights: such a sweep starts from a complete state
+    auto needs_snapshot = [&](int64_t it) { return !tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin_at(it); };
+
+    // runs `n_sw` consecutive sweeps starting at local iteration it0 (block b) as one chunk
+    auto run_chunk = [&](int64_t it0, int b, int n_sw) -> int {
+        const int64_t itg0 = h->iters_done + it0;
+        Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
+        if (u.armed) BE(be::event_wait(u.copied));             // the pinned slot is free once its copies ran
+        h->ring_use++;
+        if (h->flush_bytes) {                                   // evict L2 before the timed chunk
+            BE(be::dfill(h->flush_buf, (int)(tev_chunks & 1), (size_t)h->flush_bytes));
+            BE(be::event_record(h->tev[2 * tev_chunks]));
+        }
+        bool basedep[MAX_CHUNK];
         Row cur = cur_row(h);
-        if (h->flush_bytes) {                               // evict L2 between timed iterations
-            BE(be::dfill(h->flush_buf, (int)(it & 1), (size_t)h->flush_bytes));
-            BE(be::event_record(h->tev[2 * it]));
-        }
-
-        // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
-        if (Gt > 1) {
-            if (tape) {
-                ms.migrate = tape->mig_n[it] > 0; ms.n = tape->mig_n[it]; ms.groups.clear(); ms.u_pick.clear();
-                for (int i = 0; i < ms.n; ++i) { ms.groups.push_back(tape->mig_groups[it * Gt + i]); ms.u_pick.push_back(tape->mig_pick_u[it * Gt + i]); }
-            } else {
-                plan_migration(cfg.seed, (uint32_t)itg, Gt, cfg.alpha, ms);
-            }
-            if (ms.migrate) {
-                if (ms.n < 2 || ms.n > Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration with %d groups", ms.n); }
-                MigArgs a;
-                memset(&a, 0, sizeof a);
-                a.n = ms.n;
-                bool cross = false, any_local = false;
-                std::vector<int> src(ms.n), dst(ms.n);
-                for (int i = 0; i < ms.n; ++i) {
-                    a.groups[i] = ms.groups[i]; a.u_pick[i] = ms.u_pick[i];
-                    if (a.groups[i] < 0 || a.groups[i] >= Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration group out of range"); }
-                    dst[i] = h->group_owner[ms.groups[i]];
-                    src[i] = h->group_owner[ms.groups[(i + ms.n - 1) % ms.n]];
-                    cross |= src[i] != dst[i];
-                    any_local |= dst[i] == h->rank;
-                }
-                if (any_local || cross) {
-                    int32_t *picks = h->d_mig_log + it * MAX_MIG;
-                    BE(be::launch_mig_pick(h->dcfg, a, cur.w, picks));
-                    BE(be::launch_mig_gather(h->dcfg, a, picks, cur.theta, cur.w, cur.id, cur.acc, h->d_stage));
-                    const double *incoming = h->d_stage;
-                    if (cross) {
-                        if (!h->comm) { cleanup(); return fail(DEMCMC_ECOMM, "migration crosses ranks but demcmc_comm_init was not called"); }
-                        BE(be::d2d(h->d_stage_recv, h->d_stage, sizeof(double) * ms.n * (d + 3)));
-                        if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
-                        incoming = h->d_stage_recv;
-                    }
-                    BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc));
-                }
-                mig_events.emplace_back(it, ms);
-            }
-        }
-
-        // ---- update! (main.jl:161-167): every block is one sweep ---------------------------------
-        for (int b = 0; b < B; ++b) {
+        for (int s = 0; s < n_sw; ++s) {
+            const int64_t it = it0 + (B == 1 ? s : 0), itg = itg0 + (B == 1 ? s : 0);
             const int64_t s_local = it * B + b;
-            const uint32_t sweep = (uint32_t)(itg * B + b);
-            PlanInput pin;
-            pin.seed = cfg.seed; pin.Np = Np; pin.G_local = G; pin.group_begin = cfg.group_begin; pin.G_total = Gt;
-            pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker;
-            pin.t_kind = tape ? hk.data() + (size_t)s_local * P : nullptr;
-            pin.t_idx = tape ? hi.data() + (size_t)s_local * P * 3 : nullptr;
-            pin.base_dependency = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin;
-            plan_sweep(pin, sweep, plan);
-
-            Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
-            if (u.armed) BE(be::event_wait(u.copied));     // the pinned slot is free once its copies ran
-            h->ring_use++;
-            memcpy(u.h_order, plan.order.data(), sizeof(int32_t) * P);
-            memcpy(u.h_mut, plan.mutate.data(), G);
-            BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * P));
-            BE(be::h2d(u.d_mut, u.h_mut, G));
-            BE(be::event_record(u.copied));
-            u.armed = true;
-
-            // destination row: the history row of this iteration on the last block, else scratch
+            const bool inb = in_burnin_at(it);
+            basedep[s] = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && inb;
+            // destination row: the history row of the iteration on its last block, else scratch
             Row next;
             int next_scratch = -1;
             if (b == B - 1) next = row_of(h, true, itg);
             else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
-
-            SweepCtx ctx;
+            SweepCtx &ctx = u.h_ctx[s];
             memset(&ctx, 0, sizeof ctx);
-            ctx.sweep = sweep; ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = in_burnin; ctx.replay = tape != nullptr;
+            ctx.sweep = (uint32_t)(itg * B + b); ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
             ctx.exact_base = tape != nullptr;
             ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
             ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
-            ctx.mutate = u.d_mut;
+            ctx.mutate = u.d_mut + (size_t)s * G;
             if (tape) {
                 ctx.t_kind = t_kind + (size_t)s_local * P; ctx.t_idx = t_idx + (size_t)s_local * P * 3;
                 ctx.t_g1 = t_g1 + (size_t)s_local * P; ctx.t_g2 = t_g2 + (size_t)s_local * P; ctx.t_uacc = t_uacc + (size_t)s_local * P;
@@ -529,39 +495,114 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb;
             ctx.ll_part = h->ll_part;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
-            bool any_cross = false;
-            for (int g = 0; g < G; ++g) any_cross |= plan.mutate[g] == 0;
-            if (!tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin && any_cross)
-                BE(be::launch_base_prep(h->dcfg, cur.w, h->base_th, h->base_cw, h->base_tot));
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
-            }
-            for (int l = 0; l < plan.n_levels; ++l) {
-                Level lv;
-                lv.order = u.d_order + plan.level_off[l];
-                lv.n = plan.level_off[l + 1] - plan.level_off[l];
-                if (lv.n == 0) continue;
-                BE(be::launch_propose(h->dcfg, h->dmodel, ctx, lv));
-                const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
-                if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
-                BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part));
-                if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
-                BE(be::launch_accept(h->dcfg, h->dmodel, ctx, lv));
-                ++n_levels;
             }
             if (b == B - 1) { h->cur_hist = itg; }
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
-        if (h->flush_bytes) BE(be::event_record(h->tev[2 * it + 1]));
+        PlanInput pin;
+        pin.seed = cfg.seed; pin.Np = Np; pin.G_local = G; pin.group_begin = cfg.group_begin; pin.G_total = Gt;
+        pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker;
+        const int64_t s_first = it0 * B + b;
+        pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
+        pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
+        plan_chunk(pin, (uint32_t)(itg0 * B + b), n_sw, basedep, plan);
+
+        memcpy(u.h_order, plan.order.data(), sizeof(int32_t) * (size_t)n_sw * P);
+        memcpy(u.h_mut, plan.mutate.data(), (size_t)n_sw * G);
+        BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * (size_t)n_sw * P));
+        BE(be::h2d(u.d_mut, u.h_mut, (size_t)n_sw * G));
+        BE(be::h2d(u.d_ctx, u.h_ctx, sizeof(SweepCtx) * (size_t)n_sw));
+        BE(be::event_record(u.copied));
+        u.armed = true;
+
+        if (needs_snapshot(it0)) {                               // n_sw == 1 here
+            bool any_cross = false;
+            for (int g = 0; g < G; ++g) any_cross |= plan.mutate[g] == 0;
+            if (any_cross) BE(be::launch_base_prep(h->dcfg, u.h_ctx[0].cur_w, h->base_th, h->base_cw, h->base_tot));
+        }
+        for (int l = 0; l < plan.n_levels; ++l) {
+            Level lv;
+            lv.order = u.d_order + plan.level_off[l];
+            lv.n = plan.level_off[l + 1] - plan.level_off[l];
+            lv.ctxs = u.d_ctx;
+            if (lv.n == 0) continue;
+            BE(be::launch_propose(h->dcfg, h->dmodel, lv));
+            const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+            if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
+            BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part));
+            if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
+            BE(be::launch_accept(h->dcfg, h->dmodel, lv));
+            ++n_levels;
+        }
+        if (h->flush_bytes) { BE(be::event_record(h->tev[2 * tev_chunks + 1])); ++tev_chunks; }
+        return 0;
+    };
+
+    for (int64_t it = 0; it < n_iter;) {
+        // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
+        get_mig(it, ms);
+        if (ms.migrate) {
+            Row cur = cur_row(h);
+            if (ms.n < 2 || ms.n > Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration with %d groups", ms.n); }
+            MigArgs a;
+            memset(&a, 0, sizeof a);
+            a.n = ms.n;
+            bool cross = false, any_local = false;
+            std::vector<int> src(ms.n), dst(ms.n);
+            for (int i = 0; i < ms.n; ++i) {
+                a.groups[i] = ms.groups[i]; a.u_pick[i] = ms.u_pick[i];
+                if (a.groups[i] < 0 || a.groups[i] >= Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration group out of range"); }
+                dst[i] = h->group_owner[ms.groups[i]];
+                src[i] = h->group_owner[ms.groups[(i + ms.n - 1) % ms.n]];
+                cross |= src[i] != dst[i];
+                any_local |= dst[i] == h->rank;
+            }
+            if (any_local || cross) {
+                int32_t *picks = h->d_mig_log + it * MAX_MIG;
+                BE(be::launch_mig_pick(h->dcfg, a, cur.w, picks));
+                BE(be::launch_mig_gather(h->dcfg, a, picks, cur.theta, cur.w, cur.id, cur.acc, h->d_stage));
+                const double *incoming = h->d_stage;
+                if (cross) {
+                    if (!h->comm) { cleanup(); return fail(DEMCMC_ECOMM, "migration crosses ranks but demcmc_comm_init was not called"); }
+                    BE(be::d2d(h->d_stage_recv, h->d_stage, sizeof(double) * ms.n * (d + 3)));
+                    if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
+                    incoming = h->d_stage_recv;
+                }
+                BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc));
+            }
+            mig_events.emplace_back(it, ms);
+        }
+
+        // ---- update! (main.jl:161-167) -------------------------------------------------------------
+        if (B > 1) {                                  // blocking: every block is one sweep, one chunk each
+            for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1)) { cleanup(); return rc; }
+            ++it;
+            continue;
+        }
+        // consecutive iterations without a migration and without a sweep-start snapshot overlap on
+        // the device: plan them as one chunk (planner.h)
+        int n = 1;
+        if (!needs_snapshot(it) && h->max_chunk > 1) {
+            MigSchedule m2;
+            while (it + n < n_iter && n < h->max_chunk) {
+                get_mig(it + n, m2);
+                if (m2.migrate || needs_snapshot(it + n)) break;
+                ++n;
+            }
+        }
+        if (int rc = run_chunk(it, 0, n)) { cleanup(); return rc; }
+        it += n;
     }
     double ms_dev = 0.0;
     BE(be::timer_stop(&ms_dev));
     BE(be::sync());
-    if (h->flush_bytes) {                                   // sum of the per-iteration times, flushes excluded
+    if (h->flush_bytes) {                                   // sum of the per-chunk times, flushes excluded
         ms_dev = 0.0;
-        for (int64_t it = 0; it < n_iter; ++it) { double t = 0.0; BE(be::tevent_elapsed(h->tev[2 * it], h->tev[2 * it + 1], &t)); ms_dev += t; }
+        for (size_t c = 0; c < tev_chunks; ++c) { double t = 0.0; BE(be::tevent_elapsed(h->tev[2 * c], h->tev[2 * c + 1], &t)); ms_dev += t; }
     }
     double ms_ll = 0.0;
     for (size_t i = 0; i < tev_ll; ++i) { double t = 0.0; BE(be::tevent_elapsed(h->tev[tev_ll0 + 2 * i], h->tev[tev_ll0 + 2 * i + 1], &t)); ms_ll += t; }
@@ -676,6 +717,13 @@ int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_log
         h->flush_bytes = l2_flush_bytes;
     }
     h->time_loglik = time_loglik != 0;
+    return 0;
+}
+
+int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps)
+{
+    if (!h || n_sweeps < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    h->max_chunk = std::min<int32_t>(n_sweeps, MAX_CHUNK);
     return 0;
 }
 

@@ -2,9 +2,9 @@
 //
 //   k_propose      one warp per particle: DE / snooker / mutation proposal, kappa and block masks,
 //                  bounds, prior, snooker adjustment                       (HBM-bound, ~5 d-vectors)
-//   k_ssd          sum of squared differences sum_i sum_k (x_ik - m_pk)^2 for a tile of particles
-//                  against a slice of observations: the likelihood of the isotropic MVN and the
-//                  hierarchical normal models                              (fp64-pipe-bound)
+//   k_xdot         cross term sum_i sum_k x'_ik m'_pk of the expanded sum of squares for a tile of
+//                  particles against slices of observations: the likelihood of the isotropic MVN
+//                  and the hierarchical normal models                      (fp64-pipe-bound)
 //   k_ll_pointwise per-observation log densities (Gaussian, LNR, LBA) for a tile of particles
 //   k_accept       one warp per particle: fixed-order reduction of the partial sums, Metropolis
 //                  accept, state-row write (replaces store_samples!)       (HBM-bound)
@@ -159,32 +159,36 @@ __device__ __forceinline__ double kval(const ksum_t &k) { return isfinite(k.s) ?
 // ------------------------------------------------------------------------------------------------
 constexpr int PA_THREADS = 128;
 
-__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, SweepCtx ctx, Level lv)
+__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv)
 {
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) return;
-    propose_particle(WarpLanes(), cfg, m, ctx, lv.order[wi]);
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    propose_particle(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
 }
 
-__global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, SweepCtx ctx, Level lv)
+__global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, Level lv)
 {
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) return;
-    accept_particle(WarpLanes(), cfg, m, ctx, lv.order[wi]);
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    accept_particle(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
 }
 
-int launch_propose(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, ctx, lv);
+    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv);
     LAUNCHED("k_propose");
     return 0;
 }
 
-int launch_accept(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    k_accept<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, ctx, lv);
+    k_accept<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv);
     LAUNCHED("k_accept");
     return 0;
 }
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
     const int n_split = m.n_osplit * m.n_ksplit;
     // stage the tile's parameters (+ per-particle constants)
     if (tid < nt) {
-        const int p = lv.order ? lv.order[tile * PW_TP + tid] : tile * PW_TP + tid;
+        const int p = lv.order ? (int)((uint32_t)lv.order[tile * PW_TP + tid] & LV_POS_MASK) : tile * PW_TP + tid;
         const double *th = theta + (size_t)p * m.d;
         if (KIND == M_GAUSSIAN) { par[tid][0] = th[0]; par[tid][1] = th[1]; par[tid][2] = log(th[1]); }
         else if (KIND == M_LNR) { for (int r = 0; r <= m.n_dim; ++r) par[tid][r] = th[r]; }
@@ -278,108 +282,137 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < PW_THREADS / 32; ++w) v += red[w][tid];
-        const int p = lv.order ? lv.order[tile * PW_TP + tid] : tile * PW_TP + tid;
+        const int p = lv.order ? (int)((uint32_t)lv.order[tile * PW_TP + tid] & LV_POS_MASK) : tile * PW_TP + tid;
         part[(size_t)p * n_split + split] = v;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// SSD kernel: part[p][split] = sum over the split's observations i and dimensions k of
-// (xT[k][i] - mean_p[k])^2, register tile 4 particles x 4 observations per thread, 16x16 threads,
-// CTA tile SSD_TP(64) particles x SSD_TN(64) observations, dimensions staged SSD_KC(32) at a time.
-//   MVN:          mean_p[k] = theta_p[k]
-//   hierarchical: mean_p[k] = theta_p[0] + theta_p[2+k]   (subject k; "observations" = n_per)
-// 2 fp64 instructions (DADD, DFMA) per (observation, dimension, particle).
+// MVN / hierarchical likelihood kernel.  With centred data x' and centred means m',
+//   sum_i sum_k (x_ik - m_pk)^2 = sum x'^2 - 2 B_p + n sum_k m'_pk^2,   B_p = sum_i sum_k x'_ik m'_pk
+// and only B_p needs the O(N d) pass: ONE DFMA per (observation, dimension, particle), every
+// observation streamed for every particle (no sufficient-statistic shortcut).  Zero padding
+// contributes nothing to B, so there is no ragged-tile path.
+//
+// CTA = 128 threads, tile 64 particles x 64 observations, thread tile 4 particles x 8 observations
+// (32 independent DFMA chains).  The centred means of the CTA's dimension range stay resident in
+// shared memory; observation tiles stream through a 3-stage cp.async ring of [32 dims][64 obs].
+// Shared-memory reads are conflict-free: the 8 lanes of an observation group read one contiguous
+// 128 B row segment (the 4 particle groups of the warp broadcast), the mean reads hit 4 distinct
+// 16 B words in distinct banks.
+// A CTA processes `spc` consecutive observation SLICES and writes one partial per slice, so the
+// set of partial sums (and the summation order) is fixed by the model alone.
 // ------------------------------------------------------------------------------------------------
-constexpr int SSD_THREADS = 256;
-constexpr int SSD_MS_LD = SSD_TP + 2;       // padded row of the mean tile: conflict-free transposed stores
+constexpr int XD_THREADS = 128;
+constexpr int XD_STAGES = 3;
+constexpr int XD_MS_LD = SSD_TP + 2;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+static size_t xdot_smem_bytes(int klen)
+{
+    return sizeof(double) * ((size_t)klen * XD_MS_LD + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP;
+}
 
 template <int KIND>
-__global__ void __launch_bounds__(SSD_THREADS, 2) k_ssd(ModelDev m, const double *theta, Level lv, double *part)
+__global__ void __launch_bounds__(XD_THREADS, 3) k_xdot(ModelDev m, const double *theta, Level lv, double *part, int spc)
 {
-    __shared__ __align__(16) double xs[SSD_KC][SSD_TN];
-    __shared__ __align__(16) double ms[SSD_KC][SSD_MS_LD];
-    __shared__ int s_p[SSD_TP];
-    const int tid = threadIdx.x, to = tid & 15, tp = tid >> 4;
-    const int tile = blockIdx.x, osplit = blockIdx.y, ksplit = blockIdx.z;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, to = tid & 7, tp = tid >> 3;
+    const int tile = blockIdx.x, chunk = blockIdx.y, ksplit = blockIdx.z;
+    const int k_begin = ksplit * m.ksplit_len, k_end = min(m.ssd_k, k_begin + m.ksplit_len), klen = k_end - k_begin;
+    double *ms = reinterpret_cast<double *>(smem_raw);                 // [klen][XD_MS_LD]
+    double *xs = ms + (size_t)m.ksplit_len * XD_MS_LD;                 // [XD_STAGES][SSD_KC][SSD_TN]
+    int *s_p = reinterpret_cast<int *>(xs + XD_STAGES * SSD_KC * SSD_TN);
     const int nt = min(SSD_TP, lv.n - tile * SSD_TP);
     const int n_split = m.n_osplit * m.n_ksplit;
-    if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? lv.order[tile * SSD_TP + tid] : tile * SSD_TP + tid) : -1;
-    const int k_begin = ksplit * m.ksplit_len, k_end = min(m.ssd_k, k_begin + m.ksplit_len);
-    const int64_t o_begin = (int64_t)osplit * m.split_len, o_end = min(m.ssd_ld, o_begin + (int64_t)m.split_len);
-    double acc[4][4];
+    const int n_tiles = (int)(m.ssd_ld / SSD_TN), tps = m.ssd_tps;
+    const int slice0 = chunk * spc, slice1 = min(m.n_osplit, slice0 + spc);
+    const int T0 = slice0 * tps, T1 = min(n_tiles, slice1 * tps);
+    const int n_kc = (klen + SSD_KC - 1) / SSD_KC;
+    const int n_steps = (T1 - T0) * n_kc;
+
+    if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? (int)((uint32_t)lv.order[tile * SSD_TP + tid] & LV_POS_MASK) : tile * SSD_TP + tid) : -1;
+    __syncthreads();
+    // resident centred means, transposed to [k][particle]
+    for (int idx = tid; idx < SSD_TP * klen; idx += XD_THREADS) {
+        const int pi = idx / klen, kk = idx - pi * klen;
+        const int p = s_p[pi];
+        ms[kk * XD_MS_LD + pi] = p >= 0 ? centred_mean(m, theta + (size_t)p * m.d, k_begin + kk) : 0.0;
+    }
+
+    auto issue = [&](int q) {
+        if (q < n_steps) {
+            const int tt = T0 + q / n_kc, c = q - (q / n_kc) * n_kc;
+            const int kc = min(SSD_KC, klen - c * SSD_KC);
+            double *dst = xs + (size_t)(q % XD_STAGES) * SSD_KC * SSD_TN;
+            const double *src = m.xT + (size_t)(k_begin + c * SSD_KC) * m.ssd_ld + (size_t)tt * SSD_TN;
+#pragma unroll
+            for (int r = 0; r < (SSD_KC * SSD_TN / 2) / XD_THREADS; ++r) {
+                const int idx = tid + XD_THREADS * r, row = idx >> 5, col = idx & 31;
+                if (row < kc) cp_async16(dst + row * SSD_TN + col * 2, src + (size_t)row * m.ssd_ld + col * 2);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[4][8];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    __syncthreads();
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
 
-    for (int k0 = k_begin; k0 < k_end; k0 += SSD_KC) {
-        const int kc = min(SSD_KC, k_end - k0);
-        __syncthreads();                       // previous chunk's readers are done with ms
-        // stage the means of this chunk, transposed to [k][particle]
-        for (int idx = tid; idx < SSD_TP * SSD_KC; idx += SSD_THREADS) {
-            const int pi = idx / SSD_KC, kk = idx - pi * SSD_KC;
-            double v = 0.0;
-            const int p = s_p[pi];
-            if (p >= 0 && kk < kc) {
-                const double *th = theta + (size_t)p * m.d;
-                v = (KIND == M_HIER) ? th[0] + th[2 + k0 + kk] : th[k0 + kk];
-            }
-            ms[kk][pi] = v;
-        }
-        for (int64_t ob = o_begin; ob < o_end; ob += SSD_TN) {
-            __syncthreads();                   // previous tile's readers are done with xs (and ms is staged)
-            for (int idx = tid; idx < SSD_KC * (SSD_TN / 2); idx += SSD_THREADS) {
-                const int kk = idx / (SSD_TN / 2), c2 = idx - kk * (SSD_TN / 2);
-                double2 v = make_double2(0.0, 0.0);
-                if (kk < kc) v = *reinterpret_cast<const double2 *>(m.xT + (size_t)(k0 + kk) * m.ssd_ld + ob + 2 * c2);
-                *reinterpret_cast<double2 *>(&xs[kk][2 * c2]) = v;
-            }
-            __syncthreads();
-            const bool full = ob + SSD_TN <= m.ssd_n;
-            if (full) {
+    issue(0);
+    issue(1);
+    for (int q = 0; q < n_steps; ++q) {
+        cp_async_wait<1>();                     // stage q has landed (this thread's copies)
+        __syncthreads();                        // ... everyone's; and everyone is done with stage q-1
+        issue(q + 2);                           // refills the stage computed in the previous step
+        const int tq = q / n_kc, c = q - tq * n_kc;
+        const int kc = min(SSD_KC, klen - c * SSD_KC);
+        const double *xb = xs + (size_t)(q % XD_STAGES) * SSD_KC * SSD_TN + to * 2;
+        const double *mb = ms + (size_t)(c * SSD_KC) * XD_MS_LD + tp * 4;
 #pragma unroll 4
-                for (int kk = 0; kk < kc; ++kk) {
-                    const double2 xa = *reinterpret_cast<const double2 *>(&xs[kk][to * 4]);
-                    const double2 xb = *reinterpret_cast<const double2 *>(&xs[kk][to * 4 + 2]);
-                    const double2 ma = *reinterpret_cast<const double2 *>(&ms[kk][tp * 4]);
-                    const double2 mb = *reinterpret_cast<const double2 *>(&ms[kk][tp * 4 + 2]);
-                    const double xv[4] = { xa.x, xa.y, xb.x, xb.y };
-                    const double mv[4] = { ma.x, ma.y, mb.x, mb.y };
+        for (int kk = 0; kk < kc; ++kk) {
+            const double2 x0 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN);
+            const double2 x1 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 16);
+            const double2 x2 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 32);
+            const double2 x3 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 48);
+            const double2 m0 = *reinterpret_cast<const double2 *>(mb + kk * XD_MS_LD);
+            const double2 m1 = *reinterpret_cast<const double2 *>(mb + kk * XD_MS_LD + 2);
+            const double xv[8] = { x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y };
+            const double mv[4] = { m0.x, m0.y, m1.x, m1.y };
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) { const double t = xv[b] - mv[a]; acc[a][b] = fma(t, t, acc[a][b]); }
+                for (int b = 0; b < 8; ++b) acc[a][b] = fma(xv[b], mv[a], acc[a][b]);
+        }
+        // end of a slice: reduce the 8 observation columns and the 8 lanes of the particle group,
+        // write the slice's partial, restart the accumulators
+        const int tt = T0 + tq;
+        if (c == n_kc - 1 && ((tt + 1) % tps == 0 || tt + 1 == T1)) {
+            const int slice = tt / tps;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double v = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) + ((acc[a][4] + acc[a][5]) + (acc[a][6] + acc[a][7]));
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (to == 0) {
+                    const int p = s_p[tp * 4 + a];
+                    if (p >= 0) part[(size_t)p * n_split + (size_t)slice * m.n_ksplit + ksplit] = v;
                 }
-            } else {
-                // last, partly padded tile: skip the observations beyond ssd_n
-                bool ok[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) ok[b] = ob + to * 4 + b < m.ssd_n;
-                for (int kk = 0; kk < kc; ++kk) {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const double mv = ms[kk][tp * 4 + a];
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            if (ok[b]) { const double t = xs[kk][to * 4 + b] - mv; acc[a][b] = fma(t, t, acc[a][b]); }
-                    }
-                }
+                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
             }
         }
     }
-    // reduce: over the 4 observations of the thread, then over the 16 threads sharing a particle group
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        double v = (acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3]);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (to == 0) {
-            const int p = s_p[tp * 4 + a];
-            if (p >= 0) part[(size_t)p * n_split + osplit * m.n_ksplit + ksplit] = v;
-        }
-    }
+    cp_async_wait<0>();
 }
 
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part)
@@ -387,10 +420,22 @@ int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, 
     (void)cfg;
     if (lv.n <= 0 || m.kind == M_BINOMIAL) return 0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
-        dim3 grid((lv.n + SSD_TP - 1) / SSD_TP, m.n_osplit, m.n_ksplit);
-        if (m.kind == M_MVNORMAL) k_ssd<M_MVNORMAL><<<grid, SSD_THREADS, 0, stream()>>>(m, theta, lv, ll_part);
-        else k_ssd<M_HIER><<<grid, SSD_THREADS, 0, stream()>>>(m, theta, lv, ll_part);
-        LAUNCHED("k_ssd");
+        static bool attr_set[64] = { false };
+        const size_t smem = xdot_smem_bytes(m.ksplit_len);
+        if (!attr_set[g_dev]) {
+            CU(cudaFuncSetAttribute(k_xdot<M_MVNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
+            CU(cudaFuncSetAttribute(k_xdot<M_HIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
+            attr_set[g_dev] = true;
+        }
+        const int n_pt = (lv.n + SSD_TP - 1) / SSD_TP;
+        // slices per CTA: keep at least ~6 waves of 3 CTAs/SM when there is that much work
+        const int64_t items = (int64_t)n_pt * m.n_osplit * m.n_ksplit;
+        int spc = (int)(items / (148 * 3 * 6));
+        spc = spc < 1 ? 1 : (spc > 4 ? 4 : spc);
+        dim3 grid(n_pt, (m.n_osplit + spc - 1) / spc, m.n_ksplit);
+        if (m.kind == M_MVNORMAL) k_xdot<M_MVNORMAL><<<grid, XD_THREADS, smem, stream()>>>(m, theta, lv, ll_part, spc);
+        else k_xdot<M_HIER><<<grid, XD_THREADS, smem, stream()>>>(m, theta, lv, ll_part, spc);
+        LAUNCHED("k_xdot");
         return 0;
     }
     dim3 grid((lv.n + PW_TP - 1) / PW_TP, m.n_osplit);
@@ -403,37 +448,66 @@ int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// data packing for the SSD kernel: x[n][k] (MVN, observation-major) or y[k][n] (hierarchical,
-// subject-major) -> xT[k][ld] zero padded
+// data packing for k_xdot: x[n][k] (MVN, observation-major) or y[k][n] (hierarchical,
+// subject-major) -> centred xT[k][ld] zero padded, center[k], and sum of the squared centred data.
+// One block per dimension, fixed reduction order (deterministic).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_ssd(const double *x, double *xT, int64_t n, int k, int64_t ld, int obs_major)
+__device__ double block_sum_256(double v, double *red)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int kk = blockIdx.y;
-    if (i >= ld) return;
-    double v = 0.0;
-    if (i < n) v = obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i];
-    xT[(int64_t)kk * ld + i] = v;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) { for (int w = 0; w < 8; ++w) s += red[w]; red[8] = s; }
+    __syncthreads();
+    s = red[8];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_pack_center(const double *x, double *xT, double *center, double *colsq, int64_t n, int k,
+                                                     int64_t ld, int obs_major)
+{
+    __shared__ double red[9];
+    const int kk = blockIdx.x;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) s += obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i];
+    const double c = n > 0 ? block_sum_256(s, red) / (double)n : 0.0;
+    double q = 0.0;
+    for (int64_t i = threadIdx.x; i < ld; i += 256) {
+        double v = 0.0;
+        if (i < n) { v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - c; q += v * v; }
+        xT[(int64_t)kk * ld + i] = v;
+    }
+    q = block_sum_256(q, red);
+    if (threadIdx.x == 0) { center[kk] = c; colsq[kk] = q; }
 }
 
 int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
 {
     const size_t bytes = sizeof(double) * (size_t)m->ssd_n * m->ssd_k;
     const double *src = x_in;
-    double *tmp = nullptr;
+    double *tmp = nullptr, *colsq = (double *)dmalloc(sizeof(double) * m->ssd_k);
+    if (!colsq) return -1;
     if (!in_on_device) {
         tmp = (double *)dmalloc(bytes);
-        if (!tmp) return -1;
-        if (h2d(tmp, x_in, bytes)) { dfree(tmp); return -1; }
+        if (!tmp) { dfree(colsq); return -1; }
+        if (h2d(tmp, x_in, bytes)) { dfree(tmp); dfree(colsq); return -1; }
         src = tmp;
     }
-    dim3 grid((unsigned)((m->ssd_ld + 255) / 256), (unsigned)m->ssd_k);
-    k_pack_ssd<<<grid, 256, 0, stream()>>>(src, const_cast<double *>(m->xT), m->ssd_n, m->ssd_k, m->ssd_ld, m->kind == M_MVNORMAL ? 1 : 0);
+    k_pack_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->xT), const_cast<double *>(m->center), colsq, m->ssd_n,
+                                                  m->ssd_k, m->ssd_ld, m->kind == M_MVNORMAL ? 1 : 0);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
+    double *h = new double[m->ssd_k];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, colsq, sizeof(double) * m->ssd_k, cudaMemcpyDeviceToHost, stream());
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
-    dfree(tmp);
-    if (e != cudaSuccess) return cu_fail(e, "k_pack_ssd");
+    double xx = 0.0;
+    for (int k = 0; k < m->ssd_k; ++k) xx += h[k];
+    m->ssd_xx = xx;
+    delete[] h;
+    dfree(tmp); dfree(colsq);
+    if (e != cudaSuccess) return cu_fail(e, "k_pack_center");
     return 0;
 }
 
@@ -453,7 +527,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, Model
     double s = 0.0;
     if (m.kind != M_BINOMIAL) for (int q = co.lane(); q < n_split; q += 32) s += part[(size_t)wi * n_split + q];
     s = co.sum(s);
-    const double l = finalize_ll(m, th, s);
+    const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
     if (co.lane() == 0) {
         if (ll) ll[wi] = l;
         if (prior) prior[wi] = inb ? pr : -inf();
@@ -465,7 +539,7 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
                 double *w, double *scratch_part)
 {
     if (n <= 0) return 0;
-    Level lv; lv.order = nullptr; lv.n = (int32_t)n;
+    Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
     if (launch_loglik(cfg, m, theta, lv, scratch_part)) return -1;
     const int blocks = (int)((n * 32 + PA_THREADS - 1) / PA_THREADS);
     k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, ll, prior, w);

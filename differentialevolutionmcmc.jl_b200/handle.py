@@ -187,6 +187,9 @@ class Handle:
     def set_timing(self, l2_flush_bytes=0, time_loglik=False):
         check(_ffi.lib().demcmc_set_timing(self._h, int(l2_flush_bytes), int(bool(time_loglik))))
 
+    def set_max_chunk(self, n_sweeps):
+        check(_ffi.lib().demcmc_set_max_chunk(self._h, int(n_sweeps)))
+
     def eval(self, theta):
         th = f8(theta).reshape(-1, self.d)
         n = th.shape[0]

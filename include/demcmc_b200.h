@@ -157,10 +157,14 @@ int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, 
 int demcmc_get_migration(demcmc_handle *h, int32_t *slots);
 int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out);
 /* measurement mode for bench.py: l2_flush_bytes > 0 overwrites a buffer of that size between
- * iterations (evicting L2) and makes counters.device_ms the sum of per-iteration CUDA-event times
+ * chunks of overlapped iterations (evicting L2) and makes counters.device_ms the sum of per-chunk CUDA-event times
  * with the flushes excluded; time_loglik brackets every likelihood launch with CUDA events on the
  * launching stream and reports their sum in counters.loglike_ms */
 int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_loglik);
+/* how many consecutive sweeps (iterations without migration) the device may overlap: the tail
+ * dependency levels of one sweep share launches with the head levels of the next (default 16;
+ * 1 = a barrier after every sweep).  The result does not depend on it. */
+int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps);
 
 /* compute_posterior! pieces (src/utilities.jl:92-99) for n arbitrary parameter vectors
  * theta[n][d]: loglike[n], prior[n] (prior is -inf when out of bounds); either may be NULL */

@@ -63,34 +63,44 @@ static double kval(const ksum_t &k) { return isfinite(k.s) ? k.s + k.c : k.s; }
 int launch_pack_ssd(const double *x, int, ModelDev *m)
 {
     ++g_launches;
-    double *xT = const_cast<double *>(m->xT);
-    for (int k = 0; k < m->ssd_k; ++k)
+    double *xT = const_cast<double *>(m->xT), *center = const_cast<double *>(m->center);
+    double xx = 0.0;
+    for (int k = 0; k < m->ssd_k; ++k) {
+        auto at = [&](int64_t i) { return m->kind == M_MVNORMAL ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i]; };
+        double s = 0.0;
+        for (int64_t i = 0; i < m->ssd_n; ++i) s += at(i);
+        const double c = m->ssd_n > 0 ? s / (double)m->ssd_n : 0.0;
+        center[k] = c;
+        double q = 0.0;
         for (int64_t i = 0; i < m->ssd_ld; ++i) {
             double v = 0.0;
-            if (i < m->ssd_n) v = m->kind == M_MVNORMAL ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i];
+            if (i < m->ssd_n) { v = at(i) - c; q += v * v; }
             xT[(int64_t)k * m->ssd_ld + i] = v;
         }
+        xx += q;
+    }
+    m->ssd_xx = xx;
     return 0;
 }
 
-// contract of k_ssd / k_ll_pointwise: part[p][split] for every particle of the level
+// contract of k_xdot / k_ll_pointwise: part[p][split] for every particle of the level
 int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, const Level &lv, double *part)
 {
     ++g_launches;
     if (m.kind == M_BINOMIAL) return 0;
     const int n_split = m.n_osplit * m.n_ksplit;
     for (int q = 0; q < lv.n; ++q) {
-        const int p = lv.order ? lv.order[q] : q;
+        const int p = lv.order ? (int)((uint32_t)lv.order[q] & LV_POS_MASK) : q;
         const double *th = theta + (size_t)p * m.d;
         if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
             for (int os = 0; os < m.n_osplit; ++os)
                 for (int ks = 0; ks < m.n_ksplit; ++ks) {
                     const int k0 = ks * m.ksplit_len, k1 = std::min(m.ssd_k, k0 + m.ksplit_len);
-                    const int64_t o0 = (int64_t)os * m.split_len, o1 = std::min<int64_t>(m.ssd_n, o0 + m.split_len);
+                    const int64_t o0 = (int64_t)os * m.split_len, o1 = std::min<int64_t>(m.ssd_ld, o0 + m.split_len);
                     double s = 0.0;
                     for (int k = k0; k < k1; ++k) {
-                        const double mean = m.kind == M_HIER ? th[0] + th[2 + k] : th[k];
-                        for (int64_t i = o0; i < o1; ++i) { const double t = m.xT[(int64_t)k * m.ssd_ld + i] - mean; s += t * t; }
+                        const double mean = centred_mean(m, th, k);
+                        for (int64_t i = o0; i < o1; ++i) s += m.xT[(int64_t)k * m.ssd_ld + i] * mean;
                     }
                     part[(size_t)p * n_split + os * m.n_ksplit + ks] = s;
                 }
@@ -123,7 +133,7 @@ int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, con
 
 int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior, double *w, double *part)
 {
-    Level lv; lv.order = nullptr; lv.n = (int32_t)n;
+    Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
     launch_loglik(cfg, m, theta, lv, part);
     ++g_launches;
     const SerialLanes co;
@@ -134,7 +144,7 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
         bounds_and_prior(co, cfg, m, th, inb, pr);
         double s = 0.0;
         if (m.kind != M_BINOMIAL) for (int q = 0; q < n_split; ++q) s += part[(size_t)i * n_split + q];
-        const double l = finalize_ll(m, th, s);
+        const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
         if (ll) ll[i] = l;
         if (prior) prior[i] = inb ? pr : -inf();
         if (w) w[i] = inb ? pr + l : -inf();
@@ -165,17 +175,23 @@ int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *
     return 0;
 }
 
-int launch_propose(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     ++g_launches;
-    for (int q = 0; q < lv.n; ++q) propose_particle(SerialLanes(), cfg, m, ctx, lv.order[q]);
+    for (int q = 0; q < lv.n; ++q) {
+        const uint32_t e = (uint32_t)lv.order[q];
+        propose_particle(SerialLanes(), cfg, m, lv.ctxs[e >> LV_SLOT_SHIFT], (int)(e & LV_POS_MASK));
+    }
     return 0;
 }
 
-int launch_accept(const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, const Level &lv)
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     ++g_launches;
-    for (int q = 0; q < lv.n; ++q) accept_particle(SerialLanes(), cfg, m, ctx, lv.order[q]);
+    for (int q = 0; q < lv.n; ++q) {
+        const uint32_t e = (uint32_t)lv.order[q];
+        accept_particle(SerialLanes(), cfg, m, lv.ctxs[e >> LV_SLOT_SHIFT], (int)(e & LV_POS_MASK));
+    }
     return 0;
 }
 

@@ -192,3 +192,24 @@ def test_names_blocks_and_bounds_flattening():
     shapes = [np.shape(v) for v in theta]
     assert _flat_names(("A", "s", "v"), shapes) == ["A[1,1]", "A[2,1]", "A[1,2]", "A[2,2]", "s", "v[1]", "v[2]"]
     assert _expand_block([[[True, False], [False, True]], False, True], shapes) == [True, False, False, True, False, True, True]
+
+
+def test_overlapped_chunks_do_not_change_the_result():
+    """Consecutive sweeps share launches (planner.h); the chain must not depend on the chunk length."""
+    case = make_case("gaussian", np.random.default_rng(19))
+    theta0 = case.theta0(np.random.default_rng(4), 2 * 48)
+    outs = []
+    for chunk in (1, 3, 16):
+        h = case.handle(2, 48, seed=21, burnin=5, theta_snooker=0.2, alpha=0.05)
+        h.set_max_chunk(chunk)
+        h.set_state(theta0)
+        h.run(40)
+        outs.append((h.samples(), h.accept(), h.lp(), h.counters()["levels"]))
+        h.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+    assert outs[2][3] < 0.8 * outs[0][3]       # fewer, fatter levels
+    # and it still equals the sequential in-place sweep of the oracle
+    cfg = case.oracle_config(2, 48, seed=21, burnin=5, theta_snooker=0.2, alpha=0.05, base_snapshot=1)
+    r = O.run(cfg, case.oracle_model(), theta0, 40, record=False, trace=False)
+    assert np.array_equal(outs[2][0], r["samples"]) and np.array_equal(outs[2][1], r["accept"])
