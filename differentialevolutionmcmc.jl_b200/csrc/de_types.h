@@ -10,7 +10,7 @@ constexpr int SSD_TP = 64;        // particles per tile of the MVN / hierarchica
 constexpr int SSD_TN = 64;        // observations per tile
 constexpr int SSD_KC = 32;        // dimensions per shared-memory stage
 constexpr int SSD_KS = 64;        // max dimensions per dimension-split (mean tile resident in smem)
-constexpr int SSD_SLICES = 592;   // target number of observation slices (4 per SM)
+constexpr int SSD_SLICES = 4096;  // at most this many observation slices (one 64-observation tile each below that)
 constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
 constexpr int PW_THREADS = 256;
 

@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 
 #include "backend.h"
@@ -158,14 +159,25 @@ __device__ __forceinline__ double kval(const ksum_t &k) { return isfinite(k.s) ?
 // propose / accept: one warp per particle of the level
 // ------------------------------------------------------------------------------------------------
 constexpr int PA_THREADS = 128;
+static double *mT_buffer(size_t doubles);                 // staging of centred means for k_xdot (below)
+static size_t mT_doubles(const ModelDev &m, int n);
 
-__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv)
+__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *mT)
 {
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) return;
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
-    propose_particle(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
+    const int p = (int)(e & LV_POS_MASK);
+    propose_particle(WarpLanes(), cfg, m, ctx, p);
+    if (mT) {
+        // leave the centred means of this proposal where k_xdot wants them: mT[tile][k][64]
+        __syncwarp();
+        const double *prop = ctx.prop_theta + (size_t)p * cfg.d;
+        const size_t tile = (size_t)(wi / SSD_TP);
+        const int pi = wi % SSD_TP;
+        for (int k = threadIdx.x & 31; k < m.ssd_k; k += 32) mT[(tile * m.ssd_k + k) * SSD_TP + pi] = centred_mean(m, prop, k);
+    }
 }
 
 __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, Level lv)
@@ -180,7 +192,13 @@ __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv);
+    double *mT = nullptr;
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+        // sized once for the handle's whole population so it never grows inside a run
+        mT = mT_buffer(mT_doubles(m, std::max(lv.n, cfg.G_local * cfg.Np)));
+        if (!mT) return -1;
+    }
+    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv, mT);
     LAUNCHED("k_propose");
     return 0;
 }
@@ -295,17 +313,20 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 // contributes nothing to B, so there is no ragged-tile path.
 //
 // CTA = 128 threads, tile 64 particles x 64 observations, thread tile 4 particles x 8 observations
-// (32 independent DFMA chains).  The centred means of the CTA's dimension range stay resident in
-// shared memory; observation tiles stream through a 3-stage cp.async ring of [32 dims][64 obs].
-// Shared-memory reads are conflict-free: the 8 lanes of an observation group read one contiguous
-// 128 B row segment (the 4 particle groups of the warp broadcast), the mean reads hit 4 distinct
-// 16 B words in distinct banks.
-// A CTA processes `spc` consecutive observation SLICES and writes one partial per slice, so the
-// set of partial sums (and the summation order) is fixed by the model alone.
+// (32 independent DFMA chains).  The proposal kernel leaves the centred means of every particle
+// tile of the level in the layout this kernel wants (mT[tile][k][64]); they are copied to shared
+// memory with cp.async and stay resident, while observation tiles stream through a 3-stage
+// cp.async ring of [32 dims][64 obs].  Shared-memory reads are conflict-free: the 8 lanes of an
+// observation group read one contiguous 128 B row segment (the 4 particle groups of the warp
+// broadcast), the 4 particle groups read 4 x 32 B of one mean row.
+// The launch is ONE wave: every (particle tile, dimension split) gets C = slots / items CTAs, each
+// taking a contiguous, balanced range of observation SLICES and writing one partial per slice, so
+// the set of partial sums (and the summation order) is fixed by the model alone, independent of
+// the level size and of the GPU count.
 // ------------------------------------------------------------------------------------------------
 constexpr int XD_THREADS = 128;
 constexpr int XD_STAGES = 3;
-constexpr int XD_MS_LD = SSD_TP + 2;
+constexpr int XD_CTAS_PER_SM = 3;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -317,36 +338,48 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 static size_t xdot_smem_bytes(int klen)
 {
-    return sizeof(double) * ((size_t)klen * XD_MS_LD + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP;
+    return sizeof(double) * ((size_t)klen * SSD_TP + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(XD_THREADS, 3) k_xdot(ModelDev m, const double *theta, Level lv, double *part, int spc)
+// staging buffer of centred means, [tile][ssd_k][64], one per device, grown on demand
+static double *g_mT[64] = { nullptr };
+static size_t g_mT_cap[64] = { 0 };
+static double *mT_buffer(size_t doubles)
+{
+    if (doubles > g_mT_cap[g_dev]) {
+        cudaStreamSynchronize(stream());
+        if (g_mT[g_dev]) cudaFree(g_mT[g_dev]);
+        g_mT[g_dev] = nullptr; g_mT_cap[g_dev] = 0;
+        if (cudaMalloc(&g_mT[g_dev], sizeof(double) * doubles) != cudaSuccess) { g_be_err = "cudaMalloc(mean staging)"; return nullptr; }
+        g_mT_cap[g_dev] = doubles;
+    }
+    return g_mT[g_dev];
+}
+static size_t mT_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_TP - 1) / SSD_TP) * m.ssd_k * SSD_TP; }
+
+__global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *mT, Level lv, double *part, int C)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, to = tid & 7, tp = tid >> 3;
-    const int tile = blockIdx.x, chunk = blockIdx.y, ksplit = blockIdx.z;
+    const int tile = blockIdx.x / C, c_in = blockIdx.x - tile * C, ksplit = blockIdx.y;
     const int k_begin = ksplit * m.ksplit_len, k_end = min(m.ssd_k, k_begin + m.ksplit_len), klen = k_end - k_begin;
-    double *ms = reinterpret_cast<double *>(smem_raw);                 // [klen][XD_MS_LD]
-    double *xs = ms + (size_t)m.ksplit_len * XD_MS_LD;                 // [XD_STAGES][SSD_KC][SSD_TN]
+    double *ms = reinterpret_cast<double *>(smem_raw);                 // [klen][64] centred means
+    double *xs = ms + (size_t)m.ksplit_len * SSD_TP;                   // [XD_STAGES][SSD_KC][SSD_TN]
     int *s_p = reinterpret_cast<int *>(xs + XD_STAGES * SSD_KC * SSD_TN);
     const int nt = min(SSD_TP, lv.n - tile * SSD_TP);
     const int n_split = m.n_osplit * m.n_ksplit;
     const int n_tiles = (int)(m.ssd_ld / SSD_TN), tps = m.ssd_tps;
-    const int slice0 = chunk * spc, slice1 = min(m.n_osplit, slice0 + spc);
+    const int slice0 = (int)((int64_t)c_in * m.n_osplit / C), slice1 = (int)((int64_t)(c_in + 1) * m.n_osplit / C);
     const int T0 = slice0 * tps, T1 = min(n_tiles, slice1 * tps);
     const int n_kc = (klen + SSD_KC - 1) / SSD_KC;
     const int n_steps = (T1 - T0) * n_kc;
+    if (n_steps <= 0) return;
 
     if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? (int)((uint32_t)lv.order[tile * SSD_TP + tid] & LV_POS_MASK) : tile * SSD_TP + tid) : -1;
-    __syncthreads();
-    // resident centred means, transposed to [k][particle]
-    for (int idx = tid; idx < SSD_TP * klen; idx += XD_THREADS) {
-        const int pi = idx / klen, kk = idx - pi * klen;
-        const int p = s_p[pi];
-        ms[kk * XD_MS_LD + pi] = p >= 0 ? centred_mean(m, theta + (size_t)p * m.d, k_begin + kk) : 0.0;
+    {   // resident means: straight async copy of the tile's [klen][64] block (joins commit group 0)
+        const double *src = mT + ((size_t)tile * m.ssd_k + k_begin) * SSD_TP;
+        for (int idx = tid; idx < klen * (SSD_TP / 2); idx += XD_THREADS) cp_async16(ms + idx * 2, src + idx * 2);
     }
-
     auto issue = [&](int q) {
         if (q < n_steps) {
             const int tt = T0 + q / n_kc, c = q - (q / n_kc) * n_kc;
@@ -371,21 +404,21 @@ __global__ void __launch_bounds__(XD_THREADS, 3) k_xdot(ModelDev m, const double
     issue(0);
     issue(1);
     for (int q = 0; q < n_steps; ++q) {
-        cp_async_wait<1>();                     // stage q has landed (this thread's copies)
-        __syncthreads();                        // ... everyone's; and everyone is done with stage q-1
+        cp_async_wait<1>();                     // stage q (and, at q = 0, the means) has landed
+        __syncthreads();                        // ... for every thread; and everyone is done with stage q-1
         issue(q + 2);                           // refills the stage computed in the previous step
         const int tq = q / n_kc, c = q - tq * n_kc;
         const int kc = min(SSD_KC, klen - c * SSD_KC);
         const double *xb = xs + (size_t)(q % XD_STAGES) * SSD_KC * SSD_TN + to * 2;
-        const double *mb = ms + (size_t)(c * SSD_KC) * XD_MS_LD + tp * 4;
+        const double *mb = ms + (size_t)(c * SSD_KC) * SSD_TP + tp * 4;
 #pragma unroll 4
         for (int kk = 0; kk < kc; ++kk) {
             const double2 x0 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN);
             const double2 x1 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 16);
             const double2 x2 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 32);
             const double2 x3 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 48);
-            const double2 m0 = *reinterpret_cast<const double2 *>(mb + kk * XD_MS_LD);
-            const double2 m1 = *reinterpret_cast<const double2 *>(mb + kk * XD_MS_LD + 2);
+            const double2 m0 = *reinterpret_cast<const double2 *>(mb + kk * SSD_TP);
+            const double2 m1 = *reinterpret_cast<const double2 *>(mb + kk * SSD_TP + 2);
             const double xv[8] = { x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y };
             const double mv[4] = { m0.x, m0.y, m1.x, m1.y };
 #pragma unroll
@@ -415,28 +448,50 @@ __global__ void __launch_bounds__(XD_THREADS, 3) k_xdot(ModelDev m, const double
     cp_async_wait<0>();
 }
 
+// centred means of arbitrary parameter vectors in the k_xdot layout (demcmc_eval, initial weights)
+__global__ void __launch_bounds__(PA_THREADS) k_stage_means(ModelDev m, const double *theta, int64_t n, double *mT)
+{
+    const int64_t wi = ((int64_t)blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
+    if (wi >= n) return;
+    const double *th = theta + (size_t)wi * m.d;
+    const size_t tile = (size_t)(wi / SSD_TP);
+    const int pi = (int)(wi % SSD_TP);
+    for (int k = threadIdx.x & 31; k < m.ssd_k; k += 32) mT[(tile * m.ssd_k + k) * SSD_TP + pi] = centred_mean(m, th, k);
+}
+
+static int n_sms()
+{
+    static int sms[64] = { 0 };
+    if (!sms[g_dev]) cudaDeviceGetAttribute(&sms[g_dev], cudaDevAttrMultiProcessorCount, g_dev);
+    return sms[g_dev] > 0 ? sms[g_dev] : 148;
+}
+
+static int launch_xdot(const ModelDev &m, const double *mT, const Level &lv, double *ll_part)
+{
+    static bool attr_set[64] = { false };
+    const size_t smem = xdot_smem_bytes(m.ksplit_len);
+    if (!attr_set[g_dev]) {
+        CU(cudaFuncSetAttribute(k_xdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
+        attr_set[g_dev] = true;
+    }
+    const int n_pt = (lv.n + SSD_TP - 1) / SSD_TP;
+    const int64_t items = (int64_t)n_pt * m.n_ksplit, slots = (int64_t)XD_CTAS_PER_SM * n_sms();
+    int C = (int)(slots / items);
+    C = C < 1 ? 1 : (C > m.n_osplit ? m.n_osplit : C);
+    dim3 grid((unsigned)(n_pt * C), (unsigned)m.n_ksplit);
+    k_xdot<<<grid, XD_THREADS, smem, stream()>>>(m, mT, lv, ll_part, C);
+    LAUNCHED("k_xdot");
+    return 0;
+}
+
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part)
 {
     (void)cfg;
     if (lv.n <= 0 || m.kind == M_BINOMIAL) return 0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
-        static bool attr_set[64] = { false };
-        const size_t smem = xdot_smem_bytes(m.ksplit_len);
-        if (!attr_set[g_dev]) {
-            CU(cudaFuncSetAttribute(k_xdot<M_MVNORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
-            CU(cudaFuncSetAttribute(k_xdot<M_HIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
-            attr_set[g_dev] = true;
-        }
-        const int n_pt = (lv.n + SSD_TP - 1) / SSD_TP;
-        // slices per CTA: keep at least ~6 waves of 3 CTAs/SM when there is that much work
-        const int64_t items = (int64_t)n_pt * m.n_osplit * m.n_ksplit;
-        int spc = (int)(items / (148 * 3 * 6));
-        spc = spc < 1 ? 1 : (spc > 4 ? 4 : spc);
-        dim3 grid(n_pt, (m.n_osplit + spc - 1) / spc, m.n_ksplit);
-        if (m.kind == M_MVNORMAL) k_xdot<M_MVNORMAL><<<grid, XD_THREADS, smem, stream()>>>(m, theta, lv, ll_part, spc);
-        else k_xdot<M_HIER><<<grid, XD_THREADS, smem, stream()>>>(m, theta, lv, ll_part, spc);
-        LAUNCHED("k_xdot");
-        return 0;
+        // the proposal kernel of this level has staged the centred means
+        if (!g_mT[g_dev] || g_mT_cap[g_dev] < mT_doubles(m, lv.n)) { g_be_err = "mean staging buffer missing"; return -1; }
+        return launch_xdot(m, g_mT[g_dev], lv, ll_part);
     }
     dim3 grid((lv.n + PW_TP - 1) / PW_TP, m.n_osplit);
     if (m.kind == M_GAUSSIAN) k_ll_pointwise<M_GAUSSIAN><<<grid, PW_THREADS, 0, stream()>>>(m, theta, lv, ll_part);
@@ -540,8 +595,14 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
 {
     if (n <= 0) return 0;
     Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
-    if (launch_loglik(cfg, m, theta, lv, scratch_part)) return -1;
     const int blocks = (int)((n * 32 + PA_THREADS - 1) / PA_THREADS);
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+        double *mT = mT_buffer(mT_doubles(m, (int)n));
+        if (!mT) return -1;
+        k_stage_means<<<blocks, PA_THREADS, 0, stream()>>>(m, theta, n, mT);
+        LAUNCHED("k_stage_means");
+        if (launch_xdot(m, mT, lv, scratch_part)) return -1;
+    } else if (launch_loglik(cfg, m, theta, lv, scratch_part)) return -1;
     k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, ll, prior, w);
     LAUNCHED("k_eval_finish");
     return 0;
