@@ -1,0 +1,265 @@
+# GPULoglike.jl -- the Julia side of the B200 population step for DifferentialEvolutionMCMC.jl.
+#
+# STATUS: NOT EXECUTED.  There is no Julia toolchain in the build image or on the GPU box, so this
+# file has never been run; every ccall below is exercised through the same ABI by its Python
+# ctypes mirror (differentialevolutionmcmc.jl_b200/_ffi.py, handle.py, api.py), which the tests
+# drive.  It is written to be `include`d from src/DifferentialEvolutionMCMC.jl after utilities.jl,
+# plus `export GPULoglike, GPUPrior` (see INTEGRATION.md).
+#
+# What it adds to the package:
+#   * `GPULoglike(kind; data...)`  -- binds a model to a registered hand-written likelihood kernel
+#   * `GPUPrior(specs...)`         -- registered prior specs (one per named parameter)
+#   * `sample(model::DEModel{<:GPULoglike}, de::DE, n_iter)` and the `MCMCThreads()` method:
+#     `sample_init` (src/main.jl:263-271) runs unchanged on the host, the state is uploaded, ONE
+#     ccall runs all n_iter iterations of step!/pstep! (src/main.jl:84-107) on the device, and the
+#     unchanged `bundle_samples` (src/main.jl:222-250) builds the Chains.
+# A DEModel whose loglike is any other callable keeps using the package's CPU path; asking for the
+# GPU path with a closure throws an ArgumentError -- there is no silent CPU fallback.
+
+const LIBDEMCMC = get(ENV, "LIBDEMCMC_B200", "libdemcmc_b200.so")
+const DEMCMC_ABI_VERSION = Int32(1)
+
+const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5)
+const GPU_PRIORS = (flat = 0, normal = 1, halfcauchy = 2, uniform = 3, beta = 4, normal_ref = 5)
+
+"""
+    GPULoglike(kind::Symbol; x = nothing, choice = nothing, rt = nothing, N = nothing, k = nothing,
+               sigma = nothing, lba_floor = 1e-10)
+
+`kind ∈ (:gaussian, :mvnormal, :binomial, :lnr, :lba, :hier_normal)`.  `x` is the data vector
+(`:gaussian`), the `n_dim × n_obs` matrix handed to `MvNormal` (`:mvnormal`) or the vector of
+per-subject vectors / `n_per × n_subj` matrix (`:hier_normal`).
+"""
+struct GPULoglike{D}
+    kind::Symbol
+    data::D
+    sigma::Union{Nothing, Vector{Float64}}
+    lba_floor::Float64
+end
+
+function GPULoglike(kind::Symbol; x = nothing, choice = nothing, rt = nothing, N = nothing, k = nothing,
+    sigma = nothing, lba_floor = 1e-10)
+    haskey(GPU_KINDS, kind) || throw(ArgumentError("no registered kernel for :$kind; registered: $(keys(GPU_KINDS))"))
+    data = if kind == :binomial
+        (x = Float64[N, k], choice = nothing)
+    elseif kind in (:lnr, :lba)
+        (x = Vector{Float64}(rt), choice = Vector{Int32}(choice))
+    elseif kind == :hier_normal && x isa AbstractVector{<:AbstractVector}
+        (x = Matrix{Float64}(reduce(hcat, x)), choice = nothing)   # n_per × n_subj == C [n_subj][n_per]
+    else
+        (x = Array{Float64}(x), choice = nothing)
+    end
+    return GPULoglike(kind, data, sigma === nothing ? nothing : Vector{Float64}(sigma), Float64(lba_floor))
+end
+
+# the device evaluates it; calling it on the host is an error, never a fallback
+(::GPULoglike)(args...; kwargs...) =
+    throw(ArgumentError("GPULoglike is evaluated by libdemcmc_b200 on the device; it is not a host function"))
+
+"Registered prior specs: `(:normal, μ, σ)`, `(:halfcauchy, loc, scale)` = truncated(Cauchy(loc,scale),0,Inf), `(:uniform, a, b)`, `(:beta, a, b)`, `(:flat,)`, `(:normal_ref, mean, :name_of_sd_parameter)`."
+struct GPUPrior
+    specs::Vector{Tuple}
+end
+GPUPrior(specs::Tuple...) = GPUPrior(collect(Tuple, specs))
+
+# DEModel(; ...) wraps loglike/prior_loglike in closures (src/structs.jl:184-188), which would hide
+# the plugin object: keep it unwrapped when it is a GPULoglike.
+function DEModel(args...; prior_loglike::GPUPrior, loglike::GPULoglike, names, sample_prior, data = nothing, kwargs...)
+    return DEModel(prior_loglike, loglike, sample_prior, names)   # positional inner constructor, src/structs.jl:169-174
+end
+
+# ---- C structs (include/demcmc_b200.h) -----------------------------------------------------------
+struct CPrior
+    kind::Int32
+    ref::Int32
+    a::Float64
+    b::Float64
+end
+
+struct CModel
+    kind::Int32
+    d::Int32
+    n_obs::Int64
+    n_dim::Int32
+    n_per::Int32
+    x::Ptr{Float64}
+    choice::Ptr{Int32}
+    sigma::Ptr{Float64}
+    lba_floor::Float64
+    prior::Ptr{CPrior}
+    data_on_device::Int32
+    reserved::Int32
+end
+
+struct CConfig
+    abi_version::Int32
+    n_groups::Int32
+    Np::Int32
+    d::Int32
+    burnin::Int32
+    n_initial::Int32
+    alpha::Float64
+    beta::Float64
+    eps::Float64
+    sigma::Float64
+    kappa::Float64
+    theta_snooker::Float64
+    proposal::Int32
+    n_blocks::Int32
+    blocks::Ptr{UInt8}
+    lo::Ptr{Float64}
+    hi::Ptr{Float64}
+    seed::UInt64
+    device::Int32
+    group_begin::Int32
+    group_count::Int32
+    reserved0::Int32
+    trace::Int32
+    store_every::Int32
+end
+
+function demcmc_check(rc)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:demcmc_last_error, LIBDEMCMC), Cstring, ()))
+    error("libdemcmc_b200 error $rc: $msg")
+end
+
+# flattening in `names` order, column-major inside array parameters (get_names, src/utilities.jl:131-149)
+flatten_theta(Θ) = Float64[x for θ in Θ for x in (θ isa AbstractArray ? vec(θ) : (θ,))]
+n_elems(θ) = θ isa AbstractArray ? length(θ) : 1
+
+function expand_bounds(bounds, Θ)
+    lo, hi = Float64[], Float64[]
+    for (i, θ) in enumerate(Θ)
+        b = i <= length(bounds) ? bounds[i] : (-Inf, Inf)      # zip truncation, src/utilities.jl:74
+        append!(lo, fill(Float64(b[1]), n_elems(θ)))
+        append!(hi, fill(Float64(b[2]), n_elems(θ)))
+    end
+    return lo, hi
+end
+
+function expand_block(block, Θ)
+    out = UInt8[]
+    for (b, θ) in zip(block, Θ)
+        append!(out, b isa AbstractArray ? UInt8.(vec(b)) : fill(UInt8(b), n_elems(θ)))
+    end
+    return out
+end
+
+function prior_table(model, Θ)
+    starts = Dict{Symbol, Int}()
+    pos = 0
+    for (n, θ) in zip(model.names, Θ)
+        starts[Symbol(n)] = pos
+        pos += n_elems(θ)
+    end
+    table = CPrior[]
+    for (spec, θ) in zip(model.prior_loglike.specs, Θ)
+        kind = GPU_PRIORS[spec[1]]
+        a = length(spec) > 1 ? Float64(spec[2]) : 0.0
+        if spec[1] == :normal_ref
+            append!(table, fill(CPrior(kind, starts[Symbol(spec[3])], a, 0.0), n_elems(θ)))
+        else
+            b = length(spec) > 2 ? Float64(spec[3]) : 0.0
+            append!(table, fill(CPrior(kind, 0, a, b), n_elems(θ)))
+        end
+    end
+    return table
+end
+
+proposal_id(de) = de.generate_proposal === random_gamma ? 0 : de.generate_proposal === fixed_gamma ? 1 :
+                  de.generate_proposal === variable_gamma ? 2 :
+                  throw(ArgumentError("generate_proposal must be random_gamma, fixed_gamma or variable_gamma on the B200 path"))
+
+# ---- the sampler ---------------------------------------------------------------------------------
+function sample(model::DEModel{<:GPULoglike}, de::DE, n_iter::Int; progress = false, device = 0, seed = rand(UInt64), kwargs...)
+    return _sample_gpu(model, de, n_iter; device, seed)
+end
+function sample(model::DEModel{<:GPULoglike}, de::DE, ::MCMCThreads, n_iter::Int; progress = false, device = 0, seed = rand(UInt64), kwargs...)
+    return _sample_gpu(model, de, n_iter; device, seed)    # every group is always updated concurrently on the device
+end
+
+function _sample_gpu(model, de, n_iter; device, seed)
+    model.prior_loglike isa GPUPrior || throw(ArgumentError("prior_loglike must be a GPUPrior: a Julia closure would need a host round trip per particle"))
+    de.update_particle! === mh_update! && de.evaluate_fitness! === compute_posterior! ||
+        throw(ArgumentError("only mh_update! / compute_posterior! are built on the B200 path"))
+    de.sample === sample || throw(ArgumentError("sample = resample (DE-MCz) is not built on the B200 path yet"))
+    de.n_initial == 0 || throw(ArgumentError("n_initial > 0 belongs to resample, which is not built yet"))
+    ll = model.loglike
+    # sample_init (src/main.jl:263-271) unchanged: initial Θ and ids are the reference's own
+    groups = sample_init(model, de, n_iter)
+    particles = vcat(groups...)
+    Θ1 = particles[1].Θ
+    d = sum(n_elems, Θ1)
+    P = length(particles)
+    theta0 = reduce(hcat, (flatten_theta(p.Θ) for p in particles))          # d × P == C [P][d]
+    lo, hi = expand_bounds(de.bounds, Θ1)
+    blocks = de.blocking_on(de) ? reduce(vcat, (expand_block(b, Θ1) for b in de.blocks)) : UInt8[]
+    n_blocks = de.blocking_on(de) ? length(de.blocks) : 0
+    priors = prior_table(model, Θ1)
+    x = ll.data.x
+    choice = ll.data.choice
+    n_dim, n_per, n_obs = 0, 0, length(x)
+    if ll.kind == :mvnormal
+        n_dim, n_obs = size(x)
+    elseif ll.kind == :hier_normal
+        n_per, n_dim = size(x); n_obs = n_dim * n_per
+    elseif ll.kind == :lnr
+        n_dim = d - 1
+    elseif ll.kind == :lba
+        n_dim = d - 3
+    elseif ll.kind == :binomial
+        n_obs = 1
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    samples = zeros(Float64, n_iter, d, P)          # Julia order == the library's output order
+    accept = zeros(UInt8, n_iter, P)
+    lp = zeros(Float64, n_iter, P)
+    final_ids = zeros(Int32, P)
+    sig = ll.sigma === nothing ? Float64[] : ll.sigma
+    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids begin
+        cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, de.n_initial, de.α, de.β, de.ϵ, de.σ, de.κ,
+            de.θsnooker, proposal_id(de), n_blocks, isempty(blocks) ? C_NULL : pointer(blocks), pointer(lo), pointer(hi),
+            seed, device, 0, 0, 0, 0, 1)
+        demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        try
+            m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
+                isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0)
+            demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
+            demcmc_check(ccall((:demcmc_set_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), h[], theta0, C_NULL))
+            demcmc_check(ccall((:demcmc_run, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64), h[], n_iter))
+            demcmc_check(ccall((:demcmc_get_samples, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], samples, n_iter))
+            demcmc_check(ccall((:demcmc_get_accept, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], accept, n_iter))
+            demcmc_check(ccall((:demcmc_get_lp, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], lp, n_iter))
+            demcmc_check(ccall((:demcmc_get_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), h[], C_NULL, C_NULL, final_ids))
+        finally
+            ccall((:demcmc_destroy, LIBDEMCMC), Cint, (Ptr{Cvoid},), h[])
+        end
+    end
+    # rebuild what bundle_samples reads: de.samples (nested per named parameter) and, at final
+    # position c, the accept/lp history of the particle that ended there (src/main.jl:232-241)
+    de.iter = n_iter
+    de.samples = nest_samples(samples, Θ1)
+    for (c, p) in enumerate(particles)
+        id = final_ids[c] + 1
+        p.accept = Bool.(accept[:, id])
+        p.lp = lp[:, id]
+    end
+    groups = [particles[((g - 1) * de.Np + 1):(g * de.Np)] for g = 1:(de.n_groups)]
+    return bundle_samples(model, de, groups, n_iter)
+end
+
+# [n_iter, d, P] flat -> the reference's Array{T,3}(n_iter, n_named, P) whose elements may be arrays
+function nest_samples(flat, Θ1)
+    n_iter, _, P = size(flat)
+    out = Array{eltype(Θ1), 3}(undef, n_iter, length(Θ1), P)
+    for c = 1:P, s = 1:n_iter
+        k = 0
+        for (ni, θ) in enumerate(Θ1)
+            n = n_elems(θ)
+            out[s, ni, c] = θ isa AbstractArray ? reshape(flat[s, (k + 1):(k + n), c], size(θ)) : flat[s, k + 1, c]
+            k += n
+        end
+    end
+    return out
+end
