@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 //
 // CTA = 128 threads, tile 64 particles x 64 observations, thread tile 4 particles x 8 observations
 // (32 independent DFMA chains).  The proposal kernel leaves the centred means of every particle
-// tile of the level in the layout this kernel wants (mT[tile][k][64]); they are copied to shared
-// memory with cp.async and stay resident, while observation tiles stream through a 3-stage
-// cp.async ring of [32 dims][64 obs].  Shared-memory reads are conflict-free: the 8 lanes of an
+// tile of the level in the layout this kernel wants (mT[tile][k][64]); one TMA bulk copy brings
+// them to shared memory where they stay resident, while observation tiles stream through a
+// 3-stage ring of [32 dims][64 obs] filled by TMA bulk copies (cp.async.bulk, one 512 B row per
+// lane of warp 0) that complete on per-stage mbarriers; consumer warps release a stage through an
+// "empty" mbarrier, so there is no CTA-wide barrier and no address arithmetic in the inner loop.  Shared-memory reads are conflict-free: the 8 lanes of an
 // observation group read one contiguous 128 B row segment (the 4 particle groups of the warp
 // broadcast), the 4 particle groups read 4 x 32 B of one mean row.
 // The launch is ONE wave: every (particle tile, dimension split) gets C = slots / items CTAs, each
@@ -328,17 +330,43 @@ constexpr int XD_THREADS = 128;
 constexpr int XD_STAGES = 3;
 constexpr int XD_CTAS_PER_SM = 3;
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+// ---- TMA bulk copy + mbarrier helpers (sm_90+; SASS: UBLKCP / SYNCS) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // try_wait sleeps in hardware between polls; the bound turns a protocol bug into a trap, not a hang
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 static size_t xdot_smem_bytes(int klen)
 {
-    return sizeof(double) * ((size_t)klen * SSD_TP + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP;
+    return sizeof(double) * ((size_t)klen * SSD_TP + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP +
+           sizeof(uint64_t) * (2 * XD_STAGES + 1);
 }
 
 // staging buffer of centred means, [tile][ssd_k][64], one per device, grown on demand
@@ -359,13 +387,15 @@ static size_t mT_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_TP
 
 __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *mT, Level lv, double *part, int C)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, to = tid & 7, tp = tid >> 3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, to = tid & 7, tp = tid >> 3, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x / C, c_in = blockIdx.x - tile * C, ksplit = blockIdx.y;
     const int k_begin = ksplit * m.ksplit_len, k_end = min(m.ssd_k, k_begin + m.ksplit_len), klen = k_end - k_begin;
     double *ms = reinterpret_cast<double *>(smem_raw);                 // [klen][64] centred means
     double *xs = ms + (size_t)m.ksplit_len * SSD_TP;                   // [XD_STAGES][SSD_KC][SSD_TN]
     int *s_p = reinterpret_cast<int *>(xs + XD_STAGES * SSD_KC * SSD_TN);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_p + SSD_TP);       // full[STAGES], empty[STAGES], means
+    uint64_t *full = bars, *empty = bars + XD_STAGES, *bar_ms = bars + 2 * XD_STAGES;
     const int nt = min(SSD_TP, lv.n - tile * SSD_TP);
     const int n_split = m.n_osplit * m.n_ksplit;
     const int n_tiles = (int)(m.ssd_ld / SSD_TN), tps = m.ssd_tps;
@@ -375,25 +405,36 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int n_steps = (T1 - T0) * n_kc;
     if (n_steps <= 0) return;
 
-    if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? (int)((uint32_t)lv.order[tile * SSD_TP + tid] & LV_POS_MASK) : tile * SSD_TP + tid) : -1;
-    {   // resident means: straight async copy of the tile's [klen][64] block (joins commit group 0)
-        const double *src = mT + ((size_t)tile * m.ssd_k + k_begin) * SSD_TP;
-        for (int idx = tid; idx < klen * (SSD_TP / 2); idx += XD_THREADS) cp_async16(ms + idx * 2, src + idx * 2);
-    }
-    auto issue = [&](int q) {
-        if (q < n_steps) {
-            const int tt = T0 + q / n_kc, c = q - (q / n_kc) * n_kc;
-            const int kc = min(SSD_KC, klen - c * SSD_KC);
-            double *dst = xs + (size_t)(q % XD_STAGES) * SSD_KC * SSD_TN;
-            const double *src = m.xT + (size_t)(k_begin + c * SSD_KC) * m.ssd_ld + (size_t)tt * SSD_TN;
+    if (tid == 0) {
 #pragma unroll
-            for (int r = 0; r < (SSD_KC * SSD_TN / 2) / XD_THREADS; ++r) {
-                const int idx = tid + XD_THREADS * r, row = idx >> 5, col = idx & 31;
-                if (row < kc) cp_async16(dst + row * SSD_TN + col * 2, src + (size_t)row * m.ssd_ld + col * 2);
-            }
-        }
-        cp_async_commit();
+        for (int s = 0; s < XD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], XD_THREADS / 32); }
+        mbar_init(bar_ms, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? (int)((uint32_t)lv.order[tile * SSD_TP + tid] & LV_POS_MASK) : tile * SSD_TP + tid) : -1;
+    __syncthreads();
+
+    // producer = warp 0: one bulk copy per row of the stage ([kc] rows of 64 observations = 512 B)
+    auto produce = [&](int q) {
+        if (q >= n_steps) return;
+        const int st = q % XD_STAGES, use = q / XD_STAGES;
+        mbar_wait(&empty[st], (use & 1) ^ 1);               // every warp released the previous use of the stage
+        const int tt = T0 + q / n_kc, c = q - (q / n_kc) * n_kc;
+        const int kc = min(SSD_KC, klen - c * SSD_KC);
+        if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)(kc * SSD_TN * sizeof(double)));
+        __syncwarp();
+        if (lane < kc)
+            bulk_g2s(xs + ((size_t)st * SSD_KC + lane) * SSD_TN,
+                     m.xT + (size_t)(k_begin + c * SSD_KC + lane) * m.ssd_ld + (size_t)tt * SSD_TN, SSD_TN * sizeof(double), &full[st]);
     };
+    if (warp == 0) {
+        if (lane == 0) {                                    // the tile's [klen][64] block of centred means
+            mbar_expect_tx(bar_ms, (uint32_t)(klen * SSD_TP * sizeof(double)));
+            bulk_g2s(ms, mT + ((size_t)tile * m.ssd_k + k_begin) * SSD_TP, (uint32_t)(klen * SSD_TP * sizeof(double)), bar_ms);
+        }
+        produce(0);
+        produce(1);
+    }
 
     double acc[4][8];
 #pragma unroll
@@ -401,15 +442,14 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
 
-    issue(0);
-    issue(1);
+    mbar_wait(bar_ms, 0);
+    int tt = T0, c = 0;                                      // (observation tile, dimension chunk) of step q
     for (int q = 0; q < n_steps; ++q) {
-        cp_async_wait<1>();                     // stage q (and, at q = 0, the means) has landed
-        __syncthreads();                        // ... for every thread; and everyone is done with stage q-1
-        issue(q + 2);                           // refills the stage computed in the previous step
-        const int tq = q / n_kc, c = q - tq * n_kc;
+        const int st = q % XD_STAGES;
+        if (warp == 0) produce(q + 2);
+        mbar_wait(&full[st], (q / XD_STAGES) & 1);
         const int kc = min(SSD_KC, klen - c * SSD_KC);
-        const double *xb = xs + (size_t)(q % XD_STAGES) * SSD_KC * SSD_TN + to * 2;
+        const double *xb = xs + (size_t)st * SSD_KC * SSD_TN + to * 2;
         const double *mb = ms + (size_t)(c * SSD_KC) * SSD_TP + tp * 4;
 #pragma unroll 4
         for (int kk = 0; kk < kc; ++kk) {
@@ -426,26 +466,31 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
 #pragma unroll
                 for (int b = 0; b < 8; ++b) acc[a][b] = fma(xv[b], mv[a], acc[a][b]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done reading the stage
         // end of a slice: reduce the 8 observation columns and the 8 lanes of the particle group,
         // write the slice's partial, restart the accumulators
-        const int tt = T0 + tq;
-        if (c == n_kc - 1 && ((tt + 1) % tps == 0 || tt + 1 == T1)) {
-            const int slice = tt / tps;
+        if (c == n_kc - 1) {
+            if ((tt + 1) % tps == 0 || tt + 1 == T1) {
+                const int slice = tt / tps;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                double v = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) + ((acc[a][4] + acc[a][5]) + (acc[a][6] + acc[a][7]));
+                for (int a = 0; a < 4; ++a) {
+                    double v = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) + ((acc[a][4] + acc[a][5]) + (acc[a][6] + acc[a][7]));
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (to == 0) {
-                    const int p = s_p[tp * 4 + a];
-                    if (p >= 0) part[(size_t)p * n_split + (size_t)slice * m.n_ksplit + ksplit] = v;
+                    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (to == 0) {
+                        const int p = s_p[tp * 4 + a];
+                        if (p >= 0) part[(size_t)p * n_split + (size_t)slice * m.n_ksplit + ksplit] = v;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
                 }
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
             }
+            c = 0; ++tt;
+        } else {
+            ++c;
         }
     }
-    cp_async_wait<0>();
 }
 
 // centred means of arbitrary parameter vectors in the k_xdot layout (demcmc_eval, initial weights)
