@@ -66,7 +66,7 @@ SYMBOLS = [
     "demcmc_get_accept", "demcmc_get_lp", "demcmc_get_history_by_slot", "demcmc_get_state", "demcmc_get_trace",
     "demcmc_get_migration", "demcmc_get_counters", "demcmc_set_timing", "demcmc_set_max_chunk", "demcmc_eval", "demcmc_op_project", "demcmc_op_reset",
     "demcmc_op_de_proposal", "demcmc_op_snooker", "demcmc_op_accept", "demcmc_op_select", "demcmc_comm_unique_id",
-    "demcmc_comm_init", "demcmc_fp64_peak", "demcmc_copy_peak",
+    "demcmc_comm_init", "demcmc_fp64_peak", "demcmc_fp64_peaks", "demcmc_copy_peak",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def _declare(L):
     L.demcmc_comm_unique_id.argtypes = [_bp]
     L.demcmc_comm_init.argtypes = [C.c_void_p, _bp, C.c_int32, C.c_int32]
     L.demcmc_fp64_peak.argtypes = [C.c_int, _dp]
+    L.demcmc_fp64_peaks.argtypes = [C.c_int, _dp, _dp]
     L.demcmc_copy_peak.argtypes = [C.c_int, _dp]
 
 

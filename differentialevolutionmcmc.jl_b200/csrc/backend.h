@@ -40,7 +40,9 @@ int timer_start();
 int timer_stop(double *ms);
 
 // ---- kernels ----------------------------------------------------------------------------------
-// transposes MVN / hierarchical data into the k-major padded layout of the SSD kernel
+// centres MVN / hierarchical data and packs them for k_xdot (fills center, xT, ssd_xx, ssd_rowmax);
+// pack_ssd_doubles = size of the xT buffer the caller must allocate for the model's geometry
+size_t pack_ssd_doubles(const ModelDev &m);
 int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m /* xT allocated */);
 // init_particle: weights of n particles theta[n][d] -> w[n] (also demcmc_eval)
 int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior,
@@ -49,7 +51,9 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
 int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
 // propose -> loglik -> accept for one level of one sweep
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
-int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part);
+// MVN / hierarchical: adds the cross term into ll_acc (fixed point, see de_math.h: xd_scale; launch_propose
+// has cleared it and set ll_q); the other models write ll_part
+int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc);
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
 // [position][d+3] = {theta..., weight, id, accept flag}
@@ -72,7 +76,8 @@ int launch_op_reset(const double *prop, const double *pt, const uint8_t *mask, i
 int launch_op_accept(const double *wp, const double *wc, const double *adj, const double *u, int n, uint8_t *out);
 int launch_op_select(const double *w, int n, double u, int32_t *base_idx, int32_t *mig_idx);
 // roofline probes
-int fp64_peak(double *tflops);
+int fp64_peak(double *tflops);                             // the larger of the two below
+int fp64_peaks(double *dfma_tflops, double *dmma_tflops);   // DFMA loop, DMMA m8n8k4 loop
 int copy_peak(double *gbs);
 
 int64_t launch_count();                   // kernels launched so far (for demcmc_counters)

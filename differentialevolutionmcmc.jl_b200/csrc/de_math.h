@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define DE_HD __host__ __device__ __forceinline__
@@ -215,6 +216,36 @@ DE_HD double adjust_loglike(double sq_prop_z, double sq_t_z, int d)
     const double adj1 = pow(sqrt(sq_prop_z), (double)(d - 1));
     const double adj2 = pow(sqrt(sq_t_z), (double)(d - 1));
     return log(adj1 / adj2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-independent accumulation of the MVN / hierarchical cross term
+// ---------------------------------------------------------------------------------------------
+// Every per-row term v = sum_k x'_ik m'_k obeys |v| <= |x'_i| |m'| (Cauchy-Schwarz), so with a
+// per-particle power-of-two quantum q = 2^(e - qbits), 2^e > rowmax*|m'|, the value v rounded to a
+// multiple of q is an integer below 2^qbits and integer addition is associative: the total does
+// not depend on how observations were split over CTAs (level size, GPU count).  The rounding uses
+// the classic magic-number add: bits(v + 1.5*2^52*q) - bits(1.5*2^52*q) = round(v/q).
+struct XdScale { double magic, q; };
+DE_HD XdScale xd_scale(double msq, double rowmax, int qbits)
+{
+    XdScale s;
+    const double bound = sqrt(msq) * rowmax * 1.0009765625;
+    if (!(bound < 1e300)) { s.magic = qnan(); s.q = qnan(); return s; }       // means not finite
+    int e = 0;
+    frexp(bound, &e);                                                          // bound = f * 2^e, f in [0.5, 1)
+    if (e < -900) e = -900;
+    s.q = ldexp(1.0, e - qbits);
+    s.magic = ldexp(1.5, e - qbits + 52);
+    return s;
+}
+DE_HD long long xd_bits(double t)
+{
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(t);
+#else
+    long long b; memcpy(&b, &t, sizeof b); return b;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

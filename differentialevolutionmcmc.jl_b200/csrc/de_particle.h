@@ -194,10 +194,14 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const int n_split = m.n_osplit * m.n_ksplit;
     const double *prop = ctx.prop_theta + (size_t)p * d;
     const double *tcur = ctx.cur_theta + (size_t)p * d;
-    double part = 0.0;
-    if (m.kind != M_BINOMIAL)
-        for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
-    const double total = co.sum(part);
+    double total;
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];
+    else {
+        double part = 0.0;
+        if (m.kind != M_BINOMIAL)
+            for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
+        total = co.sum(part);
+    }
     const double ll = finalize_ll(m, prop, total, mean_sq(co, m, prop));
     const bool inb = ctx.prop_inb[p] != 0;
     const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();

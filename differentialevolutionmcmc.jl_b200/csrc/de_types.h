@@ -6,11 +6,11 @@
 namespace de {
 
 constexpr int MAX_ACC = 8;        // accumulators of LNR / LBA held in registers
-constexpr int SSD_TP = 64;        // particles per tile of the MVN / hierarchical likelihood kernel
+constexpr int SSD_TP = 32;        // particles per CTA tile of the MVN / hierarchical likelihood kernel (4 octets)
+constexpr int SSD_OCT = 8;        // particles per DMMA column tile: the granularity of a level's padding
 constexpr int SSD_TN = 64;        // observations per tile
-constexpr int SSD_KC = 32;        // dimensions per shared-memory stage
-constexpr int SSD_KS = 64;        // max dimensions per dimension-split (mean tile resident in smem)
-constexpr int SSD_SLICES = 4096;  // at most this many observation slices (one 64-observation tile each below that)
+constexpr int SSD_NJ = 13;        // max DMMA k-steps (4 dimensions each) per dimension split, held in registers
+constexpr int SSD_KS = 4 * SSD_NJ; // max dimensions per dimension split
 constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
 constexpr int PW_THREADS = 256;
 
@@ -23,13 +23,15 @@ struct ModelDev {
     int32_t n_dim, n_per;
     const double *x;          // pointwise kernels: x[n_obs] / rt[n_obs]
     const int32_t *choice;    // LNR/LBA winners (1-based)
-    const double *xT;         // MVN/hier kernel: CENTRED data xT[ssd_k][ssd_ld] = x - center[k],
-                              // observations contiguous, zero padded
+    const double *xT;         // MVN/hier kernel: CENTRED data x' = x - center[k], zero padded, packed as DMMA
+                              // A fragments (ssd_pack_index below); the host test double keeps xT[ssd_k][ssd_ld]
     const double *center;     // [ssd_k] column means removed from the data
     double ssd_xx;            // sum of the squared centred data
+    double ssd_rowmax;        // max over observations of |x'_i| (bounds every per-row cross term)
     int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension
     int32_t ssd_k;            // dimensions (MVN: n_dim; hierarchical: subjects)
-    int32_t ssd_tps;          // observation tiles per slice
+    int32_t ssd_nj;           // DMMA k-steps per dimension split = ceil(ksplit_len / 4)
+    int32_t ssd_qbits;        // fixed-point bits below the per-particle bound (de_math.h: xd_magic)
     int32_t has_sigma;
     double sigma_acc[MAX_ACC];
     double lba_floor;
@@ -40,6 +42,19 @@ struct ModelDev {
     // how many slices one CTA happens to process
     int32_t n_osplit, n_ksplit, split_len, ksplit_len;
 };
+
+// Packed layout of the centred data for k_xdot: element (observation i, dimension k) lives in the
+// DMMA m8n8k4 A fragment of (dimension split ks, row pair rp, observation tile, k-step j): lane =
+// (i%8)*4 + k%4 holds the two row tiles of the pair side by side, so one LDS.128 feeds two DMMAs
+// and a (ks, rp) stream over observation tiles is contiguous (one bulk copy per stage).
+DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n_tiles)
+{
+    const int64_t tile = i / SSD_TN;
+    const int r = (int)(i % SSD_TN) / 8, row = (int)(i % 8);
+    const int ks = k / ksplit_len, kl = k % ksplit_len;
+    const int j = kl / 4, lane = row * 4 + (kl % 4);
+    return ((((int64_t)(ks * 4 + (r >> 1)) * n_tiles + tile) * nj + j) * 32 + lane) * 2 + (r & 1);
+}
 
 struct ConfigDev {
     int32_t Np, d, G_local, group_begin, proposal, burnin, n_blocks;
@@ -73,7 +88,11 @@ struct SweepCtx {
     double *prop_prior;       // [P_local]
     double *prop_adj;         // [P_local]
     uint8_t *prop_inb;        // [P_local]
-    double *ll_part;          // [P_local][n_split]
+    double *ll_part;          // [P_local][n_split] partial sums of the pointwise kernels
+    // MVN / hierarchical: the cross term arrives as an order-independent fixed-point sum,
+    // total = ll_acc[p] * ll_q[p] (ll_q NaN: the means are not finite)
+    long long *ll_acc;        // [P_local]
+    double *ll_q;             // [P_local]
     // trace rows of this sweep or NULL
     double *tr_theta, *tr_w, *tr_adj; uint8_t *tr_acc;
 };

@@ -64,7 +64,8 @@ struct demcmc_handle {
     int cur_scratch = 0;                                // current state lives in scratch row k, or
     int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
     // proposal scratch
-    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *ll_part = nullptr;
+    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *ll_part = nullptr, *ll_q = nullptr;
+    long long *ll_acc = nullptr;
     uint8_t *prop_inb = nullptr;
     double *base_th = nullptr, *base_cw = nullptr, *base_tot = nullptr;
     double *d_lo = nullptr, *d_hi = nullptr;
@@ -199,6 +200,8 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->prop_prior = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_inb = (uint8_t *)be::dmalloc(P);
+    h->ll_acc = (long long *)be::dmalloc(sizeof(long long) * P);
+    h->ll_q = (double *)be::dmalloc(sizeof(double) * P);
     h->base_th = (double *)be::dmalloc(sizeof(double) * P);
     h->base_cw = (double *)be::dmalloc(sizeof(double) * P);
     h->base_tot = (double *)be::dmalloc(sizeof(double) * std::max(1, h->G_local));
@@ -206,7 +209,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->d_stage = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
     h->d_stage_recv = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
     bool ok = h->d_lo && h->d_hi && h->d_blocks && h->scr_theta && h->scr_w && h->scr_id && h->scr_acc && h->prop_theta &&
-              h->prop_prior && h->prop_adj && h->prop_inb && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
+              h->prop_prior && h->prop_adj && h->prop_inb && h->ll_acc && h->ll_q && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
     for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
         Upload &u = h->ring[i];
         u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P * MAX_CHUNK);
@@ -240,7 +243,7 @@ int demcmc_destroy(demcmc_handle *h)
     if (h->comm) be::comm_destroy(h->comm);
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
-                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
+                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
                      h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
@@ -305,21 +308,25 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         if (m->kind == DEMCMC_HIER_NORMAL) D.n_obs = (int64_t)m->n_dim * m->n_per;
         D.ssd_ld = (D.ssd_n + SSD_TN - 1) / SSD_TN * SSD_TN;
         if (D.ssd_ld == 0) D.ssd_ld = SSD_TN;
-        double *xT = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k * D.ssd_ld);
+        // dimension splits: balanced, at most SSD_KS dimensions (SSD_NJ DMMA k-steps) each
+        D.n_ksplit = (D.ssd_k + SSD_KS - 1) / SSD_KS;
+        D.ksplit_len = (D.ssd_k + D.n_ksplit - 1) / D.n_ksplit;
+        D.ssd_nj = (D.ksplit_len + 3) / 4;
+        D.n_osplit = 1; D.split_len = (int32_t)std::min<int64_t>(D.ssd_ld, INT32_MAX);
+        // fixed-point bits below the per-particle bound: the sum of one rounded term per
+        // (observation row, dimension split) must stay below 2^62
+        int64_t terms = D.ssd_ld * D.n_ksplit;
+        int lg = 0;
+        while (((int64_t)1 << lg) < terms) ++lg;
+        D.ssd_qbits = std::min(50, 62 - lg);
+        double *xT = (double *)be::dmalloc(sizeof(double) * std::max(be::pack_ssd_doubles(D), (size_t)D.ssd_k * D.ssd_ld));
         double *center = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k);
         if (!xT || !center) return fail(DEMCMC_ENOMEM, "data do not fit on the device");
         h->model_allocs.push_back(xT);
         h->model_allocs.push_back(center);
         D.xT = xT;
         D.center = center;
-        BE(be::launch_pack_ssd(m->x, dev, &D));       // centres the data, fills D.ssd_xx
-        // observation slices: ~4 per SM, whole 64-observation tiles; dimension splits of <= SSD_KS dims
-        const int64_t tiles = D.ssd_ld / SSD_TN;
-        D.ssd_tps = (int32_t)std::max<int64_t>(1, (tiles + SSD_SLICES - 1) / SSD_SLICES);
-        D.split_len = D.ssd_tps * SSD_TN;
-        D.n_osplit = (int32_t)((tiles + D.ssd_tps - 1) / D.ssd_tps);
-        D.ksplit_len = std::min<int32_t>(D.ssd_k, SSD_KS);
-        D.n_ksplit = (D.ssd_k + D.ksplit_len - 1) / D.ksplit_len;
+        BE(be::launch_pack_ssd(m->x, dev, &D));       // centres and packs the data, fills D.ssd_xx / D.ssd_rowmax
     } else {
         D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
         if (!D.x) return fail(DEMCMC_ENOMEM, "data upload failed");
@@ -493,7 +500,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 ctx.t_noise = t_noise + (size_t)s_local * P * d; ctx.t_keep = t_keep ? t_keep + (size_t)s_local * P * d : nullptr;
             }
             ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb;
-            ctx.ll_part = h->ll_part;
+            ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
@@ -533,7 +540,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             BE(be::launch_propose(h->dcfg, h->dmodel, lv));
             const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
             if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
-            BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part));
+            BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc));
             if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
             BE(be::launch_accept(h->dcfg, h->dmodel, lv));
             ++n_levels;
@@ -867,6 +874,14 @@ int demcmc_fp64_peak(int device, double *tflops)
     if (!tflops) return fail(DEMCMC_EINVAL, "null out");
     if (int rc = op_begin(device)) return rc;
     BE(be::fp64_peak(tflops));
+    return 0;
+}
+
+int demcmc_fp64_peaks(int device, double *dfma_tflops, double *dmma_tflops)
+{
+    if (!dfma_tflops && !dmma_tflops) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::fp64_peaks(dfma_tflops, dmma_tflops));
     return 0;
 }
 

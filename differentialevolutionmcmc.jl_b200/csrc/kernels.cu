@@ -3,8 +3,9 @@
 //   k_propose      one warp per particle: DE / snooker / mutation proposal, kappa and block masks,
 //                  bounds, prior, snooker adjustment                       (HBM-bound, ~5 d-vectors)
 //   k_xdot         cross term sum_i sum_k x'_ik m'_pk of the expanded sum of squares for a tile of
-//                  particles against slices of observations: the likelihood of the isotropic MVN
-//                  and the hierarchical normal models                      (fp64-pipe-bound)
+//                  particles against a range of observation tiles, on the fp64 tensor path
+//                  (DMMA m8n8k4): the likelihood of the isotropic MVN and the hierarchical
+//                  normal models                                           (fp64-pipe-bound)
 //   k_ll_pointwise per-observation log densities (Gaussian, LNR, LBA) for a tile of particles
 //   k_accept       one warp per particle: fixed-order reduction of the partial sums, Metropolis
 //                  accept, state-row write (replaces store_samples!)       (HBM-bound)
@@ -16,6 +17,7 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "backend.h"
 #include "de_particle.h"
@@ -159,10 +161,39 @@ __device__ __forceinline__ double kval(const ksum_t &k) { return isfinite(k.s) ?
 // propose / accept: one warp per particle of the level
 // ------------------------------------------------------------------------------------------------
 constexpr int PA_THREADS = 128;
-static double *mT_buffer(size_t doubles);                 // staging of centred means for k_xdot (below)
-static size_t mT_doubles(const ModelDev &m, int n);
 
-__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *mT)
+// per-device staging for k_xdot: the proposals' centred means as DMMA B fragments,
+// bfrag[tile of 32][dimension split][k-step j][octet][lane], and the fixed-point magic constant of
+// every particle of the level, magic[level order]
+struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; };
+static XdStage g_xs[64];
+static XdStage *xd_stage(const ModelDev &m, int n);
+
+// leaves one parameter vector's centred means where k_xdot wants them, together with the particle's
+// fixed-point scale (de_math.h: xd_scale); wi = rank of the particle in the launch
+__device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
+                                            long long *acc, double *q)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = wi / SSD_TP;
+    const int pi = (int)(wi % SSD_TP), pt = pi >> 3, n = pi & 7;
+    double msq = 0.0;
+    for (int k = lane; k < m.ssd_k; k += 32) {
+        const double v = centred_mean(m, theta, k);
+        msq += v * v;
+        const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
+        bfrag[((((size_t)tile * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 4 + pt) * 32 + n * 4 + (kl & 3)] = v;
+    }
+    msq = warp_sum(msq);
+    if (lane == 0) {
+        const XdScale sc = xd_scale(msq, m.ssd_rowmax, m.ssd_qbits);
+        magic[wi] = sc.magic;
+        *q = sc.q;
+        *acc = 0;
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
 {
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) return;
@@ -170,13 +201,9 @@ __global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev 
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     const int p = (int)(e & LV_POS_MASK);
     propose_particle(WarpLanes(), cfg, m, ctx, p);
-    if (mT) {
-        // leave the centred means of this proposal where k_xdot wants them: mT[tile][k][64]
+    if (bfrag) {
         __syncwarp();
-        const double *prop = ctx.prop_theta + (size_t)p * cfg.d;
-        const size_t tile = (size_t)(wi / SSD_TP);
-        const int pi = wi % SSD_TP;
-        for (int k = threadIdx.x & 31; k < m.ssd_k; k += 32) mT[(tile * m.ssd_k + k) * SSD_TP + pi] = centred_mean(m, prop, k);
+        stage_bfrag(m, ctx.prop_theta + (size_t)p * cfg.d, wi, bfrag, magic, ctx.ll_acc + p, ctx.ll_q + p);
     }
 }
 
@@ -192,13 +219,13 @@ __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    double *mT = nullptr;
+    XdStage *xs = nullptr;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
         // sized once for the handle's whole population so it never grows inside a run
-        mT = mT_buffer(mT_doubles(m, std::max(lv.n, cfg.G_local * cfg.Np)));
-        if (!mT) return -1;
+        xs = xd_stage(m, std::max(lv.n, cfg.G_local * cfg.Np));
+        if (!xs) return -1;
     }
-    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv, mT);
+    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr);
     LAUNCHED("k_propose");
     return 0;
 }
@@ -308,27 +335,34 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 // ------------------------------------------------------------------------------------------------
 // MVN / hierarchical likelihood kernel.  With centred data x' and centred means m',
 //   sum_i sum_k (x_ik - m_pk)^2 = sum x'^2 - 2 B_p + n sum_k m'_pk^2,   B_p = sum_i sum_k x'_ik m'_pk
-// and only B_p needs the O(N d) pass: ONE DFMA per (observation, dimension, particle), every
-// observation streamed for every particle (no sufficient-statistic shortcut).  Zero padding
-// contributes nothing to B, so there is no ragged-tile path.
+// and only B_p needs the O(N d) pass: one multiply-add per (observation, dimension, particle), every
+// observation streamed for every particle (no sufficient-statistic shortcut).
 //
-// CTA = 128 threads, tile 64 particles x 64 observations, thread tile 4 particles x 8 observations
-// (32 independent DFMA chains).  The proposal kernel leaves the centred means of every particle
-// tile of the level in the layout this kernel wants (mT[tile][k][64]); one TMA bulk copy brings
-// them to shared memory where they stay resident, while observation tiles stream through a
-// 3-stage ring of [32 dims][64 obs] filled by TMA bulk copies (cp.async.bulk, one 512 B row per
-// lane of warp 0) that complete on per-stage mbarriers; consumer warps release a stage through an
-// "empty" mbarrier, so there is no CTA-wide barrier and no address arithmetic in the inner loop.  Shared-memory reads are conflict-free: the 8 lanes of an
-// observation group read one contiguous 128 B row segment (the 4 particle groups of the warp
-// broadcast), the 4 particle groups read 4 x 32 B of one mean row.
-// The launch is ONE wave: every (particle tile, dimension split) gets C = slots / items CTAs, each
-// taking a contiguous, balanced range of observation SLICES and writing one partial per slice, so
-// the set of partial sums (and the summation order) is fixed by the model alone, independent of
-// the level size and of the GPU count.
+// B = X' M is a GEMM whose rows are summed away, so it runs on the fp64 tensor path: DMMA m8n8k4
+// measures 37.1 TFLOP/s on B200 against 33.9 for DFMA (scripts/probes/probe_dmma.cu; the two share
+// one pipe, they do not add), and it needs 8x fewer issue slots and no accumulator tile.
+//   A (8 observations x 4 dimensions)  = packed centred data, streamed
+//   B (4 dimensions x 8 particles)     = centred means of one particle octet, held in REGISTERS for
+//                                        the whole kernel (<= 13 k-steps x 4 octets per thread)
+//   C (8 observations x 8 particles)   = per-row cross terms; a row's chain runs over the k-steps
+//                                        of ONE observation tile, then is rounded to the
+//                                        particle's fixed-point grid (de_math.h: xd_scale) and added
+//                                        as an integer, which makes the total independent of how
+//                                        observation tiles were dealt to CTAs
+// CTA = 4 warps x one particle tile (32 particles = 4 octets).  Warp w owns row pair w (16 of the 64
+// observations) of every observation tile in the CTA's range: its operand stream is contiguous in
+// the packed layout, so each warp runs a PRIVATE 4-stage ring of TMA bulk copies (cp.async.bulk,
+// one copy per stage, completing on the warp's own mbarriers) and the kernel has no CTA-wide
+// barrier and no cross-warp wait at all.  Inner step: one LDS.128 (A fragments of two row tiles)
+// feeds 8 DMMAs (2 row tiles x 4 octets), 8 independent accumulator chains per warp.
+// The launch is one wave: CTAs are dealt to particle tiles in proportion to their octets (the last
+// tile of a level may hold 1..4), each taking a balanced contiguous range of observation tiles;
+// padding costs at most 7 particles per level.
 // ------------------------------------------------------------------------------------------------
 constexpr int XD_THREADS = 128;
-constexpr int XD_STAGES = 3;
-constexpr int XD_CTAS_PER_SM = 3;
+constexpr int XD_STAGES = 4;
+constexpr int XD_CTAS_PER_SM = 2;
+constexpr int XD_MIN_TILES = 8;          // observation tiles a CTA should at least stream (amortises its prologue)
 
 // ---- TMA bulk copy + mbarrier helpers (sm_90+; SASS: UBLKCP / SYNCS) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -339,10 +373,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
@@ -362,146 +392,165 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-
-static size_t xdot_smem_bytes(int klen)
+// D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor path (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    return sizeof(double) * ((size_t)klen * SSD_TP + (size_t)XD_STAGES * SSD_KC * SSD_TN) + sizeof(int) * SSD_TP +
-           sizeof(uint64_t) * (2 * XD_STAGES + 1);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// staging buffer of centred means, [tile][ssd_k][64], one per device, grown on demand
-static double *g_mT[64] = { nullptr };
-static size_t g_mT_cap[64] = { 0 };
-static double *mT_buffer(size_t doubles)
+static size_t xdot_smem_bytes(int nj)
 {
-    if (doubles > g_mT_cap[g_dev]) {
+    return (size_t)4 * XD_STAGES * nj * 64 * sizeof(double) + sizeof(uint64_t) * 4 * XD_STAGES;
+}
+
+static size_t xd_bfrag_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_TP - 1) / SSD_TP) * m.n_ksplit * m.ssd_nj * 4 * 32; }
+static XdStage *xd_stage(const ModelDev &m, int n)
+{
+    XdStage &x = g_xs[g_dev];
+    const size_t need = xd_bfrag_doubles(m, n) + (size_t)((n + SSD_TP - 1) / SSD_TP) * SSD_TP;
+    if (need > x.cap) {
         cudaStreamSynchronize(stream());
-        if (g_mT[g_dev]) cudaFree(g_mT[g_dev]);
-        g_mT[g_dev] = nullptr; g_mT_cap[g_dev] = 0;
-        if (cudaMalloc(&g_mT[g_dev], sizeof(double) * doubles) != cudaSuccess) { g_be_err = "cudaMalloc(mean staging)"; return nullptr; }
-        g_mT_cap[g_dev] = doubles;
+        if (x.bfrag) cudaFree(x.bfrag);
+        x.bfrag = nullptr; x.magic = nullptr; x.cap = 0;
+        if (cudaMalloc(&x.bfrag, sizeof(double) * need) != cudaSuccess) { g_be_err = "cudaMalloc(mean staging)"; return nullptr; }
+        x.cap = need;
     }
-    return g_mT[g_dev];
+    // the dimension slots that pad a split to whole k-steps must read as zero, and the geometry may
+    // change with the model: clear whenever the split between the two arrays moves
+    double *magic = x.bfrag + (x.cap - (size_t)((n + SSD_TP - 1) / SSD_TP) * SSD_TP);
+    if (magic != x.magic) {
+        if (cudaMemsetAsync(x.bfrag, 0, sizeof(double) * x.cap, stream()) != cudaSuccess) { g_be_err = "cudaMemset(mean staging)"; return nullptr; }
+        x.magic = magic;
+    }
+    return &x;
 }
-static size_t mT_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_TP - 1) / SSD_TP) * m.ssd_k * SSD_TP; }
 
-__global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *mT, Level lv, double *part, int C)
+// how the CTAs of one launch are dealt to the particle tiles of a level
+struct XdGrid { int32_t n_full, c_full, c_last, oct_last; };
+
+template <int NOCT>
+__device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
+                                          long long *ll_acc, int tile, int T0, int T1, unsigned char *smem_raw)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ks = blockIdx.y;
+    const int nj = m.ssd_nj;
+    const int n_tiles = (int)(m.ssd_ld / SSD_TN);
+    const uint32_t stage_doubles = (uint32_t)nj * 64, stage_bytes = stage_doubles * (uint32_t)sizeof(double);
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
+    const double *src = m.xT + (((size_t)(ks * 4 + warp) * n_tiles + T0) * nj) * 64;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < XD_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < XD_STAGES; ++s)
+            if (T0 + s < T1) {
+                mbar_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(ring + (size_t)s * stage_doubles, src + (size_t)s * stage_doubles, stage_bytes, &full[s]);
+            }
+    }
+    __syncwarp();
+
+    // this tile's centred means as B fragments, and the particles' fixed-point constants
+    double b[SSD_NJ][NOCT];
+    {
+        const double *bf = bfrag + (((size_t)tile * m.n_ksplit + ks) * nj * 4) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < SSD_NJ; ++j)
+#pragma unroll
+            for (int pt = 0; pt < NOCT; ++pt) b[j][pt] = j < nj ? bf[(j * 4 + pt) * 32] : 0.0;
+    }
+    double mg[NOCT][2];
+    unsigned long long isum[NOCT][2];
+    double acc[2][NOCT][2];
+#pragma unroll
+    for (int pt = 0; pt < NOCT; ++pt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            mg[pt][e] = magic[(size_t)tile * SSD_TP + pt * 8 + 2 * (lane & 3) + e];
+            isum[pt][e] = 0ull;
+            acc[0][pt][e] = 0.0; acc[1][pt][e] = 0.0;
+        }
+
+    for (int t = T0; t < T1; ++t) {
+        const int it = t - T0, st = it & (XD_STAGES - 1);
+        mbar_wait(&full[st], (uint32_t)(it / XD_STAGES) & 1u);
+        const double2 *xa = reinterpret_cast<const double2 *>(ring + (size_t)st * stage_doubles) + lane;
+        double2 a = xa[0];
+#pragma unroll
+        for (int j = 0; j < SSD_NJ; ++j) {
+            if (j >= nj) break;
+            double2 an = a;
+            if (j + 1 < nj) an = xa[(j + 1) * 32];
+#pragma unroll
+            for (int pt = 0; pt < NOCT; ++pt) {
+                dmma884(acc[0][pt][0], acc[0][pt][1], a.x, b[j][pt]);
+                dmma884(acc[1][pt][0], acc[1][pt][1], a.y, b[j][pt]);
+            }
+            a = an;
+        }
+        __syncwarp();                                        // every lane's reads of the stage have landed
+        if (lane == 0 && t + XD_STAGES < T1) {
+            mbar_expect_tx(&full[st], stage_bytes);
+            bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + XD_STAGES) * stage_doubles, stage_bytes, &full[st]);
+        }
+        // the rows' chains end with the observation tile: round to the particle's grid, add as integers
+#pragma unroll
+        for (int pt = 0; pt < NOCT; ++pt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[0][pt][e], mg[pt][e]));
+                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[1][pt][e], mg[pt][e]));
+                acc[0][pt][e] = 0.0; acc[1][pt][e] = 0.0;
+            }
+    }
+
+    // remove the magic offsets (two conversions per observation tile), sum the 8 rows held by the
+    // lanes of each column group, and add the CTA's share to the particles' accumulators
+    const unsigned long long n_conv = 2ull * (unsigned long long)(T1 - T0);
+#pragma unroll
+    for (int pt = 0; pt < NOCT; ++pt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            unsigned long long v = isum[pt][e] - n_conv * (unsigned long long)xd_bits(mg[pt][e]);
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int idx = tile * SSD_TP + pt * 8 + 2 * lane + e;
+            if (lane < 4 && idx < lv.n) {
+                const int p = lv.order ? (int)((uint32_t)lv.order[idx] & LV_POS_MASK) : idx;
+                atomicAdd(reinterpret_cast<unsigned long long *>(ll_acc) + p, v);
+            }
+        }
+}
+
+__global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
+                                                                     long long *ll_acc, XdGrid g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x, to = tid & 7, tp = tid >> 3, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x / C, c_in = blockIdx.x - tile * C, ksplit = blockIdx.y;
-    const int k_begin = ksplit * m.ksplit_len, k_end = min(m.ssd_k, k_begin + m.ksplit_len), klen = k_end - k_begin;
-    double *ms = reinterpret_cast<double *>(smem_raw);                 // [klen][64] centred means
-    double *xs = ms + (size_t)m.ksplit_len * SSD_TP;                   // [XD_STAGES][SSD_KC][SSD_TN]
-    int *s_p = reinterpret_cast<int *>(xs + XD_STAGES * SSD_KC * SSD_TN);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_p + SSD_TP);       // full[STAGES], empty[STAGES], means
-    uint64_t *full = bars, *empty = bars + XD_STAGES, *bar_ms = bars + 2 * XD_STAGES;
-    const int nt = min(SSD_TP, lv.n - tile * SSD_TP);
-    const int n_split = m.n_osplit * m.n_ksplit;
-    const int n_tiles = (int)(m.ssd_ld / SSD_TN), tps = m.ssd_tps;
-    const int slice0 = (int)((int64_t)c_in * m.n_osplit / C), slice1 = (int)((int64_t)(c_in + 1) * m.n_osplit / C);
-    const int T0 = slice0 * tps, T1 = min(n_tiles, slice1 * tps);
-    const int n_kc = (klen + SSD_KC - 1) / SSD_KC;
-    const int n_steps = (T1 - T0) * n_kc;
-    if (n_steps <= 0) return;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < XD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], XD_THREADS / 32); }
-        mbar_init(bar_ms, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (tid < SSD_TP) s_p[tid] = tid < nt ? (lv.order ? (int)((uint32_t)lv.order[tile * SSD_TP + tid] & LV_POS_MASK) : tile * SSD_TP + tid) : -1;
-    __syncthreads();
-
-    // producer = warp 0: one bulk copy per row of the stage ([kc] rows of 64 observations = 512 B)
-    auto produce = [&](int q) {
-        if (q >= n_steps) return;
-        const int st = q % XD_STAGES, use = q / XD_STAGES;
-        mbar_wait(&empty[st], (use & 1) ^ 1);               // every warp released the previous use of the stage
-        const int tt = T0 + q / n_kc, c = q - (q / n_kc) * n_kc;
-        const int kc = min(SSD_KC, klen - c * SSD_KC);
-        if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)(kc * SSD_TN * sizeof(double)));
-        __syncwarp();
-        if (lane < kc)
-            bulk_g2s(xs + ((size_t)st * SSD_KC + lane) * SSD_TN,
-                     m.xT + (size_t)(k_begin + c * SSD_KC + lane) * m.ssd_ld + (size_t)tt * SSD_TN, SSD_TN * sizeof(double), &full[st]);
-    };
-    if (warp == 0) {
-        if (lane == 0) {                                    // the tile's [klen][64] block of centred means
-            mbar_expect_tx(bar_ms, (uint32_t)(klen * SSD_TP * sizeof(double)));
-            bulk_g2s(ms, mT + ((size_t)tile * m.ssd_k + k_begin) * SSD_TP, (uint32_t)(klen * SSD_TP * sizeof(double)), bar_ms);
-        }
-        produce(0);
-        produce(1);
-    }
-
-    double acc[4][8];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-
-    mbar_wait(bar_ms, 0);
-    int tt = T0, c = 0;                                      // (observation tile, dimension chunk) of step q
-    for (int q = 0; q < n_steps; ++q) {
-        const int st = q % XD_STAGES;
-        if (warp == 0) produce(q + 2);
-        mbar_wait(&full[st], (q / XD_STAGES) & 1);
-        const int kc = min(SSD_KC, klen - c * SSD_KC);
-        const double *xb = xs + (size_t)st * SSD_KC * SSD_TN + to * 2;
-        const double *mb = ms + (size_t)(c * SSD_KC) * SSD_TP + tp * 4;
-#pragma unroll 4
-        for (int kk = 0; kk < kc; ++kk) {
-            const double2 x0 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN);
-            const double2 x1 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 16);
-            const double2 x2 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 32);
-            const double2 x3 = *reinterpret_cast<const double2 *>(xb + kk * SSD_TN + 48);
-            const double2 m0 = *reinterpret_cast<const double2 *>(mb + kk * SSD_TP);
-            const double2 m1 = *reinterpret_cast<const double2 *>(mb + kk * SSD_TP + 2);
-            const double xv[8] = { x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y };
-            const double mv[4] = { m0.x, m0.y, m1.x, m1.y };
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = fma(xv[b], mv[a], acc[a][b]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done reading the stage
-        // end of a slice: reduce the 8 observation columns and the 8 lanes of the particle group,
-        // write the slice's partial, restart the accumulators
-        if (c == n_kc - 1) {
-            if ((tt + 1) % tps == 0 || tt + 1 == T1) {
-                const int slice = tt / tps;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    double v = ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3])) + ((acc[a][4] + acc[a][5]) + (acc[a][6] + acc[a][7]));
-#pragma unroll
-                    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (to == 0) {
-                        const int p = s_p[tp * 4 + a];
-                        if (p >= 0) part[(size_t)p * n_split + (size_t)slice * m.n_ksplit + ksplit] = v;
-                    }
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-                }
-            }
-            c = 0; ++tt;
-        } else {
-            ++c;
-        }
+    int tile, c_in, C, noct;
+    const int n_in_full = g.n_full * g.c_full;
+    if ((int)blockIdx.x < n_in_full) { tile = blockIdx.x / g.c_full; c_in = blockIdx.x - tile * g.c_full; C = g.c_full; noct = 4; }
+    else { tile = g.n_full; c_in = blockIdx.x - n_in_full; C = g.c_last; noct = g.oct_last; }
+    const int n_tiles = (int)(m.ssd_ld / SSD_TN);
+    const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
+    if (T1 <= T0) return;
+    switch (noct) {
+    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
+    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
+    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
+    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
     }
 }
 
 // centred means of arbitrary parameter vectors in the k_xdot layout (demcmc_eval, initial weights)
-__global__ void __launch_bounds__(PA_THREADS) k_stage_means(ModelDev m, const double *theta, int64_t n, double *mT)
+__global__ void __launch_bounds__(PA_THREADS) k_stage_means(ModelDev m, const double *theta, int64_t n, double *bfrag, double *magic,
+                                                            long long *acc, double *q)
 {
     const int64_t wi = ((int64_t)blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= n) return;
-    const double *th = theta + (size_t)wi * m.d;
-    const size_t tile = (size_t)(wi / SSD_TP);
-    const int pi = (int)(wi % SSD_TP);
-    for (int k = threadIdx.x & 31; k < m.ssd_k; k += 32) mT[(tile * m.ssd_k + k) * SSD_TP + pi] = centred_mean(m, th, k);
+    stage_bfrag(m, theta + (size_t)wi * m.d, wi, bfrag, magic, acc + wi, q + wi);
 }
 
 static int n_sms()
@@ -511,32 +560,61 @@ static int n_sms()
     return sms[g_dev] > 0 ? sms[g_dev] : 148;
 }
 
-static int launch_xdot(const ModelDev &m, const double *mT, const Level &lv, double *ll_part)
+// deals the resident CTA slots of one wave to the particle tiles of a level in proportion to
+// their octets; when there are more tiles than slots, picks the split that fills whole waves best
+static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
+{
+    XdGrid g;
+    const int n32 = (n + SSD_TP - 1) / SSD_TP;
+    const int rem = n - (n32 - 1) * SSD_TP;                        // particles in the last tile, 1..32
+    g.oct_last = (rem + SSD_OCT - 1) / SSD_OCT;
+    g.n_full = g.oct_last == 4 ? n32 : n32 - 1;
+    if (g.oct_last == 4) g.oct_last = 0;
+    const int n_tiles = (int)(m.ssd_ld / SSD_TN);
+    const int c_max = std::max(1, n_tiles / XD_MIN_TILES);
+    const int per_split = std::max(1, slots / std::max(1, m.n_ksplit));
+    const int octets = 4 * g.n_full + g.oct_last;
+    if (octets <= 4 * per_split) {                                 // one wave
+        g.c_full = std::min(c_max, std::max(1, 4 * per_split / octets));
+        g.c_last = g.oct_last ? std::min(c_max, std::max(1, (g.oct_last * per_split + octets / 2) / octets)) : 0;
+        // spend what the rounding left over
+        while (g.n_full && g.c_full < c_max && g.n_full * (g.c_full + 1) + g.c_last <= per_split) ++g.c_full;
+    } else {                                                       // several waves: fill them
+        int best = 1; double best_eff = 0.0;
+        for (int c = 1; c <= std::min(c_max, 16); ++c) {
+            const double ctas = (double)(g.n_full + (g.oct_last ? 1 : 0)) * c;
+            const double eff = ctas / (ceil(ctas / per_split) * per_split);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+        }
+        g.c_full = best; g.c_last = g.oct_last ? best : 0;
+    }
+    return g;
+}
+
+static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, long long *ll_acc)
 {
     static bool attr_set[64] = { false };
-    const size_t smem = xdot_smem_bytes(m.ksplit_len);
+    const size_t smem = xdot_smem_bytes(m.ssd_nj);
     if (!attr_set[g_dev]) {
-        CU(cudaFuncSetAttribute(k_xdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_KS)));
+        CU(cudaFuncSetAttribute(k_xdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_NJ)));
         attr_set[g_dev] = true;
     }
-    const int n_pt = (lv.n + SSD_TP - 1) / SSD_TP;
-    const int64_t items = (int64_t)n_pt * m.n_ksplit, slots = (int64_t)XD_CTAS_PER_SM * n_sms();
-    int C = (int)(slots / items);
-    C = C < 1 ? 1 : (C > m.n_osplit ? m.n_osplit : C);
-    dim3 grid((unsigned)(n_pt * C), (unsigned)m.n_ksplit);
-    k_xdot<<<grid, XD_THREADS, smem, stream()>>>(m, mT, lv, ll_part, C);
+    const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
+    dim3 grid((unsigned)(g.n_full * g.c_full + g.c_last), (unsigned)m.n_ksplit);
+    k_xdot<<<grid, XD_THREADS, smem, stream()>>>(m, xs.bfrag, xs.magic, lv, ll_acc, g);
     LAUNCHED("k_xdot");
     return 0;
 }
 
-int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part)
+int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc)
 {
     (void)cfg;
     if (lv.n <= 0 || m.kind == M_BINOMIAL) return 0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
-        // the proposal kernel of this level has staged the centred means
-        if (!g_mT[g_dev] || g_mT_cap[g_dev] < mT_doubles(m, lv.n)) { g_be_err = "mean staging buffer missing"; return -1; }
-        return launch_xdot(m, g_mT[g_dev], lv, ll_part);
+        // the proposal kernel of this level has staged the centred means and cleared the accumulators
+        const XdStage &xs = g_xs[g_dev];
+        if (!xs.bfrag || !xs.magic) { g_be_err = "mean staging buffer missing"; return -1; }
+        return launch_xdot(m, xs, lv, ll_acc);
     }
     dim3 grid((lv.n + PW_TP - 1) / PW_TP, m.n_osplit);
     if (m.kind == M_GAUSSIAN) k_ll_pointwise<M_GAUSSIAN><<<grid, PW_THREADS, 0, stream()>>>(m, theta, lv, ll_part);
@@ -549,8 +627,8 @@ int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, 
 
 // ------------------------------------------------------------------------------------------------
 // data packing for k_xdot: x[n][k] (MVN, observation-major) or y[k][n] (hierarchical,
-// subject-major) -> centred xT[k][ld] zero padded, center[k], and sum of the squared centred data.
-// One block per dimension, fixed reduction order (deterministic).
+// subject-major) -> center[k], then the centred data as DMMA A fragments (de_types.h:
+// ssd_pack_index), zero padded; also sum x'^2 and max_i |x'_i|.  Fixed reduction order.
 // ------------------------------------------------------------------------------------------------
 __device__ double block_sum_256(double v, double *red)
 {
@@ -565,49 +643,78 @@ __device__ double block_sum_256(double v, double *red)
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_pack_center(const double *x, double *xT, double *center, double *colsq, int64_t n, int k,
-                                                     int64_t ld, int obs_major)
+__global__ void __launch_bounds__(256) k_col_center(const double *x, double *center, int64_t n, int k, int obs_major)
 {
     __shared__ double red[9];
     const int kk = blockIdx.x;
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += 256) s += obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i];
     const double c = n > 0 ? block_sum_256(s, red) / (double)n : 0.0;
-    double q = 0.0;
-    for (int64_t i = threadIdx.x; i < ld; i += 256) {
-        double v = 0.0;
-        if (i < n) { v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - c; q += v * v; }
-        xT[(int64_t)kk * ld + i] = v;
-    }
-    q = block_sum_256(q, red);
-    if (threadIdx.x == 0) { center[kk] = c; colsq[kk] = q; }
+    if (threadIdx.x == 0) center[kk] = c;
 }
+
+// one thread per observation: writes its centred row into the packed layout; per block the sum and
+// the maximum of the squared row norms
+__global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double *center, double *xp, double *blk_sq, double *blk_max,
+                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major)
+{
+    __shared__ double red[9];
+    __shared__ double redm[8];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double q = 0.0;
+    if (i < n)
+        for (int kk = 0; kk < k; ++kk) {
+            const double v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - center[kk];
+            q += v * v;
+            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles)] = v;
+        }
+    double mx = q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = mx;
+    const double s = block_sum_256(q, red);
+    if (threadIdx.x == 0) {
+        double mm = redm[0];
+        for (int w = 1; w < 8; ++w) mm = fmax(mm, redm[w]);
+        blk_sq[blockIdx.x] = s;
+        blk_max[blockIdx.x] = mm;
+    }
+}
+
+size_t pack_ssd_doubles(const ModelDev &m) { return (size_t)m.n_ksplit * (size_t)(m.ssd_ld / SSD_TN) * m.ssd_nj * 256; }
 
 int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
 {
     const size_t bytes = sizeof(double) * (size_t)m->ssd_n * m->ssd_k;
+    const int n_blk = (int)std::max<int64_t>(1, (m->ssd_n + 255) / 256);
     const double *src = x_in;
-    double *tmp = nullptr, *colsq = (double *)dmalloc(sizeof(double) * m->ssd_k);
-    if (!colsq) return -1;
+    double *tmp = nullptr, *blk = (double *)dmalloc(sizeof(double) * 2 * n_blk);
+    if (!blk) return -1;
     if (!in_on_device) {
         tmp = (double *)dmalloc(bytes);
-        if (!tmp) { dfree(colsq); return -1; }
-        if (h2d(tmp, x_in, bytes)) { dfree(tmp); dfree(colsq); return -1; }
+        if (!tmp) { dfree(blk); return -1; }
+        if (h2d(tmp, x_in, bytes)) { dfree(tmp); dfree(blk); return -1; }
         src = tmp;
     }
-    k_pack_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->xT), const_cast<double *>(m->center), colsq, m->ssd_n,
-                                                  m->ssd_k, m->ssd_ld, m->kind == M_MVNORMAL ? 1 : 0);
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    double *h = new double[m->ssd_k];
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, colsq, sizeof(double) * m->ssd_k, cudaMemcpyDeviceToHost, stream());
+    const int obs_major = m->kind == M_MVNORMAL ? 1 : 0;
+    cudaError_t e = cudaMemsetAsync(const_cast<double *>(m->xT), 0, sizeof(double) * pack_ssd_doubles(*m), stream());
+    if (e == cudaSuccess) e = cudaMemsetAsync(blk, 0, sizeof(double) * 2 * n_blk, stream());
+    if (e == cudaSuccess) {
+        k_col_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->center), m->ssd_n, m->ssd_k, obs_major);
+        k_pack_rows<<<n_blk, 256, 0, stream()>>>(src, m->center, const_cast<double *>(m->xT), blk, blk + n_blk, m->ssd_n, m->ssd_k,
+                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major);
+        g_launches += 2;
+        e = cudaGetLastError();
+    }
+    std::vector<double> h(2 * (size_t)n_blk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), blk, sizeof(double) * 2 * n_blk, cudaMemcpyDeviceToHost, stream());
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
-    double xx = 0.0;
-    for (int k = 0; k < m->ssd_k; ++k) xx += h[k];
+    double xx = 0.0, mx = 0.0;
+    for (int b = 0; b < n_blk; ++b) { xx += h[b]; mx = std::max(mx, h[n_blk + b]); }
     m->ssd_xx = xx;
-    delete[] h;
-    dfree(tmp); dfree(colsq);
-    if (e != cudaSuccess) return cu_fail(e, "k_pack_center");
+    m->ssd_rowmax = sqrt(mx);
+    dfree(tmp); dfree(blk);
+    if (e != cudaSuccess) return cu_fail(e, "k_pack_rows");
     return 0;
 }
 
@@ -615,7 +722,8 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
 // evaluation of arbitrary parameter vectors (init_particle weights, demcmc_eval)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, ModelDev m, const double *theta, int64_t n,
-                                                             const double *part, double *ll, double *prior, double *w)
+                                                             const double *part, const long long *acc, const double *q,
+                                                             double *ll, double *prior, double *w)
 {
     const int64_t wi = ((int64_t)blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= n) return;
@@ -625,8 +733,11 @@ __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, Model
     bounds_and_prior(co, cfg, m, th, inb, pr);
     const int n_split = m.n_osplit * m.n_ksplit;
     double s = 0.0;
-    if (m.kind != M_BINOMIAL) for (int q = co.lane(); q < n_split; q += 32) s += part[(size_t)wi * n_split + q];
-    s = co.sum(s);
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER) s = (double)acc[wi] * q[wi];
+    else {
+        if (m.kind != M_BINOMIAL) for (int c = co.lane(); c < n_split; c += 32) s += part[(size_t)wi * n_split + c];
+        s = co.sum(s);
+    }
     const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
     if (co.lane() == 0) {
         if (ll) ll[wi] = l;
@@ -641,15 +752,21 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
     if (n <= 0) return 0;
     Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
     const int blocks = (int)((n * 32 + PA_THREADS - 1) / PA_THREADS);
+    long long *acc = nullptr;
+    double *q = nullptr;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
-        double *mT = mT_buffer(mT_doubles(m, (int)n));
-        if (!mT) return -1;
-        k_stage_means<<<blocks, PA_THREADS, 0, stream()>>>(m, theta, n, mT);
+        XdStage *xs = xd_stage(m, (int)n);
+        if (!xs) return -1;
+        acc = (long long *)dmalloc(sizeof(long long) * n);
+        q = (double *)dmalloc(sizeof(double) * n);
+        if (!acc || !q) { dfree(acc); dfree(q); return -1; }
+        k_stage_means<<<blocks, PA_THREADS, 0, stream()>>>(m, theta, n, xs->bfrag, xs->magic, acc, q);
         LAUNCHED("k_stage_means");
-        if (launch_xdot(m, mT, lv, scratch_part)) return -1;
-    } else if (launch_loglik(cfg, m, theta, lv, scratch_part)) return -1;
-    k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, ll, prior, w);
+        if (launch_xdot(m, *xs, lv, acc)) { dfree(acc); dfree(q); return -1; }
+    } else if (launch_loglik(cfg, m, theta, lv, scratch_part, nullptr)) return -1;
+    k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, acc, q, ll, prior, w);
     LAUNCHED("k_eval_finish");
+    if (acc) { cudaStreamSynchronize(stream()); dfree(acc); dfree(q); }
     return 0;
 }
 
@@ -881,7 +998,24 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
     if (s == 123.456) out[0] = s;
 }
 
-int fp64_peak(double *tflops)
+// the fp64 tensor path: 8 independent DMMA m8n8k4 chains per warp
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters, double a, double b)
+{
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[2 * i], c[2 * i + 1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// DFMA loop and DMMA loop, best of 5 timed repetitions each, TFLOP/s
+int fp64_peaks(double *dfma_tflops, double *dmma_tflops)
 {
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_dev));
@@ -889,22 +1023,35 @@ int fp64_peak(double *tflops)
     if (!out) return -1;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    const int iters = 1 << 14, blocks = sms * 8;
-    double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {
-        CU(cudaEventRecord(e0, stream()));
-        k_dfma_peak<<<blocks, 256, 0, stream()>>>(out, iters, 0.999999, 1e-9);
-        ++g_launches;
-        CU(cudaEventRecord(e1, stream()));
-        CU(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, e0, e1));
-        const double fl = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
-        if (rep > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
-    }
+    const int blocks = sms * 8;
+    double best[2] = { 0.0, 0.0 };
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 6; ++rep) {
+            const int iters = which == 0 ? 1 << 14 : 1 << 12;
+            CU(cudaEventRecord(e0, stream()));
+            if (which == 0) k_dfma_peak<<<blocks, 256, 0, stream()>>>(out, iters, 0.999999, 1e-9);
+            else k_dmma_peak<<<blocks, 256, 0, stream()>>>(out, iters, 0.999999, 1e-9);
+            ++g_launches;
+            CU(cudaEventRecord(e1, stream()));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            const double fl = which == 0 ? 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks
+                                         : 8.0 * 512.0 * (double)iters * 8.0 * (double)blocks;
+            if (rep > 0) best[which] = fmax(best[which], fl / (ms * 1e-3) / 1e12);
+        }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     dfree(out);
-    *tflops = best;
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
+    return 0;
+}
+
+int fp64_peak(double *tflops)
+{
+    double a = 0.0, b = 0.0;
+    if (fp64_peaks(&a, &b)) return -1;
+    *tflops = fmax(a, b);
     return 0;
 }
 

@@ -263,6 +263,13 @@ def fp64_peak(device=0):
     return float(v[0])
 
 
+def fp64_peaks(device=0):
+    """(DFMA loop, DMMA m8n8k4 loop) in TFLOP/s; one pipe on B200, the larger is the roofline."""
+    a, b = np.zeros(1), np.zeros(1)
+    check(_ffi.lib().demcmc_fp64_peaks(device, ptr(a, _dp), ptr(b, _dp)))
+    return float(a[0]), float(b[0])
+
+
 def copy_peak(device=0):
     v = np.zeros(1)
     check(_ffi.lib().demcmc_copy_peak(device, ptr(v, _dp)))

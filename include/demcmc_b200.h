@@ -194,6 +194,9 @@ int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int3
 /* fp64 FMA peak of the device in TFLOP/s (DFMA microbenchmark; the roofline denominator that
  * MEASURED_PEAKS.json does not carry) and a copy-bandwidth probe in GB/s */
 int demcmc_fp64_peak(int device, double *tflops);
+/* both fp64 paths separately: the DFMA (CUDA-core) loop and the DMMA m8n8k4 (tensor) loop; they
+ * share one pipe on B200 (scripts/probes/probe_dmma.cu), demcmc_fp64_peak returns the larger */
+int demcmc_fp64_peaks(int device, double *dfma_tflops, double *dmma_tflops);
 int demcmc_copy_peak(int device, double *gbs);
 
 #ifdef __cplusplus

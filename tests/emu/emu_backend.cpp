@@ -60,6 +60,8 @@ static void kadd(ksum_t &k, double x)
 }
 static double kval(const ksum_t &k) { return isfinite(k.s) ? k.s + k.c : k.s; }
 
+size_t pack_ssd_doubles(const ModelDev &m) { return (size_t)m.ssd_k * (size_t)m.ssd_ld; }
+
 int launch_pack_ssd(const double *x, int, ModelDev *m)
 {
     ++g_launches;
@@ -80,11 +82,13 @@ int launch_pack_ssd(const double *x, int, ModelDev *m)
         xx += q;
     }
     m->ssd_xx = xx;
+    m->ssd_rowmax = 0.0;                      // the fixed-point scale is a CUDA-kernel detail
     return 0;
 }
 
 // contract of k_xdot / k_ll_pointwise: part[p][split] for every particle of the level
-int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, const Level &lv, double *part)
+// (MVN / hierarchical: the cross term is handed over as ll_acc = 1, ll_q = the sum)
+static int loglik_impl(const ModelDev &m, const double *theta, const Level &lv, double *part)
 {
     ++g_launches;
     if (m.kind == M_BINOMIAL) return 0;
@@ -131,10 +135,28 @@ int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, con
     return 0;
 }
 
+int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, const Level &lv, double *part, long long *)
+{
+    if (loglik_impl(m, theta, lv, part)) return -1;
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+        const int n_split = m.n_osplit * m.n_ksplit;
+        for (int q = 0; q < lv.n; ++q) {
+            const uint32_t e = (uint32_t)lv.order[q];
+            const SweepCtx &ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+            const int p = (int)(e & LV_POS_MASK);
+            double s = 0.0;
+            for (int c = 0; c < n_split; ++c) s += part[(size_t)p * n_split + c];
+            ctx.ll_acc[p] = 1;
+            ctx.ll_q[p] = s;
+        }
+    }
+    return 0;
+}
+
 int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior, double *w, double *part)
 {
     Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
-    launch_loglik(cfg, m, theta, lv, part);
+    loglik_impl(m, theta, lv, part);
     ++g_launches;
     const SerialLanes co;
     const int n_split = m.n_osplit * m.n_ksplit;
@@ -326,6 +348,7 @@ int launch_op_select(const double *w, int n, double u, int32_t *base_idx, int32_
     return 0;
 }
 int fp64_peak(double *t) { *t = 0.0; return 0; }
+int fp64_peaks(double *a, double *b) { if (a) *a = 0.0; if (b) *b = 0.0; return 0; }
 int copy_peak(double *g) { *g = 0.0; return 0; }
 
 int comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return 0; }
