@@ -163,7 +163,7 @@ __device__ __forceinline__ double kval(const ksum_t &k) { return isfinite(k.s) ?
 constexpr int PA_THREADS = 128;
 
 // per-device staging for k_xdot: the proposals' centred means as DMMA B fragments,
-// bfrag[tile of 32][dimension split][k-step j][octet][lane], and the fixed-point magic constant of
+// bfrag[octet of the level][dimension split][k-step j][lane], and the fixed-point magic constant of
 // every particle of the level, magic[level order]
 struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; };
 static XdStage g_xs[64];
@@ -175,14 +175,14 @@ __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *the
                                             long long *acc, double *q)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t tile = wi / SSD_TP;
-    const int pi = (int)(wi % SSD_TP), pt = pi >> 3, n = pi & 7;
+    const int64_t oct = wi / SSD_OCT;
+    const int n = (int)(wi % SSD_OCT);
     double msq = 0.0;
     for (int k = lane; k < m.ssd_k; k += 32) {
         const double v = centred_mean(m, theta, k);
         msq += v * v;
         const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
-        bfrag[((((size_t)tile * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 4 + pt) * 32 + n * 4 + (kl & 3)] = v;
+        bfrag[(((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32 + n * 4 + (kl & 3)] = v;
     }
     msq = warp_sum(msq);
     if (lane == 0) {
@@ -403,11 +403,11 @@ static size_t xdot_smem_bytes(int nj)
     return (size_t)4 * XD_STAGES * nj * 64 * sizeof(double) + sizeof(uint64_t) * 4 * XD_STAGES;
 }
 
-static size_t xd_bfrag_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_TP - 1) / SSD_TP) * m.n_ksplit * m.ssd_nj * 4 * 32; }
+static size_t xd_bfrag_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_OCT - 1) / SSD_OCT) * m.n_ksplit * m.ssd_nj * 32; }
 static XdStage *xd_stage(const ModelDev &m, int n)
 {
     XdStage &x = g_xs[g_dev];
-    const size_t need = xd_bfrag_doubles(m, n) + (size_t)((n + SSD_TP - 1) / SSD_TP) * SSD_TP;
+    const size_t need = xd_bfrag_doubles(m, n) + (size_t)((n + SSD_OCT - 1) / SSD_OCT) * SSD_OCT;
     if (need > x.cap) {
         cudaStreamSynchronize(stream());
         if (x.bfrag) cudaFree(x.bfrag);
@@ -417,7 +417,7 @@ static XdStage *xd_stage(const ModelDev &m, int n)
     }
     // the dimension slots that pad a split to whole k-steps must read as zero, and the geometry may
     // change with the model: clear whenever the split between the two arrays moves
-    double *magic = x.bfrag + (x.cap - (size_t)((n + SSD_TP - 1) / SSD_TP) * SSD_TP);
+    double *magic = x.bfrag + (x.cap - (size_t)((n + SSD_OCT - 1) / SSD_OCT) * SSD_OCT);
     if (magic != x.magic) {
         if (cudaMemsetAsync(x.bfrag, 0, sizeof(double) * x.cap, stream()) != cudaSuccess) { g_be_err = "cudaMemset(mean staging)"; return nullptr; }
         x.magic = magic;
@@ -426,11 +426,12 @@ static XdStage *xd_stage(const ModelDev &m, int n)
 }
 
 // how the CTAs of one launch are dealt to the particle tiles of a level
-struct XdGrid { int32_t n_full, c_full, c_last, oct_last; };
+// n_hi tiles of oct_hi octets with c_hi CTAs each, then n_lo tiles of oct_lo octets with c_lo CTAs each
+struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 
 template <int NOCT>
 __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
-                                          long long *ll_acc, int tile, int T0, int T1, unsigned char *smem_raw)
+                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ks = blockIdx.y;
     const int nj = m.ssd_nj;
@@ -456,11 +457,12 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     // this tile's centred means as B fragments, and the particles' fixed-point constants
     double b[SSD_NJ][NOCT];
     {
-        const double *bf = bfrag + (((size_t)tile * m.n_ksplit + ks) * nj * 4) * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < SSD_NJ; ++j)
+        for (int pt = 0; pt < NOCT; ++pt) {
+            const double *bf = bfrag + (((size_t)(oct0 + pt) * m.n_ksplit + ks) * nj) * 32 + lane;
 #pragma unroll
-            for (int pt = 0; pt < NOCT; ++pt) b[j][pt] = j < nj ? bf[(j * 4 + pt) * 32] : 0.0;
+            for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? bf[j * 32] : 0.0;
+        }
     }
     double mg[NOCT][2];
     unsigned long long isum[NOCT][2];
@@ -469,7 +471,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            mg[pt][e] = magic[(size_t)tile * SSD_TP + pt * 8 + 2 * (lane & 3) + e];
+            mg[pt][e] = magic[(size_t)(oct0 + pt) * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
             acc[0][pt][e] = 0.0; acc[1][pt][e] = 0.0;
         }
@@ -517,7 +519,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             unsigned long long v = isum[pt][e] - n_conv * (unsigned long long)xd_bits(mg[pt][e]);
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            const int idx = tile * SSD_TP + pt * 8 + 2 * lane + e;
+            const int idx = (oct0 + pt) * SSD_OCT + 2 * lane + e;
             if (lane < 4 && idx < lv.n) {
                 const int p = lv.order ? (int)((uint32_t)lv.order[idx] & LV_POS_MASK) : idx;
                 atomicAdd(reinterpret_cast<unsigned long long *>(ll_acc) + p, v);
@@ -529,18 +531,18 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
                                                                      long long *ll_acc, XdGrid g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    int tile, c_in, C, noct;
-    const int n_in_full = g.n_full * g.c_full;
-    if ((int)blockIdx.x < n_in_full) { tile = blockIdx.x / g.c_full; c_in = blockIdx.x - tile * g.c_full; C = g.c_full; noct = 4; }
-    else { tile = g.n_full; c_in = blockIdx.x - n_in_full; C = g.c_last; noct = g.oct_last; }
+    int oct0, c_in, C, noct;
+    const int n_in_hi = g.n_hi * g.c_hi;
+    if ((int)blockIdx.x < n_in_hi) { const int t = blockIdx.x / g.c_hi; c_in = blockIdx.x - t * g.c_hi; C = g.c_hi; noct = g.oct_hi; oct0 = t * g.oct_hi; }
+    else { const int r = blockIdx.x - n_in_hi, t = r / g.c_lo; c_in = r - t * g.c_lo; C = g.c_lo; noct = g.oct_lo; oct0 = g.n_hi * g.oct_hi + t * g.oct_lo; }
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
     if (T1 <= T0) return;
     switch (noct) {
-    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
-    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
-    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
-    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, tile, T0, T1, smem_raw); break;
+    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
+    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
+    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
+    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
     }
 }
 
@@ -560,33 +562,40 @@ static int n_sms()
     return sms[g_dev] > 0 ? sms[g_dev] : 148;
 }
 
-// deals the resident CTA slots of one wave to the particle tiles of a level in proportion to
-// their octets; when there are more tiles than slots, picks the split that fills whole waves best
+// A level's octets are dealt to particle tiles as evenly as possible (tiles of 3 and 4 octets rather
+// than 4,4,..,1: a one-octet CTA has two DMMA chains and starves next to eight-chain warps), and
+// the resident CTA slots of one wave are dealt to the tiles in proportion to their octets; when
+// there are more tiles than slots, the split that fills whole waves best is used.
 static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
 {
     XdGrid g;
-    const int n32 = (n + SSD_TP - 1) / SSD_TP;
-    const int rem = n - (n32 - 1) * SSD_TP;                        // particles in the last tile, 1..32
-    g.oct_last = (rem + SSD_OCT - 1) / SSD_OCT;
-    g.n_full = g.oct_last == 4 ? n32 : n32 - 1;
-    if (g.oct_last == 4) g.oct_last = 0;
+    const int octets = (n + SSD_OCT - 1) / SSD_OCT;
+    const int nt = (octets + 3) / 4;
+    g.oct_lo = octets / nt; g.oct_hi = g.oct_lo + 1;
+    g.n_hi = octets - g.oct_lo * nt; g.n_lo = nt - g.n_hi;
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int c_max = std::max(1, n_tiles / XD_MIN_TILES);
     const int per_split = std::max(1, slots / std::max(1, m.n_ksplit));
-    const int octets = 4 * g.n_full + g.oct_last;
-    if (octets <= 4 * per_split) {                                 // one wave
-        g.c_full = std::min(c_max, std::max(1, 4 * per_split / octets));
-        g.c_last = g.oct_last ? std::min(c_max, std::max(1, (g.oct_last * per_split + octets / 2) / octets)) : 0;
-        // spend what the rounding left over
-        while (g.n_full && g.c_full < c_max && g.n_full * (g.c_full + 1) + g.c_last <= per_split) ++g.c_full;
+    if (nt <= per_split) {                                         // one wave
+        g.c_lo = std::min(c_max, std::max(1, per_split * g.oct_lo / octets));
+        g.c_hi = g.n_hi ? std::min(c_max, std::max(1, per_split * g.oct_hi / octets)) : 1;
+        // spend what the rounding left over on whichever class is slower
+        for (;;) {
+            const int left = per_split - (g.n_hi * g.c_hi + g.n_lo * g.c_lo);
+            const bool hi_slower = g.n_hi && (int64_t)g.oct_hi * g.c_lo > (int64_t)g.oct_lo * g.c_hi;
+            if (hi_slower && left >= g.n_hi && g.c_hi < c_max) ++g.c_hi;
+            else if (left >= g.n_lo && g.c_lo < c_max) ++g.c_lo;
+            else if (g.n_hi && left >= g.n_hi && g.c_hi < c_max) ++g.c_hi;
+            else break;
+        }
     } else {                                                       // several waves: fill them
         int best = 1; double best_eff = 0.0;
         for (int c = 1; c <= std::min(c_max, 16); ++c) {
-            const double ctas = (double)(g.n_full + (g.oct_last ? 1 : 0)) * c;
+            const double ctas = (double)nt * c;
             const double eff = ctas / (ceil(ctas / per_split) * per_split);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
         }
-        g.c_full = best; g.c_last = g.oct_last ? best : 0;
+        g.c_hi = g.c_lo = best;
     }
     return g;
 }
@@ -600,7 +609,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
         attr_set[g_dev] = true;
     }
     const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
-    dim3 grid((unsigned)(g.n_full * g.c_full + g.c_last), (unsigned)m.n_ksplit);
+    dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)m.n_ksplit);
     k_xdot<<<grid, XD_THREADS, smem, stream()>>>(m, xs.bfrag, xs.magic, lv, ll_acc, g);
     LAUNCHED("k_xdot");
     return 0;

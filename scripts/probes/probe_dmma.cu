@@ -74,6 +74,39 @@ void run(const char *what, int sms, double *out, double fma_per_thread_iter, dou
     if (e != cudaSuccess) printf("  error: %s\n", cudaGetErrorString(e));
 }
 
+// DMMA throughput against resident warps per SM and independent accumulator chains per warp
+template <int CH>
+__global__ void kocc(double *out, int iters, double a, double b)
+{
+    double c[2 * CH];
+#pragma unroll
+    for (int i = 0; i < 2 * CH; ++i) c[i] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) dmma884(c[2 * i], c[2 * i + 1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * CH; ++i) s += c[i];
+    if (s == 1.2345) out[0] = s;
+}
+template <int CH>
+void occ(int warps_per_sm, int sms, double *out)
+{
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 4096;
+    float best = 1e9;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        kocc<CH><<<sms, warps_per_sm * 32>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep) best = ms < best ? ms : best;
+    }
+    const double fl = 512.0 * CH * (double)iters * warps_per_sm * sms;
+    printf("DMMA chains %2d warps/SM %2d (%.2f per SMSP): %7.2f TFLOP/s\n", CH, warps_per_sm, warps_per_sm / 4.0, fl / (best * 1e-3) / 1e12);
+}
+
 int main()
 {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -83,5 +116,6 @@ int main()
     run<2>("DMMA m16n8k16 only, 4 accumulators", sms, out, 0, 4 * 4096.0, 0, 1);
     run<3>("DFMA + DMMA m8n8k4 interleaved per warp", sms, out, 16, 8 * 512.0, 1, 1);
     run<4>("DFMA warps beside DMMA m8n8k4 warps", sms, out, 16, 8 * 512.0, 0.5, 0.5);
+    for (int w : {4, 8, 12, 16, 32}) { occ<1>(w, sms, out); occ<2>(w, sms, out); occ<4>(w, sms, out); occ<8>(w, sms, out); occ<16>(w, sms, out); }
     return 0;
 }
