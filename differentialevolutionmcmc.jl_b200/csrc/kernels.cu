@@ -362,7 +362,8 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 constexpr int XD_THREADS = 128;
 constexpr int XD_STAGES = 4;
 constexpr int XD_CTAS_PER_SM = 2;
-constexpr int XD_MIN_TILES = 8;          // observation tiles a CTA should at least stream (amortises its prologue)
+constexpr int XD_MIN_TILES = 4;          // observation tiles a CTA should at least stream (amortises its prologue)
+constexpr int XD_WAVE_TILES = 48;        // observation tiles per CTA when a level needs several waves
 
 // ---- TMA bulk copy + mbarrier helpers (sm_90+; SASS: UBLKCP / SYNCS) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -564,8 +565,8 @@ static int n_sms()
 
 // A level's octets are dealt to particle tiles as evenly as possible (tiles of 3 and 4 octets rather
 // than 4,4,..,1: a one-octet CTA has two DMMA chains and starves next to eight-chain warps), and
-// the resident CTA slots of one wave are dealt to the tiles in proportion to their octets; when
-// there are more tiles than slots, the split that fills whole waves best is used.
+// the resident CTA slots of one wave are dealt to the tiles in proportion to their octets; a level
+// too large for that is cut into many short CTAs instead.
 static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
 {
     XdGrid g;
@@ -576,7 +577,7 @@ static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int c_max = std::max(1, n_tiles / XD_MIN_TILES);
     const int per_split = std::max(1, slots / std::max(1, m.n_ksplit));
-    if (nt <= per_split) {                                         // one wave
+    if (2 * nt <= per_split) {                                     // one wave
         g.c_lo = std::min(c_max, std::max(1, per_split * g.oct_lo / octets));
         g.c_hi = g.n_hi ? std::min(c_max, std::max(1, per_split * g.oct_hi / octets)) : 1;
         // spend what the rounding left over on whichever class is slower
@@ -588,14 +589,9 @@ static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
             else if (g.n_hi && left >= g.n_hi && g.c_hi < c_max) ++g.c_hi;
             else break;
         }
-    } else {                                                       // several waves: fill them
-        int best = 1; double best_eff = 0.0;
-        for (int c = 1; c <= std::min(c_max, 16); ++c) {
-            const double ctas = (double)nt * c;
-            const double eff = ctas / (ceil(ctas / per_split) * per_split);
-            if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
-        }
-        g.c_hi = g.c_lo = best;
+    } else {
+        // several waves: many short CTAs, the hardware scheduler balances them as slots free up
+        g.c_hi = g.c_lo = std::min(c_max, std::max(1, n_tiles / XD_WAVE_TILES));
     }
     return g;
 }
