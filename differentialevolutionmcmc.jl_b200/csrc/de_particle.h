@@ -5,6 +5,8 @@
 //   C::all(b)                  logical AND over lanes
 //   C::min_int(i)              minimum over lanes
 //   C::sync()                  makes the lanes' global-memory writes visible to each other
+//   C::dependency_wait()       called once, before the first access to state written by an earlier
+//                              kernel (programmatic dependent launch); a no-op on the host
 // kernels.cu instantiates it with a 32-lane warp; the host test double with a single lane.
 #pragma once
 #include "de_types.h"
@@ -18,6 +20,7 @@ struct SerialLanes {
     DE_HD bool all(bool b) const { return b; }
     DE_HD int min_int(int x) const { return x; }
     DE_HD void sync() const {}
+    DE_HD void dependency_wait() const {}
 };
 
 // mean of dimension k of the MVN / hierarchical likelihood, relative to the data centre
@@ -99,6 +102,7 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
         kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; u_base = pl.u_base;
         if (kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, kind, cfg.proposal, ctx.in_burnin != 0, d); g1 = gg.a; g2 = gg.b; }
     }
+    co.dependency_wait();
     // a donor that sits before the target in the sweep already holds this sweep's value
     const size_t gbase = (size_t)g * Np;
 #define DE_DONOR(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
@@ -194,6 +198,10 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const int n_split = m.n_osplit * m.n_ksplit;
     const double *prop = ctx.prop_theta + (size_t)p * d;
     const double *tcur = ctx.cur_theta + (size_t)p * d;
+    const int g = p / Np, j = p - g * Np;
+    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
+    const double u = ctx.replay ? ctx.t_uacc[p] : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
+    co.dependency_wait();
     double total;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];
     else {
@@ -206,9 +214,6 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const bool inb = ctx.prop_inb[p] != 0;
     const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();
     const double adj = ctx.prop_adj[p];
-    const int g = p / Np, j = p - g * Np;
-    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
-    const double u = ctx.replay ? ctx.t_uacc[p] : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
     const double wcur = ctx.cur_w[p];
     const bool acc = accept(wprop, wcur, adj, u);
     double *dst = ctx.next_theta + (size_t)p * d;

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -43,6 +44,28 @@ static cudaStream_t stream()
 {
     if (!g_stream[g_dev]) cudaStreamCreateWithFlags(&g_stream[g_dev], cudaStreamNonBlocking);
     return g_stream[g_dev];
+}
+
+// Kernels of one level are chained with programmatic dependent launch: the next kernel's CTAs may
+// become resident and run their state-independent prologue while the previous kernel drains; each
+// kernel executes griddepcontrol.wait before it touches anything an earlier kernel wrote.
+// DEMCMC_NO_PDL=1 falls back to plain stream order (A/B measurements).
+static bool use_pdl()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DEMCMC_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 const char *name() { return "cuda-sm100a"; }
@@ -146,7 +169,12 @@ struct WarpLanes {
     __device__ __forceinline__ bool all(bool b) const { return __all_sync(0xffffffffu, b) != 0; }
     __device__ __forceinline__ int min_int(int x) const { return __reduce_min_sync(0xffffffffu, x); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // programmatic dependent launch: everything before this point touches only data that is constant
+    // for the whole chunk (schedule, tape, Philox); the state written by earlier kernels comes after
+    __device__ __forceinline__ void dependency_wait() const { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 };
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 struct ksum_t { double s, c; };
 __device__ __forceinline__ void kadd(ksum_t &k, double x)
@@ -195,8 +223,9 @@ __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *the
 
 __global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
 {
+    pdl_launch_dependents();
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
-    if (wi >= lv.n) return;
+    if (wi >= lv.n) { pdl_wait(); return; }
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     const int p = (int)(e & LV_POS_MASK);
@@ -209,8 +238,9 @@ __global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev 
 
 __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, Level lv)
 {
+    pdl_launch_dependents();
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
-    if (wi >= lv.n) return;
+    if (wi >= lv.n) { pdl_wait(); return; }
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     accept_particle(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
@@ -225,7 +255,7 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
         xs = xd_stage(m, std::max(lv.n, cfg.G_local * cfg.Np));
         if (!xs) return -1;
     }
-    k_propose<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr);
+    CU(launch_chained(k_propose, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
     LAUNCHED("k_propose");
     return 0;
 }
@@ -233,7 +263,7 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    k_accept<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, lv);
+    CU(launch_chained(k_accept, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv));
     LAUNCHED("k_accept");
     return 0;
 }
@@ -454,6 +484,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             }
     }
     __syncwarp();
+    pdl_wait();                                              // the packed data are constant; the means are not
 
     // this tile's centred means as B fragments, and the particles' fixed-point constants
     double b[SSD_NJ][NOCT];
@@ -532,13 +563,14 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
                                                                      long long *ll_acc, XdGrid g)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_launch_dependents();
     int oct0, c_in, C, noct;
     const int n_in_hi = g.n_hi * g.c_hi;
     if ((int)blockIdx.x < n_in_hi) { const int t = blockIdx.x / g.c_hi; c_in = blockIdx.x - t * g.c_hi; C = g.c_hi; noct = g.oct_hi; oct0 = t * g.oct_hi; }
     else { const int r = blockIdx.x - n_in_hi, t = r / g.c_lo; c_in = r - t * g.c_lo; C = g.c_lo; noct = g.oct_lo; oct0 = g.n_hi * g.oct_hi + t * g.oct_lo; }
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
-    if (T1 <= T0) return;
+    if (T1 <= T0) { pdl_wait(); return; }
     switch (noct) {
     case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
     case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
@@ -606,7 +638,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
     }
     const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
     dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)m.n_ksplit);
-    k_xdot<<<grid, XD_THREADS, smem, stream()>>>(m, xs.bfrag, xs.magic, lv, ll_acc, g);
+    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g));
     LAUNCHED("k_xdot");
     return 0;
 }
