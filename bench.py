@@ -262,9 +262,9 @@ def run_b200(args):
             t_e2e = time.perf_counter() - t0
             assert len(chains) == args.steps
             h2d = (x.nbytes + G * NP * d * 8) / args.steps
-            d2h = G * NP * (d * 8 + 8 + 1)
+            d2h = G * NP * (d + 2) * 8
             e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "call": "sample(model, de, n_iter) with host (pageable numpy) data; includes handle creation, upload, all iterations, download of samples/accept/lp and bundle_samples",
+                   "call": "sample(model, de, n_iter) with host (pageable numpy) data: handle creation, data upload + packing, P sample_prior() calls, all iterations, device-side bundle_samples and the download of the chains",
                    "seconds": t_e2e}
     if world > 1:
         # sharded e2e: every rank builds its handle from host buffers, runs, and downloads its by-slot history

@@ -354,10 +354,13 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         h.set_state(theta0)
         h.run(n_iter)
         de.iter = n_iter + de.n_initial
-        samples, accept, lp = h.samples(), h.accept(), h.lp()
-        _, _, final_ids = h.get_state()
-        de.samples = samples
-        return bundle_samples(model, de, samples, accept, lp, final_ids, shapes, n_iter)
+        # bundle_samples (src/main.jl:222-250) runs on the device: one gather, one download, and the
+        # host only wraps the array (Julia memory order) in a view
+        offset = de.burnin if de.discard_burnin else 0
+        arr = h.chains(offset, max(n_iter - offset, 0))
+        de.samples = arr[:, :d, :]                       # what bundle_samples keeps of de.samples
+        names = _flat_names(model.names, shapes) + ["acceptance", "lp"]
+        return Chains(arr.transpose(2, 1, 0), names, [str(n) for n in model.names])
     finally:
         h.close()
 

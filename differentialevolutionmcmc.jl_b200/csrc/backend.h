@@ -66,6 +66,10 @@ int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *pi
 int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
                          int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,
                          double *samples, double *lp, uint8_t *accept);
+// bundle_samples layout (main.jl:222-250): chains[P][d+2][n_rows] for history rows [row0, row0+n_rows);
+// final_id[P] = id at each final position, pos_scratch[P] device scratch
+int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
+                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out);
 // particle algebra known-answer ops (single warp each)
 int launch_op_project(const double *p1, const double *p2, int d, double *out);
 int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,

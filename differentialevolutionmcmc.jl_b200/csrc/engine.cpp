@@ -668,6 +668,28 @@ int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows) { return o
 int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows) { return out ? history_out(h, nullptr, nullptr, out, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
 int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, nullptr, out, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
 
+int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
+{
+    if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld iterations run", (long long)row0, (long long)(row0 + n_rows), (long long)h->iters_done);
+    if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "chains of a sharded job: gather demcmc_get_history_by_slot on the host");
+    if (!h->has_state) return fail(DEMCMC_ESTATE, "no state");
+    BE(be::set_device(h->cfg.device));
+    if (n_rows == 0) return 0;
+    const size_t P = h->P, d = h->d, n = (size_t)n_rows * P * (d + 2);
+    double *dout = (double *)be::dmalloc(sizeof(double) * n);
+    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * P);
+    int rc = 0;
+    if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging does not fit on the device");
+    if (!rc && (be::dzero(dout, sizeof(double) * n) ||
+                be::launch_chains(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, cur_row(h).id, pos, row0, n_rows, (int32_t)P, (int32_t)d,
+                                  h->cfg.group_begin * h->cfg.Np, dout) ||
+                be::d2h(out, dout, sizeof(double) * n)))
+        rc = fail(DEMCMC_ECUDA, "chain gather: %s", be::last_error());
+    be::dfree(dout); be::dfree(pos);
+    return rc;
+}
+
 int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, double *theta, double *w, int32_t *ids, uint8_t *acc)
 {
     if (!h || row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range outside the iterations run");

@@ -84,22 +84,49 @@ int set_device(int dev)
     g_dev = dev;
     return 0;
 }
+// Device memory comes from the stream-ordered allocator with an unbounded release threshold: a
+// handle that is destroyed leaves its blocks in the pool, so creating the next one (one handle per
+// sample() call) costs microseconds instead of a cudaMalloc / cudaFree pair per buffer.
+static void pool_setup()
+{
+    static bool done[64] = { false };
+    if (done[g_dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[g_dev] = true;
+}
 void *dmalloc(size_t bytes)
 {
+    pool_setup();
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
-    if (e != cudaSuccess) { cu_fail(e, "cudaMalloc"); return nullptr; }
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, stream());
+    if (e != cudaSuccess) { cu_fail(e, "cudaMallocAsync"); return nullptr; }
     return p;
 }
-void dfree(void *p) { if (p) cudaFree(p); }
+void dfree(void *p) { if (p) cudaFreeAsync(p, stream()); }
+// pinned blocks are recycled through a small free list for the same reason
+struct PinnedBlock { void *p; size_t bytes; bool busy; };
+static std::vector<PinnedBlock> g_pinned;
 void *hmalloc_pinned(size_t bytes)
 {
+    if (!bytes) bytes = 8;
+    for (auto &b : g_pinned)
+        if (!b.busy && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096) { b.busy = true; return b.p; }
     void *p = nullptr;
-    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 8);
+    cudaError_t e = cudaMallocHost(&p, bytes);
     if (e != cudaSuccess) { cu_fail(e, "cudaMallocHost"); return nullptr; }
+    g_pinned.push_back({ p, bytes, true });
     return p;
 }
-void hfree_pinned(void *p) { if (p) cudaFreeHost(p); }
+void hfree_pinned(void *p)
+{
+    if (!p) return;
+    for (auto &b : g_pinned) if (b.p == p) { b.busy = false; return; }
+    cudaFreeHost(p);
+}
 int h2d(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream())); return 0; }
 int d2h(void *dst, const void *src, size_t bytes)
 {
@@ -947,6 +974,45 @@ int launch_history_by_id(const double *rows_theta, const double *rows_w, const u
     dim3 grid((unsigned)((n_rows_dev + 255) / 256), (unsigned)P);
     k_history<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, n_rows_dev, row0, n_rows_out, P, d, id_base, samples, lp, accept);
     LAUNCHED("k_history");
+    return 0;
+}
+
+// bundle_samples (main.jl:222-250) on the device: chains[c][k][row] for rows [row0, row0+n_rows) of
+// the history; parameter columns k < d of chain c are the draws of particle id c, the columns
+// "acceptance" (d) and "lp" (d+1) belong to the particle sitting at final position c
+__global__ void __launch_bounds__(256) k_chain_pos(const int32_t *final_id, int P, int id_base, int32_t *pos_of_id)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P) return;
+    const int id = final_id[c] - id_base;
+    if (id >= 0 && id < P) pos_of_id[id] = c;
+}
+__global__ void __launch_bounds__(256) k_chains(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid,
+                                                const int32_t *pos_of_id, int64_t row0, int64_t n_rows, int P, int d, int id_base, double *out)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.y;
+    if (r >= n_rows) return;
+    const int64_t row = row0 + r;
+    const int id = rid[row * P + slot] - id_base;
+    if (id < 0 || id >= P) return;
+    const double *src = rt + (row * P + slot) * d;
+    double *dst = out + (int64_t)id * (d + 2) * n_rows + r;
+    for (int k = 0; k < d; ++k) dst[(int64_t)k * n_rows] = src[k];
+    double *dq = out + (int64_t)pos_of_id[id] * (d + 2) * n_rows + r;
+    dq[(int64_t)d * n_rows] = (double)ra[row * P + slot];
+    dq[(int64_t)(d + 1) * n_rows] = rw[row * P + slot];
+}
+
+int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
+                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out)
+{
+    k_chain_pos<<<(P + 255) / 256, 256, 0, stream()>>>(final_id, P, id_base, pos_scratch);
+    LAUNCHED("k_chain_pos");
+    if (n_rows <= 0) return 0;
+    dim3 grid((unsigned)((n_rows + 255) / 256), (unsigned)P);
+    k_chains<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, pos_scratch, row0, n_rows, P, d, id_base, out);
+    LAUNCHED("k_chains");
     return 0;
 }
 

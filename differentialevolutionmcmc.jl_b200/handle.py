@@ -157,6 +157,15 @@ class Handle:
         check(_ffi.lib().demcmc_get_lp(self._h, ptr(out, _dp), self.n_rows))
         return out
 
+    def chains(self, row0=0, n_rows=None):
+        """bundle_samples on the device: array of shape (P, d+2, n_rows) in Julia memory order, i.e.
+        out[c, k, r] == Julia Array(n_rows, d+2, P)[r+1, k+1, c+1] of iterations row0+r."""
+        n = self.iterations - row0 if n_rows is None else n_rows
+        out = np.empty((self.P, self.d + 2, max(n, 0)))
+        if n > 0:
+            check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
+        return out
+
     def history_by_slot(self, row0=0, n_rows=None):
         n = self.iterations - row0 if n_rows is None else n_rows
         th = np.zeros((n, self.P, self.d))

@@ -142,6 +142,12 @@ int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows);
  * row fastest, column = particle id - group_begin*Np */
 int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows);
 int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows);
+/* bundle_samples (src/main.jl:222-250) on the device, for history rows [row0, row0+n_rows) (row0 =
+ * burnin when discard_burnin): out[n_rows][d+2][P] in Julia order (= C order [P][d+2][n_rows]), the
+ * memory layout of the Array the reference hands to MCMCChains.Chains.  Parameter columns of chain c
+ * are the draws of particle id c; the last two columns, "acceptance" and "lp", belong to the
+ * particle sitting at final position c -- the reference's own by-position quirk (main.jl:232-241). */
+int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out);
 /* the same history as the device keeps it, rows [row0, row0+n_rows) of the iterations run, by
  * POSITION: theta[n_rows][P_local][d], w[n_rows][P_local] (= lp), ids[n_rows][P_local] (particle id
  * sitting at each position after that iteration), acc[n_rows][P_local]; any pointer may be NULL.

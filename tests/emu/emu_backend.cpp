@@ -307,6 +307,23 @@ int launch_history_by_id(const double *rt, const double *rw, const uint8_t *ra, 
     return 0;
 }
 
+int launch_chains(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid, const int32_t *final_id, int32_t *pos,
+                  int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out)
+{
+    ++g_launches;
+    for (int c = 0; c < P; ++c) { const int id = final_id[c] - id_base; if (id >= 0 && id < P) pos[id] = c; }
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (int slot = 0; slot < P; ++slot) {
+            const int64_t row = row0 + r;
+            const int id = rid[row * P + slot] - id_base;
+            if (id < 0 || id >= P) continue;
+            for (int k = 0; k < d; ++k) out[((int64_t)id * (d + 2) + k) * n_rows + r] = rt[(row * P + slot) * d + k];
+            out[((int64_t)pos[id] * (d + 2) + d) * n_rows + r] = (double)ra[row * P + slot];
+            out[((int64_t)pos[id] * (d + 2) + d + 1) * n_rows + r] = rw[row * P + slot];
+        }
+    return 0;
+}
+
 int launch_op_project(const double *p1, const double *p2, int d, double *out)
 {
     double v1 = 0, v2 = 0;

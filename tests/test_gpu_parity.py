@@ -274,3 +274,23 @@ def test_native_mvn_posterior_matches_oracle_chains():
     for k in range(dm + 1):
         ks = stats.ks_2samp(a[:, k, ::20].ravel(), b[:, k, ::20].ravel()).statistic
         assert ks < 0.06, (k, ks)
+
+
+def test_device_bundle_matches_bundle_samples():
+    """demcmc_get_chains on the device = bundle_samples (main.jl:222-250), by-position quirk included."""
+    from demcmc_b200.api import DE, DEModel, GPULoglike, GPUPrior, HalfCauchy, Normal, bundle_samples
+    case = make_case("mvnormal", np.random.default_rng(23))
+    G, Np = 3, 40
+    theta0 = case.theta0(np.random.default_rng(5), G * Np)
+    h = case.handle(G, Np, seed=5, burnin=10, alpha=0.6, theta_snooker=0.1)
+    h.set_state(theta0)
+    h.run(30)
+    ids = h.get_state()[2]
+    assert not np.array_equal(ids, np.arange(G * Np))
+    d = theta0.shape[1]
+    model = DEModel(sample_prior=lambda: [np.zeros(d - 1), 1.0], prior_loglike=GPUPrior(Normal(), HalfCauchy()),
+                    loglike=GPULoglike("mvnormal", np.zeros((3, d - 1))), names=("mu", "sigma"))
+    de = DE(sample_prior=model.sample_prior, bounds=((-1, 1), (0, 1)), n_groups=G, Np=Np, burnin=10)
+    ref = bundle_samples(model, de, h.samples(), h.accept(), h.lp(), ids, [(d - 1,), ()], 30)
+    assert np.array_equal(h.chains(10, 20).transpose(2, 1, 0), ref.value)
+    h.close()

@@ -213,3 +213,28 @@ def test_overlapped_chunks_do_not_change_the_result():
     cfg = case.oracle_config(2, 48, seed=21, burnin=5, theta_snooker=0.2, alpha=0.05, base_snapshot=1)
     r = O.run(cfg, case.oracle_model(), theta0, 40, record=False, trace=False)
     assert np.array_equal(outs[2][0], r["samples"]) and np.array_equal(outs[2][1], r["accept"])
+
+
+def test_device_bundle_matches_bundle_samples():
+    """demcmc_get_chains = bundle_samples (main.jl:222-250) including its by-position quirk: after
+    migrations the acceptance/lp columns of chain c belong to the particle at final position c."""
+    from demcmc_b200.api import DE, DEModel, GPULoglike, GPUPrior, HalfCauchy, Normal, bundle_samples
+    case = make_case("gaussian", np.random.default_rng(23))
+    theta0 = case.theta0(np.random.default_rng(5), 3 * 7)
+    h = case.handle(3, 7, seed=5, burnin=10, alpha=0.6, theta_snooker=0.1)
+    h.set_state(theta0)
+    h.run(30)
+    ids = h.get_state()[2]
+    assert not np.array_equal(ids, np.arange(21))                      # migrations moved particles
+    model = DEModel(sample_prior=lambda: [0.0, 1.0], prior_loglike=GPUPrior(Normal(), HalfCauchy()),
+                    loglike=GPULoglike("gaussian", np.zeros(3)), names=("mu", "sigma"))
+    de = DE(sample_prior=model.sample_prior, bounds=((-1, 1), (0, 1)), n_groups=3, Np=7, burnin=10)
+    ref = bundle_samples(model, de, h.samples(), h.accept(), h.lp(), ids, [(), ()], 30)
+    got = h.chains(10, 20)
+    assert got.shape == (21, 4, 20)
+    assert np.array_equal(got.transpose(2, 1, 0), ref.value)
+    assert np.array_equal(h.chains(0, 30)[:, :2, :], h.samples())
+    assert h.chains(30, 0).shape == (21, 4, 0)
+    with pytest.raises(D._ffi.DemcmcError):
+        h.chains(25, 10)
+    h.close()
