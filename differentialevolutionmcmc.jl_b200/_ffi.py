@@ -44,13 +44,14 @@ class Config(C.Structure):
                 ("kappa", C.c_double), ("theta_snooker", C.c_double),
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
                 ("seed", C.c_uint64), ("device", C.c_int32), ("group_begin", C.c_int32),
-                ("group_count", C.c_int32), ("reserved0", C.c_int32), ("trace", C.c_int32),
+                ("group_count", C.c_int32), ("donors", C.c_int32), ("trace", C.c_int32),
                 ("store_every", C.c_int32)]
 
 
 class Tape(C.Structure):
     _fields_ = [("mig_u", _dp), ("mig_n", _ip), ("mig_groups", _ip), ("mig_pick_u", _dp), ("kind", _bp),
-                ("idx", _ip), ("gamma1", _dp), ("gamma2", _dp), ("u_acc", _dp), ("noise", _dp), ("keep", _bp)]
+                ("idx", _ip), ("gamma1", _dp), ("gamma2", _dp), ("u_acc", _dp), ("noise", _dp), ("keep", _bp),
+                ("idx_row", _ip)]
 
 
 class Counters(C.Structure):
@@ -62,7 +63,7 @@ class Counters(C.Structure):
 # every symbol include/demcmc_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "demcmc_last_error", "demcmc_abi_version", "demcmc_device_count", "demcmc_backend_name", "demcmc_create",
-    "demcmc_destroy", "demcmc_set_model", "demcmc_set_state", "demcmc_run", "demcmc_replay", "demcmc_get_samples",
+    "demcmc_destroy", "demcmc_set_model", "demcmc_set_history", "demcmc_set_state", "demcmc_run", "demcmc_replay", "demcmc_get_samples",
     "demcmc_get_accept", "demcmc_get_lp", "demcmc_get_chains", "demcmc_get_history_by_slot", "demcmc_get_state", "demcmc_get_trace",
     "demcmc_get_migration", "demcmc_get_counters", "demcmc_set_timing", "demcmc_set_max_chunk", "demcmc_eval", "demcmc_op_project", "demcmc_op_reset",
     "demcmc_op_de_proposal", "demcmc_op_snooker", "demcmc_op_accept", "demcmc_op_select", "demcmc_comm_unique_id",
@@ -83,6 +84,7 @@ def _declare(L):
     L.demcmc_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     L.demcmc_destroy.argtypes = [C.c_void_p]
     L.demcmc_set_model.argtypes = [C.c_void_p, C.POINTER(Model)]
+    L.demcmc_set_history.argtypes = [C.c_void_p, _dp]
     L.demcmc_set_state.argtypes = [C.c_void_p, _dp, _ip]
     L.demcmc_run.argtypes = [C.c_void_p, C.c_int64]
     L.demcmc_replay.argtypes = [C.c_void_p, C.POINTER(Tape), C.c_int64]

@@ -129,6 +129,11 @@ class MCMCThreads:
     (src/main.jl:135-148); on the device every group is always updated concurrently."""
 
 
+def resample(*a):
+    """DE(sample=resample): DE-MCz donors from the history (src/crossover.jl:113-124)."""
+    raise TypeError("resample is a donor selector for DE(sample=...), not a host function")
+
+
 def random_gamma(*a):
     raise TypeError("random_gamma is a proposal selector for DE(generate_proposal=...), not a host function")
 
@@ -182,10 +187,11 @@ class DE:
         self.iter = 1
         if update_particle is not None or evaluate_fitness is not None:
             raise NotImplementedError("only mh_update! / compute_posterior! are built on the B200 path (optimize is not)")
-        if sample is not None:
-            raise NotImplementedError("sample = resample (DE-MCz donors from the history) is not built on the B200 path yet")
-        if self.n_initial != 0:
-            raise NotImplementedError("n_initial > 0 belongs to sample = resample, which is not built yet")
+        if sample is not None and sample is not resample:
+            raise TypeError("sample must be left at its default (donors from the current group) or be `resample`: a custom host function cannot run on the device")
+        self.sample = sample
+        if sample is resample and self.n_initial * self.n_groups * self.Np < 3:
+            raise ValueError("sample = resample draws donors from rows 1:de.iter-1 of de.samples: it needs n_initial > 0")
         if generate_proposal not in _PROPOSAL_NAMES:
             raise TypeError("generate_proposal must be random_gamma, fixed_gamma or variable_gamma: a custom host function cannot run on the device")
         self.generate_proposal = generate_proposal
@@ -332,7 +338,8 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
     seed = de.seed if de.seed is not None else int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
     h = Handle(de.n_groups, de.Np, d, lo, hi, burnin=de.burnin, n_initial=de.n_initial, alpha=de.α, beta=de.β, eps=de.ϵ,
                sigma=de.σ, kappa=de.κ, theta_snooker=de.θsnooker, proposal=_PROPOSAL_NAMES[de.generate_proposal],
-               blocks=blocks, seed=seed, device=device, trace=trace, group_begin=group_begin, group_count=group_count)
+               blocks=blocks, seed=seed, device=device, trace=trace, group_begin=group_begin, group_count=group_count,
+               resample=de.sample is resample)
     h.set_model(ll.kind, _prior_table(model, shapes), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
     return h, shapes, d
 
@@ -349,9 +356,19 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
     h, shapes, d = build_handle(model, de, device=device)
     try:
         P = de.n_groups * de.Np
-        # sample_init (src/main.jl:263-271): one sample_prior() per particle, id order
-        theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)
-        h.set_state(theta0)
+        if de.n_initial > 0:
+            # initialize_samples (src/utilities.jl:29-41): for every particle id, n_initial sample_prior()
+            # draws; init_particle then starts each particle from samples[1, :, id] (utilities.jl:15)
+            rows = np.empty((de.n_initial, P, d))
+            for p in range(P):
+                for i in range(de.n_initial):
+                    rows[i, p] = _flatten(model.sample_prior())
+            h.set_history(rows)
+            h.set_state(None)
+        else:
+            # sample_init (src/main.jl:263-271): one sample_prior() per particle, id order
+            theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)
+            h.set_state(theta0)
         h.run(n_iter)
         de.iter = n_iter + de.n_initial
         # bundle_samples (src/main.jl:222-250) runs on the device: one gather, one download, and the

@@ -60,8 +60,9 @@ int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);
 int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *theta, const double *w,
                       const int32_t *id, const uint8_t *acc, double *stage);
+// pos: id -> position map of the row being edited (resample), or nullptr
 int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
-                       double *w, int32_t *id, uint8_t *acc);
+                       double *w, int32_t *id, uint8_t *acc, int32_t *pos);
 // history rows [n_rows][P][d] by slot -> reference layout [P][d][n_rows] by id (utilities.jl:34)
 int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
                          int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,

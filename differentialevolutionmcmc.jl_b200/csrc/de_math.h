@@ -169,6 +169,43 @@ DE_HD Plan plan_particle(uint64_t seed, uint32_t sweep, uint32_t unit, int j, in
     return p;
 }
 
+// the same with de.sample = resample (crossover.jl:113-124): the donors are n distinct cells of the
+// (rows x ids) view de.samples[1:de.iter-1, 1, :], column-major cell -> (row, id); two by
+// StatsBase.samplepair, three distinct for the snooker update.  Cells are 64-bit: rows x ids can
+// pass 2^31.
+struct PlanHist { int kind; int32_t id[3]; int32_t row[3]; double u_base; };
+DE_HD int64_t rand_index64(double u, int64_t n) { int64_t i = (int64_t)(u * (double)n); return i >= n ? n - 1 : i; }
+DE_HD PlanHist plan_particle_hist(uint64_t seed, uint32_t sweep, uint32_t unit, bool mutate, double theta_snooker, int64_t ub, int64_t n_ids)
+{
+    PlanHist p; p.kind = KIND_MUTATION; p.u_base = 0.0;
+    for (int q = 0; q < 3; ++q) { p.id[q] = -1; p.row[q] = -1; }
+    if (mutate) return p;
+    const dbl2 u0 = uniform2(seed, ST_PLAN, sweep, unit, 0);
+    const dbl2 u1 = uniform2(seed, ST_PLAN, sweep, unit, 1);
+    p.u_base = u0.b;
+    const int64_t n = ub * n_ids;
+    if (!(u0.a <= theta_snooker)) {
+        p.kind = KIND_DE;
+        int64_t a = rand_index64(u1.a, n), b = rand_index64(u1.b, n - 1);
+        if (b == a) b = n - 1;
+        p.row[1] = (int32_t)(a % ub); p.id[1] = (int32_t)(a / ub);
+        p.row[2] = (int32_t)(b % ub); p.id[2] = (int32_t)(b / ub);
+    } else {
+        p.kind = KIND_SNOOKER;
+        const dbl2 u2 = uniform2(seed, ST_PLAN, sweep, unit, 2);
+        int64_t a = rand_index64(u1.a, n), b = rand_index64(u1.b, n - 1);
+        if (b >= a) ++b;
+        int64_t c = rand_index64(u2.a, n - 2);
+        const int64_t lo = a < b ? a : b, hi = a < b ? b : a;
+        if (c >= lo) ++c;
+        if (c >= hi) ++c;
+        p.row[0] = (int32_t)(a % ub); p.id[0] = (int32_t)(a / ub);
+        p.row[1] = (int32_t)(b % ub); p.id[1] = (int32_t)(b / ub);
+        p.row[2] = (int32_t)(c % ub); p.id[2] = (int32_t)(c / ub);
+    }
+    return p;
+}
+
 // gamma draws: random_gamma g1 = Uniform(0.5,1), g2 = Uniform(0.5,1) while iter <= burnin else 0
 // (crossover.jl:162-164); snooker g = Uniform(1.2,2.2) (crossover.jl:249)
 DE_HD dbl2 gamma_draw(uint64_t seed, uint32_t sweep, uint32_t unit, int kind, int proposal, bool in_burnin, int d)

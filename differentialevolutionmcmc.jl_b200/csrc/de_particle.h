@@ -91,31 +91,41 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
     const double *tcur = ctx.cur_theta + (size_t)p * d;
     double *prop = ctx.prop_theta + (size_t)p * d;
 
-    int kind, i0 = -1, i1 = -1, i2 = -1;
+    int kind, i0 = -1, i1 = -1, i2 = -1, hr0 = -1, hr1 = -1, hr2 = -1;
     double g1 = 0.0, g2 = 0.0, u_base = 0.0;
     if (ctx.replay) {
         kind = ctx.t_kind[p];
         i0 = ctx.t_idx[p * 3]; i1 = ctx.t_idx[p * 3 + 1]; i2 = ctx.t_idx[p * 3 + 2];
+        if (cfg.resample) { hr0 = ctx.t_idx_row[p * 3]; hr1 = ctx.t_idx_row[p * 3 + 1]; hr2 = ctx.t_idx_row[p * 3 + 2]; }
         g1 = ctx.t_g1[p]; g2 = ctx.t_g2[p];
     } else {
-        const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
-        kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; u_base = pl.u_base;
+        if (cfg.resample) {
+            const PlanHist pl = plan_particle_hist(cfg.seed, ctx.sweep, unit, mutate, cfg.theta_snooker, ctx.donor_rows, (int64_t)cfg.G_local * Np);
+            kind = pl.kind; i0 = pl.id[0]; i1 = pl.id[1]; i2 = pl.id[2]; hr0 = pl.row[0]; hr1 = pl.row[1]; hr2 = pl.row[2]; u_base = pl.u_base;
+        } else {
+            const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
+            kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; u_base = pl.u_base;
+        }
         if (kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, kind, cfg.proposal, ctx.in_burnin != 0, d); g1 = gg.a; g2 = gg.b; }
     }
     co.dependency_wait();
-    // a donor that sits before the target in the sweep already holds this sweep's value
+    // a donor that sits before the target in the sweep already holds this sweep's value; with
+    // de.sample = resample the donors are stored rows instead: samples[row, :, id] (crossover.jl:120)
     const size_t gbase = (size_t)g * Np;
-#define DE_DONOR(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
+    const size_t P_all = (size_t)cfg.G_local * Np;
+#define DE_SLOT(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
+#define DE_HIST(r, id) (ctx.hist_theta + ((size_t)(r) * P_all + (size_t)ctx.hist_pos[(size_t)(r) * P_all + (size_t)(id)]) * d)
+#define DE_DONOR(k, r) (cfg.resample ? DE_HIST(r, k) : DE_SLOT(k))
 
     const bool is_mut = kind == KIND_MUTATION;
     double r1 = 0.0, r2 = 0.0;
     const double *pm = nullptr, *pn = nullptr, *pb = nullptr, *pz = nullptr;
     bool has_base = false;
     if (kind == KIND_DE) {
-        pm = DE_DONOR(i1); pn = DE_DONOR(i2);
+        pm = DE_DONOR(i1, hr1); pn = DE_DONOR(i2, hr2);
         has_base = cfg.proposal == 0 && ctx.in_burnin != 0;
         if (has_base) {
-            if (ctx.exact_base) pb = DE_DONOR(i0);
+            if (ctx.exact_base) pb = DE_SLOT(i0);                  // select_base always reads the current group
             else {
                 // select_base (crossover.jl:282-289) on the sweep-start weights: first slot whose
                 // running weight sum is not below u*sum (StatsBase cumulative walk)
@@ -133,7 +143,7 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
             }
         }
     } else if (kind == KIND_SNOOKER) {
-        pz = DE_DONOR(i0); pm = DE_DONOR(i1); pn = DE_DONOR(i2);
+        pz = DE_DONOR(i0, hr0); pm = DE_DONOR(i1, hr1); pn = DE_DONOR(i2, hr2);
         // project (utilities.jl:239-246): v1 = sum(p1.*pd), v2 = sum(pd.^2)
         double v1m = 0.0, v1n = 0.0, v2 = 0.0;
         for (int k = co.lane(); k < d; k += co.width()) {
@@ -146,6 +156,8 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
         r1 = v1m / v2; r2 = v1n / v2;
     }
 #undef DE_DONOR
+#undef DE_HIST
+#undef DE_SLOT
 
     const uint8_t *mask = (ctx.block >= 0 && !is_mut) ? cfg.blocks + (size_t)ctx.block * d : nullptr;
     bool ok = true;
@@ -221,6 +233,7 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     if (co.lane() == 0) {
         ctx.next_w[p] = acc ? wprop : wcur;
         ctx.next_id[p] = ctx.cur_id[p];
+        if (ctx.next_pos) ctx.next_pos[ctx.cur_id[p] - cfg.group_begin * Np] = p;
         ctx.next_acc[p] = acc ? 1 : 0;
         if (ctx.tr_w) { ctx.tr_w[p] = wprop; ctx.tr_adj[p] = adj; ctx.tr_acc[p] = acc ? 1 : 0; }
     }

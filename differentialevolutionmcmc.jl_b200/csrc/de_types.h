@@ -58,6 +58,7 @@ DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n
 
 struct ConfigDev {
     int32_t Np, d, G_local, group_begin, proposal, burnin, n_blocks;
+    int32_t resample;         // de.sample = resample: donors are (row, id) cells of the history
     double eps, sigma, kappa, theta_snooker;
     const double *lo, *hi;    // [d]
     const uint8_t *blocks;    // [n_blocks][d]
@@ -83,6 +84,11 @@ struct SweepCtx {
     const double *base_tot;   // [G_local]
     // tape slices of this sweep, local shard (replay only)
     const uint8_t *t_kind; const int32_t *t_idx; const double *t_g1, *t_g2, *t_uacc, *t_noise; const uint8_t *t_keep;
+    const int32_t *t_idx_row; // resample: history row of each donor (t_idx then holds the particle id)
+    // resample (crossover.jl:113-124): the history by position, its id -> position map per row, and
+    // the number of rows stored before this iteration (de.iter - 1)
+    const double *hist_theta; const int32_t *hist_pos; int64_t donor_rows;
+    int32_t *next_pos;        // id -> position map of the row being written, or NULL
     // proposal scratch
     double *prop_theta;       // [P_local][d]
     double *prop_prior;       // [P_local]

@@ -58,6 +58,9 @@ struct demcmc_handle {
     double *hist_theta = nullptr, *hist_w = nullptr;
     int32_t *hist_id = nullptr;
     uint8_t *hist_acc = nullptr;
+    int32_t *hist_pos = nullptr;                        // resample: [row][id] -> position holding that id
+    int64_t n0 = 0;                                     // de.n_initial: history rows before iteration 1
+    bool has_history = false;                           // the n_initial prior rows were uploaded
     double *scr_theta = nullptr, *scr_w = nullptr;      // 3 scratch rows
     int32_t *scr_id = nullptr;
     uint8_t *scr_acc = nullptr;
@@ -107,25 +110,29 @@ static Row row_of(demcmc_handle *h, bool hist, int64_t idx)
 }
 static Row cur_row(demcmc_handle *h) { return h->cur_hist >= 0 ? row_of(h, true, h->cur_hist) : row_of(h, false, h->cur_scratch); }
 
+// history rows: [0, n0) = the n_initial prior rows (utilities.jl:35-39), row n0 + it = iteration it
 static int grow_history(demcmc_handle *h, int64_t need)
 {
     if (need <= h->hist_cap) return 0;
     int64_t cap = std::max<int64_t>(need, h->hist_cap * 2);
     const size_t P = h->P, d = h->d;
+    const int64_t have = h->hist_cap > 0 ? h->n0 + h->iters_done : 0;
     double *nt = (double *)be::dmalloc(sizeof(double) * cap * P * d);
     double *nw = (double *)be::dmalloc(sizeof(double) * cap * P);
     int32_t *ni = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P);
     uint8_t *na = (uint8_t *)be::dmalloc(cap * P);
-    if (!nt || !nw || !ni || !na) return fail(DEMCMC_ENOMEM, "history of %lld rows does not fit on the device", (long long)cap);
-    if (h->iters_done > 0) {
-        BE(be::d2d(nt, h->hist_theta, sizeof(double) * h->iters_done * P * d));
-        BE(be::d2d(nw, h->hist_w, sizeof(double) * h->iters_done * P));
-        BE(be::d2d(ni, h->hist_id, sizeof(int32_t) * h->iters_done * P));
-        BE(be::d2d(na, h->hist_acc, h->iters_done * P));
+    int32_t *np = h->cfg.donors ? (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P) : nullptr;
+    if (!nt || !nw || !ni || !na || (h->cfg.donors && !np)) return fail(DEMCMC_ENOMEM, "history of %lld rows does not fit on the device", (long long)cap);
+    if (have > 0) {
+        BE(be::d2d(nt, h->hist_theta, sizeof(double) * have * P * d));
+        BE(be::d2d(nw, h->hist_w, sizeof(double) * have * P));
+        BE(be::d2d(ni, h->hist_id, sizeof(int32_t) * have * P));
+        BE(be::d2d(na, h->hist_acc, have * P));
+        if (np) BE(be::d2d(np, h->hist_pos, sizeof(int32_t) * have * P));
         BE(be::sync());
     }
-    be::dfree(h->hist_theta); be::dfree(h->hist_w); be::dfree(h->hist_id); be::dfree(h->hist_acc);
-    h->hist_theta = nt; h->hist_w = nw; h->hist_id = ni; h->hist_acc = na; h->hist_cap = cap;
+    be::dfree(h->hist_theta); be::dfree(h->hist_w); be::dfree(h->hist_id); be::dfree(h->hist_acc); be::dfree(h->hist_pos);
+    h->hist_theta = nt; h->hist_w = nw; h->hist_id = ni; h->hist_acc = na; h->hist_pos = np; h->hist_cap = cap;
     return 0;
 }
 
@@ -169,13 +176,19 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     if (cfg->n_blocks < 0 || (cfg->n_blocks > 0 && !cfg->blocks)) return fail(DEMCMC_EINVAL, "blocks missing");
     if (cfg->proposal < 0 || cfg->proposal > 2) return fail(DEMCMC_EINVAL, "unknown generate_proposal %d", cfg->proposal);
     if (cfg->store_every > 1) return fail(DEMCMC_EUNSUPPORTED, "thinning (store_every > 1) is not built yet");
-    if (cfg->n_initial != 0) return fail(DEMCMC_EUNSUPPORTED, "n_initial > 0 / sample = resample is not built yet");
+    if (cfg->n_initial < 0 || cfg->donors < 0 || cfg->donors > 1) return fail(DEMCMC_EINVAL, "bad n_initial / donors");
+    if (cfg->donors == DEMCMC_DONORS_HISTORY) {
+        // resample (crossover.jl:113-124) draws from rows 1:de.iter-1: there must be rows to draw from
+        if ((int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3) return fail(DEMCMC_EINVAL, "sample = resample needs n_initial prior rows (at least 3 stored particles)");
+        if (cfg->group_count > 0 && cfg->group_count != cfg->n_groups) return fail(DEMCMC_EUNSUPPORTED, "sample = resample reads the history of every particle id: it is not sharded over GPUs yet");
+    }
     if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
     if (be::set_device(cfg->device) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
 
     demcmc_handle *h = new demcmc_handle();
     h->cfg = *cfg;
     h->d = cfg->d;
+    h->n0 = cfg->n_initial;
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
     h->P = h->G_local * cfg->Np;
@@ -230,7 +243,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     ConfigDev &c = h->dcfg;
     c.Np = cfg->Np; c.d = cfg->d; c.G_local = h->G_local; c.group_begin = cfg->group_begin; c.proposal = cfg->proposal;
     c.burnin = cfg->burnin; c.n_blocks = cfg->n_blocks; c.eps = cfg->eps; c.sigma = cfg->sigma; c.kappa = cfg->kappa;
-    c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
+    c.resample = cfg->donors; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
     *out = h;
     return 0;
 }
@@ -242,7 +255,7 @@ int demcmc_destroy(demcmc_handle *h)
     be::sync();
     if (h->comm) be::comm_destroy(h->comm);
     for (void *p : h->model_allocs) be::dfree(p);
-    void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
+    void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
                      h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
                      h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
@@ -346,9 +359,33 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
     return 0;
 }
 
+int demcmc_set_history(demcmc_handle *h, const double *rows)
+{
+    if (!h || !rows) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->n0 <= 0) return fail(DEMCMC_EINVAL, "the handle was created with n_initial = 0");
+    if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_history must come before the first run");
+    if (h->G_local != h->cfg.n_groups) return fail(DEMCMC_EUNSUPPORTED, "initial history rows of a sharded job");
+    BE(be::set_device(h->cfg.device));
+    if (int rc = grow_history(h, h->n0)) return rc;
+    const size_t P = h->P, d = h->d, n = (size_t)h->n0 * P;
+    // initialize_samples (utilities.jl:35-39): samples[i, :, p] by particle id; before any
+    // migration id == position, accept = false and lp = 0.0 (utilities.jl:18-20)
+    std::vector<int32_t> idv(n);
+    for (size_t i = 0; i < n; ++i) idv[i] = (int32_t)(i % P);
+    BE(be::h2d(h->hist_theta, rows, sizeof(double) * n * d));
+    BE(be::h2d(h->hist_id, idv.data(), sizeof(int32_t) * n));
+    if (h->hist_pos) BE(be::h2d(h->hist_pos, idv.data(), sizeof(int32_t) * n));
+    BE(be::dzero(h->hist_w, sizeof(double) * n));
+    BE(be::dzero(h->hist_acc, n));
+    BE(be::sync());
+    h->has_history = true;
+    return 0;
+}
+
 int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids)
 {
-    if (!h || !theta) return fail(DEMCMC_EINVAL, "null argument");
+    if (!h) return fail(DEMCMC_EINVAL, "null argument");
+    if (!theta && !(h->n0 > 0 && h->has_history)) return fail(DEMCMC_EINVAL, "null theta (allowed only after demcmc_set_history: init_particle then starts from samples[1, :, id])");
     if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model must come before set_state");
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
@@ -357,7 +394,8 @@ int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids)
     Row r = row_of(h, false, 0);
     std::vector<int32_t> idv(P);
     for (size_t p = 0; p < P; ++p) idv[p] = ids ? ids[p] : (int32_t)(h->cfg.group_begin * h->cfg.Np + p);
-    BE(be::h2d(r.theta, theta, sizeof(double) * P * d));
+    if (theta) BE(be::h2d(r.theta, theta, sizeof(double) * P * d));
+    else BE(be::d2d(r.theta, h->hist_theta, sizeof(double) * P * d));       // utilities.jl:15
     BE(be::h2d(r.id, idv.data(), sizeof(int32_t) * P));
     BE(be::dzero(r.acc, P));
     BE(be::sync());
@@ -377,11 +415,13 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     const int Np = cfg.Np, Gt = cfg.n_groups, G = h->G_local, P = h->P, d = h->d, B = h->B;
     const int64_t Pt = (int64_t)Gt * Np, S = n_iter * B;
     const int64_t pbeg = (int64_t)cfg.group_begin * Np;
-    if (int rc = grow_history(h, h->iters_done + n_iter)) return rc;
+    if (h->n0 > 0 && !h->has_history) return fail(DEMCMC_ESTATE, "n_initial > 0: demcmc_set_history must come before run");
+    if (cfg.donors && h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "sample = resample is not sharded over GPUs yet");
+    if (int rc = grow_history(h, h->n0 + h->iters_done + n_iter)) return rc;
 
     // ---- replay: upload the local shard of the tape ------------------------------------------------
     uint8_t *t_kind = nullptr, *t_keep = nullptr;
-    int32_t *t_idx = nullptr;
+    int32_t *t_idx = nullptr, *t_idx_row = nullptr;
     double *t_g1 = nullptr, *t_g2 = nullptr, *t_uacc = nullptr, *t_noise = nullptr;
     std::vector<uint8_t> hk;          // host copy of local kinds / idx for the planner
     std::vector<int32_t> hi;
@@ -392,6 +432,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             return fail(DEMCMC_EINVAL, "tape misses a required array");
         if (cfg.kappa != 1.0 && !tape->keep) return fail(DEMCMC_EINVAL, "kappa != 1 needs tape.keep");
         if (Gt > 1 && (!tape->mig_n || !tape->mig_groups || !tape->mig_pick_u)) return fail(DEMCMC_EINVAL, "tape misses the migration arrays");
+        if (cfg.donors && !tape->idx_row) return fail(DEMCMC_EINVAL, "sample = resample needs tape.idx_row");
         auto shard = [&](const void *src, size_t elem, size_t per_particle) -> void * {
             // [S][Pt][per] -> [S][P][per]
             const size_t rowb = elem * per_particle;
@@ -406,19 +447,33 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         };
         t_kind = (uint8_t *)shard(tape->kind, 1, 1);
         t_idx = (int32_t *)shard(tape->idx, 4, 3);
+        if (cfg.donors) t_idx_row = (int32_t *)shard(tape->idx_row, 4, 3);
         t_g1 = (double *)shard(tape->gamma1, 8, 1);
         t_g2 = (double *)shard(tape->gamma2, 8, 1);
         t_uacc = (double *)shard(tape->u_acc, 8, 1);
         t_noise = (double *)shard(tape->noise, 8, d);
         if (cfg.kappa != 1.0) t_keep = (uint8_t *)shard(tape->keep, 1, d);
-        if (!t_kind || !t_idx || !t_g1 || !t_g2 || !t_uacc || !t_noise || (cfg.kappa != 1.0 && !t_keep)) { cleanup(); return fail(DEMCMC_ENOMEM, "tape upload failed: %s", be::last_error()); }
+        if (!t_kind || !t_idx || (cfg.donors && !t_idx_row) || !t_g1 || !t_g2 || !t_uacc || !t_noise || (cfg.kappa != 1.0 && !t_keep)) { cleanup(); return fail(DEMCMC_ENOMEM, "tape upload failed: %s", be::last_error()); }
         hk.resize((size_t)S * P); hi.resize((size_t)S * P * 3);
         for (int64_t s = 0; s < S; ++s) {
             memcpy(hk.data() + (size_t)s * P, tape->kind + (size_t)s * Pt + pbeg, P);
             memcpy(hi.data() + (size_t)s * P * 3, tape->idx + ((size_t)s * Pt + pbeg) * 3, sizeof(int32_t) * P * 3);
         }
         for (size_t i = 0; i < hk.size(); ++i) if (hk[i] > KIND_MUTATION) { cleanup(); return fail(DEMCMC_EINVAL, "tape.kind[%zu] = %d", i, hk[i]); }
-        for (size_t i = 0; i < hi.size(); ++i) if (hk[i / 3] != KIND_MUTATION && !(hk[i / 3] == KIND_DE && i % 3 == 0 && hi[i] < 0) && (hi[i] < 0 || hi[i] >= Np)) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx[%zu] = %d out of range", i, hi[i]); }
+        for (size_t i = 0; i < hi.size(); ++i) {
+            const uint8_t k = hk[i / 3];
+            if (k == KIND_MUTATION) continue;
+            const bool base = k == KIND_DE && i % 3 == 0;          // slot of the base particle in the group, or -1
+            if (base && hi[i] < 0) continue;
+            const int64_t lim = (cfg.donors && !base) ? Pt : Np;   // resample donors are particle ids
+            if (hi[i] < 0 || hi[i] >= lim) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx[%zu] = %d out of range", i, hi[i]); }
+            if (cfg.donors && !base) {
+                const int64_t sw = (int64_t)(i / 3) / P, pl = (int64_t)(i / 3) % P;
+                const int64_t ub = h->n0 + h->iters_done + sw / B;                            // rows 1:de.iter-1
+                const int32_t r = tape->idx_row[((size_t)sw * Pt + pbeg + pl) * 3 + i % 3];
+                if (r < 0 || r >= ub) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx_row of sweep %lld particle %lld = %d outside the %lld stored rows", (long long)sw, (long long)pl, r, (long long)ub); }
+            }
+        }
     }
 
     // ---- trace and migration log of this call ------------------------------------------------------
@@ -485,7 +540,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             // destination row: the history row of the iteration on its last block, else scratch
             Row next;
             int next_scratch = -1;
-            if (b == B - 1) next = row_of(h, true, itg);
+            if (b == B - 1) next = row_of(h, true, h->n0 + itg);
             else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
             SweepCtx &ctx = u.h_ctx[s];
             memset(&ctx, 0, sizeof ctx);
@@ -498,21 +553,25 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 ctx.t_kind = t_kind + (size_t)s_local * P; ctx.t_idx = t_idx + (size_t)s_local * P * 3;
                 ctx.t_g1 = t_g1 + (size_t)s_local * P; ctx.t_g2 = t_g2 + (size_t)s_local * P; ctx.t_uacc = t_uacc + (size_t)s_local * P;
                 ctx.t_noise = t_noise + (size_t)s_local * P * d; ctx.t_keep = t_keep ? t_keep + (size_t)s_local * P * d : nullptr;
+                ctx.t_idx_row = t_idx_row ? t_idx_row + (size_t)s_local * P * 3 : nullptr;
             }
             ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb;
             ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
+            // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)
+            ctx.hist_theta = h->hist_theta; ctx.hist_pos = h->hist_pos; ctx.donor_rows = h->n0 + itg;
+            ctx.next_pos = (b == B - 1 && h->hist_pos) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
             }
-            if (b == B - 1) { h->cur_hist = itg; }
+            if (b == B - 1) { h->cur_hist = h->n0 + itg; }
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
         PlanInput pin;
         pin.seed = cfg.seed; pin.Np = Np; pin.G_local = G; pin.group_begin = cfg.group_begin; pin.G_total = Gt;
-        pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker;
+        pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
         const int64_t s_first = it0 * B + b;
         pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
         pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
@@ -579,7 +638,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                     if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
                     incoming = h->d_stage_recv;
                 }
-                BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc));
+                BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc,
+                                          (h->hist_pos && h->cur_hist >= 0) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr));
             }
             mig_events.emplace_back(it, ms);
         }
@@ -593,7 +653,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // consecutive iterations without a migration and without a sweep-start snapshot overlap on
         // the device: plan them as one chunk (planner.h)
         int n = 1;
-        if (!needs_snapshot(it) && h->max_chunk > 1) {
+        if (!needs_snapshot(it) && h->max_chunk > 1 && !cfg.donors) {   // resample reads rows of earlier sweeps: one sweep per chunk
             MigSchedule m2;
             while (it + n < n_iter && n < h->max_chunk) {
                 get_mig(it + n, m2);
@@ -652,8 +712,8 @@ static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *a
         if (ds && be::dzero(ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
         if (dl && be::dzero(dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
         if (da && be::dzero(da, n_rows * P)) rc = DEMCMC_ECUDA;
-        if (!rc && h->iters_done > 0 &&
-            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, h->iters_done, n0, n_rows, (int32_t)P, (int32_t)d,
+        if (!rc && n0 + h->iters_done > 0 && (n0 == 0 || h->has_history) &&
+            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, n0 + h->iters_done, 0, n_rows, (int32_t)P, (int32_t)d,
                                      h->cfg.group_begin * h->cfg.Np, ds, dl, da)) rc = DEMCMC_ECUDA;
         if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
         if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
@@ -671,7 +731,7 @@ int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? 
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
 {
     if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
-    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld iterations run", (long long)row0, (long long)(row0 + n_rows), (long long)h->iters_done);
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n0 + h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)(h->n0 + h->iters_done));
     if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "chains of a sharded job: gather demcmc_get_history_by_slot on the host");
     if (!h->has_state) return fail(DEMCMC_ESTATE, "no state");
     BE(be::set_device(h->cfg.device));
@@ -696,6 +756,7 @@ int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, d
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
     if (n_rows == 0) return 0;
+    row0 += h->n0;                                           // rows of the iterations come after the n_initial rows
     if (theta) BE(be::d2h(theta, h->hist_theta + row0 * P * d, sizeof(double) * n_rows * P * d));
     if (w) BE(be::d2h(w, h->hist_w + row0 * P, sizeof(double) * n_rows * P));
     if (ids) BE(be::d2h(ids, h->hist_id + row0 * P, sizeof(int32_t) * n_rows * P));

@@ -916,14 +916,17 @@ __global__ void __launch_bounds__(128) k_mig_gather(ConfigDev cfg, MigArgs a, co
 
 // shift_particles! (migration.jl:109-116): position i receives the particle picked at position i-1
 __global__ void __launch_bounds__(128) k_mig_scatter(ConfigDev cfg, MigArgs a, const int32_t *picks, const double *stage,
-                                                     double *theta, double *w, int32_t *id, uint8_t *acc)
+                                                     double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos)
 {
     const int i = blockIdx.x, gl = a.groups[i] - cfg.group_begin;
     if (gl < 0 || gl >= cfg.G_local) return;
     const size_t p = (size_t)gl * cfg.Np + picks[i];
     const double *row = stage + (size_t)((i + a.n - 1) % a.n) * (cfg.d + 3);
     for (int k = threadIdx.x; k < cfg.d; k += blockDim.x) theta[p * cfg.d + k] = row[k];
-    if (threadIdx.x == 0) { w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2]; }
+    if (threadIdx.x == 0) {
+        w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2];
+        if (pos) pos[(int32_t)row[cfg.d + 1] - cfg.group_begin * cfg.Np] = (int32_t)p;
+    }
 }
 
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks)
@@ -940,9 +943,9 @@ int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *pic
     return 0;
 }
 int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
-                       double *w, int32_t *id, uint8_t *acc)
+                       double *w, int32_t *id, uint8_t *acc, int32_t *pos)
 {
-    k_mig_scatter<<<a.n, 128, 0, stream()>>>(cfg, a, picks, stage, theta, w, id, acc);
+    k_mig_scatter<<<a.n, 128, 0, stream()>>>(cfg, a, picks, stage, theta, w, id, acc, pos);
     LAUNCHED("k_mig_scatter");
     return 0;
 }

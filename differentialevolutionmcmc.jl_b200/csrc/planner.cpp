@@ -29,7 +29,10 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
                 int l = lp[j] + 1;                                   // its own previous update
                 if (!mutate) {
                     int dep[3], nd = 0;
-                    if (tk) {
+                    if (in.resample) {
+                        // only select_base still reads the current group (replay, burn-in)
+                        if (tk && tk[g * Np + j] == KIND_DE && base_dependency && base_dependency[s]) dep[nd++] = ti[(size_t)(g * Np + j) * 3];
+                    } else if (tk) {
                         const int32_t *ix = ti + (size_t)(g * Np + j) * 3;
                         if (tk[g * Np + j] == KIND_SNOOKER) { dep[nd++] = ix[0]; dep[nd++] = ix[1]; dep[nd++] = ix[2]; }
                         else { dep[nd++] = ix[1]; dep[nd++] = ix[2]; if (base_dependency && base_dependency[s]) dep[nd++] = ix[0]; }

@@ -29,6 +29,7 @@ struct PlanInput {
     int32_t Np, G_local, group_begin, G_total;
     int32_t proposal;          // 0 random_gamma
     double beta, theta_snooker;
+    bool resample;             // donors come from stored rows (crossover.jl:113-124): no donor dependencies inside a sweep
     // replay: tape slices [sweep][P_local] of the chunk's FIRST sweep onwards, else nullptr
     const uint8_t *t_kind;     // [n_sweeps][P_local]
     const int32_t *t_idx;      // [n_sweeps][P_local][3]

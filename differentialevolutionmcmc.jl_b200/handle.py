@@ -18,7 +18,7 @@ class Handle:
 
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None, seed=0,
-                 device=0, group_begin=0, group_count=0, trace=False, store_every=1):
+                 device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False):
         self._h = C.c_void_p()
         self.lo, self.hi = f8(lo), f8(hi)
         if self.lo.shape != (d,) or self.hi.shape != (d,):
@@ -28,7 +28,7 @@ class Handle:
         prop = PROPOSALS[proposal] if isinstance(proposal, str) else int(proposal)
         self.cfg = _ffi.Config(_ffi.ABI_VERSION, n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa,
                                theta_snooker, prop, nb, ptr(self.blocks, _bp), ptr(self.lo, _dp), ptr(self.hi, _dp),
-                               int(seed) & (2**64 - 1), device, group_begin, group_count, 0, int(bool(trace)), store_every)
+                               int(seed) & (2**64 - 1), device, group_begin, group_count, int(bool(resample)), int(bool(trace)), store_every)
         self.n_groups, self.Np, self.d = n_groups, Np, d
         self.G_local = group_count if group_count > 0 else n_groups
         self.P = self.G_local * Np
@@ -99,8 +99,15 @@ class Handle:
         check(_ffi.lib().demcmc_set_model(self._h, C.byref(m)))
 
     # ---- state ---------------------------------------------------------------------------------
-    def set_state(self, theta, ids=None):
-        th = f8(theta).reshape(self.P, self.d)
+    def set_history(self, rows):
+        """initialize_samples (utilities.jl:29-41): rows[n_initial][P][d], row i = the i-th sample_prior()
+        draw of every particle id."""
+        r = f8(rows).reshape(self.n_initial, self.P, self.d)
+        check(_ffi.lib().demcmc_set_history(self._h, ptr(r, _dp)))
+
+    def set_state(self, theta=None, ids=None):
+        """theta=None after set_history: init_particle starts from samples[1, :, id] (utilities.jl:15)."""
+        th = None if theta is None else f8(theta).reshape(self.P, self.d)
         idv = None if ids is None else np.ascontiguousarray(ids, dtype=np.int32)
         check(_ffi.lib().demcmc_set_state(self._h, ptr(th, _dp), ptr(idv, _ip)))
 
@@ -130,7 +137,7 @@ class Handle:
         t = _ffi.Tape(ptr(get("mig_u", "f8"), _dp), ptr(get("mig_n", "i4"), _ip), ptr(get("mig_groups", "i4"), _ip),
                       ptr(get("mig_pick_u", "f8"), _dp), ptr(get("kind", "u1"), _bp), ptr(get("idx", "i4"), _ip),
                       ptr(get("gamma1", "f8"), _dp), ptr(get("gamma2", "f8"), _dp), ptr(get("u_acc", "f8"), _dp),
-                      ptr(get("noise", "f8"), _dp), ptr(get("keep", "u1"), _bp))
+                      ptr(get("noise", "f8"), _dp), ptr(get("keep", "u1"), _bp), ptr(get("idx_row", "i4"), _ip))
         check(_ffi.lib().demcmc_replay(self._h, C.byref(t), int(n_iter)))
         self.iterations += n_iter
         self._last_iters = n_iter

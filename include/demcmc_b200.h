@@ -38,6 +38,8 @@ enum { DEMCMC_PRIOR_FLAT = 0, DEMCMC_PRIOR_NORMAL = 1, DEMCMC_PRIOR_HALFCAUCHY =
        DEMCMC_PRIOR_UNIFORM = 3, DEMCMC_PRIOR_BETA = 4, DEMCMC_PRIOR_NORMAL_REF = 5 };
 /* DE.generate_proposal (src/structs.jl:71, src/crossover.jl:154-226) */
 enum { DEMCMC_RANDOM_GAMMA = 0, DEMCMC_FIXED_GAMMA = 1, DEMCMC_VARIABLE_GAMMA = 2 };
+/* DE.sample (src/structs.jl:74): where the donor particles come from */
+enum { DEMCMC_DONORS_CURRENT = 0, DEMCMC_DONORS_HISTORY = 1 };
 /* per-particle update kind on the replay tape */
 enum { DEMCMC_KIND_DE = 0, DEMCMC_KIND_SNOOKER = 1, DEMCMC_KIND_MUTATION = 2 };
 
@@ -74,7 +76,7 @@ typedef struct {
     int32_t Np;              /* de.Np (>= 3: samplepair needs two donors besides the target) */
     int32_t d;
     int32_t burnin;          /* de.burnin */
-    int32_t n_initial;       /* de.n_initial (history rows before iteration 1; resample is not built yet) */
+    int32_t n_initial;       /* de.n_initial: prior rows stored before iteration 1 (utilities.jl:35-39) */
     double alpha, beta, eps, sigma, kappa, theta_snooker; /* de.α β ϵ σ κ θsnooker */
     int32_t proposal;        /* DEMCMC_RANDOM_GAMMA ... */
     int32_t n_blocks;        /* 0: blocking_on(de) == false; else blocking on every iteration */
@@ -84,7 +86,10 @@ typedef struct {
     int32_t device;          /* CUDA device ordinal */
     int32_t group_begin;     /* first group held by this handle (multi-GPU: groups shard over ranks) */
     int32_t group_count;     /* groups held by this handle; 0 => all */
-    int32_t reserved0;       /* must be 0 */
+    int32_t donors;          /* de.sample (src/structs.jl:74): DEMCMC_DONORS_CURRENT = `sample` (donors from the
+                                current group, crossover.jl:138-140), DEMCMC_DONORS_HISTORY = `resample`
+                                (DE-MCz: donors from de.samples[1:de.iter-1, :, :], crossover.jl:113-124;
+                                needs n_initial > 0 and demcmc_set_history; single GPU) */
     int32_t trace;           /* 1: keep per-sweep proposals / proposal weights / log_adj for
                                 demcmc_get_trace (parity tests) */
     int32_t store_every;     /* 1 = keep every iteration (reference behaviour, utilities.jl:161-180) */
@@ -105,6 +110,8 @@ typedef struct {
     const double  *u_acc;       /* [S][P]       rand() in accept      (src/utilities.jl:57)       */
     const double  *noise;       /* [S][P][d]    b_k or N(0,sigma) draws (crossover.jl:168, mutation.jl:18) */
     const uint8_t *keep;        /* [S][P][d]    recombination restores theta_t,k; NULL if kappa==1 */
+    const int32_t *idx_row;     /* [S][P][3]    resample only: 0-based row of de.samples of each donor; idx then
+                                                holds the donor's 0-based particle id (the DE base stays a slot) */
 } demcmc_tape;
 
 typedef struct {
@@ -125,8 +132,13 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out);
 int demcmc_destroy(demcmc_handle *h);
 /* DEModel(; loglike = GPULoglike(...), prior_loglike = ..., data) (src/structs.jl:176-189) */
 int demcmc_set_model(demcmc_handle *h, const demcmc_model *model);
+/* initialize_samples (src/utilities.jl:29-41) when n_initial > 0: rows[n_initial][P][d], row i = the
+ * i-th sample_prior() draw of every particle id; they become rows 1..n_initial of de.samples */
+int demcmc_set_history(demcmc_handle *h, const double *rows);
 /* sample_init / init_particle (src/main.jl:263-271, src/utilities.jl:13-22): theta[P_local][d] by
- * position, ids[P_local] (NULL: id = global position).  Evaluates the initial weights on the device. */
+ * position, ids[P_local] (NULL: id = global position).  Evaluates the initial weights on the device.
+ * theta may be NULL after demcmc_set_history: the particles then start from samples[1, :, id]
+ * (utilities.jl:15). */
 int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids);
 /* the `for iter = 1:n_iter ... stepfun(model, de, groups)` loop of _sample (src/main.jl:33-38),
  * i.e. n_iter x step!/pstep! (src/main.jl:84-107), entirely on the device */
@@ -136,14 +148,14 @@ int demcmc_replay(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter);
 
 /* de.samples (src/utilities.jl:29-41,161-180): out[n_rows][d][P_local] in Julia order (row
  * fastest, then parameter, then particle id - group_begin*Np); n_rows = iterations run so far +
- * n_initial; rows < n_initial are zero-filled */
+ * n_initial; rows < n_initial are the prior rows of demcmc_set_history */
 int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows);
 /* Particle.accept / Particle.lp (src/structs.jl:202-208, utilities.jl:207-208): [n_rows][P_local],
  * row fastest, column = particle id - group_begin*Np */
 int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows);
 int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows);
-/* bundle_samples (src/main.jl:222-250) on the device, for history rows [row0, row0+n_rows) (row0 =
- * burnin when discard_burnin): out[n_rows][d+2][P] in Julia order (= C order [P][d+2][n_rows]), the
+/* bundle_samples (src/main.jl:222-250) on the device, for rows [row0, row0+n_rows) of de.samples
+ * (n_initial rows included, as the reference indexes them; row0 = burnin when discard_burnin): out[n_rows][d+2][P] in Julia order (= C order [P][d+2][n_rows]), the
  * memory layout of the Array the reference hands to MCMCChains.Chains.  Parameter columns of chain c
  * are the draws of particle id c; the last two columns, "acceptance" and "lp", belong to the
  * particle sitting at final position c -- the reference's own by-position quirk (main.jl:232-241). */

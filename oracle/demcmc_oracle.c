@@ -399,6 +399,7 @@ typedef struct {
     particle **slot;     /* [P] pointers: groups[g][j] = slot[g*Np+j] */
     uint8_t *accept;     /* [n_rows][P] row fastest, column = id */
     double *lp;
+    const double *samples; /* de.samples, [n_rows][d][P] row fastest (resample reads it) */
 } sampler;
 
 #define TAPE_GET(field, i, gen) ((S->tin && S->tin->field) ? S->tin->field[i] : (gen))
@@ -415,6 +416,15 @@ static void mh_update(sampler *S, particle *cur, const double *prop, double wpro
     if (S->trace && S->trace->accepted) S->trace->accepted[ti] = (uint8_t)acc;
 }
 
+static int64_t rand_index64(double u, int64_t n) { int64_t i = (int64_t)(u * (double)n); return i >= n ? n - 1 : i; }
+
+/* resample (crossover.jl:113-124): Theta = de.samples[row, :, id] */
+static void history_theta(const sampler *S, int64_t row, int id, double *out)
+{
+    const int d = S->cfg->d;
+    for (int k = 0; k < d; ++k) out[k] = S->samples[row + S->n_rows * (k + (int64_t)d * id)];
+}
+
 /* one group's mutate_or_crossover! (main.jl:199-207) for sweep s (block bl or -1) */
 static void update_group(sampler *S, int g, int64_t it, int bl)
 {
@@ -425,8 +435,10 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
     int64_t de_iter = it + 1 + c->n_initial;
     particle **grp = S->slot + (size_t)g * Np;
     double u2[2];
-    double *prop = (double *)malloc(sizeof(double) * (size_t)d * 2);
-    double *noise = prop + d, *snap_theta = NULL, *snap_w = NULL;
+    double *prop = (double *)malloc(sizeof(double) * (size_t)d * 5);
+    double *noise = prop + d, *h0 = prop + 2 * d, *h1 = prop + 3 * d, *h2 = prop + 4 * d, *snap_theta = NULL, *snap_w = NULL;
+    /* resample draws from the ub = de.iter - 1 rows stored so far, all P ids (crossover.jl:115-116,124) */
+    const int64_t ub = row, n_cell = ub * (int64_t)S->P;
     double *wbuf = (double *)malloc(sizeof(double) * (size_t)Np);
     if (c->base_snapshot) {
         snap_theta = (double *)malloc(sizeof(double) * (size_t)Np * d);
@@ -444,7 +456,7 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
         particle *pt = grp[j];
         uint32_t unit = (uint32_t)(g * Np + j);
         int64_t ti = s * S->P + unit;
-        int kind, i0 = -1, i1 = -1, i2 = -1;
+        int kind, i0 = -1, i1 = -1, i2 = -1, r0 = -1, r1 = -1, r2 = -1;
         double g1 = 0.0, g2 = 0.0, u_snk = 0.0, u_base = 0.0, log_adj = 0.0;
 
         if (mutate) {
@@ -495,12 +507,25 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
                 }
                 /* Pm,Pn = sample(setdiff(group,[Pt]), 2; replace=false) (crossover.jl:158-160);
                  * StatsBase.samplepair: i1=rand(1:n); i2=rand(1:n-1); i2==i1 && (i2=n) */
+                const double *pm, *pn;
+                if (c->resample) {
+                    /* sample(CartesianIndices(samples[1:ub, 1, :]), 2; replace=false): samplepair over
+                     * the ub x P cells, column-major cell -> (row, id) */
+                    int64_t a = rand_index64(ui[0], n_cell), b = rand_index64(ui[1], n_cell - 1);
+                    if (b == a) b = n_cell - 1;
+                    r1 = (int)(a % ub); i1 = (int)(a / ub); r2 = (int)(b % ub); i2 = (int)(b / ub);
+                    if (S->tin && S->tin->idx) { i1 = S->tin->idx[ti * 3 + 1]; i2 = S->tin->idx[ti * 3 + 2]; r1 = S->tin->idx_row[ti * 3 + 1]; r2 = S->tin->idx_row[ti * 3 + 2]; }
+                    history_theta(S, r1, i1, h1); history_theta(S, r2, i2, h2);
+                    pm = h1; pn = h2;
+                } else {
                 int n = Np - 1;
                 int a = rand_index(ui[0], n), b = rand_index(ui[1], n - 1);
                 if (b == a) b = n - 1;
                 i1 = a >= j ? a + 1 : a;
                 i2 = b >= j ? b + 1 : b;
                 if (S->tin && S->tin->idx) { i1 = S->tin->idx[ti * 3 + 1]; i2 = S->tin->idx[ti * 3 + 2]; }
+                pm = grp[i1]->theta; pn = grp[i2]->theta;
+                }
                 if (c->proposal == ORC_RANDOM_GAMMA) {
                     g1 = 0.5 + (1.0 - 0.5) * u2[0];                       /* crossover.jl:162 */
                     g2 = de_iter > c->burnin ? 0.0 : 0.5 + (1.0 - 0.5) * u2[1]; /* :164 */
@@ -511,9 +536,23 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
                 }
                 g1 = TAPE_GET(gamma1, ti, g1);
                 g2 = TAPE_GET(gamma2, ti, g2);
-                orc_de_proposal(pt->theta, grp[i1]->theta, grp[i2]->theta, pb, g1, g2, noise, d, prop);
+                orc_de_proposal(pt->theta, pm, pn, pb, g1, g2, noise, d, prop);
             } else {
                 /* Pz,Pm,Pn = sample(group, 3; replace=false): whole group incl. Pt (crossover.jl:241) */
+                if (c->resample) {
+                    /* three distinct cells of the history (crossover.jl:241 with de.sample = resample) */
+                    int64_t a = rand_index64(ui[0], n_cell), b = rand_index64(ui[1], n_cell - 1);
+                    if (b >= a) ++b;
+                    int64_t cc = rand_index64(ui[2], n_cell - 2), lo = a < b ? a : b, hi = a < b ? b : a;
+                    if (cc >= lo) ++cc;
+                    if (cc >= hi) ++cc;
+                    r0 = (int)(a % ub); i0 = (int)(a / ub); r1 = (int)(b % ub); i1 = (int)(b / ub); r2 = (int)(cc % ub); i2 = (int)(cc / ub);
+                    if (S->tin && S->tin->idx) {
+                        i0 = S->tin->idx[ti * 3]; i1 = S->tin->idx[ti * 3 + 1]; i2 = S->tin->idx[ti * 3 + 2];
+                        r0 = S->tin->idx_row[ti * 3]; r1 = S->tin->idx_row[ti * 3 + 1]; r2 = S->tin->idx_row[ti * 3 + 2];
+                    }
+                    history_theta(S, r0, i0, h0); history_theta(S, r1, i1, h1); history_theta(S, r2, i2, h2);
+                } else {
                 int a = rand_index(ui[0], Np), b = rand_index(ui[1], Np - 1);
                 if (b >= a) ++b;
                 int cc = rand_index(ui[2], Np - 2), lo = a < b ? a : b, hi = a < b ? b : a;
@@ -521,9 +560,12 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
                 if (cc >= hi) ++cc;
                 i0 = a; i1 = b; i2 = cc;
                 if (S->tin && S->tin->idx) { i0 = S->tin->idx[ti * 3]; i1 = S->tin->idx[ti * 3 + 1]; i2 = S->tin->idx[ti * 3 + 2]; }
+                memcpy(h0, grp[i0]->theta, sizeof(double) * d);   /* Pz as it is NOW (adjust_loglike reads it after the proposal) */
+                memcpy(h1, grp[i1]->theta, sizeof(double) * d); memcpy(h2, grp[i2]->theta, sizeof(double) * d);
+                }
                 g1 = 1.2 + (2.2 - 1.2) * u2[0];                           /* crossover.jl:249 */
                 g1 = TAPE_GET(gamma1, ti, g1);
-                orc_snooker_proposal(pt->theta, grp[i0]->theta, grp[i1]->theta, grp[i2]->theta, g1, noise, d, prop);
+                orc_snooker_proposal(pt->theta, h0, h1, h2, g1, noise, d, prop);
             }
             /* recombination! (crossover.jl:301-321) */
             if (c->kappa != 1.0) {
@@ -538,7 +580,7 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
             }
             /* reset! (crossover.jl:84,93) then adjust_loglike (crossover.jl:85) */
             if (bl >= 0) orc_reset(prop, pt->theta, c->blocks + (size_t)bl * d, d);
-            if (snooker) log_adj = orc_adjust_loglike(pt->theta, prop, grp[i0]->theta, d);
+            if (snooker) log_adj = orc_adjust_loglike(pt->theta, prop, h0, d);
         }
         TAPE_PUT(kind, ti, (uint8_t)kind);
         TAPE_PUT(u_snk, ti, u_snk);
@@ -546,6 +588,7 @@ static void update_group(sampler *S, int g, int64_t it, int bl)
         TAPE_PUT(gamma1, ti, g1);
         TAPE_PUT(gamma2, ti, g2);
         if (S->tout && S->tout->idx) { S->tout->idx[ti * 3] = i0; S->tout->idx[ti * 3 + 1] = i1; S->tout->idx[ti * 3 + 2] = i2; }
+        if (S->tout && S->tout->idx_row) { S->tout->idx_row[ti * 3] = r0; S->tout->idx_row[ti * 3 + 1] = r1; S->tout->idx_row[ti * 3 + 2] = r2; }
 
         double wprop = orc_posterior(c, S->model, prop);          /* evaluate_fitness! */
         orc_uniform2(c->seed, ST_ACC, (uint32_t)s, unit, 0, u2);
@@ -613,12 +656,16 @@ int orc_run(const orc_config *cfg, const orc_model *model, const double *theta0,
             int32_t *final_id, double *final_theta, double *final_weight)
 {
     if (!cfg || !model || !theta0 || cfg->Np < 3 || cfg->n_groups < 1 || cfg->d != model->d) return -1;
+    /* resample needs stored rows to draw from: n_initial prior rows (utilities.jl:35-39), at least 3 cells */
+    if (cfg->resample && (!samples || (int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3)) return -2;
+    if (cfg->resample && tape_in && tape_in->idx && !tape_in->idx_row) return -3;
+    if (cfg->n_initial > 0 && !samples) return -2;
     sampler Sv, *S = &Sv;
     memset(S, 0, sizeof(*S));
     int G = cfg->n_groups, Np = cfg->Np, d = cfg->d, P = G * Np;
     S->cfg = cfg; S->model = model; S->tin = tape_in; S->tout = tape_out; S->trace = trace;
     S->B = cfg->n_blocks > 0 ? cfg->n_blocks : 1; S->P = P;
-    S->n_iter = n_iter; S->n_rows = n_iter + cfg->n_initial;
+    S->n_iter = n_iter; S->n_rows = n_iter + cfg->n_initial; S->samples = samples;
     int own_acc = accept == NULL, own_lp = lp == NULL;
     S->accept = own_acc ? (uint8_t *)calloc((size_t)S->n_rows * P, 1) : accept;
     S->lp = own_lp ? (double *)calloc((size_t)S->n_rows * P, sizeof(double)) : lp;
@@ -630,6 +677,9 @@ int orc_run(const orc_config *cfg, const orc_model *model, const double *theta0,
     double *thetas = (double *)malloc(sizeof(double) * (size_t)P * d);
     S->slot = (particle **)malloc(sizeof(particle *) * (size_t)P);
     memcpy(thetas, theta0, sizeof(double) * (size_t)P * d);
+    /* init_particle (utilities.jl:15): with n_initial > 0 the particle starts from samples[1, :, id] */
+    if (cfg->n_initial > 0)
+        for (int p = 0; p < P; ++p) for (int k = 0; k < d; ++k) thetas[(size_t)p * d + k] = samples[0 + S->n_rows * (k + (int64_t)d * p)];
     /* sample_init (main.jl:263-271): ids 1..P group-major; weight via evaluate_fitness! */
     #pragma omp parallel for schedule(static) num_threads(cfg->n_threads > 1 ? cfg->n_threads : 1)
     for (int p = 0; p < P; ++p) {

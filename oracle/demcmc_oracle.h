@@ -68,6 +68,10 @@ typedef struct {
                                 documented native-mode deviation of the B200 path, burn-in only) */
     int32_t n_threads;       /* >1: one OpenMP task per group (main.jl:135-148) */
     uint64_t seed;           /* Philox key for generated draws */
+    int32_t resample;        /* 1: de.sample = resample (crossover.jl:113-124): donors are n distinct
+                                (row, id) cells of de.samples[1:de.iter-1, :, :] (DE-MCz); needs
+                                n_initial > 0 and the caller's prior rows in `samples` */
+    int32_t reserved;
 } orc_config;
 
 /* Structured replay tape.  All indices are 0-based slot indices inside
@@ -90,6 +94,8 @@ typedef struct {
     double  *u_acc;       /* [S][P]                                                      */
     double  *noise;       /* [S][P][d]       b_k (crossover) or N(0,sigma) (mutation)    */
     uint8_t *keep;        /* [S][P][d]       1 = recombination restores theta_t,k        */
+    int32_t *idx_row;     /* [S][P][3]       resample: history row of each donor (idx then holds
+                                             the donor's particle id); -1 where unused            */
 } orc_tape;
 
 /* Optional per-sweep trace for teacher-forced comparison.  NULL pointers are skipped. */
@@ -109,7 +115,10 @@ typedef struct {
 /* Runs n_iter iterations of step!/pstep! (main.jl:84-107).
  *  theta0[P][d]       initial state by slot (= id order, main.jl:263-271)
  *  samples            [n_rows][d][P] Fortran order exactly as utilities.jl:34 (row fastest),
- *                     n_rows = n_iter + n_initial; rows < n_initial are left untouched
+ *                     n_rows = n_iter + n_initial; rows < n_initial are the caller's
+ *                     initialize_samples prior draws (utilities.jl:29-41) and are left untouched;
+ *                     with n_initial > 0 the initial state is samples[0, :, id]
+ *                     (init_particle, utilities.jl:15) and theta0 is ignored
  *  accept [n_rows][P] (row fastest, column = particle id), lp likewise
  *  final_id[P]        particle id sitting at each slot after the run (0-based)
  *  final_theta[P][d], final_weight[P]

@@ -39,12 +39,13 @@ class _Config(C.Structure):
                 ("n_initial", C.c_int32), ("alpha", C.c_double), ("beta", C.c_double), ("eps", C.c_double),
                 ("sigma", C.c_double), ("kappa", C.c_double), ("theta_snooker", C.c_double),
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
-                ("base_snapshot", C.c_int32), ("n_threads", C.c_int32), ("seed", C.c_uint64)]
+                ("base_snapshot", C.c_int32), ("n_threads", C.c_int32), ("seed", C.c_uint64),
+                ("resample", C.c_int32), ("reserved", C.c_int32)]
 
 
 _TAPE_FIELDS = [("mig_u", "f8"), ("mig_n", "i4"), ("mig_groups", "i4"), ("mig_pick_u", "f8"), ("mig_slots", "i4"),
                 ("mut_u", "f8"), ("kind", "u1"), ("idx", "i4"), ("u_snk", "f8"), ("u_base", "f8"),
-                ("gamma1", "f8"), ("gamma2", "f8"), ("u_acc", "f8"), ("noise", "f8"), ("keep", "u1")]
+                ("gamma1", "f8"), ("gamma2", "f8"), ("u_acc", "f8"), ("noise", "f8"), ("keep", "u1"), ("idx_row", "i4")]
 _TRACE_FIELDS = [("prop_theta", "f8"), ("prop_weight", "f8"), ("log_adj", "f8"), ("accepted", "u1"),
                  ("state_theta", "f8"), ("state_weight", "f8"), ("state_id", "i4"),
                  ("pre_theta", "f8"), ("pre_weight", "f8"), ("pre_id", "i4")]
@@ -128,7 +129,7 @@ class Model:
 class Config:
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None,
-                 base_snapshot=0, n_threads=1, seed=0):
+                 base_snapshot=0, n_threads=1, seed=0, resample=False):
         self.lo, self.hi = _f8(lo), _f8(hi)
         assert self.lo.shape == (d,) and self.hi.shape == (d,)
         self.blocks = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, d)
@@ -137,7 +138,8 @@ class Config:
             alpha = 0.0  # structs.jl:102-105
         self.c = _Config(n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa, theta_snooker,
                          PROPOSALS[proposal], nb, _ptr(self.blocks, _bp), _ptr(self.lo, _dp), _ptr(self.hi, _dp),
-                         int(base_snapshot), int(n_threads), int(seed))
+                         int(base_snapshot), int(n_threads), int(seed), int(bool(resample)), 0)
+        self.resample = bool(resample)
         self.n_groups, self.Np, self.d, self.n_initial = n_groups, Np, d, n_initial
         self.B = max(1, nb)
         self.P = n_groups * Np
@@ -148,7 +150,7 @@ def tape_shapes(cfg: Config, n_iter: int):
     return {"mig_u": (n_iter,), "mig_n": (n_iter,), "mig_groups": (n_iter, G), "mig_pick_u": (n_iter, G),
             "mig_slots": (n_iter, G), "mut_u": (S, G), "kind": (S, P), "idx": (S, P, 3), "u_snk": (S, P),
             "u_base": (S, P), "gamma1": (S, P), "gamma2": (S, P), "u_acc": (S, P), "noise": (S, P, d),
-            "keep": (S, P, d)}
+            "keep": (S, P, d), "idx_row": (S, P, 3)}
 
 
 def trace_shapes(cfg: Config, n_iter: int):
@@ -172,7 +174,7 @@ def _pack(struct_cls, fields, arrays):
     return s
 
 
-def run(cfg: Config, model: Model, theta0, n_iter, tape_in=None, record=True, trace=True, history=True):
+def run(cfg: Config, model: Model, theta0, n_iter, tape_in=None, record=True, trace=True, history=True, init_rows=None):
     """Run the oracle.  Returns a dict with samples/accept/lp (reference layout), final state,
     and optionally the recorded tape and the per-sweep trace."""
     L = lib()
@@ -183,6 +185,9 @@ def run(cfg: Config, model: Model, theta0, n_iter, tape_in=None, record=True, tr
     if history:
         # Julia Array{T,3}(n_rows, d, P): row fastest => numpy shape (P, d, n_rows) C-order
         out["samples"] = np.zeros((P, d, n_rows))
+        if cfg.n_initial > 0:
+            # initialize_samples (utilities.jl:29-41): init_rows[i][id][k] are the caller's prior draws
+            out["samples"][:, :, :cfg.n_initial] = _f8(init_rows).reshape(cfg.n_initial, P, d).transpose(1, 2, 0)
         out["accept"] = np.zeros((P, n_rows), dtype=np.uint8)
         out["lp"] = np.zeros((P, n_rows))
     out["final_id"] = np.zeros(P, dtype=np.int32)
@@ -191,6 +196,8 @@ def run(cfg: Config, model: Model, theta0, n_iter, tape_in=None, record=True, tr
     tape_out = _alloc(_TAPE_FIELDS, tape_shapes(cfg, n_iter)) if record else None
     if tape_out is not None and cfg.c.kappa == 1.0:
         tape_out["keep"] = None
+    if tape_out is not None and not cfg.resample:
+        tape_out["idx_row"] = None
     tr = _alloc(_TRACE_FIELDS, trace_shapes(cfg, n_iter)) if trace else None
     tin = _pack(_Tape, _TAPE_FIELDS, tape_in) if tape_in is not None else None
     tout = _pack(_Tape, _TAPE_FIELDS, tape_out) if record else None

@@ -140,11 +140,18 @@ def compare_run(case, G, Np, n_iter, mode, seed=5, rng_seed=0, rtol=1e-12, **kw)
     rng = np.random.default_rng(rng_seed)
     theta0 = case.theta0(rng, G * Np)
     okw = dict(kw)
+    n0 = kw.get("n_initial", 0)
+    # initialize_samples (utilities.jl:35-39): n_initial prior draws per particle id; the chain starts from row 1
+    init_rows = np.stack([case.theta0(rng, G * Np) for _ in range(n0)]) if n0 else None
     cfg = case.oracle_config(G, Np, seed=seed, base_snapshot=1 if mode == "native" else 0, **okw)
-    r = O.run(cfg, case.oracle_model(), theta0, n_iter)
+    r = O.run(cfg, case.oracle_model(), theta0, n_iter, init_rows=init_rows)
     h = case.handle(G, Np, seed=seed, trace=True, **kw)
     try:
-        h.set_state(theta0)
+        if n0:
+            h.set_history(init_rows)
+            h.set_state(None)
+        else:
+            h.set_state(theta0)
         if mode == "native":
             h.run(n_iter)
         else:
@@ -164,13 +171,18 @@ def forced_run(case, G, Np, n_iter, mode, seed=5, rng_seed=0, **kw):
     positive Lyapunov exponent).  Returns the same structure as compare_run."""
     rng = np.random.default_rng(rng_seed)
     theta0 = case.theta0(rng, G * Np)
+    n0 = kw.get("n_initial", 0)
+    init_rows = np.stack([case.theta0(rng, G * Np) for _ in range(n0)]) if n0 else None
     cfg = case.oracle_config(G, Np, seed=seed, base_snapshot=1 if mode == "native" else 0, **kw)
-    r = O.run(cfg, case.oracle_model(), theta0, n_iter)
+    r = O.run(cfg, case.oracle_model(), theta0, n_iter, init_rows=init_rows)
     h = case.handle(G, Np, seed=seed, trace=True, **kw)
     traces, migs = [], []
     try:
         for it in range(n_iter):
-            if it == 0:
+            if it == 0 and n0:
+                h.set_history(init_rows)
+                h.set_state(None)
+            elif it == 0:
                 h.set_state(theta0)
             else:
                 h.set_state(r["trace"]["state_theta"][it - 1], r["trace"]["state_id"][it - 1])
@@ -203,3 +215,22 @@ def rel_err(a, b):
     if not fin.any():
         return 0.0
     return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(1.0, np.abs(b[fin]))))
+
+
+def mvn_resample_check(n_iter, burnin, sd_atol, seed=505514):
+    """The assertions of test/multivariate_normal_tests.jl:62-69 on the bound library."""
+    rng = np.random.default_rng(seed)
+    n_mu, n_d = 30, 100
+    data = rng.normal(0.0, 1.0, size=(n_d, n_mu))
+    model = D.DEModel(sample_prior=lambda: [rng.normal(0, 1, n_mu), abs(rng.standard_cauchy())],
+                      prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                      loglike=D.GPULoglike("mvnormal", data), names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), sample=D.resample, burnin=burnin,
+              n_initial=(n_mu + 1) * 4, Np=3, n_groups=1, θsnooker=0.1, seed=7)
+    chains = D.sample(model, de, D.MCMCThreads(), n_iter)
+    assert len(chains) == n_iter - burnin
+    means, sds = chains.mean()[:n_mu], chains.std()[:n_mu]
+    assert np.all(np.abs(sds - 0.1) < sd_atol), sds
+    assert np.all(np.abs(means) < 0.3)
+    assert abs(means.std(ddof=1) - 0.1) < 0.02
+    assert np.corrcoef(data.mean(axis=0), means)[0, 1] > 0.98

@@ -277,7 +277,7 @@ int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *pic
     return 0;
 }
 
-int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta, double *w, int32_t *id, uint8_t *acc)
+int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos)
 {
     ++g_launches;
     for (int i = 0; i < a.n; ++i) {
@@ -287,6 +287,7 @@ int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *pi
         const double *row = stage + (size_t)((i + a.n - 1) % a.n) * (cfg.d + 3);
         memcpy(theta + p * cfg.d, row, sizeof(double) * cfg.d);
         w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2];
+        if (pos) pos[id[p] - cfg.group_begin * cfg.Np] = (int32_t)p;
     }
     return 0;
 }

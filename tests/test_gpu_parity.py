@@ -294,3 +294,24 @@ def test_device_bundle_matches_bundle_samples():
     ref = bundle_samples(model, de, h.samples(), h.accept(), h.lp(), ids, [(d - 1,), ()], 30)
     assert np.array_equal(h.chains(10, 20).transpose(2, 1, 0), ref.value)
     h.close()
+
+
+# ---- de.sample = resample (DE-MCz, crossover.jl:113-124) and n_initial ---------------------------
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model", ["gaussian", "mvnormal", "lba"])
+def test_resample_from_history(mode, model):
+    case = make_case(model, np.random.default_rng(31))
+    r, out = forced_run(case, 3, 6, 12, mode, burnin=6, n_initial=5, resample=True, theta_snooker=0.3, alpha=0.4)
+    check(r, out, rtol_w=RTOL_W.get(model))
+    assert np.array_equal(out["samples"][:, :, :5], r["samples"][:, :, :5])
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_resample_blocking_hierarchical(mode):      # Examples/Hierarchical_Example.jl: blocks + resample + n_initial
+    case = make_case("hier_normal", np.random.default_rng(32))
+    r, out = forced_run(case, 2, 8, 10, mode, burnin=5, n_initial=4, resample=True, blocks=hier_blocks(9), alpha=0.3)
+    check(r, out)
+
+
+def test_sample_api_mvn_resample():                 # test/multivariate_normal_tests.jl at its own size
+    common.mvn_resample_check(n_iter=50_000, burnin=5000, sd_atol=0.01)

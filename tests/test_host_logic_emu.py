@@ -112,8 +112,18 @@ def test_abi_error_paths():
     case = make_case("gaussian", np.random.default_rng(17))
     with pytest.raises(D._ffi.DemcmcError, match="Np must be >= 3"):
         D.Handle(2, 2, 2, case.lo, case.hi)
-    with pytest.raises(D._ffi.DemcmcError, match="resample"):
-        D.Handle(2, 4, 2, case.lo, case.hi, n_initial=12)
+    with pytest.raises(D._ffi.DemcmcError, match="resample needs n_initial"):
+        D.Handle(2, 4, 2, case.lo, case.hi, resample=True)
+    with pytest.raises(D._ffi.DemcmcError, match="not sharded"):
+        D.Handle(2, 4, 2, case.lo, case.hi, resample=True, n_initial=3, group_begin=0, group_count=1)
+    h = D.Handle(2, 4, 2, case.lo, case.hi, n_initial=2)
+    h.set_model("gaussian", case.prior, x=case.data["x"])
+    with pytest.raises(D._ffi.DemcmcError, match="null theta"):
+        h.set_state(None)
+    h.set_state(np.ones((8, 2)))
+    with pytest.raises(D._ffi.DemcmcError, match="set_history"):
+        h.run(1)
+    h.close()
     h = D.Handle(2, 4, 2, case.lo, case.hi)
     with pytest.raises(D._ffi.DemcmcError, match="set_model"):
         h.set_state(np.zeros((8, 2)))
@@ -181,8 +191,10 @@ def test_closure_raises_instead_of_cpu_fallback():
                        loglike=D.GPULoglike("gaussian", np.zeros(3)), names=("μ", "σ"))
     with pytest.raises(TypeError, match="GPUPrior"):
         D.sample(model2, de, 10)
-    with pytest.raises(NotImplementedError):
-        D.DE(sample_prior=model.sample_prior, bounds=((-1, 1),), Np=4, sample="resample")
+    with pytest.raises(TypeError, match="custom host function"):
+        D.DE(sample_prior=model.sample_prior, bounds=((-1, 1),), Np=4, sample=lambda *a: None)
+    with pytest.raises(ValueError, match="n_initial"):
+        D.DE(sample_prior=model.sample_prior, bounds=((-1, 1),), Np=4, sample=D.resample)
 
 
 def test_names_blocks_and_bounds_flattening():
@@ -238,3 +250,40 @@ def test_device_bundle_matches_bundle_samples():
     with pytest.raises(D._ffi.DemcmcError):
         h.chains(25, 10)
     h.close()
+
+
+# ---- de.sample = resample (DE-MCz donors from the history, crossover.jl:113-124) and n_initial ----
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("kw", [dict(theta_snooker=0.3), dict(proposal="fixed_gamma", kappa=0.7, theta_snooker=0.1),
+                                dict(alpha=0.6, theta_snooker=0.2)])
+def test_resample_from_history(mode, kw):
+    case = make_case("gaussian", np.random.default_rng(31))
+    r, out = compare_run(case, 3, 6, 40, mode, burnin=15, n_initial=5, resample=True, **kw)
+    check(r, out)
+    # the first n_initial rows of de.samples are the prior rows, and the chain started from row 1
+    assert np.array_equal(out["samples"][:, :, :5], r["samples"][:, :, :5])
+    assert (r["tape"]["idx_row"][r["tape"]["kind"] == O.KIND_SNOOKER] >= 0).all()
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_resample_blocking_hierarchical(mode):
+    """Examples/Hierarchical_Example.jl: blocks + sample = resample + n_initial."""
+    case = make_case("hier_normal", np.random.default_rng(32))
+    r, out = compare_run(case, 2, 8, 30, mode, burnin=10, n_initial=4, resample=True, blocks=hier_blocks(9), alpha=0.3)
+    check(r, out)
+
+
+def test_n_initial_without_resample():
+    """n_initial > 0 with the default donors: prior rows are stored, bundle_samples' window is not
+    shifted by n_initial (main.jl:226-234)."""
+    case = make_case("gaussian", np.random.default_rng(33))
+    r, out = compare_run(case, 2, 5, 25, "native", burnin=5, n_initial=3)
+    check(r, out)
+    assert out["samples"].shape[2] == 28
+
+
+def test_sample_api_mvn_resample():
+    """test/multivariate_normal_tests.jl restated at its own size: MvNormal(mu, sigma^2 I), 30 means, 100
+    observations, DE(sample = resample, n_initial = 124, Np = 3, n_groups = 1, theta_snooker = 0.1),
+    50 000 iterations, and the reference's own assertions (:62-69)."""
+    common.mvn_resample_check(n_iter=50_000, burnin=5000, sd_atol=0.01)
