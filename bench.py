@@ -159,6 +159,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; libdemcmc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")         # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D._ffi.use_library(D._ffi.DEFAULT_LIB)
     assert D._ffi.lib().demcmc_backend_name() == b"cuda-sm100a"
@@ -299,7 +300,7 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])",
                            "groups_total": G, "particles_total": G * NP, "parallelism": f"groups sharded over {world} GPU(s); NCCL send/recv migration",
-                           "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten before every chunk of overlapped steps (a chunk ends at each migration, at most 16 steps; steps inside a chunk share launches so there is no per-step boundary), per-chunk CUDA events, flush excluded",
+                           "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten before every segment = a migration (with its NCCL exchange) plus the chunk of overlapped steps that follows it (a chunk ends at the next migration, at most 16 steps; steps inside a chunk share launches so there is no per-step boundary); per-segment CUDA events, flush excluded",
                            "timing": "CUDA events on the library's launching stream (demcmc_counters.device_ms), max over ranks"},
                 "value_steady_no_flush": updates / (ms_steady * 1e-3) if world == 1 else None,
                 "gpu_launches": int(launches), "clocks": ck, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,

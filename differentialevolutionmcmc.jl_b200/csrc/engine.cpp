@@ -499,7 +499,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     int64_t n_levels = 0;
     // timing events: one pair per chunk when the L2 flush is on; the likelihood launches get their
     // own pairs after those
-    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter * B : 0), tev_ll0 = tev_need, tev_ll = 0, tev_chunks = 0;
+    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter : 0), tev_ll0 = tev_need, tev_ll = 0, tev_chunks = 0;
     if (h->time_loglik) tev_need += 2 * (size_t)S * 64;
     while (h->tev.size() < tev_need) { void *e = be::tevent_create(); if (!e) { cleanup(); return fail(DEMCMC_ECUDA, "event pool: %s", be::last_error()); } h->tev.push_back(e); }
     BE(be::timer_start());
@@ -526,10 +526,6 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
         if (u.armed) BE(be::event_wait(u.copied));             // the pinned slot is free once its copies ran
         h->ring_use++;
-        if (h->flush_bytes) {                                   // evict L2 before the timed chunk
-            BE(be::dfill(h->flush_buf, (int)(tev_chunks & 1), (size_t)h->flush_bytes));
-            BE(be::event_record(h->tev[2 * tev_chunks]));
-        }
         bool basedep[MAX_CHUNK];
         Row cur = cur_row(h);
         for (int s = 0; s < n_sw; ++s) {
@@ -604,11 +600,25 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             BE(be::launch_accept(h->dcfg, h->dmodel, lv));
             ++n_levels;
         }
-        if (h->flush_bytes) { BE(be::event_record(h->tev[2 * tev_chunks + 1])); ++tev_chunks; }
+        return 0;
+    };
+    // measurement mode: one timed segment = the migration (with its NCCL exchange) plus the chunk(s)
+    // that follow it; the L2 flush in front of the segment is outside the bracket
+    auto seg_begin = [&]() -> int {
+        if (!h->flush_bytes) return 0;
+        BE(be::dfill(h->flush_buf, (int)(tev_chunks & 1), (size_t)h->flush_bytes));
+        BE(be::event_record(h->tev[2 * tev_chunks]));
+        return 0;
+    };
+    auto seg_end = [&]() -> int {
+        if (!h->flush_bytes) return 0;
+        BE(be::event_record(h->tev[2 * tev_chunks + 1]));
+        ++tev_chunks;
         return 0;
     };
 
     for (int64_t it = 0; it < n_iter;) {
+        if (int rc = seg_begin()) { cleanup(); return rc; }
         // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
         get_mig(it, ms);
         if (ms.migrate) {
@@ -647,6 +657,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // ---- update! (main.jl:161-167) -------------------------------------------------------------
         if (B > 1) {                                  // blocking: every block is one sweep, one chunk each
             for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1)) { cleanup(); return rc; }
+            if (int rc = seg_end()) { cleanup(); return rc; }
             ++it;
             continue;
         }
@@ -662,12 +673,13 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             }
         }
         if (int rc = run_chunk(it, 0, n)) { cleanup(); return rc; }
+        if (int rc = seg_end()) { cleanup(); return rc; }
         it += n;
     }
     double ms_dev = 0.0;
     BE(be::timer_stop(&ms_dev));
     BE(be::sync());
-    if (h->flush_bytes) {                                   // sum of the per-chunk times, flushes excluded
+    if (h->flush_bytes) {                                   // sum of the per-segment times (migration + chunk), flushes excluded
         ms_dev = 0.0;
         for (size_t c = 0; c < tev_chunks; ++c) { double t = 0.0; BE(be::tevent_elapsed(h->tev[2 * c], h->tev[2 * c + 1], &t)); ms_dev += t; }
     }

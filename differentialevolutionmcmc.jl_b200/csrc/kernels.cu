@@ -1225,19 +1225,44 @@ int comm_unique_id(uint8_t id[128])
     memcpy(id, u.internal, 128);
     return 0;
 }
+// One communicator per (device, rank, n_ranks) is kept for the life of the process: every handle
+// of a job that is sharded the same way reuses it (creating one costs about a second), and the
+// unique id of later calls is ignored -- all ranks take the same branch, so this stays collective.
+struct CommSlot { int rank = -1, n = 0; nccl_comm c = nullptr; };
+static CommSlot g_comm[64];
+
 int comm_init(const uint8_t id[128], int rank, int n_ranks, void **comm)
 {
     if (nccl_load()) return -1;
+    CommSlot &slot = g_comm[g_dev];
+    if (slot.c && slot.rank == rank && slot.n == n_ranks) { *comm = slot.c; return 0; }
     nccl_uid u;
     memcpy(u.internal, id, 128);
     nccl_comm c = nullptr;
     NC(g_nccl.CommInitRank(&c, n_ranks, u, rank));
     *comm = c;
+    // NCCL opens point-to-point connections lazily: exchange one row with every peer now, so the
+    // first migration that crosses ranks does not pay for the connection setup
+    if (n_ranks > 1) {
+        double *buf = (double *)dmalloc(sizeof(double) * 2 * n_ranks);
+        if (!buf) return -1;
+        NC(g_nccl.GroupStart());
+        for (int r = 0; r < n_ranks; ++r) {
+            if (r == rank) continue;
+            NC(g_nccl.Send(buf + r, 1, 8 /* ncclFloat64 */, r, c, stream()));
+            NC(g_nccl.Recv(buf + n_ranks + r, 1, 8, r, c, stream()));
+        }
+        NC(g_nccl.GroupEnd());
+        CU(cudaStreamSynchronize(stream()));
+        dfree(buf);
+    }
+    if (slot.c && g_nccl.lib) g_nccl.CommDestroy(slot.c);
+    slot.rank = rank; slot.n = n_ranks; slot.c = c;
     return 0;
 }
 int comm_destroy(void *comm)
 {
-    if (comm && g_nccl.lib) g_nccl.CommDestroy((nccl_comm)comm);
+    (void)comm;                                              // owned by the per-device slot above
     return 0;
 }
 int comm_exchange(void *comm, int rank, int n, const int *src_rank, const int *dst_rank, double *stage_send,
