@@ -113,7 +113,7 @@ struct CConfig
     device::Int32
     group_begin::Int32
     group_count::Int32
-    reserved0::Int32
+    donors::Int32          # 0 = sample (current group), 1 = resample (history, DE-MCz)
     trace::Int32
     store_every::Int32
 end
@@ -183,8 +183,9 @@ function _sample_gpu(model, de, n_iter; device, seed)
     model.prior_loglike isa GPUPrior || throw(ArgumentError("prior_loglike must be a GPUPrior: a Julia closure would need a host round trip per particle"))
     de.update_particle! === mh_update! && de.evaluate_fitness! === compute_posterior! ||
         throw(ArgumentError("only mh_update! / compute_posterior! are built on the B200 path"))
-    de.sample === sample || throw(ArgumentError("sample = resample (DE-MCz) is not built on the B200 path yet"))
-    de.n_initial == 0 || throw(ArgumentError("n_initial > 0 belongs to resample, which is not built yet"))
+    de.sample === sample || de.sample === resample ||
+        throw(ArgumentError("de.sample must be `sample` or `resample`: a custom donor function cannot run on the device"))
+    donors = de.sample === resample ? Int32(1) : Int32(0)
     ll = model.loglike
     # sample_init (src/main.jl:263-271) unchanged: initial Θ and ids are the reference's own
     groups = sample_init(model, de, n_iter)
@@ -212,25 +213,35 @@ function _sample_gpu(model, de, n_iter; device, seed)
         n_obs = 1
     end
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    samples = zeros(Float64, n_iter, d, P)          # Julia order == the library's output order
-    accept = zeros(UInt8, n_iter, P)
-    lp = zeros(Float64, n_iter, P)
+    n_rows = n_iter + de.n_initial
+    samples = zeros(Float64, n_rows, d, P)          # Julia order == the library's output order
+    accept = zeros(UInt8, n_rows, P)
+    lp = zeros(Float64, n_rows, P)
     final_ids = zeros(Int32, P)
+    # initialize_samples (src/utilities.jl:29-41) already filled rows 1:n_initial of de.samples with
+    # prior draws; the library wants them as [n_initial][P][d]
+    init_rows = de.n_initial > 0 ?
+        Float64[flatten_theta(de.samples[i, :, p])[k] for k = 1:d, p = 1:P, i = 1:(de.n_initial)] : Float64[]
     sig = ll.sigma === nothing ? Float64[] : ll.sigma
-    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids begin
+    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids init_rows begin
         cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, de.n_initial, de.α, de.β, de.ϵ, de.σ, de.κ,
             de.θsnooker, proposal_id(de), n_blocks, isempty(blocks) ? C_NULL : pointer(blocks), pointer(lo), pointer(hi),
-            seed, device, 0, 0, 0, 0, 1)
+            seed, device, 0, 0, donors, 0, 1)
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
                 isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0)
             demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
+            if de.n_initial > 0
+                demcmc_check(ccall((:demcmc_set_history, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], init_rows))
+            end
+            # init_particle (src/utilities.jl:13-22) already started every particle from samples[1, :, id]
+            # when n_initial > 0, so theta0 is right in both cases
             demcmc_check(ccall((:demcmc_set_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), h[], theta0, C_NULL))
             demcmc_check(ccall((:demcmc_run, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64), h[], n_iter))
-            demcmc_check(ccall((:demcmc_get_samples, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], samples, n_iter))
-            demcmc_check(ccall((:demcmc_get_accept, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], accept, n_iter))
-            demcmc_check(ccall((:demcmc_get_lp, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], lp, n_iter))
+            demcmc_check(ccall((:demcmc_get_samples, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], samples, n_rows))
+            demcmc_check(ccall((:demcmc_get_accept, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], accept, n_rows))
+            demcmc_check(ccall((:demcmc_get_lp, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], lp, n_rows))
             demcmc_check(ccall((:demcmc_get_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), h[], C_NULL, C_NULL, final_ids))
         finally
             ccall((:demcmc_destroy, LIBDEMCMC), Cint, (Ptr{Cvoid},), h[])
@@ -238,7 +249,7 @@ function _sample_gpu(model, de, n_iter; device, seed)
     end
     # rebuild what bundle_samples reads: de.samples (nested per named parameter) and, at final
     # position c, the accept/lp history of the particle that ended there (src/main.jl:232-241)
-    de.iter = n_iter
+    de.iter = n_iter + de.n_initial
     de.samples = nest_samples(samples, Θ1)
     for (c, p) in enumerate(particles)
         id = final_ids[c] + 1
@@ -247,6 +258,17 @@ function _sample_gpu(model, de, n_iter; device, seed)
     end
     groups = [particles[((g - 1) * de.Np + 1):(g * de.Np)] for g = 1:(de.n_groups)]
     return bundle_samples(model, de, groups, n_iter)
+end
+
+# Faster exit when only the Chains are wanted: bundle_samples (src/main.jl:222-250) runs on the device
+# and one download returns its Array{Float64,3}(Ns, d + 2, P) in Julia order, ready for
+# `Chains(v, all_names, (parameters = [model.names...], internals = ["acceptance", "lp"]))`.
+function device_bundle(h, de, n_iter, d, P)
+    Ns = de.discard_burnin ? n_iter - de.burnin : n_iter
+    offset = de.discard_burnin ? de.burnin : 0
+    v = zeros(Float64, Ns, d + 2, P)
+    GC.@preserve v demcmc_check(ccall((:demcmc_get_chains, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), h, offset, Ns, v))
+    return v
 end
 
 # [n_iter, d, P] flat -> the reference's Array{T,3}(n_iter, n_named, P) whose elements may be arrays
