@@ -25,6 +25,14 @@ int d2d(void *dst, const void *src, size_t bytes);
 int dzero(void *dst, size_t bytes);
 int sync();
 
+// lanes: independent kernel chains on separate streams (lane 0 = the engine stream).  set_lane
+// selects where the launchers below enqueue; lane_fork makes lanes 1..n-1 wait for everything
+// enqueued on lane 0 so far, lane_join makes lane 0 wait for the other lanes.
+constexpr int MAX_LANES = 2;
+void set_lane(int lane);
+int lane_fork(int n_lanes);
+int lane_join(int n_lanes);
+
 void *event_create();
 void event_destroy(void *ev);
 int event_record(void *ev);               // on the engine stream

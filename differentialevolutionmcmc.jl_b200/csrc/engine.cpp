@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -76,6 +77,7 @@ struct demcmc_handle {
     // schedule ring
     static constexpr int RING = 4;
     int max_chunk = MAX_CHUNK;                          // sweeps overlapped on the device (1 = a barrier per sweep)
+    int n_lanes = 2;                                    // concurrent kernel chains over independent sets of groups
     Upload ring[RING];
     int64_t ring_use = 0;
     // migration
@@ -189,6 +191,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->cfg = *cfg;
     h->d = cfg->d;
     h->n0 = cfg->n_initial;
+    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), be::MAX_LANES));   // A/B measurements
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
     h->P = h->G_local * cfg->Np;
@@ -503,7 +506,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     if (h->time_loglik) tev_need += 2 * (size_t)S * 64;
     while (h->tev.size() < tev_need) { void *e = be::tevent_create(); if (!e) { cleanup(); return fail(DEMCMC_ECUDA, "event pool: %s", be::last_error()); } h->tev.push_back(e); }
     BE(be::timer_start());
-    ChunkPlan plan;
+    ChunkPlan plans[be::MAX_LANES];
     MigSchedule ms;
 
     auto get_mig = [&](int64_t it, MigSchedule &out) {
@@ -565,16 +568,29 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
-        PlanInput pin;
-        pin.seed = cfg.seed; pin.Np = Np; pin.G_local = G; pin.group_begin = cfg.group_begin; pin.G_total = Gt;
-        pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
-        const int64_t s_first = it0 * B + b;
-        pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
-        pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
-        plan_chunk(pin, (uint32_t)(itg0 * B + b), n_sw, basedep, plan);
-
-        memcpy(u.h_order, plan.order.data(), sizeof(int32_t) * (size_t)n_sw * P);
-        memcpy(u.h_mut, plan.mutate.data(), (size_t)n_sw * G);
+        // Lanes: the groups split into independent sets (groups never read each other between
+        // migrations), each planned on its own and launched as its own kernel chain on its own
+        // stream, so one lane's likelihood kernel runs while the other lane proposes / accepts.
+        const int n_lanes = (h->n_lanes > 1 && G >= 2 && !h->time_loglik) ? 2 : 1;
+        int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
+        std::vector<uint8_t> mut((size_t)n_sw * G, 0);
+        for (int ln = 0; ln < n_lanes; ++ln) {
+            const int g0 = ln == 0 ? 0 : (G + 1) / 2, g1 = (n_lanes == 1 || ln == 1) ? G : (G + 1) / 2;
+            PlanInput pin;
+            pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
+            pin.pos_offset = g0 * Np; pin.P_stride = P;
+            pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
+            const int64_t s_first = it0 * B + b;
+            pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
+            pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
+            plan_chunk(pin, (uint32_t)(itg0 * B + b), n_sw, basedep, plans[ln]);
+            const ChunkPlan &pl = plans[ln];
+            memcpy(u.h_order + lane_off[ln], pl.order.data(), sizeof(int32_t) * pl.order.size());
+            lane_off[ln + 1] = lane_off[ln] + (int32_t)pl.order.size();
+            for (int s2 = 0; s2 < n_sw; ++s2)
+                for (int g = g0; g < g1; ++g) mut[(size_t)s2 * G + g] = pl.mutate[(size_t)s2 * (g1 - g0) + (g - g0)];
+        }
+        memcpy(u.h_mut, mut.data(), mut.size());
         BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * (size_t)n_sw * P));
         BE(be::h2d(u.d_mut, u.h_mut, (size_t)n_sw * G));
         BE(be::h2d(u.d_ctx, u.h_ctx, sizeof(SweepCtx) * (size_t)n_sw));
@@ -583,23 +599,35 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 
         if (needs_snapshot(it0)) {                               // n_sw == 1 here
             bool any_cross = false;
-            for (int g = 0; g < G; ++g) any_cross |= plan.mutate[g] == 0;
+            for (int g = 0; g < G; ++g) any_cross |= mut[g] == 0;
             if (any_cross) BE(be::launch_base_prep(h->dcfg, u.h_ctx[0].cur_w, h->base_th, h->base_cw, h->base_tot));
         }
-        for (int l = 0; l < plan.n_levels; ++l) {
-            Level lv;
-            lv.order = u.d_order + plan.level_off[l];
-            lv.n = plan.level_off[l + 1] - plan.level_off[l];
-            lv.ctxs = u.d_ctx;
-            if (lv.n == 0) continue;
-            BE(be::launch_propose(h->dcfg, h->dmodel, lv));
-            const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
-            if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
-            BE(be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc));
-            if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
-            BE(be::launch_accept(h->dcfg, h->dmodel, lv));
-            ++n_levels;
-        }
+        BE(be::lane_fork(n_lanes));
+        int max_levels = 0;
+        for (int ln = 0; ln < n_lanes; ++ln) max_levels = std::max(max_levels, plans[ln].n_levels);
+        int rc_launch = 0;
+        for (int l = 0; l < max_levels && !rc_launch; ++l)
+            for (int ln = 0; ln < n_lanes && !rc_launch; ++ln) {
+                const ChunkPlan &pl = plans[ln];
+                if (l >= pl.n_levels) continue;
+                Level lv;
+                lv.order = u.d_order + lane_off[ln] + pl.level_off[l];
+                lv.n = pl.level_off[l + 1] - pl.level_off[l];
+                lv.ctxs = u.d_ctx;
+                if (lv.n == 0) continue;
+                be::set_lane(ln);
+                const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+                if (be::launch_propose(h->dcfg, h->dmodel, lv) ||
+                    (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll])) ||
+                    be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc) ||
+                    (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])) ||
+                    be::launch_accept(h->dcfg, h->dmodel, lv)) rc_launch = 1;
+                if (tl) ++tev_ll;
+                ++n_levels;
+            }
+        be::set_lane(0);
+        if (rc_launch) return fail(DEMCMC_ECUDA, "level launch: %s", be::last_error());
+        BE(be::lane_join(n_lanes));
         return 0;
     };
     // measurement mode: one timed segment = the migration (with its NCCL exchange) plus the chunk(s)
@@ -826,6 +854,13 @@ int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps)
 {
     if (!h || n_sweeps < 1) return fail(DEMCMC_EINVAL, "bad argument");
     h->max_chunk = std::min<int32_t>(n_sweeps, MAX_CHUNK);
+    return 0;
+}
+
+int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
+{
+    if (!h || n_lanes < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    h->n_lanes = std::min<int32_t>(n_lanes, be::MAX_LANES);
     return 0;
 }
 

@@ -29,7 +29,12 @@ namespace be {
 static thread_local std::string g_be_err;
 static int64_t g_launches = 0;
 static int g_dev = 0;
-static cudaStream_t g_stream[64] = { nullptr };
+// Lanes: independent sets of groups run as concurrent kernel chains, one stream per lane, so the
+// likelihood kernel of one lane covers the propose / accept latency of the other (engine.cpp).
+// Lane 0 is the engine stream; every copy, event and one-off kernel runs there.
+static int g_lane = 0;
+static cudaStream_t g_stream[64][MAX_LANES] = { { nullptr } };
+static cudaEvent_t g_lane_ev[64][MAX_LANES] = { { nullptr } };
 static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 
 static int cu_fail(cudaError_t e, const char *what)
@@ -42,8 +47,8 @@ static int cu_fail(cudaError_t e, const char *what)
 
 static cudaStream_t stream()
 {
-    if (!g_stream[g_dev]) cudaStreamCreateWithFlags(&g_stream[g_dev], cudaStreamNonBlocking);
-    return g_stream[g_dev];
+    if (!g_stream[g_dev][g_lane]) cudaStreamCreateWithFlags(&g_stream[g_dev][g_lane], cudaStreamNonBlocking);
+    return g_stream[g_dev][g_lane];
 }
 
 // Kernels of one level are chained with programmatic dependent launch: the next kernel's CTAs may
@@ -66,6 +71,38 @@ static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+void set_lane(int lane) { g_lane = (lane >= 0 && lane < MAX_LANES) ? lane : 0; }
+static cudaEvent_t lane_event(int lane)
+{
+    if (!g_lane_ev[g_dev][lane]) cudaEventCreateWithFlags(&g_lane_ev[g_dev][lane], cudaEventDisableTiming);
+    return g_lane_ev[g_dev][lane];
+}
+int lane_fork(int n_lanes)
+{
+    if (n_lanes < 2) return 0;
+    const int keep = g_lane;
+    g_lane = 0;
+    cudaStream_t s0 = stream();
+    CU(cudaEventRecord(lane_event(0), s0));
+    for (int l = 1; l < n_lanes && l < MAX_LANES; ++l) { g_lane = l; CU(cudaStreamWaitEvent(stream(), lane_event(0), 0)); }
+    g_lane = keep;
+    return 0;
+}
+int lane_join(int n_lanes)
+{
+    if (n_lanes < 2) return 0;
+    const int keep = g_lane;
+    g_lane = 0;
+    cudaStream_t s0 = stream();
+    for (int l = 1; l < n_lanes && l < MAX_LANES; ++l) {
+        g_lane = l;
+        CU(cudaEventRecord(lane_event(l), stream()));
+        CU(cudaStreamWaitEvent(s0, lane_event(l), 0));
+    }
+    g_lane = keep;
+    return 0;
 }
 
 const char *name() { return "cuda-sm100a"; }
@@ -221,7 +258,7 @@ constexpr int PA_THREADS = 128;
 // bfrag[octet of the level][dimension split][k-step j][lane], and the fixed-point magic constant of
 // every particle of the level, magic[level order]
 struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; };
-static XdStage g_xs[64];
+static XdStage g_xs[64][MAX_LANES];
 static XdStage *xd_stage(const ModelDev &m, int n);
 
 // leaves one parameter vector's centred means where k_xdot wants them, together with the particle's
@@ -464,7 +501,7 @@ static size_t xdot_smem_bytes(int nj)
 static size_t xd_bfrag_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_OCT - 1) / SSD_OCT) * m.n_ksplit * m.ssd_nj * 32; }
 static XdStage *xd_stage(const ModelDev &m, int n)
 {
-    XdStage &x = g_xs[g_dev];
+    XdStage &x = g_xs[g_dev][g_lane];
     const size_t need = xd_bfrag_doubles(m, n) + (size_t)((n + SSD_OCT - 1) / SSD_OCT) * SSD_OCT;
     if (need > x.cap) {
         cudaStreamSynchronize(stream());
@@ -676,7 +713,7 @@ int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, 
     if (lv.n <= 0 || m.kind == M_BINOMIAL) return 0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
         // the proposal kernel of this level has staged the centred means and cleared the accumulators
-        const XdStage &xs = g_xs[g_dev];
+        const XdStage &xs = g_xs[g_dev][g_lane];
         if (!xs.bfrag || !xs.magic) { g_be_err = "mean staging buffer missing"; return -1; }
         return launch_xdot(m, xs, lv, ll_acc);
     }

@@ -8,6 +8,7 @@ namespace de {
 void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bool *base_dependency, ChunkPlan &out)
 {
     const int Np = in.Np, G = in.G_local, P = Np * G;
+    const int stride = in.P_stride > 0 ? in.P_stride : P;
     out.n_sweeps = n_sweeps;
     out.mutate.assign((size_t)n_sweeps * G, 0);
     out.order.resize((size_t)n_sweeps * P);
@@ -15,8 +16,8 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
     int max_level = 0;
     for (int s = 0; s < n_sweeps; ++s) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
-        const uint8_t *tk = in.t_kind ? in.t_kind + (size_t)s * P : nullptr;
-        const int32_t *ti = in.t_idx ? in.t_idx + (size_t)s * P * 3 : nullptr;
+        const uint8_t *tk = in.t_kind ? in.t_kind + (size_t)s * stride + in.pos_offset : nullptr;
+        const int32_t *ti = in.t_idx ? in.t_idx + ((size_t)s * stride + in.pos_offset) * 3 : nullptr;
         for (int g = 0; g < G; ++g) {
             const int gg = in.group_begin + g;
             bool mutate;
@@ -62,7 +63,7 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
     std::vector<int32_t> cursor(out.level_off.begin(), out.level_off.end() - 1);
     for (int s = 0; s < n_sweeps; ++s)
         for (int p = 0; p < P; ++p)
-            out.order[cursor[level[(size_t)s * P + p]]++] = (int32_t)(((uint32_t)s << ENTRY_SLOT_SHIFT) | (uint32_t)p);
+            out.order[cursor[level[(size_t)s * P + p]]++] = (int32_t)(((uint32_t)s << ENTRY_SLOT_SHIFT) | (uint32_t)(in.pos_offset + p));
 }
 
 void plan_migration(uint64_t seed, uint32_t iter0, int32_t G, double alpha, MigSchedule &out)

@@ -26,7 +26,9 @@ constexpr int MAX_CHUNK = 16;                        // sweeps planned and launc
 
 struct PlanInput {
     uint64_t seed;
-    int32_t Np, G_local, group_begin, G_total;
+    int32_t Np, G_local, group_begin, G_total;   // the groups this plan covers: G_local of them from global group group_begin
+    int32_t pos_offset = 0;    // local position of the first particle covered (entries and tape slices are offset by it)
+    int32_t P_stride = 0;      // particles per sweep in the tape slices (0: Np * G_local)
     int32_t proposal;          // 0 random_gamma
     double beta, theta_snooker;
     bool resample;             // donors come from stored rows (crossover.jl:113-124): no donor dependencies inside a sweep

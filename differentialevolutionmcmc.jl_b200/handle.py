@@ -206,6 +206,9 @@ class Handle:
     def set_max_chunk(self, n_sweeps):
         check(_ffi.lib().demcmc_set_max_chunk(self._h, int(n_sweeps)))
 
+    def set_lanes(self, n_lanes):
+        check(_ffi.lib().demcmc_set_lanes(self._h, int(n_lanes)))
+
     def eval(self, theta):
         th = f8(theta).reshape(-1, self.d)
         n = th.shape[0]

@@ -39,6 +39,9 @@ int d2h(void *d, const void *s, size_t b) { if (b) memcpy(d, s, b); return 0; }
 int d2d(void *d, const void *s, size_t b) { if (b) memmove(d, s, b); return 0; }
 int dzero(void *d, size_t b) { if (b) memset(d, 0, b); return 0; }
 int sync() { return 0; }
+void set_lane(int) {}
+int lane_fork(int) { return 0; }
+int lane_join(int) { return 0; }
 void *event_create() { return malloc(8); }
 void event_destroy(void *e) { free(e); }
 int event_record(void *) { return 0; }

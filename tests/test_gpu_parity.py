@@ -315,3 +315,22 @@ def test_resample_blocking_hierarchical(mode):      # Examples/Hierarchical_Exam
 
 def test_sample_api_mvn_resample():                 # test/multivariate_normal_tests.jl at its own size
     common.mvn_resample_check(n_iter=50_000, burnin=5000, sd_atol=0.01)
+
+
+def test_lanes_and_chunks_do_not_change_the_result():
+    """Concurrent kernel chains over independent sets of groups (demcmc_set_lanes), programmatic
+    dependent launch and overlapped chunks are execution schedules only: bit-identical chains."""
+    case = make_case("mvnormal", np.random.default_rng(41), n_obs=3000)
+    G, Np = 4, 48
+    theta0 = case.theta0(np.random.default_rng(6), G * Np)
+    outs = []
+    for lanes, chunk in ((1, 1), (1, 16), (2, 16), (2, 3)):
+        h = case.handle(G, Np, seed=8, burnin=6, theta_snooker=0.2, alpha=0.3)
+        h.set_lanes(lanes)
+        h.set_max_chunk(chunk)
+        h.set_state(theta0)
+        h.run(30)
+        outs.append((h.samples(), h.accept(), h.lp(), h.get_state()[2]))
+        h.close()
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))

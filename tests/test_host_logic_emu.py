@@ -214,6 +214,7 @@ def test_overlapped_chunks_do_not_change_the_result():
     for chunk in (1, 3, 16):
         h = case.handle(2, 48, seed=21, burnin=5, theta_snooker=0.2, alpha=0.05)
         h.set_max_chunk(chunk)
+        h.set_lanes(1)
         h.set_state(theta0)
         h.run(40)
         outs.append((h.samples(), h.accept(), h.lp(), h.counters()["levels"]))
@@ -287,3 +288,19 @@ def test_sample_api_mvn_resample():
     observations, DE(sample = resample, n_initial = 124, Np = 3, n_groups = 1, theta_snooker = 0.1),
     50 000 iterations, and the reference's own assertions (:62-69)."""
     common.mvn_resample_check(n_iter=50_000, burnin=5000, sd_atol=0.01)
+
+
+def test_lanes_do_not_change_the_result():
+    """Independent sets of groups run as concurrent kernel chains (demcmc_set_lanes); the chain must
+    not depend on how many there are, with or without a tape, blocking, migrations."""
+    case = make_case("hier_normal", np.random.default_rng(41))
+    theta0 = case.theta0(np.random.default_rng(6), 3 * 10)
+    outs = []
+    for lanes in (1, 2):
+        h = case.handle(3, 10, seed=8, burnin=6, theta_snooker=0.2, alpha=0.4, blocks=hier_blocks(9))
+        h.set_lanes(lanes)
+        h.set_state(theta0)
+        h.run(25)
+        outs.append((h.samples(), h.accept(), h.lp(), h.get_state()[2]))
+        h.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
