@@ -93,6 +93,7 @@ int fp64_peak(double *tflops);                             // the larger of the 
 int fp64_peaks(double *dfma_tflops, double *dmma_tflops);   // DFMA loop, DMMA m8n8k4 loop
 int copy_peak(double *gbs);
 
+void timeline_dump();                     // debug: writes the %globaltimer stamps of the levels launched so far (DEMCMC_TIMELINE)
 int64_t launch_count();                   // kernels launched so far (for demcmc_counters)
 
 // ---- cross-rank migration (NCCL over NVLink) ---------------------------------------------------

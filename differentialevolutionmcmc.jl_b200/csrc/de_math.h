@@ -311,31 +311,44 @@ DE_HD double normlogccdf(double z)
 #endif
 }
 
-struct Prior { int32_t kind; int32_t ref; double a, b; };
+// c0, c1: the parameter-only terms of the log density, computed once on the host (prior_constants)
+// so the per-proposal evaluation carries at most one transcendental per element
+struct Prior { int32_t kind; int32_t ref; double a, b, c0, c1; };
 enum { PRIOR_FLAT = 0, PRIOR_NORMAL = 1, PRIOR_HALFCAUCHY = 2, PRIOR_UNIFORM = 3, PRIOR_BETA = 4, PRIOR_NORMAL_REF = 5 };
+
+inline void prior_constants(Prior &p)
+{
+    p.c0 = 0.0; p.c1 = 0.0;
+    switch (p.kind) {
+    case PRIOR_NORMAL: p.c0 = log(p.b); break;
+    case PRIOR_HALFCAUCHY: p.c0 = log(p.b); p.c1 = log(1.0 - (atan((0.0 - p.a) / p.b) / DE_PI + 0.5)); break;
+    case PRIOR_UNIFORM: p.c0 = log(p.b - p.a); break;
+    case PRIOR_BETA: p.c0 = lgamma(p.a) + lgamma(p.b) - lgamma(p.a + p.b); break;
+    default: break;
+    }
+}
 
 // one term of prior_loglike; sd_ref = theta[p.ref] for NORMAL_REF
 DE_HD double prior_elem(const Prior &p, double x, double sd_ref)
 {
     switch (p.kind) {
     case PRIOR_FLAT: return 0.0;
-    case PRIOR_NORMAL: return normlogpdf(p.a, p.b, x);
+    case PRIOR_NORMAL: { const double z = (x - p.a) / p.b; return -(z * z + DE_LOG2PI) / 2.0 - p.c0; }
     case PRIOR_NORMAL_REF: return normlogpdf(p.a, sd_ref, x);
     case PRIOR_HALFCAUCHY: {
         if (!(x >= 0.0)) return x != x ? qnan() : -inf();
         const double z = (x - p.a) / p.b;
-        const double lcdf = atan((0.0 - p.a) / p.b) / DE_PI + 0.5;
-        return -(log1p(z * z) + DE_LOGPI + log(p.b)) - log(1.0 - lcdf);
+        return -(log1p(z * z) + DE_LOGPI + p.c0) - p.c1;
     }
     case PRIOR_UNIFORM:
         if (x != x) return qnan();
-        return (x >= p.a && x <= p.b) ? -log(p.b - p.a) : -inf();
+        return (x >= p.a && x <= p.b) ? -p.c0 : -inf();
     case PRIOR_BETA: {
         if (x != x) return qnan();
         if (!(x >= 0.0 && x <= 1.0)) return -inf();
         const double t1 = (p.a == 1.0) ? 0.0 : (p.a - 1.0) * log(x);
         const double t2 = (p.b == 1.0) ? 0.0 : (p.b - 1.0) * log1p(-x);
-        return t1 + t2 - (lgamma(p.a) + lgamma(p.b) - lgamma(p.a + p.b));
+        return t1 + t2 - p.c0;
     }
     }
     return qnan();

@@ -23,6 +23,14 @@ struct SerialLanes {
     DE_HD void dependency_wait() const {}
 };
 
+// What a backend wants to do with every element of a proposal while it is still in a register
+// (kernels.cu stages the likelihood kernel's operands there); the host test double does nothing.
+struct NullSink {
+    DE_HD void prefetch(int, int) {}
+    DE_HD void elem(int, int, double) {}
+};
+constexpr int PROP_PRE = 2;   // elements per lane whose state-independent inputs are fetched before the dependency wait
+
 // mean of dimension k of the MVN / hierarchical likelihood, relative to the data centre
 DE_HD double centred_mean(const ModelDev &m, const double *theta, int k)
 {
@@ -81,8 +89,8 @@ DE_HD void bounds_and_prior(const C &co, const ConfigDev &cfg, const ModelDev &m
 
 // crossover!(model,de,group,pt[,block]) / mutation! up to evaluate_fitness!: writes the proposal,
 // its prior, bounds flag and snooker adjustment (crossover.jl:30-99,154-273,301-352; mutation.jl:13-25)
-template <class C>
-DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, int p)
+template <class C, class S>
+DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, int p, S &sink)
 {
     const int Np = cfg.Np, d = cfg.d;
     const int g = p / Np, j = p - g * Np;
@@ -108,16 +116,26 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
         }
         if (kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, kind, cfg.proposal, ctx.in_burnin != 0, d); g1 = gg.a; g2 = gg.b; }
     }
+    // everything an element needs that does not depend on the state -- its noise draw, bounds, prior
+    // spec -- is fetched for the first PROP_PRE elements of the lane before the dependency wait
+    const bool is_mut = kind == KIND_MUTATION;
+    auto noise_at = [&](int k) { return ctx.replay ? ctx.t_noise[(size_t)p * d + k] : noise_elem(cfg.seed, ctx.sweep, unit, k, is_mut, cfg.eps, cfg.sigma); };
+    double pre_nz[PROP_PRE], pre_lo[PROP_PRE], pre_hi[PROP_PRE];
+    Prior pre_pr[PROP_PRE];
+DE_PRAGMA_UNROLL
+    for (int q = 0; q < PROP_PRE; ++q) {
+        const int k = co.lane() + q * co.width();
+        pre_nz[q] = 0.0; pre_lo[q] = 0.0; pre_hi[q] = 0.0; pre_pr[q].kind = PRIOR_FLAT;
+        if (k < d) { pre_nz[q] = noise_at(k); pre_lo[q] = cfg.lo[k]; pre_hi[q] = cfg.hi[k]; pre_pr[q] = m.prior[k]; sink.prefetch(q, k); }
+    }
     co.dependency_wait();
     // a donor that sits before the target in the sweep already holds this sweep's value; with
-    // de.sample = resample the donors are stored rows instead: samples[row, :, id] (crossover.jl:120)
     const size_t gbase = (size_t)g * Np;
     const size_t P_all = (size_t)cfg.G_local * Np;
 #define DE_SLOT(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
 #define DE_HIST(r, id) (ctx.hist_theta + ((size_t)(r) * P_all + (size_t)ctx.hist_pos[(size_t)(r) * P_all + (size_t)(id)]) * d)
 #define DE_DONOR(k, r) (cfg.resample ? DE_HIST(r, k) : DE_SLOT(k))
 
-    const bool is_mut = kind == KIND_MUTATION;
     double r1 = 0.0, r2 = 0.0;
     const double *pm = nullptr, *pn = nullptr, *pb = nullptr, *pz = nullptr;
     bool has_base = false;
@@ -161,10 +179,10 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
 
     const uint8_t *mask = (ctx.block >= 0 && !is_mut) ? cfg.blocks + (size_t)ctx.block * d : nullptr;
     bool ok = true;
-    double sq1 = 0.0, sq2 = 0.0;
-    for (int k = co.lane(); k < d; k += co.width()) {
+    double sq1 = 0.0, sq2 = 0.0, ps = 0.0;
+    const bool one_pass = m.prior_has_ref == 0;                            // no prior reads another parameter
+    auto body = [&](int q, int k, double nz, double lo, double hi, const Prior &pr) {
         const double t = tcur[k];
-        const double nz = ctx.replay ? ctx.t_noise[(size_t)p * d + k] : noise_elem(cfg.seed, ctx.sweep, unit, k, is_mut, cfg.eps, cfg.sigma);
         double v;
         if (is_mut) v = add(t, nz);                                            // utilities.jl:291-298
         else if (kind == KIND_DE) v = de_elem(t, pm[k], pn[k], has_base ? pb[k] : t, g1, g2, has_base, nz);
@@ -180,15 +198,24 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
             const double a = sub(v, pz[k]), b = sub(t, pz[k]);
             sq1 = add(sq1, mul(a, a)); sq2 = add(sq2, mul(b, b));
         }
-        ok = ok && (v >= cfg.lo[k] && v <= cfg.hi[k]);
+        ok = ok && (v >= lo && v <= hi);
         prop[k] = v;
         if (ctx.tr_theta) ctx.tr_theta[(size_t)p * d + k] = v;
+        if (one_pass) ps += prior_elem(pr, v, 0.0);
+        sink.elem(q, k, v);
+    };
+DE_PRAGMA_UNROLL
+    for (int q = 0; q < PROP_PRE; ++q) {
+        const int k = co.lane() + q * co.width();
+        if (k < d) body(q, k, pre_nz[q], pre_lo[q], pre_hi[q], pre_pr[q]);
     }
-    co.sync();
-    double ps = 0.0;
-    for (int k = co.lane(); k < d; k += co.width()) {
-        const Prior pr = m.prior[k];
-        ps += prior_elem(pr, prop[k], pr.kind == PRIOR_NORMAL_REF ? prop[pr.ref] : 0.0);
+    for (int k = co.lane() + PROP_PRE * co.width(); k < d; k += co.width()) body(PROP_PRE, k, noise_at(k), cfg.lo[k], cfg.hi[k], m.prior[k]);
+    if (!one_pass) {
+        co.sync();
+        for (int k = co.lane(); k < d; k += co.width()) {
+            const Prior pr = m.prior[k];
+            ps += prior_elem(pr, prop[k], pr.kind == PRIOR_NORMAL_REF ? prop[pr.ref] : 0.0);
+        }
     }
     const bool inb = co.all(ok);
     ps = co.sum(ps);
@@ -222,7 +249,8 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
             for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
         total = co.sum(part);
     }
-    const double ll = finalize_ll(m, prop, total, mean_sq(co, m, prop));
+    const double msq = (m.kind == M_MVNORMAL || m.kind == M_HIER) ? ctx.prop_msq[p] : 0.0;
+    const double ll = finalize_ll(m, prop, total, msq);
     const bool inb = ctx.prop_inb[p] != 0;
     const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();
     const double adj = ctx.prop_adj[p];

@@ -37,6 +37,7 @@ struct ModelDev {
     double lba_floor;
     double binom_N, binom_k;
     const Prior *prior;       // [d]
+    int32_t prior_has_ref;    // some prior reads another parameter (NORMAL_REF): priors need the whole proposal
     // partition of the likelihood sum: slice s covers observations [s*split_len, ...) x dimension
     // split; fixed by the model alone so the summation order never depends on the GPU count or on
     // how many slices one CTA happens to process
@@ -93,6 +94,7 @@ struct SweepCtx {
     double *prop_theta;       // [P_local][d]
     double *prop_prior;       // [P_local]
     double *prop_adj;         // [P_local]
+    double *prop_msq;         // [P_local] sum_k m'_k^2 of the proposal (MVN / hierarchical), written with the proposal
     uint8_t *prop_inb;        // [P_local]
     double *ll_part;          // [P_local][n_split] partial sums of the pointwise kernels
     // MVN / hierarchical: the cross term arrives as an order-independent fixed-point sum,

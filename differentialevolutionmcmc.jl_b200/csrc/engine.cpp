@@ -68,7 +68,7 @@ struct demcmc_handle {
     int cur_scratch = 0;                                // current state lives in scratch row k, or
     int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
     // proposal scratch
-    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *ll_part = nullptr, *ll_q = nullptr;
+    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *prop_msq = nullptr, *ll_part = nullptr, *ll_q = nullptr;
     long long *ll_acc = nullptr;
     uint8_t *prop_inb = nullptr;
     double *base_th = nullptr, *base_cw = nullptr, *base_tot = nullptr;
@@ -215,6 +215,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->prop_theta = (double *)be::dmalloc(sizeof(double) * P * d);
     h->prop_prior = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_msq = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_inb = (uint8_t *)be::dmalloc(P);
     h->ll_acc = (long long *)be::dmalloc(sizeof(long long) * P);
     h->ll_q = (double *)be::dmalloc(sizeof(double) * P);
@@ -225,7 +226,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->d_stage = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
     h->d_stage_recv = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
     bool ok = h->d_lo && h->d_hi && h->d_blocks && h->scr_theta && h->scr_w && h->scr_id && h->scr_acc && h->prop_theta &&
-              h->prop_prior && h->prop_adj && h->prop_inb && h->ll_acc && h->ll_q && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
+              h->prop_prior && h->prop_adj && h->prop_msq && h->prop_inb && h->ll_acc && h->ll_q && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
     for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
         Upload &u = h->ring[i];
         u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P * MAX_CHUNK);
@@ -256,10 +257,11 @@ int demcmc_destroy(demcmc_handle *h)
     if (!h) return 0;
     be::set_device(h->cfg.device);
     be::sync();
+    be::timeline_dump();
     if (h->comm) be::comm_destroy(h->comm);
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
-                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
+                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_msq, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
                      h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
@@ -308,6 +310,8 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         pr[k].kind = m->prior[k].kind; pr[k].ref = m->prior[k].ref; pr[k].a = m->prior[k].a; pr[k].b = m->prior[k].b;
         if (pr[k].kind < 0 || pr[k].kind > PRIOR_NORMAL_REF) return fail(DEMCMC_EUNSUPPORTED, "prior kind %d of parameter %d is not registered", pr[k].kind, k);
         if (pr[k].kind == PRIOR_NORMAL_REF && (pr[k].ref < 0 || pr[k].ref >= m->d)) return fail(DEMCMC_EINVAL, "prior ref out of range");
+        if (pr[k].kind == PRIOR_NORMAL_REF) D.prior_has_ref = 1;
+        prior_constants(pr[k]);
     }
     D.prior = (const Prior *)upload(pr.data(), sizeof(Prior) * pr.size(), false);
     if (!D.prior) return fail(DEMCMC_ENOMEM, "prior upload failed");
@@ -554,7 +558,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 ctx.t_noise = t_noise + (size_t)s_local * P * d; ctx.t_keep = t_keep ? t_keep + (size_t)s_local * P * d : nullptr;
                 ctx.t_idx_row = t_idx_row ? t_idx_row + (size_t)s_local * P * 3 : nullptr;
             }
-            ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb;
+            ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb; ctx.prop_msq = h->prop_msq;
             ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
             // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)

@@ -73,6 +73,52 @@ static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---- debug timeline (DEMCMC_TIMELINE=<levels> DEMCMC_TIMELINE_FILE=<csv>): every kernel of a level
+// stamps %globaltimer into one 16-word slot, so the gaps between the kernels of a PDL chain can be
+// read without events (which would break the chain) and without a profiler (which serialises it)
+enum { TL_P0 = 0, TL_P1, TL_X0, TL_X0MAX, TL_XWAIT, TL_XFIRST, TL_XLOOP0, TL_XLOOP1, TL_X1, TL_A0, TL_A1, TL_N, TL_WORDS = 16 };
+static unsigned long long *g_tl = nullptr;
+static int g_tl_cap = -1, g_tl_level = 0;
+static unsigned long long *tl_slot()
+{
+    if (g_tl_cap < 0) {
+        const char *e = getenv("DEMCMC_TIMELINE");
+        g_tl_cap = e ? atoi(e) : 0;
+        if (g_tl_cap > 0 && (cudaMalloc(&g_tl, sizeof(unsigned long long) * TL_WORDS * g_tl_cap) != cudaSuccess ||
+                             cudaMemset(g_tl, 0, sizeof(unsigned long long) * TL_WORDS * g_tl_cap) != cudaSuccess)) g_tl_cap = 0;
+    }
+    return (g_tl_cap > 0 && g_tl_level < g_tl_cap) ? g_tl + (size_t)TL_WORDS * g_tl_level : nullptr;
+}
+void timeline_dump()
+{
+    if (g_tl_cap <= 0 || !g_tl) return;
+    const char *path = getenv("DEMCMC_TIMELINE_FILE");
+    if (!path) return;
+    cudaDeviceSynchronize();
+    const int n = g_tl_level < g_tl_cap ? g_tl_level : g_tl_cap;
+    std::vector<unsigned long long> h((size_t)TL_WORDS * (n > 0 ? n : 1));
+    if (n <= 0 || cudaMemcpy(h.data(), g_tl, sizeof(unsigned long long) * TL_WORDS * n, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    FILE *f = fopen(path, "w");
+    if (!f) return;
+    fprintf(f, "level,n,propose_start,propose_end,xdot_start,xdot_last_start,xdot_wait_done,xdot_first_data,xdot_loop_end_min,xdot_loop_end_max,xdot_end,accept_start,accept_end\n");
+    const unsigned long long t0 = ~h[TL_P0];
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long *w = h.data() + (size_t)TL_WORDS * i;
+        auto rel = [&](unsigned long long v) { return (double)((long long)(v - t0)) * 1e-3; };
+        fprintf(f, "%d,%llu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, w[TL_N], rel(~w[TL_P0]), rel(w[TL_P1]), rel(~w[TL_X0]), rel(w[TL_X0MAX]),
+                rel(w[TL_XWAIT]), rel(w[TL_XFIRST]), rel(~w[TL_XLOOP0]), rel(w[TL_XLOOP1]), rel(w[TL_X1]), rel(~w[TL_A0]), rel(w[TL_A1]));
+    }
+    fclose(f);
+}
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_min(unsigned long long *tl, int w) { if (tl) atomicMax(tl + w, ~gtime()); }
+__device__ __forceinline__ void tl_max(unsigned long long *tl, int w) { if (tl) atomicMax(tl + w, gtime()); }
+
 void set_lane(int lane) { g_lane = (lane >= 0 && lane < MAX_LANES) ? lane : 0; }
 static cudaEvent_t lane_event(int lane)
 {
@@ -263,51 +309,86 @@ static XdStage *xd_stage(const ModelDev &m, int n);
 
 // leaves one parameter vector's centred means where k_xdot wants them, together with the particle's
 // fixed-point scale (de_math.h: xd_scale); wi = rank of the particle in the launch
-__device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
-                                            long long *acc, double *q)
+__device__ __forceinline__ void stage_scale(const ModelDev &m, double msq, int64_t wi, double *magic, long long *acc, double *q, double *msq_out)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t oct = wi / SSD_OCT;
-    const int n = (int)(wi % SSD_OCT);
-    double msq = 0.0;
-    for (int k = lane; k < m.ssd_k; k += 32) {
-        const double v = centred_mean(m, theta, k);
-        msq += v * v;
-        const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
-        bfrag[(((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32 + n * 4 + (kl & 3)] = v;
-    }
-    msq = warp_sum(msq);
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
         const XdScale sc = xd_scale(msq, m.ssd_rowmax, m.ssd_qbits);
         magic[wi] = sc.magic;
         *q = sc.q;
         *acc = 0;
+        if (msq_out) *msq_out = msq;
     }
 }
+__device__ __forceinline__ size_t bfrag_index(const ModelDev &m, int64_t wi, int k)
+{
+    const int64_t oct = wi / SSD_OCT;
+    const int n = (int)(wi % SSD_OCT);
+    const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
+    return (((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32 + n * 4 + (kl & 3);
+}
+__device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
+                                            long long *acc, double *q, double *msq_out)
+{
+    const int lane = threadIdx.x & 31;
+    double msq = 0.0;
+    for (int k = lane; k < m.ssd_k; k += 32) {
+        const double v = centred_mean(m, theta, k);
+        msq += v * v;
+        bfrag[bfrag_index(m, wi, k)] = v;
+    }
+    stage_scale(m, warp_sum(msq), wi, magic, acc, q, msq_out);
+}
 
-__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
+// the MVN model's means ARE proposal elements: stage them while they are still in registers
+// (the data centre of the lane's first elements is fetched before the dependency wait)
+struct StageSink {
+    const ModelDev &m;
+    double *bfrag;
+    int64_t wi;
+    bool on;
+    double cen[PROP_PRE];
+    double msq;
+    __device__ __forceinline__ void prefetch(int q, int k) { if (on && k < m.ssd_k) cen[q] = m.center[k]; }
+    __device__ __forceinline__ void elem(int q, int k, double v)
+    {
+        if (!on || k >= m.ssd_k) return;
+        const double c = v - (q < PROP_PRE ? cen[q] : m.center[k]);
+        msq += c * c;
+        bfrag[bfrag_index(m, wi, k)] = c;
+    }
+};
+
+__global__ void __launch_bounds__(PA_THREADS) k_propose(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic, unsigned long long *tl)
 {
     pdl_launch_dependents();
+    if ((threadIdx.x & 31) == 0) tl_min(tl, TL_P0);
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) { pdl_wait(); return; }
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     const int p = (int)(e & LV_POS_MASK);
-    propose_particle(WarpLanes(), cfg, m, ctx, p);
+    StageSink sink = { m, bfrag, wi, bfrag != nullptr && m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
+    propose_particle(WarpLanes(), cfg, m, ctx, p, sink);
     if (bfrag) {
-        __syncwarp();
-        stage_bfrag(m, ctx.prop_theta + (size_t)p * cfg.d, wi, bfrag, magic, ctx.ll_acc + p, ctx.ll_q + p);
+        if (sink.on) stage_scale(m, warp_sum(sink.msq), wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
+        else {
+            __syncwarp();
+            stage_bfrag(m, ctx.prop_theta + (size_t)p * cfg.d, wi, bfrag, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
+        }
     }
+    if ((threadIdx.x & 31) == 0) { tl_max(tl, TL_P1); if (tl && wi == 0) tl[TL_N] = (unsigned long long)lv.n; }
 }
 
-__global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, Level lv)
+__global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m, Level lv, unsigned long long *tl)
 {
     pdl_launch_dependents();
+    if ((threadIdx.x & 31) == 0) tl_min(tl, TL_A0);
     const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= lv.n) { pdl_wait(); return; }
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     accept_particle(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
+    if ((threadIdx.x & 31) == 0) tl_max(tl, TL_A1);
 }
 
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
@@ -319,7 +400,7 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
         xs = xd_stage(m, std::max(lv.n, cfg.G_local * cfg.Np));
         if (!xs) return -1;
     }
-    CU(launch_chained(k_propose, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
+    CU(launch_chained(k_propose, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr, tl_slot()));
     LAUNCHED("k_propose");
     return 0;
 }
@@ -327,8 +408,9 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
-    CU(launch_chained(k_accept, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv));
+    CU(launch_chained(k_accept, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, tl_slot()));
     LAUNCHED("k_accept");
+    if (g_tl_cap > 0) ++g_tl_level;
     return 0;
 }
 
@@ -526,7 +608,7 @@ struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 
 template <int NOCT>
 __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
-                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw)
+                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw, unsigned long long *tl)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ks = blockIdx.y;
     const int nj = m.ssd_nj;
@@ -549,6 +631,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     }
     __syncwarp();
     pdl_wait();                                              // the packed data are constant; the means are not
+    if (tid == 0) tl_max(tl, TL_XWAIT);
 
     // this tile's centred means as B fragments, and the particles' fixed-point constants
     double b[SSD_NJ][NOCT];
@@ -575,6 +658,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     for (int t = T0; t < T1; ++t) {
         const int it = t - T0, st = it & (XD_STAGES - 1);
         mbar_wait(&full[st], (uint32_t)(it / XD_STAGES) & 1u);
+        if (tl && tid == 0 && t == T0) tl_max(tl, TL_XFIRST);
         const double2 *xa = reinterpret_cast<const double2 *>(ring + (size_t)st * stage_doubles) + lane;
         double2 a = xa[0];
 #pragma unroll
@@ -605,6 +689,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             }
     }
 
+    if (tid == 0) { tl_min(tl, TL_XLOOP0); tl_max(tl, TL_XLOOP1); }
     // remove the magic offsets (two conversions per observation tile), sum the 8 rows held by the
     // lanes of each column group, and add the CTA's share to the particles' accumulators
     const unsigned long long n_conv = 2ull * (unsigned long long)(T1 - T0);
@@ -621,13 +706,15 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
                 atomicAdd(reinterpret_cast<unsigned long long *>(ll_acc) + p, v);
             }
         }
+    if (tid == 0) tl_max(tl, TL_X1);
 }
 
 __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
-                                                                     long long *ll_acc, XdGrid g)
+                                                                     long long *ll_acc, XdGrid g, unsigned long long *tl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_launch_dependents();
+    if (threadIdx.x == 0) { tl_min(tl, TL_X0); tl_max(tl, TL_X0MAX); }
     int oct0, c_in, C, noct;
     const int n_in_hi = g.n_hi * g.c_hi;
     if ((int)blockIdx.x < n_in_hi) { const int t = blockIdx.x / g.c_hi; c_in = blockIdx.x - t * g.c_hi; C = g.c_hi; noct = g.oct_hi; oct0 = t * g.oct_hi; }
@@ -636,10 +723,10 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
     if (T1 <= T0) { pdl_wait(); return; }
     switch (noct) {
-    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
-    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
-    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
-    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw); break;
+    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
+    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
+    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
+    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
     }
 }
 
@@ -649,7 +736,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_stage_means(ModelDev m, const do
 {
     const int64_t wi = ((int64_t)blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= n) return;
-    stage_bfrag(m, theta + (size_t)wi * m.d, wi, bfrag, magic, acc + wi, q + wi);
+    stage_bfrag(m, theta + (size_t)wi * m.d, wi, bfrag, magic, acc + wi, q + wi, nullptr);
 }
 
 static int n_sms()
@@ -702,7 +789,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
     }
     const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
     dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)m.n_ksplit);
-    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g));
+    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, lv.ctxs ? tl_slot() : (unsigned long long *)nullptr));
     LAUNCHED("k_xdot");
     return 0;
 }

@@ -1,0 +1,39 @@
+"""Kernel timeline of the level chain from %globaltimer stamps (no events, no profiler).
+Usage on the GPU box:  DEMCMC_LANES=1 python scripts/timeline.py [out.csv]   -> prints per-level gaps"""
+import os, sys, csv
+out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.csv"
+os.environ["DEMCMC_TIMELINE"] = "4000"
+os.environ["DEMCMC_TIMELINE_FILE"] = out
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+import demcmc_b200 as D
+D._ffi.use_library(D._ffi.DEFAULT_LIB)
+x, prior, lo, hi, theta0 = bench.workload(4)
+h = D.Handle(4, 256, 51, lo, hi, burnin=0, theta_snooker=0.1, seed=20261017)
+h.set_model("mvnormal", prior, x=x)
+h.set_state(theta0)
+h.run(60)
+h.close()
+rows = list(csv.DictReader(open(out)))
+R = [{k: float(v) for k, v in r.items()} for r in rows]
+R = [r for r in R if r["n"] > 0][40:]                      # skip the warm-up levels
+def mean(f): return float(np.mean([f(r) for r in R]))
+print("levels", len(R), "mean n", mean(lambda r: r["n"]))
+print("propose            %.2f us" % mean(lambda r: r["propose_end"] - r["propose_start"]))
+print("propose -> xdot    %.2f us (first xdot CTA start after propose end)" % mean(lambda r: r["xdot_start"] - r["propose_end"]))
+print("xdot CTA start spread %.2f us" % mean(lambda r: r["xdot_last_start"] - r["xdot_start"]))
+print("xdot start -> wait done %.2f us" % mean(lambda r: r["xdot_wait_done"] - r["xdot_start"]))
+print("propose end -> xdot wait done %.2f us" % mean(lambda r: r["xdot_wait_done"] - r["propose_end"]))
+print("wait done -> first data %.2f us" % mean(lambda r: r["xdot_first_data"] - r["xdot_wait_done"]))
+print("xdot main loop (wait done -> last loop end) %.2f us" % mean(lambda r: r["xdot_loop_end_max"] - r["xdot_wait_done"]))
+print("loop end spread (max - min) %.2f us" % mean(lambda r: r["xdot_loop_end_max"] - r["xdot_loop_end_min"]))
+print("xdot tail (loop end -> end) %.2f us" % mean(lambda r: r["xdot_end"] - r["xdot_loop_end_max"]))
+print("xdot total %.2f us" % mean(lambda r: r["xdot_end"] - r["xdot_start"]))
+print("xdot end -> accept start %.2f us" % mean(lambda r: r["accept_start"] - r["xdot_end"]))
+print("accept             %.2f us" % mean(lambda r: r["accept_end"] - r["accept_start"]))
+nxt = [R[i + 1]["propose_start"] - R[i]["accept_end"] for i in range(len(R) - 1)]
+print("accept end -> next propose start %.2f us" % float(np.mean(nxt)))
+print("level period %.2f us" % float(np.mean([R[i + 1]["propose_start"] - R[i]["propose_start"] for i in range(len(R) - 1)])))
+ideal = mean(lambda r: np.ceil(r["n"] / 8) * 1563 * 8 * 13 * 16 / (148 * 4) / 1965.0)
+print("ideal DMMA time of the level %.2f us" % ideal)

@@ -53,6 +53,7 @@ int dfill(void *d, int v, size_t b) { if (b) memset(d, v, b); return 0; }
 int timer_start() { return 0; }
 int timer_stop(double *ms) { *ms = 0.0; return 0; }
 int64_t launch_count() { return g_launches; }
+void timeline_dump() {}
 
 struct ksum_t { double s, c; };
 static void kadd(ksum_t &k, double x)
@@ -205,7 +206,11 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
     ++g_launches;
     for (int q = 0; q < lv.n; ++q) {
         const uint32_t e = (uint32_t)lv.order[q];
-        propose_particle(SerialLanes(), cfg, m, lv.ctxs[e >> LV_SLOT_SHIFT], (int)(e & LV_POS_MASK));
+        const SweepCtx &ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+        const int p = (int)(e & LV_POS_MASK);
+        NullSink sink;
+        propose_particle(SerialLanes(), cfg, m, ctx, p, sink);
+        ctx.prop_msq[p] = mean_sq(SerialLanes(), m, ctx.prop_theta + (size_t)p * cfg.d);
     }
     return 0;
 }
