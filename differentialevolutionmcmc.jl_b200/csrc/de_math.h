@@ -258,8 +258,9 @@ DE_HD double adjust_loglike(double sq_prop_z, double sq_t_z, int d)
 // ---------------------------------------------------------------------------------------------
 // order-independent accumulation of the MVN / hierarchical cross term
 // ---------------------------------------------------------------------------------------------
-// Every per-row term v = sum_k x'_ik m'_k obeys |v| <= |x'_i| |m'| (Cauchy-Schwarz), so with a
-// per-particle power-of-two quantum q = 2^(e - qbits), 2^e > rowmax*|m'|, the value v rounded to a
+// Every per-row term v = sum_k x'_ik m'_k obeys |v| <= |x'_i| |m'| (Cauchy-Schwarz); a chain of the
+// kernel sums two rows, hence rowmax = 2 max_i |x'_i|.  With a per-particle power-of-two quantum
+// q = 2^(e - qbits), 2^e > rowmax*|m'|, the value v rounded to a
 // multiple of q is an integer below 2^qbits and integer addition is associative: the total does
 // not depend on how observations were split over CTAs (level size, GPU count).  The rounding uses
 // the classic magic-number add: bits(v + 1.5*2^52*q) - bits(1.5*2^52*q) = round(v/q).

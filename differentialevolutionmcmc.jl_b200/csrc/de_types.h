@@ -27,7 +27,7 @@ struct ModelDev {
                               // A fragments (ssd_pack_index below); the host test double keeps xT[ssd_k][ssd_ld]
     const double *center;     // [ssd_k] column means removed from the data
     double ssd_xx;            // sum of the squared centred data
-    double ssd_rowmax;        // max over observations of |x'_i| (bounds every per-row cross term)
+    double ssd_rowmax;        // 2 max_i |x'_i|: bounds every chain of k_xdot (the cross terms of two observation rows)
     int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension
     int32_t ssd_k;            // dimensions (MVN: n_dim; hierarchical: subjects)
     int32_t ssd_nj;           // DMMA k-steps per dimension split = ceil(ksplit_len / 4)

@@ -78,14 +78,21 @@ static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // read without events (which would break the chain) and without a profiler (which serialises it)
 enum { TL_P0 = 0, TL_P1, TL_X0, TL_X0MAX, TL_XWAIT, TL_XFIRST, TL_XLOOP0, TL_XLOOP1, TL_X1, TL_A0, TL_A1, TL_N, TL_WORDS = 16 };
 static unsigned long long *g_tl = nullptr;
-static int g_tl_cap = -1, g_tl_level = 0;
+static int g_tl_cap = -1, g_tl_level = 0, g_tl_cta_level = -1;
+constexpr int TL_CTA_WORDS = 4, TL_CTA_MAX = 4096;
+static unsigned long long *tl_cta()      // per-CTA stamps of the one level named by DEMCMC_TIMELINE_CTA
+{
+    return (g_tl_cap > 0 && g_tl && g_tl_level == g_tl_cta_level) ? g_tl + (size_t)TL_WORDS * g_tl_cap : nullptr;
+}
 static unsigned long long *tl_slot()
 {
     if (g_tl_cap < 0) {
         const char *e = getenv("DEMCMC_TIMELINE");
         g_tl_cap = e ? atoi(e) : 0;
-        if (g_tl_cap > 0 && (cudaMalloc(&g_tl, sizeof(unsigned long long) * TL_WORDS * g_tl_cap) != cudaSuccess ||
-                             cudaMemset(g_tl, 0, sizeof(unsigned long long) * TL_WORDS * g_tl_cap) != cudaSuccess)) g_tl_cap = 0;
+        const size_t words = (size_t)TL_WORDS * g_tl_cap + (size_t)TL_CTA_WORDS * TL_CTA_MAX;
+        if (g_tl_cap > 0 && (cudaMalloc(&g_tl, sizeof(unsigned long long) * words) != cudaSuccess ||
+                             cudaMemset(g_tl, 0, sizeof(unsigned long long) * words) != cudaSuccess)) g_tl_cap = 0;
+        if (const char *c = getenv("DEMCMC_TIMELINE_CTA")) g_tl_cta_level = atoi(c);
     }
     return (g_tl_cap > 0 && g_tl_level < g_tl_cap) ? g_tl + (size_t)TL_WORDS * g_tl_level : nullptr;
 }
@@ -109,6 +116,21 @@ void timeline_dump()
                 rel(w[TL_XWAIT]), rel(w[TL_XFIRST]), rel(~w[TL_XLOOP0]), rel(w[TL_XLOOP1]), rel(w[TL_X1]), rel(~w[TL_A0]), rel(w[TL_A1]));
     }
     fclose(f);
+    if (g_tl_cta_level >= 0) {
+        std::vector<unsigned long long> c((size_t)TL_CTA_WORDS * TL_CTA_MAX);
+        if (cudaMemcpy(c.data(), g_tl + (size_t)TL_WORDS * g_tl_cap, sizeof(unsigned long long) * c.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            std::string p2 = std::string(path) + ".cta";
+            FILE *g = fopen(p2.c_str(), "w");
+            if (g) {
+                fprintf(g, "cta,start,wait_done,loop_end,tiles\n");
+                unsigned long long c0 = ~0ull;
+                for (int i = 0; i < TL_CTA_MAX; ++i) if (c[(size_t)i * 4]) c0 = c[(size_t)i * 4] < c0 ? c[(size_t)i * 4] : c0;
+                for (int i = 0; i < TL_CTA_MAX; ++i) if (c[(size_t)i * 4])
+                    fprintf(g, "%d,%.3f,%.3f,%.3f,%llu\n", i, (double)(c[(size_t)i * 4] - c0) * 1e-3, (double)(c[(size_t)i * 4 + 1] - c0) * 1e-3, (double)(c[(size_t)i * 4 + 2] - c0) * 1e-3, c[(size_t)i * 4 + 3]);
+                fclose(g);
+            }
+        }
+    }
 }
 __device__ __forceinline__ unsigned long long gtime()
 {
@@ -520,7 +542,7 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 //   A (8 observations x 4 dimensions)  = packed centred data, streamed
 //   B (4 dimensions x 8 particles)     = centred means of one particle octet, held in REGISTERS for
 //                                        the whole kernel (<= 13 k-steps x 4 octets per thread)
-//   C (8 observations x 8 particles)   = per-row cross terms; a row's chain runs over the k-steps
+//   C (8 observations x 8 particles)   = per-row-pair cross terms; a chain runs over the k-steps
 //                                        of ONE observation tile, then is rounded to the
 //                                        particle's fixed-point grid (de_math.h: xd_scale) and added
 //                                        as an integer, which makes the total independent of how
@@ -530,7 +552,8 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 // the packed layout, so each warp runs a PRIVATE 4-stage ring of TMA bulk copies (cp.async.bulk,
 // one copy per stage, completing on the warp's own mbarriers) and the kernel has no CTA-wide
 // barrier and no cross-warp wait at all.  Inner step: one LDS.128 (A fragments of two row tiles)
-// feeds 8 DMMAs (2 row tiles x 4 octets), 8 independent accumulator chains per warp.
+// feeds 8 DMMAs (2 row tiles x 4 octets) on 4 accumulator chains per warp (one per octet; the two
+// row tiles of the pair add into the same chain, 4 DMMAs apart, so a tile ends with 8 conversions).
 // The launch is one wave: CTAs are dealt to particle tiles in proportion to their octets (the last
 // tile of a level may hold 1..4), each taking a balanced contiguous range of observation tiles;
 // padding costs at most 7 particles per level.
@@ -606,12 +629,12 @@ static XdStage *xd_stage(const ModelDev &m, int n)
 // n_hi tiles of oct_hi octets with c_hi CTAs each, then n_lo tiles of oct_lo octets with c_lo CTAs each
 struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 
-template <int NOCT>
+template <int NOCT, int NJC>            // NJC: the model's k-steps when known at compile time (13), else 0
 __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
-                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw, unsigned long long *tl)
+                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw, unsigned long long *tl, unsigned long long *tlc)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ks = blockIdx.y;
-    const int nj = m.ssd_nj;
+    const int nj = NJC ? NJC : m.ssd_nj;
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const uint32_t stage_doubles = (uint32_t)nj * 64, stage_bytes = stage_doubles * (uint32_t)sizeof(double);
     double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
@@ -632,6 +655,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     __syncwarp();
     pdl_wait();                                              // the packed data are constant; the means are not
     if (tid == 0) tl_max(tl, TL_XWAIT);
+    if (tlc && tid == 0 && blockIdx.x < TL_CTA_MAX) { tlc[blockIdx.x * 4 + 1] = gtime(); tlc[blockIdx.x * 4 + 3] = (unsigned long long)(T1 - T0) * 10 + NOCT; }
 
     // this tile's centred means as B fragments, and the particles' fixed-point constants
     double b[SSD_NJ][NOCT];
@@ -645,14 +669,14 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     }
     double mg[NOCT][2];
     unsigned long long isum[NOCT][2];
-    double acc[2][NOCT][2];
+    double acc[NOCT][2];                                     // one chain per octet: both row tiles of the pair add into it
 #pragma unroll
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             mg[pt][e] = magic[(size_t)(oct0 + pt) * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
-            acc[0][pt][e] = 0.0; acc[1][pt][e] = 0.0;
+            acc[pt][e] = 0.0;
         }
 
     for (int t = T0; t < T1; ++t) {
@@ -667,10 +691,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             double2 an = a;
             if (j + 1 < nj) an = xa[(j + 1) * 32];
 #pragma unroll
-            for (int pt = 0; pt < NOCT; ++pt) {
-                dmma884(acc[0][pt][0], acc[0][pt][1], a.x, b[j][pt]);
-                dmma884(acc[1][pt][0], acc[1][pt][1], a.y, b[j][pt]);
-            }
+            for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.x, b[j][pt]);
+#pragma unroll
+            for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
             a = an;
         }
         __syncwarp();                                        // every lane's reads of the stage have landed
@@ -683,16 +706,16 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
         for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[0][pt][e], mg[pt][e]));
-                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[1][pt][e], mg[pt][e]));
-                acc[0][pt][e] = 0.0; acc[1][pt][e] = 0.0;
+                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[pt][e], mg[pt][e]));
+                acc[pt][e] = 0.0;
             }
     }
 
     if (tid == 0) { tl_min(tl, TL_XLOOP0); tl_max(tl, TL_XLOOP1); }
-    // remove the magic offsets (two conversions per observation tile), sum the 8 rows held by the
+    if (tlc && tid == 0 && blockIdx.x < TL_CTA_MAX) tlc[blockIdx.x * 4 + 2] = gtime();
+    // remove the magic offsets (one conversion per observation tile), sum the 8 rows held by the
     // lanes of each column group, and add the CTA's share to the particles' accumulators
-    const unsigned long long n_conv = 2ull * (unsigned long long)(T1 - T0);
+    const unsigned long long n_conv = (unsigned long long)(T1 - T0);
 #pragma unroll
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
@@ -710,11 +733,11 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
 }
 
 __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
-                                                                     long long *ll_acc, XdGrid g, unsigned long long *tl)
+                                                                     long long *ll_acc, XdGrid g, unsigned long long *tl, unsigned long long *tlc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_launch_dependents();
-    if (threadIdx.x == 0) { tl_min(tl, TL_X0); tl_max(tl, TL_X0MAX); }
+    if (threadIdx.x == 0) { tl_min(tl, TL_X0); tl_max(tl, TL_X0MAX); if (tlc && blockIdx.x < TL_CTA_MAX) tlc[blockIdx.x * 4] = gtime(); }
     int oct0, c_in, C, noct;
     const int n_in_hi = g.n_hi * g.c_hi;
     if ((int)blockIdx.x < n_in_hi) { const int t = blockIdx.x / g.c_hi; c_in = blockIdx.x - t * g.c_hi; C = g.c_hi; noct = g.oct_hi; oct0 = t * g.oct_hi; }
@@ -722,12 +745,13 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
     if (T1 <= T0) { pdl_wait(); return; }
-    switch (noct) {
-    case 4: xdot_body<4>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
-    case 3: xdot_body<3>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
-    case 2: xdot_body<2>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
-    default: xdot_body<1>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl); break;
+#define XD_CALL(NO, NJC) xdot_body<NO, NJC>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl, tlc)
+    if (m.ssd_nj == SSD_NJ) {
+        switch (noct) { case 4: XD_CALL(4, SSD_NJ); break; case 3: XD_CALL(3, SSD_NJ); break; case 2: XD_CALL(2, SSD_NJ); break; default: XD_CALL(1, SSD_NJ); break; }
+    } else {
+        switch (noct) { case 4: XD_CALL(4, 0); break; case 3: XD_CALL(3, 0); break; case 2: XD_CALL(2, 0); break; default: XD_CALL(1, 0); break; }
     }
+#undef XD_CALL
 }
 
 // centred means of arbitrary parameter vectors in the k_xdot layout (demcmc_eval, initial weights)
@@ -789,7 +813,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
     }
     const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
     dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)m.n_ksplit);
-    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, lv.ctxs ? tl_slot() : (unsigned long long *)nullptr));
+    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, lv.ctxs ? tl_slot() : (unsigned long long *)nullptr, lv.ctxs ? tl_cta() : (unsigned long long *)nullptr));
     LAUNCHED("k_xdot");
     return 0;
 }
@@ -900,7 +924,7 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
     double xx = 0.0, mx = 0.0;
     for (int b = 0; b < n_blk; ++b) { xx += h[b]; mx = std::max(mx, h[n_blk + b]); }
     m->ssd_xx = xx;
-    m->ssd_rowmax = sqrt(mx);
+    m->ssd_rowmax = 2.0 * sqrt(mx);                          // a chain of k_xdot sums the terms of TWO observation rows
     dfree(tmp); dfree(blk);
     if (e != cudaSuccess) return cu_fail(e, "k_pack_rows");
     return 0;

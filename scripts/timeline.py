@@ -37,3 +37,14 @@ print("accept end -> next propose start %.2f us" % float(np.mean(nxt)))
 print("level period %.2f us" % float(np.mean([R[i + 1]["propose_start"] - R[i]["propose_start"] for i in range(len(R) - 1)])))
 ideal = mean(lambda r: np.ceil(r["n"] / 8) * 1563 * 8 * 13 * 16 / (148 * 4) / 1965.0)
 print("ideal DMMA time of the level %.2f us" % ideal)
+cta_file = out + ".cta"
+if os.path.exists(cta_file):
+    C = [{k: float(v) for k, v in r.items()} for r in csv.DictReader(open(cta_file))]
+    dur = np.array([c["loop_end"] - c["wait_done"] for c in C]); tiles = np.array([c["tiles"] // 10 for c in C]); noct = np.array([c["tiles"] % 10 for c in C])
+    print("per-CTA loop durations of one level: n_cta %d, min %.1f median %.1f p90 %.1f max %.1f us; wait_done spread %.1f us" % (
+        len(C), dur.min(), np.median(dur), np.percentile(dur, 90), dur.max(), max(c["wait_done"] for c in C) - min(c["wait_done"] for c in C)))
+    per_tile = dur / (tiles * noct / 4.0)
+    print("us per (tile x 4 octets): min %.3f median %.3f max %.3f; ideal at 2 CTAs/SM %.3f" % (per_tile.min(), np.median(per_tile), per_tile.max(), 13 * 8 * 16 * 2 / 1965.0))
+    for q in (0, len(C) // 4, len(C) // 2, 3 * len(C) // 4, len(C) - 1):
+        c = sorted(C, key=lambda c: c["loop_end"])[q]
+        print("  cta %4d tiles %3d oct %d start %.1f wait %.1f end %.1f" % (c["cta"], c["tiles"] // 10, c["tiles"] % 10, c["start"], c["wait_done"], c["loop_end"]))
