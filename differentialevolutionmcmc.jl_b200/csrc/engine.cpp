@@ -77,7 +77,7 @@ struct demcmc_handle {
     // schedule ring
     static constexpr int RING = 4;
     int max_chunk = MAX_CHUNK;                          // sweeps overlapped on the device (1 = a barrier per sweep)
-    int n_lanes = 2;                                    // concurrent kernel chains over independent sets of groups
+    int n_lanes = 1;                                    // concurrent kernel chains over independent sets of groups (demcmc_set_lanes)
     Upload ring[RING];
     int64_t ring_use = 0;
     // migration

@@ -669,17 +669,31 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     }
     double mg[NOCT][2];
     unsigned long long isum[NOCT][2];
-    double acc[NOCT][2];                                     // one chain per octet: both row tiles of the pair add into it
+    // one chain per octet (both row tiles of the pair add into it), and TWO sets of them used by
+    // alternate observation tiles: a tile's chains are rounded to the fixed-point grid one k-step
+    // into the NEXT tile, when they have drained on their own, so the tile boundary costs neither a
+    // pipe drain nor a block of conversions
+    double accA[NOCT][2], accB[NOCT][2];
 #pragma unroll
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             mg[pt][e] = magic[(size_t)(oct0 + pt) * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
-            acc[pt][e] = 0.0;
+            accA[pt][e] = 0.0; accB[pt][e] = 0.0;
         }
-
-    for (int t = T0; t < T1; ++t) {
+    auto convert = [&](double (&acc)[NOCT][2]) {
+#pragma unroll
+        for (int pt = 0; pt < NOCT; ++pt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[pt][e], mg[pt][e]));
+                acc[pt][e] = 0.0;
+            }
+    };
+    // one observation tile: its DMMAs go to `acc`; `prev` (the other set) is converted after the
+    // first k-step when it holds the previous tile
+    auto tile = [&](int t, double (&acc)[NOCT][2], double (&prev)[NOCT][2], bool have_prev) {
         const int it = t - T0, st = it & (XD_STAGES - 1);
         mbar_wait(&full[st], (uint32_t)(it / XD_STAGES) & 1u);
         if (tl && tid == 0 && t == T0) tl_max(tl, TL_XFIRST);
@@ -695,21 +709,22 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
 #pragma unroll
             for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
             a = an;
+            if (j == 0 && have_prev) convert(prev);
         }
         __syncwarp();                                        // every lane's reads of the stage have landed
         if (lane == 0 && t + XD_STAGES < T1) {
             mbar_expect_tx(&full[st], stage_bytes);
             bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + XD_STAGES) * stage_doubles, stage_bytes, &full[st]);
         }
-        // the rows' chains end with the observation tile: round to the particle's grid, add as integers
-#pragma unroll
-        for (int pt = 0; pt < NOCT; ++pt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                isum[pt][e] += (unsigned long long)xd_bits(__dadd_rn(acc[pt][e], mg[pt][e]));
-                acc[pt][e] = 0.0;
-            }
+    };
+    int t = T0;
+    tile(t++, accA, accB, false);
+    for (; t + 1 < T1; t += 2) {
+        tile(t, accB, accA, true);
+        tile(t + 1, accA, accB, true);
     }
+    if (t < T1) { tile(t, accB, accA, true); convert(accB); }
+    else convert(accA);
 
     if (tid == 0) { tl_min(tl, TL_XLOOP0); tl_max(tl, TL_XLOOP1); }
     if (tlc && tid == 0 && blockIdx.x < TL_CTA_MAX) tlc[blockIdx.x * 4 + 2] = gtime();

@@ -184,9 +184,9 @@ int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_log
  * 1 = a barrier after every sweep).  The result does not depend on it. */
 int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps);
 /* how many independent sets of groups run as concurrent kernel chains (groups never read each other
- * between migrations, src/main.jl:161-167): with 2 (the default when the handle holds >= 2 groups)
- * the likelihood kernel of one set hides the propose / accept latency of the other.  1 = one chain.
- * The result does not depend on it. */
+ * between migrations, src/main.jl:161-167): with 2 the likelihood kernel of one set can hide the
+ * propose / accept latency of the other.  Default 1: since those two kernels were shortened the second
+ * chain only adds launches (profiles/README.md).  The result does not depend on it. */
 int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes);
 
 /* compute_posterior! pieces (src/utilities.jl:92-99) for n arbitrary parameter vectors
