@@ -477,7 +477,7 @@ int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *
 template <int KIND>
 __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const double *theta, Level lv, double *part)
 {
-    constexpr int NPAR = MAX_ACC + 4;
+    constexpr int NPAR = MAX_ACC + 5;
     __shared__ double par[PW_TP][NPAR];
     __shared__ double red[PW_THREADS / 32][PW_TP];
     const int tile = blockIdx.x, split = blockIdx.y, tid = threadIdx.x;
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
             for (int r = 0; r < m.n_dim; ++r) { par[tid][r] = th[r]; pneg *= norm_cdf(-th[r]); }
             par[tid][m.n_dim] = th[m.n_dim]; par[tid][m.n_dim + 1] = th[m.n_dim + 1]; par[tid][m.n_dim + 2] = th[m.n_dim + 2];
             par[tid][m.n_dim + 3] = 1.0 / (1.0 - pneg);
+            par[tid][m.n_dim + 4] = 1.0 / th[m.n_dim];
         }
     }
     __syncthreads();
