@@ -9,4 +9,5 @@ from . import _ffi  # noqa: F401
 from .handle import (Handle, comm_unique_id, copy_peak, fp64_peak, fp64_peaks, op_accept, op_de_proposal, op_project,  # noqa: F401
                      op_reset, op_select, op_snooker)
 from .api import (DE, DEModel, Beta, Chains, Flat, GPULoglike, GPUPrior, HalfCauchy, MCMCThreads, Normal,  # noqa: F401
-                  NormalRef, Uniform, fixed_gamma, random_gamma, resample, sample, variable_gamma)
+                  NormalRef, Particle, Uniform, compute_posterior, evaluate_fun, fixed_gamma, get_optimal, maximize,
+                  mh_update, minimize, optimize, random_gamma, resample, sample, variable_gamma)

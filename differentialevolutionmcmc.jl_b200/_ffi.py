@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libdemcmc_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -45,7 +45,7 @@ class Config(C.Structure):
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
                 ("seed", C.c_uint64), ("device", C.c_int32), ("group_begin", C.c_int32),
                 ("group_count", C.c_int32), ("donors", C.c_int32), ("trace", C.c_int32),
-                ("store_every", C.c_int32)]
+                ("store_every", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32)]
 
 
 class Tape(C.Structure):

@@ -92,7 +92,7 @@ class GPULoglike:
     GPULoglike("lba", choice=c, rt=t)            sum(logpdf.(LBA(;ν,A,k,τ), c, t))
     GPULoglike("hier_normal", Y)                 Y is n_subj × n_per (Examples/Hierarchical_Example.jl)
     """
-    KINDS = ("gaussian", "mvnormal", "binomial", "lnr", "lba", "hier_normal")
+    KINDS = ("gaussian", "mvnormal", "binomial", "lnr", "lba", "hier_normal", "rastrigin")
 
     def __init__(self, kind, x=None, *, choice=None, rt=None, N=None, k=None, sigma=None, lba_floor=1e-10):
         kind = str(kind).lstrip(":")
@@ -102,7 +102,9 @@ class GPULoglike:
         self.choice = None
         self.sigma = sigma
         self.lba_floor = lba_floor
-        if kind == "binomial":
+        if kind == "rastrigin":              # the objective of test/optimization_tests.jl:15-23: no data
+            self.x = np.zeros(0)
+        elif kind == "binomial":
             if N is None or k is None:
                 raise ValueError("binomial needs N and k")
             self.x = np.array([float(N), float(k)])
@@ -132,6 +134,29 @@ class MCMCThreads:
 def resample(*a):
     """DE(sample=resample): DE-MCz donors from the history (src/crossover.jl:113-124)."""
     raise TypeError("resample is a donor selector for DE(sample=...), not a host function")
+
+
+def maximize(*a):
+    """DE(update_particle=maximize): the greedy maximize! of optimize (src/utilities.jl:212-218)."""
+    raise TypeError("maximize is an update selector for DE(update_particle=...), not a host function")
+
+
+def minimize(*a):
+    """DE(update_particle=minimize): minimize! (src/utilities.jl:220-226)."""
+    raise TypeError("minimize is an update selector")
+
+
+def mh_update(*a):
+    raise TypeError("mh_update is an update selector")
+
+
+def evaluate_fun(*a):
+    """DE(evaluate_fitness=evaluate_fun): the registered kernel alone, no prior (src/utilities.jl:113-120)."""
+    raise TypeError("evaluate_fun is a fitness selector")
+
+
+def compute_posterior(*a):
+    raise TypeError("compute_posterior is a fitness selector")
 
 
 def random_gamma(*a):
@@ -185,8 +210,12 @@ class DE:
         self.bounds = tuple(bounds)
         self.n_initial = int(n_initial)
         self.iter = 1
-        if update_particle is not None or evaluate_fitness is not None:
-            raise NotImplementedError("only mh_update! / compute_posterior! are built on the B200 path (optimize is not)")
+        if update_particle not in (None, mh_update, maximize, minimize):
+            raise TypeError("update_particle must be mh_update, maximize or minimize: a custom host function cannot run on the device")
+        if evaluate_fitness not in (None, compute_posterior, evaluate_fun):
+            raise TypeError("evaluate_fitness must be compute_posterior or evaluate_fun")
+        self.update_particle = update_particle or mh_update
+        self.evaluate_fitness = evaluate_fitness or compute_posterior
         if sample is not None and sample is not resample:
             raise TypeError("sample must be left at its default (donors from the current group) or be `resample`: a custom host function cannot run on the device")
         self.sample = sample
@@ -295,8 +324,10 @@ def _expand_block(block, shapes):
     return out
 
 
-def _prior_table(model, shapes):
+def _prior_table(model, shapes, needed=True):
     pl = model.prior_loglike
+    if pl is None and not needed:          # evaluate_fun! never calls prior_loglike (utilities.jl:113-120)
+        return [("flat", 0.0, 0.0, 0)] * sum(int(np.prod(sh)) if len(sh) else 1 for sh in shapes)
     if not isinstance(pl, GPUPrior):
         raise TypeError(
             "prior_loglike must be a GPUPrior of registered specs: a host closure would need a host round trip per "
@@ -339,8 +370,9 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
     h = Handle(de.n_groups, de.Np, d, lo, hi, burnin=de.burnin, n_initial=de.n_initial, alpha=de.α, beta=de.β, eps=de.ϵ,
                sigma=de.σ, kappa=de.κ, theta_snooker=de.θsnooker, proposal=_PROPOSAL_NAMES[de.generate_proposal],
                blocks=blocks, seed=seed, device=device, trace=trace, group_begin=group_begin, group_count=group_count,
-               resample=de.sample is resample)
-    h.set_model(ll.kind, _prior_table(model, shapes), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
+               resample=de.sample is resample, update={mh_update: "mh", maximize: "maximize", minimize: "minimize"}[de.update_particle],
+               fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior")
+    h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
     return h, shapes, d
 
 
@@ -380,6 +412,55 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         return Chains(arr.transpose(2, 1, 0), names, [str(n) for n in model.names])
     finally:
         h.close()
+
+
+class Particle:
+    """What optimize returns per particle (src/structs.jl:202-223): Θ (one entry per named parameter),
+    weight and id."""
+
+    def __init__(self, Θ, weight, id):
+        self.Θ, self.weight, self.id = Θ, weight, id
+
+
+def optimize(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
+    """optimize(model, de, n_iter) / optimize(model, de, MCMCThreads(), n_iter) (src/optimize.jl:17-66):
+    the same population step with de.update_particle = maximize / minimize and
+    de.evaluate_fitness = evaluate_fun; returns vcat(groups...) as a list of Particles."""
+    if len(args) == 2 and isinstance(args[0], MCMCThreads):
+        n_iter = int(args[1])
+    elif len(args) == 1:
+        n_iter = int(args[0])
+    else:
+        raise TypeError("optimize(model, de, n_iter) or optimize(model, de, MCMCThreads(), n_iter)")
+    h, shapes, d = build_handle(model, de, device=device)
+    try:
+        P = de.n_groups * de.Np
+        theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)
+        h.set_state(theta0)
+        h.run(n_iter)
+        de.iter = n_iter
+        th, w, ids = h.get_state()
+    finally:
+        h.close()
+    out = []
+    for c in range(P):
+        Θ, k = [], 0
+        for sh in shapes:
+            n = int(np.prod(sh)) if len(sh) else 1
+            Θ.append(th[c, k:k + n].reshape(sh, order="F") if len(sh) else float(th[c, k]))
+            k += n
+        out.append(Particle(Θ, float(w[c]), int(ids[c]) + 1))
+    return out
+
+
+def get_optimal(de: DE, model: DEModel, particles):
+    """get_optimal (src/utilities.jl:258-266): the best particle's Θ by name and its weight."""
+    better = (lambda a, b: a > b) if de.update_particle is maximize else (lambda a, b: a < b)
+    mx = particles[0]
+    for p in particles:
+        if better(p.weight, mx.weight):
+            mx = p
+    return {str(n): v for n, v in zip(model.names, mx.Θ)}, mx.weight
 
 
 def bundle_samples(model, de, samples, accept, lp, final_ids, shapes, n_iter):

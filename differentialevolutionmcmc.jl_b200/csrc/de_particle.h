@@ -67,6 +67,11 @@ DE_HD double finalize_ll(const ModelDev &m, const double *theta, double total, d
         return -(double)m.n_obs * (DE_LOG2PI / 2.0 + log(sig)) - (ssd / (sig * sig)) / 2.0;
     }
     case M_BINOMIAL: return binomial_ll(m.binom_N, m.binom_k, theta[0]);
+    case M_RASTRIGIN: {     // test/optimization_tests.jl:15-23
+        double y = 10.0 * (double)m.d;
+        for (int i = 0; i < m.d; ++i) y += +(theta[i] * theta[i]) - 10.0 * cos(2.0 * DE_PI * theta[i]);
+        return y;
+    }
     default: return total;
     }
 }
@@ -245,24 +250,28 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];
     else {
         double part = 0.0;
-        if (m.kind != M_BINOMIAL)
+        if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN)
             for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
         total = co.sum(part);
     }
     const double msq = (m.kind == M_MVNORMAL || m.kind == M_HIER) ? ctx.prop_msq[p] : 0.0;
     const double ll = finalize_ll(m, prop, total, msq);
     const bool inb = ctx.prop_inb[p] != 0;
-    const double wprop = inb ? add(ctx.prop_prior[p], ll) : -inf();
+    // compute_posterior! (utilities.jl:92-99), or evaluate_fun! (utilities.jl:113-120): the kernel
+    // alone, and out of bounds loses every comparison
+    const double wprop = cfg.fitness == FITNESS_FUN ? (inb ? ll : (cfg.update == UPDATE_MAXIMIZE ? -inf() : inf()))
+                                                    : (inb ? add(ctx.prop_prior[p], ll) : -inf());
     const double adj = ctx.prop_adj[p];
     const double wcur = ctx.cur_w[p];
-    const bool acc = accept(wprop, wcur, adj, u);
+    // mh_update! (utilities.jl:201-210), maximize! / minimize! (utilities.jl:212-226)
+    const bool acc = cfg.update == UPDATE_MAXIMIZE ? wprop > wcur : cfg.update == UPDATE_MINIMIZE ? wprop < wcur : accept(wprop, wcur, adj, u);
     double *dst = ctx.next_theta + (size_t)p * d;
     for (int k = co.lane(); k < d; k += co.width()) dst[k] = acc ? prop[k] : tcur[k];
     if (co.lane() == 0) {
         ctx.next_w[p] = acc ? wprop : wcur;
         ctx.next_id[p] = ctx.cur_id[p];
         if (ctx.next_pos) ctx.next_pos[ctx.cur_id[p] - cfg.group_begin * Np] = p;
-        ctx.next_acc[p] = acc ? 1 : 0;
+        ctx.next_acc[p] = (acc && cfg.update == UPDATE_MH) ? 1 : 0;       // maximize!/minimize! never write Particle.accept
         if (ctx.tr_w) { ctx.tr_w[p] = wprop; ctx.tr_adj[p] = adj; ctx.tr_acc[p] = acc ? 1 : 0; }
     }
 }

@@ -14,7 +14,9 @@ constexpr int SSD_KS = 4 * SSD_NJ; // max dimensions per dimension split
 constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
 constexpr int PW_THREADS = 256;
 
-enum ModelKind { M_GAUSSIAN = 0, M_MVNORMAL = 1, M_BINOMIAL = 2, M_LNR = 3, M_LBA = 4, M_HIER = 5 };
+enum ModelKind { M_GAUSSIAN = 0, M_MVNORMAL = 1, M_BINOMIAL = 2, M_LNR = 3, M_LBA = 4, M_HIER = 5, M_RASTRIGIN = 6 };
+enum { UPDATE_MH = 0, UPDATE_MAXIMIZE = 1, UPDATE_MINIMIZE = 2 };
+enum { FITNESS_POSTERIOR = 0, FITNESS_FUN = 1 };
 
 // The registered likelihood a handle is bound to (GPULoglike), device-resident.
 struct ModelDev {
@@ -60,6 +62,7 @@ DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n
 struct ConfigDev {
     int32_t Np, d, G_local, group_begin, proposal, burnin, n_blocks;
     int32_t resample;         // de.sample = resample: donors are (row, id) cells of the history
+    int32_t update, fitness;  // UPDATE_* / FITNESS_*: mh_update! + compute_posterior!, or the optimize path
     double eps, sigma, kappa, theta_snooker;
     const double *lo, *hi;    // [d]
     const uint8_t *blocks;    // [n_blocks][d]

@@ -179,6 +179,9 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     if (cfg->proposal < 0 || cfg->proposal > 2) return fail(DEMCMC_EINVAL, "unknown generate_proposal %d", cfg->proposal);
     if (cfg->store_every > 1) return fail(DEMCMC_EUNSUPPORTED, "thinning (store_every > 1) is not built yet");
     if (cfg->n_initial < 0 || cfg->donors < 0 || cfg->donors > 1) return fail(DEMCMC_EINVAL, "bad n_initial / donors");
+    if (cfg->update < 0 || cfg->update > DEMCMC_UPDATE_MINIMIZE || cfg->fitness < 0 || cfg->fitness > DEMCMC_FITNESS_FUN) return fail(DEMCMC_EINVAL, "unknown update_particle! / evaluate_fitness! kind");
+    if (cfg->update != DEMCMC_UPDATE_MH && cfg->theta_snooker != 0.0)
+        return fail(DEMCMC_EINVAL, "maximize! / minimize! take no log_adj: with theta_snooker > 0 the reference throws a MethodError (crossover.jl:38)");
     if (cfg->donors == DEMCMC_DONORS_HISTORY) {
         // resample (crossover.jl:113-124) draws from rows 1:de.iter-1: there must be rows to draw from
         if ((int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3) return fail(DEMCMC_EINVAL, "sample = resample needs n_initial prior rows (at least 3 stored particles)");
@@ -247,7 +250,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     ConfigDev &c = h->dcfg;
     c.Np = cfg->Np; c.d = cfg->d; c.G_local = h->G_local; c.group_begin = cfg->group_begin; c.proposal = cfg->proposal;
     c.burnin = cfg->burnin; c.n_blocks = cfg->n_blocks; c.eps = cfg->eps; c.sigma = cfg->sigma; c.kappa = cfg->kappa;
-    c.resample = cfg->donors; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
+    c.resample = cfg->donors; c.update = cfg->update; c.fitness = cfg->fitness; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
     *out = h;
     return 0;
 }
@@ -297,10 +300,11 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
     case DEMCMC_LNR: want_d = m->n_dim + 1; break;
     case DEMCMC_LBA: want_d = m->n_dim + 3; break;
     case DEMCMC_HIER_NORMAL: want_d = m->n_dim + 3; break;
+    case DEMCMC_RASTRIGIN: want_d = m->d; break;
     default: return fail(DEMCMC_EUNSUPPORTED, "no registered kernel for model kind %d: arbitrary closures are not supported and there is no CPU fallback", m->kind);
     }
     if (m->d != want_d) return fail(DEMCMC_EINVAL, "model kind %d expects d = %d, got %d", m->kind, want_d, m->d);
-    if (!m->x) return fail(DEMCMC_EINVAL, "model data missing");
+    if (!m->x && m->kind != DEMCMC_RASTRIGIN) return fail(DEMCMC_EINVAL, "model data missing");
     if ((m->kind == DEMCMC_LNR || m->kind == DEMCMC_LBA) && (!m->choice || m->n_dim < 2 || m->n_dim > MAX_ACC))
         return fail(DEMCMC_EINVAL, "LNR/LBA need choices and 2..%d accumulators", MAX_ACC);
     if (m->n_obs < 0) return fail(DEMCMC_EINVAL, "negative n_obs");
@@ -317,7 +321,9 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
     if (!D.prior) return fail(DEMCMC_ENOMEM, "prior upload failed");
     const bool dev = m->data_on_device != 0;
     D.n_osplit = 1; D.n_ksplit = 1; D.split_len = 0; D.ksplit_len = 0;
-    if (m->kind == DEMCMC_BINOMIAL) {
+    if (m->kind == DEMCMC_RASTRIGIN) {
+        D.n_obs = 0;                                  // an objective of the parameters alone (optimize path)
+    } else if (m->kind == DEMCMC_BINOMIAL) {
         double nk[2];
         if (dev) { BE(be::d2h(nk, m->x, sizeof nk)); } else memcpy(nk, m->x, sizeof nk);
         D.binom_N = nk[0]; D.binom_k = nk[1]; D.n_obs = 1;
@@ -750,6 +756,7 @@ static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *a
     int rc = 0;
     if (samples) ds = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P * d));
     if (lp) dl = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P));
+    const bool lp_written = h->cfg.update == DEMCMC_UPDATE_MH;     // maximize!/minimize! leave Particle.lp at 0.0
     if (accept) da = (uint8_t *)be::dmalloc(std::max<size_t>(1, n_rows * P));
     if ((samples && !ds) || (lp && !dl) || (accept && !da)) rc = fail(DEMCMC_ENOMEM, "output staging does not fit on the device");
     if (!rc && n_rows > 0) {
@@ -758,7 +765,7 @@ static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *a
         if (da && be::dzero(da, n_rows * P)) rc = DEMCMC_ECUDA;
         if (!rc && n0 + h->iters_done > 0 && (n0 == 0 || h->has_history) &&
             be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, n0 + h->iters_done, 0, n_rows, (int32_t)P, (int32_t)d,
-                                     h->cfg.group_begin * h->cfg.Np, ds, dl, da)) rc = DEMCMC_ECUDA;
+                                     h->cfg.group_begin * h->cfg.Np, ds, lp_written ? dl : nullptr, da)) rc = DEMCMC_ECUDA;
         if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
         if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
         if (!rc && da && be::d2h(accept, da, n_rows * P)) rc = DEMCMC_ECUDA;

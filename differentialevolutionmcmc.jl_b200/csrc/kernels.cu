@@ -837,7 +837,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc)
 {
     (void)cfg;
-    if (lv.n <= 0 || m.kind == M_BINOMIAL) return 0;
+    if (lv.n <= 0 || m.kind == M_BINOMIAL || m.kind == M_RASTRIGIN) return 0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
         // the proposal kernel of this level has staged the centred means and cleared the accumulators
         const XdStage &xs = g_xs[g_dev][g_lane];
@@ -963,14 +963,14 @@ __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, Model
     double s = 0.0;
     if (m.kind == M_MVNORMAL || m.kind == M_HIER) s = (double)acc[wi] * q[wi];
     else {
-        if (m.kind != M_BINOMIAL) for (int c = co.lane(); c < n_split; c += 32) s += part[(size_t)wi * n_split + c];
+        if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN) for (int c = co.lane(); c < n_split; c += 32) s += part[(size_t)wi * n_split + c];
         s = co.sum(s);
     }
     const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
     if (co.lane() == 0) {
         if (ll) ll[wi] = l;
         if (prior) prior[wi] = inb ? pr : -inf();
-        if (w) w[wi] = inb ? add(pr, l) : -inf();
+        if (w) w[wi] = cfg.fitness == FITNESS_FUN ? (inb ? l : (cfg.update == UPDATE_MAXIMIZE ? -inf() : inf())) : (inb ? add(pr, l) : -inf());
     }
 }
 

@@ -8,7 +8,9 @@ import numpy as np
 from . import _ffi
 from ._ffi import _bp, _dp, _ip, check, f8, ptr
 
-KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5}
+KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6}
+UPDATES = {"mh": 0, "maximize": 1, "minimize": 2}
+FITNESS = {"posterior": 0, "fun": 1}
 PRIORS = {"flat": 0, "normal": 1, "halfcauchy": 2, "uniform": 3, "beta": 4, "normal_ref": 5}
 PROPOSALS = {"random_gamma": 0, "fixed_gamma": 1, "variable_gamma": 2}
 
@@ -18,7 +20,7 @@ class Handle:
 
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None, seed=0,
-                 device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False):
+                 device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False, update="mh", fitness="posterior"):
         self._h = C.c_void_p()
         self.lo, self.hi = f8(lo), f8(hi)
         if self.lo.shape != (d,) or self.hi.shape != (d,):
@@ -28,7 +30,8 @@ class Handle:
         prop = PROPOSALS[proposal] if isinstance(proposal, str) else int(proposal)
         self.cfg = _ffi.Config(_ffi.ABI_VERSION, n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa,
                                theta_snooker, prop, nb, ptr(self.blocks, _bp), ptr(self.lo, _dp), ptr(self.hi, _dp),
-                               int(seed) & (2**64 - 1), device, group_begin, group_count, int(bool(resample)), int(bool(trace)), store_every)
+                               int(seed) & (2**64 - 1), device, group_begin, group_count, int(bool(resample)), int(bool(trace)), store_every,
+                               UPDATES[update], FITNESS[fitness])
         self.n_groups, self.Np, self.d = n_groups, Np, d
         self.G_local = group_count if group_count > 0 else n_groups
         self.P = self.G_local * Np
@@ -78,7 +81,7 @@ class Handle:
             if n_obs is None:
                 raise ValueError("n_obs is required with device pointers")
         else:
-            xs = f8(x)
+            xs = f8(x if x is not None else [])
             cs = None if choice is None else np.ascontiguousarray(choice, dtype=np.int32)
             xp = xs.ctypes.data
             cp = cs.ctypes.data if cs is not None else None
@@ -89,6 +92,8 @@ class Handle:
                 n_obs = n_dim * n_per
             elif kind == "binomial":
                 n_obs = 1
+            elif kind == "rastrigin":
+                n_obs = 0
             else:
                 n_obs = xs.shape[0]
                 if kind in ("lnr", "lba") and not n_dim:

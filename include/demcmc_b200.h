@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DEMCMC_ABI_VERSION 1
+#define DEMCMC_ABI_VERSION 2
 
 enum { DEMCMC_OK = 0, DEMCMC_EINVAL = -1, DEMCMC_ENODEVICE = -2, DEMCMC_ECUDA = -3, DEMCMC_ENOMEM = -4,
        DEMCMC_ESTATE = -5, DEMCMC_EUNSUPPORTED = -6, DEMCMC_ECOMM = -7 };
@@ -32,7 +32,13 @@ enum { DEMCMC_OK = 0, DEMCMC_EINVAL = -1, DEMCMC_ENODEVICE = -2, DEMCMC_ECUDA = 
 /* GPULoglike kinds: the registered hand-written likelihood kernels (replace the user closures
  * `loglike(data, theta...)`, e.g. Examples/Gaussian_Example.jl:26-28) */
 enum { DEMCMC_GAUSSIAN = 0, DEMCMC_MVNORMAL = 1, DEMCMC_BINOMIAL = 2, DEMCMC_LNR = 3, DEMCMC_LBA = 4,
-       DEMCMC_HIER_NORMAL = 5 };
+       DEMCMC_HIER_NORMAL = 5,
+       DEMCMC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23 (optimize path; no data) */ };
+/* de.update_particle! (src/utilities.jl:201-226): mh_update!, or the greedy maximize! / minimize! of
+ * optimize (src/optimize.jl); de.evaluate_fitness! (src/utilities.jl:92-120): compute_posterior!, or
+ * evaluate_fun! = the registered kernel alone, no prior, out of bounds = -/+Inf */
+enum { DEMCMC_UPDATE_MH = 0, DEMCMC_UPDATE_MAXIMIZE = 1, DEMCMC_UPDATE_MINIMIZE = 2 };
+enum { DEMCMC_FITNESS_POSTERIOR = 0, DEMCMC_FITNESS_FUN = 1 };
 /* registered prior specs (replace `prior_loglike(theta...)`, e.g. Examples/Gaussian_Example.jl:11-16) */
 enum { DEMCMC_PRIOR_FLAT = 0, DEMCMC_PRIOR_NORMAL = 1, DEMCMC_PRIOR_HALFCAUCHY = 2,
        DEMCMC_PRIOR_UNIFORM = 3, DEMCMC_PRIOR_BETA = 4, DEMCMC_PRIOR_NORMAL_REF = 5 };
@@ -93,6 +99,10 @@ typedef struct {
     int32_t trace;           /* 1: keep per-sweep proposals / proposal weights / log_adj for
                                 demcmc_get_trace (parity tests) */
     int32_t store_every;     /* 1 = keep every iteration (reference behaviour, utilities.jl:161-180) */
+    int32_t update;          /* DEMCMC_UPDATE_*; maximize!/minimize! need theta_snooker == 0 (they take no log_adj:
+                                the reference's snooker branch would throw a MethodError, crossover.jl:38) and
+                                leave accept / lp untouched (false / 0.0) */
+    int32_t fitness;         /* DEMCMC_FITNESS_* */
 } demcmc_config;
 
 /* Structured replay tape: the reference's own random draws, recorded

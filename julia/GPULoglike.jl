@@ -17,9 +17,9 @@
 # GPU path with a closure throws an ArgumentError -- there is no silent CPU fallback.
 
 const LIBDEMCMC = get(ENV, "LIBDEMCMC_B200", "libdemcmc_b200.so")
-const DEMCMC_ABI_VERSION = Int32(1)
+const DEMCMC_ABI_VERSION = Int32(2)
 
-const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5)
+const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5, rastrigin = 6)
 const GPU_PRIORS = (flat = 0, normal = 1, halfcauchy = 2, uniform = 3, beta = 4, normal_ref = 5)
 
 """
@@ -116,6 +116,8 @@ struct CConfig
     donors::Int32          # 0 = sample (current group), 1 = resample (history, DE-MCz)
     trace::Int32
     store_every::Int32
+    update::Int32          # 0 mh_update!, 1 maximize!, 2 minimize!
+    fitness::Int32         # 0 compute_posterior!, 1 evaluate_fun!
 end
 
 function demcmc_check(rc)
@@ -179,10 +181,13 @@ function sample(model::DEModel{<:GPULoglike}, de::DE, ::MCMCThreads, n_iter::Int
     return _sample_gpu(model, de, n_iter; device, seed)    # every group is always updated concurrently on the device
 end
 
-function _sample_gpu(model, de, n_iter; device, seed)
-    model.prior_loglike isa GPUPrior || throw(ArgumentError("prior_loglike must be a GPUPrior: a Julia closure would need a host round trip per particle"))
-    de.update_particle! === mh_update! && de.evaluate_fitness! === compute_posterior! ||
-        throw(ArgumentError("only mh_update! / compute_posterior! are built on the B200 path"))
+function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
+    model.prior_loglike isa GPUPrior || de.evaluate_fitness! === evaluate_fun! ||
+        throw(ArgumentError("prior_loglike must be a GPUPrior: a Julia closure would need a host round trip per particle"))
+    update = de.update_particle! === mh_update! ? Int32(0) : de.update_particle! === maximize! ? Int32(1) :
+             de.update_particle! === minimize! ? Int32(2) : throw(ArgumentError("update_particle! must be mh_update!, maximize! or minimize!"))
+    fitness = de.evaluate_fitness! === compute_posterior! ? Int32(0) : de.evaluate_fitness! === evaluate_fun! ? Int32(1) :
+              throw(ArgumentError("evaluate_fitness! must be compute_posterior! or evaluate_fun!"))
     de.sample === sample || de.sample === resample ||
         throw(ArgumentError("de.sample must be `sample` or `resample`: a custom donor function cannot run on the device"))
     donors = de.sample === resample ? Int32(1) : Int32(0)
@@ -218,15 +223,17 @@ function _sample_gpu(model, de, n_iter; device, seed)
     accept = zeros(UInt8, n_rows, P)
     lp = zeros(Float64, n_rows, P)
     final_ids = zeros(Int32, P)
+    final_theta = zeros(Float64, d, P)               # d × P == C [P][d]
+    final_weight = zeros(Float64, P)
     # initialize_samples (src/utilities.jl:29-41) already filled rows 1:n_initial of de.samples with
     # prior draws; the library wants them as [n_initial][P][d]
     init_rows = de.n_initial > 0 ?
         Float64[flatten_theta(de.samples[i, :, p])[k] for k = 1:d, p = 1:P, i = 1:(de.n_initial)] : Float64[]
     sig = ll.sigma === nothing ? Float64[] : ll.sigma
-    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids init_rows begin
+    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids final_theta final_weight init_rows begin
         cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, de.n_initial, de.α, de.β, de.ϵ, de.σ, de.κ,
             de.θsnooker, proposal_id(de), n_blocks, isempty(blocks) ? C_NULL : pointer(blocks), pointer(lo), pointer(hi),
-            seed, device, 0, 0, donors, 0, 1)
+            seed, device, 0, 0, donors, 0, 1, update, fitness)
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
@@ -242,7 +249,7 @@ function _sample_gpu(model, de, n_iter; device, seed)
             demcmc_check(ccall((:demcmc_get_samples, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], samples, n_rows))
             demcmc_check(ccall((:demcmc_get_accept, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], accept, n_rows))
             demcmc_check(ccall((:demcmc_get_lp, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], lp, n_rows))
-            demcmc_check(ccall((:demcmc_get_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), h[], C_NULL, C_NULL, final_ids))
+            demcmc_check(ccall((:demcmc_get_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), h[], final_theta, final_weight, final_ids))
         finally
             ccall((:demcmc_destroy, LIBDEMCMC), Cint, (Ptr{Cvoid},), h[])
         end
@@ -255,6 +262,15 @@ function _sample_gpu(model, de, n_iter; device, seed)
         id = final_ids[c] + 1
         p.accept = Bool.(accept[:, id])
         p.lp = lp[:, id]
+    end
+    if return_particles                              # optimize: vcat(groups...) in final position order
+        for (c, p) in enumerate(particles)
+            k = 0
+            p.Θ = as_union([begin n = n_elems(θ); v = θ isa AbstractArray ? reshape(final_theta[(k + 1):(k + n), c], size(θ)) : final_theta[k + 1, c]; k += n; v end for θ in Θ1])
+            p.weight = final_weight[c]
+            p.id = final_ids[c] + 1
+        end
+        return nothing, particles
     end
     groups = [particles[((g - 1) * de.Np + 1):(g * de.Np)] for g = 1:(de.n_groups)]
     return bundle_samples(model, de, groups, n_iter)
@@ -285,3 +301,15 @@ function nest_samples(flat, Θ1)
     end
     return out
 end
+
+
+# optimize(model, de, n_iter) (src/optimize.jl:17-66) for a GPULoglike model: the same device loop with
+# de.update_particle! = maximize!/minimize! and de.evaluate_fitness! = evaluate_fun! (both travel in
+# demcmc_config.update / .fitness).  _sample_gpu already rebuilt de.samples; the particles come back
+# from the final rows of it plus demcmc_get_state, so get_optimal(de, model, particles)
+# (src/utilities.jl:258-266) works unchanged.
+function optimize(model::DEModel{<:GPULoglike}, de::DE, n_iter::Int; progress = false, device = 0, seed = rand(UInt64), kwargs...)
+    _, particles = _sample_gpu(model, de, n_iter; device, seed, return_particles = true)
+    return particles
+end
+optimize(model::DEModel{<:GPULoglike}, de::DE, ::MCMCThreads, n_iter::Int; kwargs...) = optimize(model, de, n_iter; kwargs...)

@@ -232,6 +232,12 @@ double orc_loglike(const orc_model *m, const double *theta)
     case ORC_LNR: return ll_lnr(m, theta);
     case ORC_LBA: return ll_lba(m, theta);
     case ORC_HIER_NORMAL: return ll_hier(m, theta);
+    case ORC_RASTRIGIN: {       /* test/optimization_tests.jl:15-23 */
+        const double A = 10.0;
+        double y = A * (double)m->d;
+        for (int i = 0; i < m->d; ++i) y += +(theta[i] * theta[i]) - A * cos(2.0 * M_PI * theta[i]);
+        return y;
+    }
     }
     return NAN;
 }
@@ -247,6 +253,11 @@ static int in_bounds(const orc_config *cfg, const double *theta)
 /* compute_posterior! (utilities.jl:92-99) */
 double orc_posterior(const orc_config *cfg, const orc_model *m, const double *theta)
 {
+    if (cfg->fitness == ORC_FITNESS_FUN) {
+        /* evaluate_fun! (utilities.jl:113-120): the objective alone; out of bounds loses every comparison */
+        if (in_bounds(cfg, theta)) return orc_loglike(m, theta);
+        return cfg->update == ORC_UPDATE_MAXIMIZE ? -INFINITY : INFINITY;
+    }
     if (in_bounds(cfg, theta)) return orc_prior_loglike(m, theta) + orc_loglike(m, theta);
     return -INFINITY;
 }
@@ -409,10 +420,16 @@ typedef struct {
 static void mh_update(sampler *S, particle *cur, const double *prop, double wprop, double log_adj,
                       double u, int64_t row, int64_t ti)
 {
-    int acc = orc_accept(wprop, cur->weight, log_adj, u);
+    int acc;
+    if (S->cfg->update == ORC_UPDATE_MAXIMIZE) acc = wprop > cur->weight;         /* maximize! (utilities.jl:212-218) */
+    else if (S->cfg->update == ORC_UPDATE_MINIMIZE) acc = wprop < cur->weight;    /* minimize! (utilities.jl:220-226) */
+    else acc = orc_accept(wprop, cur->weight, log_adj, u);
     if (acc) { memcpy(cur->theta, prop, sizeof(double) * (size_t)S->cfg->d); cur->weight = wprop; }
-    S->accept[row + S->n_rows * cur->id] = (uint8_t)acc;
-    S->lp[row + S->n_rows * cur->id] = cur->weight;
+    /* maximize! / minimize! never touch Particle.accept / Particle.lp (they stay false / 0.0) */
+    if (S->cfg->update == ORC_UPDATE_MH) {
+        S->accept[row + S->n_rows * cur->id] = (uint8_t)acc;
+        S->lp[row + S->n_rows * cur->id] = cur->weight;
+    }
     if (S->trace && S->trace->accepted) S->trace->accepted[ti] = (uint8_t)acc;
 }
 

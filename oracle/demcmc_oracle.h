@@ -25,7 +25,11 @@ extern "C" {
 #endif
 
 /* registered likelihood kernels */
-enum { ORC_GAUSSIAN = 0, ORC_MVNORMAL = 1, ORC_BINOMIAL = 2, ORC_LNR = 3, ORC_LBA = 4, ORC_HIER_NORMAL = 5 };
+enum { ORC_GAUSSIAN = 0, ORC_MVNORMAL = 1, ORC_BINOMIAL = 2, ORC_LNR = 3, ORC_LBA = 4, ORC_HIER_NORMAL = 5,
+       ORC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23; no data */ };
+/* de.update_particle! (utilities.jl:201-226) and de.evaluate_fitness! (utilities.jl:92-120) */
+enum { ORC_UPDATE_MH = 0, ORC_UPDATE_MAXIMIZE = 1, ORC_UPDATE_MINIMIZE = 2 };
+enum { ORC_FITNESS_POSTERIOR = 0, ORC_FITNESS_FUN = 1 };
 /* registered prior specs, one per flattened parameter element */
 enum { ORC_PRIOR_FLAT = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_HALFCAUCHY = 2, ORC_PRIOR_UNIFORM = 3,
        ORC_PRIOR_BETA = 4, ORC_PRIOR_NORMAL_REF = 5 };
@@ -71,6 +75,8 @@ typedef struct {
     int32_t resample;        /* 1: de.sample = resample (crossover.jl:113-124): donors are n distinct
                                 (row, id) cells of de.samples[1:de.iter-1, :, :] (DE-MCz); needs
                                 n_initial > 0 and the caller's prior rows in `samples` */
+    int32_t update;          /* ORC_UPDATE_*: mh_update!, maximize!, minimize! (the optimize path) */
+    int32_t fitness;         /* ORC_FITNESS_*: compute_posterior! or evaluate_fun! (loglike only, no prior) */
     int32_t reserved;
 } orc_config;
 

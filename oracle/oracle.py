@@ -14,7 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5}
+KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6}
+UPDATES = {"mh": 0, "maximize": 1, "minimize": 2}
+FITNESS = {"posterior": 0, "fun": 1}
 PRIORS = {"flat": 0, "normal": 1, "halfcauchy": 2, "uniform": 3, "beta": 4, "normal_ref": 5}
 PROPOSALS = {"random_gamma": 0, "fixed_gamma": 1, "variable_gamma": 2}
 KIND_DE, KIND_SNOOKER, KIND_MUTATION = 0, 1, 2
@@ -40,7 +42,7 @@ class _Config(C.Structure):
                 ("sigma", C.c_double), ("kappa", C.c_double), ("theta_snooker", C.c_double),
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
                 ("base_snapshot", C.c_int32), ("n_threads", C.c_int32), ("seed", C.c_uint64),
-                ("resample", C.c_int32), ("reserved", C.c_int32)]
+                ("resample", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32), ("reserved", C.c_int32)]
 
 
 _TAPE_FIELDS = [("mig_u", "f8"), ("mig_n", "i4"), ("mig_groups", "i4"), ("mig_pick_u", "f8"), ("mig_slots", "i4"),
@@ -129,7 +131,7 @@ class Model:
 class Config:
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None,
-                 base_snapshot=0, n_threads=1, seed=0, resample=False):
+                 base_snapshot=0, n_threads=1, seed=0, resample=False, update="mh", fitness="posterior"):
         self.lo, self.hi = _f8(lo), _f8(hi)
         assert self.lo.shape == (d,) and self.hi.shape == (d,)
         self.blocks = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, d)
@@ -138,7 +140,7 @@ class Config:
             alpha = 0.0  # structs.jl:102-105
         self.c = _Config(n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa, theta_snooker,
                          PROPOSALS[proposal], nb, _ptr(self.blocks, _bp), _ptr(self.lo, _dp), _ptr(self.hi, _dp),
-                         int(base_snapshot), int(n_threads), int(seed), int(bool(resample)), 0)
+                         int(base_snapshot), int(n_threads), int(seed), int(bool(resample)), UPDATES[update], FITNESS[fitness], 0)
         self.resample = bool(resample)
         self.n_groups, self.Np, self.d, self.n_initial = n_groups, Np, d, n_initial
         self.B = max(1, nb)

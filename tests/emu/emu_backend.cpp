@@ -95,7 +95,7 @@ int launch_pack_ssd(const double *x, int, ModelDev *m)
 static int loglik_impl(const ModelDev &m, const double *theta, const Level &lv, double *part)
 {
     ++g_launches;
-    if (m.kind == M_BINOMIAL) return 0;
+    if (m.kind == M_BINOMIAL || m.kind == M_RASTRIGIN) return 0;
     const int n_split = m.n_osplit * m.n_ksplit;
     for (int q = 0; q < lv.n; ++q) {
         const int p = lv.order ? (int)((uint32_t)lv.order[q] & LV_POS_MASK) : q;
@@ -169,11 +169,11 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
         bool inb; double pr;
         bounds_and_prior(co, cfg, m, th, inb, pr);
         double s = 0.0;
-        if (m.kind != M_BINOMIAL) for (int q = 0; q < n_split; ++q) s += part[(size_t)i * n_split + q];
+        if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN) for (int q = 0; q < n_split; ++q) s += part[(size_t)i * n_split + q];
         const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
         if (ll) ll[i] = l;
         if (prior) prior[i] = inb ? pr : -inf();
-        if (w) w[i] = inb ? pr + l : -inf();
+        if (w) w[i] = cfg.fitness == FITNESS_FUN ? (inb ? l : (cfg.update == UPDATE_MAXIMIZE ? -inf() : inf())) : (inb ? pr + l : -inf());
     }
     return 0;
 }

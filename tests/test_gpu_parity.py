@@ -334,3 +334,17 @@ def test_lanes_and_chunks_do_not_change_the_result():
         h.close()
     for o in outs[1:]:
         assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))
+
+
+# ---- the optimize path (optimize.jl; maximize! / minimize! + evaluate_fun!) -------------------------
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
+def test_optimize_updates(mode, model, update):
+    case = make_case(model, np.random.default_rng(51))
+    r, out = forced_run(case, 2, 6, 25, mode, burnin=10, update=update, fitness="fun", alpha=0.3)
+    check(r, out)
+    assert not out["accept"].any() and not out["lp"].any()
+
+
+def test_optimize_api():                            # test/optimization_tests.jl at its own size
+    common.optimize_checks()

@@ -304,3 +304,23 @@ def test_lanes_do_not_change_the_result():
         outs.append((h.samples(), h.accept(), h.lp(), h.get_state()[2]))
         h.close()
     assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+# ---- the optimize path: maximize! / minimize! + evaluate_fun! (optimize.jl, utilities.jl:113-120,212-226) ----
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
+def test_optimize_updates(mode, model, update):
+    case = make_case(model, np.random.default_rng(51))
+    r, out = compare_run(case, 2, 6, 60, mode, burnin=20, update=update, fitness="fun", alpha=0.3)
+    check(r, out)
+    # maximize!/minimize! never write Particle.accept / Particle.lp
+    assert not out["accept"].any() and not out["lp"].any()
+    w = out["state"][1]
+    assert np.all(np.isfinite(w))
+
+
+def test_optimize_api():
+    common.optimize_checks()
+    case = make_case("gaussian", np.random.default_rng(52))
+    with pytest.raises(D._ffi.DemcmcError, match="MethodError"):
+        D.Handle(2, 4, 2, case.lo, case.hi, update="maximize", fitness="fun", theta_snooker=0.1)
