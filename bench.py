@@ -87,6 +87,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram bytes read + written per k_xdot launch from the committed `ncu --set full` capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_k_xdot_traffic.json")))
+        return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -237,7 +246,7 @@ def run_b200(args):
     achieved = flops / (ms_ll * 1e-3) / 1e12 if ms_ll > 0 else None
     roofline = {"bound": "fp64", "kernel": "k_xdot<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
-                "traffic": None,
+                "traffic": ncu_traffic(),
                 "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
                 "avg_launch_ms": ms_ll / max(1, ll_launches), "share_of_step": ms_ll / ms_pass2 if ms_pass2 > 0 else None,
                 "measured_in": "a second pass of the same steps with CUDA events around every k_xdot launch (ms_per_step of that pass: %.4f)" % (ms_pass2 / args.steps),
