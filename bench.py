@@ -49,42 +49,81 @@ def workload(n_groups, seed=50514):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md):
+    NVML polled every 2 ms from a thread of this process (the timed region of a short run is a few
+    tens of milliseconds -- `nvidia-smi -lms 100` would not land one sample in it); nvidia-smi is the
+    fallback when NVML cannot be loaded."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.stop_flag, self.thread, self.src = index, uuid, [], False, None, None
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for u in (f"GPU-{uuid}", str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(ids[index]) if index < len(ids) else index)
+            self.nv, self.h, self.src = pynvml, h, "nvml"
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = self.h = None
+
+    def _poll_nvml(self):
+        nv, h = self.nv, self.h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.max_mhz = float(out[1])
+                self.rows.append((time.time(), float(out[0]), int(out[2].strip(), 16)))
+            except Exception:
+                time.sleep(0.05)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            self.src, self.max_mhz = "nvidia-smi", None
+        self.thread = threading.Thread(target=self._poll_nvml if self.nv is not None else self._poll_smi, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+    def stop(self, windows):
+        """windows: [(t0, t1, label)] of GPU-busy passes of the same workload; the first is the timed region."""
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        t0, t1, _ = windows[0]
+        timed = [r for r in self.rows if t0 <= r[0] <= t1]
+        used, where = timed, "timed region"
+        if not used:                                  # region shorter than one poll: the identical passes that follow it
+            used = [r for r in self.rows if any(a <= r[0] <= b for a, b, _ in windows)]
+            where = "timed region + the identical passes after it"
+        sm = [r[1] for r in used]
+        bits = 0
+        for r in used:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": [n for b, n in self.REASONS if bits & b],
+                "samples": len(sm), "samples_in_timed_region": len(timed), "window": where, "source": self.src}
 
 
 def ncu_traffic():
@@ -133,7 +172,7 @@ def cpu_updates_per_s(steps, warmup, budget_s=100.0):
     t_init = per_update * GROUPS_PER_GPU * np_sample        # initial-weight evaluations are not updates
     ups = n / max(t - t_init, 1e-9)
     sample = (f"{steps} iterations of the same model/data (d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups) with "
-              f"{np_sample} particles per group instead of {NP} ({n} particle updates)")
+              f"{np_sample} particles per group" + ("" if np_sample == NP else f" instead of {NP}") + f" ({n} particle updates)")
     return ups, cores, sample, t / max(1, steps) * 1e3
 
 
@@ -199,7 +238,11 @@ def run_b200(args):
     h.set_timing(L2_FLUSH_BYTES, False)
     h.run(args.warmup)
     c0 = h.counters()
-    clocks = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    clocks = ClockSampler(local, uuid)
     clocks.start()
     barrier()
     t0 = time.time()
@@ -207,15 +250,17 @@ def run_b200(args):
     barrier()
     t1 = time.time()
     c1 = h.counters()
-    ck = clocks.stop(t0, t1)
+    windows = [(t0, t1, "timed")]
     wall_timed = t1 - t0
     # second pass of the same length with every likelihood launch bracketed by CUDA events on the
     # launching stream (this is what the roofline of the dominant kernel is computed from; the
     # events between kernels switch off the programmatic-dependent-launch overlap of the first pass)
     h.set_timing(L2_FLUSH_BYTES, True)
     barrier()
+    tw = time.time()
     h.run(args.steps)
     barrier()
+    windows.append((tw, time.time(), "roofline pass"))
     c2 = h.counters()
     ms = torch.tensor([c1["device_ms"]], dtype=torch.float64, device=f"cuda:{local}")
     ms_ll = torch.tensor([c2["loglike_ms"]], dtype=torch.float64, device=f"cuda:{local}")
@@ -233,9 +278,12 @@ def run_b200(args):
     # steady state without the L2 flush (how a real run behaves: the data set stays in L2)
     h.set_timing(0, False)
     barrier()
+    tw = time.time()
     h.run(args.steps)
     barrier()
+    windows.append((tw, time.time(), "steady pass"))
     ms_steady = h.counters()["device_ms"]
+    ck = clocks.stop(windows)
     h.close()
 
     # ---- roofline of the dominant kernel (k_ssd, the likelihood) ----------------------------------
@@ -244,7 +292,7 @@ def run_b200(args):
     fp64_peak = max(dfma_peak, dmma_peak)
     flops = 2.0 * N_OBS * N_DIM * (updates / world)                  # contraction form: one DFMA per (obs, dim, particle)
     achieved = flops / (ms_ll * 1e-3) / 1e12 if ms_ll > 0 else None
-    roofline = {"bound": "fp64", "kernel": "k_xdot<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "pipe": "fp64 tensor path (DMMA m8n8k4)", "kernel": "k_xdot<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
                 "traffic": ncu_traffic(),
                 "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
@@ -252,7 +300,7 @@ def run_b200(args):
                 "measured_in": "a second pass of the same steps with CUDA events around every k_xdot launch (ms_per_step of that pass: %.4f)" % (ms_pass2 / args.steps),
                 "peak_source": "measured in this run (MEASURED_PEAKS.json has no fp64 entry): the larger of a DFMA loop and a DMMA m8n8k4 loop, 8 warps x 8 CTAs/SM; the two fp64 paths share one pipe on B200",
                 "peak_dfma": dfma_peak, "peak_dmma": dmma_peak,
-                "note": "bound = fp64 pipe (the contract's enum offers hbm/tensor; this is the fp64 tensor path, DMMA m8n8k4): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work",
+                "note": "bound = the fp64 tensor path (DMMA m8n8k4; peak = this run's fp64 microbenchmarks, not the bf16 figure of MEASURED_PEAKS.json): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work",
                 "hbm_gbs_measured": peaks.get("hbm_gbs")}
 
     # ---- end to end through the public API with HOST buffers -------------------------------------
@@ -276,6 +324,16 @@ def run_b200(args):
             e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "call": "sample(model, de, n_iter) with host (pageable numpy) data: handle creation, data upload + packing, P sample_prior() calls, all iterations, device-side bundle_samples and the download of the chains",
                    "seconds": t_e2e}
+            # ESS/s (the second half of BASELINE.json's metric): min over parameters of the bulk ESS of the
+            # second half of that same run (all chains pooled) / the wall time of the whole call
+            if args.steps >= 100 and not args.no_ess:
+                from demcmc_b200.diagnostics import bulk_ess
+                half = chains.value[args.steps // 2:, :d, :]
+                ess = [bulk_ess(half[:, k, :]) for k in range(d)]
+                e2e["ess"] = {"min_bulk_ess": float(np.nanmin(ess)), "median_bulk_ess": float(np.nanmedian(ess)),
+                              "ess_per_s": float(np.nanmin(ess)) / t_e2e, "draws": int(half.shape[0]), "chains": int(half.shape[2]),
+                              "note": "started from prior draws with burnin=0; draws of the second half of the run, "
+                                      "rank-normalised split bulk ESS (Vehtari et al. 2021), min over the 51 parameters"}
     if world > 1:
         # sharded e2e: every rank builds its handle from host buffers, runs, and downloads its by-slot history
         barrier()
@@ -322,10 +380,11 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s estimate of the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

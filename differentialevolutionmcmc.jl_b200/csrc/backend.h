@@ -63,6 +63,12 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // has cleared it and set ll_q); the other models write ll_part
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc);
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
+// all levels of a chunk in ONE persistent, warp-specialised launch (MVN / hierarchical): level l
+// holds the entries d_order[level_off[l] .. + level_n[l]); its proposals wait for the accepts of
+// level dep[l] (< l, or -1); the scalar warps run their accepts `lag` levels behind their proposals.
+// Returns 1 when the chunk does not fit that kernel (launch it level by level instead), -1 on error.
+int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
+                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc);
 // migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
 // [position][d+3] = {theta..., weight, id, accept flag}
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);

@@ -581,7 +581,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // Lanes: the groups split into independent sets (groups never read each other between
         // migrations), each planned on its own and launched as its own kernel chain on its own
         // stream, so one lane's likelihood kernel runs while the other lane proposes / accepts.
-        const int n_lanes = (h->n_lanes > 1 && G >= 2 && !h->time_loglik) ? 2 : 1;
+        const int n_lanes = (h->n_lanes > 1 && G >= 2) ? 2 : 1;
         int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
         std::vector<uint8_t> mut((size_t)n_sw * G, 0);
         for (int ln = 0; ln < n_lanes; ++ln) {
@@ -612,9 +612,35 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             for (int g = 0; g < G; ++g) any_cross |= mut[g] == 0;
             if (any_cross) BE(be::launch_base_prep(h->dcfg, u.h_ctx[0].cur_w, h->base_th, h->base_cw, h->base_tot));
         }
-        BE(be::lane_fork(n_lanes));
         int max_levels = 0;
         for (int ln = 0; ln < n_lanes; ++ln) max_levels = std::max(max_levels, plans[ln].n_levels);
+        // ---- the persistent path: the whole chunk in one launch (MVN / hierarchical) ---------------
+        // levels of the lanes alternate; a level's proposals wait for the previous level of its lane
+        {
+            std::vector<int32_t> off, cnt, dep;
+            int last[be::MAX_LANES] = { -1, -1 };
+            for (int l = 0; l < max_levels; ++l)
+                for (int ln = 0; ln < n_lanes; ++ln) {
+                    const ChunkPlan &pl = plans[ln];
+                    if (l >= pl.n_levels || pl.level_off[l + 1] == pl.level_off[l]) continue;
+                    off.push_back(lane_off[ln] + pl.level_off[l]);
+                    cnt.push_back(pl.level_off[l + 1] - pl.level_off[l]);
+                    dep.push_back(last[ln]);
+                    last[ln] = (int)off.size() - 1;
+                }
+            const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+            if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
+            const int rc = off.empty() ? 1 : be::launch_chunk_persist(h->dcfg, h->dmodel, u.d_order, u.d_ctx, off.data(), cnt.data(), dep.data(),
+                                                                      (int)off.size(), n_lanes > 1 ? 1 : 0, h->ll_acc);
+            if (rc < 0) return fail(DEMCMC_ECUDA, "chunk launch: %s", be::last_error());
+            if (rc == 0) {
+                if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
+                n_levels += (int64_t)off.size();
+                ++h->ctr.persistent_chunks;
+                return 0;
+            }
+        }
+        BE(be::lane_fork(n_lanes));
         int rc_launch = 0;
         for (int l = 0; l < max_levels && !rc_launch; ++l)
             for (int ln = 0; ln < n_lanes && !rc_launch; ++ln) {

@@ -128,6 +128,7 @@ typedef struct {
     int64_t iterations, sweeps, particle_updates, loglike_evals, kernel_launches, levels;
     double device_ms;        /* CUDA-event time of the last run/replay call */
     double loglike_ms;       /* of which: likelihood kernels (0 unless timing was requested) */
+    int64_t persistent_chunks; /* chunks (<= 16 overlapped sweeps) that ran as ONE persistent launch */
 } demcmc_counters;
 
 typedef struct demcmc_handle demcmc_handle;

@@ -215,6 +215,10 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
     return 0;
 }
 
+// the persistent chunk kernel exists on the device only: the engine falls back to level-by-level launches
+int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
+                         const int32_t *, int, int, long long *) { return 1; }
+
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     ++g_launches;
