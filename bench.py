@@ -272,7 +272,9 @@ def run_b200(args):
     ms, ms_ll, ms_pass2 = float(ms.item()), float(ms_ll.item()), float(ms_pass2.item())
     updates = (c1["particle_updates"] - c0["particle_updates"]) * world
     launches = c1["kernel_launches"] - c0["kernel_launches"]
-    ll_launches = c2["levels"] - c1["levels"]
+    persistent = (c2["persistent_chunks"] - c1["persistent_chunks"]) > 0
+    ll_launches = (c2["persistent_chunks"] - c1["persistent_chunks"]) if persistent else (c2["levels"] - c1["levels"])
+    ll_levels = c2["levels"] - c1["levels"]
     value = updates / (ms * 1e-3)
 
     # steady state without the L2 flush (how a real run behaves: the data set stays in L2)
@@ -292,15 +294,21 @@ def run_b200(args):
     fp64_peak = max(dfma_peak, dmma_peak)
     flops = 2.0 * N_OBS * N_DIM * (updates / world)                  # contraction form: one DFMA per (obs, dim, particle)
     achieved = flops / (ms_ll * 1e-3) / 1e12 if ms_ll > 0 else None
-    roofline = {"bound": "tensor", "pipe": "fp64 tensor path (DMMA m8n8k4)", "kernel": "k_xdot<MVN>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    kname = ("k_chunk_persist (persistent, warp-specialised: DMMA likelihood + proposals + accepts of all levels of a chunk of <= 16 steps)"
+             if persistent else "k_xdot<MVN>")
+    measured_in = (("a second pass of the same steps with CUDA events around every k_chunk_persist launch (one launch per chunk; "
+                    "%d dependency levels in %d launches; ms_per_step of that pass: %.4f)" % (ll_levels, ll_launches, ms_pass2 / args.steps))
+                   if persistent else
+                   "a second pass of the same steps with CUDA events around every k_xdot launch (ms_per_step of that pass: %.4f)" % (ms_pass2 / args.steps))
+    roofline = {"bound": "tensor", "pipe": "fp64 tensor path (DMMA m8n8k4)", "kernel": kname, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
                 "traffic": ncu_traffic(),
                 "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
                 "avg_launch_ms": ms_ll / max(1, ll_launches), "share_of_step": ms_ll / ms_pass2 if ms_pass2 > 0 else None,
-                "measured_in": "a second pass of the same steps with CUDA events around every k_xdot launch (ms_per_step of that pass: %.4f)" % (ms_pass2 / args.steps),
+                "measured_in": measured_in,
                 "peak_source": "measured in this run (MEASURED_PEAKS.json has no fp64 entry): the larger of a DFMA loop and a DMMA m8n8k4 loop, 8 warps x 8 CTAs/SM; the two fp64 paths share one pipe on B200",
                 "peak_dfma": dfma_peak, "peak_dmma": dmma_peak,
-                "note": "bound = the fp64 tensor path (DMMA m8n8k4; peak = this run's fp64 microbenchmarks, not the bf16 figure of MEASURED_PEAKS.json): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work",
+                "note": "bound = the fp64 tensor path (DMMA m8n8k4; peak = this run's fp64 microbenchmarks, not the bf16 figure of MEASURED_PEAKS.json): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work; for the persistent kernel the duration includes the proposals and accepts it runs (6 of the 148 SMs do only those)",
                 "hbm_gbs_measured": peaks.get("hbm_gbs")}
 
     # ---- end to end through the public API with HOST buffers -------------------------------------

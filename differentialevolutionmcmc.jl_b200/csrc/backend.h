@@ -67,6 +67,7 @@ int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // holds the entries d_order[level_off[l] .. + level_n[l]); its proposals wait for the accepts of
 // level dep[l] (< l, or -1); the scalar warps run their accepts `lag` levels behind their proposals.
 // Returns 1 when the chunk does not fit that kernel (launch it level by level instead), -1 on error.
+int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m);   // lanes that kernel wants for this job; 0 = use the level-by-level path
 int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
                          const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc);
 // migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out

@@ -338,6 +338,7 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         D.n_ksplit = (D.ssd_k + SSD_KS - 1) / SSD_KS;
         D.ksplit_len = (D.ssd_k + D.n_ksplit - 1) / D.n_ksplit;
         D.ssd_nj = (D.ksplit_len + 3) / 4;
+        { const char *e = getenv("DEMCMC_NO_HALF_STEP"); D.ssd_half = (D.ksplit_len % 4 == 2 && !(e && e[0] == '1')) ? 1 : 0; }
         D.n_osplit = 1; D.split_len = (int32_t)std::min<int64_t>(D.ssd_ld, INT32_MAX);
         // fixed-point bits below the per-particle bound: the sum of one rounded term per
         // (observation row, dimension split) must stay below 2^62
@@ -581,7 +582,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // Lanes: the groups split into independent sets (groups never read each other between
         // migrations), each planned on its own and launched as its own kernel chain on its own
         // stream, so one lane's likelihood kernel runs while the other lane proposes / accepts.
-        const int n_lanes = (h->n_lanes > 1 && G >= 2) ? 2 : 1;
+        // the persistent chunk kernel alternates the levels of two lanes; the level-by-level path
+        // runs the handle's lanes (default 1) as concurrent kernel chains
+        const int persist_lanes = be::chunk_persist_lanes(h->dcfg, h->dmodel);
+        const int n_lanes = persist_lanes ? persist_lanes : ((h->n_lanes > 1 && G >= 2) ? 2 : 1);
         int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
         std::vector<uint8_t> mut((size_t)n_sw * G, 0);
         for (int ln = 0; ln < n_lanes; ++ln) {
@@ -616,7 +620,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         for (int ln = 0; ln < n_lanes; ++ln) max_levels = std::max(max_levels, plans[ln].n_levels);
         // ---- the persistent path: the whole chunk in one launch (MVN / hierarchical) ---------------
         // levels of the lanes alternate; a level's proposals wait for the previous level of its lane
-        {
+        if (persist_lanes) {
             std::vector<int32_t> off, cnt, dep;
             int last[be::MAX_LANES] = { -1, -1 };
             for (int l = 0; l < max_levels; ++l)

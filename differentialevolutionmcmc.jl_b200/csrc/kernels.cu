@@ -390,6 +390,13 @@ __device__ __forceinline__ size_t bfrag_index(const ModelDev &m, int64_t wi, int
     const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
     return (((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32 + n * 4 + (kl & 3);
 }
+// a half step's B fragment repeats its two means in rows 2-3 (de_types.h: ssd_half)
+__device__ __forceinline__ void bfrag_store(const ModelDev &m, double *bfrag, int64_t wi, int k, double v)
+{
+    const size_t i = bfrag_index(m, wi, k);
+    bfrag[i] = v;
+    if (m.ssd_half && (k % m.ksplit_len) >= 4 * (m.ssd_nj - 1)) bfrag[i + 2] = v;
+}
 __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
                                             long long *acc, double *q, double *msq_out)
 {
@@ -398,7 +405,7 @@ __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *the
     for (int k = lane; k < m.ssd_k; k += 32) {
         const double v = centred_mean(m, theta, k);
         msq += v * v;
-        bfrag[bfrag_index(m, wi, k)] = v;
+        bfrag_store(m, bfrag, wi, k, v);
     }
     stage_scale(m, warp_sum(msq), wi, magic, acc, q, msq_out);
 }
@@ -418,7 +425,7 @@ struct StageSink {
         if (!on || k >= m.ssd_k) return;
         const double c = v - (q < PROP_PRE ? cen[q] : m.center[k]);
         msq += c * c;
-        bfrag[bfrag_index(m, wi, k)] = c;
+        bfrag_store(m, bfrag, wi, k, c);
     }
 };
 
@@ -679,13 +686,15 @@ struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 // item to the next without re-initialising anything).
 struct XdWarp { int warp, ks; double *ring; uint64_t *full; uint32_t it_base; };
 
-template <int NOCT, int NJC, class WAIT>   // NJC: the model's k-steps when known at compile time (13), else 0
+template <int NOCT, int NJC, bool HALF, class WAIT>   // NJC: the model's k-steps when known at compile time (13), else 0;
+                                                      // HALF: (with NJC) the last k-step is a half step (de_types.h: ssd_half)
 __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
                                           long long *ll_acc, int oct0, int T0, int T1, XdWarp &xw, const WAIT &dependency_wait,
                                           unsigned long long *tl, unsigned long long *tlc)
 {
     const int tid = threadIdx.x, warp = xw.warp, lane = tid & 31, ks = xw.ks;
     const int nj = NJC ? NJC : m.ssd_nj;
+    const bool half = NJC ? HALF : (m.ssd_half != 0);
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const uint32_t stage_doubles = (uint32_t)nj * 64, stage_bytes = stage_doubles * (uint32_t)sizeof(double);
     double *ring = xw.ring;
@@ -758,8 +767,10 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             if (j + 1 < nj) an = xa[(j + 1) * 32];
 #pragma unroll
             for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.x, b[j][pt]);
+            if (!(half && j == nj - 1)) {
 #pragma unroll
-            for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
+                for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
+            }
             a = an;
             if (j == 0 && have_prev) convert(prev);
         }
@@ -830,11 +841,13 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const PdlWait wait;
-#define XD_CALL(NO, NJC) xdot_body<NO, NJC>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
-    if (m.ssd_nj == SSD_NJ) {
-        switch (noct) { case 4: XD_CALL(4, SSD_NJ); break; case 3: XD_CALL(3, SSD_NJ); break; case 2: XD_CALL(2, SSD_NJ); break; default: XD_CALL(1, SSD_NJ); break; }
+#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
+    if (m.ssd_nj == SSD_NJ && m.ssd_half) {
+        switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
+    } else if (m.ssd_nj == SSD_NJ) {
+        switch (noct) { case 4: XD_CALL(4, SSD_NJ, false); break; case 3: XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
     } else {
-        switch (noct) { case 4: XD_CALL(4, 0); break; case 3: XD_CALL(3, 0); break; case 2: XD_CALL(2, 0); break; default: XD_CALL(1, 0); break; }
+        switch (noct) { case 4: XD_CALL(4, 0, false); break; case 3: XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
     }
 #undef XD_CALL
 }
@@ -995,27 +1008,23 @@ struct FlagWait {
 // per level: stamps (min stored complemented) and, summed over the DMMA warps, the nanoseconds spent
 // waiting for the proposals, in the item (B fragments, DMMA loop, flush) and in the arrive
 enum { PT_P0 = 0, PT_PW, PT_P1, PT_XW0, PT_XW1, PT_X1, PT_AW0, PT_A1, PT_SUM_WAIT, PT_SUM_ITEM, PT_SUM_ARRIVE, PT_ITEMS, PT_WORDS = 16 };
-// DMMA warps: the arrive of the PREVIOUS item (a fence that waits for its atomics, then the counter)
-// is deferred until this item's B fragments have been requested, so the fence overlaps the load
-// latency -- unless this item's proposals are not staged yet: then it goes out before the wait
-// (an accept somewhere may be waiting for it; nothing may wait behind a flag with a signal pending)
+// DMMA warps.  (Deferring the arrive of the previous item behind this item's B-fragment loads was
+// tried: carrying the pending counter across items makes ptxas drop the raised register budget of
+// the setmaxnreg region -- 125 registers and B fragments reloaded from local memory inside the
+// DMMA loop.  scripts/regcheck.sh prints the highest register the kernel uses; keep it near 230.)
 template <bool TL>
 struct DmmaWait {
     const int32_t *c0; int t0;
-    mutable int32_t *pending;
     unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
     __device__ __forceinline__ void operator()() const
     {
-        if (ld_acquire(c0) < t0) {
-            if (pending) { arrive(pending); pending = nullptr; }
-            wait_ge(c0, t0);
-        }
+        wait_ge(c0, t0);
         if (TL && tl) {
             t_done = gtime();
             if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
         }
     }
-    __device__ __forceinline__ void after_loads() const { if (pending) { arrive(pending); pending = nullptr; } }
+    __device__ __forceinline__ void after_loads() const {}
 };
 struct FlagLanes : WarpLanes {
     FlagWait w;
@@ -1064,7 +1073,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
         }
         __syncwarp();
         const int n_tiles = (int)(m.ssd_ld / SSD_TN);
-        int32_t *pending = nullptr;                          // xdot_done counter of the item just finished
         for (int L = 0; L < ck.n_levels; ++L) {
             const PLevel &pl = ck.lv[L];
             const XdGrid g = pl.g;
@@ -1079,30 +1087,30 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
                 const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
                 const int n_in_tile = min(pl.n, (oct0 + noct) * SSD_OCT) - oct0 * SSD_OCT;
                 unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-                const DmmaWait<TL> wait = { ck.prop_done + pl.tile_base + tile, n_in_tile, pending, tl, 0ull };
+                const DmmaWait<TL> wait = { ck.prop_done + pl.tile_base + tile, n_in_tile, tl, 0ull };
                 const unsigned long long t_a = (TL && tl) ? gtime() : 0ull;
                 xw.ks = ks;
                 if (T1 > T0) {
                     const double *bf = ck.bfrag[L & 1], *mgc = ck.magic[L & 1];
-#define PK_CALL(NO, NJC) xdot_body<NO, NJC>(m, bf, mgc, lv, ck.ll_acc, oct0, T0, T1, xw, wait, nullptr, nullptr)
-                    if (m.ssd_nj == SSD_NJ) {
-                        switch (noct) { case 4: PK_CALL(4, SSD_NJ); break; case 3: PK_CALL(3, SSD_NJ); break; case 2: PK_CALL(2, SSD_NJ); break; default: PK_CALL(1, SSD_NJ); break; }
+#define PK_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF>(m, bf, mgc, lv, ck.ll_acc, oct0, T0, T1, xw, wait, nullptr, nullptr)
+                    if (m.ssd_nj == SSD_NJ && m.ssd_half) {
+                        switch (noct) { case 4: PK_CALL(4, SSD_NJ, true); break; case 3: PK_CALL(3, SSD_NJ, true); break; case 2: PK_CALL(2, SSD_NJ, true); break; default: PK_CALL(1, SSD_NJ, true); break; }
+                    } else if (m.ssd_nj == SSD_NJ) {
+                        switch (noct) { case 4: PK_CALL(4, SSD_NJ, false); break; case 3: PK_CALL(3, SSD_NJ, false); break; case 2: PK_CALL(2, SSD_NJ, false); break; default: PK_CALL(1, SSD_NJ, false); break; }
                     } else {
-                        switch (noct) { case 4: PK_CALL(4, 0); break; case 3: PK_CALL(3, 0); break; case 2: PK_CALL(2, 0); break; default: PK_CALL(1, 0); break; }
+                        switch (noct) { case 4: PK_CALL(4, 0, false); break; case 3: PK_CALL(3, 0, false); break; case 2: PK_CALL(2, 0, false); break; default: PK_CALL(1, 0, false); break; }
                     }
 #undef PK_CALL
                 }
-                if (T1 <= T0 && pending) arrive(pending);        // (an item that ran has sent it: after_loads)
-                pending = ck.xdot_done + pl.tile_base + tile;
+                const unsigned long long t_b = (TL && tl) ? gtime() : 0ull;
+                arrive(ck.xdot_done + pl.tile_base + tile);
                 if (TL && tl && lane == 0 && T1 > T0) {
-                    const unsigned long long t_b = gtime();
                     atomicMax(tl + PT_X1, t_b);
                     atomicAdd(tl + PT_SUM_WAIT, wait.t_done - t_a); atomicAdd(tl + PT_SUM_ITEM, t_b - wait.t_done);
                     atomicAdd(tl + PT_ITEMS, 1ull);
                 }
             }
         }
-        if (pending) arrive(pending);
         return;
     }
     // ---- scalar warps ---------------------------------------------------------------------------
@@ -1187,6 +1195,30 @@ static void pk_timeline_dump()
     fclose(f);
 }
 
+static int persist_enabled()
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("DEMCMC_PERSIST"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    return enabled;
+}
+static int persist_scalar_ctas()
+{
+    static int n_scalar = -1;
+    if (n_scalar < 0) { const char *e = getenv("DEMCMC_PK_SCALAR_CTAS"); n_scalar = e ? std::max(1, std::min(atoi(e), 64)) : PK_SCALAR_CTAS; }
+    return n_scalar;
+}
+// How many lanes (independent sets of groups with alternating levels) the persistent kernel wants
+// for this job, or 0 when the job is better served level by level: other models, a single group
+// (nothing to alternate with: the scalar part of every level would sit on the critical path with
+// fewer warps than k_propose has), or levels far larger than the scalar warps.
+int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m)
+{
+    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER)) return 0;
+    if (cfg.G_local < 2) return 0;
+    if ((int64_t)cfg.G_local * cfg.Np / 8 > (int64_t)4 * PK_WARPS * persist_scalar_ctas()) return 0;   // ~ a level per lane
+    return 2;
+}
+
 // Runs the levels [level_off[l], level_off[l] + level_n[l]) of a chunk (entries in d_order) in one persistent
 // launch.  dep[l] = the level whose accepts the proposals of level l wait for (-1: none), lag = how
 // many levels the accepts trail the proposals in the scalar warps' program (0 or 1).
@@ -1194,12 +1226,9 @@ static void pk_timeline_dump()
 int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
                          const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc)
 {
-    static int enabled = -1;
-    if (enabled < 0) { const char *e = getenv("DEMCMC_PERSIST"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    if (!enabled || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
+    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
     static PChunk ck;                                        // 9 KB: not on the stack of every call
-    static int n_scalar = -1;
-    if (n_scalar < 0) { const char *e = getenv("DEMCMC_PK_SCALAR_CTAS"); n_scalar = e ? std::max(1, std::min(atoi(e), 64)) : PK_SCALAR_CTAS; }
+    const int n_scalar = persist_scalar_ctas();
     const int sms = n_sms(), slots = XD_CTAS_PER_SM * (sms - n_scalar);
     int tiles = 0, n_max = 0;
     for (int l = 0; l < n_levels; ++l) {
@@ -1303,7 +1332,7 @@ __global__ void __launch_bounds__(256) k_col_center(const double *x, double *cen
 // one thread per observation: writes its centred row into the packed layout; per block the sum and
 // the maximum of the squared row norms
 __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double *center, double *xp, double *blk_sq, double *blk_max,
-                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major)
+                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major, int half)
 {
     __shared__ double red[9];
     __shared__ double redm[8];
@@ -1313,7 +1342,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double
         for (int kk = 0; kk < k; ++kk) {
             const double v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - center[kk];
             q += v * v;
-            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles)] = v;
+            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles, half)] = v;
         }
     double mx = q;
 #pragma unroll
@@ -1349,7 +1378,7 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
     if (e == cudaSuccess) {
         k_col_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->center), m->ssd_n, m->ssd_k, obs_major);
         k_pack_rows<<<n_blk, 256, 0, stream()>>>(src, m->center, const_cast<double *>(m->xT), blk, blk + n_blk, m->ssd_n, m->ssd_k,
-                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major);
+                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major, m->ssd_half);
         g_launches += 2;
         e = cudaGetLastError();
     }

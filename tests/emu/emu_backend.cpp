@@ -216,6 +216,7 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 }
 
 // the persistent chunk kernel exists on the device only: the engine falls back to level-by-level launches
+int chunk_persist_lanes(const ConfigDev &, const ModelDev &) { return 0; }
 int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
                          const int32_t *, int, int, long long *) { return 1; }
 
