@@ -686,10 +686,15 @@ struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 // item to the next without re-initialising anything).
 struct XdWarp { int warp, ks; double *ring; uint64_t *full; uint32_t it_base; };
 
-template <int NOCT, int NJC, bool HALF, class WAIT>   // NJC: the model's k-steps when known at compile time (13), else 0;
-                                                      // HALF: (with NJC) the last k-step is a half step (de_types.h: ssd_half)
-__device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
-                                          long long *ll_acc, int oct0, int T0, int T1, XdWarp &xw, const WAIT &dependency_wait,
+// NJC: the model's k-steps when known at compile time (13), else 0; HALF: (with NJC) the last k-step is
+// a half step (de_types.h: ssd_half); STAGES: depth of the warp's operand ring.
+// bsrc / b_oct_stride: the tile's B fragments [octet][k-step][lane] (global staging buffer, or the
+// shared-memory copy the persistent kernel's helper warp made); msrc: its 8 magic constants per octet.
+// HOOKS: operator()() = wait until the means may be read; after_loads() = they are in registers;
+// item_end() = the tile's cross terms have been added to ll_acc.
+template <int NOCT, int NJC, bool HALF, int STAGES, class HOOKS>
+__device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc, size_t b_oct_stride, const double *msrc, const Level &lv,
+                                          long long *ll_acc, int oct0, int T0, int T1, XdWarp &xw, const HOOKS &dependency_wait,
                                           unsigned long long *tl, unsigned long long *tlc)
 {
     const int tid = threadIdx.x, warp = xw.warp, lane = tid & 31, ks = xw.ks;
@@ -704,9 +709,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < XD_STAGES; ++s)
+        for (int s = 0; s < STAGES; ++s)
             if (T0 + s < T1) {
-                const uint32_t st = (it_base + (uint32_t)s) & (XD_STAGES - 1);
+                const uint32_t st = (it_base + (uint32_t)s) % STAGES;
                 mbar_expect_tx(&full[st], stage_bytes);
                 bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)s * stage_doubles, stage_bytes, &full[st]);
             }
@@ -721,9 +726,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     {
 #pragma unroll
         for (int pt = 0; pt < NOCT; ++pt) {
-            const double *bf = bfrag + (((size_t)(oct0 + pt) * m.n_ksplit + ks) * nj) * 32 + lane;
+            const double *bf = bsrc + (size_t)pt * b_oct_stride + lane;
 #pragma unroll
-            for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? __ldcg(bf + j * 32) : 0.0;
+            for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? bf[j * 32] : 0.0;
         }
     }
     double mg[NOCT][2];
@@ -737,7 +742,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            mg[pt][e] = __ldcg(magic + (size_t)(oct0 + pt) * SSD_OCT + 2 * (lane & 3) + e);
+            mg[pt][e] = msrc[pt * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
             accA[pt][e] = 0.0; accB[pt][e] = 0.0;
         }
@@ -755,8 +760,8 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
     // first k-step when it holds the previous tile
     auto tile = [&](int t, double (&acc)[NOCT][2], double (&prev)[NOCT][2], bool have_prev) {
         const int it = t - T0;
-        const uint32_t gi = it_base + (uint32_t)it, st = gi & (XD_STAGES - 1);
-        mbar_wait(&full[st], (gi / XD_STAGES) & 1u);
+        const uint32_t gi = it_base + (uint32_t)it, st = gi % STAGES;
+        mbar_wait(&full[st], (gi / STAGES) & 1u);
         if (tl && tid == 0 && t == T0) tl_max(tl, TL_XFIRST);
         const double2 *xa = reinterpret_cast<const double2 *>(ring + (size_t)st * stage_doubles) + lane;
         double2 a = xa[0];
@@ -775,9 +780,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
             if (j == 0 && have_prev) convert(prev);
         }
         __syncwarp();                                        // every lane's reads of the stage have landed
-        if (lane == 0 && t + XD_STAGES < T1) {
+        if (lane == 0 && t + STAGES < T1) {
             mbar_expect_tx(&full[st], stage_bytes);
-            bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + XD_STAGES) * stage_doubles, stage_bytes, &full[st]);
+            bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + STAGES) * stage_doubles, stage_bytes, &full[st]);
         }
     };
     int t = T0;
@@ -807,6 +812,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
                 atomicAdd(reinterpret_cast<unsigned long long *>(ll_acc) + p, v);
             }
         }
+    dependency_wait.item_end();
     if (tid == 0) tl_max(tl, TL_X1);
     xw.it_base = it_base + (uint32_t)(T1 - T0);
 }
@@ -814,6 +820,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag
 struct PdlWait {
     __device__ __forceinline__ void operator()() const { pdl_wait(); }
     __device__ __forceinline__ void after_loads() const {}
+    __device__ __forceinline__ void item_end() const {}
 };
 
 __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
@@ -841,7 +848,9 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const PdlWait wait;
-#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
+    const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + blockIdx.y) * m.ssd_nj) * 32, *msrc = magic + (size_t)oct0 * SSD_OCT;
+    const size_t bstride = (size_t)m.n_ksplit * m.ssd_nj * 32;
+#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
     if (m.ssd_nj == SSD_NJ && m.ssd_half) {
         switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
     } else if (m.ssd_nj == SSD_NJ) {
@@ -942,7 +951,7 @@ constexpr int PK_MAX_LEVELS = 192;
 constexpr int PK_MAX_TILES = 8192;
 constexpr int PK_WARPS = 16;                    // per CTA: 4 per SM sub-partition, 128 registers each at launch
 constexpr int PK_THREADS = PK_WARPS * 32;
-constexpr int PK_REGS_DMMA = 232, PK_REGS_IDLE = 24;     // per sub-partition 2 * 232 + 2 * 24 = 512 = 4 * 128, the launch allocation
+constexpr int PK_REGS_DMMA = 216, PK_REGS_HELPER = 56, PK_REGS_IDLE = 24;   // per sub-partition 2 * 216 + 56 + 24 = 512 = 4 * 128, the launch allocation
 constexpr int PK_SCALAR_CTAS = 6;               // CTAs (SMs) given to the scalar warps: 96 warps, one update each per level of ~100
 
 struct PLevel { int32_t order_off, n, n_items, dep, tile_base, pad; XdGrid g; };
@@ -1040,6 +1049,54 @@ struct ProposeLanes : WarpLanes {
     __device__ __forceinline__ void dependency_wait() const { pending(); w(); }
 };
 
+// one item of a level: (dimension split, particle tile, observation-tile range), as k_xdot's grid deals them
+struct PkItem { int ks, tile, oct0, noct, T0, T1, n_in_tile; };
+__device__ __forceinline__ PkItem pk_item(const PLevel &pl, int n_tiles, int q)
+{
+    PkItem it;
+    const XdGrid &g = pl.g;
+    it.ks = q / pl.n_items;
+    const int bx = q - it.ks * pl.n_items;
+    int c_in, C;
+    const int n_in_hi = g.n_hi * g.c_hi;
+    if (bx < n_in_hi) { it.tile = bx / g.c_hi; c_in = bx - it.tile * g.c_hi; C = g.c_hi; it.noct = g.oct_hi; it.oct0 = it.tile * g.oct_hi; }
+    else { const int r = bx - n_in_hi, t = r / g.c_lo; it.tile = g.n_hi + t; c_in = r - t * g.c_lo; C = g.c_lo; it.noct = g.oct_lo; it.oct0 = g.n_hi * g.oct_hi + t * g.oct_lo; }
+    it.T0 = (int)((int64_t)c_in * n_tiles / C); it.T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
+    it.n_in_tile = min(pl.n, (it.oct0 + it.noct) * SSD_OCT) - it.oct0 * SSD_OCT;
+    return it;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// what the DMMA warps of a virtual CTA see of an item: the helper warp's shared-memory copy of the
+// tile's B fragments (b_full), and the two signals back to it (b_empty: the copy is in registers;
+// item_done: the cross terms are in ll_acc)
+template <bool TL>
+struct VctaHooks {
+    uint64_t *b_full, *b_empty, *item_done;
+    uint32_t parity;
+    unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
+    __device__ __forceinline__ void operator()() const
+    {
+        mbar_wait(b_full, parity);
+        if (TL && tl) {
+            t_done = gtime();
+            if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
+        }
+    }
+    __device__ __forceinline__ void after_loads() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }
+    __device__ __forceinline__ void item_end() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(item_done); }
+};
+
+constexpr int PK_STAGES = 3;                    // ring depth of the persistent kernel (the fourth stage's memory holds the B copies)
+static size_t pk_bbuf_doubles(int nj) { return (size_t)4 * nj * 32 + 4 * SSD_OCT; }
+static size_t pk_smem_bytes(int nj)
+{
+    return sizeof(double) * ((size_t)8 * PK_STAGES * nj * 64 + 2 * pk_bbuf_doubles(nj)) + sizeof(uint64_t) * (8 * PK_STAGES + 6);
+}
+
 template <bool TL>
 __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_constant__ ConfigDev cfg, const __grid_constant__ ModelDev m,
                                                                  const __grid_constant__ PChunk ck)
@@ -1049,64 +1106,121 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
     // Roles.  The scalar part of the step (Philox, pow/log/exp, priors) runs on the same fp64 pipe as
     // DMMA: next to two DMMA warps a scalar warp's dependent fp64 chain takes 3-4x as long (measured:
     // 26 us instead of 8 per proposal).  So the last n_scalar_ctas CTAs are scalar-only (16 warps at
-    // the launch's 128 registers), and in the DMMA CTAs warps 8-15 hand their registers to warps 0-7
-    // (setmaxnreg: 232 each) and leave.
+    // the launch's 128 registers).  In the DMMA CTAs warps 0-7 are the two virtual CTAs (setmaxnreg:
+    // 216 registers each), warps 8 and 9 are their HELPERS (56 registers): a helper polls the
+    // proposal counter of its virtual CTA's next item, copies that tile's B fragments and magic
+    // constants into shared memory while the DMMA warps are still in the previous item, and
+    // publishes a finished item (fence + xdot_done) on their behalf -- so the DMMA warps never touch
+    // a global flag, never wait on an L2 round trip for their operands and never stall in a fence.
+    // Warps 10-15 give their registers back and leave.
     const int n_dmma_ctas = (int)gridDim.x - ck.n_scalar_ctas;
     const bool scalar_cta = (int)blockIdx.x >= n_dmma_ctas;
+    const int nj = m.ssd_nj;
+    const uint32_t stage_doubles = (uint32_t)nj * 64;
+    double *const ring0 = reinterpret_cast<double *>(smem_raw);
+    double *const bbuf0 = ring0 + (size_t)8 * PK_STAGES * stage_doubles;
+    const size_t bbuf_doubles = (size_t)4 * nj * 32 + 4 * SSD_OCT;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(bbuf0 + 2 * bbuf_doubles);     // full[8][PK_STAGES], then per virtual CTA b_full, b_empty, item_done
+    uint64_t *const vbars = bars + 8 * PK_STAGES;
+    if (!scalar_cta) {
+        if (threadIdx.x == 0) {
+            for (int vc = 0; vc < 2; ++vc) { mbar_init(&vbars[vc * 3 + 0], 1); mbar_init(&vbars[vc * 3 + 1], 4); mbar_init(&vbars[vc * 3 + 2], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();                                         // the only CTA-wide barrier: before any warp leaves
+    }
+    const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     if (!scalar_cta && warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_IDLE));
+        if (warp >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_IDLE)); return; }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_HELPER));
+        if (warp >= 10) return;
+        // ---- helper warp of virtual CTA vc ----------------------------------------------------------
+        const int vc = warp - 8, v = blockIdx.x * 2 + vc, NV = n_dmma_ctas * 2;
+        double *const bbuf = bbuf0 + (size_t)vc * bbuf_doubles, *const mbuf = bbuf + (size_t)4 * nj * 32;
+        uint64_t *const b_full = &vbars[vc * 3 + 0], *const b_empty = &vbars[vc * 3 + 1], *const item_done = &vbars[vc * 3 + 2];
+        uint32_t n = 0;                                          // items handed to the DMMA warps so far
+        int32_t *prev_ctr = nullptr;                             // xdot_done counter of the item they are working on
+        auto publish = [&](int32_t *ctr) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 4;\n" ::"l"(ctr) : "memory");
+        };
+        for (int L = 0; L < ck.n_levels; ++L) {
+            const PLevel &pl = ck.lv[L];
+            const int total = pl.n_items * m.n_ksplit;
+            for (int q = v; q < total; q += NV) {
+                const PkItem it = pk_item(pl, n_tiles, q);
+                int32_t *ctr = ck.xdot_done + pl.tile_base + it.tile;
+                if (it.T1 <= it.T0) { publish(ctr); continue; }  // (k_xdot's grids never deal an empty range)
+                const int32_t *flag = ck.prop_done + pl.tile_base + it.tile;
+                const double *bsrc = ck.bfrag[L & 1] + (((size_t)it.oct0 * m.n_ksplit + it.ks) * nj) * 32;
+                const double *msrc = ck.magic[L & 1] + (size_t)it.oct0 * SSD_OCT;
+                const size_t bstride = (size_t)m.n_ksplit * nj * 32;
+                bool filled = false;
+                const unsigned long long t0 = gtime();
+                while (prev_ctr || !filled) {
+                    if (prev_ctr && mbar_try_wait(item_done, (n - 1) & 1u)) { publish(prev_ctr); prev_ctr = nullptr; }
+                    if (!filled && (n == 0 || mbar_try_wait(b_empty, (n - 1) & 1u)) && ld_acquire(flag) >= it.n_in_tile) {
+                        for (int pt = 0; pt < it.noct; ++pt)
+                            for (int j = 0; j < nj; ++j) bbuf[((size_t)pt * nj + j) * 32 + lane] = __ldcg(bsrc + pt * bstride + j * 32 + lane);
+                        if (lane < it.noct * SSD_OCT) mbuf[lane] = __ldcg(msrc + lane);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(b_full);
+                        filled = true;
+                    } else if (!filled || prev_ctr) {
+                        __nanosleep(64);
+                        if (gtime() - t0 > 20000000000ull) __trap();
+                    }
+                }
+                prev_ctr = ctr; ++n;
+            }
+        }
+        if (prev_ctr) { mbar_wait(item_done, (n - 1) & 1u); publish(prev_ctr); }
         return;
     }
     if (!scalar_cta) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_DMMA));
         // ---- DMMA warps ---------------------------------------------------------------------------
         const int vc = warp >> 2, v = blockIdx.x * 2 + vc, NV = n_dmma_ctas * 2;
-        const uint32_t stage_doubles = (uint32_t)m.ssd_nj * 64;
         XdWarp xw;
         xw.warp = warp & 3; xw.ks = 0; xw.it_base = 0;
-        xw.ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
-        xw.full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)8 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
+        xw.ring = ring0 + (size_t)warp * PK_STAGES * stage_doubles;
+        xw.full = bars + warp * PK_STAGES;
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < XD_STAGES; ++s) mbar_init(&xw.full[s], 1);
+            for (int s = 0; s < PK_STAGES; ++s) mbar_init(&xw.full[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
         __syncwarp();
-        const int n_tiles = (int)(m.ssd_ld / SSD_TN);
+        const double *const bbuf = bbuf0 + (size_t)vc * bbuf_doubles, *const mbuf = bbuf + (size_t)4 * nj * 32;
+        uint32_t n = 0;
         for (int L = 0; L < ck.n_levels; ++L) {
             const PLevel &pl = ck.lv[L];
-            const XdGrid g = pl.g;
             Level lv; lv.order = ck.order + pl.order_off; lv.n = pl.n; lv.ctxs = ck.ctxs;
             const int total = pl.n_items * m.n_ksplit;
             for (int q = v; q < total; q += NV) {
-                const int ks = q / pl.n_items, bx = q - ks * pl.n_items;
-                int tile, oct0, noct, c_in, C;
-                const int n_in_hi = g.n_hi * g.c_hi;
-                if (bx < n_in_hi) { tile = bx / g.c_hi; c_in = bx - tile * g.c_hi; C = g.c_hi; noct = g.oct_hi; oct0 = tile * g.oct_hi; }
-                else { const int r = bx - n_in_hi, t = r / g.c_lo; tile = g.n_hi + t; c_in = r - t * g.c_lo; C = g.c_lo; noct = g.oct_lo; oct0 = g.n_hi * g.oct_hi + t * g.oct_lo; }
-                const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
-                const int n_in_tile = min(pl.n, (oct0 + noct) * SSD_OCT) - oct0 * SSD_OCT;
+                const PkItem it = pk_item(pl, n_tiles, q);
+                if (it.T1 <= it.T0) continue;
                 unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-                const DmmaWait<TL> wait = { ck.prop_done + pl.tile_base + tile, n_in_tile, tl, 0ull };
+                const VctaHooks<TL> hooks = { &vbars[vc * 3 + 0], &vbars[vc * 3 + 1], &vbars[vc * 3 + 2], n & 1u, tl, 0ull };
                 const unsigned long long t_a = (TL && tl) ? gtime() : 0ull;
-                xw.ks = ks;
-                if (T1 > T0) {
-                    const double *bf = ck.bfrag[L & 1], *mgc = ck.magic[L & 1];
-#define PK_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF>(m, bf, mgc, lv, ck.ll_acc, oct0, T0, T1, xw, wait, nullptr, nullptr)
-                    if (m.ssd_nj == SSD_NJ && m.ssd_half) {
-                        switch (noct) { case 4: PK_CALL(4, SSD_NJ, true); break; case 3: PK_CALL(3, SSD_NJ, true); break; case 2: PK_CALL(2, SSD_NJ, true); break; default: PK_CALL(1, SSD_NJ, true); break; }
-                    } else if (m.ssd_nj == SSD_NJ) {
-                        switch (noct) { case 4: PK_CALL(4, SSD_NJ, false); break; case 3: PK_CALL(3, SSD_NJ, false); break; case 2: PK_CALL(2, SSD_NJ, false); break; default: PK_CALL(1, SSD_NJ, false); break; }
-                    } else {
-                        switch (noct) { case 4: PK_CALL(4, 0, false); break; case 3: PK_CALL(3, 0, false); break; case 2: PK_CALL(2, 0, false); break; default: PK_CALL(1, 0, false); break; }
-                    }
-#undef PK_CALL
+                xw.ks = it.ks;
+                const int oct0 = it.oct0, T0 = it.T0, T1 = it.T1;
+                const size_t bstride = (size_t)nj * 32;
+#define PK_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, PK_STAGES>(m, bbuf, bstride, mbuf, lv, ck.ll_acc, oct0, T0, T1, xw, hooks, nullptr, nullptr)
+                if (m.ssd_nj == SSD_NJ && m.ssd_half) {
+                    switch (it.noct) { case 4: PK_CALL(4, SSD_NJ, true); break; case 3: PK_CALL(3, SSD_NJ, true); break; case 2: PK_CALL(2, SSD_NJ, true); break; default: PK_CALL(1, SSD_NJ, true); break; }
+                } else if (m.ssd_nj == SSD_NJ) {
+                    switch (it.noct) { case 4: PK_CALL(4, SSD_NJ, false); break; case 3: PK_CALL(3, SSD_NJ, false); break; case 2: PK_CALL(2, SSD_NJ, false); break; default: PK_CALL(1, SSD_NJ, false); break; }
+                } else {
+                    switch (it.noct) { case 4: PK_CALL(4, 0, false); break; case 3: PK_CALL(3, 0, false); break; case 2: PK_CALL(2, 0, false); break; default: PK_CALL(1, 0, false); break; }
                 }
-                const unsigned long long t_b = (TL && tl) ? gtime() : 0ull;
-                arrive(ck.xdot_done + pl.tile_base + tile);
-                if (TL && tl && lane == 0 && T1 > T0) {
+#undef PK_CALL
+                ++n;
+                if (TL && tl && lane == 0) {
+                    const unsigned long long t_b = gtime();
                     atomicMax(tl + PT_X1, t_b);
-                    atomicAdd(tl + PT_SUM_WAIT, wait.t_done - t_a); atomicAdd(tl + PT_SUM_ITEM, t_b - wait.t_done);
+                    atomicAdd(tl + PT_SUM_WAIT, hooks.t_done - t_a); atomicAdd(tl + PT_SUM_ITEM, t_b - hooks.t_done);
                     atomicAdd(tl + PT_ITEMS, 1ull);
                 }
             }
@@ -1270,10 +1384,10 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
     }
     CU(cudaMemsetAsync(ctr[g_dev], 0, sizeof(int32_t) * (PK_MAX_LEVELS + PK_MAX_TILES + (size_t)tiles), stream()));
     static bool attr_set[64] = { false };
-    const size_t smem = 2 * xdot_smem_bytes(m.ssd_nj);
+    const size_t smem = pk_smem_bytes(m.ssd_nj);
     if (!attr_set[g_dev]) {
-        CU(cudaFuncSetAttribute(k_chunk_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * xdot_smem_bytes(SSD_NJ))));
-        CU(cudaFuncSetAttribute(k_chunk_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * xdot_smem_bytes(SSD_NJ))));
+        CU(cudaFuncSetAttribute(k_chunk_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem_bytes(SSD_NJ)));
+        CU(cudaFuncSetAttribute(k_chunk_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem_bytes(SSD_NJ)));
         attr_set[g_dev] = true;
     }
     if (ck.tl) k_chunk_persist<true><<<sms, PK_THREADS, smem, stream()>>>(cfg, m, ck);
