@@ -126,10 +126,10 @@ class ClockSampler:
                 "samples": len(sm), "samples_in_timed_region": len(timed), "window": where, "source": self.src}
 
 
-def ncu_traffic():
-    """dram bytes read + written per k_xdot launch from the committed `ncu --set full` capture."""
+def ncu_traffic(persistent=False):
+    """dram bytes read + written per launch of the dominant kernel from the committed `ncu --set full` capture."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_k_xdot_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_k_chunk_persist_traffic.json" if persistent else "r01_k_xdot_traffic.json")))
         return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
     except (OSError, KeyError, ValueError):
         return None
@@ -302,7 +302,7 @@ def run_b200(args):
                    "a second pass of the same steps with CUDA events around every k_xdot launch (ms_per_step of that pass: %.4f)" % (ms_pass2 / args.steps))
     roofline = {"bound": "tensor", "pipe": "fp64 tensor path (DMMA m8n8k4)", "kernel": kname, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if achieved else None,
-                "traffic": ncu_traffic(),
+                "traffic": ncu_traffic(persistent),
                 "algorithmic_flops_per_launch": flops / max(1, ll_launches), "launches": ll_launches,
                 "avg_launch_ms": ms_ll / max(1, ll_launches), "share_of_step": ms_ll / ms_pass2 if ms_pass2 > 0 else None,
                 "measured_in": measured_in,

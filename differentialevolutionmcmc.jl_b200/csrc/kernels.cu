@@ -1000,14 +1000,24 @@ __device__ __forceinline__ void arrive(int32_t *ctr)
     if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(ctr) : "memory");
 }
 
+// the scalar warps are few (96) and sit on the critical path of a level: they poll without back-off
+__device__ __forceinline__ void wait_ge_fast(const int32_t *ctr, int target)
+{
+    if (ld_acquire(ctr) >= target) return;
+    const unsigned long long t0 = gtime();
+    while (ld_acquire(ctr) < target) {
+        __nanosleep(20);
+        if (gtime() - t0 > 20000000000ull) __trap();
+    }
+}
 struct FlagWait {
     const int32_t *c0; int t0; const int32_t *c1; int t1;
     unsigned long long *tl; int w_min, w_max;            // debug timeline: stamp when the wait is over
     mutable unsigned long long t_done;
     __device__ __forceinline__ void operator()() const
     {
-        if (c0) wait_ge(c0, t0);
-        if (c1) wait_ge(c1, t1);
+        if (c0) wait_ge_fast(c0, t0);
+        if (c1) wait_ge_fast(c1, t1);
         if (tl) {
             t_done = gtime();
             if ((threadIdx.x & 31) == 0) { if (w_min >= 0) atomicMax(tl + w_min, ~t_done); if (w_max >= 0) atomicMax(tl + w_max, t_done); }
@@ -1016,7 +1026,8 @@ struct FlagWait {
 };
 // per level: stamps (min stored complemented) and, summed over the DMMA warps, the nanoseconds spent
 // waiting for the proposals, in the item (B fragments, DMMA loop, flush) and in the arrive
-enum { PT_P0 = 0, PT_PW, PT_P1, PT_XW0, PT_XW1, PT_X1, PT_AW0, PT_A1, PT_SUM_WAIT, PT_SUM_ITEM, PT_SUM_ARRIVE, PT_ITEMS, PT_WORDS = 16 };
+enum { PT_P0 = 0, PT_PW, PT_P1, PT_XW0, PT_XW1, PT_X1, PT_AW0, PT_A1, PT_SUM_WAIT, PT_SUM_ITEM, PT_SUM_ARRIVE, PT_ITEMS,
+       PT_S_PRE, PT_S_BODY, PT_S_STAGE, PT_S_ARR, PT_S_N, PT_A_BODY, PT_A_ARR, PT_A_N, PT_WORDS = 24 };
 // DMMA warps.  (Deferring the arrive of the previous item behind this item's B-fragment loads was
 // tried: carrying the pending counter across items makes ptxas drop the raised register budget of
 // the setmaxnreg region -- 125 registers and B fragments reloaded from local memory inside the
@@ -1161,14 +1172,19 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
                 while (prev_ctr || !filled) {
                     if (prev_ctr && mbar_try_wait(item_done, (n - 1) & 1u)) { publish(prev_ctr); prev_ctr = nullptr; }
                     if (!filled && (n == 0 || mbar_try_wait(b_empty, (n - 1) & 1u)) && ld_acquire(flag) >= it.n_in_tile) {
-                        for (int pt = 0; pt < it.noct; ++pt)
-                            for (int j = 0; j < nj; ++j) bbuf[((size_t)pt * nj + j) * 32 + lane] = __ldcg(bsrc + pt * bstride + j * 32 + lane);
-                        if (lane < it.noct * SSD_OCT) mbuf[lane] = __ldcg(msrc + lane);
+                        // the staged means were written with ordinary stores on other SMs and acquired just
+                        // above; the copies read them through the async proxy, and complete on b_full
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                            const uint32_t oct_bytes = (uint32_t)nj * 32 * sizeof(double), mg_bytes = (uint32_t)it.noct * SSD_OCT * sizeof(double);
+                            mbar_expect_tx(b_full, oct_bytes * (uint32_t)it.noct + mg_bytes);
+                            for (int pt = 0; pt < it.noct; ++pt) bulk_g2s(bbuf + (size_t)pt * nj * 32, bsrc + pt * bstride, oct_bytes, b_full);
+                            bulk_g2s(mbuf, msrc, mg_bytes, b_full);
+                        }
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(b_full);
                         filled = true;
                     } else if (!filled || prev_ctr) {
-                        __nanosleep(64);
+                        __nanosleep(32);
                         if (gtime() - t0 > 20000000000ull) __trap();
                     }
                 }
@@ -1240,8 +1256,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
             unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
             co.w = { ck.xdot_done + pl.tile_base + tile, xd_tile_ctas(pl.g, tile) * 4 * m.n_ksplit, nullptr, 0, tl, PT_AW0, -1, 0ull };
             accept_particle(co, cfg, m, ctx, (int)(e & LV_POS_MASK));
+            const unsigned long long ta1 = (TL && tl) ? gtime() : 0ull;
             arrive(ck.acc_done + L);
-            if (tl && lane == 0) atomicMax(tl + PT_A1, gtime());
+            if (TL && tl && lane == 0) {
+                const unsigned long long ta2 = gtime();
+                atomicMax(tl + PT_A1, ta2);
+                atomicAdd(tl + PT_A_BODY, ta1 - co.w.t_done); atomicAdd(tl + PT_A_ARR, ta2 - ta1); atomicAdd(tl + PT_A_N, 1ull);
+            }
         }
     };
     int next_acc = 0;
@@ -1257,12 +1278,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
             const int p = (int)(e & LV_POS_MASK);
             double *bfrag = ck.bfrag[L & 1], *magic = ck.magic[L & 1];
             unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-            if (tl && lane == 0) atomicMax(tl + PT_P0, ~gtime());
+            const unsigned long long tp0 = (TL && tl) ? gtime() : 0ull;
+            if (tl && lane == 0) atomicMax(tl + PT_P0, ~tp0);
             const FlagWait fw = { pl.dep >= 0 ? ck.acc_done + pl.dep : nullptr, pl.dep >= 0 ? ck.lv[pl.dep].n : 0,
                                   L >= 2 ? ck.acc_done + (L - 2) : nullptr, L >= 2 ? ck.lv[L - 2].n : 0, tl, PT_PW, -1, 0ull };
             const ProposeLanes<decltype(pending)> co(pending, fw);
             StageSink sink = { m, bfrag, wi, m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
             propose_particle(co, cfg, m, ctx, p, sink);
+            const unsigned long long tp1 = (TL && tl) ? gtime() : 0ull;
             if (sink.on) stage_scale(m, warp_sum(sink.msq), wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
             else {
                 __syncwarp();
@@ -1270,8 +1293,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
             }
             int tile, oct0, noct;
             xd_tile_of_octet(pl.g, wi / SSD_OCT, tile, oct0, noct);
+            const unsigned long long tp2 = (TL && tl) ? gtime() : 0ull;
             arrive(ck.prop_done + pl.tile_base + tile);
-            if (tl && lane == 0) atomicMax(tl + PT_P1, gtime());
+            if (TL && tl && lane == 0) {
+                const unsigned long long tp3 = gtime();
+                atomicMax(tl + PT_P1, tp3);
+                // prologue + pending accepts + dependency wait | body | staging | arrive
+                atomicAdd(tl + PT_S_PRE, co.w.t_done - tp0); atomicAdd(tl + PT_S_BODY, tp1 - co.w.t_done);
+                atomicAdd(tl + PT_S_STAGE, tp2 - tp1); atomicAdd(tl + PT_S_ARR, tp3 - tp2); atomicAdd(tl + PT_S_N, 1ull);
+            }
         }
         pending();                                           // a warp without a proposal in this level
         if (ck.lag == 0) while (next_acc <= L) accept_level(next_acc++);
@@ -1295,25 +1325,27 @@ static void pk_timeline_dump()
     if (cudaMemcpy(h.data(), g_ptl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     FILE *f = fopen(path, "w");
     if (!f) return;
-    fprintf(f, "level,chunk,n,propose_first_start,propose_dep_ready,propose_last_end,xdot_first_ready,xdot_last_ready,xdot_last_end,accept_first_ready,accept_last_end,warp_items,wait_us_per_item,work_us_per_item,arrive_us_per_item\n");
+    fprintf(f, "level,chunk,n,propose_first_start,propose_dep_ready,propose_last_end,xdot_first_ready,xdot_last_ready,xdot_last_end,accept_first_ready,accept_last_end,warp_items,wait_us_per_item,work_us_per_item,arrive_us_per_item,prop_pre_us,prop_body_us,prop_stage_us,prop_arrive_us,acc_body_us,acc_arrive_us\n");
     unsigned long long t0 = ~0ull;
     for (int i = 0; i < n; ++i) if (h[(size_t)i * PT_WORDS + PT_P0]) t0 = std::min(t0, ~h[(size_t)i * PT_WORDS + PT_P0]);
     auto rel = [&](unsigned long long v) { return v ? (double)((long long)(v - t0)) * 1e-3 : -1.0; };
     for (int i = 0; i < n; ++i) {
         const unsigned long long *w = h.data() + (size_t)i * PT_WORDS;
         const double ni = w[PT_ITEMS] ? (double)w[PT_ITEMS] : 1.0;
-        fprintf(f, "%d,%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%llu,%.3f,%.3f,%.3f\n", i, g_ptl_chunk[i], g_ptl_n[i], rel(~w[PT_P0]), rel(~w[PT_PW]), rel(w[PT_P1]),
+        const double ns = w[PT_S_N] ? (double)w[PT_S_N] * 1e3 : 1.0, na = w[PT_A_N] ? (double)w[PT_A_N] * 1e3 : 1.0;
+        fprintf(f, "%d,%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%llu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, g_ptl_chunk[i], g_ptl_n[i], rel(~w[PT_P0]), rel(~w[PT_PW]), rel(w[PT_P1]),
                 rel(~w[PT_XW0]), rel(w[PT_XW1]), rel(w[PT_X1]), rel(~w[PT_AW0]), rel(w[PT_A1]), w[PT_ITEMS],
-                (double)w[PT_SUM_WAIT] * 1e-3 / ni, (double)w[PT_SUM_ITEM] * 1e-3 / ni, (double)w[PT_SUM_ARRIVE] * 1e-3 / ni);
+                (double)w[PT_SUM_WAIT] * 1e-3 / ni, (double)w[PT_SUM_ITEM] * 1e-3 / ni, (double)w[PT_SUM_ARRIVE] * 1e-3 / ni,
+                (double)w[PT_S_PRE] / ns, (double)w[PT_S_BODY] / ns, (double)w[PT_S_STAGE] / ns, (double)w[PT_S_ARR] / ns,
+                (double)w[PT_A_BODY] / na, (double)w[PT_A_ARR] / na);
     }
     fclose(f);
 }
 
-static int persist_enabled()
+static int persist_enabled()                                  // DEMCMC_PERSIST=0: level-by-level launches (A/B runs, tests)
 {
-    static int enabled = -1;
-    if (enabled < 0) { const char *e = getenv("DEMCMC_PERSIST"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    return enabled;
+    const char *e = getenv("DEMCMC_PERSIST");
+    return (e && e[0] == '0') ? 0 : 1;
 }
 static int persist_scalar_ctas()
 {

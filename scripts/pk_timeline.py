@@ -41,4 +41,7 @@ for ch in sorted(set(r["chunk"] for r in R)):
 print("level period (last item end to last item end) %.2f us" % float(np.mean(per)))
 print("per DMMA warp and item: wait for proposals %.2f us, item (B fragments + DMMA loop + flush) %.2f us, arrive %.2f us" % (
     mean(lambda r: r["wait_us_per_item"]), mean(lambda r: r["work_us_per_item"]), mean(lambda r: r["arrive_us_per_item"])))
+print("per proposal: prologue + pending accepts + dependency wait %.2f us, body %.2f us, staging %.2f us, arrive %.2f us; per accept: body %.2f us, arrive %.2f us" % (
+    mean(lambda r: r["prop_pre_us"]), mean(lambda r: r["prop_body_us"]), mean(lambda r: r["prop_stage_us"]), mean(lambda r: r["prop_arrive_us"]),
+    mean(lambda r: r["acc_body_us"]), mean(lambda r: r["acc_arrive_us"])))
 print("ideal DMMA time of a level (13 k-steps, octet padding) %.2f us" % mean(lambda r: np.ceil(r["n"] / 8) * 1563 * 8 * 13 * 16 / (148 * 4) / 1965.0))

@@ -336,6 +336,43 @@ def test_lanes_and_chunks_do_not_change_the_result():
         assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))
 
 
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.3, burnin=6)),
+                                      ("mvnormal", dict(theta_snooker=0.0, alpha=0.1, burnin=0, kappa=0.8)),
+                                      ("hier_normal", dict(theta_snooker=0.0, alpha=0.2, burnin=4))])
+def test_persistent_chunk_kernel_is_a_schedule_only(model, kw, monkeypatch):
+    """k_chunk_persist (all levels of a chunk in one warp-specialised launch: DMMA warps, helper warps,
+    scalar CTAs, counter-based dependencies, two alternating lanes) against the level-by-level
+    launches of k_propose / k_xdot / k_accept: bit-identical chains, and the counters show which
+    path ran."""
+    case = make_case(model, np.random.default_rng(43), n_obs=4000 if model == "mvnormal" else 700)
+    if model == "hier_normal":
+        kw = dict(kw, blocks=hier_blocks(case.d - 3))          # blocking_on: every block is its own chunk
+    G, Np = 4, 40
+    theta0 = case.theta0(np.random.default_rng(7), G * Np)
+    outs, chunks, launches = [], [], []
+    for persist in ("0", "1"):
+        monkeypatch.setenv("DEMCMC_PERSIST", persist)
+        h = case.handle(G, Np, seed=9, **kw)
+        h.set_state(theta0)
+        h.run(40)
+        c = h.counters()
+        outs.append((h.samples(), h.accept(), h.lp(), h.get_state()[2]))
+        chunks.append(c["persistent_chunks"]); launches.append(c["kernel_launches"])
+        h.close()
+    assert chunks[0] == 0 and chunks[1] > 0, chunks
+    assert launches[1] < launches[0] / 4, launches
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+def test_persistent_chunk_kernel_replays_the_oracle(monkeypatch):
+    """Replay through the persistent kernel: the reference's draws from the tape, accept decisions
+    identical to the oracle's, log densities within 1e-12 relative (teacher-forced per iteration)."""
+    monkeypatch.setenv("DEMCMC_PERSIST", "1")
+    case = make_case("mvnormal", np.random.default_rng(47), n_obs=2500)
+    r, out = forced_run(case, 4, 24, 12, "replay", burnin=5, theta_snooker=0.15, alpha=0.3)
+    check(r, out)
+
+
 # ---- the optimize path (optimize.jl; maximize! / minimize! + evaluate_fun!) -------------------------
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
