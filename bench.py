@@ -206,8 +206,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libdemcmc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # stdout carries the one JSON line only: whatever a library prints there (NCCL's version banner,
+    # for one) goes to stderr -- file descriptor 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")         # stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D._ffi.use_library(D._ffi.DEFAULT_LIB)
     assert D._ffi.lib().demcmc_backend_name() == b"cuda-sm100a"
@@ -380,7 +385,10 @@ def run_b200(args):
                 "value_steady_no_flush": updates / (ms_steady * 1e-3) if world == 1 else None,
                 "gpu_launches": int(launches), "clocks": ck, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall_timed}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

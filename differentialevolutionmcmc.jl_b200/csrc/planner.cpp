@@ -13,6 +13,8 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
     out.mutate.assign((size_t)n_sweeps * G, 0);
     out.order.resize((size_t)n_sweeps * P);
     std::vector<int32_t> level((size_t)n_sweeps * P, 0), prev(P, -1), cur(P, 0);
+    // dependencies of every update as update indices (sweep * P + position), for the shaping pass below
+    std::vector<int32_t> deps((size_t)n_sweeps * P * 4, -1);
     int max_level = 0;
     for (int s = 0; s < n_sweeps; ++s) {
         const uint32_t sweep = sweep0 + (uint32_t)s;
@@ -28,6 +30,8 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
             const int32_t *lp = prev.data() + g * Np;
             for (int j = 0; j < Np; ++j) {
                 int l = lp[j] + 1;                                   // its own previous update
+                int32_t *du = deps.data() + ((size_t)s * P + g * Np + j) * 4;
+                if (s > 0) du[0] = (int32_t)((size_t)(s - 1) * P + g * Np + j);
                 if (!mutate) {
                     int dep[3], nd = 0;
                     if (in.resample) {
@@ -46,6 +50,8 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
                         const int k = dep[q];
                         if (k < 0 || k == j) continue;
                         l = std::max(l, (k < j ? lc[k] : lp[k]) + 1);
+                        if (k < j) du[1 + q] = (int32_t)((size_t)s * P + g * Np + k);
+                        else if (s > 0) du[1 + q] = (int32_t)((size_t)(s - 1) * P + g * Np + k);
                     }
                 }
                 lc[j] = l;
@@ -54,6 +60,35 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
             }
         }
         prev = cur;
+    }
+    // Shaping: the likelihood kernel pads every level to whole octets of particles (DMMA n = 8), on
+    // average 3.5 idle columns per level.  An update whose dependents all sit two or more levels
+    // later may run one level later at no cost, so each level hands its remainder (n mod 8) to the
+    // next one where it can.  Any schedule that respects the dependencies gives the same chain.
+    if (in.shape_octets && max_level > 0) {
+        const size_t U = level.size();
+        std::vector<int32_t> latest(U, max_level);
+        for (size_t v = U; v-- > 0;)                                   // dependents come later in (sweep, slot) order
+            for (int q = 0; q < 4; ++q) {
+                const int32_t u = deps[v * 4 + q];
+                if (u >= 0) latest[u] = std::min(latest[u], level[v] - 1);
+            }
+        std::vector<std::vector<int32_t>> members(max_level + 1);
+        for (size_t u = 0; u < U; ++u) members[level[u]].push_back((int32_t)u);
+        for (int l = 0; l < max_level; ++l) {
+            int r = (int)(members[l].size() % 8);
+            if (r == 0 || members[l].size() < 8) continue;
+            // later entries first: they keep the level's (sweep, slot) order intact for the rest
+            for (size_t i = members[l].size(); i-- > 0 && r > 0;) {
+                const int32_t u = members[l][i];
+                if (latest[u] <= l) continue;
+                // a dependent that was itself moved gives even more room; the bound stays valid
+                level[u] = l + 1;
+                members[l + 1].push_back(u);
+                members[l][i] = -1;
+                --r;
+            }
+        }
     }
     // stable counting sort of all (sweep, position) entries by level
     out.n_levels = max_level + 1;

@@ -31,6 +31,8 @@ struct PlanInput {
     int32_t P_stride = 0;      // particles per sweep in the tape slices (0: Np * G_local)
     int32_t proposal;          // 0 random_gamma
     double beta, theta_snooker;
+    bool shape_octets = false; // hand each level's remainder modulo 8 to the next level where the dependencies allow
+                               // (the DMMA likelihood kernel pads levels to whole octets of particles)
     bool resample;             // donors come from stored rows (crossover.jl:113-124): no donor dependencies inside a sweep
     // replay: tape slices [sweep][P_local] of the chunk's FIRST sweep onwards, else nullptr
     const uint8_t *t_kind;     // [n_sweeps][P_local]
