@@ -1,0 +1,108 @@
+// backend.h -- the device side of libdemcmc_b200 as seen by the host engine: memory, streams and
+// one launcher per kernel.  kernels.cu implements it with CUDA for sm_100a.  (tests/emu/ holds a
+// host-only test double of the same interface so the engine's host logic can be unit-tested on a
+// machine without a GPU; it is never built into or loaded by the product.)
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "de_types.h"
+
+namespace de {
+namespace be {
+
+const char *name();                       // "cuda-sm100a" or "emu"
+int device_count();
+int set_device(int dev);                  // 0 or error
+const char *last_error();
+
+void *dmalloc(size_t bytes);              // nullptr on failure
+void dfree(void *p);
+void *hmalloc_pinned(size_t bytes);
+void hfree_pinned(void *p);
+int h2d(void *dst, const void *src, size_t bytes);         // on the engine stream, async if src pinned
+int d2h(void *dst, const void *src, size_t bytes);         // synchronous
+int d2d(void *dst, const void *src, size_t bytes);
+int dzero(void *dst, size_t bytes);
+int sync();
+
+// lanes: independent kernel chains on separate streams (lane 0 = the engine stream).  set_lane
+// selects where the launchers below enqueue; lane_fork makes lanes 1..n-1 wait for everything
+// enqueued on lane 0 so far, lane_join makes lane 0 wait for the other lanes.
+constexpr int MAX_LANES = 2;
+void set_lane(int lane);
+int lane_fork(int n_lanes);
+int lane_join(int n_lanes);
+
+void *event_create();
+void event_destroy(void *ev);
+int event_record(void *ev);               // on the engine stream
+int event_wait(void *ev);                 // host waits
+
+void *tevent_create();                    // timing-capable event
+void tevent_destroy(void *ev);
+int tevent_elapsed(void *a, void *b, double *ms);
+int dfill(void *dst, int byte, size_t bytes);
+
+// CUDA-event stopwatch on the engine stream
+int timer_start();
+int timer_stop(double *ms);
+
+// ---- kernels ----------------------------------------------------------------------------------
+// centres MVN / hierarchical data and packs them for k_xdot (fills center, xT, ssd_xx, ssd_rowmax);
+// pack_ssd_doubles = size of the xT buffer the caller must allocate for the model's geometry
+size_t pack_ssd_doubles(const ModelDev &m);
+int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m /* xT allocated */);
+// init_particle: weights of n particles theta[n][d] -> w[n] (also demcmc_eval)
+int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior,
+                double *w, double *scratch_part);
+// select_base preparation on the sweep-start weights: cw[P] running sums, tot[G]; th[P] is scratch
+int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
+// propose -> loglik -> accept for one level of one sweep
+int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
+// MVN / hierarchical: adds the cross term into ll_acc (fixed point, see de_math.h: xd_scale; launch_propose
+// has cleared it and set ll_q); the other models write ll_part
+int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc);
+int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
+// migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
+// [position][d+3] = {theta..., weight, id, accept flag}
+int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);
+int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *theta, const double *w,
+                      const int32_t *id, const uint8_t *acc, double *stage);
+// pos: id -> position map of the row being edited (resample), or nullptr
+int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
+                       double *w, int32_t *id, uint8_t *acc, int32_t *pos);
+// history rows [n_rows][P][d] by slot -> reference layout [P][d][n_rows] by id (utilities.jl:34)
+int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
+                         int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,
+                         double *samples, double *lp, uint8_t *accept);
+// bundle_samples layout (main.jl:222-250): chains[P][d+2][n_rows] for history rows [row0, row0+n_rows);
+// final_id[P] = id at each final position, pos_scratch[P] device scratch
+int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
+                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out);
+// particle algebra known-answer ops (single warp each)
+int launch_op_project(const double *p1, const double *p2, int d, double *out);
+int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,
+                      int d, double *out, double *log_adj);
+int launch_op_de(const double *pt, const double *pm, const double *pn, const double *pb, double g1, double g2,
+                 const double *b, int d, double *out);
+int launch_op_reset(const double *prop, const double *pt, const uint8_t *mask, int d, double *out);
+int launch_op_accept(const double *wp, const double *wc, const double *adj, const double *u, int n, uint8_t *out);
+int launch_op_select(const double *w, int n, double u, int32_t *base_idx, int32_t *mig_idx);
+// roofline probes
+int fp64_peak(double *tflops);                             // the larger of the two below
+int fp64_peaks(double *dfma_tflops, double *dmma_tflops);   // DFMA loop, DMMA m8n8k4 loop
+int copy_peak(double *gbs);
+
+void timeline_dump();                     // debug: writes the %globaltimer stamps of the levels launched so far (DEMCMC_TIMELINE)
+int64_t launch_count();                   // kernels launched so far (for demcmc_counters)
+
+// ---- cross-rank migration (NCCL over NVLink) ---------------------------------------------------
+int comm_unique_id(uint8_t id[128]);
+int comm_init(const uint8_t id[128], int rank, int n_ranks, void **comm);
+int comm_destroy(void *comm);
+// grouped send/recv of stage rows: for each position i, src_rank[i] sends row send_pos[i] to dst_rank[i]
+int comm_exchange(void *comm, int rank, int n, const int *src_rank, const int *dst_rank, double *stage_send,
+                  double *stage_recv, int row_len);
+
+} // namespace be
+} // namespace de

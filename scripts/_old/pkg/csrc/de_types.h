@@ -33,10 +33,6 @@ struct ModelDev {
     int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension
     int32_t ssd_k;            // dimensions (MVN: n_dim; hierarchical: subjects)
     int32_t ssd_nj;           // DMMA k-steps per dimension split = ceil(ksplit_len / 4)
-    int32_t ssd_half;         // ksplit_len % 4 == 2: the last k-step is a HALF step -- its two dimensions of BOTH row
-                              // tiles of a pair share one A fragment (columns 0-1: first row tile, 2-3: second), the B
-                              // fragment repeats the two means (at load time), and the step costs one DMMA instead of two (d = 50:
-                              // 25 DMMAs per row pair and octet instead of 26)
     int32_t ssd_qbits;        // fixed-point bits below the per-particle bound (de_math.h: xd_magic)
     int32_t has_sigma;
     double sigma_acc[MAX_ACC];
@@ -54,15 +50,13 @@ struct ModelDev {
 // DMMA m8n8k4 A fragment of (dimension split ks, row pair rp, observation tile, k-step j): lane =
 // (i%8)*4 + k%4 holds the two row tiles of the pair side by side, so one LDS.128 feeds two DMMAs
 // and a (ks, rp) stream over observation tiles is contiguous (one bulk copy per stage).
-DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n_tiles, int half)
+DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n_tiles)
 {
     const int64_t tile = i / SSD_TN;
     const int r = (int)(i % SSD_TN) / 8, row = (int)(i % 8);
     const int ks = k / ksplit_len, kl = k % ksplit_len;
-    const int j = kl / 4;
-    const int64_t frag = (((int64_t)(ks * 4 + (r >> 1)) * n_tiles + tile) * nj + j) * 32;
-    if (half && j == nj - 1) return (frag + row * 4 + (kl % 4) + 2 * (r & 1)) * 2;   // one fragment for both row tiles
-    return (frag + row * 4 + (kl % 4)) * 2 + (r & 1);
+    const int j = kl / 4, lane = row * 4 + (kl % 4);
+    return ((((int64_t)(ks * 4 + (r >> 1)) * n_tiles + tile) * nj + j) * 32 + lane) * 2 + (r & 1);
 }
 
 struct ConfigDev {

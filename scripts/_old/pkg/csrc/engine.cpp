@@ -1,0 +1,1037 @@
+// engine.cpp -- host side of libdemcmc_b200: the handle, the iteration loop of _sample
+// (src/main.jl:33-38) and the C ABI of include/demcmc_b200.h.  All arithmetic on particles happens
+// in the kernels behind backend.h; the host only schedules (planner.h) and moves buffers.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/demcmc_b200.h"
+#include "backend.h"
+#include "de_types.h"
+#include "planner.h"
+
+using namespace de;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define BE(call) do { if ((call) != 0) return fail(DEMCMC_ECUDA, "%s: %s", #call, be::last_error()); } while (0)
+
+namespace {
+
+struct Row { double *theta; double *w; int32_t *id; uint8_t *acc; };
+
+struct Upload {            // pinned staging + device copy of one sweep's schedule
+    int32_t *h_order = nullptr, *d_order = nullptr;   // [MAX_CHUNK][P] level-sorted entries
+    uint8_t *h_mut = nullptr, *d_mut = nullptr;       // [MAX_CHUNK][G]
+    SweepCtx *h_ctx = nullptr, *d_ctx = nullptr;      // [MAX_CHUNK]
+    void *copied = nullptr;  // event: the H2D copies out of the pinned buffers have run
+    bool armed = false;
+};
+
+} // namespace
+
+struct demcmc_handle {
+    demcmc_config cfg;
+    std::vector<uint8_t> blocks;
+    std::vector<double> lo, hi;
+    int G_local = 0, P = 0, B = 1, d = 0;
+    ConfigDev dcfg;
+    ModelDev dmodel;
+    bool has_model = false, has_state = false;
+    std::vector<void *> model_allocs;
+    // state rows
+    int64_t hist_cap = 0, iters_done = 0;
+    double *hist_theta = nullptr, *hist_w = nullptr;
+    int32_t *hist_id = nullptr;
+    uint8_t *hist_acc = nullptr;
+    int32_t *hist_pos = nullptr;                        // resample: [row][id] -> position holding that id
+    int64_t n0 = 0;                                     // de.n_initial: history rows before iteration 1
+    bool has_history = false;                           // the n_initial prior rows were uploaded
+    double *scr_theta = nullptr, *scr_w = nullptr;      // 3 scratch rows
+    int32_t *scr_id = nullptr;
+    uint8_t *scr_acc = nullptr;
+    int cur_scratch = 0;                                // current state lives in scratch row k, or
+    int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
+    // proposal scratch
+    double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *prop_msq = nullptr, *ll_part = nullptr, *ll_q = nullptr;
+    long long *ll_acc = nullptr;
+    uint8_t *prop_inb = nullptr;
+    double *base_th = nullptr, *base_cw = nullptr, *base_tot = nullptr;
+    double *d_lo = nullptr, *d_hi = nullptr;
+    uint8_t *d_blocks = nullptr;
+    // schedule ring
+    static constexpr int RING = 4;
+    int max_chunk = MAX_CHUNK;                          // sweeps overlapped on the device (1 = a barrier per sweep)
+    int n_lanes = 1;                                    // concurrent kernel chains over independent sets of groups (demcmc_set_lanes)
+    Upload ring[RING];
+    int64_t ring_use = 0;
+    // migration
+    int32_t *d_picks = nullptr;
+    double *d_stage = nullptr, *d_stage_recv = nullptr;
+    std::vector<int32_t> last_mig_slots;                // [n_iter][G_total] of the last call
+    int32_t *d_mig_log = nullptr;                       // device log of picks of the last call
+    int64_t mig_log_iters = 0;
+    // trace of the last call
+    double *tr_theta = nullptr, *tr_w = nullptr, *tr_adj = nullptr;
+    uint8_t *tr_acc = nullptr;
+    int64_t tr_sweeps = 0;
+    // comm
+    void *comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::vector<int> group_owner;                       // [G_total] rank owning each group
+    demcmc_counters ctr;
+    // measurement mode (demcmc_set_timing)
+    int64_t flush_bytes = 0;
+    bool time_loglik = false;
+    void *flush_buf = nullptr;
+    std::vector<void *> tev;                            // pool of timing events
+};
+
+static Row row_of(demcmc_handle *h, bool hist, int64_t idx)
+{
+    const size_t P = h->P, d = h->d;
+    Row r;
+    if (hist) { r.theta = h->hist_theta + idx * P * d; r.w = h->hist_w + idx * P; r.id = h->hist_id + idx * P; r.acc = h->hist_acc + idx * P; }
+    else { r.theta = h->scr_theta + idx * P * d; r.w = h->scr_w + idx * P; r.id = h->scr_id + idx * P; r.acc = h->scr_acc + idx * P; }
+    return r;
+}
+static Row cur_row(demcmc_handle *h) { return h->cur_hist >= 0 ? row_of(h, true, h->cur_hist) : row_of(h, false, h->cur_scratch); }
+
+// history rows: [0, n0) = the n_initial prior rows (utilities.jl:35-39), row n0 + it = iteration it
+static int grow_history(demcmc_handle *h, int64_t need)
+{
+    if (need <= h->hist_cap) return 0;
+    int64_t cap = std::max<int64_t>(need, h->hist_cap * 2);
+    const size_t P = h->P, d = h->d;
+    const int64_t have = h->hist_cap > 0 ? h->n0 + h->iters_done : 0;
+    double *nt = (double *)be::dmalloc(sizeof(double) * cap * P * d);
+    double *nw = (double *)be::dmalloc(sizeof(double) * cap * P);
+    int32_t *ni = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P);
+    uint8_t *na = (uint8_t *)be::dmalloc(cap * P);
+    int32_t *np = h->cfg.donors ? (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P) : nullptr;
+    if (!nt || !nw || !ni || !na || (h->cfg.donors && !np)) return fail(DEMCMC_ENOMEM, "history of %lld rows does not fit on the device", (long long)cap);
+    if (have > 0) {
+        BE(be::d2d(nt, h->hist_theta, sizeof(double) * have * P * d));
+        BE(be::d2d(nw, h->hist_w, sizeof(double) * have * P));
+        BE(be::d2d(ni, h->hist_id, sizeof(int32_t) * have * P));
+        BE(be::d2d(na, h->hist_acc, have * P));
+        if (np) BE(be::d2d(np, h->hist_pos, sizeof(int32_t) * have * P));
+        BE(be::sync());
+    }
+    be::dfree(h->hist_theta); be::dfree(h->hist_w); be::dfree(h->hist_id); be::dfree(h->hist_acc); be::dfree(h->hist_pos);
+    h->hist_theta = nt; h->hist_w = nw; h->hist_id = ni; h->hist_acc = na; h->hist_pos = np; h->hist_cap = cap;
+    return 0;
+}
+
+// ---- particle algebra ops (known-answer tests) --------------------------------------------------
+namespace {
+struct DevBuf {
+    std::vector<void *> p;
+    ~DevBuf() { for (void *q : p) be::dfree(q); }
+    template <typename T> T *up(const T *src, size_t n)
+    {
+        T *q = (T *)be::dmalloc(std::max<size_t>(8, sizeof(T) * n));
+        if (!q) return nullptr;
+        p.push_back(q);
+        if (src && n && be::h2d(q, src, sizeof(T) * n)) return nullptr;
+        return q;
+    }
+};
+int op_begin(int device)
+{
+    if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback");
+    if (be::set_device(device)) return fail(DEMCMC_ENODEVICE, "cannot select device %d", device);
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+const char *demcmc_last_error(void) { return g_err.c_str(); }
+int demcmc_abi_version(void) { return DEMCMC_ABI_VERSION; }
+int demcmc_device_count(void) { return be::device_count(); }
+const char *demcmc_backend_name(void) { return be::name(); }
+
+int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
+{
+    if (!cfg || !out) return fail(DEMCMC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DEMCMC_ABI_VERSION) return fail(DEMCMC_EINVAL, "abi_version %d != %d", cfg->abi_version, DEMCMC_ABI_VERSION);
+    if (cfg->Np < 3) return fail(DEMCMC_EINVAL, "Np must be >= 3 (two donors besides the target, crossover.jl:158-160)");
+    if (cfg->n_groups < 1 || cfg->d < 1 || !cfg->lo || !cfg->hi) return fail(DEMCMC_EINVAL, "bad n_groups/d/bounds");
+    if (cfg->n_groups > MAX_MIG) return fail(DEMCMC_EUNSUPPORTED, "n_groups > %d", MAX_MIG);
+    if (cfg->n_blocks < 0 || (cfg->n_blocks > 0 && !cfg->blocks)) return fail(DEMCMC_EINVAL, "blocks missing");
+    if (cfg->proposal < 0 || cfg->proposal > 2) return fail(DEMCMC_EINVAL, "unknown generate_proposal %d", cfg->proposal);
+    if (cfg->store_every > 1) return fail(DEMCMC_EUNSUPPORTED, "thinning (store_every > 1) is not built yet");
+    if (cfg->n_initial < 0 || cfg->donors < 0 || cfg->donors > 1) return fail(DEMCMC_EINVAL, "bad n_initial / donors");
+    if (cfg->update < 0 || cfg->update > DEMCMC_UPDATE_MINIMIZE || cfg->fitness < 0 || cfg->fitness > DEMCMC_FITNESS_FUN) return fail(DEMCMC_EINVAL, "unknown update_particle! / evaluate_fitness! kind");
+    if (cfg->update != DEMCMC_UPDATE_MH && cfg->theta_snooker != 0.0)
+        return fail(DEMCMC_EINVAL, "maximize! / minimize! take no log_adj: with theta_snooker > 0 the reference throws a MethodError (crossover.jl:38)");
+    if (cfg->donors == DEMCMC_DONORS_HISTORY) {
+        // resample (crossover.jl:113-124) draws from rows 1:de.iter-1: there must be rows to draw from
+        if ((int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3) return fail(DEMCMC_EINVAL, "sample = resample needs n_initial prior rows (at least 3 stored particles)");
+        if (cfg->group_count > 0 && cfg->group_count != cfg->n_groups) return fail(DEMCMC_EUNSUPPORTED, "sample = resample reads the history of every particle id: it is not sharded over GPUs yet");
+    }
+    if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
+    if (be::set_device(cfg->device) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
+
+    demcmc_handle *h = new demcmc_handle();
+    h->cfg = *cfg;
+    h->d = cfg->d;
+    h->n0 = cfg->n_initial;
+    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), be::MAX_LANES));   // A/B measurements
+    h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
+    if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
+    h->P = h->G_local * cfg->Np;
+    h->B = cfg->n_blocks > 0 ? cfg->n_blocks : 1;
+    h->lo.assign(cfg->lo, cfg->lo + cfg->d);
+    h->hi.assign(cfg->hi, cfg->hi + cfg->d);
+    if (cfg->n_blocks > 0) h->blocks.assign(cfg->blocks, cfg->blocks + (size_t)cfg->n_blocks * cfg->d);
+    if (cfg->n_groups == 1) h->cfg.alpha = 0.0;   // structs.jl:102-105
+    memset(&h->ctr, 0, sizeof h->ctr);
+    memset(&h->dmodel, 0, sizeof h->dmodel);
+    h->group_owner.assign(cfg->n_groups, 0);
+
+    const size_t P = h->P, d = h->d;
+    h->d_lo = (double *)be::dmalloc(sizeof(double) * d);
+    h->d_hi = (double *)be::dmalloc(sizeof(double) * d);
+    h->d_blocks = (uint8_t *)be::dmalloc(std::max<size_t>(1, h->blocks.size()));
+    h->scr_theta = (double *)be::dmalloc(sizeof(double) * 3 * P * d);
+    h->scr_w = (double *)be::dmalloc(sizeof(double) * 3 * P);
+    h->scr_id = (int32_t *)be::dmalloc(sizeof(int32_t) * 3 * P);
+    h->scr_acc = (uint8_t *)be::dmalloc(3 * P);
+    h->prop_theta = (double *)be::dmalloc(sizeof(double) * P * d);
+    h->prop_prior = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_msq = (double *)be::dmalloc(sizeof(double) * P);
+    h->prop_inb = (uint8_t *)be::dmalloc(P);
+    h->ll_acc = (long long *)be::dmalloc(sizeof(long long) * P);
+    h->ll_q = (double *)be::dmalloc(sizeof(double) * P);
+    h->base_th = (double *)be::dmalloc(sizeof(double) * P);
+    h->base_cw = (double *)be::dmalloc(sizeof(double) * P);
+    h->base_tot = (double *)be::dmalloc(sizeof(double) * std::max(1, h->G_local));
+    h->d_picks = (int32_t *)be::dmalloc(sizeof(int32_t) * MAX_MIG);
+    h->d_stage = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
+    h->d_stage_recv = (double *)be::dmalloc(sizeof(double) * MAX_MIG * (d + 3));
+    bool ok = h->d_lo && h->d_hi && h->d_blocks && h->scr_theta && h->scr_w && h->scr_id && h->scr_acc && h->prop_theta &&
+              h->prop_prior && h->prop_adj && h->prop_msq && h->prop_inb && h->ll_acc && h->ll_q && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
+    for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
+        Upload &u = h->ring[i];
+        u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P * MAX_CHUNK);
+        u.h_mut = (uint8_t *)be::hmalloc_pinned(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
+        u.h_ctx = (SweepCtx *)be::hmalloc_pinned(sizeof(SweepCtx) * MAX_CHUNK);
+        u.d_order = (int32_t *)be::dmalloc(sizeof(int32_t) * P * MAX_CHUNK);
+        u.d_mut = (uint8_t *)be::dmalloc(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
+        u.d_ctx = (SweepCtx *)be::dmalloc(sizeof(SweepCtx) * MAX_CHUNK);
+        u.copied = be::event_create();
+        ok = u.h_order && u.h_mut && u.h_ctx && u.d_order && u.d_mut && u.d_ctx && u.copied;
+    }
+    if (!ok) { demcmc_destroy(h); return fail(DEMCMC_ENOMEM, "device allocation failed: %s", be::last_error()); }
+    if (be::h2d(h->d_lo, h->lo.data(), sizeof(double) * d) || be::h2d(h->d_hi, h->hi.data(), sizeof(double) * d) ||
+        (!h->blocks.empty() && be::h2d(h->d_blocks, h->blocks.data(), h->blocks.size())) || be::sync()) {
+        demcmc_destroy(h);
+        return fail(DEMCMC_ECUDA, "upload failed: %s", be::last_error());
+    }
+    ConfigDev &c = h->dcfg;
+    c.Np = cfg->Np; c.d = cfg->d; c.G_local = h->G_local; c.group_begin = cfg->group_begin; c.proposal = cfg->proposal;
+    c.burnin = cfg->burnin; c.n_blocks = cfg->n_blocks; c.eps = cfg->eps; c.sigma = cfg->sigma; c.kappa = cfg->kappa;
+    c.resample = cfg->donors; c.update = cfg->update; c.fitness = cfg->fitness; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
+    *out = h;
+    return 0;
+}
+
+int demcmc_destroy(demcmc_handle *h)
+{
+    if (!h) return 0;
+    be::set_device(h->cfg.device);
+    be::sync();
+    be::timeline_dump();
+    if (h->comm) be::comm_destroy(h->comm);
+    for (void *p : h->model_allocs) be::dfree(p);
+    void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
+                     h->prop_theta, h->prop_prior, h->prop_adj, h->prop_msq, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
+                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
+    for (void *e : h->tev) be::tevent_destroy(e);
+    for (void *p : ptrs) be::dfree(p);
+    for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::hfree_pinned(u.h_ctx); be::dfree(u.d_order); be::dfree(u.d_mut); be::dfree(u.d_ctx); be::event_destroy(u.copied); }
+    delete h;
+    return 0;
+}
+
+int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
+{
+    if (!h || !m || !m->prior) return fail(DEMCMC_EINVAL, "null argument");
+    if (m->d != h->d) return fail(DEMCMC_EINVAL, "model.d %d != config.d %d", m->d, h->d);
+    BE(be::set_device(h->cfg.device));
+    for (void *p : h->model_allocs) be::dfree(p);
+    h->model_allocs.clear();
+    be::dfree(h->ll_part); h->ll_part = nullptr;
+    ModelDev &D = h->dmodel;
+    memset(&D, 0, sizeof D);
+    D.kind = m->kind; D.d = m->d; D.n_obs = m->n_obs; D.n_dim = m->n_dim; D.n_per = m->n_per; D.lba_floor = m->lba_floor;
+    auto upload = [&](const void *src, size_t bytes, bool on_dev) -> void * {
+        void *p = be::dmalloc(std::max<size_t>(bytes, 8));
+        if (!p) return nullptr;
+        h->model_allocs.push_back(p);
+        if (bytes && (on_dev ? be::d2d(p, src, bytes) : be::h2d(p, src, bytes))) return nullptr;
+        return p;
+    };
+    // parameter-count contract of each registered kernel
+    int want_d = -1;
+    switch (m->kind) {
+    case DEMCMC_GAUSSIAN: want_d = 2; break;
+    case DEMCMC_MVNORMAL: want_d = m->n_dim + 1; break;
+    case DEMCMC_BINOMIAL: want_d = 1; break;
+    case DEMCMC_LNR: want_d = m->n_dim + 1; break;
+    case DEMCMC_LBA: want_d = m->n_dim + 3; break;
+    case DEMCMC_HIER_NORMAL: want_d = m->n_dim + 3; break;
+    case DEMCMC_RASTRIGIN: want_d = m->d; break;
+    default: return fail(DEMCMC_EUNSUPPORTED, "no registered kernel for model kind %d: arbitrary closures are not supported and there is no CPU fallback", m->kind);
+    }
+    if (m->d != want_d) return fail(DEMCMC_EINVAL, "model kind %d expects d = %d, got %d", m->kind, want_d, m->d);
+    if (!m->x && m->kind != DEMCMC_RASTRIGIN) return fail(DEMCMC_EINVAL, "model data missing");
+    if ((m->kind == DEMCMC_LNR || m->kind == DEMCMC_LBA) && (!m->choice || m->n_dim < 2 || m->n_dim > MAX_ACC))
+        return fail(DEMCMC_EINVAL, "LNR/LBA need choices and 2..%d accumulators", MAX_ACC);
+    if (m->n_obs < 0) return fail(DEMCMC_EINVAL, "negative n_obs");
+
+    std::vector<Prior> pr(m->d);
+    for (int k = 0; k < m->d; ++k) {
+        pr[k].kind = m->prior[k].kind; pr[k].ref = m->prior[k].ref; pr[k].a = m->prior[k].a; pr[k].b = m->prior[k].b;
+        if (pr[k].kind < 0 || pr[k].kind > PRIOR_NORMAL_REF) return fail(DEMCMC_EUNSUPPORTED, "prior kind %d of parameter %d is not registered", pr[k].kind, k);
+        if (pr[k].kind == PRIOR_NORMAL_REF && (pr[k].ref < 0 || pr[k].ref >= m->d)) return fail(DEMCMC_EINVAL, "prior ref out of range");
+        if (pr[k].kind == PRIOR_NORMAL_REF) D.prior_has_ref = 1;
+        prior_constants(pr[k]);
+    }
+    D.prior = (const Prior *)upload(pr.data(), sizeof(Prior) * pr.size(), false);
+    if (!D.prior) return fail(DEMCMC_ENOMEM, "prior upload failed");
+    const bool dev = m->data_on_device != 0;
+    D.n_osplit = 1; D.n_ksplit = 1; D.split_len = 0; D.ksplit_len = 0;
+    if (m->kind == DEMCMC_RASTRIGIN) {
+        D.n_obs = 0;                                  // an objective of the parameters alone (optimize path)
+    } else if (m->kind == DEMCMC_BINOMIAL) {
+        double nk[2];
+        if (dev) { BE(be::d2h(nk, m->x, sizeof nk)); } else memcpy(nk, m->x, sizeof nk);
+        D.binom_N = nk[0]; D.binom_k = nk[1]; D.n_obs = 1;
+    } else if (m->kind == DEMCMC_MVNORMAL || m->kind == DEMCMC_HIER_NORMAL) {
+        // SSD layout: xT[k][ld]; MVN: k = dimension, obs = n_obs; hierarchical: k = subject, obs = n_per
+        D.ssd_k = m->n_dim;
+        D.ssd_n = m->kind == DEMCMC_MVNORMAL ? m->n_obs : m->n_per;
+        if (m->kind == DEMCMC_HIER_NORMAL) D.n_obs = (int64_t)m->n_dim * m->n_per;
+        D.ssd_ld = (D.ssd_n + SSD_TN - 1) / SSD_TN * SSD_TN;
+        if (D.ssd_ld == 0) D.ssd_ld = SSD_TN;
+        // dimension splits: balanced, at most SSD_KS dimensions (SSD_NJ DMMA k-steps) each
+        D.n_ksplit = (D.ssd_k + SSD_KS - 1) / SSD_KS;
+        D.ksplit_len = (D.ssd_k + D.n_ksplit - 1) / D.n_ksplit;
+        D.ssd_nj = (D.ksplit_len + 3) / 4;
+        D.n_osplit = 1; D.split_len = (int32_t)std::min<int64_t>(D.ssd_ld, INT32_MAX);
+        // fixed-point bits below the per-particle bound: the sum of one rounded term per
+        // (observation row, dimension split) must stay below 2^62
+        int64_t terms = D.ssd_ld * D.n_ksplit;
+        int lg = 0;
+        while (((int64_t)1 << lg) < terms) ++lg;
+        D.ssd_qbits = std::min(50, 62 - lg);
+        double *xT = (double *)be::dmalloc(sizeof(double) * std::max(be::pack_ssd_doubles(D), (size_t)D.ssd_k * D.ssd_ld));
+        double *center = (double *)be::dmalloc(sizeof(double) * (size_t)D.ssd_k);
+        if (!xT || !center) return fail(DEMCMC_ENOMEM, "data do not fit on the device");
+        h->model_allocs.push_back(xT);
+        h->model_allocs.push_back(center);
+        D.xT = xT;
+        D.center = center;
+        BE(be::launch_pack_ssd(m->x, dev, &D));       // centres and packs the data, fills D.ssd_xx / D.ssd_rowmax
+    } else {
+        D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
+        if (!D.x) return fail(DEMCMC_ENOMEM, "data upload failed");
+        if (m->choice) { D.choice = (const int32_t *)upload(m->choice, sizeof(int32_t) * m->n_obs, dev); if (!D.choice) return fail(DEMCMC_ENOMEM, "data upload failed"); }
+        if (m->sigma) { D.has_sigma = 1; for (int r = 0; r < m->n_dim && r < MAX_ACC; ++r) D.sigma_acc[r] = m->sigma[r]; }
+        const int64_t chunk = PW_THREADS;
+        const int64_t chunks = std::max<int64_t>(1, (m->n_obs + chunk - 1) / chunk);
+        const int64_t per = std::max<int64_t>(1, (chunks + 147) / 148);
+        D.split_len = (int32_t)(per * chunk);
+        D.n_osplit = (int32_t)std::max<int64_t>(1, (m->n_obs + D.split_len - 1) / D.split_len);
+    }
+    const size_t n_split = (size_t)D.n_osplit * D.n_ksplit;
+    h->ll_part = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, (size_t)h->P * n_split));
+    if (!h->ll_part) return fail(DEMCMC_ENOMEM, "partial-sum workspace does not fit");
+    BE(be::sync());
+    h->has_model = true;
+    return 0;
+}
+
+int demcmc_set_history(demcmc_handle *h, const double *rows)
+{
+    if (!h || !rows) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->n0 <= 0) return fail(DEMCMC_EINVAL, "the handle was created with n_initial = 0");
+    if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_history must come before the first run");
+    if (h->G_local != h->cfg.n_groups) return fail(DEMCMC_EUNSUPPORTED, "initial history rows of a sharded job");
+    BE(be::set_device(h->cfg.device));
+    if (int rc = grow_history(h, h->n0)) return rc;
+    const size_t P = h->P, d = h->d, n = (size_t)h->n0 * P;
+    // initialize_samples (utilities.jl:35-39): samples[i, :, p] by particle id; before any
+    // migration id == position, accept = false and lp = 0.0 (utilities.jl:18-20)
+    std::vector<int32_t> idv(n);
+    for (size_t i = 0; i < n; ++i) idv[i] = (int32_t)(i % P);
+    BE(be::h2d(h->hist_theta, rows, sizeof(double) * n * d));
+    BE(be::h2d(h->hist_id, idv.data(), sizeof(int32_t) * n));
+    if (h->hist_pos) BE(be::h2d(h->hist_pos, idv.data(), sizeof(int32_t) * n));
+    BE(be::dzero(h->hist_w, sizeof(double) * n));
+    BE(be::dzero(h->hist_acc, n));
+    BE(be::sync());
+    h->has_history = true;
+    return 0;
+}
+
+int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null argument");
+    if (!theta && !(h->n0 > 0 && h->has_history)) return fail(DEMCMC_EINVAL, "null theta (allowed only after demcmc_set_history: init_particle then starts from samples[1, :, id])");
+    if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model must come before set_state");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    // the current state moves to scratch row 0 (history rows already written stay as they are)
+    h->cur_hist = -1; h->cur_scratch = 0;
+    Row r = row_of(h, false, 0);
+    std::vector<int32_t> idv(P);
+    for (size_t p = 0; p < P; ++p) idv[p] = ids ? ids[p] : (int32_t)(h->cfg.group_begin * h->cfg.Np + p);
+    if (theta) BE(be::h2d(r.theta, theta, sizeof(double) * P * d));
+    else BE(be::d2d(r.theta, h->hist_theta, sizeof(double) * P * d));       // utilities.jl:15
+    BE(be::h2d(r.id, idv.data(), sizeof(int32_t) * P));
+    BE(be::dzero(r.acc, P));
+    BE(be::sync());
+    // init_particle (utilities.jl:13-22): weight through evaluate_fitness!
+    BE(be::launch_eval(h->dcfg, h->dmodel, r.theta, (int64_t)P, nullptr, nullptr, r.w, h->ll_part));
+    BE(be::sync());
+    h->has_state = true;
+    return 0;
+}
+
+static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
+{
+    if (!h || n_iter < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (!h->has_model || !h->has_state) return fail(DEMCMC_ESTATE, "set_model and set_state must come before run");
+    BE(be::set_device(h->cfg.device));
+    const demcmc_config &cfg = h->cfg;
+    const int Np = cfg.Np, Gt = cfg.n_groups, G = h->G_local, P = h->P, d = h->d, B = h->B;
+    const int64_t Pt = (int64_t)Gt * Np, S = n_iter * B;
+    const int64_t pbeg = (int64_t)cfg.group_begin * Np;
+    if (h->n0 > 0 && !h->has_history) return fail(DEMCMC_ESTATE, "n_initial > 0: demcmc_set_history must come before run");
+    if (cfg.donors && h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "sample = resample is not sharded over GPUs yet");
+    if (int rc = grow_history(h, h->n0 + h->iters_done + n_iter)) return rc;
+
+    // ---- replay: upload the local shard of the tape ------------------------------------------------
+    uint8_t *t_kind = nullptr, *t_keep = nullptr;
+    int32_t *t_idx = nullptr, *t_idx_row = nullptr;
+    double *t_g1 = nullptr, *t_g2 = nullptr, *t_uacc = nullptr, *t_noise = nullptr;
+    std::vector<uint8_t> hk;          // host copy of local kinds / idx for the planner
+    std::vector<int32_t> hi;
+    std::vector<void *> tmp;
+    auto cleanup = [&]() { for (void *p : tmp) be::dfree(p); tmp.clear(); };
+    if (tape) {
+        if (!tape->kind || !tape->idx || !tape->gamma1 || !tape->gamma2 || !tape->u_acc || !tape->noise)
+            return fail(DEMCMC_EINVAL, "tape misses a required array");
+        if (cfg.kappa != 1.0 && !tape->keep) return fail(DEMCMC_EINVAL, "kappa != 1 needs tape.keep");
+        if (Gt > 1 && (!tape->mig_n || !tape->mig_groups || !tape->mig_pick_u)) return fail(DEMCMC_EINVAL, "tape misses the migration arrays");
+        if (cfg.donors && !tape->idx_row) return fail(DEMCMC_EINVAL, "sample = resample needs tape.idx_row");
+        auto shard = [&](const void *src, size_t elem, size_t per_particle) -> void * {
+            // [S][Pt][per] -> [S][P][per]
+            const size_t rowb = elem * per_particle;
+            std::vector<uint8_t> buf((size_t)S * P * rowb);
+            for (int64_t s = 0; s < S; ++s)
+                memcpy(buf.data() + (size_t)s * P * rowb, (const uint8_t *)src + ((size_t)s * Pt + pbeg) * rowb, (size_t)P * rowb);
+            void *p = be::dmalloc(std::max<size_t>(8, buf.size()));
+            if (!p) return nullptr;
+            tmp.push_back(p);
+            if (!buf.empty() && (be::h2d(p, buf.data(), buf.size()) || be::sync())) return nullptr;
+            return p;
+        };
+        t_kind = (uint8_t *)shard(tape->kind, 1, 1);
+        t_idx = (int32_t *)shard(tape->idx, 4, 3);
+        if (cfg.donors) t_idx_row = (int32_t *)shard(tape->idx_row, 4, 3);
+        t_g1 = (double *)shard(tape->gamma1, 8, 1);
+        t_g2 = (double *)shard(tape->gamma2, 8, 1);
+        t_uacc = (double *)shard(tape->u_acc, 8, 1);
+        t_noise = (double *)shard(tape->noise, 8, d);
+        if (cfg.kappa != 1.0) t_keep = (uint8_t *)shard(tape->keep, 1, d);
+        if (!t_kind || !t_idx || (cfg.donors && !t_idx_row) || !t_g1 || !t_g2 || !t_uacc || !t_noise || (cfg.kappa != 1.0 && !t_keep)) { cleanup(); return fail(DEMCMC_ENOMEM, "tape upload failed: %s", be::last_error()); }
+        hk.resize((size_t)S * P); hi.resize((size_t)S * P * 3);
+        for (int64_t s = 0; s < S; ++s) {
+            memcpy(hk.data() + (size_t)s * P, tape->kind + (size_t)s * Pt + pbeg, P);
+            memcpy(hi.data() + (size_t)s * P * 3, tape->idx + ((size_t)s * Pt + pbeg) * 3, sizeof(int32_t) * P * 3);
+        }
+        for (size_t i = 0; i < hk.size(); ++i) if (hk[i] > KIND_MUTATION) { cleanup(); return fail(DEMCMC_EINVAL, "tape.kind[%zu] = %d", i, hk[i]); }
+        for (size_t i = 0; i < hi.size(); ++i) {
+            const uint8_t k = hk[i / 3];
+            if (k == KIND_MUTATION) continue;
+            const bool base = k == KIND_DE && i % 3 == 0;          // slot of the base particle in the group, or -1
+            if (base && hi[i] < 0) continue;
+            const int64_t lim = (cfg.donors && !base) ? Pt : Np;   // resample donors are particle ids
+            if (hi[i] < 0 || hi[i] >= lim) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx[%zu] = %d out of range", i, hi[i]); }
+            if (cfg.donors && !base) {
+                const int64_t sw = (int64_t)(i / 3) / P, pl = (int64_t)(i / 3) % P;
+                const int64_t ub = h->n0 + h->iters_done + sw / B;                            // rows 1:de.iter-1
+                const int32_t r = tape->idx_row[((size_t)sw * Pt + pbeg + pl) * 3 + i % 3];
+                if (r < 0 || r >= ub) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx_row of sweep %lld particle %lld = %d outside the %lld stored rows", (long long)sw, (long long)pl, r, (long long)ub); }
+            }
+        }
+    }
+
+    // ---- trace and migration log of this call ------------------------------------------------------
+    be::dfree(h->tr_theta); be::dfree(h->tr_w); be::dfree(h->tr_adj); be::dfree(h->tr_acc);
+    h->tr_theta = h->tr_w = h->tr_adj = nullptr; h->tr_acc = nullptr; h->tr_sweeps = 0;
+    if (cfg.trace && S > 0) {
+        h->tr_theta = (double *)be::dmalloc(sizeof(double) * S * P * d);
+        h->tr_w = (double *)be::dmalloc(sizeof(double) * S * P);
+        h->tr_adj = (double *)be::dmalloc(sizeof(double) * S * P);
+        h->tr_acc = (uint8_t *)be::dmalloc((size_t)S * P);
+        if (!h->tr_theta || !h->tr_w || !h->tr_adj || !h->tr_acc) { cleanup(); return fail(DEMCMC_ENOMEM, "trace buffers do not fit"); }
+        h->tr_sweeps = S;
+    }
+    be::dfree(h->d_mig_log); h->d_mig_log = nullptr; h->mig_log_iters = n_iter;
+    h->last_mig_slots.assign((size_t)std::max<int64_t>(1, n_iter) * Gt, -1);
+    std::vector<std::pair<int64_t, MigSchedule>> mig_events;      // iterations that migrated
+    if (n_iter > 0) {
+        h->d_mig_log = (int32_t *)be::dmalloc(sizeof(int32_t) * n_iter * MAX_MIG);
+        if (!h->d_mig_log) { cleanup(); return fail(DEMCMC_ENOMEM, "migration log"); }
+    }
+
+    const int64_t launches0 = be::launch_count();
+    int64_t n_levels = 0;
+    // timing events: one pair per chunk when the L2 flush is on; the likelihood launches get their
+    // own pairs after those
+    size_t tev_need = (h->flush_bytes ? 2 * (size_t)n_iter : 0), tev_ll0 = tev_need, tev_ll = 0, tev_chunks = 0;
+    if (h->time_loglik) tev_need += 2 * (size_t)S * 64;
+    while (h->tev.size() < tev_need) { void *e = be::tevent_create(); if (!e) { cleanup(); return fail(DEMCMC_ECUDA, "event pool: %s", be::last_error()); } h->tev.push_back(e); }
+    BE(be::timer_start());
+    ChunkPlan plans[be::MAX_LANES];
+    MigSchedule ms;
+
+    auto get_mig = [&](int64_t it, MigSchedule &out) {
+        out.migrate = false; out.n = 0; out.groups.clear(); out.u_pick.clear();
+        if (Gt < 2) return;
+        if (tape) {
+            out.n = tape->mig_n[it]; out.migrate = out.n > 0;
+            for (int i = 0; i < out.n; ++i) { out.groups.push_back(tape->mig_groups[it * Gt + i]); out.u_pick.push_back(tape->mig_pick_u[it * Gt + i]); }
+        } else {
+            plan_migration(cfg.seed, (uint32_t)(h->iters_done + it), Gt, cfg.alpha, out);
+        }
+    };
+    auto in_burnin_at = [&](int64_t it) { return h->iters_done + it + 1 + cfg.n_initial <= cfg.burnin; };   // de.iter <= burnin
+    // native select_base reads the sweep-start weights: such a sweep starts from a complete state
+    auto needs_snapshot = [&](int64_t it) { return !tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin_at(it); };
+
+    // runs `n_sw` consecutive sweeps starting at local iteration it0 (block b) as one chunk
+    auto run_chunk = [&](int64_t it0, int b, int n_sw) -> int {
+        const int64_t itg0 = h->iters_done + it0;
+        Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
+        if (u.armed) BE(be::event_wait(u.copied));             // the pinned slot is free once its copies ran
+        h->ring_use++;
+        bool basedep[MAX_CHUNK];
+        Row cur = cur_row(h);
+        for (int s = 0; s < n_sw; ++s) {
+            const int64_t it = it0 + (B == 1 ? s : 0), itg = itg0 + (B == 1 ? s : 0);
+            const int64_t s_local = it * B + b;
+            const bool inb = in_burnin_at(it);
+            basedep[s] = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && inb;
+            // destination row: the history row of the iteration on its last block, else scratch
+            Row next;
+            int next_scratch = -1;
+            if (b == B - 1) next = row_of(h, true, h->n0 + itg);
+            else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
+            SweepCtx &ctx = u.h_ctx[s];
+            memset(&ctx, 0, sizeof ctx);
+            ctx.sweep = (uint32_t)(itg * B + b); ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
+            ctx.exact_base = tape != nullptr;
+            ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
+            ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
+            ctx.mutate = u.d_mut + (size_t)s * G;
+            if (tape) {
+                ctx.t_kind = t_kind + (size_t)s_local * P; ctx.t_idx = t_idx + (size_t)s_local * P * 3;
+                ctx.t_g1 = t_g1 + (size_t)s_local * P; ctx.t_g2 = t_g2 + (size_t)s_local * P; ctx.t_uacc = t_uacc + (size_t)s_local * P;
+                ctx.t_noise = t_noise + (size_t)s_local * P * d; ctx.t_keep = t_keep ? t_keep + (size_t)s_local * P * d : nullptr;
+                ctx.t_idx_row = t_idx_row ? t_idx_row + (size_t)s_local * P * 3 : nullptr;
+            }
+            ctx.prop_theta = h->prop_theta; ctx.prop_prior = h->prop_prior; ctx.prop_adj = h->prop_adj; ctx.prop_inb = h->prop_inb; ctx.prop_msq = h->prop_msq;
+            ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
+            ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
+            // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)
+            ctx.hist_theta = h->hist_theta; ctx.hist_pos = h->hist_pos; ctx.donor_rows = h->n0 + itg;
+            ctx.next_pos = (b == B - 1 && h->hist_pos) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
+            if (h->tr_sweeps) {
+                ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
+                ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
+            }
+            if (b == B - 1) { h->cur_hist = h->n0 + itg; }
+            else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
+            cur = next;
+        }
+        // Lanes: the groups split into independent sets (groups never read each other between
+        // migrations), each planned on its own and launched as its own kernel chain on its own
+        // stream, so one lane's likelihood kernel runs while the other lane proposes / accepts.
+        const int n_lanes = (h->n_lanes > 1 && G >= 2 && !h->time_loglik) ? 2 : 1;
+        int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
+        std::vector<uint8_t> mut((size_t)n_sw * G, 0);
+        for (int ln = 0; ln < n_lanes; ++ln) {
+            const int g0 = ln == 0 ? 0 : (G + 1) / 2, g1 = (n_lanes == 1 || ln == 1) ? G : (G + 1) / 2;
+            PlanInput pin;
+            pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
+            pin.pos_offset = g0 * Np; pin.P_stride = P;
+            pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
+            const int64_t s_first = it0 * B + b;
+            pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
+            pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
+            plan_chunk(pin, (uint32_t)(itg0 * B + b), n_sw, basedep, plans[ln]);
+            const ChunkPlan &pl = plans[ln];
+            memcpy(u.h_order + lane_off[ln], pl.order.data(), sizeof(int32_t) * pl.order.size());
+            lane_off[ln + 1] = lane_off[ln] + (int32_t)pl.order.size();
+            for (int s2 = 0; s2 < n_sw; ++s2)
+                for (int g = g0; g < g1; ++g) mut[(size_t)s2 * G + g] = pl.mutate[(size_t)s2 * (g1 - g0) + (g - g0)];
+        }
+        memcpy(u.h_mut, mut.data(), mut.size());
+        BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * (size_t)n_sw * P));
+        BE(be::h2d(u.d_mut, u.h_mut, (size_t)n_sw * G));
+        BE(be::h2d(u.d_ctx, u.h_ctx, sizeof(SweepCtx) * (size_t)n_sw));
+        BE(be::event_record(u.copied));
+        u.armed = true;
+
+        if (needs_snapshot(it0)) {                               // n_sw == 1 here
+            bool any_cross = false;
+            for (int g = 0; g < G; ++g) any_cross |= mut[g] == 0;
+            if (any_cross) BE(be::launch_base_prep(h->dcfg, u.h_ctx[0].cur_w, h->base_th, h->base_cw, h->base_tot));
+        }
+        BE(be::lane_fork(n_lanes));
+        int max_levels = 0;
+        for (int ln = 0; ln < n_lanes; ++ln) max_levels = std::max(max_levels, plans[ln].n_levels);
+        int rc_launch = 0;
+        for (int l = 0; l < max_levels && !rc_launch; ++l)
+            for (int ln = 0; ln < n_lanes && !rc_launch; ++ln) {
+                const ChunkPlan &pl = plans[ln];
+                if (l >= pl.n_levels) continue;
+                Level lv;
+                lv.order = u.d_order + lane_off[ln] + pl.level_off[l];
+                lv.n = pl.level_off[l + 1] - pl.level_off[l];
+                lv.ctxs = u.d_ctx;
+                if (lv.n == 0) continue;
+                be::set_lane(ln);
+                const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+                if (be::launch_propose(h->dcfg, h->dmodel, lv) ||
+                    (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll])) ||
+                    be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc) ||
+                    (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])) ||
+                    be::launch_accept(h->dcfg, h->dmodel, lv)) rc_launch = 1;
+                if (tl) ++tev_ll;
+                ++n_levels;
+            }
+        be::set_lane(0);
+        if (rc_launch) return fail(DEMCMC_ECUDA, "level launch: %s", be::last_error());
+        BE(be::lane_join(n_lanes));
+        return 0;
+    };
+    // measurement mode: one timed segment = the migration (with its NCCL exchange) plus the chunk(s)
+    // that follow it; the L2 flush in front of the segment is outside the bracket
+    auto seg_begin = [&]() -> int {
+        if (!h->flush_bytes) return 0;
+        BE(be::dfill(h->flush_buf, (int)(tev_chunks & 1), (size_t)h->flush_bytes));
+        BE(be::event_record(h->tev[2 * tev_chunks]));
+        return 0;
+    };
+    auto seg_end = [&]() -> int {
+        if (!h->flush_bytes) return 0;
+        BE(be::event_record(h->tev[2 * tev_chunks + 1]));
+        ++tev_chunks;
+        return 0;
+    };
+
+    for (int64_t it = 0; it < n_iter;) {
+        if (int rc = seg_begin()) { cleanup(); return rc; }
+        // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
+        get_mig(it, ms);
+        if (ms.migrate) {
+            Row cur = cur_row(h);
+            if (ms.n < 2 || ms.n > Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration with %d groups", ms.n); }
+            MigArgs a;
+            memset(&a, 0, sizeof a);
+            a.n = ms.n;
+            bool cross = false, any_local = false;
+            std::vector<int> src(ms.n), dst(ms.n);
+            for (int i = 0; i < ms.n; ++i) {
+                a.groups[i] = ms.groups[i]; a.u_pick[i] = ms.u_pick[i];
+                if (a.groups[i] < 0 || a.groups[i] >= Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration group out of range"); }
+                dst[i] = h->group_owner[ms.groups[i]];
+                src[i] = h->group_owner[ms.groups[(i + ms.n - 1) % ms.n]];
+                cross |= src[i] != dst[i];
+                any_local |= dst[i] == h->rank;
+            }
+            if (any_local || cross) {
+                int32_t *picks = h->d_mig_log + it * MAX_MIG;
+                BE(be::launch_mig_pick(h->dcfg, a, cur.w, picks));
+                BE(be::launch_mig_gather(h->dcfg, a, picks, cur.theta, cur.w, cur.id, cur.acc, h->d_stage));
+                const double *incoming = h->d_stage;
+                if (cross) {
+                    if (!h->comm) { cleanup(); return fail(DEMCMC_ECOMM, "migration crosses ranks but demcmc_comm_init was not called"); }
+                    BE(be::d2d(h->d_stage_recv, h->d_stage, sizeof(double) * ms.n * (d + 3)));
+                    if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
+                    incoming = h->d_stage_recv;
+                }
+                BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc,
+                                          (h->hist_pos && h->cur_hist >= 0) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr));
+            }
+            mig_events.emplace_back(it, ms);
+        }
+
+        // ---- update! (main.jl:161-167) -------------------------------------------------------------
+        if (B > 1) {                                  // blocking: every block is one sweep, one chunk each
+            for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1)) { cleanup(); return rc; }
+            if (int rc = seg_end()) { cleanup(); return rc; }
+            ++it;
+            continue;
+        }
+        // consecutive iterations without a migration and without a sweep-start snapshot overlap on
+        // the device: plan them as one chunk (planner.h)
+        int n = 1;
+        if (!needs_snapshot(it) && h->max_chunk > 1 && !cfg.donors) {   // resample reads rows of earlier sweeps: one sweep per chunk
+            MigSchedule m2;
+            while (it + n < n_iter && n < h->max_chunk) {
+                get_mig(it + n, m2);
+                if (m2.migrate || needs_snapshot(it + n)) break;
+                ++n;
+            }
+        }
+        if (int rc = run_chunk(it, 0, n)) { cleanup(); return rc; }
+        if (int rc = seg_end()) { cleanup(); return rc; }
+        it += n;
+    }
+    double ms_dev = 0.0;
+    BE(be::timer_stop(&ms_dev));
+    BE(be::sync());
+    if (h->flush_bytes) {                                   // sum of the per-segment times (migration + chunk), flushes excluded
+        ms_dev = 0.0;
+        for (size_t c = 0; c < tev_chunks; ++c) { double t = 0.0; BE(be::tevent_elapsed(h->tev[2 * c], h->tev[2 * c + 1], &t)); ms_dev += t; }
+    }
+    double ms_ll = 0.0;
+    for (size_t i = 0; i < tev_ll; ++i) { double t = 0.0; BE(be::tevent_elapsed(h->tev[tev_ll0 + 2 * i], h->tev[tev_ll0 + 2 * i + 1], &t)); ms_ll += t; }
+    h->ctr.loglike_ms = ms_ll;
+    // migration log -> host
+    for (auto &ev : mig_events) {
+        std::vector<int32_t> picks(ev.second.n);
+        BE(be::d2h(picks.data(), h->d_mig_log + ev.first * MAX_MIG, sizeof(int32_t) * ev.second.n));
+        for (int i = 0; i < ev.second.n; ++i) h->last_mig_slots[ev.first * Gt + i] = picks[i];
+    }
+    cleanup();
+    h->iters_done += n_iter;
+    h->ctr.iterations += n_iter; h->ctr.sweeps += S; h->ctr.particle_updates += S * P; h->ctr.loglike_evals += S * P;
+    h->ctr.kernel_launches += be::launch_count() - launches0; h->ctr.levels += n_levels; h->ctr.device_ms = ms_dev;
+    return 0;
+}
+
+int demcmc_run(demcmc_handle *h, int64_t n_iter) { return run_impl(h, nullptr, n_iter); }
+int demcmc_replay(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
+{
+    if (!tape) return fail(DEMCMC_EINVAL, "null tape");
+    return run_impl(h, tape, n_iter);
+}
+
+static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *accept, int64_t n_rows)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (n_rows != h->iters_done + h->cfg.n_initial) return fail(DEMCMC_EINVAL, "n_rows %lld != iterations run %lld + n_initial", (long long)n_rows, (long long)h->iters_done);
+    if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "by-id history of a sharded job: gather demcmc_get_history_by_slot on the host");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    const int64_t n0 = h->cfg.n_initial;
+    double *ds = nullptr, *dl = nullptr; uint8_t *da = nullptr;
+    int rc = 0;
+    if (samples) ds = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P * d));
+    if (lp) dl = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * P));
+    const bool lp_written = h->cfg.update == DEMCMC_UPDATE_MH;     // maximize!/minimize! leave Particle.lp at 0.0
+    if (accept) da = (uint8_t *)be::dmalloc(std::max<size_t>(1, n_rows * P));
+    if ((samples && !ds) || (lp && !dl) || (accept && !da)) rc = fail(DEMCMC_ENOMEM, "output staging does not fit on the device");
+    if (!rc && n_rows > 0) {
+        if (ds && be::dzero(ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
+        if (dl && be::dzero(dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
+        if (da && be::dzero(da, n_rows * P)) rc = DEMCMC_ECUDA;
+        if (!rc && n0 + h->iters_done > 0 && (n0 == 0 || h->has_history) &&
+            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, n0 + h->iters_done, 0, n_rows, (int32_t)P, (int32_t)d,
+                                     h->cfg.group_begin * h->cfg.Np, ds, lp_written ? dl : nullptr, da)) rc = DEMCMC_ECUDA;
+        if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
+        if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
+        if (!rc && da && be::d2h(accept, da, n_rows * P)) rc = DEMCMC_ECUDA;
+        if (rc == DEMCMC_ECUDA) fail(rc, "history gather: %s", be::last_error());
+    }
+    be::dfree(ds); be::dfree(dl); be::dfree(da);
+    return rc;
+}
+
+int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, out, nullptr, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows) { return out ? history_out(h, nullptr, nullptr, out, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, nullptr, out, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
+
+int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
+{
+    if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n0 + h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)(h->n0 + h->iters_done));
+    if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "chains of a sharded job: gather demcmc_get_history_by_slot on the host");
+    if (!h->has_state) return fail(DEMCMC_ESTATE, "no state");
+    BE(be::set_device(h->cfg.device));
+    if (n_rows == 0) return 0;
+    const size_t P = h->P, d = h->d, n = (size_t)n_rows * P * (d + 2);
+    double *dout = (double *)be::dmalloc(sizeof(double) * n);
+    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * P);
+    int rc = 0;
+    if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging does not fit on the device");
+    if (!rc && (be::dzero(dout, sizeof(double) * n) ||
+                be::launch_chains(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, cur_row(h).id, pos, row0, n_rows, (int32_t)P, (int32_t)d,
+                                  h->cfg.group_begin * h->cfg.Np, dout) ||
+                be::d2h(out, dout, sizeof(double) * n)))
+        rc = fail(DEMCMC_ECUDA, "chain gather: %s", be::last_error());
+    be::dfree(dout); be::dfree(pos);
+    return rc;
+}
+
+int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, double *theta, double *w, int32_t *ids, uint8_t *acc)
+{
+    if (!h || row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range outside the iterations run");
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    if (n_rows == 0) return 0;
+    row0 += h->n0;                                           // rows of the iterations come after the n_initial rows
+    if (theta) BE(be::d2h(theta, h->hist_theta + row0 * P * d, sizeof(double) * n_rows * P * d));
+    if (w) BE(be::d2h(w, h->hist_w + row0 * P, sizeof(double) * n_rows * P));
+    if (ids) BE(be::d2h(ids, h->hist_id + row0 * P, sizeof(int32_t) * n_rows * P));
+    if (acc) BE(be::d2h(acc, h->hist_acc + row0 * P, n_rows * P));
+    return 0;
+}
+
+int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *ids)
+{
+    if (!h || !h->has_state) return fail(DEMCMC_ESTATE, "no state");
+    BE(be::set_device(h->cfg.device));
+    Row r = cur_row(h);
+    const size_t P = h->P, d = h->d;
+    if (theta) BE(be::d2h(theta, r.theta, sizeof(double) * P * d));
+    if (weight) BE(be::d2h(weight, r.w, sizeof(double) * P));
+    if (ids) BE(be::d2h(ids, r.id, sizeof(int32_t) * P));
+    return 0;
+}
+
+int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, double *log_adj, uint8_t *accepted)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (!h->tr_sweeps) return fail(DEMCMC_ESTATE, "no trace: create the handle with cfg.trace = 1 and run first");
+    BE(be::set_device(h->cfg.device));
+    const size_t n = (size_t)h->tr_sweeps * h->P;
+    if (prop_theta) BE(be::d2h(prop_theta, h->tr_theta, sizeof(double) * n * h->d));
+    if (prop_weight) BE(be::d2h(prop_weight, h->tr_w, sizeof(double) * n));
+    if (log_adj) BE(be::d2h(log_adj, h->tr_adj, sizeof(double) * n));
+    if (accepted) BE(be::d2h(accepted, h->tr_acc, n));
+    return 0;
+}
+
+int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
+{
+    if (!h || !slots) return fail(DEMCMC_EINVAL, "null argument");
+    memcpy(slots, h->last_mig_slots.data(), sizeof(int32_t) * (size_t)h->mig_log_iters * h->cfg.n_groups);
+    return 0;
+}
+
+int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_loglik)
+{
+    if (!h || l2_flush_bytes < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    BE(be::set_device(h->cfg.device));
+    be::dfree(h->flush_buf); h->flush_buf = nullptr; h->flush_bytes = 0;
+    if (l2_flush_bytes > 0) {
+        h->flush_buf = be::dmalloc((size_t)l2_flush_bytes);
+        if (!h->flush_buf) return fail(DEMCMC_ENOMEM, "flush buffer");
+        h->flush_bytes = l2_flush_bytes;
+    }
+    h->time_loglik = time_loglik != 0;
+    return 0;
+}
+
+int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps)
+{
+    if (!h || n_sweeps < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    h->max_chunk = std::min<int32_t>(n_sweeps, MAX_CHUNK);
+    return 0;
+}
+
+int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
+{
+    if (!h || n_lanes < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    h->n_lanes = std::min<int32_t>(n_lanes, be::MAX_LANES);
+    return 0;
+}
+
+int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out)
+{
+    if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
+    *out = h->ctr;
+    return 0;
+}
+
+int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior)
+{
+    if (!h || !theta || n < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model first");
+    BE(be::set_device(h->cfg.device));
+    if (n == 0) return 0;
+    const size_t d = h->d, ns = (size_t)h->dmodel.n_osplit * h->dmodel.n_ksplit;
+    double *dt = (double *)be::dmalloc(sizeof(double) * n * d), *dl = (double *)be::dmalloc(sizeof(double) * n),
+           *dp = (double *)be::dmalloc(sizeof(double) * n), *part = (double *)be::dmalloc(sizeof(double) * n * ns);
+    int rc = 0;
+    if (!dt || !dl || !dp || !part) rc = fail(DEMCMC_ENOMEM, "eval staging does not fit");
+    if (!rc && (be::h2d(dt, theta, sizeof(double) * n * d) || be::sync() ||
+                be::launch_eval(h->dcfg, h->dmodel, dt, n, dl, dp, nullptr, part) ||
+                (loglike && be::d2h(loglike, dl, sizeof(double) * n)) || (prior && be::d2h(prior, dp, sizeof(double) * n))))
+        rc = fail(DEMCMC_ECUDA, "eval: %s", be::last_error());
+    be::dfree(dt); be::dfree(dl); be::dfree(dp); be::dfree(part);
+    return rc;
+}
+
+
+int demcmc_op_project(int device, const double *p1, const double *p2, int32_t d, double *out)
+{
+    if (!p1 || !p2 || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(p1, d), *c = b.up(p2, d), *o = b.up<double>(nullptr, d);
+    if (!a || !c || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_project(a, c, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_reset(int device, const double *prop, const double *pt, const uint8_t *mask, int32_t d, double *out)
+{
+    if (!prop || !pt || !mask || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(prop, d), *c = b.up(pt, d), *o = b.up<double>(nullptr, d);
+    uint8_t *m = b.up(mask, d);
+    if (!a || !c || !o || !m) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_reset(a, c, m, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_de_proposal(int device, const double *pt, const double *pm, const double *pn, const double *pb,
+                          double g1, double g2, const double *bn, int32_t d, double *out)
+{
+    if (!pt || !pm || !pn || !bn || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *t = b.up(pt, d), *m = b.up(pm, d), *n = b.up(pn, d), *bb = pb ? b.up(pb, d) : nullptr, *nz = b.up(bn, d), *o = b.up<double>(nullptr, d);
+    if (!t || !m || !n || !nz || !o || (pb && !bb)) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_de(t, m, n, bb, g1, g2, nz, d, o));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    return 0;
+}
+
+int demcmc_op_snooker(int device, const double *pt, const double *pz, const double *pm, const double *pn,
+                      double g, const double *bn, int32_t d, double *out, double *log_adj)
+{
+    if (!pt || !pz || !pm || !pn || !bn || !out || d < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *t = b.up(pt, d), *z = b.up(pz, d), *m = b.up(pm, d), *n = b.up(pn, d), *nz = b.up(bn, d), *o = b.up<double>(nullptr, d), *la = b.up<double>(nullptr, 1);
+    if (!t || !z || !m || !n || !nz || !o || !la) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_snooker(t, z, m, n, g, nz, d, o, la));
+    BE(be::d2h(out, o, sizeof(double) * d));
+    if (log_adj) BE(be::d2h(log_adj, la, sizeof(double)));
+    return 0;
+}
+
+int demcmc_op_accept(int device, const double *w_prop, const double *w_cur, const double *log_adj, const double *u, int32_t n, uint8_t *out)
+{
+    if (!w_prop || !w_cur || !log_adj || !u || !out || n < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(w_prop, n), *c = b.up(w_cur, n), *l = b.up(log_adj, n), *uu = b.up(u, n);
+    uint8_t *o = b.up<uint8_t>(nullptr, n);
+    if (!a || !c || !l || !uu || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_accept(a, c, l, uu, n, o));
+    BE(be::d2h(out, o, n));
+    return 0;
+}
+
+int demcmc_op_select(int device, const double *w, int32_t n, double u, int32_t *base_idx, int32_t *migrate_idx)
+{
+    if (!w || n < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (int rc = op_begin(device)) return rc;
+    DevBuf b;
+    double *a = b.up(w, n);
+    int32_t *o = b.up<int32_t>(nullptr, 2);
+    if (!a || !o) return fail(DEMCMC_ENOMEM, "alloc");
+    BE(be::sync());
+    BE(be::launch_op_select(a, n, u, o, o + 1));
+    int32_t r[2];
+    BE(be::d2h(r, o, sizeof r));
+    if (base_idx) *base_idx = r[0];
+    if (migrate_idx) *migrate_idx = r[1];
+    return 0;
+}
+
+int demcmc_comm_unique_id(uint8_t id[128])
+{
+    if (!id) return fail(DEMCMC_EINVAL, "null id");
+    if (be::comm_unique_id(id)) return fail(DEMCMC_ECOMM, "%s", be::last_error());
+    return 0;
+}
+
+int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int32_t n_ranks)
+{
+    if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(DEMCMC_EINVAL, "bad argument");
+    const int Gt = h->cfg.n_groups;
+    if (Gt % n_ranks) return fail(DEMCMC_EINVAL, "n_groups %d is not a multiple of the %d ranks", Gt, n_ranks);
+    const int per = Gt / n_ranks;
+    if (h->cfg.group_begin != rank * per || h->G_local != per) return fail(DEMCMC_EINVAL, "handle holds groups [%d,%d) but rank %d of %d must hold [%d,%d)", h->cfg.group_begin, h->cfg.group_begin + h->G_local, rank, n_ranks, rank * per, rank * per + per);
+    BE(be::set_device(h->cfg.device));
+    if (n_ranks > 1 && be::comm_init(id, rank, n_ranks, &h->comm)) return fail(DEMCMC_ECOMM, "%s", be::last_error());
+    h->rank = rank; h->n_ranks = n_ranks;
+    for (int g = 0; g < Gt; ++g) h->group_owner[g] = g / per;
+    return 0;
+}
+
+int demcmc_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::fp64_peak(tflops));
+    return 0;
+}
+
+int demcmc_fp64_peaks(int device, double *dfma_tflops, double *dmma_tflops)
+{
+    if (!dfma_tflops && !dmma_tflops) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::fp64_peaks(dfma_tflops, dmma_tflops));
+    return 0;
+}
+
+int demcmc_copy_peak(int device, double *gbs)
+{
+    if (!gbs) return fail(DEMCMC_EINVAL, "null out");
+    if (int rc = op_begin(device)) return rc;
+    BE(be::copy_peak(gbs));
+    return 0;
+}
+
+} // extern "C"

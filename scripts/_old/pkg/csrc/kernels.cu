@@ -18,7 +18,6 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "backend.h"
@@ -97,10 +96,8 @@ static unsigned long long *tl_slot()
     }
     return (g_tl_cap > 0 && g_tl_level < g_tl_cap) ? g_tl + (size_t)TL_WORDS * g_tl_level : nullptr;
 }
-static void pk_timeline_dump();
 void timeline_dump()
 {
-    pk_timeline_dump();
     if (g_tl_cap <= 0 || !g_tl) return;
     const char *path = getenv("DEMCMC_TIMELINE_FILE");
     if (!path) return;
@@ -236,48 +233,9 @@ void hfree_pinned(void *p)
     cudaFreeHost(p);
 }
 int h2d(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream())); return 0; }
-// Large downloads (the chains of a run: hundreds of MB into a freshly allocated, never-touched
-// caller buffer) do not go through the driver's pageable path -- measured on the B200 box it takes
-// anything from 57 ms to 2.2 s for the same 217 MB, depending on how the destination pages fault.
-// They are pipelined through two pinned staging blocks instead: chunk c+1 crosses PCIe while four
-// host threads copy chunk c into the caller's pages (the first touch of those pages is the cost).
-static int d2h_staged(void *dst, const void *src, size_t bytes)
-{
-    constexpr size_t CHUNK = (size_t)16 << 20;
-    constexpr int NT = 4;
-    static void *stage[64][2] = { { nullptr } };
-    static cudaEvent_t done[64][2] = { { nullptr } };
-    for (int b = 0; b < 2; ++b) {
-        if (!stage[g_dev][b]) CU(cudaMallocHost(&stage[g_dev][b], CHUNK));
-        if (!done[g_dev][b]) CU(cudaEventCreateWithFlags(&done[g_dev][b], cudaEventDisableTiming));
-    }
-    const size_t n_chunks = (bytes + CHUNK - 1) / CHUNK;
-    auto issue = [&](size_t c) -> cudaError_t {
-        const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
-        cudaError_t e = cudaMemcpyAsync(stage[g_dev][c & 1], (const char *)src + off, len, cudaMemcpyDeviceToHost, stream());
-        return e != cudaSuccess ? e : cudaEventRecord(done[g_dev][c & 1], stream());
-    };
-    CU(issue(0));
-    for (size_t c = 0; c < n_chunks; ++c) {
-        CU(cudaEventSynchronize(done[g_dev][c & 1]));
-        if (c + 1 < n_chunks) CU(issue(c + 1));                  // the other block: its host copy finished last round
-        const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
-        const char *from = (const char *)stage[g_dev][c & 1];
-        char *to = (char *)dst + off;
-        std::thread th[NT];
-        const size_t part = ((len / NT) + 4095) & ~(size_t)4095;
-        for (int t = 0; t < NT; ++t) {
-            const size_t o = std::min(len, (size_t)t * part), l = std::min(part, len - o);
-            th[t] = std::thread([=]() { if (l) memcpy(to + o, from + o, l); });
-        }
-        for (int t = 0; t < NT; ++t) th[t].join();
-    }
-    return 0;
-}
 int d2h(void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return 0;
-    if (bytes >= ((size_t)32 << 20)) return d2h_staged(dst, src, bytes);
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
     CU(cudaStreamSynchronize(stream()));
     return 0;
@@ -672,45 +630,31 @@ static XdStage *xd_stage(const ModelDev &m, int n)
 // n_hi tiles of oct_hi octets with c_hi CTAs each, then n_lo tiles of oct_lo octets with c_lo CTAs each
 struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
 
-// Where one warp of k_xdot / k_chunk_persist keeps its operand ring: the warp's index inside its
-// 4-warp CTA (= the row pair it owns), the dimension split, the ring and its `full` barriers, and the
-// number of stages it has consumed so far (the barriers are initialised once per kernel; stage and
-// phase parity follow from the running count, so the persistent kernel carries the ring from one
-// item to the next without re-initialising anything).
-struct XdWarp { int warp, ks; double *ring; uint64_t *full; uint32_t it_base; };
-
-// NJC: the model's k-steps when known at compile time (13), else 0; HALF: (with NJC) the last k-step is
-// a half step (de_types.h: ssd_half); STAGES: depth of the warp's operand ring.
-// bsrc / b_oct_stride: the tile's B fragments [octet][k-step][lane] (global staging buffer, or the
-// shared-memory copy the persistent kernel's helper warp made); msrc: its 8 magic constants per octet.
-// HOOKS: operator()() = wait until the means may be read; after_loads() = they are in registers;
-// item_end() = the tile's cross terms have been added to ll_acc.
-template <int NOCT, int NJC, bool HALF, int STAGES, class HOOKS>
-__device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc, size_t b_oct_stride, const double *msrc, const Level &lv,
-                                          long long *ll_acc, int oct0, int T0, int T1, XdWarp &xw, const HOOKS &dependency_wait,
-                                          unsigned long long *tl, unsigned long long *tlc)
+template <int NOCT, int NJC>            // NJC: the model's k-steps when known at compile time (13), else 0
+__device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bfrag, const double *magic, const Level &lv,
+                                          long long *ll_acc, int oct0, int T0, int T1, unsigned char *smem_raw, unsigned long long *tl, unsigned long long *tlc)
 {
-    const int tid = threadIdx.x, warp = xw.warp, lane = tid & 31, ks = xw.ks;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ks = blockIdx.y;
     const int nj = NJC ? NJC : m.ssd_nj;
-    const bool half = NJC ? HALF : (m.ssd_half != 0);
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const uint32_t stage_doubles = (uint32_t)nj * 64, stage_bytes = stage_doubles * (uint32_t)sizeof(double);
-    double *ring = xw.ring;
-    uint64_t *full = xw.full;
-    const uint32_t it_base = xw.it_base;
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
     const double *src = m.xT + (((size_t)(ks * 4 + warp) * n_tiles + T0) * nj) * 64;
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s)
+        for (int s = 0; s < XD_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < XD_STAGES; ++s)
             if (T0 + s < T1) {
-                const uint32_t st = (it_base + (uint32_t)s) % STAGES;
-                mbar_expect_tx(&full[st], stage_bytes);
-                bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)s * stage_doubles, stage_bytes, &full[st]);
+                mbar_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(ring + (size_t)s * stage_doubles, src + (size_t)s * stage_doubles, stage_bytes, &full[s]);
             }
     }
     __syncwarp();
-    dependency_wait();                                       // the packed data are constant; the means are not
+    pdl_wait();                                              // the packed data are constant; the means are not
     if (tid == 0) tl_max(tl, TL_XWAIT);
     if (tlc && tid == 0 && blockIdx.x < TL_CTA_MAX) { tlc[blockIdx.x * 4 + 1] = gtime(); tlc[blockIdx.x * 4 + 3] = (unsigned long long)(T1 - T0) * 10 + NOCT; }
 
@@ -719,11 +663,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     {
 #pragma unroll
         for (int pt = 0; pt < NOCT; ++pt) {
-            // a half step's B fragment repeats its two means in rows 2-3 (de_types.h: ssd_half): the staged
-            // fragment holds them once, lanes of rows 2-3 read the slots of rows 0-1
-            const double *bf = bsrc + (size_t)pt * b_oct_stride;
+            const double *bf = bfrag + (((size_t)(oct0 + pt) * m.n_ksplit + ks) * nj) * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? bf[j * 32 + ((half && j == nj - 1) ? (lane & ~2) : lane)] : 0.0;
+            for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? bf[j * 32] : 0.0;
         }
     }
     double mg[NOCT][2];
@@ -737,11 +679,10 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            mg[pt][e] = msrc[pt * SSD_OCT + 2 * (lane & 3) + e];
+            mg[pt][e] = magic[(size_t)(oct0 + pt) * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
             accA[pt][e] = 0.0; accB[pt][e] = 0.0;
         }
-    dependency_wait.after_loads();
     auto convert = [&](double (&acc)[NOCT][2]) {
 #pragma unroll
         for (int pt = 0; pt < NOCT; ++pt)
@@ -754,9 +695,8 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     // one observation tile: its DMMAs go to `acc`; `prev` (the other set) is converted after the
     // first k-step when it holds the previous tile
     auto tile = [&](int t, double (&acc)[NOCT][2], double (&prev)[NOCT][2], bool have_prev) {
-        const int it = t - T0;
-        const uint32_t gi = it_base + (uint32_t)it, st = gi % STAGES;
-        mbar_wait(&full[st], (gi / STAGES) & 1u);
+        const int it = t - T0, st = it & (XD_STAGES - 1);
+        mbar_wait(&full[st], (uint32_t)(it / XD_STAGES) & 1u);
         if (tl && tid == 0 && t == T0) tl_max(tl, TL_XFIRST);
         const double2 *xa = reinterpret_cast<const double2 *>(ring + (size_t)st * stage_doubles) + lane;
         double2 a = xa[0];
@@ -767,17 +707,15 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
             if (j + 1 < nj) an = xa[(j + 1) * 32];
 #pragma unroll
             for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.x, b[j][pt]);
-            if (!(half && j == nj - 1)) {
 #pragma unroll
-                for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
-            }
+            for (int pt = 0; pt < NOCT; ++pt) dmma884(acc[pt][0], acc[pt][1], a.y, b[j][pt]);
             a = an;
             if (j == 0 && have_prev) convert(prev);
         }
         __syncwarp();                                        // every lane's reads of the stage have landed
-        if (lane == 0 && t + STAGES < T1) {
+        if (lane == 0 && t + XD_STAGES < T1) {
             mbar_expect_tx(&full[st], stage_bytes);
-            bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + STAGES) * stage_doubles, stage_bytes, &full[st]);
+            bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + XD_STAGES) * stage_doubles, stage_bytes, &full[st]);
         }
     };
     int t = T0;
@@ -807,16 +745,8 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
                 atomicAdd(reinterpret_cast<unsigned long long *>(ll_acc) + p, v);
             }
         }
-    dependency_wait.item_end();
     if (tid == 0) tl_max(tl, TL_X1);
-    xw.it_base = it_base + (uint32_t)(T1 - T0);
 }
-
-struct PdlWait {
-    __device__ __forceinline__ void operator()() const { pdl_wait(); }
-    __device__ __forceinline__ void after_loads() const {}
-    __device__ __forceinline__ void item_end() const {}
-};
 
 __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
                                                                      long long *ll_acc, XdGrid g, unsigned long long *tl, unsigned long long *tlc)
@@ -831,27 +761,11 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
     const int T0 = (int)((int64_t)c_in * n_tiles / C), T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
     if (T1 <= T0) { pdl_wait(); return; }
-    const int warp = threadIdx.x >> 5;
-    const uint32_t stage_doubles = (uint32_t)m.ssd_nj * 64;
-    XdWarp xw;
-    xw.warp = warp; xw.ks = blockIdx.y; xw.it_base = 0;
-    xw.ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
-    xw.full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int s = 0; s < XD_STAGES; ++s) mbar_init(&xw.full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    const PdlWait wait;
-    const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + blockIdx.y) * m.ssd_nj) * 32, *msrc = magic + (size_t)oct0 * SSD_OCT;
-    const size_t bstride = (size_t)m.n_ksplit * m.ssd_nj * 32;
-#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
-    if (m.ssd_nj == SSD_NJ && m.ssd_half) {
-        switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
-    } else if (m.ssd_nj == SSD_NJ) {
-        switch (noct) { case 4: XD_CALL(4, SSD_NJ, false); break; case 3: XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
+#define XD_CALL(NO, NJC) xdot_body<NO, NJC>(m, bfrag, magic, lv, ll_acc, oct0, T0, T1, smem_raw, tl, tlc)
+    if (m.ssd_nj == SSD_NJ) {
+        switch (noct) { case 4: XD_CALL(4, SSD_NJ); break; case 3: XD_CALL(3, SSD_NJ); break; case 2: XD_CALL(2, SSD_NJ); break; default: XD_CALL(1, SSD_NJ); break; }
     } else {
-        switch (noct) { case 4: XD_CALL(4, 0, false); break; case 3: XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
+        switch (noct) { case 4: XD_CALL(4, 0); break; case 3: XD_CALL(3, 0); break; case 2: XD_CALL(2, 0); break; default: XD_CALL(1, 0); break; }
     }
 #undef XD_CALL
 }
@@ -920,509 +834,6 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// The persistent chunk kernel: ALL levels of a chunk (up to 16 overlapped sweeps) in ONE launch,
-// one CTA per SM, warp-specialised, no kernel boundary and no host involvement between levels.
-//   warps 0-7   two "virtual CTAs" of k_xdot (4 warps each, same private TMA rings, same inner loop);
-//               virtual CTA v walks the levels in order and takes the items (particle tile x
-//               observation range x dimension split) v, v + 2*gridDim, ... of each
-//   warps 8-9   scalar warps: one particle update at a time -- proposal (the body of k_propose) and,
-//               once the update's likelihood has arrived, the Metropolis accept (the body of k_accept)
-// Dependencies are counters in global memory (release on arrive, acquire on poll):
-//   prop_done[tile]   proposals of a particle tile staged          -> its DMMA items may start
-//   xdot_done[tile]   warps that have added their share to ll_acc  -> its accepts may start
-//   acc_done[level]   accepts finished                             -> proposals of levels that depend on it
-// Every level names the level its proposals wait for (`dep`): the previous level of the same lane.
-// With two lanes (independent sets of groups) the levels of the lanes alternate, so the DMMA warps
-// work on one lane while the scalar warps accept / propose the other: the tensor pipe never waits
-// for the scalar part of the step.  The staging buffers of the means alternate between two copies
-// (level parity), guarded by acc_done[level - 2].
-// Deadlock freedom: every wait is on work that comes EARLIER in every warp's own program order
-// (levels are walked in order by all warps; an accept waits for DMMA items of its own level, those
-// wait for proposals of that level, those for accepts of earlier levels), and the launch is one CTA
-// per SM, so all CTAs are resident.  A wait that lasts 20 s traps instead of hanging the device.
-// ------------------------------------------------------------------------------------------------
-constexpr int PK_MAX_LEVELS = 192;
-constexpr int PK_MAX_TILES = 8192;
-constexpr int PK_WARPS = 16;                    // per CTA: 4 per SM sub-partition, 128 registers each at launch
-constexpr int PK_THREADS = PK_WARPS * 32;
-constexpr int PK_REGS_DMMA = 216, PK_REGS_HELPER = 56, PK_REGS_IDLE = 24;   // per sub-partition 2 * 216 + 56 + 24 = 512 = 4 * 128, the launch allocation
-constexpr int PK_SCALAR_CTAS = 6;               // CTAs (SMs) given to the scalar warps: 96 warps, one update each per level of ~100
-
-struct PLevel { int32_t order_off, n, n_items, dep, tile_base, pad; XdGrid g; };
-struct PChunk {
-    int32_t n_levels, lag, n_scalar_ctas;
-    const int32_t *order;
-    const SweepCtx *ctxs;
-    int32_t *acc_done, *prop_done, *xdot_done;       // zeroed before the launch
-    double *bfrag[2], *magic[2];
-    long long *ll_acc;
-    unsigned long long *tl;                          // debug timeline [level][PT_WORDS] or nullptr
-    PLevel lv[PK_MAX_LEVELS];
-};
-
-// particle tile of an octet / of a launch index, as k_xdot deals them (XdGrid)
-__host__ __device__ __forceinline__ void xd_tile_of_octet(const XdGrid &g, int oct, int &tile, int &oct0, int &noct)
-{
-    const int nh = g.n_hi * g.oct_hi;
-    if (oct < nh) { tile = oct / g.oct_hi; oct0 = tile * g.oct_hi; noct = g.oct_hi; }
-    else { const int t = (oct - nh) / g.oct_lo; tile = g.n_hi + t; oct0 = nh + t * g.oct_lo; noct = g.oct_lo; }
-}
-__host__ __device__ __forceinline__ int xd_tile_ctas(const XdGrid &g, int tile) { return tile < g.n_hi ? g.c_hi : g.c_lo; }
-
-__device__ __forceinline__ int ld_acquire(const int32_t *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void wait_ge(const int32_t *ctr, int target)
-{
-    if (ld_acquire(ctr) >= target) return;
-    const unsigned long long t0 = gtime();
-    unsigned ns = 64;
-    while (ld_acquire(ctr) < target) {
-        __nanosleep(ns);
-        if (ns < 256) ns += 64;
-        if (gtime() - t0 > 20000000000ull) __trap();
-    }
-}
-// every lane has fenced its own writes before lane 0 publishes
-__device__ __forceinline__ void arrive(int32_t *ctr)
-{
-    __threadfence();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(ctr) : "memory");
-}
-
-// the scalar warps are few (96) and sit on the critical path of a level: they poll without back-off
-__device__ __forceinline__ void wait_ge_fast(const int32_t *ctr, int target)
-{
-    if (ld_acquire(ctr) >= target) return;
-    const unsigned long long t0 = gtime();
-    while (ld_acquire(ctr) < target) {
-        __nanosleep(20);
-        if (gtime() - t0 > 20000000000ull) __trap();
-    }
-}
-struct FlagWait {
-    const int32_t *c0; int t0; const int32_t *c1; int t1;
-    unsigned long long *tl; int w_min, w_max;            // debug timeline: stamp when the wait is over
-    mutable unsigned long long t_done;
-    __device__ __forceinline__ void operator()() const
-    {
-        if (c0) wait_ge_fast(c0, t0);
-        if (c1) wait_ge_fast(c1, t1);
-        if (tl) {
-            t_done = gtime();
-            if ((threadIdx.x & 31) == 0) { if (w_min >= 0) atomicMax(tl + w_min, ~t_done); if (w_max >= 0) atomicMax(tl + w_max, t_done); }
-        }
-    }
-};
-// per level: stamps (min stored complemented) and, summed over the DMMA warps, the nanoseconds spent
-// waiting for the proposals, in the item (B fragments, DMMA loop, flush) and in the arrive
-enum { PT_P0 = 0, PT_PW, PT_P1, PT_XW0, PT_XW1, PT_X1, PT_AW0, PT_A1, PT_SUM_WAIT, PT_SUM_ITEM, PT_SUM_ARRIVE, PT_ITEMS,
-       PT_S_PRE, PT_S_BODY, PT_S_STAGE, PT_S_ARR, PT_S_N, PT_A_BODY, PT_A_ARR, PT_A_N, PT_WORDS = 24 };
-// DMMA warps.  (Deferring the arrive of the previous item behind this item's B-fragment loads was
-// tried: carrying the pending counter across items makes ptxas drop the raised register budget of
-// the setmaxnreg region -- 125 registers and B fragments reloaded from local memory inside the
-// DMMA loop.  scripts/regcheck.sh prints the highest register the kernel uses; keep it near 230.)
-template <bool TL>
-struct DmmaWait {
-    const int32_t *c0; int t0;
-    unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
-    __device__ __forceinline__ void operator()() const
-    {
-        wait_ge(c0, t0);
-        if (TL && tl) {
-            t_done = gtime();
-            if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
-        }
-    }
-    __device__ __forceinline__ void after_loads() const {}
-};
-struct FlagLanes : WarpLanes {
-    FlagWait w;
-    __device__ __forceinline__ void dependency_wait() const { w(); }
-};
-// a proposal whose dependency wait first runs the warp's own pending accepts: the state-independent
-// prologue of the proposal (Philox plan, noise, bounds, prior specs) is then over before the
-// likelihood of the level it waits for has even arrived
-template <class PENDING>
-struct ProposeLanes : WarpLanes {
-    const PENDING &pending; FlagWait w;
-    __device__ __forceinline__ ProposeLanes(const PENDING &p, const FlagWait &fw) : pending(p), w(fw) {}
-    __device__ __forceinline__ void dependency_wait() const { pending(); w(); }
-};
-
-// one item of a level: (dimension split, particle tile, observation-tile range), as k_xdot's grid deals them
-struct PkItem { int ks, tile, oct0, noct, T0, T1, n_in_tile; };
-__device__ __forceinline__ PkItem pk_item(const PLevel &pl, int n_tiles, int q)
-{
-    PkItem it;
-    const XdGrid &g = pl.g;
-    it.ks = q / pl.n_items;
-    const int bx = q - it.ks * pl.n_items;
-    int c_in, C;
-    const int n_in_hi = g.n_hi * g.c_hi;
-    if (bx < n_in_hi) { it.tile = bx / g.c_hi; c_in = bx - it.tile * g.c_hi; C = g.c_hi; it.noct = g.oct_hi; it.oct0 = it.tile * g.oct_hi; }
-    else { const int r = bx - n_in_hi, t = r / g.c_lo; it.tile = g.n_hi + t; c_in = r - t * g.c_lo; C = g.c_lo; it.noct = g.oct_lo; it.oct0 = g.n_hi * g.oct_hi + t * g.oct_lo; }
-    it.T0 = (int)((int64_t)c_in * n_tiles / C); it.T1 = (int)((int64_t)(c_in + 1) * n_tiles / C);
-    it.n_in_tile = min(pl.n, (it.oct0 + it.noct) * SSD_OCT) - it.oct0 * SSD_OCT;
-    return it;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// what the DMMA warps of a virtual CTA see of an item: the helper warp's shared-memory copy of the
-// tile's B fragments (b_full), and the two signals back to it (b_empty: the copy is in registers;
-// item_done: the cross terms are in ll_acc)
-template <bool TL>
-struct VctaHooks {
-    uint64_t *b_full, *b_empty, *item_done;
-    uint32_t parity;
-    unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
-    __device__ __forceinline__ void operator()() const
-    {
-        mbar_wait(b_full, parity);
-        if (TL && tl) {
-            t_done = gtime();
-            if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
-        }
-    }
-    __device__ __forceinline__ void after_loads() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }
-    __device__ __forceinline__ void item_end() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(item_done); }
-};
-
-constexpr int PK_STAGES = 3;                    // ring depth of the persistent kernel (the fourth stage's memory holds the B copies)
-static size_t pk_bbuf_doubles(int nj) { return (size_t)4 * nj * 32 + 4 * SSD_OCT; }
-static size_t pk_smem_bytes(int nj)
-{
-    return sizeof(double) * ((size_t)8 * PK_STAGES * nj * 64 + 2 * pk_bbuf_doubles(nj)) + sizeof(uint64_t) * (8 * PK_STAGES + 6);
-}
-
-template <bool TL>
-__global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_constant__ ConfigDev cfg, const __grid_constant__ ModelDev m,
-                                                                 const __grid_constant__ PChunk ck)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Roles.  The scalar part of the step (Philox, pow/log/exp, priors) runs on the same fp64 pipe as
-    // DMMA: next to two DMMA warps a scalar warp's dependent fp64 chain takes 3-4x as long (measured:
-    // 26 us instead of 8 per proposal).  So the last n_scalar_ctas CTAs are scalar-only (16 warps at
-    // the launch's 128 registers).  In the DMMA CTAs warps 0-7 are the two virtual CTAs (setmaxnreg:
-    // 216 registers each), warps 8 and 9 are their HELPERS (56 registers): a helper polls the
-    // proposal counter of its virtual CTA's next item, copies that tile's B fragments and magic
-    // constants into shared memory while the DMMA warps are still in the previous item, and
-    // publishes a finished item (fence + xdot_done) on their behalf -- so the DMMA warps never touch
-    // a global flag, never wait on an L2 round trip for their operands and never stall in a fence.
-    // Warps 10-15 give their registers back and leave.
-    const int n_dmma_ctas = (int)gridDim.x - ck.n_scalar_ctas;
-    const bool scalar_cta = (int)blockIdx.x >= n_dmma_ctas;
-    const int nj = m.ssd_nj;
-    const uint32_t stage_doubles = (uint32_t)nj * 64;
-    double *const ring0 = reinterpret_cast<double *>(smem_raw);
-    double *const bbuf0 = ring0 + (size_t)8 * PK_STAGES * stage_doubles;
-    const size_t bbuf_doubles = (size_t)4 * nj * 32 + 4 * SSD_OCT;
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(bbuf0 + 2 * bbuf_doubles);     // full[8][PK_STAGES], then per virtual CTA b_full, b_empty, item_done
-    uint64_t *const vbars = bars + 8 * PK_STAGES;
-    if (!scalar_cta) {
-        if (threadIdx.x == 0) {
-            for (int vc = 0; vc < 2; ++vc) { mbar_init(&vbars[vc * 3 + 0], 1); mbar_init(&vbars[vc * 3 + 1], 4); mbar_init(&vbars[vc * 3 + 2], 4); }
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
-        __syncthreads();                                         // the only CTA-wide barrier: before any warp leaves
-    }
-    const int n_tiles = (int)(m.ssd_ld / SSD_TN);
-    if (!scalar_cta && warp >= 8) {
-        if (warp >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_IDLE)); return; }
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_HELPER));
-        if (warp >= 10) return;
-        // ---- helper warp of virtual CTA vc ----------------------------------------------------------
-        const int vc = warp - 8, v = blockIdx.x * 2 + vc, NV = n_dmma_ctas * 2;
-        double *const bbuf = bbuf0 + (size_t)vc * bbuf_doubles, *const mbuf = bbuf + (size_t)4 * nj * 32;
-        uint64_t *const b_full = &vbars[vc * 3 + 0], *const b_empty = &vbars[vc * 3 + 1], *const item_done = &vbars[vc * 3 + 2];
-        uint32_t n = 0;                                          // items handed to the DMMA warps so far
-        int32_t *prev_ctr = nullptr;                             // xdot_done counter of the item they are working on
-        auto publish = [&](int32_t *ctr) {
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 4;\n" ::"l"(ctr) : "memory");
-        };
-        for (int L = 0; L < ck.n_levels; ++L) {
-            const PLevel &pl = ck.lv[L];
-            const int total = pl.n_items * m.n_ksplit;
-            for (int q = v; q < total; q += NV) {
-                const PkItem it = pk_item(pl, n_tiles, q);
-                int32_t *ctr = ck.xdot_done + pl.tile_base + it.tile;
-                if (it.T1 <= it.T0) { publish(ctr); continue; }  // (k_xdot's grids never deal an empty range)
-                const int32_t *flag = ck.prop_done + pl.tile_base + it.tile;
-                const double *bsrc = ck.bfrag[L & 1] + (((size_t)it.oct0 * m.n_ksplit + it.ks) * nj) * 32;
-                const double *msrc = ck.magic[L & 1] + (size_t)it.oct0 * SSD_OCT;
-                const size_t bstride = (size_t)m.n_ksplit * nj * 32;
-                bool filled = false;
-                const unsigned long long t0 = gtime();
-                while (prev_ctr || !filled) {
-                    if (prev_ctr && mbar_try_wait(item_done, (n - 1) & 1u)) { publish(prev_ctr); prev_ctr = nullptr; }
-                    if (!filled && (n == 0 || mbar_try_wait(b_empty, (n - 1) & 1u)) && ld_acquire(flag) >= it.n_in_tile) {
-                        // the staged means were written with ordinary stores on other SMs and acquired just
-                        // above; the copies read them through the async proxy, and complete on b_full
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.global;\n" ::: "memory");
-                            const uint32_t oct_bytes = (uint32_t)nj * 32 * sizeof(double), mg_bytes = (uint32_t)it.noct * SSD_OCT * sizeof(double);
-                            mbar_expect_tx(b_full, oct_bytes * (uint32_t)it.noct + mg_bytes);
-                            for (int pt = 0; pt < it.noct; ++pt) bulk_g2s(bbuf + (size_t)pt * nj * 32, bsrc + pt * bstride, oct_bytes, b_full);
-                            bulk_g2s(mbuf, msrc, mg_bytes, b_full);
-                        }
-                        __syncwarp();
-                        filled = true;
-                    } else if (!filled || prev_ctr) {
-                        __nanosleep(32);
-                        if (gtime() - t0 > 20000000000ull) __trap();
-                    }
-                }
-                prev_ctr = ctr; ++n;
-            }
-        }
-        if (prev_ctr) { mbar_wait(item_done, (n - 1) & 1u); publish(prev_ctr); }
-        return;
-    }
-    if (!scalar_cta) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PK_REGS_DMMA));
-        // ---- DMMA warps ---------------------------------------------------------------------------
-        const int vc = warp >> 2, v = blockIdx.x * 2 + vc, NV = n_dmma_ctas * 2;
-        XdWarp xw;
-        xw.warp = warp & 3; xw.ks = 0; xw.it_base = 0;
-        xw.ring = ring0 + (size_t)warp * PK_STAGES * stage_doubles;
-        xw.full = bars + warp * PK_STAGES;
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < PK_STAGES; ++s) mbar_init(&xw.full[s], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
-        __syncwarp();
-        const double *const bbuf = bbuf0 + (size_t)vc * bbuf_doubles, *const mbuf = bbuf + (size_t)4 * nj * 32;
-        uint32_t n = 0;
-        for (int L = 0; L < ck.n_levels; ++L) {
-            const PLevel &pl = ck.lv[L];
-            Level lv; lv.order = ck.order + pl.order_off; lv.n = pl.n; lv.ctxs = ck.ctxs;
-            const int total = pl.n_items * m.n_ksplit;
-            for (int q = v; q < total; q += NV) {
-                const PkItem it = pk_item(pl, n_tiles, q);
-                if (it.T1 <= it.T0) continue;
-                unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-                const VctaHooks<TL> hooks = { &vbars[vc * 3 + 0], &vbars[vc * 3 + 1], &vbars[vc * 3 + 2], n & 1u, tl, 0ull };
-                const unsigned long long t_a = (TL && tl) ? gtime() : 0ull;
-                xw.ks = it.ks;
-                const int oct0 = it.oct0, T0 = it.T0, T1 = it.T1;
-                const size_t bstride = (size_t)nj * 32;
-#define PK_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, PK_STAGES>(m, bbuf, bstride, mbuf, lv, ck.ll_acc, oct0, T0, T1, xw, hooks, nullptr, nullptr)
-                if (m.ssd_nj == SSD_NJ && m.ssd_half) {
-                    switch (it.noct) { case 4: PK_CALL(4, SSD_NJ, true); break; case 3: PK_CALL(3, SSD_NJ, true); break; case 2: PK_CALL(2, SSD_NJ, true); break; default: PK_CALL(1, SSD_NJ, true); break; }
-                } else if (m.ssd_nj == SSD_NJ) {
-                    switch (it.noct) { case 4: PK_CALL(4, SSD_NJ, false); break; case 3: PK_CALL(3, SSD_NJ, false); break; case 2: PK_CALL(2, SSD_NJ, false); break; default: PK_CALL(1, SSD_NJ, false); break; }
-                } else {
-                    switch (it.noct) { case 4: PK_CALL(4, 0, false); break; case 3: PK_CALL(3, 0, false); break; case 2: PK_CALL(2, 0, false); break; default: PK_CALL(1, 0, false); break; }
-                }
-#undef PK_CALL
-                ++n;
-                if (TL && tl && lane == 0) {
-                    const unsigned long long t_b = gtime();
-                    atomicMax(tl + PT_X1, t_b);
-                    atomicAdd(tl + PT_SUM_WAIT, hooks.t_done - t_a); atomicAdd(tl + PT_SUM_ITEM, t_b - hooks.t_done);
-                    atomicAdd(tl + PT_ITEMS, 1ull);
-                }
-            }
-        }
-        return;
-    }
-    // ---- scalar warps ---------------------------------------------------------------------------
-    const int sw = ((int)blockIdx.x - n_dmma_ctas) * PK_WARPS + warp, NS = ck.n_scalar_ctas * PK_WARPS;
-    auto accept_level = [&](int L) {
-        const PLevel &pl = ck.lv[L];
-        for (int wi = sw; wi < pl.n; wi += NS) {
-            const uint32_t e = (uint32_t)ck.order[pl.order_off + wi];
-            const SweepCtx ctx = ck.ctxs[e >> LV_SLOT_SHIFT];
-            int tile, oct0, noct;
-            xd_tile_of_octet(pl.g, wi / SSD_OCT, tile, oct0, noct);
-            FlagLanes co;
-            unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-            co.w = { ck.xdot_done + pl.tile_base + tile, xd_tile_ctas(pl.g, tile) * 4 * m.n_ksplit, nullptr, 0, tl, PT_AW0, -1, 0ull };
-            accept_particle(co, cfg, m, ctx, (int)(e & LV_POS_MASK));
-            const unsigned long long ta1 = (TL && tl) ? gtime() : 0ull;
-            arrive(ck.acc_done + L);
-            if (TL && tl && lane == 0) {
-                const unsigned long long ta2 = gtime();
-                atomicMax(tl + PT_A1, ta2);
-                atomicAdd(tl + PT_A_BODY, ta1 - co.w.t_done); atomicAdd(tl + PT_A_ARR, ta2 - ta1); atomicAdd(tl + PT_A_N, 1ull);
-            }
-        }
-    };
-    int next_acc = 0;
-    for (int L = 0; L < ck.n_levels; ++L) {
-        const PLevel &pl = ck.lv[L];
-        // the accepts this level's proposals (or its staging buffer) wait for: inside the first
-        // proposal's dependency wait when this warp has one, else here
-        const int must = max(pl.dep, L - 2);
-        auto pending = [&]() { while (next_acc <= must) accept_level(next_acc++); };
-        for (int wi = sw; wi < pl.n; wi += NS) {
-            const uint32_t e = (uint32_t)ck.order[pl.order_off + wi];
-            const SweepCtx ctx = ck.ctxs[e >> LV_SLOT_SHIFT];
-            const int p = (int)(e & LV_POS_MASK);
-            double *bfrag = ck.bfrag[L & 1], *magic = ck.magic[L & 1];
-            unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-            const unsigned long long tp0 = (TL && tl) ? gtime() : 0ull;
-            if (tl && lane == 0) atomicMax(tl + PT_P0, ~tp0);
-            const FlagWait fw = { pl.dep >= 0 ? ck.acc_done + pl.dep : nullptr, pl.dep >= 0 ? ck.lv[pl.dep].n : 0,
-                                  L >= 2 ? ck.acc_done + (L - 2) : nullptr, L >= 2 ? ck.lv[L - 2].n : 0, tl, PT_PW, -1, 0ull };
-            const ProposeLanes<decltype(pending)> co(pending, fw);
-            StageSink sink = { m, bfrag, wi, m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
-            propose_particle(co, cfg, m, ctx, p, sink);
-            const unsigned long long tp1 = (TL && tl) ? gtime() : 0ull;
-            if (sink.on) stage_scale(m, warp_sum(sink.msq), wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
-            else {
-                __syncwarp();
-                stage_bfrag(m, ctx.prop_theta + (size_t)p * cfg.d, wi, bfrag, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
-            }
-            int tile, oct0, noct;
-            xd_tile_of_octet(pl.g, wi / SSD_OCT, tile, oct0, noct);
-            const unsigned long long tp2 = (TL && tl) ? gtime() : 0ull;
-            arrive(ck.prop_done + pl.tile_base + tile);
-            if (TL && tl && lane == 0) {
-                const unsigned long long tp3 = gtime();
-                atomicMax(tl + PT_P1, tp3);
-                // prologue + pending accepts + dependency wait | body | staging | arrive
-                atomicAdd(tl + PT_S_PRE, co.w.t_done - tp0); atomicAdd(tl + PT_S_BODY, tp1 - co.w.t_done);
-                atomicAdd(tl + PT_S_STAGE, tp2 - tp1); atomicAdd(tl + PT_S_ARR, tp3 - tp2); atomicAdd(tl + PT_S_N, 1ull);
-            }
-        }
-        pending();                                           // a warp without a proposal in this level
-        if (ck.lag == 0) while (next_acc <= L) accept_level(next_acc++);
-    }
-    while (next_acc < ck.n_levels) accept_level(next_acc++);
-}
-
-static XdGrid xdot_grid(const ModelDev &m, int n, int slots);
-
-// debug timeline of the persistent kernel (DEMCMC_PK_TIMELINE=<levels> DEMCMC_PK_TIMELINE_FILE=<csv>)
-static unsigned long long *g_ptl = nullptr;
-static int g_ptl_cap = -1, g_ptl_level = 0;
-static std::vector<int> g_ptl_n, g_ptl_chunk;
-static void pk_timeline_dump()
-{
-    const char *path = getenv("DEMCMC_PK_TIMELINE_FILE");
-    if (g_ptl_cap <= 0 || !g_ptl || !path || g_ptl_level == 0) return;
-    cudaDeviceSynchronize();
-    const int n = g_ptl_level;
-    std::vector<unsigned long long> h((size_t)PT_WORDS * n);
-    if (cudaMemcpy(h.data(), g_ptl, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return;
-    FILE *f = fopen(path, "w");
-    if (!f) return;
-    fprintf(f, "level,chunk,n,propose_first_start,propose_dep_ready,propose_last_end,xdot_first_ready,xdot_last_ready,xdot_last_end,accept_first_ready,accept_last_end,warp_items,wait_us_per_item,work_us_per_item,arrive_us_per_item,prop_pre_us,prop_body_us,prop_stage_us,prop_arrive_us,acc_body_us,acc_arrive_us\n");
-    unsigned long long t0 = ~0ull;
-    for (int i = 0; i < n; ++i) if (h[(size_t)i * PT_WORDS + PT_P0]) t0 = std::min(t0, ~h[(size_t)i * PT_WORDS + PT_P0]);
-    auto rel = [&](unsigned long long v) { return v ? (double)((long long)(v - t0)) * 1e-3 : -1.0; };
-    for (int i = 0; i < n; ++i) {
-        const unsigned long long *w = h.data() + (size_t)i * PT_WORDS;
-        const double ni = w[PT_ITEMS] ? (double)w[PT_ITEMS] : 1.0;
-        const double ns = w[PT_S_N] ? (double)w[PT_S_N] * 1e3 : 1.0, na = w[PT_A_N] ? (double)w[PT_A_N] * 1e3 : 1.0;
-        fprintf(f, "%d,%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%llu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, g_ptl_chunk[i], g_ptl_n[i], rel(~w[PT_P0]), rel(~w[PT_PW]), rel(w[PT_P1]),
-                rel(~w[PT_XW0]), rel(w[PT_XW1]), rel(w[PT_X1]), rel(~w[PT_AW0]), rel(w[PT_A1]), w[PT_ITEMS],
-                (double)w[PT_SUM_WAIT] * 1e-3 / ni, (double)w[PT_SUM_ITEM] * 1e-3 / ni, (double)w[PT_SUM_ARRIVE] * 1e-3 / ni,
-                (double)w[PT_S_PRE] / ns, (double)w[PT_S_BODY] / ns, (double)w[PT_S_STAGE] / ns, (double)w[PT_S_ARR] / ns,
-                (double)w[PT_A_BODY] / na, (double)w[PT_A_ARR] / na);
-    }
-    fclose(f);
-}
-
-static int persist_enabled()                                  // DEMCMC_PERSIST=0: level-by-level launches (A/B runs, tests)
-{
-    const char *e = getenv("DEMCMC_PERSIST");
-    return (e && e[0] == '0') ? 0 : 1;
-}
-static int persist_scalar_ctas()
-{
-    static int n_scalar = -1;
-    if (n_scalar < 0) { const char *e = getenv("DEMCMC_PK_SCALAR_CTAS"); n_scalar = e ? std::max(1, std::min(atoi(e), 64)) : PK_SCALAR_CTAS; }
-    return n_scalar;
-}
-// How many lanes (independent sets of groups with alternating levels) the persistent kernel wants
-// for this job, or 0 when the job is better served level by level: other models, a single group
-// (nothing to alternate with: the scalar part of every level would sit on the critical path with
-// fewer warps than k_propose has), or levels far larger than the scalar warps.
-int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m)
-{
-    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER)) return 0;
-    if (cfg.G_local < 2) return 0;
-    if ((int64_t)cfg.G_local * cfg.Np / 8 > (int64_t)4 * PK_WARPS * persist_scalar_ctas()) return 0;   // ~ a level per lane
-    return 2;
-}
-
-// Runs the levels [level_off[l], level_off[l] + level_n[l]) of a chunk (entries in d_order) in one persistent
-// launch.  dep[l] = the level whose accepts the proposals of level l wait for (-1: none), lag = how
-// many levels the accepts trail the proposals in the scalar warps' program (0 or 1).
-// Returns 1 when the chunk does not fit this kernel (the caller launches the levels one by one).
-int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
-                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc)
-{
-    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
-    static PChunk ck;                                        // 9 KB: not on the stack of every call
-    const int n_scalar = persist_scalar_ctas();
-    const int sms = n_sms(), slots = XD_CTAS_PER_SM * (sms - n_scalar);
-    int tiles = 0, n_max = 0;
-    for (int l = 0; l < n_levels; ++l) {
-        PLevel &pl = ck.lv[l];
-        pl.order_off = level_off[l]; pl.n = level_n[l]; pl.dep = dep[l]; pl.tile_base = tiles; pl.pad = 0;
-        if (pl.n <= 0 || pl.dep >= l) return 1;
-        pl.g = xdot_grid(m, pl.n, slots);
-        pl.n_items = pl.g.n_hi * pl.g.c_hi + pl.g.n_lo * pl.g.c_lo;
-        tiles += pl.g.n_hi + pl.g.n_lo;
-        n_max = std::max(n_max, pl.n);
-    }
-    if (tiles > PK_MAX_TILES) return 1;
-    // the scalar warps take one update at a time: levels far larger than their number are better
-    // served by the wide propose / accept kernels of the level-by-level path
-    if (n_max > 8 * PK_WARPS * n_scalar) return 1;
-    static int32_t *ctr[64] = { nullptr };
-    if (!ctr[g_dev]) CU(cudaMalloc(&ctr[g_dev], sizeof(int32_t) * (PK_MAX_LEVELS + 2 * PK_MAX_TILES)));
-    XdStage *xs[2];
-    const int keep = g_lane;
-    for (int b = 0; b < 2; ++b) { g_lane = b; xs[b] = xd_stage(m, std::max(n_max, cfg.G_local * cfg.Np)); }
-    g_lane = keep;
-    if (!xs[0] || !xs[1]) return -1;
-    ck.n_levels = n_levels; ck.lag = lag; ck.n_scalar_ctas = n_scalar; ck.order = d_order; ck.ctxs = d_ctx;
-    ck.acc_done = ctr[g_dev]; ck.prop_done = ctr[g_dev] + PK_MAX_LEVELS; ck.xdot_done = ck.prop_done + PK_MAX_TILES;
-    for (int b = 0; b < 2; ++b) { ck.bfrag[b] = xs[b]->bfrag; ck.magic[b] = xs[b]->magic; }
-    ck.ll_acc = ll_acc;
-    if (g_ptl_cap < 0) {
-        const char *e = getenv("DEMCMC_PK_TIMELINE");
-        g_ptl_cap = e ? atoi(e) : 0;
-        if (g_ptl_cap > 0 && (cudaMalloc(&g_ptl, sizeof(unsigned long long) * PT_WORDS * g_ptl_cap) != cudaSuccess ||
-                              cudaMemset(g_ptl, 0, sizeof(unsigned long long) * PT_WORDS * g_ptl_cap) != cudaSuccess)) g_ptl_cap = 0;
-    }
-    ck.tl = nullptr;
-    if (g_ptl_cap > 0 && g_ptl_level + n_levels <= g_ptl_cap) {
-        static int chunk_no = 0;
-        ck.tl = g_ptl + (size_t)PT_WORDS * g_ptl_level;
-        for (int l = 0; l < n_levels; ++l) { g_ptl_n.push_back(ck.lv[l].n); g_ptl_chunk.push_back(chunk_no); }
-        g_ptl_level += n_levels; ++chunk_no;
-    }
-    CU(cudaMemsetAsync(ctr[g_dev], 0, sizeof(int32_t) * (PK_MAX_LEVELS + PK_MAX_TILES + (size_t)tiles), stream()));
-    static bool attr_set[64] = { false };
-    const size_t smem = pk_smem_bytes(m.ssd_nj);
-    if (!attr_set[g_dev]) {
-        CU(cudaFuncSetAttribute(k_chunk_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem_bytes(SSD_NJ)));
-        CU(cudaFuncSetAttribute(k_chunk_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem_bytes(SSD_NJ)));
-        attr_set[g_dev] = true;
-    }
-    if (ck.tl) k_chunk_persist<true><<<sms, PK_THREADS, smem, stream()>>>(cfg, m, ck);
-    else k_chunk_persist<false><<<sms, PK_THREADS, smem, stream()>>>(cfg, m, ck);
-    LAUNCHED("k_chunk_persist");
-    return 0;
-}
-
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc)
 {
     (void)cfg;
@@ -1473,7 +884,7 @@ __global__ void __launch_bounds__(256) k_col_center(const double *x, double *cen
 // one thread per observation: writes its centred row into the packed layout; per block the sum and
 // the maximum of the squared row norms
 __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double *center, double *xp, double *blk_sq, double *blk_max,
-                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major, int half)
+                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major)
 {
     __shared__ double red[9];
     __shared__ double redm[8];
@@ -1483,7 +894,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double
         for (int kk = 0; kk < k; ++kk) {
             const double v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - center[kk];
             q += v * v;
-            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles, half)] = v;
+            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles)] = v;
         }
     double mx = q;
 #pragma unroll
@@ -1519,7 +930,7 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
     if (e == cudaSuccess) {
         k_col_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->center), m->ssd_n, m->ssd_k, obs_major);
         k_pack_rows<<<n_blk, 256, 0, stream()>>>(src, m->center, const_cast<double *>(m->xT), blk, blk + n_blk, m->ssd_n, m->ssd_k,
-                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major, m->ssd_half);
+                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major);
         g_launches += 2;
         e = cudaGetLastError();
     }
