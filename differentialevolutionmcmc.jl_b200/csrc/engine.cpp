@@ -593,7 +593,11 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             PlanInput pin;
             pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
             pin.pos_offset = g0 * Np; pin.P_stride = P;
-            { const char *e = getenv("DEMCMC_NO_SHAPE"); pin.shape_octets = (h->dmodel.kind == M_MVNORMAL || h->dmodel.kind == M_HIER) && !(e && e[0] == '1'); }
+            {
+                const char *e = getenv("DEMCMC_SHAPE");       // 0 = off, else the modulus (A/B runs)
+                const int mod = e ? atoi(e) : 8;
+                pin.shape_octets = (h->dmodel.kind == M_MVNORMAL || h->dmodel.kind == M_HIER) ? std::max(0, mod) : 0;
+            }
             pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
             const int64_t s_first = it0 * B + b;
             pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps

@@ -76,8 +76,8 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
         std::vector<std::vector<int32_t>> members(max_level + 1);
         for (size_t u = 0; u < U; ++u) members[level[u]].push_back((int32_t)u);
         for (int l = 0; l < max_level; ++l) {
-            int r = (int)(members[l].size() % 8);
-            if (r == 0 || members[l].size() < 8) continue;
+            int r = (int)(members[l].size() % (size_t)in.shape_octets);
+            if (r == 0 || (int)members[l].size() < in.shape_octets) continue;
             // later entries first: they keep the level's (sweep, slot) order intact for the rest
             for (size_t i = members[l].size(); i-- > 0 && r > 0;) {
                 const int32_t u = members[l][i];

@@ -31,8 +31,9 @@ struct PlanInput {
     int32_t P_stride = 0;      // particles per sweep in the tape slices (0: Np * G_local)
     int32_t proposal;          // 0 random_gamma
     double beta, theta_snooker;
-    bool shape_octets = false; // hand each level's remainder modulo 8 to the next level where the dependencies allow
-                               // (the DMMA likelihood kernel pads levels to whole octets of particles)
+    int32_t shape_octets = 0;  // > 0: hand each level's remainder modulo this many updates to the next level where the
+                               // dependencies allow (the DMMA likelihood kernel pads levels to whole octets of particles,
+                               // and its particle tiles are most efficient with four octets: 8 or 32)
     bool resample;             // donors come from stored rows (crossover.jl:113-124): no donor dependencies inside a sweep
     // replay: tape slices [sweep][P_local] of the chunk's FIRST sweep onwards, else nullptr
     const uint8_t *t_kind;     // [n_sweeps][P_local]
