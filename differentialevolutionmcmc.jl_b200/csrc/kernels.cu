@@ -455,6 +455,91 @@ __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m
     if ((threadIdx.x & 31) == 0) tl_max(tl, TL_A1);
 }
 
+// ---- wide variants: one CTA of PAW_THREADS threads per particle when the parameter vector is long
+// (hierarchical normal with 1000 subjects: d = 1003).  With one warp per particle the proposal is a
+// 32-iteration chain of dependent loads, Philox draws and prior terms per lane (90 us per level on
+// configs[3]); eight warps cut the chain to four iterations.  Same per-element arithmetic
+// (de_particle.h), block-wide reductions in a fixed order.
+constexpr int PAW_THREADS = 256;
+constexpr int PAW_MIN_D = 256;           // parameter count from which the wide kernels are used
+
+struct BlockLanes {
+    double *red;                          // shared scratch: PAW_THREADS / 32 doubles
+    int *ired;
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    __device__ __forceinline__ int width() const { return PAW_THREADS; }
+    __device__ __forceinline__ double sum(double x) const
+    {
+        const double v = warp_sum(x);
+        __syncthreads();                                      // the scratch of the previous reduction has been read
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < PAW_THREADS / 32; ++w) s += red[w];
+        return s;
+    }
+    __device__ __forceinline__ bool all(bool b) const { return __syncthreads_and(b ? 1 : 0) != 0; }
+    __device__ __forceinline__ int min_int(int x) const
+    {
+        const int v = __reduce_min_sync(0xffffffffu, x);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int r = ired[0];
+#pragma unroll
+        for (int w = 1; w < PAW_THREADS / 32; ++w) r = min(r, ired[w]);
+        return r;
+    }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void dependency_wait() const { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+};
+
+__global__ void __launch_bounds__(PAW_THREADS) k_propose_wide(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
+{
+    __shared__ double red[PAW_THREADS / 32];
+    __shared__ int ired[PAW_THREADS / 32];
+    pdl_launch_dependents();
+    const int wi = blockIdx.x;
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    const int p = (int)(e & LV_POS_MASK);
+    const BlockLanes co = { red, ired };
+    StageSink sink = { m, bfrag, wi, bfrag != nullptr && m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
+    propose_particle(co, cfg, m, ctx, p, sink);
+    if (!bfrag) return;
+    double msq = sink.msq;
+    if (!sink.on) {
+        __syncthreads();                                          // the proposal is complete in global memory
+        const double *theta = ctx.prop_theta + (size_t)p * cfg.d;
+        msq = 0.0;
+        for (int k = threadIdx.x; k < m.ssd_k; k += PAW_THREADS) {
+            const double v = centred_mean(m, theta, k);
+            msq += v * v;
+            bfrag[bfrag_index(m, wi, k)] = v;
+        }
+    }
+    msq = co.sum(msq);
+    if (threadIdx.x < 32) stage_scale(m, msq, wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
+}
+
+__global__ void __launch_bounds__(PAW_THREADS) k_accept_wide(ConfigDev cfg, ModelDev m, Level lv)
+{
+    __shared__ double red[PAW_THREADS / 32];
+    __shared__ int ired[PAW_THREADS / 32];
+    pdl_launch_dependents();
+    const uint32_t e = (uint32_t)lv.order[blockIdx.x];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    const BlockLanes co = { red, ired };
+    accept_particle(co, cfg, m, ctx, (int)(e & LV_POS_MASK));
+}
+
+static bool wide_enabled(const ConfigDev &cfg)
+{
+    const char *e = getenv("DEMCMC_NO_WIDE");
+    return cfg.d >= PAW_MIN_D && !(e && e[0] == '1');
+}
+
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
@@ -464,6 +549,11 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
         xs = xd_stage(m, std::max(lv.n, cfg.G_local * cfg.Np));
         if (!xs) return -1;
     }
+    if (wide_enabled(cfg) && lv.ctxs) {
+        CU(launch_chained(k_propose_wide, dim3(lv.n), dim3(PAW_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
+        LAUNCHED("k_propose_wide");
+        return 0;
+    }
     CU(launch_chained(k_propose, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr, tl_slot()));
     LAUNCHED("k_propose");
     return 0;
@@ -472,6 +562,12 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
+    if (wide_enabled(cfg) && lv.ctxs) {
+        CU(launch_chained(k_accept_wide, dim3(lv.n), dim3(PAW_THREADS), 0, cfg, m, lv));
+        LAUNCHED("k_accept_wide");
+        if (g_tl_cap > 0) ++g_tl_level;
+        return 0;
+    }
     CU(launch_chained(k_accept, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv, tl_slot()));
     LAUNCHED("k_accept");
     if (g_tl_cap > 0) ++g_tl_level;

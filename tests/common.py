@@ -82,7 +82,7 @@ def halfcauchy(rng):
     return abs(rng.standard_cauchy())
 
 
-def make_case(name, rng, n_obs=None):
+def make_case(name, rng, n_obs=None, n_subjects=9):
     if name == "gaussian":
         n = n_obs or 50
         x = rng.normal(0.0, 1.0, n)
@@ -114,7 +114,7 @@ def make_case(name, rng, n_obs=None):
                     lambda r: [abs(r.normal(1, 5)), abs(r.normal(1, 5)), abs(r.normal(0.8, 0.2)), abs(r.normal(0.2, 0.1)), r.uniform(0, mn)],
                     dict(x=rt, choice=choice, n_dim=2))
     if name == "hier_normal":
-        S, n = 9, (n_obs or 12)
+        S, n = n_subjects, (n_obs or 12)
         b0 = rng.normal(0, 1, S)
         y = rng.normal(1.0 + b0[:, None], 0.5, size=(S, n))
         prior = [("normal", 1, 1), ("halfcauchy", 0, 1)] + [("normal_ref", 0, 0, 1)] * S + [("halfcauchy", 0, 1)]

@@ -373,6 +373,30 @@ def test_persistent_chunk_kernel_replays_the_oracle(monkeypatch):
     check(r, out)
 
 
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_wide_kernels_long_parameter_vectors(mode, monkeypatch):
+    """d >= 256 (hierarchical normal with 300 subjects, d = 303, parameter blocks): the proposal and the
+    accept run as one CTA of 256 threads per particle (k_propose_wide / k_accept_wide) -- same
+    accept decisions as the oracle, values within 1e-12; and the same chain as the one-warp kernels."""
+    case = make_case("hier_normal", np.random.default_rng(61), n_obs=20, n_subjects=300)
+    S = case.d - 3
+    r, out = forced_run(case, 2, 10, 8, mode, burnin=4, blocks=hier_blocks(S), alpha=0.3)
+    check(r, out)
+    theta0 = case.theta0(np.random.default_rng(3), 2 * 10)
+    outs = []
+    for no_wide in ("1", "0"):
+        monkeypatch.setenv("DEMCMC_NO_WIDE", no_wide)
+        h = case.handle(2, 10, seed=4, burnin=3, blocks=hier_blocks(S), alpha=0.3)
+        h.set_state(theta0)
+        h.run(12)
+        outs.append((h.samples(), h.accept(), h.lp()))
+        h.close()
+    assert np.array_equal(outs[0][1], outs[1][1])                       # accept decisions
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-9, atol=1e-12)    # reductions differ in order only
+    fin = np.isfinite(outs[0][2])
+    assert np.allclose(outs[0][2][fin], outs[1][2][fin], rtol=1e-9, atol=1e-9)
+
+
 # ---- the optimize path (optimize.jl; maximize! / minimize! + evaluate_fun!) -------------------------
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
