@@ -460,9 +460,9 @@ __global__ void __launch_bounds__(PA_THREADS) k_accept(ConfigDev cfg, ModelDev m
 // 32-iteration chain of dependent loads, Philox draws and prior terms per lane (90 us per level on
 // configs[3]); eight warps cut the chain to four iterations.  Same per-element arithmetic
 // (de_particle.h), block-wide reductions in a fixed order.
-constexpr int PAW_THREADS = 256;
 constexpr int PAW_MIN_D = 256;           // parameter count from which the wide kernels are used
 
+template <int PAW_THREADS>
 struct BlockLanes {
     double *red;                          // shared scratch: PAW_THREADS / 32 doubles
     int *ired;
@@ -495,7 +495,8 @@ struct BlockLanes {
     __device__ __forceinline__ void dependency_wait() const { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 };
 
-__global__ void __launch_bounds__(PAW_THREADS) k_propose_wide(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
+template <int PAW_THREADS, int MINB>
+__global__ void __launch_bounds__(PAW_THREADS, MINB) k_propose_wide(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
 {
     __shared__ double red[PAW_THREADS / 32];
     __shared__ int ired[PAW_THREADS / 32];
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(PAW_THREADS) k_propose_wide(ConfigDev cfg, Mod
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     const int p = (int)(e & LV_POS_MASK);
-    const BlockLanes co = { red, ired };
+    const BlockLanes<PAW_THREADS> co = { red, ired };
     StageSink sink = { m, bfrag, wi, bfrag != nullptr && m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
     propose_particle(co, cfg, m, ctx, p, sink);
     if (!bfrag) return;
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(PAW_THREADS) k_propose_wide(ConfigDev cfg, Mod
     if (threadIdx.x < 32) stage_scale(m, msq, wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
 }
 
+template <int PAW_THREADS>
 __global__ void __launch_bounds__(PAW_THREADS) k_accept_wide(ConfigDev cfg, ModelDev m, Level lv)
 {
     __shared__ double red[PAW_THREADS / 32];
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(PAW_THREADS) k_accept_wide(ConfigDev cfg, Mode
     pdl_launch_dependents();
     const uint32_t e = (uint32_t)lv.order[blockIdx.x];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
-    const BlockLanes co = { red, ired };
+    const BlockLanes<PAW_THREADS> co = { red, ired };
     accept_particle(co, cfg, m, ctx, (int)(e & LV_POS_MASK));
 }
 
@@ -550,7 +552,9 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
         if (!xs) return -1;
     }
     if (wide_enabled(cfg) && lv.ctxs) {
-        CU(launch_chained(k_propose_wide, dim3(lv.n), dim3(PAW_THREADS), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
+        // 256 threads, 4 CTAs per SM (64 registers, a few spills): measured on configs[3] against
+        // 2 / 3 CTAs per SM and 512 threads x 1 / 2: 14.9 vs 12.7 / 14.0 / 10.8 / 13.5 M updates/s
+        CU(launch_chained(k_propose_wide<256, 4>, dim3(lv.n), dim3(256), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
         LAUNCHED("k_propose_wide");
         return 0;
     }
@@ -563,7 +567,7 @@ int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
     if (wide_enabled(cfg) && lv.ctxs) {
-        CU(launch_chained(k_accept_wide, dim3(lv.n), dim3(PAW_THREADS), 0, cfg, m, lv));
+        CU(launch_chained(k_accept_wide<256>, dim3(lv.n), dim3(256), 0, cfg, m, lv));
         LAUNCHED("k_accept_wide");
         if (g_tl_cap > 0) ++g_tl_level;
         return 0;
