@@ -1468,7 +1468,7 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
                          const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc)
 {
     if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
-    static PChunk ck;                                        // 9 KB: not on the stack of every call
+    static thread_local PChunk ck;                           // 9 KB: not on the stack of every call
     const int n_scalar = persist_scalar_ctas();
     const int sms = n_sms(), slots = XD_CTAS_PER_SM * (sms - n_scalar);
     int tiles = 0, n_max = 0;
