@@ -97,6 +97,20 @@ def run(name, iters=None):
     updates = c1["particle_updates"] - c0["particle_updates"]
     ms = c1["device_ms"]
     acc = h.accept()[:, -n_iter:].mean()
+    # the likelihood kernel by itself (MVN / hierarchical): a second pass with CUDA events around every
+    # launch of the dominant kernel (k_xdot per level, or k_chunk_persist per chunk)
+    ll = None
+    if c["flops"]:
+        h.set_timing(0, True)
+        h.run(n_iter)
+        c2 = h.counters()
+        if c2["loglike_ms"] > 0:
+            dfma, dmma = D.fp64_peaks(0)
+            tf = c["flops"] * (c2["particle_updates"] - c1["particle_updates"]) / (c2["loglike_ms"] * 1e-3) / 1e12
+            persistent = c2["persistent_chunks"] > c1["persistent_chunks"]
+            ll = {"kernel": "k_chunk_persist (whole chunk: proposals and accepts included)" if persistent else "k_xdot",
+                  "tflops_event_bracketed": tf, "of_measured_dmma_peak": tf / max(dfma, dmma), "peak_dmma_tflops": dmma,
+                  "share_of_step": c2["loglike_ms"] / c2["device_ms"]}
     h.close()
     line = {"config": name, "workload": c["what"], "particle_updates_per_s": updates / (ms * 1e-3), "ms_per_iteration": ms / n_iter,
             "iterations": n_iter, "particles": P, "sweeps_per_iteration": h.B, "levels_per_sweep": (c1["levels"] - c0["levels"]) / (n_iter * h.B),
@@ -104,6 +118,7 @@ def run(name, iters=None):
             "timing": "CUDA events on the library's stream around the whole call (demcmc_counters.device_ms), data resident, no L2 flush"}
     if c["flops"]:
         line["likelihood_tflops_whole_step"] = c["flops"] * updates / (ms * 1e-3) / 1e12
+        line["likelihood_kernel"] = ll
     return line
 
 
