@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libdemcmc_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -814,7 +814,14 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     if (tid == 0) tl_max(tl, TL_XWAIT);
     if (tlc && tid == 0 && blockIdx.x < TL_CTA_MAX) { tlc[blockIdx.x * 4 + 1] = gtime(); tlc[blockIdx.x * 4 + 3] = (unsigned long long)(T1 - T0) * 10 + NOCT; }
 
-    // this tile's centred means as B fragments, and the particles' fixed-point constants
+    // this tile's centred means as B fragments, and the particles' fixed-point constants (requested
+    // first: a warp's shared-memory loads complete in order, so once the first observation tile has
+    // consumed every B fragment the constants have landed too -- that is when after_loads() runs)
+    double mg[NOCT][2];
+#pragma unroll
+    for (int pt = 0; pt < NOCT; ++pt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) mg[pt][e] = msrc[pt * SSD_OCT + 2 * (lane & 3) + e];
     double b[SSD_NJ][NOCT];
     {
 #pragma unroll
@@ -826,7 +833,6 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
             for (int j = 0; j < SSD_NJ; ++j) b[j][pt] = j < nj ? bf[j * 32 + ((half && j == nj - 1) ? (lane & ~2) : lane)] : 0.0;
         }
     }
-    double mg[NOCT][2];
     unsigned long long isum[NOCT][2];
     // one chain per octet (both row tiles of the pair add into it), and TWO sets of them used by
     // alternate observation tiles: a tile's chains are rounded to the fixed-point grid one k-step
@@ -837,11 +843,9 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     for (int pt = 0; pt < NOCT; ++pt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            mg[pt][e] = msrc[pt * SSD_OCT + 2 * (lane & 3) + e];
             isum[pt][e] = 0ull;
             accA[pt][e] = 0.0; accB[pt][e] = 0.0;
         }
-    dependency_wait.after_loads();
     auto convert = [&](double (&acc)[NOCT][2]) {
 #pragma unroll
         for (int pt = 0; pt < NOCT; ++pt)
@@ -882,6 +886,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     };
     int t = T0;
     tile(t++, accA, accB, false);
+    dependency_wait.after_loads();                           // every B fragment has been an operand of a DMMA by now
     for (; t + 1 < T1; t += 2) {
         tile(t, accB, accA, true);
         tile(t + 1, accA, accB, true);
