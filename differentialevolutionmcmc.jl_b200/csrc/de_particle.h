@@ -217,9 +217,17 @@ DE_PRAGMA_UNROLL
     for (int k = co.lane() + PROP_PRE * co.width(); k < d; k += co.width()) body(PROP_PRE, k, noise_at(k), cfg.lo[k], cfg.hi[k], m.prior[k]);
     if (!one_pass) {
         co.sync();
+        // hierarchical priors: a thousand elements share one sd parameter, so its logarithm is kept
+        // (the value normlogpdf would compute, just not a thousand times)
+        double ref_sd = qnan(), ref_log = 0.0;
         for (int k = co.lane(); k < d; k += co.width()) {
             const Prior pr = m.prior[k];
-            ps += prior_elem(pr, prop[k], pr.kind == PRIOR_NORMAL_REF ? prop[pr.ref] : 0.0);
+            if (pr.kind == PRIOR_NORMAL_REF) {
+                const double sd = prop[pr.ref];
+                if (!(sd == ref_sd)) { ref_sd = sd; ref_log = log(sd); }
+                const double z = (prop[k] - pr.a) / sd;
+                ps += -(z * z + DE_LOG2PI) / 2.0 - ref_log;
+            } else ps += prior_elem(pr, prop[k], 0.0);
         }
     }
     const bool inb = co.all(ok);
