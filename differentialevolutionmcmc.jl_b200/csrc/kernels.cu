@@ -646,6 +646,25 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
     const int64_t i0 = (int64_t)split * m.split_len;
     const int64_t i1 = min(m.n_obs, i0 + (int64_t)m.split_len);
     const double *sg = m.has_sigma ? m.sigma_acc : nullptr;
+    if (KIND != M_GAUSSIAN) {
+        // LNR / LBA: ONE copy of the density in the instruction stream, particles in the outer loop.
+        // With the eight particles of the tile unrolled around it the loop body was 108 KB of code and
+        // a quarter of the stall samples were instruction fetches (ncu: no_instructions 24 %); the
+        // CTA's slice of observations (a few KB) stays in L1 across the particles.  Same summation
+        // order per particle as the unrolled form: bit-identical sums.
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+            double a = 0.0;
+            for (int64_t i = i0 + tid; i < i1; i += PW_THREADS) {
+                const double x = m.x[i];
+                const int c = m.choice[i] - 1;
+                if (KIND == M_LNR) a += lnr_obs(par[t], m.n_dim, sg, x, c);
+                else a += lba_obs(par[t], m.n_dim, par[t][m.n_dim + 3], m.lba_floor, x, c);
+            }
+            const double v = warp_sum(a);
+            if ((tid & 31) == 0) red[tid >> 5][t] = v;
+        }
+    } else
     for (int64_t i = i0 + tid; i < i1; i += PW_THREADS) {
         const double x = m.x[i];
         const int c = (KIND == M_GAUSSIAN) ? 0 : m.choice[i] - 1;
@@ -658,10 +677,12 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
             }
         }
     }
+    if (KIND == M_GAUSSIAN) {
 #pragma unroll
-    for (int t = 0; t < PW_TP; ++t) {
-        const double v = warp_sum(acc[t]);
-        if ((tid & 31) == 0) red[tid >> 5][t] = v;
+        for (int t = 0; t < PW_TP; ++t) {
+            const double v = warp_sum(acc[t]);
+            if ((tid & 31) == 0) red[tid >> 5][t] = v;
+        }
     }
     __syncthreads();
     if (tid < nt) {
