@@ -86,6 +86,8 @@ int launch_history_by_id(const double *rows_theta, const double *rows_w, const u
 // final_id[P] = id at each final position, pos_scratch[P] device scratch
 int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
                   const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out);
+// pooled per-parameter mean and sum of squared deviations of n vectors x[n][d] (fixed reduction order)
+int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *m2 /* device [d] each */);
 // particle algebra known-answer ops (single warp each)
 int launch_op_project(const double *p1, const double *p2, int d, double *out);
 int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,

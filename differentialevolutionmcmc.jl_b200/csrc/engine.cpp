@@ -814,6 +814,24 @@ int demcmc_get_samples(demcmc_handle *h, double *out, int64_t n_rows) { return o
 int demcmc_get_accept(demcmc_handle *h, uint8_t *out, int64_t n_rows) { return out ? history_out(h, nullptr, nullptr, out, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
 int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? history_out(h, nullptr, out, nullptr, n_rows) : fail(DEMCMC_EINVAL, "null out"); }
 
+int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *count, double *mean, double *m2)
+{
+    if (!h || !count || !mean || !m2) return fail(DEMCMC_EINVAL, "null argument");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n0 + h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)(h->n0 + h->iters_done));
+    BE(be::set_device(h->cfg.device));
+    const size_t P = h->P, d = h->d;
+    *count = n_rows * (int64_t)P;
+    if (n_rows == 0) { for (size_t k = 0; k < d; ++k) { mean[k] = 0.0; m2[k] = 0.0; } return 0; }
+    double *out = (double *)be::dmalloc(sizeof(double) * 2 * d);
+    if (!out) return fail(DEMCMC_ENOMEM, "moments staging");
+    int rc = 0;
+    if (be::launch_moments(h->hist_theta + (size_t)row0 * P * d, n_rows * (int64_t)P, (int32_t)d, out, out + d) ||
+        be::d2h(mean, out, sizeof(double) * d) || be::d2h(m2, out + d, sizeof(double) * d))
+        rc = fail(DEMCMC_ECUDA, "moments: %s", be::last_error());
+    be::dfree(out);
+    return rc;
+}
+
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
 {
     if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");

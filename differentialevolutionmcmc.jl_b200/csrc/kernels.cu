@@ -1899,6 +1899,55 @@ int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// streaming moments of the history: Welford per thread over the vectors of its block, Chan's merge
+// of the per-block partials in block order (deterministic; lanes run along the parameters, so the
+// reads coalesce)
+// ------------------------------------------------------------------------------------------------
+constexpr int MOM_BLOCKS = 592, MOM_THREADS = 128;
+__global__ void __launch_bounds__(MOM_THREADS) k_moments_partial(const double *x, int64_t n, int d, double *pmean, double *pm2)
+{
+    for (int k = threadIdx.x; k < d; k += MOM_THREADS) {
+        double mean = 0.0, m2 = 0.0, cnt = 0.0;
+        for (int64_t r = blockIdx.x; r < n; r += MOM_BLOCKS) {
+            const double v = x[r * d + k];
+            cnt += 1.0;
+            const double dl = v - mean;
+            mean += dl / cnt;
+            m2 += dl * (v - mean);
+        }
+        pmean[(size_t)blockIdx.x * d + k] = mean;
+        pm2[(size_t)blockIdx.x * d + k] = m2;
+    }
+}
+__global__ void __launch_bounds__(MOM_THREADS) k_moments_merge(const double *pmean, const double *pm2, int64_t n, int d, double *mean, double *m2)
+{
+    const int k = blockIdx.x * MOM_THREADS + threadIdx.x;
+    if (k >= d) return;
+    double ca = 0.0, ma = 0.0, sa = 0.0;
+    for (int b = 0; b < MOM_BLOCKS; ++b) {
+        const double cb = (double)((n - b + MOM_BLOCKS - 1) / MOM_BLOCKS);       // vectors block b saw
+        if (cb <= 0.0) break;
+        const double mb = pmean[(size_t)b * d + k], sb = pm2[(size_t)b * d + k];
+        const double dl = mb - ma, c = ca + cb;
+        ma += dl * (cb / c);
+        sa += sb + dl * dl * (ca * cb / c);
+        ca = c;
+    }
+    mean[k] = ma; m2[k] = sa;
+}
+int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *m2)
+{
+    double *part = (double *)dmalloc(sizeof(double) * 2 * (size_t)MOM_BLOCKS * d);
+    if (!part) return -1;
+    k_moments_partial<<<MOM_BLOCKS, MOM_THREADS, 0, stream()>>>(x, n, d, part, part + (size_t)MOM_BLOCKS * d);
+    LAUNCHED("k_moments_partial");
+    k_moments_merge<<<(d + MOM_THREADS - 1) / MOM_THREADS, MOM_THREADS, 0, stream()>>>(part, part + (size_t)MOM_BLOCKS * d, n, d, mean, m2);
+    LAUNCHED("k_moments_merge");
+    dfree(part);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // particle algebra ops (single warp)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_op_project(const double *p1, const double *p2, int d, double *out)

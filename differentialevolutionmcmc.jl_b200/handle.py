@@ -178,6 +178,15 @@ class Handle:
             check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
         return out
 
+    def moments(self, row0=0, n_rows=None):
+        """Pooled posterior summary computed on the device (no download of the draws): (count, mean[d],
+        var[d] with ddof=1) over history rows [row0, row0+n_rows) and all local particles."""
+        n = self.iterations - row0 if n_rows is None else n_rows
+        cnt = C.c_int64(0)
+        mean, m2 = np.zeros(self.d), np.zeros(self.d)
+        check(_ffi.lib().demcmc_get_moments(self._h, int(row0), int(n), C.byref(cnt), ptr(mean, _dp), ptr(m2, _dp)))
+        return cnt.value, mean, m2 / max(cnt.value - 1, 1)
+
     def history_by_slot(self, row0=0, n_rows=None):
         n = self.iterations - row0 if n_rows is None else n_rows
         th = np.zeros((n, self.P, self.d))

@@ -171,6 +171,12 @@ int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows);
  * are the draws of particle id c; the last two columns, "acceptance" and "lp", belong to the
  * particle sitting at final position c -- the reference's own by-position quirk (main.jl:232-241). */
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out);
+/* Streaming summary on the device (the history, not the compute, is what stops scaling --
+ * configs[4] would hand 423 GB of draws to the host): pooled over history rows [row0, row0+n_rows) and all
+ * local particles, per flattened parameter k: mean[k] and m2[k] = sum (x - mean[k])^2, with *count =
+ * n_rows * P_local draws, i.e. what MCMCChains' mean / std of the pooled chains reduce to
+ * (var = m2 / (count - 1)).  Shards of a multi-GPU job merge (count, mean, m2) with Chan's update. */
+int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *count, double *mean, double *m2);
 /* the same history as the device keeps it, rows [row0, row0+n_rows) of the iterations run, by
  * POSITION: theta[n_rows][P_local][d], w[n_rows][P_local] (= lp), ids[n_rows][P_local] (particle id
  * sitting at each position after that iteration), acc[n_rows][P_local]; any pointer may be NULL.

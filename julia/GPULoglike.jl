@@ -287,6 +287,17 @@ function device_bundle(h, de, n_iter, d, P)
     return v
 end
 
+# Pooled posterior mean / variance of the flattened parameters over rows offset+1 .. offset+Ns of
+# de.samples, computed on the device: what `describe(chains)` reports as mean and std, without the
+# download of the draws (configs[4] would hand 423 GB to the host).
+function device_moments(h, offset, Ns, d)
+    count = Ref{Int64}(0)
+    mean = zeros(Float64, d); m2 = zeros(Float64, d)
+    GC.@preserve mean m2 demcmc_check(ccall((:demcmc_get_moments, LIBDEMCMC), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ref{Int64}, Ptr{Float64}, Ptr{Float64}), h, offset, Ns, count, mean, m2))
+    return count[], mean, m2 ./ max(count[] - 1, 1)
+end
+
 # [n_iter, d, P] flat -> the reference's Array{T,3}(n_iter, n_named, P) whose elements may be arrays
 function nest_samples(flat, Θ1)
     n_iter, _, P = size(flat)

@@ -216,6 +216,17 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 }
 
 // the persistent chunk kernel exists on the device only: the engine falls back to level-by-level launches
+int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *m2)
+{
+    ++g_launches;
+    for (int k = 0; k < d; ++k) {
+        double mu = 0.0, s = 0.0;
+        for (int64_t r = 0; r < n; ++r) { const double v = x[r * d + k], dl = v - mu; mu += dl / (double)(r + 1); s += dl * (v - mu); }
+        mean[k] = mu; m2[k] = s;
+    }
+    return 0;
+}
+
 int chunk_persist_lanes(const ConfigDev &, const ModelDev &) { return 0; }
 int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
                          const int32_t *, int, int, long long *) { return 1; }

@@ -296,6 +296,25 @@ def test_device_bundle_matches_bundle_samples():
     h.close()
 
 
+def test_device_moments_match_the_chains():
+    """demcmc_get_moments (k_moments_partial / k_moments_merge): pooled mean and variance per parameter of
+    a row range of the history, against numpy on the downloaded rows; more vectors than blocks, fewer
+    vectors than blocks, and d above one block of threads."""
+    for model, kwm, G, Np, n_iter, row0 in (("mvnormal", {}, 4, 40, 30, 8), ("gaussian", {}, 2, 6, 12, 0),
+                                            ("hier_normal", dict(n_obs=10, n_subjects=200), 2, 8, 6, 1)):
+        case = make_case(model, np.random.default_rng(31), **kwm)
+        h = case.handle(G, Np, seed=6, burnin=3, alpha=0.4)
+        h.set_state(case.theta0(np.random.default_rng(8), G * Np))
+        h.run(n_iter)
+        th = h.history_by_slot(row0, n_iter - row0)[0]
+        cnt, mean, var = h.moments(row0, n_iter - row0)
+        flat = th.reshape(-1, th.shape[2])
+        assert cnt == flat.shape[0]
+        assert np.allclose(mean, flat.mean(axis=0), rtol=1e-12, atol=1e-13)
+        assert np.allclose(var, flat.var(axis=0, ddof=1), rtol=1e-9, atol=1e-13)
+        h.close()
+
+
 # ---- de.sample = resample (DE-MCz, crossover.jl:113-124) and n_initial ---------------------------
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("model", ["gaussian", "mvnormal", "lba"])

@@ -253,6 +253,25 @@ def test_device_bundle_matches_bundle_samples():
     h.close()
 
 
+def test_device_moments_match_the_chains():
+    """demcmc_get_moments: pooled mean / variance per parameter over a row range, computed by the
+    backend from the stored rows, against numpy on the downloaded history."""
+    case = make_case("gaussian", np.random.default_rng(29))
+    h = case.handle(3, 7, seed=6, burnin=5, alpha=0.4)
+    h.set_state(case.theta0(np.random.default_rng(8), 21))
+    h.run(40)
+    th = h.history_by_slot(10, 30)[0]                                   # [30][21][d]
+    cnt, mean, var = h.moments(10, 30)
+    flat = th.reshape(-1, th.shape[2])
+    assert cnt == flat.shape[0]
+    assert np.allclose(mean, flat.mean(axis=0), rtol=1e-12, atol=1e-14)
+    assert np.allclose(var, flat.var(axis=0, ddof=1), rtol=1e-10, atol=1e-14)
+    assert h.moments(40, 0)[0] == 0
+    with pytest.raises(D._ffi.DemcmcError):
+        h.moments(35, 10)
+    h.close()
+
+
 # ---- de.sample = resample (DE-MCz donors from the history, crossover.jl:113-124) and n_initial ----
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("kw", [dict(theta_snooker=0.3), dict(proposal="fixed_gamma", kappa=0.7, theta_snooker=0.1),
