@@ -63,6 +63,9 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // has cleared it and set ll_q); the other models write ll_part
 int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, const Level &lv, double *ll_part, long long *ll_acc);
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
+// small pointwise problems: propose + likelihood + accept of a level in one launch, one warp per
+// particle; returns 1 when the model / size does not qualify (launch the three kernels instead)
+int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // all levels of a chunk in ONE persistent, warp-specialised launch (MVN / hierarchical): level l
 // holds the entries d_order[level_off[l] .. + level_n[l]); its proposals wait for the accepts of
 // level dep[l] (< l, or -1); the scalar warps run their accepts `lag` levels behind their proposals.

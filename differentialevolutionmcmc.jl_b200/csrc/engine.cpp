@@ -662,6 +662,11 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 if (lv.n == 0) continue;
                 be::set_lane(ln);
                 const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
+                if (!tl) {
+                    const int fused = be::launch_level_fused(h->dcfg, h->dmodel, lv);
+                    if (fused < 0) { rc_launch = 1; break; }
+                    if (fused == 0) { ++n_levels; continue; }
+                }
                 if (be::launch_propose(h->dcfg, h->dmodel, lv) ||
                     (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll])) ||
                     be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc) ||

@@ -616,6 +616,78 @@ int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *
 // ------------------------------------------------------------------------------------------------
 // pointwise likelihood kernels: block = PW_TP particles x one observation split
 // ------------------------------------------------------------------------------------------------
+// a particle's parameters (+ per-particle constants) as the per-observation densities want them
+template <int KIND>
+__device__ __forceinline__ void pointwise_par(const ModelDev &m, const double *th, double *par)
+{
+    if (KIND == M_GAUSSIAN) { par[0] = th[0]; par[1] = th[1]; par[2] = log(th[1]); }
+    else if (KIND == M_LNR) { for (int r = 0; r <= m.n_dim; ++r) par[r] = th[r]; }
+    else {
+        double pneg = 1.0;
+        for (int r = 0; r < m.n_dim; ++r) { par[r] = th[r]; pneg *= norm_cdf(-th[r]); }
+        par[m.n_dim] = th[m.n_dim]; par[m.n_dim + 1] = th[m.n_dim + 1]; par[m.n_dim + 2] = th[m.n_dim + 2];
+        par[m.n_dim + 3] = 1.0 / (1.0 - pneg);
+        par[m.n_dim + 4] = 1.0 / th[m.n_dim];
+    }
+}
+
+// Small pointwise problems (the reference's own examples and tests: tens of observations, a handful
+// of particles per group): the whole update of a particle -- proposal, likelihood over all
+// observations, accept -- by ONE warp in ONE launch per level.  The three-kernel chain of a level
+// costs ~13 us of launches and hand-offs, which is all there is to do on configs[0].
+struct NoWaitLanes : WarpLanes { __device__ __forceinline__ void dependency_wait() const {} };
+template <int KIND>
+__global__ void __launch_bounds__(PA_THREADS) k_level_fused(ConfigDev cfg, ModelDev m, Level lv)
+{
+    pdl_launch_dependents();
+    const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
+    if (wi >= lv.n) { pdl_wait(); return; }
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    const int p = (int)(e & LV_POS_MASK), lane = threadIdx.x & 31;
+    NullSink sink;
+    propose_particle(WarpLanes(), cfg, m, ctx, p, sink);
+    __syncwarp();
+    if (KIND == M_GAUSSIAN || KIND == M_LNR || KIND == M_LBA) {
+        double par[MAX_ACC + 5];
+        pointwise_par<KIND>(m, ctx.prop_theta + (size_t)p * cfg.d, par);
+        const double *sg = m.has_sigma ? m.sigma_acc : nullptr;
+        double a = 0.0;
+        for (int64_t i = lane; i < m.n_obs; i += 32) {
+            const double x = m.x[i];
+            if (KIND == M_GAUSSIAN) a += gaussian_obs(par, x);
+            else if (KIND == M_LNR) a += lnr_obs(par, m.n_dim, sg, x, m.choice[i] - 1);
+            else a += lba_obs(par, m.n_dim, par[m.n_dim + 3], m.lba_floor, x, m.choice[i] - 1);
+        }
+        a = warp_sum(a);
+        if (lane == 0) ctx.ll_part[(size_t)p] = a;               // n_split == 1 on this path
+        __syncwarp();
+    }
+    accept_particle(NoWaitLanes(), cfg, m, ctx, p);
+}
+constexpr int64_t FUSED_MAX_OBS = 256;
+
+// returns 1 when the level is not a small pointwise one (the caller launches the three kernels)
+int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
+{
+    const char *env = getenv("DEMCMC_NO_FUSED");
+    if (env && env[0] == '1') return 1;
+    if (m.kind == M_MVNORMAL || m.kind == M_HIER || !lv.ctxs || cfg.d > 64) return 1;
+    if ((m.kind == M_GAUSSIAN || m.kind == M_LNR || m.kind == M_LBA) && (m.n_obs > FUSED_MAX_OBS || m.n_osplit * m.n_ksplit != 1)) return 1;
+    const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
+    switch (m.kind) {
+    case M_GAUSSIAN: CU(launch_chained(k_level_fused<M_GAUSSIAN>, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv)); break;
+    case M_LNR: CU(launch_chained(k_level_fused<M_LNR>, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv)); break;
+    case M_LBA: CU(launch_chained(k_level_fused<M_LBA>, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv)); break;
+    case M_BINOMIAL: CU(launch_chained(k_level_fused<M_BINOMIAL>, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv)); break;
+    case M_RASTRIGIN: CU(launch_chained(k_level_fused<M_RASTRIGIN>, dim3(blocks), dim3(PA_THREADS), 0, cfg, m, lv)); break;
+    default: return 1;
+    }
+    LAUNCHED("k_level_fused");
+    if (g_tl_cap > 0) ++g_tl_level;
+    return 0;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const double *theta, Level lv, double *part)
 {
@@ -628,16 +700,7 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
     // stage the tile's parameters (+ per-particle constants)
     if (tid < nt) {
         const int p = lv.order ? (int)((uint32_t)lv.order[tile * PW_TP + tid] & LV_POS_MASK) : tile * PW_TP + tid;
-        const double *th = theta + (size_t)p * m.d;
-        if (KIND == M_GAUSSIAN) { par[tid][0] = th[0]; par[tid][1] = th[1]; par[tid][2] = log(th[1]); }
-        else if (KIND == M_LNR) { for (int r = 0; r <= m.n_dim; ++r) par[tid][r] = th[r]; }
-        else {
-            double pneg = 1.0;
-            for (int r = 0; r < m.n_dim; ++r) { par[tid][r] = th[r]; pneg *= norm_cdf(-th[r]); }
-            par[tid][m.n_dim] = th[m.n_dim]; par[tid][m.n_dim + 1] = th[m.n_dim + 1]; par[tid][m.n_dim + 2] = th[m.n_dim + 2];
-            par[tid][m.n_dim + 3] = 1.0 / (1.0 - pneg);
-            par[tid][m.n_dim + 4] = 1.0 / th[m.n_dim];
-        }
+        pointwise_par<KIND>(m, theta + (size_t)p * m.d, par[tid]);
     }
     __syncthreads();
     double acc[PW_TP];

@@ -227,6 +227,7 @@ int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *
     return 0;
 }
 
+int launch_level_fused(const ConfigDev &, const ModelDev &, const Level &) { return 1; }
 int chunk_persist_lanes(const ConfigDev &, const ModelDev &) { return 0; }
 int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
                          const int32_t *, int, int, long long *) { return 1; }

@@ -100,6 +100,37 @@ def test_population_step_all_models(mode, model):
     check(r, out, rtol_w=RTOL_W.get(model))
 
 
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model", ["gaussian", "lnr", "lba"])
+def test_pointwise_models_above_the_fused_size(mode, model):
+    """Up to 256 observations a level of a pointwise model is ONE launch (k_level_fused: one warp does the
+    proposal, the likelihood and the accept of a particle); above, k_propose / k_ll_pointwise / k_accept.
+    The default cases of this file are below that size; these are above it, and the two paths are
+    compared with each other at a size both accept."""
+    case = make_case(model, np.random.default_rng(71), n_obs=900)
+    r, out = forced_run(case, 2, 8, 10, mode, burnin=5, theta_snooker=0.2, alpha=0.3)
+    check(r, out)
+
+
+@pytest.mark.parametrize("model", ["gaussian", "lnr", "lba", "binomial"])
+def test_fused_level_kernel_against_the_three_kernel_chain(model, monkeypatch):
+    case = make_case(model, np.random.default_rng(73))
+    theta0 = case.theta0(np.random.default_rng(9), 3 * 8)
+    outs = []
+    for no_fused in ("1", "0"):
+        monkeypatch.setenv("DEMCMC_NO_FUSED", no_fused)
+        h = case.handle(3, 8, seed=12, burnin=8, theta_snooker=0.2, alpha=0.3)
+        h.set_state(theta0)
+        h.run(25)
+        outs.append((h.samples(), h.accept(), h.lp(), h.counters()["kernel_launches"]))
+        h.close()
+    assert outs[1][3] < outs[0][3] * 0.7                                 # one launch per level instead of three (binomial: two)
+    assert np.array_equal(outs[0][1], outs[1][1])                       # accept decisions
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-9, atol=1e-12)    # the likelihood sums differ in order only
+    fin = np.isfinite(outs[0][2])
+    assert np.allclose(outs[0][2][fin], outs[1][2][fin], rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.parametrize("model", ["gaussian", "mvnormal", "binomial"])
 def test_unforced_short_replay(model):
     """Without teacher forcing, over a run short enough that rounding differences are not yet
