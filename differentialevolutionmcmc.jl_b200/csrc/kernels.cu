@@ -941,7 +941,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
     };
     // one observation tile: its DMMAs go to `acc`; `prev` (the other set) is converted after the
     // first k-step when it holds the previous tile
-    auto tile = [&](int t, double (&acc)[NOCT][2], double (&prev)[NOCT][2], bool have_prev) {
+    auto tile = [&](int t, double (&acc)[NOCT][2], double (&prev)[NOCT][2], bool have_prev, bool first = false) {
         const int it = t - T0;
         const uint32_t gi = it_base + (uint32_t)it, st = gi % STAGES;
         mbar_wait(&full[st], (gi / STAGES) & 1u);
@@ -963,14 +963,14 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
             if (j == 0 && have_prev) convert(prev);
         }
         __syncwarp();                                        // every lane's reads of the stage have landed
+        if (first) dependency_wait.after_loads();            // ... and every B fragment has been an operand of a DMMA
         if (lane == 0 && t + STAGES < T1) {
             mbar_expect_tx(&full[st], stage_bytes);
             bulk_g2s(ring + (size_t)st * stage_doubles, src + (size_t)(it + STAGES) * stage_doubles, stage_bytes, &full[st]);
         }
     };
     int t = T0;
-    tile(t++, accA, accB, false);
-    dependency_wait.after_loads();                           // every B fragment has been an operand of a DMMA by now
+    tile(t++, accA, accB, false, true);
     for (; t + 1 < T1; t += 2) {
         tile(t, accB, accA, true);
         tile(t + 1, accA, accB, true);
@@ -1281,7 +1281,7 @@ struct VctaHooks {
             if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
         }
     }
-    __device__ __forceinline__ void after_loads() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }
+    __device__ __forceinline__ void after_loads() const { if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }   // called right after a __syncwarp
     __device__ __forceinline__ void item_end() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(item_done); }
 };
 
