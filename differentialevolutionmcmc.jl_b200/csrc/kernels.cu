@@ -1606,8 +1606,17 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
         CU(cudaFuncSetAttribute(k_chunk_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem_bytes(SSD_NJ)));
         attr_set[g_dev] = true;
     }
-    if (ck.tl) k_chunk_persist<true><<<sms, PK_THREADS, smem, stream()>>>(cfg, m, ck);
-    else k_chunk_persist<false><<<sms, PK_THREADS, smem, stream()>>>(cfg, m, ck);
+    // a cooperative launch: CUDA itself guarantees (or refuses) that all CTAs are resident at once,
+    // which is what the counter waits between CTAs rely on
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(sms); lc.blockDim = dim3(PK_THREADS); lc.dynamicSmemBytes = smem; lc.stream = stream();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    const cudaError_t le = ck.tl ? cudaLaunchKernelEx(&lc, k_chunk_persist<true>, cfg, m, ck) : cudaLaunchKernelEx(&lc, k_chunk_persist<false>, cfg, m, ck);
+    if (le == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return 1; }   // not all resident here: level by level
+    if (le != cudaSuccess) return cu_fail(le, "k_chunk_persist");
     LAUNCHED("k_chunk_persist");
     return 0;
 }
