@@ -56,6 +56,7 @@ struct demcmc_handle {
     std::vector<void *> model_allocs;
     // state rows
     int64_t hist_cap = 0, iters_done = 0;
+    int64_t iter_offset = 0;                            // iterations the chain ran before this handle (demcmc_set_iteration)
     double *hist_theta = nullptr, *hist_w = nullptr;
     int32_t *hist_id = nullptr;
     uint8_t *hist_acc = nullptr;
@@ -431,6 +432,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     const int64_t pbeg = (int64_t)cfg.group_begin * Np;
     if (h->n0 > 0 && !h->has_history) return fail(DEMCMC_ESTATE, "n_initial > 0: demcmc_set_history must come before run");
     if (cfg.donors && h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "sample = resample is not sharded over GPUs yet");
+    if (cfg.donors && h->iter_offset > 0) return fail(DEMCMC_EUNSUPPORTED, "sample = resample draws donors from the rows of earlier iterations: a resumed handle does not hold them");
     if (int rc = grow_history(h, h->n0 + h->iters_done + n_iter)) return rc;
 
     // ---- replay: upload the local shard of the tape ------------------------------------------------
@@ -527,10 +529,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             out.n = tape->mig_n[it]; out.migrate = out.n > 0;
             for (int i = 0; i < out.n; ++i) { out.groups.push_back(tape->mig_groups[it * Gt + i]); out.u_pick.push_back(tape->mig_pick_u[it * Gt + i]); }
         } else {
-            plan_migration(cfg.seed, (uint32_t)(h->iters_done + it), Gt, cfg.alpha, out);
+            plan_migration(cfg.seed, (uint32_t)(h->iter_offset + h->iters_done + it), Gt, cfg.alpha, out);
         }
     };
-    auto in_burnin_at = [&](int64_t it) { return h->iters_done + it + 1 + cfg.n_initial <= cfg.burnin; };   // de.iter <= burnin
+    auto in_burnin_at = [&](int64_t it) { return h->iter_offset + h->iters_done + it + 1 + cfg.n_initial <= cfg.burnin; };   // de.iter <= burnin
     // native select_base reads the sweep-start weights: such a sweep starts from a complete state
     auto needs_snapshot = [&](int64_t it) { return !tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin_at(it); };
 
@@ -554,7 +556,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
             SweepCtx &ctx = u.h_ctx[s];
             memset(&ctx, 0, sizeof ctx);
-            ctx.sweep = (uint32_t)(itg * B + b); ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
+            ctx.sweep = (uint32_t)((h->iter_offset + itg) * B + b); ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
             ctx.exact_base = tape != nullptr;
             ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
             ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
@@ -602,7 +604,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const int64_t s_first = it0 * B + b;
             pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
             pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
-            plan_chunk(pin, (uint32_t)(itg0 * B + b), n_sw, basedep, plans[ln]);
+            plan_chunk(pin, (uint32_t)((h->iter_offset + itg0) * B + b), n_sw, basedep, plans[ln]);
             const ChunkPlan &pl = plans[ln];
             memcpy(u.h_order + lane_off[ln], pl.order.data(), sizeof(int32_t) * pl.order.size());
             lane_off[ln + 1] = lane_off[ln] + (int32_t)pl.order.size();
@@ -916,6 +918,24 @@ int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_log
         h->flush_bytes = l2_flush_bytes;
     }
     h->time_loglik = time_loglik != 0;
+    return 0;
+}
+
+int demcmc_set_weights(demcmc_handle *h, const double *w)
+{
+    if (!h || !w) return fail(DEMCMC_EINVAL, "null argument");
+    if (!h->has_state) return fail(DEMCMC_ESTATE, "set_state must come before set_weights");
+    BE(be::set_device(h->cfg.device));
+    BE(be::h2d(cur_row(h).w, w, sizeof(double) * (size_t)h->P));
+    BE(be::sync());
+    return 0;
+}
+
+int demcmc_set_iteration(demcmc_handle *h, int64_t iterations_done)
+{
+    if (!h || iterations_done < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_iteration must come before the first run of the handle");
+    h->iter_offset = iterations_done;
     return 0;
 }
 

@@ -178,6 +178,15 @@ class Handle:
             check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
         return out
 
+    def set_weights(self, w):
+        """The weights the saved particles carried (get_state()[1]); after set_state."""
+        check(_ffi.lib().demcmc_set_weights(self._h, ptr(f8(w).reshape(self.P), _dp)))
+
+    def set_iteration(self, iterations_done):
+        """Resume: this handle continues a chain that already ran `iterations_done` iterations elsewhere
+        (set_state with the saved theta and ids first or after; before the first run)."""
+        check(_ffi.lib().demcmc_set_iteration(self._h, int(iterations_done)))
+
     def moments(self, row0=0, n_rows=None):
         """Pooled posterior summary computed on the device (no download of the draws): (count, mean[d],
         var[d] with ddof=1) over history rows [row0, row0+n_rows) and all local particles."""

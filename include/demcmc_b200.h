@@ -171,6 +171,17 @@ int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows);
  * are the draws of particle id c; the last two columns, "acceptance" and "lp", belong to the
  * particle sitting at final position c -- the reference's own by-position quirk (main.jl:232-241). */
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out);
+/* Checkpoint / resume: a handle created from a saved state (demcmc_get_state ->
+ * demcmc_set_state with the ids) continues a chain that has already run `iterations_done` iterations:
+ * the Philox counters, de.iter <= burnin (crossover.jl:164) and the migration schedule carry on from
+ * there, so run(a) + save + resume + run(b) gives the very chain of run(a + b).  History rows of the new
+ * handle start at 0.  Before the first run of the handle; not with sample = resample (its donors are
+ * rows of the earlier iterations). */
+int demcmc_set_iteration(demcmc_handle *h, int64_t iterations_done);
+/* ... and the weights (Particle.weight, src/structs.jl:205) the saved particles carried, w[P_local] as
+ * demcmc_get_state returned them: demcmc_set_state re-evaluates them, which for the pointwise models sums
+ * the observations in another order (same value to ~1e-15 relative, not the same bits). */
+int demcmc_set_weights(demcmc_handle *h, const double *w);
 /* Streaming summary on the device (the history, not the compute, is what stops scaling --
  * configs[4] would hand 423 GB of draws to the host): pooled over history rows [row0, row0+n_rows) and all
  * local particles, per flattened parameter k: mean[k] and m2[k] = sum (x - mean[k])^2, with *count =

@@ -287,6 +287,23 @@ function device_bundle(h, de, n_iter, d, P)
     return v
 end
 
+# Checkpoint / resume: `state = device_state(h)` after `n_done` iterations; later, on a fresh handle,
+# `resume!(h2, state, n_done)` and the chain continues exactly (same Philox counters, burn-in switch and
+# migration schedule) -- the reference itself has no such facility (its RNG is the task-local one).
+function device_state(h, P, d)
+    θ = zeros(Float64, d, P); w = zeros(Float64, P); ids = zeros(Int32, P)
+    GC.@preserve θ w ids demcmc_check(ccall((:demcmc_get_state, LIBDEMCMC), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), h, θ, w, ids))
+    return (θ = θ, w = w, ids = ids)
+end
+function resume!(h, state, n_done)
+    GC.@preserve state begin
+        demcmc_check(ccall((:demcmc_set_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), h, state.θ, state.ids))
+        demcmc_check(ccall((:demcmc_set_weights, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, state.w))
+    end
+    demcmc_check(ccall((:demcmc_set_iteration, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64), h, n_done))
+end
+
 # Pooled posterior mean / variance of the flattened parameters over rows offset+1 .. offset+Ns of
 # de.samples, computed on the device: what `describe(chains)` reports as mean and std, without the
 # download of the draws (configs[4] would hand 423 GB to the host).
