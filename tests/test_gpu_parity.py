@@ -224,6 +224,43 @@ def test_mvn_full_size_sufficient_statistics():
     assert np.max(np.abs(parts[0] + parts[1] - ll) / np.abs(ll)) <= RTOL
 
 
+def test_mvn_full_size_posterior_through_the_persistent_kernel():
+    """Config 2 at its own size (d=50, 1e5 obs, 4 x 256, crossover + snooker) run natively through the
+    persistent chunk kernel: the pooled posterior must sit on the analytic one -- mu_k ~ N(N xbar_k /
+    (N + 1), sigma^2 / (N + 1)) given sigma, sigma close to the pooled sd of the centred data -- and the
+    device-side moments must agree with the downloaded draws."""
+    rng = np.random.default_rng(50514)
+    n, dm, G, Np = 100_000, 50, 4, 256
+    mu = rng.normal(size=dm)
+    x = rng.normal(mu, 1.0, size=(n, dm))
+    prior = [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)]
+    lo, hi = [-np.inf] * dm + [0], [np.inf] * (dm + 1)
+    xbar = x.mean(axis=0)
+    s_pool = np.sqrt(((x - xbar) ** 2).sum() / (n * dm))
+    # start near the mode (a cold start needs thousands of iterations at d = 51; this test is about the kernel)
+    theta0 = np.column_stack([xbar + rng.normal(0, 1.0 / np.sqrt(n), size=(G * Np, dm)), s_pool * (1 + rng.normal(0, 5e-4, G * Np))])
+    n_iter, burn = 700, 300
+    with D.Handle(G, Np, dm + 1, lo, hi, seed=77, burnin=0, theta_snooker=0.1) as h:
+        h.set_model("mvnormal", prior, x=x)
+        h.set_state(theta0)
+        h.run(n_iter)
+        c = h.counters()
+        assert c["persistent_chunks"] > 0
+        cnt, mean, var = h.moments(burn, n_iter - burn)
+        th = h.history_by_slot(burn, n_iter - burn)[0].reshape(-1, dm + 1)
+        acc = h.accept()[:, burn:].mean()
+    assert cnt == th.shape[0]
+    assert np.allclose(mean, th.mean(axis=0), rtol=1e-12, atol=1e-13) and np.allclose(var, th.var(axis=0, ddof=1), rtol=1e-8)
+    assert 0.01 < acc < 0.6, acc
+    post_mean = n * xbar / (n + 1.0)
+    post_sd = s_pool / np.sqrt(n + 1.0)
+    z = (mean[:dm] - post_mean) / post_sd
+    assert np.max(np.abs(z)) < 0.6, np.max(np.abs(z))                     # pooled mean of ~1e5 correlated draws
+    ratio = np.sqrt(var[:dm]) / post_sd
+    assert 0.6 < ratio.min() and ratio.max() < 1.5, (ratio.min(), ratio.max())
+    assert abs(mean[dm] / s_pool - 1.0) < 2e-3
+
+
 def test_lba_full_size_additivity():
     """Config 3 shape (1e5 trials): additivity over trial slices and agreement with the oracle on
     a bounded sample of particles."""
