@@ -697,6 +697,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         return 0;
     };
 
+    int64_t chunks_this_call = 0;
     for (int64_t it = 0; it < n_iter;) {
         if (int rc = seg_begin()) { cleanup(); return rc; }
         // ---- migration! (main.jl:85, migration.jl:11-19) on the current row, in place -----------
@@ -744,9 +745,14 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // consecutive iterations without a migration and without a sweep-start snapshot overlap on
         // the device: plan them as one chunk (planner.h)
         int n = 1;
+        // slow start: the device idles while the host plans the first chunk of a call (49 ms for 16
+        // sweeps of 32768 particles), so the first chunks are short -- 2, 4, 8 sweeps -- and the long
+        // ones are planned while the device is busy with their predecessors
+        const int chunk_cap = (int)std::min<int64_t>(h->max_chunk, (int64_t)2 << std::min<int64_t>(chunks_this_call, 8));
+        ++chunks_this_call;
         if (!needs_snapshot(it) && h->max_chunk > 1 && !cfg.donors) {   // resample reads rows of earlier sweeps: one sweep per chunk
             MigSchedule m2;
-            while (it + n < n_iter && n < h->max_chunk) {
+            while (it + n < n_iter && n < chunk_cap) {
                 get_mig(it + n, m2);
                 if (m2.migrate || needs_snapshot(it + n)) break;
                 ++n;
