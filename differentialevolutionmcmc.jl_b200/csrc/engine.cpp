@@ -36,6 +36,10 @@ namespace {
 struct Row { double *theta; double *w; int32_t *id; uint8_t *acc; };
 
 struct Upload {            // pinned staging + device copy of one sweep's schedule
+    // ONE pinned block and ONE device block per slot, copied with one cudaMemcpyAsync per chunk:
+    // [SweepCtx x MAX_CHUNK][mutate flags MAX_CHUNK x G, padded][level-sorted entries MAX_CHUNK x P]
+    uint8_t *h_blk = nullptr, *d_blk = nullptr;
+    size_t off_mut = 0, off_order = 0, bytes = 0;
     int32_t *h_order = nullptr, *d_order = nullptr;   // [MAX_CHUNK][P] level-sorted entries
     uint8_t *h_mut = nullptr, *d_mut = nullptr;       // [MAX_CHUNK][G]
     SweepCtx *h_ctx = nullptr, *d_ctx = nullptr;      // [MAX_CHUNK]
@@ -233,14 +237,17 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
               h->prop_prior && h->prop_adj && h->prop_msq && h->prop_inb && h->ll_acc && h->ll_q && h->base_th && h->base_cw && h->base_tot && h->d_picks && h->d_stage && h->d_stage_recv;
     for (int i = 0; i < demcmc_handle::RING && ok; ++i) {
         Upload &u = h->ring[i];
-        u.h_order = (int32_t *)be::hmalloc_pinned(sizeof(int32_t) * P * MAX_CHUNK);
-        u.h_mut = (uint8_t *)be::hmalloc_pinned(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
-        u.h_ctx = (SweepCtx *)be::hmalloc_pinned(sizeof(SweepCtx) * MAX_CHUNK);
-        u.d_order = (int32_t *)be::dmalloc(sizeof(int32_t) * P * MAX_CHUNK);
-        u.d_mut = (uint8_t *)be::dmalloc(std::max<size_t>(16, (size_t)h->G_local * MAX_CHUNK));
-        u.d_ctx = (SweepCtx *)be::dmalloc(sizeof(SweepCtx) * MAX_CHUNK);
+        u.off_mut = sizeof(SweepCtx) * MAX_CHUNK;
+        u.off_order = (u.off_mut + (size_t)h->G_local * MAX_CHUNK + 63) & ~(size_t)63;
+        u.bytes = u.off_order + sizeof(int32_t) * P * MAX_CHUNK;
+        u.h_blk = (uint8_t *)be::hmalloc_pinned(u.bytes);
+        u.d_blk = (uint8_t *)be::dmalloc(u.bytes);
         u.copied = be::event_create();
-        ok = u.h_order && u.h_mut && u.h_ctx && u.d_order && u.d_mut && u.d_ctx && u.copied;
+        ok = u.h_blk && u.d_blk && u.copied;
+        if (ok) {
+            u.h_ctx = (SweepCtx *)u.h_blk; u.h_mut = u.h_blk + u.off_mut; u.h_order = (int32_t *)(u.h_blk + u.off_order);
+            u.d_ctx = (SweepCtx *)u.d_blk; u.d_mut = u.d_blk + u.off_mut; u.d_order = (int32_t *)(u.d_blk + u.off_order);
+        }
     }
     if (!ok) { demcmc_destroy(h); return fail(DEMCMC_ENOMEM, "device allocation failed: %s", be::last_error()); }
     if (be::h2d(h->d_lo, h->lo.data(), sizeof(double) * d) || be::h2d(h->d_hi, h->hi.data(), sizeof(double) * d) ||
@@ -269,7 +276,7 @@ int demcmc_destroy(demcmc_handle *h)
                      h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
-    for (auto &u : h->ring) { be::hfree_pinned(u.h_order); be::hfree_pinned(u.h_mut); be::hfree_pinned(u.h_ctx); be::dfree(u.d_order); be::dfree(u.d_mut); be::dfree(u.d_ctx); be::event_destroy(u.copied); }
+    for (auto &u : h->ring) { be::hfree_pinned(u.h_blk); be::dfree(u.d_blk); be::event_destroy(u.copied); }
     delete h;
     return 0;
 }
@@ -612,9 +619,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 for (int g = g0; g < g1; ++g) mut[(size_t)s2 * G + g] = pl.mutate[(size_t)s2 * (g1 - g0) + (g - g0)];
         }
         memcpy(u.h_mut, mut.data(), mut.size());
-        BE(be::h2d(u.d_order, u.h_order, sizeof(int32_t) * (size_t)n_sw * P));
-        BE(be::h2d(u.d_mut, u.h_mut, (size_t)n_sw * G));
-        BE(be::h2d(u.d_ctx, u.h_ctx, sizeof(SweepCtx) * (size_t)n_sw));
+        BE(be::h2d(u.d_blk, u.h_blk, u.off_order + sizeof(int32_t) * (size_t)n_sw * P));   // contexts, flags and entries in one copy
         BE(be::event_record(u.copied));
         u.armed = true;
 
