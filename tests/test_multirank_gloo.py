@@ -88,3 +88,72 @@ def test_two_ranks_equal_one(tmp_path, emu):
     # each rank logged the picks of its own groups
     merged = np.maximum(parts[0]["mig"], parts[1]["mig"])
     assert np.array_equal(merged, mig)
+
+
+WORKER_API = r'''
+import ctypes as C, os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DEMCMC_ROOT"]); sys.path.insert(0, os.path.join(os.environ["DEMCMC_ROOT"], "tests"))
+import common
+from common import D
+from demcmc_b200 import distributed
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["MASTER_PORT"], rank=rank, world_size=world)
+common.use_emu()
+L = D._ffi.lib()
+FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p)
+def exchange(rk, n, src, dst, send, recv, row_len, user):
+    reqs, bufs = [], []
+    for i in range(n):
+        if src[i] == dst[i]:
+            continue
+        r = (i + n - 1) % n
+        if rk == src[i]:
+            t = torch.from_numpy(np.ctypeslib.as_array(send, shape=(n * row_len,))[r * row_len:(r + 1) * row_len].copy())
+            reqs.append(dist.isend(t, dst[i], tag=i))
+        if rk == dst[i]:
+            t = torch.empty(row_len, dtype=torch.float64)
+            bufs.append((r, t))
+            reqs.append(dist.irecv(t, src[i], tag=i))
+    for q in reqs:
+        q.wait()
+    out = np.ctypeslib.as_array(recv, shape=(n * row_len,))
+    for r, t in bufs:
+        out[r * row_len:(r + 1) * row_len] = t.numpy()
+    return 0
+cb = FN(exchange)
+L.demcmc_emu_set_exchange(cb, None)
+exec(os.environ["DEMCMC_MODEL"])
+chains = distributed.sample(model, de, 50, device=0, unique_id=b"\\0" * 128)
+if rank == 0:
+    np.save(os.environ["DEMCMC_OUT"] + ".npy", chains.value)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+MODEL = r'''
+rng = np.random.default_rng(3)
+x = np.random.default_rng(11).normal(0.3, 1.2, 40)
+model = D.DEModel(sample_prior=lambda: [rng.normal(), abs(rng.standard_cauchy()) + 0.1], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                  loglike=D.GPULoglike("gaussian", x), names=("mu", "sigma"))
+de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=4, Np=5, burnin=20, seed=99, **{"α": 0.5, "θsnooker": 0.2})
+'''
+
+
+def test_distributed_sample_equals_single_process(tmp_path, emu):
+    """demcmc_b200.distributed.sample on two ranks (the user-facing call of a sharded job) returns the
+    very Chains of the single-process sample(): same sample_prior() draws, same seed, ids followed
+    through migrations across the rank boundary, bundle_samples on the gathered history."""
+    out = str(tmp_path / "api")
+    env = dict(os.environ, DEMCMC_ROOT=common.ROOT, DEMCMC_OUT=out, MASTER_PORT="29573", WORLD_SIZE="2", OMP_NUM_THREADS="1", DEMCMC_MODEL=MODEL)
+    procs = [subprocess.Popen([sys.executable, "-c", WORKER_API], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    logs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    got = np.load(out + ".npy")
+    D = common.D
+    ns = {"np": np, "D": D}
+    exec(MODEL, ns)
+    ref = D.sample(ns["model"], ns["de"], 50)
+    assert got.shape == ref.value.shape == (30, 4, 20)
+    assert np.array_equal(got, ref.value)
