@@ -112,6 +112,11 @@ int64_t launch_count();                   // kernels launched so far (for demcmc
 int comm_unique_id(uint8_t id[128]);
 int comm_init(const uint8_t id[128], int rank, int n_ranks, void **comm);
 int comm_destroy(void *comm);
+// every rank contributes bytes_per_rank bytes; recv holds the contributions in rank order (resample
+// on a sharded job: the replicated copy of a history row)
+int comm_allgather(void *comm, const void *send, void *recv, size_t bytes_per_rank);
+// pos[ids[q]] = q for q < n (the id -> position map of a gathered history row)
+int launch_pos_from_ids(const int32_t *ids, int32_t n, int32_t *pos);
 // grouped send/recv of stage rows: for each position i, src_rank[i] sends row send_pos[i] to dst_rank[i]
 int comm_exchange(void *comm, int rank, int n, const int *src_rank, const int *dst_rank, double *stage_send,
                   double *stage_recv, int row_len);

@@ -113,7 +113,7 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
         g1 = ctx.t_g1[p]; g2 = ctx.t_g2[p];
     } else {
         if (cfg.resample) {
-            const PlanHist pl = plan_particle_hist(cfg.seed, ctx.sweep, unit, mutate, cfg.theta_snooker, ctx.donor_rows, (int64_t)cfg.G_local * Np);
+            const PlanHist pl = plan_particle_hist(cfg.seed, ctx.sweep, unit, mutate, cfg.theta_snooker, ctx.donor_rows, (int64_t)cfg.P_hist);
             kind = pl.kind; i0 = pl.id[0]; i1 = pl.id[1]; i2 = pl.id[2]; hr0 = pl.row[0]; hr1 = pl.row[1]; hr2 = pl.row[2]; u_base = pl.u_base;
         } else {
             const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
@@ -136,7 +136,7 @@ DE_PRAGMA_UNROLL
     co.dependency_wait();
     // a donor that sits before the target in the sweep already holds this sweep's value; with
     const size_t gbase = (size_t)g * Np;
-    const size_t P_all = (size_t)cfg.G_local * Np;
+    const size_t P_all = (size_t)cfg.P_hist;
 #define DE_SLOT(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
 #define DE_HIST(r, id) (ctx.hist_theta + ((size_t)(r) * P_all + (size_t)ctx.hist_pos[(size_t)(r) * P_all + (size_t)(id)]) * d)
 #define DE_DONOR(k, r) (cfg.resample ? DE_HIST(r, k) : DE_SLOT(k))

@@ -68,6 +68,8 @@ DE_HD int64_t ssd_pack_index(int64_t i, int k, int ksplit_len, int nj, int64_t n
 struct ConfigDev {
     int32_t Np, d, G_local, group_begin, proposal, burnin, n_blocks;
     int32_t resample;         // de.sample = resample: donors are (row, id) cells of the history
+    int32_t P_hist;           // particle ids per history row the donors are drawn from: all P of the job (a sharded
+                              // job keeps a replicated copy of every row, gathered over the ranks after each iteration)
     int32_t update, fitness;  // UPDATE_* / FITNESS_*: mh_update! + compute_posterior!, or the optimize path
     double eps, sigma, kappa, theta_snooker;
     const double *lo, *hi;    // [d]

@@ -65,6 +65,11 @@ struct demcmc_handle {
     int32_t *hist_id = nullptr;
     uint8_t *hist_acc = nullptr;
     int32_t *hist_pos = nullptr;                        // resample: [row][id] -> position holding that id
+    // resample on a sharded job: every rank keeps a replicated copy of every history row of ALL ranks
+    // (positions in rank order) and its id -> global position map, gathered after each iteration
+    double *ghist_theta = nullptr;                      // [row][P_total][d]
+    int32_t *ghist_pos = nullptr;                       // [row][P_total]
+    int32_t *gid_tmp = nullptr;                         // [P_total] gathered ids of one row
     int64_t n0 = 0;                                     // de.n_initial: history rows before iteration 1
     bool has_history = false;                           // the n_initial prior rows were uploaded
     double *scr_theta = nullptr, *scr_w = nullptr;      // 3 scratch rows
@@ -138,8 +143,34 @@ static int grow_history(demcmc_handle *h, int64_t need)
         if (np) BE(be::d2d(np, h->hist_pos, sizeof(int32_t) * have * P));
         BE(be::sync());
     }
+    if (h->cfg.donors && h->n_ranks > 1) {
+        const size_t Pt = (size_t)h->cfg.n_groups * h->cfg.Np;
+        double *gt = (double *)be::dmalloc(sizeof(double) * cap * Pt * d);
+        int32_t *gp = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * Pt);
+        if (!h->gid_tmp) h->gid_tmp = (int32_t *)be::dmalloc(sizeof(int32_t) * Pt);
+        if (!gt || !gp || !h->gid_tmp) return fail(DEMCMC_ENOMEM, "replicated history of %lld rows does not fit on the device", (long long)cap);
+        if (have > 0 && h->ghist_theta) {
+            BE(be::d2d(gt, h->ghist_theta, sizeof(double) * have * Pt * d));
+            BE(be::d2d(gp, h->ghist_pos, sizeof(int32_t) * have * Pt));
+            BE(be::sync());
+        }
+        be::dfree(h->ghist_theta); be::dfree(h->ghist_pos);
+        h->ghist_theta = gt; h->ghist_pos = gp;
+    }
     be::dfree(h->hist_theta); be::dfree(h->hist_w); be::dfree(h->hist_id); be::dfree(h->hist_acc); be::dfree(h->hist_pos);
     h->hist_theta = nt; h->hist_w = nw; h->hist_id = ni; h->hist_acc = na; h->hist_pos = np; h->hist_cap = cap;
+    return 0;
+}
+
+// resample on a sharded job: the replicated copy of history row `row` (theta and the id -> position
+// map) from every rank's slice, in rank order = global position order
+static int gather_row(demcmc_handle *h, int64_t row)
+{
+    const size_t P = h->P, d = h->d, Pt = (size_t)h->cfg.n_groups * h->cfg.Np;
+    if (be::comm_allgather(h->comm, h->hist_theta + (size_t)row * P * d, h->ghist_theta + (size_t)row * Pt * d, sizeof(double) * P * d) ||
+        be::comm_allgather(h->comm, h->hist_id + (size_t)row * P, h->gid_tmp, sizeof(int32_t) * P) ||
+        be::launch_pos_from_ids(h->gid_tmp, (int32_t)Pt, h->ghist_pos + (size_t)row * Pt))
+        return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
     return 0;
 }
 
@@ -190,7 +221,6 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     if (cfg->donors == DEMCMC_DONORS_HISTORY) {
         // resample (crossover.jl:113-124) draws from rows 1:de.iter-1: there must be rows to draw from
         if ((int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3) return fail(DEMCMC_EINVAL, "sample = resample needs n_initial prior rows (at least 3 stored particles)");
-        if (cfg->group_count > 0 && cfg->group_count != cfg->n_groups) return fail(DEMCMC_EUNSUPPORTED, "sample = resample reads the history of every particle id: it is not sharded over GPUs yet");
     }
     if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
     if (be::set_device(cfg->device) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
@@ -258,7 +288,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     ConfigDev &c = h->dcfg;
     c.Np = cfg->Np; c.d = cfg->d; c.G_local = h->G_local; c.group_begin = cfg->group_begin; c.proposal = cfg->proposal;
     c.burnin = cfg->burnin; c.n_blocks = cfg->n_blocks; c.eps = cfg->eps; c.sigma = cfg->sigma; c.kappa = cfg->kappa;
-    c.resample = cfg->donors; c.update = cfg->update; c.fitness = cfg->fitness; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
+    c.resample = cfg->donors; c.P_hist = h->P; c.update = cfg->update; c.fitness = cfg->fitness; c.theta_snooker = cfg->theta_snooker; c.lo = h->d_lo; c.hi = h->d_hi; c.blocks = h->d_blocks; c.seed = cfg->seed;
     *out = h;
     return 0;
 }
@@ -269,6 +299,7 @@ int demcmc_destroy(demcmc_handle *h)
     be::set_device(h->cfg.device);
     be::sync();
     be::timeline_dump();
+    be::dfree(h->ghist_theta); be::dfree(h->ghist_pos); be::dfree(h->gid_tmp);
     if (h->comm) be::comm_destroy(h->comm);
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
@@ -386,17 +417,30 @@ int demcmc_set_history(demcmc_handle *h, const double *rows)
     if (!h || !rows) return fail(DEMCMC_EINVAL, "null argument");
     if (h->n0 <= 0) return fail(DEMCMC_EINVAL, "the handle was created with n_initial = 0");
     if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_history must come before the first run");
-    if (h->G_local != h->cfg.n_groups) return fail(DEMCMC_EUNSUPPORTED, "initial history rows of a sharded job");
+    // sample = resample on a sharded job: rows of ALL ids (the donors' history is replicated); otherwise the
+    // rows of the handle's own particles
+    const bool sharded = h->G_local != h->cfg.n_groups && h->cfg.donors;
+    if (sharded && h->n_ranks <= 1) return fail(DEMCMC_ESTATE, "initial history rows of a sharded resample job: demcmc_comm_init must come first");
     BE(be::set_device(h->cfg.device));
     if (int rc = grow_history(h, h->n0)) return rc;
     const size_t P = h->P, d = h->d, n = (size_t)h->n0 * P;
+    const size_t Pt = (size_t)h->cfg.n_groups * h->cfg.Np, pbeg = (size_t)h->cfg.group_begin * h->cfg.Np;
     // initialize_samples (utilities.jl:35-39): samples[i, :, p] by particle id; before any
-    // migration id == position, accept = false and lp = 0.0 (utilities.jl:18-20)
+    // migration id == position, accept = false and lp = 0.0 (utilities.jl:18-20).  A sharded job
+    // passes the rows of ALL ids ([n_initial][P_total][d]): its slice is this rank's history, the
+    // whole is the replicated copy the donors are drawn from.
     std::vector<int32_t> idv(n);
-    for (size_t i = 0; i < n; ++i) idv[i] = (int32_t)(i % P);
-    BE(be::h2d(h->hist_theta, rows, sizeof(double) * n * d));
+    for (size_t i = 0; i < n; ++i) idv[i] = (int32_t)(pbeg + i % P);
+    if (!sharded) BE(be::h2d(h->hist_theta, rows, sizeof(double) * n * d));
+    else {
+        for (int64_t r = 0; r < h->n0; ++r) BE(be::h2d(h->hist_theta + (size_t)r * P * d, rows + ((size_t)r * Pt + pbeg) * d, sizeof(double) * P * d));
+        std::vector<int32_t> gid((size_t)h->n0 * Pt);
+        for (size_t i = 0; i < gid.size(); ++i) gid[i] = (int32_t)(i % Pt);
+        BE(be::h2d(h->ghist_theta, rows, sizeof(double) * (size_t)h->n0 * Pt * d));
+        BE(be::h2d(h->ghist_pos, gid.data(), sizeof(int32_t) * gid.size()));
+    }
     BE(be::h2d(h->hist_id, idv.data(), sizeof(int32_t) * n));
-    if (h->hist_pos) BE(be::h2d(h->hist_pos, idv.data(), sizeof(int32_t) * n));
+    if (h->hist_pos) { for (size_t i = 0; i < n; ++i) idv[i] = (int32_t)(i % P); BE(be::h2d(h->hist_pos, idv.data(), sizeof(int32_t) * n)); }
     BE(be::dzero(h->hist_w, sizeof(double) * n));
     BE(be::dzero(h->hist_acc, n));
     BE(be::sync());
@@ -438,7 +482,9 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     const int64_t Pt = (int64_t)Gt * Np, S = n_iter * B;
     const int64_t pbeg = (int64_t)cfg.group_begin * Np;
     if (h->n0 > 0 && !h->has_history) return fail(DEMCMC_ESTATE, "n_initial > 0: demcmc_set_history must come before run");
-    if (cfg.donors && h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "sample = resample is not sharded over GPUs yet");
+    if (cfg.donors && G != Gt && h->n_ranks <= 1) return fail(DEMCMC_ESTATE, "sample = resample on a sharded job reads the history of every particle id: demcmc_comm_init must come first");
+    const bool ghist = cfg.donors && h->n_ranks > 1;              // donors come from the replicated history
+    h->dcfg.P_hist = ghist ? (int32_t)Pt : (int32_t)P;
     if (cfg.donors && h->iter_offset > 0) return fail(DEMCMC_EUNSUPPORTED, "sample = resample draws donors from the rows of earlier iterations: a resumed handle does not hold them");
     if (int rc = grow_history(h, h->n0 + h->iters_done + n_iter)) return rc;
 
@@ -578,8 +624,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
             // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)
-            ctx.hist_theta = h->hist_theta; ctx.hist_pos = h->hist_pos; ctx.donor_rows = h->n0 + itg;
-            ctx.next_pos = (b == B - 1 && h->hist_pos) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
+            ctx.hist_theta = ghist ? h->ghist_theta : h->hist_theta; ctx.hist_pos = ghist ? h->ghist_pos : h->hist_pos; ctx.donor_rows = h->n0 + itg;
+            ctx.next_pos = (b == B - 1 && h->hist_pos && !ghist) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
@@ -735,14 +781,18 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                     incoming = h->d_stage_recv;
                 }
                 BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc,
-                                          (h->hist_pos && h->cur_hist >= 0) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr));
+                                          (h->hist_pos && h->cur_hist >= 0 && !ghist) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr));
             }
+            // the migration edited a stored row: refresh its replicated copy (collective: every rank, the
+            // schedule is the same everywhere)
+            if (ghist && h->cur_hist >= 0) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
             mig_events.emplace_back(it, ms);
         }
 
         // ---- update! (main.jl:161-167) -------------------------------------------------------------
         if (B > 1) {                                  // blocking: every block is one sweep, one chunk each
             for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1)) { cleanup(); return rc; }
+            if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
             if (int rc = seg_end()) { cleanup(); return rc; }
             ++it;
             continue;
@@ -764,6 +814,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             }
         }
         if (int rc = run_chunk(it, 0, n)) { cleanup(); return rc; }
+        if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }     // n == 1 with resample
         if (int rc = seg_end()) { cleanup(); return rc; }
         it += n;
     }

@@ -2198,6 +2198,7 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -2211,6 +2212,7 @@ static int nccl_load()
 #define SYM(field, sym) do { *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, sym); if (!g_nccl.field) { g_be_err = std::string("libnccl misses ") + sym; g_nccl.lib = nullptr; return -1; } } while (0)
     SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
     SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(AllGather, "ncclAllGather");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return 0;
@@ -2263,6 +2265,22 @@ int comm_init(const uint8_t id[128], int rank, int n_ranks, void **comm)
 int comm_destroy(void *comm)
 {
     (void)comm;                                              // owned by the per-device slot above
+    return 0;
+}
+int comm_allgather(void *comm, const void *send, void *recv, size_t bytes_per_rank)
+{
+    NC(g_nccl.AllGather(send, recv, bytes_per_rank, 0 /* ncclInt8 */, (nccl_comm)comm, stream()));
+    return 0;
+}
+__global__ void __launch_bounds__(256) k_pos_from_ids(const int32_t *ids, int n, int32_t *pos)
+{
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q < n) { const int id = ids[q]; if (id >= 0 && id < n) pos[id] = q; }
+}
+int launch_pos_from_ids(const int32_t *ids, int32_t n, int32_t *pos)
+{
+    k_pos_from_ids<<<(n + 255) / 256, 256, 0, stream()>>>(ids, n, pos);
+    LAUNCHED("k_pos_from_ids");
     return 0;
 }
 int comm_exchange(void *comm, int rank, int n, const int *src_rank, const int *dst_rank, double *stage_send,

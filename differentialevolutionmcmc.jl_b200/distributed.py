@@ -31,8 +31,7 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
     rank, world = dist.get_rank(), dist.get_world_size()
     if de.n_groups % world:
         raise ValueError(f"n_groups = {de.n_groups} does not divide over {world} ranks")
-    if de.sample is resample or de.n_initial > 0:
-        raise NotImplementedError("sample = resample / n_initial > 0 read every particle's history: single GPU for now")
+    init_rows = None
     per = de.n_groups // world
     P, P_local = de.n_groups * de.Np, per * de.Np
     if de.seed is None:                                     # every rank must plan the same migrations
@@ -44,12 +43,31 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
         box = [(unique_id if unique_id is not None else comm_unique_id()) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         h.comm_init(box[0], rank, world)
-        # sample_init (src/main.jl:263-271): one sample_prior() per particle in id order -- drawn once, on rank 0
-        box = [np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64) if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        h.set_state(box[0][rank * P_local:(rank + 1) * P_local])
+        if de.n_initial > 0:
+            # initialize_samples (src/utilities.jl:29-41): n_initial sample_prior() draws per particle id, drawn
+            # once on rank 0; every rank keeps ALL of them (resample draws donors from every id's history) and
+            # init_particle starts each particle from samples[1, :, id] (utilities.jl:15)
+            rows = None
+            if rank == 0:
+                rows = np.empty((de.n_initial, P, d))
+                for p in range(P):
+                    for i in range(de.n_initial):
+                        rows[i, p] = _flatten(model.sample_prior())
+            box = [rows]
+            dist.broadcast_object_list(box, src=0)
+            init_rows = box[0]
+            if de.sample is resample:
+                h.set_history(box[0])
+            else:
+                h.set_history(box[0][:, rank * P_local:(rank + 1) * P_local])
+            h.set_state(None)
+        else:
+            # sample_init (src/main.jl:263-271): one sample_prior() per particle in id order -- drawn once, on rank 0
+            box = [np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            h.set_state(box[0][rank * P_local:(rank + 1) * P_local])
         h.run(n_iter)
-        de.iter = n_iter
+        de.iter = n_iter + de.n_initial
         part = h.history_by_slot()                           # theta[n][P_local][d], w, ids, acc -- by position
         parts = [None] * world if rank == 0 else None
         dist.gather_object(part, parts, dst=0)
@@ -69,5 +87,12 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
     samples[ids, :, rows] = th
     lp[ids, rows] = w
     accept[ids, rows] = acc
+    if init_rows is not None:
+        # rows 1..n_initial of de.samples are the prior draws (utilities.jl:35-39); bundle_samples then keeps
+        # rows burnin+1..n_iter of the n_iter + n_initial array -- not shifted by n_initial (main.jl:226-234)
+        n0 = de.n_initial
+        samples = np.concatenate([init_rows.transpose(1, 2, 0), samples], axis=2)
+        lp = np.concatenate([np.zeros((P, n0)), lp], axis=1)
+        accept = np.concatenate([np.zeros((P, n0), dtype=np.uint8), accept], axis=1)
     de.samples = samples
     return bundle_samples(model, de, samples, accept, lp, ids[-1], shapes, n_iter)

@@ -107,7 +107,7 @@ class Handle:
     def set_history(self, rows):
         """initialize_samples (utilities.jl:29-41): rows[n_initial][P][d], row i = the i-th sample_prior()
         draw of every particle id."""
-        r = f8(rows).reshape(self.n_initial, self.P, self.d)
+        r = f8(rows).reshape(self.n_initial, -1, self.d)     # P of the handle, or P of the whole job when sharded
         check(_ffi.lib().demcmc_set_history(self._h, ptr(r, _dp)))
 
     def set_state(self, theta=None, ids=None):

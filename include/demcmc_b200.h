@@ -95,7 +95,9 @@ typedef struct {
     int32_t donors;          /* de.sample (src/structs.jl:74): DEMCMC_DONORS_CURRENT = `sample` (donors from the
                                 current group, crossover.jl:138-140), DEMCMC_DONORS_HISTORY = `resample`
                                 (DE-MCz: donors from de.samples[1:de.iter-1, :, :], crossover.jl:113-124;
-                                needs n_initial > 0 and demcmc_set_history; single GPU) */
+                                needs n_initial > 0 and demcmc_set_history; on a sharded job every rank keeps a
+                                replicated copy of the history, gathered with ncclAllGather after each
+                                iteration and after each migration) */
     int32_t trace;           /* 1: keep per-sweep proposals / proposal weights / log_adj for
                                 demcmc_get_trace (parity tests) */
     int32_t store_every;     /* 1 = keep every iteration (reference behaviour, utilities.jl:161-180) */
@@ -144,7 +146,9 @@ int demcmc_destroy(demcmc_handle *h);
 /* DEModel(; loglike = GPULoglike(...), prior_loglike = ..., data) (src/structs.jl:176-189) */
 int demcmc_set_model(demcmc_handle *h, const demcmc_model *model);
 /* initialize_samples (src/utilities.jl:29-41) when n_initial > 0: rows[n_initial][P][d], row i = the
- * i-th sample_prior() draw of every particle id; they become rows 1..n_initial of de.samples */
+ * i-th sample_prior() draw of every particle id; they become rows 1..n_initial of de.samples.  A sharded
+ * job passes the rows of its own particles, [n_initial][P_local][d] -- unless sample = resample: then (after
+ * demcmc_comm_init) every rank passes the rows of ALL ids, rows[n_initial][P_total][d]. */
 int demcmc_set_history(demcmc_handle *h, const double *rows);
 /* sample_init / init_particle (src/main.jl:263-271, src/utilities.jl:13-22): theta[P_local][d] by
  * position, ids[P_local] (NULL: id = global position).  Evaluates the initial weights on the device.

@@ -15,11 +15,15 @@ D._ffi.use_library(D._ffi.DEFAULT_LIB)
 n, dm, G, Np, n_iter = 20000, 50, 4 * world, 64, 120
 x = np.random.default_rng(5).normal(np.random.default_rng(6).normal(size=dm), 1.0, size=(n, dm))
 
+RESAMPLE = len(sys.argv) > 1 and sys.argv[1] == "resample"
+
+
 def make():
     rng = np.random.default_rng(3)
     model = D.DEModel(sample_prior=lambda: [rng.normal(size=dm), abs(rng.standard_cauchy()) + 0.2], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
                       loglike=D.GPULoglike("mvnormal", x), names=("mu", "sigma"))
-    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=Np, burnin=40, seed=2026, **{"α": 0.3, "θsnooker": 0.1})
+    extra = dict(n_initial=12, sample=D.resample) if RESAMPLE else {}     # DE-MCz donors: replicated history, ncclAllGather per iteration
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=Np, burnin=40, seed=2026, **{"α": 0.3, "θsnooker": 0.1}, **extra)
     return model, de
 
 model, de = make()
@@ -32,7 +36,7 @@ if rank == 0:
     model, de = make()
     ref = D.sample(model, de, n_iter, device=local)
     same = np.array_equal(chains.value, ref.value)
-    print(f"distributed.sample on {world} GPUs: chains {chains.value.shape}, identical to the single-GPU sample(): {same}; "
+    print(f"distributed.sample{' (sample = resample)' if RESAMPLE else ''} on {world} GPUs: chains {chains.value.shape}, identical to the single-GPU sample(): {same}; "
           f"{G * Np * n_iter / dt:.0f} particle-updates/s end to end", flush=True)
     assert same
 dist.barrier()

@@ -397,6 +397,20 @@ int copy_peak(double *g) { *g = 0.0; return 0; }
 int comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return 0; }
 int comm_init(const uint8_t *, int, int, void **comm) { *comm = malloc(8); return 0; }
 int comm_destroy(void *comm) { free(comm); return 0; }
+typedef int (*allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *user);
+static allgather_fn g_allgather = nullptr;
+static void *g_allgather_user = nullptr;
+int comm_allgather(void *, const void *send, void *recv, size_t bytes_per_rank)
+{
+    if (!g_allgather) { g_err = "emu: no allgather hook installed"; return -1; }
+    return g_allgather(send, recv, bytes_per_rank, g_allgather_user);
+}
+int launch_pos_from_ids(const int32_t *ids, int32_t n, int32_t *pos)
+{
+    ++g_launches;
+    for (int q = 0; q < n; ++q) if (ids[q] >= 0 && ids[q] < n) pos[ids[q]] = q;
+    return 0;
+}
 int comm_exchange(void *, int rank, int n, const int *src_rank, const int *dst_rank, double *send, double *recv, int row_len)
 {
     if (!g_exchange) { g_err = "emu: no exchange hook installed"; return -1; }
@@ -406,6 +420,11 @@ int comm_exchange(void *, int rank, int n, const int *src_rank, const int *dst_r
 } // namespace be
 } // namespace de
 
+extern "C" void demcmc_emu_set_allgather(de::be::allgather_fn fn, void *user)
+{
+    de::be::g_allgather = fn;
+    de::be::g_allgather_user = user;
+}
 extern "C" void demcmc_emu_set_exchange(de::be::exchange_fn fn, void *user)
 {
     de::be::g_exchange = fn;

@@ -114,8 +114,12 @@ def test_abi_error_paths():
         D.Handle(2, 2, 2, case.lo, case.hi)
     with pytest.raises(D._ffi.DemcmcError, match="resample needs n_initial"):
         D.Handle(2, 4, 2, case.lo, case.hi, resample=True)
-    with pytest.raises(D._ffi.DemcmcError, match="not sharded"):
-        D.Handle(2, 4, 2, case.lo, case.hi, resample=True, n_initial=3, group_begin=0, group_count=1)
+    # resample on a shard of the groups reads every particle id's history: the replicated copy needs the communicator
+    hs = D.Handle(2, 4, 2, case.lo, case.hi, resample=True, n_initial=3, group_begin=0, group_count=1)
+    hs.set_model("gaussian", case.prior, x=case.data["x"])
+    with pytest.raises(D._ffi.DemcmcError, match="demcmc_comm_init must come first"):
+        hs.set_history(np.ones((3, 8, 2)))
+    hs.close()
     h = D.Handle(2, 4, 2, case.lo, case.hi, n_initial=2)
     h.set_model("gaussian", case.prior, x=case.data["x"])
     with pytest.raises(D._ffi.DemcmcError, match="null theta"):
