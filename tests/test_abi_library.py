@@ -63,3 +63,26 @@ def test_product_package_never_references_the_oracle_or_the_test_double():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), (f, "mentions the oracle")
                 assert "libdemcmc_emu" not in text, f
+
+
+def test_persistent_kernel_keeps_its_register_budget():
+    """k_chunk_persist raises the register budget of its DMMA warps with setmaxnreg (216) because a tile's B
+    fragments live in registers; ptxas honours that only for some code shapes and otherwise
+    quietly allocates the region within the launch's 128 registers, reloading B fragments from local
+    memory inside the DMMA loop.  The SASS must show registers above 200 in use, the tensor-path and TMA
+    instructions the design rests on, and no spill traffic next to a DMMA."""
+    _build()
+    sass = subprocess.run(["cuobjdump", "-sass", common.CUDA_LIB], capture_output=True, text=True).stdout.split("\n")
+    starts = [i for i, l in enumerate(sass) if "Function :" in l]
+    fn = [i for i in starts if "k_chunk_persistILb0" in sass[i]]
+    assert fn, "k_chunk_persist<false> not in the library"
+    end = min([i for i in starts if i > fn[0]] + [len(sass)])
+    seg = [l for l in sass[fn[0]:end] if "/*" in l and not l.strip().startswith("/* 0x")]
+    regs = max(int(m) for l in seg for m in re.findall(r"\bR(\d+)\b", l))
+    assert regs >= 200, regs
+    text = "\n".join(seg)
+    for mnemonic in ("DMMA.8x8x4", "UBLKCP", "SYNCS", "USETMAXREG", "CCTL.IVALL", "ATOMG.E.ADD.64", "REDG.E.ADD.S32.STRONG.GPU"):
+        assert mnemonic in text, mnemonic
+    spill = [i for i, l in enumerate(seg) if re.search(r"\b(LDL|STL)\b", l)]
+    near = [i for i in spill if any("DMMA" in seg[j] for j in range(max(0, i - 6), min(len(seg), i + 7)))]
+    assert not near, f"{len(near)} local-memory accesses within 6 instructions of a DMMA"
