@@ -1165,17 +1165,6 @@ __device__ __forceinline__ int ld_acquire(const int32_t *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void wait_ge(const int32_t *ctr, int target)
-{
-    if (ld_acquire(ctr) >= target) return;
-    const unsigned long long t0 = gtime();
-    unsigned ns = 64;
-    while (ld_acquire(ctr) < target) {
-        __nanosleep(ns);
-        if (ns < 256) ns += 64;
-        if (gtime() - t0 > 20000000000ull) __trap();
-    }
-}
 // every lane has fenced its own writes before lane 0 publishes
 __device__ __forceinline__ void arrive(int32_t *ctr)
 {
@@ -1212,24 +1201,11 @@ struct FlagWait {
 // waiting for the proposals, in the item (B fragments, DMMA loop, flush) and in the arrive
 enum { PT_P0 = 0, PT_PW, PT_P1, PT_XW0, PT_XW1, PT_X1, PT_AW0, PT_A1, PT_SUM_WAIT, PT_SUM_ITEM, PT_SUM_ARRIVE, PT_ITEMS,
        PT_S_PRE, PT_S_BODY, PT_S_STAGE, PT_S_ARR, PT_S_N, PT_A_BODY, PT_A_ARR, PT_A_N, PT_WORDS = 24 };
-// DMMA warps.  (Deferring the arrive of the previous item behind this item's B-fragment loads was
-// tried: carrying the pending counter across items makes ptxas drop the raised register budget of
-// the setmaxnreg region -- 125 registers and B fragments reloaded from local memory inside the
-// DMMA loop.  scripts/regcheck.sh prints the highest register the kernel uses; keep it near 230.)
-template <bool TL>
-struct DmmaWait {
-    const int32_t *c0; int t0;
-    unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
-    __device__ __forceinline__ void operator()() const
-    {
-        wait_ge(c0, t0);
-        if (TL && tl) {
-            t_done = gtime();
-            if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
-        }
-    }
-    __device__ __forceinline__ void after_loads() const {}
-};
+// (Tried and dropped: the DMMA warps deferring the arrive of a finished item behind the next item's
+// B-fragment loads.  Carrying the pending counter across items made ptxas drop the raised register
+// budget of the setmaxnreg region -- 125 registers, B fragments reloaded from local memory inside
+// the DMMA loop.  The helper warps do that job now; scripts/regcheck.sh and
+// tests/test_abi_library.py watch the register budget.)
 struct FlagLanes : WarpLanes {
     FlagWait w;
     __device__ __forceinline__ void dependency_wait() const { w(); }
