@@ -64,7 +64,7 @@ class Counters(C.Structure):
 SYMBOLS = [
     "demcmc_last_error", "demcmc_abi_version", "demcmc_device_count", "demcmc_backend_name", "demcmc_create",
     "demcmc_destroy", "demcmc_set_model", "demcmc_set_history", "demcmc_set_state", "demcmc_run", "demcmc_replay", "demcmc_get_samples",
-    "demcmc_get_accept", "demcmc_get_lp", "demcmc_get_chains", "demcmc_get_moments", "demcmc_set_iteration", "demcmc_set_weights", "demcmc_get_history_by_slot", "demcmc_get_state", "demcmc_get_trace",
+    "demcmc_get_accept", "demcmc_get_lp", "demcmc_get_chains", "demcmc_get_moments", "demcmc_set_iteration", "demcmc_set_weights", "demcmc_set_blocking_schedule", "demcmc_get_history_by_slot", "demcmc_get_state", "demcmc_get_trace",
     "demcmc_get_migration", "demcmc_get_counters", "demcmc_set_timing", "demcmc_set_max_chunk", "demcmc_set_lanes", "demcmc_eval", "demcmc_op_project", "demcmc_op_reset",
     "demcmc_op_de_proposal", "demcmc_op_snooker", "demcmc_op_accept", "demcmc_op_select", "demcmc_comm_unique_id",
     "demcmc_comm_init", "demcmc_fp64_peak", "demcmc_fp64_peaks", "demcmc_copy_peak",
@@ -94,6 +94,7 @@ def _declare(L):
     L.demcmc_get_chains.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp]
     L.demcmc_set_iteration.argtypes = [C.c_void_p, C.c_int64]
     L.demcmc_set_weights.argtypes = [C.c_void_p, _dp]
+    L.demcmc_set_blocking_schedule.argtypes = [C.c_void_p, _bp, C.c_int64]
     L.demcmc_get_moments.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64), _dp, _dp]
     L.demcmc_get_history_by_slot.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, _ip, _bp]
     L.demcmc_get_state.argtypes = [C.c_void_p, _dp, _dp, _ip]

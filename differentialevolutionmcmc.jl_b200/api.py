@@ -351,7 +351,21 @@ def _prior_table(model, shapes, needed=True):
     return table
 
 
-def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0):
+def _blocking_schedule(de: DE, n_iter):
+    """blocking_on(de) is a function of the sampler, evaluated once per iteration with de.iter = iter +
+    n_initial (src/main.jl:34,137,162): evaluated here for the n_iter iterations to come."""
+    keep = de.iter
+    try:
+        on = []
+        for it in range(1, n_iter + 1):
+            de.iter = it + de.n_initial
+            on.append(bool(de.blocking_on(de)))
+    finally:
+        de.iter = keep
+    return on
+
+
+def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0, n_iter=None):
     """Everything `sample` does before the iteration loop; also used by bench.py and the tests."""
     ll = model.loglike
     if not isinstance(ll, GPULoglike):
@@ -363,15 +377,18 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
     d = len(_flatten(theta0))
     lo = [(-np.inf if b is None else float(b[0])) for b in _expand(list(de.bounds), shapes, "bounds")]
     hi = [(np.inf if b is None else float(b[1])) for b in _expand(list(de.bounds), shapes, "bounds")]
-    blocks = None
-    if de.blocking_on(de):
+    blocks, schedule = None, None
+    on = _blocking_schedule(de, n_iter) if n_iter is not None else [bool(de.blocking_on(de))]
+    if any(on):
         blocks = np.array([_expand_block(b, shapes) for b in de.blocks], dtype=np.uint8)
+        if not all(on):
+            schedule = on                                   # block updating in some iterations only
     seed = de.seed if de.seed is not None else int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
     h = Handle(de.n_groups, de.Np, d, lo, hi, burnin=de.burnin, n_initial=de.n_initial, alpha=de.α, beta=de.β, eps=de.ϵ,
                sigma=de.σ, kappa=de.κ, theta_snooker=de.θsnooker, proposal=_PROPOSAL_NAMES[de.generate_proposal],
                blocks=blocks, seed=seed, device=device, trace=trace, group_begin=group_begin, group_count=group_count,
                resample=de.sample is resample, update={mh_update: "mh", maximize: "maximize", minimize: "minimize"}[de.update_particle],
-               fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior")
+               fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior", blocking_schedule=schedule)
     h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
     return h, shapes, d
 
@@ -385,7 +402,7 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         n_iter = int(args[0])
     else:
         raise TypeError("sample(model, de, n_iter) or sample(model, de, MCMCThreads(), n_iter)")
-    h, shapes, d = build_handle(model, de, device=device)
+    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter)
     try:
         P = de.n_groups * de.Np
         if de.n_initial > 0:
@@ -432,7 +449,7 @@ def optimize(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         n_iter = int(args[0])
     else:
         raise TypeError("optimize(model, de, n_iter) or optimize(model, de, MCMCThreads(), n_iter)")
-    h, shapes, d = build_handle(model, de, device=device)
+    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter)
     try:
         P = de.n_groups * de.Np
         theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)

@@ -61,6 +61,7 @@ struct demcmc_handle {
     // state rows
     int64_t hist_cap = 0, iters_done = 0;
     int64_t iter_offset = 0;                            // iterations the chain ran before this handle (demcmc_set_iteration)
+    std::vector<uint8_t> block_on;                      // blocking_on(de) per absolute iteration (demcmc_set_blocking_schedule); beyond it: on
     double *hist_theta = nullptr, *hist_w = nullptr;
     int32_t *hist_id = nullptr;
     uint8_t *hist_acc = nullptr;
@@ -554,6 +555,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         h->tr_adj = (double *)be::dmalloc(sizeof(double) * S * P);
         h->tr_acc = (uint8_t *)be::dmalloc((size_t)S * P);
         if (!h->tr_theta || !h->tr_w || !h->tr_adj || !h->tr_acc) { cleanup(); return fail(DEMCMC_ENOMEM, "trace buffers do not fit"); }
+        if (!h->block_on.empty()) {                              // sweep slots of unblocked iterations stay unused: read as zero
+            BE(be::dzero(h->tr_theta, sizeof(double) * S * P * d)); BE(be::dzero(h->tr_w, sizeof(double) * S * P));
+            BE(be::dzero(h->tr_adj, sizeof(double) * S * P)); BE(be::dzero(h->tr_acc, (size_t)S * P));
+        }
         h->tr_sweeps = S;
     }
     be::dfree(h->d_mig_log); h->d_mig_log = nullptr; h->mig_log_iters = n_iter;
@@ -590,7 +595,15 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     auto needs_snapshot = [&](int64_t it) { return !tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && in_burnin_at(it); };
 
     // runs `n_sw` consecutive sweeps starting at local iteration it0 (block b) as one chunk
-    auto run_chunk = [&](int64_t it0, int b, int n_sw) -> int {
+    // blocking_on(de) (main.jl:137,162) of local iteration `it`
+    auto blocking_at = [&](int64_t it) {
+        if (B <= 1) return false;
+        const int64_t a = h->iter_offset + h->iters_done + it;
+        return a >= (int64_t)h->block_on.size() || h->block_on[(size_t)a] != 0;
+    };
+    int64_t sweeps_run = 0;
+    auto run_chunk = [&](int64_t it0, int b, int n_sw, bool blocked) -> int {
+        sweeps_run += n_sw;
         const int64_t itg0 = h->iters_done + it0;
         Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
         if (u.armed) BE(be::event_wait(u.copied));             // the pinned slot is free once its copies ran
@@ -598,18 +611,19 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         bool basedep[MAX_CHUNK];
         Row cur = cur_row(h);
         for (int s = 0; s < n_sw; ++s) {
-            const int64_t it = it0 + (B == 1 ? s : 0), itg = itg0 + (B == 1 ? s : 0);
+            const int64_t it = it0 + (blocked ? 0 : s), itg = itg0 + (blocked ? 0 : s);
+            const bool last = !blocked || b == B - 1;             // this sweep completes its iteration
             const int64_t s_local = it * B + b;
             const bool inb = in_burnin_at(it);
             basedep[s] = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && inb;
             // destination row: the history row of the iteration on its last block, else scratch
             Row next;
             int next_scratch = -1;
-            if (b == B - 1) next = row_of(h, true, h->n0 + itg);
+            if (last) next = row_of(h, true, h->n0 + itg);
             else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
             SweepCtx &ctx = u.h_ctx[s];
             memset(&ctx, 0, sizeof ctx);
-            ctx.sweep = (uint32_t)((h->iter_offset + itg) * B + b); ctx.block = cfg.n_blocks > 0 ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
+            ctx.sweep = (uint32_t)((h->iter_offset + itg) * B + b); ctx.block = blocked ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
             ctx.exact_base = tape != nullptr;
             ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
             ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
@@ -625,12 +639,12 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
             // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)
             ctx.hist_theta = ghist ? h->ghist_theta : h->hist_theta; ctx.hist_pos = ghist ? h->ghist_pos : h->hist_pos; ctx.donor_rows = h->n0 + itg;
-            ctx.next_pos = (b == B - 1 && h->hist_pos && !ghist) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
+            ctx.next_pos = (last && h->hist_pos && !ghist) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
             }
-            if (b == B - 1) { h->cur_hist = h->n0 + itg; }
+            if (last) { h->cur_hist = h->n0 + itg; }
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
@@ -647,7 +661,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const int g0 = ln == 0 ? 0 : (G + 1) / 2, g1 = (n_lanes == 1 || ln == 1) ? G : (G + 1) / 2;
             PlanInput pin;
             pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
-            pin.pos_offset = g0 * Np; pin.P_stride = P;
+            pin.pos_offset = g0 * Np; pin.P_stride = blocked ? P : P * B;   // consecutive sweeps of an unblocked chunk are consecutive iterations
+            pin.sweep_stride = blocked ? 1 : B;
             {
                 const char *e = getenv("DEMCMC_SHAPE");       // 0 = off, else the modulus (A/B runs)
                 const int mod = e ? atoi(e) : 8;
@@ -790,8 +805,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         }
 
         // ---- update! (main.jl:161-167) -------------------------------------------------------------
-        if (B > 1) {                                  // blocking: every block is one sweep, one chunk each
-            for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1)) { cleanup(); return rc; }
+        if (blocking_at(it)) {                        // blocking: every block is one sweep, one chunk each
+            for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1, true)) { cleanup(); return rc; }
             if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
             if (int rc = seg_end()) { cleanup(); return rc; }
             ++it;
@@ -809,11 +824,11 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             MigSchedule m2;
             while (it + n < n_iter && n < chunk_cap) {
                 get_mig(it + n, m2);
-                if (m2.migrate || needs_snapshot(it + n)) break;
+                if (m2.migrate || needs_snapshot(it + n) || blocking_at(it + n)) break;
                 ++n;
             }
         }
-        if (int rc = run_chunk(it, 0, n)) { cleanup(); return rc; }
+        if (int rc = run_chunk(it, 0, n, false)) { cleanup(); return rc; }
         if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }     // n == 1 with resample
         if (int rc = seg_end()) { cleanup(); return rc; }
         it += n;
@@ -836,7 +851,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     }
     cleanup();
     h->iters_done += n_iter;
-    h->ctr.iterations += n_iter; h->ctr.sweeps += S; h->ctr.particle_updates += S * P; h->ctr.loglike_evals += S * P;
+    h->ctr.iterations += n_iter; h->ctr.sweeps += sweeps_run; h->ctr.particle_updates += sweeps_run * P; h->ctr.loglike_evals += sweeps_run * P;
     h->ctr.kernel_launches += be::launch_count() - launches0; h->ctr.levels += n_levels; h->ctr.device_ms = ms_dev;
     return 0;
 }
@@ -980,6 +995,14 @@ int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_log
         h->flush_bytes = l2_flush_bytes;
     }
     h->time_loglik = time_loglik != 0;
+    return 0;
+}
+
+int demcmc_set_blocking_schedule(demcmc_handle *h, const uint8_t *on, int64_t n)
+{
+    if (!h || n < 0 || (n > 0 && !on)) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->cfg.n_blocks <= 0) return fail(DEMCMC_EINVAL, "the handle was created without parameter blocks");
+    h->block_on.assign(on, on + n);
     return 0;
 }
 

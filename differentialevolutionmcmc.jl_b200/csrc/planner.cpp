@@ -17,7 +17,7 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
     std::vector<int32_t> deps((size_t)n_sweeps * P * 4, -1);
     int max_level = 0;
     for (int s = 0; s < n_sweeps; ++s) {
-        const uint32_t sweep = sweep0 + (uint32_t)s;
+        const uint32_t sweep = sweep0 + (uint32_t)s * (uint32_t)in.sweep_stride;
         const uint8_t *tk = in.t_kind ? in.t_kind + (size_t)s * stride + in.pos_offset : nullptr;
         const int32_t *ti = in.t_idx ? in.t_idx + ((size_t)s * stride + in.pos_offset) * 3 : nullptr;
         for (int g = 0; g < G; ++g) {

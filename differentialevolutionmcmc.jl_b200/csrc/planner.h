@@ -29,6 +29,8 @@ struct PlanInput {
     int32_t Np, G_local, group_begin, G_total;   // the groups this plan covers: G_local of them from global group group_begin
     int32_t pos_offset = 0;    // local position of the first particle covered (entries and tape slices are offset by it)
     int32_t P_stride = 0;      // particles per sweep in the tape slices (0: Np * G_local)
+    int32_t sweep_stride = 1;  // Philox sweep coordinate of consecutive sweeps of the chunk: sweep0 + s * sweep_stride
+                               // (unblocked iterations of a model with B parameter blocks: B)
     int32_t proposal;          // 0 random_gamma
     double beta, theta_snooker;
     int32_t shape_octets = 0;  // > 0: hand each level's remainder modulo this many updates to the next level where the

@@ -38,7 +38,7 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
         box = [int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0]) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         de.seed = box[0]
-    h, shapes, d = build_handle(model, de, device=rank if device is None else device, group_begin=rank * per, group_count=per)
+    h, shapes, d = build_handle(model, de, device=rank if device is None else device, group_begin=rank * per, group_count=per, n_iter=n_iter)
     try:
         box = [(unique_id if unique_id is not None else comm_unique_id()) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)

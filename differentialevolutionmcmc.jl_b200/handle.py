@@ -20,7 +20,8 @@ class Handle:
 
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None, seed=0,
-                 device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False, update="mh", fitness="posterior"):
+                 device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False, update="mh", fitness="posterior",
+                 blocking_schedule=None):
         self._h = C.c_void_p()
         self.lo, self.hi = f8(lo), f8(hi)
         if self.lo.shape != (d,) or self.hi.shape != (d,):
@@ -42,6 +43,8 @@ class Handle:
         self._last_iters = 0
         self._keep = []
         check(_ffi.lib().demcmc_create(C.byref(self.cfg), C.byref(self._h)))
+        if blocking_schedule is not None:
+            self.set_blocking_schedule(blocking_schedule)
 
     def close(self):
         if self._h:
@@ -177,6 +180,11 @@ class Handle:
         if n > 0:
             check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
         return out
+
+    def set_blocking_schedule(self, on):
+        """blocking_on(de) per iteration (0-based from the chain's first iteration); beyond it: blocked."""
+        a = np.ascontiguousarray(on, dtype=np.uint8).reshape(-1)
+        check(_ffi.lib().demcmc_set_blocking_schedule(self._h, ptr(a, _bp), a.size))
 
     def set_weights(self, w):
         """The weights the saved particles carried (get_state()[1]); after set_state."""

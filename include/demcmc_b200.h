@@ -182,6 +182,12 @@ int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *ou
  * handle start at 0.  Before the first run of the handle; not with sample = resample (its donors are
  * rows of the earlier iterations). */
 int demcmc_set_iteration(demcmc_handle *h, int64_t iterations_done);
+/* blocking_on(de) (src/structs.jl:75, main.jl:137,162) is a function of the sampler evaluated every
+ * iteration; the wrapper evaluates it for the iterations to come and passes the result: on[i] != 0 =>
+ * iteration i (0-based, counted from the chain's first iteration: demcmc_set_iteration included) runs
+ * block_update! over the handle's blocks, else update! with every parameter at once.  Iterations beyond
+ * n are blocked.  Without this call every iteration is blocked (the handle was created with blocks). */
+int demcmc_set_blocking_schedule(demcmc_handle *h, const uint8_t *on, int64_t n);
 /* ... and the weights (Particle.weight, src/structs.jl:205) the saved particles carried, w[P_local] as
  * demcmc_get_state returned them: demcmc_set_state re-evaluates them, which for the pointwise models sums
  * the observations in another order (same value to ~1e-15 relative, not the same bits). */

@@ -200,8 +200,12 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
     P = length(particles)
     theta0 = reduce(hcat, (flatten_theta(p.Θ) for p in particles))          # d × P == C [P][d]
     lo, hi = expand_bounds(de.bounds, Θ1)
-    blocks = de.blocking_on(de) ? reduce(vcat, (expand_block(b, Θ1) for b in de.blocks)) : UInt8[]
-    n_blocks = de.blocking_on(de) ? length(de.blocks) : 0
+    # blocking_on(de) is evaluated every iteration with de.iter = iter + n_initial (src/main.jl:34,137,162)
+    iter_keep = de.iter
+    block_on = UInt8[(de.iter = it + de.n_initial; de.blocking_on(de) ? 1 : 0) for it = 1:n_iter]
+    de.iter = iter_keep
+    blocks = any(!iszero, block_on) ? reduce(vcat, (expand_block(b, Θ1) for b in de.blocks)) : UInt8[]
+    n_blocks = any(!iszero, block_on) ? length(de.blocks) : 0
     priors = prior_table(model, Θ1)
     x = ll.data.x
     choice = ll.data.choice
@@ -239,6 +243,9 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
                 isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0)
             demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
+            if n_blocks > 0 && !all(!iszero, block_on)         # block updating in some iterations only
+                GC.@preserve block_on demcmc_check(ccall((:demcmc_set_blocking_schedule, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], block_on, length(block_on)))
+            end
             if de.n_initial > 0
                 demcmc_check(ccall((:demcmc_set_history, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}), h[], init_rows))
             end

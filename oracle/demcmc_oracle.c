@@ -721,7 +721,8 @@ int orc_run(const orc_config *cfg, const orc_model *model, const double *theta0,
         /* update! / p_update! (main.jl:135-167): groups are independent between migrations */
         #pragma omp parallel for schedule(dynamic, 1) num_threads(cfg->n_threads > 1 ? cfg->n_threads : 1)
         for (int g = 0; g < G; ++g) {
-            if (cfg->n_blocks > 0) for (int bl = 0; bl < cfg->n_blocks; ++bl) update_group(S, g, it, bl); /* block_update! (main.jl:174-179) */
+            const int on = cfg->n_blocks > 0 && (!cfg->block_on || it >= cfg->n_block_on || cfg->block_on[it]);   /* de.blocking_on(de) (main.jl:137,162) */
+            if (on) for (int bl = 0; bl < cfg->n_blocks; ++bl) update_group(S, g, it, bl); /* block_update! (main.jl:174-179) */
             else update_group(S, g, it, -1);
         }
         /* store_samples! (utilities.jl:161-180): samples[iter, :, p.id] = p.Theta */

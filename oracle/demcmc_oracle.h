@@ -78,6 +78,12 @@ typedef struct {
     int32_t update;          /* ORC_UPDATE_*: mh_update!, maximize!, minimize! (the optimize path) */
     int32_t fitness;         /* ORC_FITNESS_*: compute_posterior! or evaluate_fun! (loglike only, no prior) */
     int32_t reserved;
+    /* blocking_on(de) per iteration (main.jl:137,162: a function of the sampler, evaluated every
+     * iteration): block_on[it] != 0 => block_update! in iteration it, else update! (all parameters at
+     * once).  NULL, or it >= n_block_on => on whenever n_blocks > 0.  A sweep of an unblocked
+     * iteration is sweep slot it*B + 0 of the tape / trace arrays; slots 1..B-1 stay unused. */
+    const uint8_t *block_on;
+    int64_t n_block_on;
 } orc_config;
 
 /* Structured replay tape.  All indices are 0-based slot indices inside

@@ -42,7 +42,8 @@ class _Config(C.Structure):
                 ("sigma", C.c_double), ("kappa", C.c_double), ("theta_snooker", C.c_double),
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
                 ("base_snapshot", C.c_int32), ("n_threads", C.c_int32), ("seed", C.c_uint64),
-                ("resample", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32), ("reserved", C.c_int32)]
+                ("resample", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32), ("reserved", C.c_int32),
+                ("block_on", _bp), ("n_block_on", C.c_int64)]
 
 
 _TAPE_FIELDS = [("mig_u", "f8"), ("mig_n", "i4"), ("mig_groups", "i4"), ("mig_pick_u", "f8"), ("mig_slots", "i4"),
@@ -131,7 +132,7 @@ class Model:
 class Config:
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None,
-                 base_snapshot=0, n_threads=1, seed=0, resample=False, update="mh", fitness="posterior"):
+                 base_snapshot=0, n_threads=1, seed=0, resample=False, update="mh", fitness="posterior", blocking_schedule=None):
         self.lo, self.hi = _f8(lo), _f8(hi)
         assert self.lo.shape == (d,) and self.hi.shape == (d,)
         self.blocks = None if blocks is None else np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, d)
@@ -141,6 +142,11 @@ class Config:
         self.c = _Config(n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa, theta_snooker,
                          PROPOSALS[proposal], nb, _ptr(self.blocks, _bp), _ptr(self.lo, _dp), _ptr(self.hi, _dp),
                          int(base_snapshot), int(n_threads), int(seed), int(bool(resample)), UPDATES[update], FITNESS[fitness], 0)
+        # blocking_on(de) per iteration (main.jl:137,162); None = on in every iteration (when there are blocks)
+        self.blocking_schedule = None if blocking_schedule is None else np.ascontiguousarray(blocking_schedule, dtype=np.uint8)
+        if self.blocking_schedule is not None:
+            self.c.block_on = _ptr(self.blocking_schedule, _bp)
+            self.c.n_block_on = self.blocking_schedule.size
         self.resample = bool(resample)
         self.n_groups, self.Np, self.d, self.n_initial = n_groups, Np, d, n_initial
         self.B = max(1, nb)

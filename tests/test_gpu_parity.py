@@ -364,6 +364,30 @@ def test_device_bundle_matches_bundle_samples():
     h.close()
 
 
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_blocking_on_as_a_function_of_the_iteration(mode):
+    """blocking_on(de) is evaluated every iteration (main.jl:137,162): a schedule that switches block updating
+    on and off -- block_update! over the blocks in some iterations, update! with all parameters in the others,
+    consecutive unblocked iterations overlapped in one chunk."""
+    case = make_case("hier_normal", np.random.default_rng(91))
+    sched = [1, 0, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 0, 1]
+    r, out = forced_run(case, 2, 8, len(sched), mode, burnin=6, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched)
+    check(r, out)
+    # unforced, as one call: same chain as iteration by iteration in native mode
+    if mode == "native":
+        theta0 = case.theta0(np.random.default_rng(0), 16)
+        h = case.handle(2, 8, seed=5, burnin=6, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched)
+        h.set_state(theta0)
+        h.run(len(sched))
+        assert h.counters()["sweeps"] == sum(2 if s else 1 for s in sched)
+        h.close()
+    # unforced and short: runs of unblocked iterations share a chunk (overlapped sweeps with the blocks' sweep stride)
+    sched2 = [0, 0, 0, 1, 0, 0, 0, 0]
+    r, out = compare_run(case, 2, 8, len(sched2), mode, burnin=3, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched2)
+    assert np.array_equal(out["accept"], r["accept"])
+    assert rel_err(out["samples"], r["samples"]) < 1e-9
+
+
 def test_checkpoint_resume_is_exact():
     """run(a) + get_state + a NEW handle (set_state, set_weights, set_iteration) + run(b) = run(a + b): the
     Philox counters, the burn-in switch and the migration schedule continue."""

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import common
-from common import ALL_MODELS, D, O, compare_run, hier_blocks, make_case, rel_err
+from common import ALL_MODELS, D, O, compare_run, forced_run, hier_blocks, make_case, rel_err
 
 pytestmark = pytest.mark.usefixtures("emu")
 
@@ -185,6 +185,37 @@ def test_sample_api_gaussian_posterior():
     assert len(D.sample(model, de2, D.MCMCThreads(), 250)) == 250
 
 
+def test_sample_api_blocking_on_function():
+    """DE(blocking_on = de -> ..., blocks = ...): the wrapper evaluates the function for every iteration with
+    de.iter = iter + n_initial (src/main.jl:34,137,162) and hands the schedule to the library -- the chains
+    equal those of a handle given the same schedule explicitly."""
+    def make():
+        rng = np.random.default_rng(12)
+        data = np.random.default_rng(13).normal(0.4, 1.3, 40)
+        model = D.DEModel(sample_prior=lambda: [rng.normal(0, 3), abs(rng.standard_cauchy()) + 0.1],
+                          prior_loglike=D.GPUPrior(D.Normal(0, 10), D.HalfCauchy(0, 1)),
+                          loglike=D.GPULoglike("gaussian", data), names=("μ", "σ"))
+        return model, data
+    model, data = make()
+    seen = []
+    on = lambda de: (seen.append(de.iter), de.iter % 3 == 0)[1]
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), burnin=10, Np=5, n_groups=2, seed=4,
+              blocking_on=on, blocks=[[True, False], [False, True]], discard_burnin=False)
+    chains = D.sample(model, de, 30)
+    assert seen[:30] == list(range(1, 31))
+    model2, _ = make()
+    theta0 = np.array([[*model2.sample_prior()] for _ in range(11)])[1:]        # build_handle draws one for the shapes first
+    h = D.Handle(2, 5, 2, [-np.inf, 0.0], [np.inf, np.inf], burnin=10, seed=4, blocks=np.array([[1, 0], [0, 1]], dtype=np.uint8),
+                 blocking_schedule=[1 if it % 3 == 0 else 0 for it in range(1, 31)])
+    h.set_model("gaussian", [("normal", 0, 10), ("halfcauchy", 0, 1)], x=data)
+    h.set_state(theta0)
+    h.run(30)
+    assert h.counters()["sweeps"] == 30 + 10
+    ref = h.chains(0, 30)
+    h.close()
+    assert np.array_equal(chains.value, ref.transpose(2, 1, 0))
+
+
 def test_closure_raises_instead_of_cpu_fallback():
     model = D.DEModel(sample_prior=lambda: [0.0, 1.0], prior_loglike=D.GPUPrior(D.Normal(), D.HalfCauchy()),
                       loglike=lambda data, mu, sigma: 0.0, names=("μ", "σ"), data=np.zeros(3))
@@ -255,6 +286,30 @@ def test_device_bundle_matches_bundle_samples():
     with pytest.raises(D._ffi.DemcmcError):
         h.chains(25, 10)
     h.close()
+
+
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_blocking_on_as_a_function_of_the_iteration(mode):
+    """blocking_on(de) is evaluated every iteration (main.jl:137,162): a schedule that switches block updating
+    on and off -- block_update! over the blocks in some iterations, update! with all parameters in the others,
+    consecutive unblocked iterations overlapped in one chunk."""
+    case = make_case("hier_normal", np.random.default_rng(91))
+    sched = [1, 0, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 0, 1]
+    r, out = forced_run(case, 2, 8, len(sched), mode, burnin=6, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched)
+    check(r, out)
+    # unforced, as one call: same chain as iteration by iteration in native mode
+    if mode == "native":
+        theta0 = case.theta0(np.random.default_rng(0), 16)
+        h = case.handle(2, 8, seed=5, burnin=6, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched)
+        h.set_state(theta0)
+        h.run(len(sched))
+        assert h.counters()["sweeps"] == sum(2 if s else 1 for s in sched)
+        h.close()
+    # unforced and short: runs of unblocked iterations share a chunk (overlapped sweeps with the blocks' sweep stride)
+    sched2 = [0, 0, 0, 1, 0, 0, 0, 0]
+    r, out = compare_run(case, 2, 8, len(sched2), mode, burnin=3, blocks=hier_blocks(9), alpha=0.3, blocking_schedule=sched2)
+    assert np.array_equal(out["accept"], r["accept"])
+    assert rel_err(out["samples"], r["samples"]) < 1e-9
 
 
 def test_checkpoint_resume_is_exact():
