@@ -670,7 +670,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             }
             pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
             const int64_t s_first = it0 * B + b;
-            pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // B == 1 whenever n_sw > 1: consecutive sweeps
+            pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // a chunk of several sweeps is unblocked: its sweeps are P_stride apart in the tape
             pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
             plan_chunk(pin, (uint32_t)((h->iter_offset + itg0) * B + b), n_sw, basedep, plans[ln]);
             const ChunkPlan &pl = plans[ln];
