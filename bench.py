@@ -32,6 +32,7 @@ METRIC = "particle-updates/sec (loglike evals incl.)"
 UNIT = "particle-updates/s"
 N_OBS, N_DIM, GROUPS_PER_GPU, NP = 100_000, 50, 4, 256
 THETA_SNOOKER = 0.1
+CONFIG_NAME = "BASELINE configs[1]"
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -398,7 +399,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])",
+                "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} ({CONFIG_NAME})",
                            "groups_total": G, "particles_total": G * NP, "parallelism": f"groups sharded over {world} GPU(s); NCCL send/recv migration",
                            "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten before every segment = a migration (with its NCCL exchange) plus the chunk of overlapped steps that follows it (a chunk ends at the next migration, at most 16 steps; steps inside a chunk share launches so there is no per-step boundary); per-segment CUDA events, flush excluded",
                            "timing": "CUDA events on the library's launching stream (demcmc_counters.device_ms), max over ranks"},
@@ -421,7 +422,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s estimate of the e2e leg")
+    # the same step on another BASELINE shape (the contract's line is the default, configs[1]); configs[4] is
+    # --dim 100 --particles 4096 --groups-per-gpu 8 on 8 GPUs
+    ap.add_argument("--dim", type=int, default=None, help="dimensions of the multivariate normal (default 50)")
+    ap.add_argument("--particles", type=int, default=None, help="particles per group (default 256)")
+    ap.add_argument("--groups-per-gpu", type=int, default=None, help="groups per GPU (default 4)")
     args = ap.parse_args()
+    global N_DIM, NP, GROUPS_PER_GPU
+    shape_given = args.dim or args.particles or args.groups_per_gpu
+    N_DIM, NP, GROUPS_PER_GPU = args.dim or N_DIM, args.particles or NP, args.groups_per_gpu or GROUPS_PER_GPU
+    if shape_given:
+        global CONFIG_NAME
+        CONFIG_NAME = ("BASELINE configs[4]: 64 groups x 4096 across 8 GPUs" if (N_DIM, NP, GROUPS_PER_GPU, args.gpus) == (100, 4096, 8, 8)
+                       else "a shape given on the command line, not a BASELINE config")
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
