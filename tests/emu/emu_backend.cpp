@@ -430,3 +430,60 @@ extern "C" void demcmc_emu_set_exchange(de::be::exchange_fn fn, void *user)
     de::be::g_exchange = fn;
     de::be::g_exchange_user = user;
 }
+
+// ---- property check of the planner (tests/test_planner_properties.py): every update of a chunk appears
+// exactly once, and every dependency of an update -- its own previous update, donors with a smaller slot in
+// the same sweep, donors with a larger slot in the previous sweep (crossover.jl:12-17) -- sits in a strictly
+// earlier level, with or without the octet shaping.  Returns 0, or a negative code naming the violation.
+#include "planner.h"
+extern "C" int demcmc_emu_plan_check(uint64_t seed, int Np, int G, int n_sweeps, double beta, double theta_snooker, int shape,
+                                      int sweep_stride, int *n_levels_out, int *padded_out)
+{
+    using namespace de;
+    PlanInput in{};
+    in.seed = seed; in.Np = Np; in.G_local = G; in.group_begin = 0; in.G_total = G; in.proposal = 0; in.beta = beta;
+    in.theta_snooker = theta_snooker; in.resample = false; in.t_kind = nullptr; in.t_idx = nullptr; in.shape_octets = shape;
+    in.sweep_stride = sweep_stride;
+    bool bd[MAX_CHUNK] = { false };
+    ChunkPlan pl;
+    const uint32_t sweep0 = 7;
+    plan_chunk(in, sweep0, n_sweeps, bd, pl);
+    const int P = Np * G;
+    std::vector<int> level((size_t)n_sweeps * P, -1);
+    if ((int)pl.order.size() != n_sweeps * P || (int)pl.level_off.size() != pl.n_levels + 1) return -1;
+    int padded = 0;
+    for (int l = 0; l < pl.n_levels; ++l) {
+        const int n = pl.level_off[l + 1] - pl.level_off[l];
+        if (n < 0) return -2;
+        padded += (n + 7) / 8 * 8;
+        for (int q = pl.level_off[l]; q < pl.level_off[l + 1]; ++q) {
+            const uint32_t e = (uint32_t)pl.order[q];
+            const int s = (int)(e >> ENTRY_SLOT_SHIFT), p = (int)(e & ENTRY_POS_MASK);
+            if (s < 0 || s >= n_sweeps || p < 0 || p >= P || level[(size_t)s * P + p] >= 0) return -3;
+            level[(size_t)s * P + p] = l;
+        }
+    }
+    for (int s = 0; s < n_sweeps; ++s)
+        for (int g = 0; g < G; ++g) {
+            const uint32_t sweep = sweep0 + (uint32_t)s * (uint32_t)sweep_stride;
+            const bool mutate = pl.mutate[(size_t)s * G + g] != 0;
+            if (mutate != (uniform2(seed, ST_MUT, sweep, (uint32_t)g, 0).a <= beta)) return -4;
+            for (int j = 0; j < Np; ++j) {
+                const int me = level[(size_t)s * P + g * Np + j];
+                if (me < 0) return -5;
+                if (s > 0 && level[(size_t)(s - 1) * P + g * Np + j] >= me) return -6;
+                if (mutate) continue;
+                const Plan pp = plan_particle(seed, sweep, (uint32_t)(g * Np + j), j, Np, false, theta_snooker);
+                const int dep[3] = { pp.kind == KIND_SNOOKER ? pp.i0 : -1, pp.i1, pp.i2 };
+                for (int q = 0; q < 3; ++q) {
+                    const int k = dep[q];
+                    if (k < 0 || k == j) continue;
+                    if (k < j) { if (level[(size_t)s * P + g * Np + k] >= me) return -7; }
+                    else if (s > 0 && level[(size_t)(s - 1) * P + g * Np + k] >= me) return -8;
+                }
+            }
+        }
+    if (n_levels_out) *n_levels_out = pl.n_levels;
+    if (padded_out) *padded_out = padded;
+    return 0;
+}

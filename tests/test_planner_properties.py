@@ -1,0 +1,44 @@
+"""Property test of the host planner (csrc/planner.cpp) through a hook of the host-only test double:
+for random group sizes, chunk lengths, mutation / snooker rates and seeds, every update appears exactly
+once and every dependency -- own previous update, donors with a smaller slot in the same sweep, donors
+with a larger slot in the previous sweep (the reference's sequential in-place sweep, crossover.jl:12-17) --
+sits in a strictly earlier level; the octet shaping must keep that and must not add padded columns."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import common
+
+
+@pytest.fixture(scope="module")
+def plan_check(emu):
+    L = C.CDLL(common.EMU_LIB)
+    f = L.demcmc_emu_plan_check
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    f.restype = C.c_int
+    return f
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 2**63 - 1), Np=st.integers(3, 300), G=st.integers(1, 6), n_sweeps=st.integers(1, 16),
+       beta=st.sampled_from([0.0, 0.1, 0.5]), snooker=st.sampled_from([0.0, 0.1, 0.6]), stride=st.sampled_from([1, 2, 3]))
+def test_levels_respect_every_dependency(plan_check, seed, Np, G, n_sweeps, beta, snooker, stride):
+    out = {}
+    for shape in (0, 8, 32):
+        nl, padded = C.c_int(0), C.c_int(0)
+        rc = plan_check(seed, Np, G, n_sweeps, beta, snooker, shape, stride, C.byref(nl), C.byref(padded))
+        assert rc == 0, (rc, shape)
+        out[shape] = (nl.value, padded.value)
+    assert out[8][0] == out[0][0] and out[32][0] == out[0][0]           # shaping never adds a level
+    assert out[8][1] <= out[0][1]                                        # ... and never more padded DMMA columns
+
+
+def test_shaping_removes_most_padding_at_the_bench_shape(plan_check):
+    res = {}
+    for shape in (0, 8):
+        nl, padded = C.c_int(0), C.c_int(0)
+        assert plan_check(20261017, 256, 2, 16, 0.1, 0.1, shape, 1, C.byref(nl), C.byref(padded)) == 0
+        res[shape] = padded.value - 16 * 512
+    assert res[8] < 0.4 * res[0], res
