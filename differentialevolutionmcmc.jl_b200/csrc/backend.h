@@ -51,10 +51,12 @@ int timer_stop(double *ms);
 // centres MVN / hierarchical data and packs them for k_xdot (fills center, xT, ssd_xx, ssd_rowmax);
 // pack_ssd_doubles = size of the xT buffer the caller must allocate for the model's geometry
 size_t pack_ssd_doubles(const ModelDev &m);
-int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m /* xT allocated */);
+// center_host: nullptr = centre on the column means, else the [ssd_k] vector to centre on (host memory)
+int launch_pack_ssd(const double *x_in, int in_on_device, const double *center_host, ModelDev *m /* xT allocated */);
 // init_particle: weights of n particles theta[n][d] -> w[n] (also demcmc_eval)
+// xdot (MVN / hierarchical, may be nullptr): the cross term of every vector as the likelihood kernel produced it
 int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior,
-                double *w, double *scratch_part);
+                double *w, double *scratch_part, double *xdot = nullptr);
 // select_base preparation on the sweep-start weights: cw[P] running sums, tot[G]; th[P] is scratch
 int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
 // propose -> loglik -> accept for one level of one sweep

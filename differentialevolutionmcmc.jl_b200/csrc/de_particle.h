@@ -281,6 +281,7 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
         if (ctx.next_pos) ctx.next_pos[ctx.cur_id[p] - cfg.group_begin * Np] = p;
         ctx.next_acc[p] = (acc && cfg.update == UPDATE_MH) ? 1 : 0;       // maximize!/minimize! never write Particle.accept
         if (ctx.tr_w) { ctx.tr_w[p] = wprop; ctx.tr_adj[p] = adj; ctx.tr_acc[p] = acc ? 1 : 0; }
+        if (ctx.tr_xdot) ctx.tr_xdot[p] = total;
     }
 }
 

@@ -38,6 +38,11 @@ struct ModelDev {
                               // fragment repeats the two means (at load time), and the step costs one DMMA instead of two (d = 50:
                               // 25 DMMAs per row pair and octet instead of 26)
     int32_t ssd_qbits;        // fixed-point bits below the per-particle bound (de_math.h: xd_magic)
+    int32_t center_given;     // the data were centred on a caller-supplied vector (demcmc_model.center), not on their column
+                              // means: the cross term is then not analytically zero (parity tests of k_xdot / k_chunk_persist)
+    int32_t debug_corrupt;    // DEMCMC_TEST_CORRUPT (mutation tests: the parity tests of the cross term must FAIL with it):
+                              // 1 = B fragments staged with particle and dimension swapped inside a fragment,
+                              // 2 = the half k-step of the second row tile packed over the first, 3 = last k-step not staged
     int32_t has_sigma;
     double sigma_acc[MAX_ACC];
     double lba_floor;
@@ -114,6 +119,7 @@ struct SweepCtx {
     double *ll_q;             // [P_local]
     // trace rows of this sweep or NULL
     double *tr_theta, *tr_w, *tr_adj; uint8_t *tr_acc;
+    double *tr_xdot;          // MVN / hierarchical: the cross term the likelihood kernel produced for the proposal
 };
 
 // One launch: the (sweep slot, local position) updates of one dependency level.  Entry encoding:

@@ -98,7 +98,7 @@ struct demcmc_handle {
     int32_t *d_mig_log = nullptr;                       // device log of picks of the last call
     int64_t mig_log_iters = 0;
     // trace of the last call
-    double *tr_theta = nullptr, *tr_w = nullptr, *tr_adj = nullptr;
+    double *tr_theta = nullptr, *tr_w = nullptr, *tr_adj = nullptr, *tr_xdot = nullptr;
     uint8_t *tr_acc = nullptr;
     int64_t tr_sweeps = 0;
     // comm
@@ -109,6 +109,7 @@ struct demcmc_handle {
     // measurement mode (demcmc_set_timing)
     int64_t flush_bytes = 0;
     bool time_loglik = false;
+    bool suffstat = false;                              // demcmc_set_sufficient_stat: the O(N d) stream is skipped
     void *flush_buf = nullptr;
     std::vector<void *> tev;                            // pool of timing events
 };
@@ -305,7 +306,7 @@ int demcmc_destroy(demcmc_handle *h)
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
                      h->prop_theta, h->prop_prior, h->prop_adj, h->prop_msq, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
-                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_acc, h->flush_buf };
+                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_xdot, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
     for (auto &u : h->ring) { be::hfree_pinned(u.h_blk); be::dfree(u.d_blk); be::event_destroy(u.copied); }
@@ -379,6 +380,9 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         D.ksplit_len = (D.ssd_k + D.n_ksplit - 1) / D.n_ksplit;
         D.ssd_nj = (D.ksplit_len + 3) / 4;
         { const char *e = getenv("DEMCMC_NO_HALF_STEP"); D.ssd_half = (D.ksplit_len % 4 == 2 && !(e && e[0] == '1')) ? 1 : 0; }
+        { const char *e = getenv("DEMCMC_TEST_CORRUPT"); D.debug_corrupt = e ? atoi(e) : 0; }     // mutation tests (de_types.h)
+        D.center_given = m->center ? 1 : 0;
+        if (h->suffstat && m->center) return fail(DEMCMC_EINVAL, "sufficient-statistic mode needs the data centred on their column means (model.center = NULL)");
         D.n_osplit = 1; D.split_len = (int32_t)std::min<int64_t>(D.ssd_ld, INT32_MAX);
         // fixed-point bits below the per-particle bound: the sum of one rounded term per
         // (observation row, dimension split) must stay below 2^62
@@ -393,7 +397,7 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         h->model_allocs.push_back(center);
         D.xT = xT;
         D.center = center;
-        BE(be::launch_pack_ssd(m->x, dev, &D));       // centres and packs the data, fills D.ssd_xx / D.ssd_rowmax
+        BE(be::launch_pack_ssd(m->x, dev, m->center, &D));       // centres and packs the data, fills D.ssd_xx / D.ssd_rowmax
     } else {
         D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
         if (!D.x) return fail(DEMCMC_ENOMEM, "data upload failed");
@@ -547,14 +551,17 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     }
 
     // ---- trace and migration log of this call ------------------------------------------------------
-    be::dfree(h->tr_theta); be::dfree(h->tr_w); be::dfree(h->tr_adj); be::dfree(h->tr_acc);
-    h->tr_theta = h->tr_w = h->tr_adj = nullptr; h->tr_acc = nullptr; h->tr_sweeps = 0;
+    be::dfree(h->tr_theta); be::dfree(h->tr_w); be::dfree(h->tr_adj); be::dfree(h->tr_acc); be::dfree(h->tr_xdot);
+    h->tr_theta = h->tr_w = h->tr_adj = h->tr_xdot = nullptr; h->tr_acc = nullptr; h->tr_sweeps = 0;
+    const bool ssd_model = h->dmodel.kind == M_MVNORMAL || h->dmodel.kind == M_HIER;
     if (cfg.trace && S > 0) {
         h->tr_theta = (double *)be::dmalloc(sizeof(double) * S * P * d);
         h->tr_w = (double *)be::dmalloc(sizeof(double) * S * P);
         h->tr_adj = (double *)be::dmalloc(sizeof(double) * S * P);
         h->tr_acc = (uint8_t *)be::dmalloc((size_t)S * P);
-        if (!h->tr_theta || !h->tr_w || !h->tr_adj || !h->tr_acc) { cleanup(); return fail(DEMCMC_ENOMEM, "trace buffers do not fit"); }
+        if (ssd_model) h->tr_xdot = (double *)be::dmalloc(sizeof(double) * S * P);
+        if (!h->tr_theta || !h->tr_w || !h->tr_adj || !h->tr_acc || (ssd_model && !h->tr_xdot)) { cleanup(); return fail(DEMCMC_ENOMEM, "trace buffers do not fit"); }
+        if (h->tr_xdot) BE(be::dzero(h->tr_xdot, sizeof(double) * S * P));
         if (!h->block_on.empty()) {                              // sweep slots of unblocked iterations stay unused: read as zero
             BE(be::dzero(h->tr_theta, sizeof(double) * S * P * d)); BE(be::dzero(h->tr_w, sizeof(double) * S * P));
             BE(be::dzero(h->tr_adj, sizeof(double) * S * P)); BE(be::dzero(h->tr_acc, (size_t)S * P));
@@ -643,6 +650,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
+                ctx.tr_xdot = h->tr_xdot ? h->tr_xdot + (size_t)s_local * P : nullptr;
             }
             if (last) { h->cur_hist = h->n0 + itg; }
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
@@ -653,7 +661,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // stream, so one lane's likelihood kernel runs while the other lane proposes / accepts.
         // the persistent chunk kernel alternates the levels of two lanes; the level-by-level path
         // runs the handle's lanes (default 1) as concurrent kernel chains
-        const int persist_lanes = be::chunk_persist_lanes(h->dcfg, h->dmodel);
+        const bool skip_stream = h->suffstat && ssd_model;       // B == 0 analytically: propose -> accept, nothing streamed
+        const int persist_lanes = skip_stream ? 0 : be::chunk_persist_lanes(h->dcfg, h->dmodel);
         const int n_lanes = persist_lanes ? persist_lanes : ((h->n_lanes > 1 && G >= 2) ? 2 : 1);
         int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
         std::vector<uint8_t> mut((size_t)n_sw * G, 0);
@@ -737,7 +746,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 }
                 if (be::launch_propose(h->dcfg, h->dmodel, lv) ||
                     (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll])) ||
-                    be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc) ||
+                    (!skip_stream && be::launch_loglik(h->dcfg, h->dmodel, h->prop_theta, lv, h->ll_part, h->ll_acc)) ||
                     (tl && be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])) ||
                     be::launch_accept(h->dcfg, h->dmodel, lv)) rc_launch = 1;
                 if (tl) ++tev_ll;
@@ -977,6 +986,23 @@ int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, 
     return 0;
 }
 
+int demcmc_get_trace_xdot(demcmc_handle *h, double *xdot)
+{
+    if (!h || !xdot) return fail(DEMCMC_EINVAL, "null argument");
+    if (!h->tr_sweeps || !h->tr_xdot) return fail(DEMCMC_ESTATE, "no cross-term trace: MVNORMAL / HIER_NORMAL handle created with cfg.trace = 1, after a run");
+    BE(be::set_device(h->cfg.device));
+    BE(be::d2h(xdot, h->tr_xdot, sizeof(double) * (size_t)h->tr_sweeps * h->P));
+    return 0;
+}
+
+int demcmc_set_sufficient_stat(demcmc_handle *h, int32_t on)
+{
+    if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (on && h->has_model && h->dmodel.center_given) return fail(DEMCMC_EINVAL, "the model was centred on a caller-supplied vector: its cross term is not zero");
+    h->suffstat = on != 0;
+    return 0;
+}
+
 int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
 {
     if (!h || !slots) return fail(DEMCMC_EINVAL, "null argument");
@@ -1045,7 +1071,15 @@ int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out)
     return 0;
 }
 
-int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior)
+static int eval_impl(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior, double *xdot);
+int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior) { return eval_impl(h, theta, n, loglike, prior, nullptr); }
+int demcmc_eval_xdot(demcmc_handle *h, const double *theta, int64_t n, double *xdot)
+{
+    if (!xdot) return fail(DEMCMC_EINVAL, "null out");
+    if (h && h->has_model && h->dmodel.kind != M_MVNORMAL && h->dmodel.kind != M_HIER) return fail(DEMCMC_EINVAL, "only MVNORMAL / HIER_NORMAL have a cross term");
+    return eval_impl(h, theta, n, nullptr, nullptr, xdot);
+}
+static int eval_impl(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior, double *xdot)
 {
     if (!h || !theta || n < 0) return fail(DEMCMC_EINVAL, "bad argument");
     if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model first");
@@ -1053,14 +1087,16 @@ int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglik
     if (n == 0) return 0;
     const size_t d = h->d, ns = (size_t)h->dmodel.n_osplit * h->dmodel.n_ksplit;
     double *dt = (double *)be::dmalloc(sizeof(double) * n * d), *dl = (double *)be::dmalloc(sizeof(double) * n),
-           *dp = (double *)be::dmalloc(sizeof(double) * n), *part = (double *)be::dmalloc(sizeof(double) * n * ns);
+           *dp = (double *)be::dmalloc(sizeof(double) * n), *part = (double *)be::dmalloc(sizeof(double) * n * ns),
+           *dx = (double *)be::dmalloc(sizeof(double) * n);
     int rc = 0;
-    if (!dt || !dl || !dp || !part) rc = fail(DEMCMC_ENOMEM, "eval staging does not fit");
+    if (!dt || !dl || !dp || !part || !dx) rc = fail(DEMCMC_ENOMEM, "eval staging does not fit");
     if (!rc && (be::h2d(dt, theta, sizeof(double) * n * d) || be::sync() ||
-                be::launch_eval(h->dcfg, h->dmodel, dt, n, dl, dp, nullptr, part) ||
-                (loglike && be::d2h(loglike, dl, sizeof(double) * n)) || (prior && be::d2h(prior, dp, sizeof(double) * n))))
+                be::launch_eval(h->dcfg, h->dmodel, dt, n, dl, dp, nullptr, part, dx) ||
+                (loglike && be::d2h(loglike, dl, sizeof(double) * n)) || (prior && be::d2h(prior, dp, sizeof(double) * n)) ||
+                (xdot && be::d2h(xdot, dx, sizeof(double) * n))))
         rc = fail(DEMCMC_ECUDA, "eval: %s", be::last_error());
-    be::dfree(dt); be::dfree(dl); be::dfree(dp); be::dfree(part);
+    be::dfree(dt); be::dfree(dl); be::dfree(dp); be::dfree(part); be::dfree(dx);
     return rc;
 }
 

@@ -388,7 +388,12 @@ __device__ __forceinline__ size_t bfrag_index(const ModelDev &m, int64_t wi, int
     const int64_t oct = wi / SSD_OCT;
     const int n = (int)(wi % SSD_OCT);
     const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
-    return (((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32 + n * 4 + (kl & 3);
+    const size_t frag = (((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32;
+    if (m.debug_corrupt) {                                   // mutation tests only (de_types.h: debug_corrupt)
+        if (m.debug_corrupt == 1) return frag + (kl & 3) * 8 + n;
+        if (m.debug_corrupt == 3 && m.ssd_nj > 1 && (kl >> 2) == m.ssd_nj - 1) return frag - 32 + n * 4 + (kl & 3);
+    }
+    return frag + n * 4 + (kl & 3);
 }
 __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
                                             long long *acc, double *q, double *msq_out)
@@ -1647,7 +1652,7 @@ __global__ void __launch_bounds__(256) k_col_center(const double *x, double *cen
 // one thread per observation: writes its centred row into the packed layout; per block the sum and
 // the maximum of the squared row norms
 __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double *center, double *xp, double *blk_sq, double *blk_max,
-                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major, int half)
+                                                   int64_t n, int k, int ksplit_len, int nj, int64_t n_tiles, int obs_major, int half, int corrupt)
 {
     __shared__ double red[9];
     __shared__ double redm[8];
@@ -1657,7 +1662,9 @@ __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double
         for (int kk = 0; kk < k; ++kk) {
             const double v = (obs_major ? x[i * k + kk] : x[(int64_t)kk * n + i]) - center[kk];
             q += v * v;
-            xp[ssd_pack_index(i, kk, ksplit_len, nj, n_tiles, half)] = v;
+            // (mutation test 2: the second row tile of a pair packs its half k-step over the first tile's)
+            const int64_t ip = (corrupt == 2 && half && (kk % ksplit_len) / 4 == nj - 1) ? (i & ~(int64_t)8) : i;
+            xp[ssd_pack_index(ip, kk, ksplit_len, nj, n_tiles, half)] = v;
         }
     double mx = q;
 #pragma unroll
@@ -1674,7 +1681,7 @@ __global__ void __launch_bounds__(256) k_pack_rows(const double *x, const double
 
 size_t pack_ssd_doubles(const ModelDev &m) { return (size_t)m.n_ksplit * (size_t)(m.ssd_ld / SSD_TN) * m.ssd_nj * 256; }
 
-int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
+int launch_pack_ssd(const double *x_in, int in_on_device, const double *center_host, ModelDev *m)
 {
     const size_t bytes = sizeof(double) * (size_t)m->ssd_n * m->ssd_k;
     const int n_blk = (int)std::max<int64_t>(1, (m->ssd_n + 255) / 256);
@@ -1690,10 +1697,11 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
     const int obs_major = m->kind == M_MVNORMAL ? 1 : 0;
     cudaError_t e = cudaMemsetAsync(const_cast<double *>(m->xT), 0, sizeof(double) * pack_ssd_doubles(*m), stream());
     if (e == cudaSuccess) e = cudaMemsetAsync(blk, 0, sizeof(double) * 2 * n_blk, stream());
+    if (e == cudaSuccess && center_host) e = cudaMemcpyAsync(const_cast<double *>(m->center), center_host, sizeof(double) * m->ssd_k, cudaMemcpyHostToDevice, stream());
     if (e == cudaSuccess) {
-        k_col_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->center), m->ssd_n, m->ssd_k, obs_major);
+        if (!center_host) k_col_center<<<m->ssd_k, 256, 0, stream()>>>(src, const_cast<double *>(m->center), m->ssd_n, m->ssd_k, obs_major);
         k_pack_rows<<<n_blk, 256, 0, stream()>>>(src, m->center, const_cast<double *>(m->xT), blk, blk + n_blk, m->ssd_n, m->ssd_k,
-                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major, m->ssd_half);
+                                                 m->ksplit_len, m->ssd_nj, m->ssd_ld / SSD_TN, obs_major, m->ssd_half, m->debug_corrupt);
         g_launches += 2;
         e = cudaGetLastError();
     }
@@ -1714,7 +1722,7 @@ int launch_pack_ssd(const double *x_in, int in_on_device, ModelDev *m)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, ModelDev m, const double *theta, int64_t n,
                                                              const double *part, const long long *acc, const double *q,
-                                                             double *ll, double *prior, double *w)
+                                                             double *ll, double *prior, double *w, double *xdot)
 {
     const int64_t wi = ((int64_t)blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
     if (wi >= n) return;
@@ -1732,13 +1740,14 @@ __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, Model
     const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
     if (co.lane() == 0) {
         if (ll) ll[wi] = l;
+        if (xdot) xdot[wi] = s;
         if (prior) prior[wi] = inb ? pr : -inf();
         if (w) w[wi] = cfg.fitness == FITNESS_FUN ? (inb ? l : (cfg.update == UPDATE_MAXIMIZE ? -inf() : inf())) : (inb ? add(pr, l) : -inf());
     }
 }
 
 int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior,
-                double *w, double *scratch_part)
+                double *w, double *scratch_part, double *xdot)
 {
     if (n <= 0) return 0;
     Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
@@ -1755,7 +1764,7 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
         LAUNCHED("k_stage_means");
         if (launch_xdot(m, *xs, lv, acc)) { dfree(acc); dfree(q); return -1; }
     } else if (launch_loglik(cfg, m, theta, lv, scratch_part, nullptr)) return -1;
-    k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, acc, q, ll, prior, w);
+    k_eval_finish<<<blocks, PA_THREADS, 0, stream()>>>(cfg, m, theta, n, scratch_part, acc, q, ll, prior, w, xdot);
     LAUNCHED("k_eval_finish");
     if (acc) { cudaStreamSynchronize(stream()); dfree(acc); dfree(q); }
     return 0;

@@ -65,9 +65,11 @@ class Handle:
 
     # ---- model ---------------------------------------------------------------------------------
     def set_model(self, kind, prior, x=None, choice=None, sigma=None, lba_floor=1e-10, device_ptrs=None, n_obs=None,
-                  n_dim=0, n_per=0):
+                  n_dim=0, n_per=0, center=None):
         """Bind a registered likelihood kernel.  `prior` is a list of (name, a, b, ref) per
-        flattened parameter.  `device_ptrs=(x_ptr, choice_ptr)` passes data already in HBM."""
+        flattened parameter.  `device_ptrs=(x_ptr, choice_ptr)` passes data already in HBM.
+        `center` (mvnormal / hier_normal, test hook): centre the data on this vector instead of on their
+        column means, which makes the streamed cross term non-zero (demcmc_model.center)."""
         d = self.d
         if len(prior) != d:
             raise ValueError(f"need {d} prior specs, got {len(prior)}")
@@ -102,8 +104,11 @@ class Handle:
                 if kind in ("lnr", "lba") and not n_dim:
                     n_dim = d - 1 if kind == "lnr" else d - 3
         sg = None if sigma is None else f8(sigma)
-        m = _ffi.Model(kind_id, d, int(n_obs), int(n_dim), int(n_per), xp, cp, ptr(sg, _dp), float(lba_floor), pr, on_dev, 0)
-        self._keep = [xs, cs, sg, pr]
+        cen = None if center is None else f8(center).reshape(-1)
+        if cen is not None and cen.size != int(n_dim):
+            raise ValueError(f"center needs {n_dim} entries")
+        m = _ffi.Model(kind_id, d, int(n_obs), int(n_dim), int(n_per), xp, cp, ptr(sg, _dp), float(lba_floor), pr, on_dev, 0, ptr(cen, _dp))
+        self._keep = [xs, cs, sg, pr, cen]
         check(_ffi.lib().demcmc_set_model(self._h, C.byref(m)))
 
     # ---- state ---------------------------------------------------------------------------------
@@ -220,6 +225,24 @@ class Handle:
         check(_ffi.lib().demcmc_get_trace(self._h, ptr(out["prop_theta"], _dp), ptr(out["prop_weight"], _dp),
                                           ptr(out["log_adj"], _dp), ptr(out["accepted"], _bp)))
         return out
+
+    def trace_xdot(self):
+        """mvnormal / hier_normal: the cross term B the streamed likelihood kernel produced for every proposal
+        of the last call, [S][P] (demcmc_get_trace_xdot)."""
+        out = np.zeros((self._last_iters * self.B, self.P))
+        check(_ffi.lib().demcmc_get_trace_xdot(self._h, ptr(out, _dp)))
+        return out
+
+    def eval_xdot(self, theta):
+        th = f8(theta).reshape(-1, self.d)
+        out = np.zeros(th.shape[0])
+        check(_ffi.lib().demcmc_eval_xdot(self._h, ptr(th, _dp), th.shape[0], ptr(out, _dp)))
+        return out
+
+    def set_sufficient_stat(self, on=True):
+        """Skip the O(N d) stream of the mvnormal / hier_normal likelihood (its cross term is analytically zero
+        with mean-centred data); reported separately by bench.py, off by default."""
+        check(_ffi.lib().demcmc_set_sufficient_stat(self._h, int(bool(on))))
 
     def migration_slots(self):
         out = np.full((max(1, self._last_iters), self.n_groups), -1, dtype=np.int32)

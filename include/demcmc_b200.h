@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DEMCMC_ABI_VERSION 3
+#define DEMCMC_ABI_VERSION 4
 
 enum { DEMCMC_OK = 0, DEMCMC_EINVAL = -1, DEMCMC_ENODEVICE = -2, DEMCMC_ECUDA = -3, DEMCMC_ENOMEM = -4,
        DEMCMC_ESTATE = -5, DEMCMC_EUNSUPPORTED = -6, DEMCMC_ECOMM = -7 };
@@ -73,6 +73,13 @@ typedef struct {
     const demcmc_prior *prior; /* [d], host memory */
     int32_t data_on_device; /* 1: x / choice are device pointers on the handle's device */
     int32_t reserved;
+    const double *center;   /* MVNORMAL / HIER_NORMAL: NULL (the default) = the kernel centres the data on their column
+                               means, x' = x - mean: the sum of squares is then  sum x'^2 - 2 B + n sum m'^2  with the
+                               streamed cross term B = sum_i sum_k x'_ik m'_k ANALYTICALLY ZERO (sum_i x'_ik = 0) -- the
+                               most accurate split, and the reason no likelihood value can show whether the O(N d)
+                               stream was computed correctly.  center[n_dim] (host memory) centres on THAT vector
+                               instead: B is then n (mean - center).m', not zero, and demcmc_get_trace_xdot /
+                               demcmc_eval_xdot expose it, which is how the parity tests pin the DMMA kernels. */
 } demcmc_model;
 
 /* Mirrors the DE sampler struct field by field (src/structs.jl:57-131). */
@@ -209,6 +216,11 @@ int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *i
 /* per-sweep trace of the LAST run/replay call (needs cfg.trace): prop_theta[S][P_local][d],
  * prop_weight[S][P_local], log_adj[S][P_local], accepted[S][P_local]; any pointer may be NULL */
 int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, double *log_adj, uint8_t *accepted);
+/* ... and, MVNORMAL / HIER_NORMAL only, what the streamed likelihood kernel (k_xdot / k_chunk_persist) itself
+ * produced for every proposal of that call: xdot[S][P_local] = B = sum_i sum_k (x_ik - center_k)(mean_pk - center_k),
+ * the cross term of the expanded sum of squares (Multivariate_Guassian_Example.jl:31-33 has no such intermediate:
+ * this is a test hook, see demcmc_model.center) */
+int demcmc_get_trace_xdot(demcmc_handle *h, double *xdot);
 /* migration picks of the last call: slots[n_iter][G] (-1 where the group did not migrate) */
 int demcmc_get_migration(demcmc_handle *h, int32_t *slots);
 int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out);
@@ -230,6 +242,14 @@ int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes);
 /* compute_posterior! pieces (src/utilities.jl:92-99) for n arbitrary parameter vectors
  * theta[n][d]: loglike[n], prior[n] (prior is -inf when out of bounds); either may be NULL */
 int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior);
+/* the cross term B (see demcmc_get_trace_xdot) of n arbitrary parameter vectors theta[n][d], through k_xdot */
+int demcmc_eval_xdot(demcmc_handle *h, const double *theta, int64_t n, double *xdot);
+/* SURVEY hard part 7: with the data centred on their column means the cross term is analytically zero, so the
+ * MVNORMAL / HIER_NORMAL likelihood follows from O(d) sufficient statistics alone.  on = 1 skips the O(N d) stream
+ * (k_xdot / k_chunk_persist are not launched; B is taken as 0).  Off by default: the headline metric counts
+ * "loglike evals incl.", i.e. every observation streamed for every particle; bench.py reports this mode
+ * separately (value_sufficient_stat).  Refused when the model was given an explicit center. */
+int demcmc_set_sufficient_stat(demcmc_handle *h, int32_t on);
 
 /* Particle algebra on the device, for the reference's known-answer tests (test/utility_tests.jl):
  * project (utilities.jl:239-246), reset! (crossover.jl:336-352), random_gamma body

@@ -66,7 +66,7 @@ static double kval(const ksum_t &k) { return isfinite(k.s) ? k.s + k.c : k.s; }
 
 size_t pack_ssd_doubles(const ModelDev &m) { return (size_t)m.ssd_k * (size_t)m.ssd_ld; }
 
-int launch_pack_ssd(const double *x, int, ModelDev *m)
+int launch_pack_ssd(const double *x, int, const double *center_host, ModelDev *m)
 {
     ++g_launches;
     double *xT = const_cast<double *>(m->xT), *center = const_cast<double *>(m->center);
@@ -75,7 +75,7 @@ int launch_pack_ssd(const double *x, int, ModelDev *m)
         auto at = [&](int64_t i) { return m->kind == M_MVNORMAL ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i]; };
         double s = 0.0;
         for (int64_t i = 0; i < m->ssd_n; ++i) s += at(i);
-        const double c = m->ssd_n > 0 ? s / (double)m->ssd_n : 0.0;
+        const double c = center_host ? center_host[k] : (m->ssd_n > 0 ? s / (double)m->ssd_n : 0.0);
         center[k] = c;
         double q = 0.0;
         for (int64_t i = 0; i < m->ssd_ld; ++i) {
@@ -107,7 +107,8 @@ static int loglik_impl(const ModelDev &m, const double *theta, const Level &lv, 
                     const int64_t o0 = (int64_t)os * m.split_len, o1 = std::min<int64_t>(m.ssd_ld, o0 + m.split_len);
                     double s = 0.0;
                     for (int k = k0; k < k1; ++k) {
-                        const double mean = centred_mean(m, th, k);
+                        // DEMCMC_TEST_CORRUPT (mutation tests): the wrong dimension's mean, scaled and shifted
+                        const double mean = m.debug_corrupt ? centred_mean(m, th, (k + 1) % m.ssd_k) * 3.0 + 17.0 : centred_mean(m, th, k);
                         for (int64_t i = o0; i < o1; ++i) s += m.xT[(int64_t)k * m.ssd_ld + i] * mean;
                     }
                     part[(size_t)p * n_split + os * m.n_ksplit + ks] = s;
@@ -157,7 +158,7 @@ int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, con
     return 0;
 }
 
-int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior, double *w, double *part)
+int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, int64_t n, double *ll, double *prior, double *w, double *part, double *xdot)
 {
     Level lv; lv.order = nullptr; lv.n = (int32_t)n; lv.ctxs = nullptr;
     loglik_impl(m, theta, lv, part);
@@ -172,6 +173,7 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
         if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN) for (int q = 0; q < n_split; ++q) s += part[(size_t)i * n_split + q];
         const double l = finalize_ll(m, th, s, mean_sq(co, m, th));
         if (ll) ll[i] = l;
+        if (xdot) xdot[i] = s;
         if (prior) prior[i] = inb ? pr : -inf();
         if (w) w[i] = cfg.fitness == FITNESS_FUN ? (inb ? l : (cfg.update == UPDATE_MAXIMIZE ? -inf() : inf())) : (inb ? pr + l : -inf());
     }

@@ -430,3 +430,28 @@ def test_optimize_api():
     case = make_case("gaussian", np.random.default_rng(52))
     with pytest.raises(D._ffi.DemcmcError, match="MethodError"):
         D.Handle(2, 4, 2, case.lo, case.hi, update="maximize", fitness="fun", theta_snooker=0.1)
+
+
+# ---- the cross term on operands whose answer is not zero (tests/xdot_common.py) -----------------------------
+@pytest.mark.parametrize("kind,n,k", [("mvnormal", 130, 50), ("mvnormal", 65, 100), ("hier_normal", 50, 120)])
+def test_cross_term_with_a_given_centre(emu, kind, n, k):
+    import xdot_common as X
+    err, ll, case, th = X.eval_error(kind, n, k, 19, seed=k)
+    assert err <= X.TOL
+    m = O.Model(kind, case["d"], case["prior"], x=case["x"])
+    assert common.rel_err(ll, np.array([O.loglike(m, t) for t in th])) <= 1e-11
+    kw = dict(blocks=common.hier_blocks(k)) if kind == "hier_normal" else dict(theta_snooker=0.2)
+    err, ctr, n_checked = X.run_error(kind, n, k, 2, 9, 4, seed=k, **kw)
+    assert n_checked > 0 and err <= X.TOL
+
+
+def test_cross_term_mutation_is_caught_by_the_cpu_suite(emu):
+    """a test double whose cross term used the wrong dimension's mean x 3 + 17 passed all 93 CPU tests.
+    DEMCMC_TEST_CORRUPT makes the double do exactly that; the parity check must now fail."""
+    import os, subprocess, sys
+    script = os.path.join(os.path.dirname(__file__), "xdot_common.py")
+    env = dict(os.environ)
+    env.pop("DEMCMC_TEST_CORRUPT", None)
+    assert subprocess.run([sys.executable, script, common.EMU_LIB], env=env, capture_output=True).returncode == 0
+    env["DEMCMC_TEST_CORRUPT"] = "1"
+    assert subprocess.run([sys.executable, script, common.EMU_LIB], env=env, capture_output=True).returncode == 3
