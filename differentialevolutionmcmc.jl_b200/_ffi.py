@@ -45,7 +45,8 @@ class Config(C.Structure):
                 ("proposal", C.c_int32), ("n_blocks", C.c_int32), ("blocks", _bp), ("lo", _dp), ("hi", _dp),
                 ("seed", C.c_uint64), ("device", C.c_int32), ("group_begin", C.c_int32),
                 ("group_count", C.c_int32), ("donors", C.c_int32), ("trace", C.c_int32),
-                ("store_every", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32)]
+                ("store_every", C.c_int32), ("update", C.c_int32), ("fitness", C.c_int32),
+                ("n_devices", C.c_int32), ("devices", _ip)]
 
 
 class Tape(C.Structure):

@@ -187,6 +187,12 @@ class DEModel:
         self.data = data
 
 
+def GPUDEModel(*, prior_loglike=None, loglike, names, sample_prior):
+    """The GPU model's own constructor of julia/GPULoglike.jl (there the package's keyword constructor DEModel(args...; ...)
+    must stay untouched for CPU models); here simply DEModel."""
+    return DEModel(prior_loglike=prior_loglike, loglike=loglike, names=names, sample_prior=sample_prior)
+
+
 class DE:
     """DE(; n_groups=4, Np, burnin=1000, discard_burnin=true, α=.1, β=.1, ϵ=.001, σ=.05, κ=1.0,
     θsnooker=0.0, bounds, n_initial=0, generate_proposal=random_gamma, blocking_on=x->false,
@@ -365,7 +371,7 @@ def _blocking_schedule(de: DE, n_iter):
     return on
 
 
-def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0, n_iter=None):
+def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0, n_iter=None, devices=None, store_every=1):
     """Everything `sample` does before the iteration loop; also used by bench.py and the tests."""
     ll = model.loglike
     if not isinstance(ll, GPULoglike):
@@ -388,21 +394,24 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
                sigma=de.σ, kappa=de.κ, theta_snooker=de.θsnooker, proposal=_PROPOSAL_NAMES[de.generate_proposal],
                blocks=blocks, seed=seed, device=device, trace=trace, group_begin=group_begin, group_count=group_count,
                resample=de.sample is resample, update={mh_update: "mh", maximize: "maximize", minimize: "minimize"}[de.update_particle],
-               fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior", blocking_schedule=schedule)
+               fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior", blocking_schedule=schedule, devices=devices,
+               store_every=store_every)
     h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
     return h, shapes, d
 
 
-def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
+def sample(model: DEModel, de: DE, *args, progress=False, device=0, devices=None, store_every=1, **kwargs):
     """sample(model, de, n_iter) / sample(model, de, MCMCThreads(), n_iter): runs all n_iter
-    iterations on the device in ONE library call and returns the chains (src/main.jl:19-71)."""
+    iterations on the device in ONE library call and returns the chains (src/main.jl:19-71).
+    devices=[0, 1, ...]: the groups shard over several GPUs of the box from this one process (demcmc_config.n_devices).
+    store_every=k: thinning -- the Chains hold iterations k, 2k, ... (burnin is then counted in kept rows: burnin // k)."""
     if len(args) == 2 and isinstance(args[0], MCMCThreads):
         n_iter = int(args[1])
     elif len(args) == 1:
         n_iter = int(args[0])
     else:
         raise TypeError("sample(model, de, n_iter) or sample(model, de, MCMCThreads(), n_iter)")
-    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter)
+    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter, devices=devices, store_every=store_every)
     try:
         P = de.n_groups * de.Np
         if de.n_initial > 0:
@@ -422,8 +431,8 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         de.iter = n_iter + de.n_initial
         # bundle_samples (src/main.jl:222-250) runs on the device: one gather, one download, and the
         # host only wraps the array (Julia memory order) in a view
-        offset = de.burnin if de.discard_burnin else 0
-        arr = h.chains(offset, max(n_iter - offset, 0))
+        offset = (de.burnin // h.store_every) if de.discard_burnin else 0
+        arr = h.chains(offset, max(n_iter // h.store_every - offset, 0))
         de.samples = arr[:, :d, :]                       # what bundle_samples keeps of de.samples
         names = _flat_names(model.names, shapes) + ["acceptance", "lp"]
         return Chains(arr.transpose(2, 1, 0), names, [str(n) for n in model.names])

@@ -80,17 +80,34 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);
 int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *theta, const double *w,
                       const int32_t *id, const uint8_t *acc, double *stage);
-// pos: id -> position map of the row being edited (resample), or nullptr
+// pos: id -> position map of the row being edited (resample), or nullptr.  mbox != nullptr: rows whose source is
+// another rank (a.src_rank[i] != rank) are taken from slot `slot` of this rank's mailbox once their flag shows `tag`
 int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
-                       double *w, int32_t *id, uint8_t *acc, int32_t *pos);
+                       double *w, int32_t *id, uint8_t *acc, int32_t *pos, const Mbox *mbox = nullptr, int rank = 0,
+                       int slot = 0, unsigned long long tag = 0);
+// P2P migration: rows of `stage` produced on this rank and consumed on another are stored into the consumer's mailbox
+// (peer-mapped) and published with `tag`
+int launch_mig_push(const ConfigDev &cfg, const MigArgs &a, const double *stage, const PeerTable &peers, const Mbox &geom,
+                    int rank, int slot, unsigned long long tag);
+int mbox_create(int depth, int max_rows, int row_len, Mbox *out);     // plain cudaMalloc (IPC-capable), flags zeroed
+void mbox_destroy(Mbox *m);
+int mbox_export(const Mbox &m, uint8_t handle[128]);                  // two cudaIpcMemHandle_t
+int mbox_open(const uint8_t handle[128], Mbox *peer);                 // maps a peer process's mailbox here
+void mbox_close(Mbox *peer);
+int enable_peer_access(int dev, int peer_dev);                        // 0, or -1 when the pair has no P2P path
 // history rows [n_rows][P][d] by slot -> reference layout [P][d][n_rows] by id (utilities.jl:34)
 int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
                          int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,
-                         double *samples, double *lp, uint8_t *accept);
+                         double *samples, double *lp, uint8_t *accept, int32_t P_ids = 0);
+// (P = slots per stored row of THIS shard; P_ids = particle ids the outputs cover, id - id_base in [0, P_ids), 0 => P.
+// The shards of a multi-device handle pass the whole job's id range and write into one output through peer access.)
 // bundle_samples layout (main.jl:222-250): chains[P][d+2][n_rows] for history rows [row0, row0+n_rows);
 // final_id[P] = id at each final position, pos_scratch[P] device scratch
 int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
-                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out);
+                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out,
+                  int32_t P_ids = 0, int32_t pos_base = 0, int phase = 3);
+// (phase 1: pos_scratch[id] = pos_base + final position of id; phase 2: the rows; 3: both.  A multi-device handle runs
+// phase 1 on every shard, then phase 2 on every shard, all on one pos_scratch[P_ids] and one output.)
 // pooled per-parameter mean and sum of squared deviations of n vectors x[n][d] (fixed reduction order)
 int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *m2 /* device [d] each */);
 // particle algebra known-answer ops (single warp each)
@@ -117,6 +134,8 @@ int comm_destroy(void *comm);
 // every rank contributes bytes_per_rank bytes; recv holds the contributions in rank order (resample
 // on a sharded job: the replicated copy of a history row)
 int comm_allgather(void *comm, const void *send, void *recv, size_t bytes_per_rank);
+// device-side barrier on the engine stream: every rank's earlier work has completed before any rank's later work starts
+int comm_barrier(void *comm);
 // pos[ids[q]] = q for q < n (the id -> position map of a gathered history row)
 int launch_pos_from_ids(const int32_t *ids, int32_t n, int32_t *pos);
 // grouped send/recv of stage rows: for each position i, src_rank[i] sends row send_pos[i] to dst_rank[i]

@@ -130,10 +130,19 @@ constexpr int LV_SLOT_SHIFT = 24;
 constexpr uint32_t LV_POS_MASK = (1u << LV_SLOT_SHIFT) - 1;
 
 constexpr int MAX_MIG = 128;      // groups in one migration cycle (kernel-parameter block)
+constexpr int MAX_RANKS = 16;     // GPUs of one box a job may shard over
 struct MigArgs {
     int32_t n;                      // migrating groups
     int32_t groups[MAX_MIG];        // ordered subset (global group ids)
     double u_pick[MAX_MIG];         // uniform of select_particle per position
+    int8_t src_rank[MAX_MIG];       // rank that holds the particle position i receives (picked at position i-1, cyclic)
+    int8_t dst_rank[MAX_MIG];       // rank that holds the group at position i
 };
+// The migration mailbox of one rank, as mapped into this process / device: rows[depth][max_rows][row_len] and one
+// 64-bit flag per row.  A sender stores the row with ordinary stores over NVLink (peer-mapped memory), fences at system
+// scope and publishes the event's tag in the flag; the receiver's scatter kernel acquires the flag.  No host call and no
+// collective sits between a rank's chunks, and only the ranks of the cycle ever wait for each other.
+struct Mbox { double *rows; unsigned long long *flags; int32_t depth, max_rows, row_len; };
+struct PeerTable { double *rows[MAX_RANKS]; unsigned long long *flags[MAX_RANKS]; };
 
 } // namespace de

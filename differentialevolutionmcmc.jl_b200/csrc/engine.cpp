@@ -7,7 +7,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/demcmc_b200.h"
@@ -49,6 +53,7 @@ struct Upload {            // pinned staging + device copy of one sweep's schedu
 
 } // namespace
 
+struct MultiState;
 struct demcmc_handle {
     demcmc_config cfg;
     std::vector<uint8_t> blocks;
@@ -71,11 +76,14 @@ struct demcmc_handle {
     double *ghist_theta = nullptr;                      // [row][P_total][d]
     int32_t *ghist_pos = nullptr;                       // [row][P_total]
     int32_t *gid_tmp = nullptr;                         // [P_total] gathered ids of one row
+    int64_t k_store = 1;                                // store_every: iteration it (1-based, counted on this handle) is kept iff it % k_store == 0
+    int n_scratch = 3;                                  // scratch state rows (write-once within a chunk): 3, or MAX_CHUNK + 2 when thinning
     int64_t n0 = 0;                                     // de.n_initial: history rows before iteration 1
     bool has_history = false;                           // the n_initial prior rows were uploaded
     double *scr_theta = nullptr, *scr_w = nullptr;      // 3 scratch rows
     int32_t *scr_id = nullptr;
     uint8_t *scr_acc = nullptr;
+    int scr_cursor = 0;                                 // last scratch row handed out (ring)
     int cur_scratch = 0;                                // current state lives in scratch row k, or
     int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
     // proposal scratch
@@ -104,6 +112,20 @@ struct demcmc_handle {
     // comm
     void *comm = nullptr;
     int rank = 0, n_ranks = 1;
+    // P2P migration mailbox (de_types.h: Mbox): this rank's own, and every rank's as mapped here.  Used instead of the
+    // NCCL send/recv exchange when every peer could be mapped (multi-process: CUDA IPC; one process: peer access).
+    Mbox mbox = { nullptr, nullptr, 0, 0, 0 };
+    PeerTable peers = {};
+    std::vector<Mbox> peer_maps;                        // IPC mappings to close (multi-process)
+    bool mbox_on = false;
+    bool mbox_shared = false;                           // the mailbox belongs to the process-wide cache (multi-process jobs)
+    uint64_t mbox_seq = 0, *mbox_seq_p = &mbox_seq;     // cross-rank migration events so far (the same on every rank)
+    std::function<int()> mbox_barrier;                  // all ranks have consumed every event so far (slot reuse)
+    // multi-device handle (cfg.n_devices > 1): one child handle per device, driven by one host thread each
+    std::vector<demcmc_handle *> kids;
+    demcmc_handle *parent = nullptr;
+    struct MultiState *multi = nullptr;
+    std::vector<int32_t> devices;
     std::vector<int> group_owner;                       // [G_total] rank owning each group
     demcmc_counters ctr;
     // measurement mode (demcmc_set_timing)
@@ -122,15 +144,20 @@ static Row row_of(demcmc_handle *h, bool hist, int64_t idx)
     else { r.theta = h->scr_theta + idx * P * d; r.w = h->scr_w + idx * P; r.id = h->scr_id + idx * P; r.acc = h->scr_acc + idx * P; }
     return r;
 }
+// history rows held after `iters` iterations of this handle: the n_initial prior rows + every k_store-th iteration
+static int64_t stored_rows(const demcmc_handle *h, int64_t iters) { return h->n0 + iters / h->k_store; }
+static int64_t stored_rows(const demcmc_handle *h) { return stored_rows(h, h->iters_done); }
 static Row cur_row(demcmc_handle *h) { return h->cur_hist >= 0 ? row_of(h, true, h->cur_hist) : row_of(h, false, h->cur_scratch); }
 
 // history rows: [0, n0) = the n_initial prior rows (utilities.jl:35-39), row n0 + it = iteration it
 static int grow_history(demcmc_handle *h, int64_t need)
 {
     if (need <= h->hist_cap) return 0;
-    int64_t cap = std::max<int64_t>(need, h->hist_cap * 2);
+    // exactly what the call needs the first time (sample() runs once: no over-allocation); a handle that keeps
+    // being extended grows by halves so the copies stay amortised
+    int64_t cap = h->hist_cap > 0 ? std::max<int64_t>(need, h->hist_cap + h->hist_cap / 2) : need;
     const size_t P = h->P, d = h->d;
-    const int64_t have = h->hist_cap > 0 ? h->n0 + h->iters_done : 0;
+    const int64_t have = h->hist_cap > 0 ? stored_rows(h) : 0;
     double *nt = (double *)be::dmalloc(sizeof(double) * cap * P * d);
     double *nw = (double *)be::dmalloc(sizeof(double) * cap * P);
     int32_t *ni = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * P);
@@ -198,6 +225,226 @@ int op_begin(int device)
 }
 } // namespace
 
+// ---- P2P migration mailbox ------------------------------------------------------------------------------------
+static bool mbox_wanted()
+{
+    const char *e = getenv("DEMCMC_MIG");                 // DEMCMC_MIG=nccl: keep the NCCL send/recv exchange (A/B runs, fallback)
+    return !(e && strcmp(e, "nccl") == 0);
+}
+// Multi-process jobs keep ONE mailbox (and its IPC mappings of every peer) per device for the life of the process,
+// like the NCCL communicator: handles come and go (one per sample() call), the mapping does not, so nothing exported
+// is ever freed under a peer and a new handle pays no IPC set-up.  The event counter lives with the mailbox and only
+// ever grows, so a flag left by an earlier handle can never equal a later tag.
+struct MboxShared { size_t cap_doubles = 0, cap_flags = 0; int n_ranks = 0, rank = -1; Mbox box = { nullptr, nullptr, 0, 0, 0 }; PeerTable peers = {}; uint64_t seq = 0; };
+static MboxShared g_mbox_shared[64];
+static void mbox_geometry(const demcmc_handle *h, int *depth, int *max_rows, int *row_len)
+{
+    *row_len = h->d + 3; *max_rows = std::min(h->cfg.n_groups, (int)MAX_MIG);
+    const size_t ev_bytes = sizeof(double) * (size_t)*row_len * *max_rows;
+    *depth = (int)std::max<size_t>(16, std::min<size_t>(1024, ((size_t)64 << 20) / std::max<size_t>(1, ev_bytes)));
+}
+static int mbox_alloc(demcmc_handle *h)
+{
+    const int row_len = h->d + 3, max_rows = std::min(h->cfg.n_groups, (int)MAX_MIG);
+    const size_t ev_bytes = sizeof(double) * (size_t)row_len * max_rows;
+    const int depth = (int)std::max<size_t>(16, std::min<size_t>(1024, ((size_t)64 << 20) / std::max<size_t>(1, ev_bytes)));
+    if (be::mbox_create(depth, max_rows, row_len, &h->mbox)) return -1;
+    return 0;
+}
+
+// ---- multi-device handle: fan a call out over the children, one host thread per device -------------------------
+namespace {
+struct HostBarrier {
+    std::mutex m; std::condition_variable cv; int n = 0, waiting = 0; uint64_t gen = 0;
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const uint64_t g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+}
+struct MultiState { HostBarrier barrier; };
+
+template <class F>
+static int for_kids(demcmc_handle *h, F f, bool parallel = true)
+{
+    const size_t n = h->kids.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    if (!parallel || n == 1) {
+        for (size_t i = 0; i < n; ++i) { rc[i] = f(h->kids[i], (int)i); if (rc[i]) { msg[i] = g_err; break; } }
+    } else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < n; ++i)
+            th.emplace_back([&, i]() { rc[i] = f(h->kids[i], (int)i); if (rc[i]) msg[i] = g_err; });     // g_err is thread-local
+        for (auto &t : th) t.join();
+    }
+    for (size_t i = 0; i < n; ++i) if (rc[i]) return fail(rc[i], "device %d: %s", h->kids[i]->cfg.device, msg[i].c_str());
+    return 0;
+}
+
+
+// ---- the multi-device entry points (cfg.n_devices > 1) ---------------------------------------------------------
+static int multi_create(const demcmc_config *cfg, demcmc_handle **out)
+{
+    const int N = cfg->n_devices;
+    if (!cfg->devices) return fail(DEMCMC_EINVAL, "n_devices = %d but devices is NULL", N);
+    if (N > MAX_RANKS) return fail(DEMCMC_EUNSUPPORTED, "n_devices > %d", (int)MAX_RANKS);
+    if (cfg->n_groups % N) return fail(DEMCMC_EINVAL, "n_groups %d is not a multiple of the %d devices", cfg->n_groups, N);
+    if (cfg->group_begin != 0 || (cfg->group_count != 0 && cfg->group_count != cfg->n_groups)) return fail(DEMCMC_EINVAL, "a multi-device handle holds every group: group_begin / group_count must be 0");
+    if (cfg->donors) return fail(DEMCMC_EUNSUPPORTED, "sample = resample on a multi-device handle (its replicated history is gathered with NCCL: shard the job over processes instead, demcmc_comm_init)");
+    for (int i = 0; i < N; ++i) for (int j = 0; j < i; ++j) if (cfg->devices[i] == cfg->devices[j]) return fail(DEMCMC_EINVAL, "device %d listed twice", cfg->devices[i]);
+    if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
+    demcmc_handle *p = new demcmc_handle();
+    p->cfg = *cfg; p->cfg.devices = nullptr;
+    p->devices.assign(cfg->devices, cfg->devices + N);
+    p->d = cfg->d; p->n0 = cfg->n_initial; p->k_store = std::max(1, cfg->store_every);
+    p->G_local = cfg->n_groups; p->P = cfg->n_groups * cfg->Np; p->B = cfg->n_blocks > 0 ? cfg->n_blocks : 1;
+    memset(&p->ctr, 0, sizeof p->ctr);
+    p->multi = new MultiState();
+    p->multi->barrier.n = N;
+    const int per = cfg->n_groups / N;
+    for (int i = 0; i < N; ++i) {
+        demcmc_config c = *cfg;
+        c.n_devices = 0; c.devices = nullptr; c.device = cfg->devices[i]; c.group_begin = i * per; c.group_count = per;
+        demcmc_handle *k = nullptr;
+        const int rc = demcmc_create(&c, &k);
+        if (rc) { const std::string m = g_err; demcmc_destroy(p); return fail(rc, "device %d: %s", c.device, m.c_str()); }
+        k->parent = p; k->rank = i; k->n_ranks = N;
+        for (int g = 0; g < cfg->n_groups; ++g) k->group_owner[g] = g / per;
+        p->kids.push_back(k);
+    }
+    // migration between the devices: peer-mapped mailboxes, no host call between a device's chunks
+    for (int i = 0; i < N; ++i) {
+        demcmc_handle *k = p->kids[i];
+        if (be::set_device(k->cfg.device) || mbox_alloc(k)) { const std::string m = be::last_error(); demcmc_destroy(p); return fail(DEMCMC_ENOMEM, "migration mailbox on device %d: %s", cfg->devices[i], m.c_str()); }
+        for (int j = 0; j < N; ++j)
+            if (j != i && be::enable_peer_access(cfg->devices[i], cfg->devices[j])) {
+                const std::string m = be::last_error(); demcmc_destroy(p);
+                return fail(DEMCMC_EUNSUPPORTED, "devices %d and %d: %s (a multi-device handle needs P2P between its GPUs; shard over processes with demcmc_comm_init otherwise)", cfg->devices[i], cfg->devices[j], m.c_str());
+            }
+    }
+    for (int i = 0; i < N; ++i) {
+        demcmc_handle *k = p->kids[i];
+        for (int j = 0; j < N; ++j) { k->peers.rows[j] = p->kids[j]->mbox.rows; k->peers.flags[j] = p->kids[j]->mbox.flags; }
+        k->mbox_on = true;
+        MultiState *ms = p->multi;
+        k->mbox_barrier = [ms]() { if (be::sync()) return -1; ms->barrier.wait(); return 0; };
+    }
+    *out = p;
+    return 0;
+}
+
+static int multi_destroy(demcmc_handle *p)
+{
+    for (demcmc_handle *k : p->kids) demcmc_destroy(k);
+    delete p->multi;
+    delete p;
+    return 0;
+}
+
+// [rows][P_total][w] (host) <- per-kid [rows][P_local][w]
+template <class T, class F>
+static int multi_interleave(demcmc_handle *p, T *out, int64_t rows, size_t w, F get)
+{
+    if (!out) return 0;
+    const size_t Pt = p->P;
+    size_t off = 0;
+    for (demcmc_handle *k : p->kids) {
+        const size_t Pl = k->P;
+        std::vector<T> tmp((size_t)rows * Pl * w);
+        if (int rc = get(k, tmp.data())) return rc;
+        for (int64_t r = 0; r < rows; ++r) memcpy(out + ((size_t)r * Pt + off) * w, tmp.data() + (size_t)r * Pl * w, sizeof(T) * Pl * w);
+        off += Pl;
+    }
+    return 0;
+}
+
+static int multi_history_out(demcmc_handle *p, double *samples, double *lp, uint8_t *accept, int64_t n_rows)
+{
+    demcmc_handle *k0 = p->kids[0];
+    if (n_rows != stored_rows(k0)) return fail(DEMCMC_EINVAL, "n_rows %lld != the %lld stored rows (iterations run / store_every + n_initial)", (long long)n_rows, (long long)stored_rows(k0));
+    // one output on the first device, written by every device through peer access, downloaded once
+    BE(be::set_device(k0->cfg.device));
+    const size_t Pt = p->P, d = p->d;
+    double *ds = nullptr, *dl = nullptr; uint8_t *da = nullptr;
+    int rc = 0;
+    if (samples) ds = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * Pt * d));
+    if (lp) dl = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * Pt));
+    if (accept) da = (uint8_t *)be::dmalloc(std::max<size_t>(1, n_rows * Pt));
+    const bool lp_written = p->cfg.update == DEMCMC_UPDATE_MH;
+    if ((samples && !ds) || (lp && !dl) || (accept && !da)) rc = fail(DEMCMC_ENOMEM, "output staging does not fit on device %d", k0->cfg.device);
+    if (!rc && n_rows > 0) {
+        if ((ds && be::dzero(ds, sizeof(double) * n_rows * Pt * d)) || (dl && be::dzero(dl, sizeof(double) * n_rows * Pt)) || (da && be::dzero(da, n_rows * Pt)) || be::sync()) rc = DEMCMC_ECUDA;
+        for (demcmc_handle *k : p->kids) {
+            if (rc) break;
+            if (be::set_device(k->cfg.device) ||
+                (stored_rows(k) > 0 && (k->n0 == 0 || k->has_history) &&
+                 be::launch_history_by_id(k->hist_theta, k->hist_w, k->hist_acc, k->hist_id, stored_rows(k), 0, n_rows, (int32_t)k->P, (int32_t)d, 0, ds, lp_written ? dl : nullptr, da, (int32_t)Pt)) ||
+                be::sync()) rc = DEMCMC_ECUDA;
+        }
+        if (!rc && be::set_device(k0->cfg.device)) rc = DEMCMC_ECUDA;
+        if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * Pt * d)) rc = DEMCMC_ECUDA;
+        if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * Pt)) rc = DEMCMC_ECUDA;
+        if (!rc && da && be::d2h(accept, da, n_rows * Pt)) rc = DEMCMC_ECUDA;
+        if (rc == DEMCMC_ECUDA) fail(rc, "history gather: %s", be::last_error());
+    }
+    be::set_device(k0->cfg.device);
+    be::dfree(ds); be::dfree(dl); be::dfree(da);
+    return rc;
+}
+
+static int multi_get_chains(demcmc_handle *p, int64_t row0, int64_t n_rows, double *out)
+{
+    demcmc_handle *k0 = p->kids[0];
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > stored_rows(k0)) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)stored_rows(k0));
+    if (!k0->has_state) return fail(DEMCMC_ESTATE, "no state");
+    if (n_rows == 0) return 0;
+    BE(be::set_device(k0->cfg.device));
+    const size_t Pt = p->P, d = p->d, n = (size_t)n_rows * Pt * (d + 2);
+    double *dout = (double *)be::dmalloc(sizeof(double) * n);
+    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * Pt);
+    int rc = 0;
+    if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging does not fit on device %d", k0->cfg.device);
+    if (!rc && (be::dzero(dout, sizeof(double) * n) || be::sync())) rc = DEMCMC_ECUDA;
+    for (int phase = 1; phase <= 2 && !rc; ++phase)           // every device's final positions first, then the rows
+        for (demcmc_handle *k : p->kids) {
+            if (be::set_device(k->cfg.device) ||
+                be::launch_chains(k->hist_theta, k->hist_w, k->hist_acc, k->hist_id, cur_row(k).id, pos, row0, n_rows, (int32_t)k->P, (int32_t)d, 0, dout,
+                                  (int32_t)Pt, k->cfg.group_begin * k->cfg.Np, phase) ||
+                be::sync()) { rc = DEMCMC_ECUDA; break; }
+        }
+    if (!rc && (be::set_device(k0->cfg.device) || be::d2h(out, dout, sizeof(double) * n))) rc = DEMCMC_ECUDA;
+    if (rc == DEMCMC_ECUDA) fail(rc, "chain gather: %s", be::last_error());
+    be::set_device(k0->cfg.device);
+    be::dfree(dout); be::dfree(pos);
+    return rc;
+}
+
+static int multi_get_moments(demcmc_handle *p, int64_t row0, int64_t n_rows, int64_t *count, double *mean, double *m2)
+{
+    const size_t d = p->d;
+    std::vector<double> mk(d), sk(d);
+    double ca = 0.0;
+    for (size_t k = 0; k < d; ++k) { mean[k] = 0.0; m2[k] = 0.0; }
+    for (demcmc_handle *kid : p->kids) {                     // Chan's merge in device order (deterministic)
+        int64_t c = 0;
+        if (int rc = demcmc_get_moments(kid, row0, n_rows, &c, mk.data(), sk.data())) return rc;
+        const double cb = (double)c, cn = ca + cb;
+        if (cb > 0)
+            for (size_t k = 0; k < d; ++k) {
+                const double dl = mk[k] - mean[k];
+                mean[k] += dl * (cb / cn);
+                m2[k] += sk[k] + dl * dl * (ca * cb / cn);
+            }
+        ca = cn;
+    }
+    *count = (int64_t)ca;
+    return 0;
+}
+
 extern "C" {
 
 const char *demcmc_last_error(void) { return g_err.c_str(); }
@@ -210,12 +457,13 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     if (!cfg || !out) return fail(DEMCMC_EINVAL, "null argument");
     *out = nullptr;
     if (cfg->abi_version != DEMCMC_ABI_VERSION) return fail(DEMCMC_EINVAL, "abi_version %d != %d", cfg->abi_version, DEMCMC_ABI_VERSION);
+    if (cfg->n_devices < 0) return fail(DEMCMC_EINVAL, "negative n_devices");
     if (cfg->Np < 3) return fail(DEMCMC_EINVAL, "Np must be >= 3 (two donors besides the target, crossover.jl:158-160)");
     if (cfg->n_groups < 1 || cfg->d < 1 || !cfg->lo || !cfg->hi) return fail(DEMCMC_EINVAL, "bad n_groups/d/bounds");
     if (cfg->n_groups > MAX_MIG) return fail(DEMCMC_EUNSUPPORTED, "n_groups > %d", MAX_MIG);
     if (cfg->n_blocks < 0 || (cfg->n_blocks > 0 && !cfg->blocks)) return fail(DEMCMC_EINVAL, "blocks missing");
     if (cfg->proposal < 0 || cfg->proposal > 2) return fail(DEMCMC_EINVAL, "unknown generate_proposal %d", cfg->proposal);
-    if (cfg->store_every > 1) return fail(DEMCMC_EUNSUPPORTED, "thinning (store_every > 1) is not built yet");
+    if (cfg->store_every < 0) return fail(DEMCMC_EINVAL, "store_every must be >= 1 (0 is read as 1)");
     if (cfg->n_initial < 0 || cfg->donors < 0 || cfg->donors > 1) return fail(DEMCMC_EINVAL, "bad n_initial / donors");
     if (cfg->update < 0 || cfg->update > DEMCMC_UPDATE_MINIMIZE || cfg->fitness < 0 || cfg->fitness > DEMCMC_FITNESS_FUN) return fail(DEMCMC_EINVAL, "unknown update_particle! / evaluate_fitness! kind");
     if (cfg->update != DEMCMC_UPDATE_MH && cfg->theta_snooker != 0.0)
@@ -224,13 +472,18 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
         // resample (crossover.jl:113-124) draws from rows 1:de.iter-1: there must be rows to draw from
         if ((int64_t)cfg->n_initial * cfg->n_groups * cfg->Np < 3) return fail(DEMCMC_EINVAL, "sample = resample needs n_initial prior rows (at least 3 stored particles)");
     }
+    if (cfg->n_devices > 1) return multi_create(cfg, out);
     if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
-    if (be::set_device(cfg->device) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
+    const int dev0 = (cfg->n_devices == 1 && cfg->devices) ? cfg->devices[0] : cfg->device;
+    if (be::set_device(dev0) != 0) return fail(DEMCMC_ENODEVICE, "cannot select device %d: %s", cfg->device, be::last_error());
 
     demcmc_handle *h = new demcmc_handle();
     h->cfg = *cfg;
+    h->cfg.device = dev0; h->cfg.n_devices = 0; h->cfg.devices = nullptr;
     h->d = cfg->d;
     h->n0 = cfg->n_initial;
+    h->k_store = std::max(1, cfg->store_every);
+    h->n_scratch = h->k_store > 1 ? MAX_CHUNK + 2 : 3;
     if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), be::MAX_LANES));   // A/B measurements
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
@@ -248,10 +501,10 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->d_lo = (double *)be::dmalloc(sizeof(double) * d);
     h->d_hi = (double *)be::dmalloc(sizeof(double) * d);
     h->d_blocks = (uint8_t *)be::dmalloc(std::max<size_t>(1, h->blocks.size()));
-    h->scr_theta = (double *)be::dmalloc(sizeof(double) * 3 * P * d);
-    h->scr_w = (double *)be::dmalloc(sizeof(double) * 3 * P);
-    h->scr_id = (int32_t *)be::dmalloc(sizeof(int32_t) * 3 * P);
-    h->scr_acc = (uint8_t *)be::dmalloc(3 * P);
+    h->scr_theta = (double *)be::dmalloc(sizeof(double) * h->n_scratch * P * d);
+    h->scr_w = (double *)be::dmalloc(sizeof(double) * h->n_scratch * P);
+    h->scr_id = (int32_t *)be::dmalloc(sizeof(int32_t) * h->n_scratch * P);
+    h->scr_acc = (uint8_t *)be::dmalloc((size_t)h->n_scratch * P);
     h->prop_theta = (double *)be::dmalloc(sizeof(double) * P * d);
     h->prop_prior = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
@@ -298,8 +551,10 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
 int demcmc_destroy(demcmc_handle *h)
 {
     if (!h) return 0;
+    if (h->multi) return multi_destroy(h);
     be::set_device(h->cfg.device);
     be::sync();
+    if (!h->mbox_shared) { for (Mbox &m : h->peer_maps) be::mbox_close(&m); be::mbox_destroy(&h->mbox); }
     be::timeline_dump();
     be::dfree(h->ghist_theta); be::dfree(h->ghist_pos); be::dfree(h->gid_tmp);
     if (h->comm) be::comm_destroy(h->comm);
@@ -317,6 +572,11 @@ int demcmc_destroy(demcmc_handle *h)
 int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
 {
     if (!h || !m || !m->prior) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->multi) {
+        const int rc = for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_model(k, m); });
+        if (!rc) { h->has_model = true; h->dmodel = h->kids[0]->dmodel; }
+        return rc;
+    }
     if (m->d != h->d) return fail(DEMCMC_EINVAL, "model.d %d != config.d %d", m->d, h->d);
     BE(be::set_device(h->cfg.device));
     for (void *p : h->model_allocs) be::dfree(p);
@@ -422,6 +682,17 @@ int demcmc_set_history(demcmc_handle *h, const double *rows)
     if (!h || !rows) return fail(DEMCMC_EINVAL, "null argument");
     if (h->n0 <= 0) return fail(DEMCMC_EINVAL, "the handle was created with n_initial = 0");
     if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_history must come before the first run");
+    if (h->multi) {                                          // rows[n_initial][P_total][d] -> every device its own ids
+        const size_t Pt = h->P, dd = h->d;
+        const int rc = for_kids(h, [&](demcmc_handle *k, int) {
+            const size_t Pl = k->P, pb = (size_t)k->cfg.group_begin * k->cfg.Np;
+            std::vector<double> part((size_t)h->n0 * Pl * dd);
+            for (int64_t r = 0; r < h->n0; ++r) memcpy(part.data() + (size_t)r * Pl * dd, rows + ((size_t)r * Pt + pb) * dd, sizeof(double) * Pl * dd);
+            return demcmc_set_history(k, part.data());
+        });
+        if (!rc) h->has_history = true;
+        return rc;
+    }
     // sample = resample on a sharded job: rows of ALL ids (the donors' history is replicated); otherwise the
     // rows of the handle's own particles
     const bool sharded = h->G_local != h->cfg.n_groups && h->cfg.donors;
@@ -458,10 +729,18 @@ int demcmc_set_state(demcmc_handle *h, const double *theta, const int32_t *ids)
     if (!h) return fail(DEMCMC_EINVAL, "null argument");
     if (!theta && !(h->n0 > 0 && h->has_history)) return fail(DEMCMC_EINVAL, "null theta (allowed only after demcmc_set_history: init_particle then starts from samples[1, :, id])");
     if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model must come before set_state");
+    if (h->multi) {
+        const int rc = for_kids(h, [&](demcmc_handle *k, int) {
+            const size_t pb = (size_t)k->cfg.group_begin * k->cfg.Np;
+            return demcmc_set_state(k, theta ? theta + pb * h->d : nullptr, ids ? ids + pb : nullptr);
+        });
+        if (!rc) h->has_state = true;
+        return rc;
+    }
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
     // the current state moves to scratch row 0 (history rows already written stay as they are)
-    h->cur_hist = -1; h->cur_scratch = 0;
+    h->cur_hist = -1; h->cur_scratch = 0; h->scr_cursor = 0;
     Row r = row_of(h, false, 0);
     std::vector<int32_t> idv(P);
     for (size_t p = 0; p < P; ++p) idv[p] = ids ? ids[p] : (int32_t)(h->cfg.group_begin * h->cfg.Np + p);
@@ -491,7 +770,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     const bool ghist = cfg.donors && h->n_ranks > 1;              // donors come from the replicated history
     h->dcfg.P_hist = ghist ? (int32_t)Pt : (int32_t)P;
     if (cfg.donors && h->iter_offset > 0) return fail(DEMCMC_EUNSUPPORTED, "sample = resample draws donors from the rows of earlier iterations: a resumed handle does not hold them");
-    if (int rc = grow_history(h, h->n0 + h->iters_done + n_iter)) return rc;
+    if (int rc = grow_history(h, stored_rows(h, h->iters_done + n_iter))) return rc;
 
     // ---- replay: upload the local shard of the tape ------------------------------------------------
     uint8_t *t_kind = nullptr, *t_keep = nullptr;
@@ -543,7 +822,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             if (hi[i] < 0 || hi[i] >= lim) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx[%zu] = %d out of range", i, hi[i]); }
             if (cfg.donors && !base) {
                 const int64_t sw = (int64_t)(i / 3) / P, pl = (int64_t)(i / 3) % P;
-                const int64_t ub = h->n0 + h->iters_done + sw / B;                            // rows 1:de.iter-1
+                const int64_t ub = stored_rows(h, h->iters_done + sw / B);                   // rows 1:de.iter-1
                 const int32_t r = tape->idx_row[((size_t)sw * Pt + pbeg + pl) * 3 + i % 3];
                 if (r < 0 || r >= ub) { cleanup(); return fail(DEMCMC_EINVAL, "tape.idx_row of sweep %lld particle %lld = %d outside the %lld stored rows", (long long)sw, (long long)pl, r, (long long)ub); }
             }
@@ -624,10 +903,20 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const bool inb = in_burnin_at(it);
             basedep[s] = tape && cfg.proposal == DEMCMC_RANDOM_GAMMA && inb;
             // destination row: the history row of the iteration on its last block, else scratch
+            // (thinning: only every k_store-th iteration has a history row; the others live in the scratch ring,
+            // whose MAX_CHUNK + 2 rows keep every row of a chunk write-once)
+            const bool stored = last && (itg + 1) % h->k_store == 0;
+            const int64_t hist_row = h->n0 + (itg + 1) / h->k_store - 1;
             Row next;
             int next_scratch = -1;
-            if (last) next = row_of(h, true, h->n0 + itg);
-            else { next_scratch = (h->cur_hist >= 0) ? 0 : (h->cur_scratch + 1) % 3; next = row_of(h, false, next_scratch); }
+            if (stored) next = row_of(h, true, hist_row);
+            else {
+                // never the row of an earlier sweep of this chunk: overlapped sweeps read each other's rows out of
+                // order (a late update of sweep t still reads row t-1 while sweep t+3 is being written)
+                next_scratch = h->scr_cursor = (h->scr_cursor + 1) % h->n_scratch;
+                if (h->cur_hist < 0 && next_scratch == h->cur_scratch) next_scratch = h->scr_cursor = (h->scr_cursor + 1) % h->n_scratch;
+                next = row_of(h, false, next_scratch);
+            }
             SweepCtx &ctx = u.h_ctx[s];
             memset(&ctx, 0, sizeof ctx);
             ctx.sweep = (uint32_t)((h->iter_offset + itg) * B + b); ctx.block = blocked ? b : -1; ctx.in_burnin = inb; ctx.replay = tape != nullptr;
@@ -645,14 +934,14 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             ctx.ll_part = h->ll_part; ctx.ll_acc = h->ll_acc; ctx.ll_q = h->ll_q;
             ctx.base_cw = h->base_cw; ctx.base_tot = h->base_tot;
             // resample: donors are (row, id) cells of the rows stored before this iteration (crossover.jl:115)
-            ctx.hist_theta = ghist ? h->ghist_theta : h->hist_theta; ctx.hist_pos = ghist ? h->ghist_pos : h->hist_pos; ctx.donor_rows = h->n0 + itg;
-            ctx.next_pos = (last && h->hist_pos && !ghist) ? h->hist_pos + (size_t)(h->n0 + itg) * P : nullptr;
+            ctx.hist_theta = ghist ? h->ghist_theta : h->hist_theta; ctx.hist_pos = ghist ? h->ghist_pos : h->hist_pos; ctx.donor_rows = stored_rows(h, itg);
+            ctx.next_pos = (stored && h->hist_pos && !ghist) ? h->hist_pos + (size_t)hist_row * P : nullptr;
             if (h->tr_sweeps) {
                 ctx.tr_theta = h->tr_theta + (size_t)s_local * P * d; ctx.tr_w = h->tr_w + (size_t)s_local * P;
                 ctx.tr_adj = h->tr_adj + (size_t)s_local * P; ctx.tr_acc = h->tr_acc + (size_t)s_local * P;
                 ctx.tr_xdot = h->tr_xdot ? h->tr_xdot + (size_t)s_local * P : nullptr;
             }
-            if (last) { h->cur_hist = h->n0 + itg; }
+            if (stored) { h->cur_hist = hist_row; }
             else { h->cur_hist = -1; h->cur_scratch = next_scratch; }
             cur = next;
         }
@@ -790,22 +1079,39 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 if (a.groups[i] < 0 || a.groups[i] >= Gt) { cleanup(); return fail(DEMCMC_EINVAL, "migration group out of range"); }
                 dst[i] = h->group_owner[ms.groups[i]];
                 src[i] = h->group_owner[ms.groups[(i + ms.n - 1) % ms.n]];
+                a.src_rank[i] = (int8_t)src[i]; a.dst_rank[i] = (int8_t)dst[i];
                 cross |= src[i] != dst[i];
                 any_local |= dst[i] == h->rank;
+            }
+            // a cycle that spans ranks is one mailbox EVENT on every rank (the schedule is the same everywhere): slot
+            // seq % depth, published under the tag seq + 1; before a slot is used again every rank must have consumed it
+            const bool use_mbox = cross && h->mbox_on;
+            int mb_slot = 0;
+            unsigned long long mb_tag = 0;
+            if (use_mbox) {
+                uint64_t &seq = *h->mbox_seq_p;
+                if (seq > 0 && seq % (uint64_t)h->mbox.depth == 0 && h->mbox_barrier)
+                    if (h->mbox_barrier()) { cleanup(); return fail(DEMCMC_ECOMM, "mailbox barrier: %s", be::last_error()); }
+                mb_slot = (int)(seq % (uint64_t)h->mbox.depth);
+                mb_tag = seq + 1;
+                ++seq;
             }
             if (any_local || cross) {
                 int32_t *picks = h->d_mig_log + it * MAX_MIG;
                 BE(be::launch_mig_pick(h->dcfg, a, cur.w, picks));
                 BE(be::launch_mig_gather(h->dcfg, a, picks, cur.theta, cur.w, cur.id, cur.acc, h->d_stage));
                 const double *incoming = h->d_stage;
-                if (cross) {
+                if (use_mbox) {
+                    BE(be::launch_mig_push(h->dcfg, a, h->d_stage, h->peers, h->mbox, h->rank, mb_slot, mb_tag));
+                } else if (cross) {
                     if (!h->comm) { cleanup(); return fail(DEMCMC_ECOMM, "migration crosses ranks but demcmc_comm_init was not called"); }
                     BE(be::d2d(h->d_stage_recv, h->d_stage, sizeof(double) * ms.n * (d + 3)));
                     if (be::comm_exchange(h->comm, h->rank, ms.n, src.data(), dst.data(), h->d_stage, h->d_stage_recv, d + 3)) { cleanup(); return fail(DEMCMC_ECOMM, "%s", be::last_error()); }
                     incoming = h->d_stage_recv;
                 }
                 BE(be::launch_mig_scatter(h->dcfg, a, picks, incoming, cur.theta, cur.w, cur.id, cur.acc,
-                                          (h->hist_pos && h->cur_hist >= 0 && !ghist) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr));
+                                          (h->hist_pos && h->cur_hist >= 0 && !ghist) ? h->hist_pos + (size_t)h->cur_hist * P : nullptr,
+                                          use_mbox ? &h->mbox : nullptr, h->rank, mb_slot, mb_tag));
             }
             // the migration edited a stored row: refresh its replicated copy (collective: every rank, the
             // schedule is the same everywhere)
@@ -816,7 +1122,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // ---- update! (main.jl:161-167) -------------------------------------------------------------
         if (blocking_at(it)) {                        // blocking: every block is one sweep, one chunk each
             for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1, true)) { cleanup(); return rc; }
-            if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
+            if (ghist && h->cur_hist >= 0) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
             if (int rc = seg_end()) { cleanup(); return rc; }
             ++it;
             continue;
@@ -838,7 +1144,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             }
         }
         if (int rc = run_chunk(it, 0, n, false)) { cleanup(); return rc; }
-        if (ghist) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }     // n == 1 with resample
+        if (ghist && h->cur_hist >= 0) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }     // n == 1 with resample
         if (int rc = seg_end()) { cleanup(); return rc; }
         it += n;
     }
@@ -865,17 +1171,27 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     return 0;
 }
 
-int demcmc_run(demcmc_handle *h, int64_t n_iter) { return run_impl(h, nullptr, n_iter); }
+// a multi-device handle: one host thread per device, each running the loop of its own groups; the devices meet only in
+// the migration mailboxes (and in a host barrier when a mailbox slot comes up for reuse)
+static int multi_run(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
+{
+    if (n_iter < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    const int rc = for_kids(h, [&](demcmc_handle *k, int) { return run_impl(k, tape, n_iter); });
+    if (!rc) h->iters_done += n_iter;
+    return rc;
+}
+int demcmc_run(demcmc_handle *h, int64_t n_iter) { return (h && h->multi) ? multi_run(h, nullptr, n_iter) : run_impl(h, nullptr, n_iter); }
 int demcmc_replay(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 {
     if (!tape) return fail(DEMCMC_EINVAL, "null tape");
-    return run_impl(h, tape, n_iter);
+    return (h && h->multi) ? multi_run(h, tape, n_iter) : run_impl(h, tape, n_iter);
 }
 
 static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *accept, int64_t n_rows)
 {
     if (!h) return fail(DEMCMC_EINVAL, "null handle");
-    if (n_rows != h->iters_done + h->cfg.n_initial) return fail(DEMCMC_EINVAL, "n_rows %lld != iterations run %lld + n_initial", (long long)n_rows, (long long)h->iters_done);
+    if (h->multi) return multi_history_out(h, samples, lp, accept, n_rows);
+    if (n_rows != stored_rows(h)) return fail(DEMCMC_EINVAL, "n_rows %lld != the %lld stored rows (iterations run / store_every + n_initial)", (long long)n_rows, (long long)stored_rows(h));
     if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "by-id history of a sharded job: gather demcmc_get_history_by_slot on the host");
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
@@ -891,8 +1207,8 @@ static int history_out(demcmc_handle *h, double *samples, double *lp, uint8_t *a
         if (ds && be::dzero(ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
         if (dl && be::dzero(dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
         if (da && be::dzero(da, n_rows * P)) rc = DEMCMC_ECUDA;
-        if (!rc && n0 + h->iters_done > 0 && (n0 == 0 || h->has_history) &&
-            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, n0 + h->iters_done, 0, n_rows, (int32_t)P, (int32_t)d,
+        if (!rc && stored_rows(h) > 0 && (n0 == 0 || h->has_history) &&
+            be::launch_history_by_id(h->hist_theta, h->hist_w, h->hist_acc, h->hist_id, stored_rows(h), 0, n_rows, (int32_t)P, (int32_t)d,
                                      h->cfg.group_begin * h->cfg.Np, ds, lp_written ? dl : nullptr, da)) rc = DEMCMC_ECUDA;
         if (!rc && ds && be::d2h(samples, ds, sizeof(double) * n_rows * P * d)) rc = DEMCMC_ECUDA;
         if (!rc && dl && be::d2h(lp, dl, sizeof(double) * n_rows * P)) rc = DEMCMC_ECUDA;
@@ -910,7 +1226,8 @@ int demcmc_get_lp(demcmc_handle *h, double *out, int64_t n_rows) { return out ? 
 int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *count, double *mean, double *m2)
 {
     if (!h || !count || !mean || !m2) return fail(DEMCMC_EINVAL, "null argument");
-    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n0 + h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)(h->n0 + h->iters_done));
+    if (h->multi) return multi_get_moments(h, row0, n_rows, count, mean, m2);
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > stored_rows(h)) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)stored_rows(h));
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
     *count = n_rows * (int64_t)P;
@@ -928,7 +1245,8 @@ int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
 {
     if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
-    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n0 + h->iters_done) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)(h->n0 + h->iters_done));
+    if (h->multi) return multi_get_chains(h, row0, n_rows, out);
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > stored_rows(h)) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows", (long long)row0, (long long)(row0 + n_rows), (long long)stored_rows(h));
     if (h->n_ranks > 1) return fail(DEMCMC_EUNSUPPORTED, "chains of a sharded job: gather demcmc_get_history_by_slot on the host");
     if (!h->has_state) return fail(DEMCMC_ESTATE, "no state");
     BE(be::set_device(h->cfg.device));
@@ -949,7 +1267,14 @@ int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *ou
 
 int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, double *theta, double *w, int32_t *ids, uint8_t *acc)
 {
-    if (!h || row0 < 0 || n_rows < 0 || row0 + n_rows > h->iters_done) return fail(DEMCMC_EINVAL, "row range outside the iterations run");
+    if (h && h->multi) {
+        const size_t dd = h->d;
+        if (int rc = multi_interleave(h, theta, n_rows, dd, [&](demcmc_handle *k, double *o) { return demcmc_get_history_by_slot(k, row0, n_rows, o, nullptr, nullptr, nullptr); })) return rc;
+        if (int rc = multi_interleave(h, w, n_rows, 1, [&](demcmc_handle *k, double *o) { return demcmc_get_history_by_slot(k, row0, n_rows, nullptr, o, nullptr, nullptr); })) return rc;
+        if (int rc = multi_interleave(h, ids, n_rows, 1, [&](demcmc_handle *k, int32_t *o) { return demcmc_get_history_by_slot(k, row0, n_rows, nullptr, nullptr, o, nullptr); })) return rc;
+        return multi_interleave(h, acc, n_rows, 1, [&](demcmc_handle *k, uint8_t *o) { return demcmc_get_history_by_slot(k, row0, n_rows, nullptr, nullptr, nullptr, o); });
+    }
+    if (!h || row0 < 0 || n_rows < 0 || row0 + n_rows > stored_rows(h) - h->n0) return fail(DEMCMC_EINVAL, "row range outside the stored iterations");
     BE(be::set_device(h->cfg.device));
     const size_t P = h->P, d = h->d;
     if (n_rows == 0) return 0;
@@ -964,6 +1289,11 @@ int demcmc_get_history_by_slot(demcmc_handle *h, int64_t row0, int64_t n_rows, d
 int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *ids)
 {
     if (!h || !h->has_state) return fail(DEMCMC_ESTATE, "no state");
+    if (h->multi)
+        return for_kids(h, [&](demcmc_handle *k, int) {
+            const size_t pb = (size_t)k->cfg.group_begin * k->cfg.Np;
+            return demcmc_get_state(k, theta ? theta + pb * h->d : nullptr, weight ? weight + pb : nullptr, ids ? ids + pb : nullptr);
+        }, false);
     BE(be::set_device(h->cfg.device));
     Row r = cur_row(h);
     const size_t P = h->P, d = h->d;
@@ -976,6 +1306,14 @@ int demcmc_get_state(demcmc_handle *h, double *theta, double *weight, int32_t *i
 int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, double *log_adj, uint8_t *accepted)
 {
     if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (h->multi) {
+        const int64_t S = h->kids[0]->tr_sweeps;
+        if (!S) return fail(DEMCMC_ESTATE, "no trace: create the handle with cfg.trace = 1 and run first");
+        if (int rc = multi_interleave(h, prop_theta, S, (size_t)h->d, [&](demcmc_handle *k, double *o) { return demcmc_get_trace(k, o, nullptr, nullptr, nullptr); })) return rc;
+        if (int rc = multi_interleave(h, prop_weight, S, 1, [&](demcmc_handle *k, double *o) { return demcmc_get_trace(k, nullptr, o, nullptr, nullptr); })) return rc;
+        if (int rc = multi_interleave(h, log_adj, S, 1, [&](demcmc_handle *k, double *o) { return demcmc_get_trace(k, nullptr, nullptr, o, nullptr); })) return rc;
+        return multi_interleave(h, accepted, S, 1, [&](demcmc_handle *k, uint8_t *o) { return demcmc_get_trace(k, nullptr, nullptr, nullptr, o); });
+    }
     if (!h->tr_sweeps) return fail(DEMCMC_ESTATE, "no trace: create the handle with cfg.trace = 1 and run first");
     BE(be::set_device(h->cfg.device));
     const size_t n = (size_t)h->tr_sweeps * h->P;
@@ -989,6 +1327,7 @@ int demcmc_get_trace(demcmc_handle *h, double *prop_theta, double *prop_weight, 
 int demcmc_get_trace_xdot(demcmc_handle *h, double *xdot)
 {
     if (!h || !xdot) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->multi) return multi_interleave(h, xdot, h->kids[0]->tr_sweeps, 1, [&](demcmc_handle *k, double *o) { return demcmc_get_trace_xdot(k, o); });
     if (!h->tr_sweeps || !h->tr_xdot) return fail(DEMCMC_ESTATE, "no cross-term trace: MVNORMAL / HIER_NORMAL handle created with cfg.trace = 1, after a run");
     BE(be::set_device(h->cfg.device));
     BE(be::d2h(xdot, h->tr_xdot, sizeof(double) * (size_t)h->tr_sweeps * h->P));
@@ -998,6 +1337,7 @@ int demcmc_get_trace_xdot(demcmc_handle *h, double *xdot)
 int demcmc_set_sufficient_stat(demcmc_handle *h, int32_t on)
 {
     if (!h) return fail(DEMCMC_EINVAL, "null handle");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_sufficient_stat(k, on); }, false);
     if (on && h->has_model && h->dmodel.center_given) return fail(DEMCMC_EINVAL, "the model was centred on a caller-supplied vector: its cross term is not zero");
     h->suffstat = on != 0;
     return 0;
@@ -1006,6 +1346,16 @@ int demcmc_set_sufficient_stat(demcmc_handle *h, int32_t on)
 int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
 {
     if (!h || !slots) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->multi) {                                          // every device logged the picks of its own groups (-1 elsewhere)
+        const size_t n = (size_t)h->kids[0]->mig_log_iters * h->cfg.n_groups;
+        std::vector<int32_t> tmp(std::max<size_t>(1, n));
+        for (size_t i = 0; i < n; ++i) slots[i] = -1;
+        for (demcmc_handle *k : h->kids) {
+            if (int rc = demcmc_get_migration(k, tmp.data())) return rc;
+            for (size_t i = 0; i < n; ++i) slots[i] = std::max(slots[i], tmp[i]);
+        }
+        return 0;
+    }
     memcpy(slots, h->last_mig_slots.data(), sizeof(int32_t) * (size_t)h->mig_log_iters * h->cfg.n_groups);
     return 0;
 }
@@ -1013,6 +1363,7 @@ int demcmc_get_migration(demcmc_handle *h, int32_t *slots)
 int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_loglik)
 {
     if (!h || l2_flush_bytes < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_timing(k, l2_flush_bytes, time_loglik); }, false);
     BE(be::set_device(h->cfg.device));
     be::dfree(h->flush_buf); h->flush_buf = nullptr; h->flush_bytes = 0;
     if (l2_flush_bytes > 0) {
@@ -1027,6 +1378,7 @@ int demcmc_set_timing(demcmc_handle *h, int64_t l2_flush_bytes, int32_t time_log
 int demcmc_set_blocking_schedule(demcmc_handle *h, const uint8_t *on, int64_t n)
 {
     if (!h || n < 0 || (n > 0 && !on)) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_blocking_schedule(k, on, n); }, false);
     if (h->cfg.n_blocks <= 0) return fail(DEMCMC_EINVAL, "the handle was created without parameter blocks");
     h->block_on.assign(on, on + n);
     return 0;
@@ -1036,6 +1388,7 @@ int demcmc_set_weights(demcmc_handle *h, const double *w)
 {
     if (!h || !w) return fail(DEMCMC_EINVAL, "null argument");
     if (!h->has_state) return fail(DEMCMC_ESTATE, "set_state must come before set_weights");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_weights(k, w + (size_t)k->cfg.group_begin * k->cfg.Np); }, false);
     BE(be::set_device(h->cfg.device));
     BE(be::h2d(cur_row(h).w, w, sizeof(double) * (size_t)h->P));
     BE(be::sync());
@@ -1045,6 +1398,7 @@ int demcmc_set_weights(demcmc_handle *h, const double *w)
 int demcmc_set_iteration(demcmc_handle *h, int64_t iterations_done)
 {
     if (!h || iterations_done < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_iteration(k, iterations_done); }, false);
     if (h->iters_done > 0) return fail(DEMCMC_ESTATE, "set_iteration must come before the first run of the handle");
     h->iter_offset = iterations_done;
     return 0;
@@ -1053,6 +1407,7 @@ int demcmc_set_iteration(demcmc_handle *h, int64_t iterations_done)
 int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps)
 {
     if (!h || n_sweeps < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_max_chunk(k, n_sweeps); }, false);
     h->max_chunk = std::min<int32_t>(n_sweeps, MAX_CHUNK);
     return 0;
 }
@@ -1060,6 +1415,7 @@ int demcmc_set_max_chunk(demcmc_handle *h, int32_t n_sweeps)
 int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
 {
     if (!h || n_lanes < 1) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_lanes(k, n_lanes); }, false);
     h->n_lanes = std::min<int32_t>(n_lanes, be::MAX_LANES);
     return 0;
 }
@@ -1067,6 +1423,17 @@ int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
 int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out)
 {
     if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
+    if (h->multi) {                                          // work summed over the devices, time = the slowest device
+        demcmc_counters c = h->kids[0]->ctr;
+        for (size_t i = 1; i < h->kids.size(); ++i) {
+            const demcmc_counters &k = h->kids[i]->ctr;
+            c.particle_updates += k.particle_updates; c.loglike_evals += k.loglike_evals; c.kernel_launches += k.kernel_launches;
+            c.levels += k.levels; c.persistent_chunks += k.persistent_chunks;
+            c.device_ms = std::max(c.device_ms, k.device_ms); c.loglike_ms = std::max(c.loglike_ms, k.loglike_ms);
+        }
+        *out = c;
+        return 0;
+    }
     *out = h->ctr;
     return 0;
 }
@@ -1083,6 +1450,7 @@ static int eval_impl(demcmc_handle *h, const double *theta, int64_t n, double *l
 {
     if (!h || !theta || n < 0) return fail(DEMCMC_EINVAL, "bad argument");
     if (!h->has_model) return fail(DEMCMC_ESTATE, "set_model first");
+    if (h->multi) return eval_impl(h->kids[0], theta, n, loglike, prior, xdot);
     BE(be::set_device(h->cfg.device));
     if (n == 0) return 0;
     const size_t d = h->d, ns = (size_t)h->dmodel.n_osplit * h->dmodel.n_ksplit;
@@ -1198,6 +1566,8 @@ int demcmc_comm_unique_id(uint8_t id[128])
 int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int32_t n_ranks)
 {
     if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(DEMCMC_EINVAL, "bad argument");
+    if (h->multi || h->parent) return fail(DEMCMC_EINVAL, "a multi-device handle shards over the GPUs of this process by itself: demcmc_comm_init is for one handle per process");
+    if (n_ranks > MAX_RANKS) return fail(DEMCMC_EUNSUPPORTED, "more than %d ranks", (int)MAX_RANKS);
     const int Gt = h->cfg.n_groups;
     if (Gt % n_ranks) return fail(DEMCMC_EINVAL, "n_groups %d is not a multiple of the %d ranks", Gt, n_ranks);
     const int per = Gt / n_ranks;
@@ -1206,6 +1576,58 @@ int demcmc_comm_init(demcmc_handle *h, const uint8_t id[128], int32_t rank, int3
     if (n_ranks > 1 && be::comm_init(id, rank, n_ranks, &h->comm)) return fail(DEMCMC_ECOMM, "%s", be::last_error());
     h->rank = rank; h->n_ranks = n_ranks;
     for (int g = 0; g < Gt; ++g) h->group_owner[g] = g / per;
+    // P2P migration: every rank maps every other rank's mailbox (CUDA IPC over NVLink); the handles travel through the
+    // communicator.  All ranks take the same decision (two all-gathers of status bytes); any failure anywhere leaves
+    // the NCCL send/recv exchange in place.
+    if (n_ranks > 1 && mbox_wanted() && !h->mbox_on) {
+        MboxShared &sh = g_mbox_shared[h->cfg.device];
+        int depth, max_rows, row_len;
+        mbox_geometry(h, &depth, &max_rows, &row_len);
+        const size_t need_d = (size_t)depth * max_rows * row_len, need_f = (size_t)depth * max_rows;
+        constexpr size_t REC = 136;                          // 128-byte handle blob + status byte, 8-byte aligned
+        std::vector<uint8_t> mine(REC, 0), all(REC * n_ranks, 0);
+        uint8_t *dsend = (uint8_t *)be::dmalloc(REC), *drecv = (uint8_t *)be::dmalloc(REC * n_ranks);
+        // every rank calls gather() the same number of times whatever happened locally: the status bytes carry failures
+        auto gather = [&](uint8_t status) {
+            mine[128] = status;
+            const bool sent = dsend && drecv && !be::h2d(dsend, mine.data(), REC) && !be::comm_allgather(h->comm, dsend, drecv, REC) &&
+                              !be::d2h(all.data(), drecv, REC * n_ranks);
+            int lo = 255;
+            for (int r = 0; r < n_ranks; ++r) lo = std::min<int>(lo, all[REC * r + 128]);
+            return sent ? lo : 0;                            // the smallest status anybody reported
+        };
+        const bool fits = sh.box.rows && sh.n_ranks == n_ranks && sh.rank == rank && sh.cap_doubles >= need_d && sh.cap_flags >= need_f;
+        bool use = false;
+        if (gather(fits ? 2 : 1) == 2) use = true;           // round 1: does everybody's cached mailbox fit this job?
+        else {
+            Mbox fresh = { nullptr, nullptr, 0, 0, 0 };
+            const bool made = be::mbox_create(depth, max_rows, row_len, &fresh) == 0 && be::mbox_export(fresh, mine.data()) == 0;
+            const bool all_made = gather(made ? 1 : 0) == 1; // round 2: everybody publishes a new mailbox
+            PeerTable pt = {};
+            bool opened = all_made;
+            for (int r = 0; r < n_ranks && opened; ++r) {
+                if (r == rank) { pt.rows[r] = fresh.rows; pt.flags[r] = fresh.flags; continue; }
+                Mbox pm = { nullptr, nullptr, 0, 0, 0 };
+                if (be::mbox_open(all.data() + REC * r, &pm)) opened = false;
+                else { pt.rows[r] = pm.rows; pt.flags[r] = pm.flags; }
+            }
+            if (gather(opened ? 1 : 0) == 1) {               // round 3: everybody mapped everybody
+                // (an older mailbox stays mapped by the peers: it is abandoned, never freed under them)
+                sh.box = fresh; sh.peers = pt; sh.cap_doubles = need_d; sh.cap_flags = need_f; sh.n_ranks = n_ranks; sh.rank = rank;
+                use = true;
+            }
+        }
+        be::dfree(dsend); be::dfree(drecv);
+        if (use) {
+            h->mbox = sh.box; h->mbox.depth = depth; h->mbox.max_rows = max_rows; h->mbox.row_len = row_len;
+            h->peers = sh.peers;
+            h->mbox_shared = true;                            // owned by the process, not by the handle
+            h->mbox_seq_p = &sh.seq;                          // ... and so is the event counter: it only ever grows
+            h->mbox_on = true;
+            void *comm = h->comm;
+            h->mbox_barrier = [comm]() { return be::comm_barrier(comm); };
+        }
+    }
     return 0;
 }
 

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,16 +28,21 @@
 namespace de {
 namespace be {
 
+// Threading: one host thread drives one device at a time (a multi-device handle runs one thread per device,
+// engine.cpp).  What is "current" (device, lane, launch counter) is thread-local; what belongs to a device
+// (streams, events, staging buffers, the NCCL communicator) lives in per-device slots whose lazy creation is
+// serialised by g_mu.  Two handles on the SAME device must not be driven from two threads at once.
+static std::mutex g_mu;
 static thread_local std::string g_be_err;
-static int64_t g_launches = 0;
-static int g_dev = 0;
+static thread_local int64_t g_launches = 0;
+static thread_local int g_dev = 0;
 // Lanes: independent sets of groups run as concurrent kernel chains, one stream per lane, so the
 // likelihood kernel of one lane covers the propose / accept latency of the other (engine.cpp).
 // Lane 0 is the engine stream; every copy, event and one-off kernel runs there.
-static int g_lane = 0;
+static thread_local int g_lane = 0;
 static cudaStream_t g_stream[64][MAX_LANES] = { { nullptr } };
 static cudaEvent_t g_lane_ev[64][MAX_LANES] = { { nullptr } };
-static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+static cudaEvent_t g_t0[64] = { nullptr }, g_t1[64] = { nullptr };
 
 static int cu_fail(cudaError_t e, const char *what)
 {
@@ -48,7 +54,10 @@ static int cu_fail(cudaError_t e, const char *what)
 
 static cudaStream_t stream()
 {
-    if (!g_stream[g_dev][g_lane]) cudaStreamCreateWithFlags(&g_stream[g_dev][g_lane], cudaStreamNonBlocking);
+    if (!g_stream[g_dev][g_lane]) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_stream[g_dev][g_lane]) cudaStreamCreateWithFlags(&g_stream[g_dev][g_lane], cudaStreamNonBlocking);
+    }
     return g_stream[g_dev][g_lane];
 }
 
@@ -221,6 +230,7 @@ static std::vector<PinnedBlock> g_pinned;
 void *hmalloc_pinned(size_t bytes)
 {
     if (!bytes) bytes = 8;
+    std::lock_guard<std::mutex> lk(g_mu);
     for (auto &b : g_pinned)
         if (!b.busy && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096) { b.busy = true; return b.p; }
     void *p = nullptr;
@@ -232,6 +242,7 @@ void *hmalloc_pinned(size_t bytes)
 void hfree_pinned(void *p)
 {
     if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mu);
     for (auto &b : g_pinned) if (b.p == p) { b.busy = false; return; }
     cudaFreeHost(p);
 }
@@ -311,16 +322,16 @@ int tevent_elapsed(void *a, void *b, double *ms)
 int dfill(void *dst, int byte, size_t bytes) { if (bytes) CU(cudaMemsetAsync(dst, byte, bytes, stream())); return 0; }
 int timer_start()
 {
-    if (!g_t0) { CU(cudaEventCreate(&g_t0)); CU(cudaEventCreate(&g_t1)); }
-    CU(cudaEventRecord(g_t0, stream()));
+    if (!g_t0[g_dev]) { CU(cudaEventCreate(&g_t0[g_dev])); CU(cudaEventCreate(&g_t1[g_dev])); }
+    CU(cudaEventRecord(g_t0[g_dev], stream()));
     return 0;
 }
 int timer_stop(double *ms)
 {
-    CU(cudaEventRecord(g_t1, stream()));
-    CU(cudaEventSynchronize(g_t1));
+    CU(cudaEventRecord(g_t1[g_dev], stream()));
+    CU(cudaEventSynchronize(g_t1[g_dev]));
     float f = 0.f;
-    CU(cudaEventElapsedTime(&f, g_t0, g_t1));
+    CU(cudaEventElapsedTime(&f, g_t0[g_dev], g_t1[g_dev]));
     *ms = f;
     return 0;
 }
@@ -1851,18 +1862,56 @@ __global__ void __launch_bounds__(128) k_mig_gather(ConfigDev cfg, MigArgs a, co
 }
 
 // shift_particles! (migration.jl:109-116): position i receives the particle picked at position i-1
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(128) k_mig_scatter(ConfigDev cfg, MigArgs a, const int32_t *picks, const double *stage,
-                                                     double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos)
+                                                     double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos,
+                                                     Mbox mbox, int rank, int slot, unsigned long long tag)
 {
     const int i = blockIdx.x, gl = a.groups[i] - cfg.group_begin;
     if (gl < 0 || gl >= cfg.G_local) return;
     const size_t p = (size_t)gl * cfg.Np + picks[i];
-    const double *row = stage + (size_t)((i + a.n - 1) % a.n) * (cfg.d + 3);
-    for (int k = threadIdx.x; k < cfg.d; k += blockDim.x) theta[p * cfg.d + k] = row[k];
-    if (threadIdx.x == 0) {
-        w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2];
-        if (pos) pos[(int32_t)row[cfg.d + 1] - cfg.group_begin * cfg.Np] = (int32_t)p;
+    const int r = (i + a.n - 1) % a.n;
+    const double *row = stage + (size_t)r * (cfg.d + 3);
+    if (mbox.rows && a.src_rank[i] != rank) {
+        // the row was produced on another rank: it arrives in this rank's mailbox (k_mig_push over NVLink)
+        const size_t cell = (size_t)slot * mbox.max_rows + r;
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = gtime();
+            while (ld_acquire_sys_u64(mbox.flags + cell) != tag) {
+                __nanosleep(100);
+                if (gtime() - t0 > 30000000000ull) __trap();      // a peer that never arrives: trap, do not hang the device
+            }
+        }
+        __syncthreads();
+        row = mbox.rows + cell * mbox.row_len;
     }
+    for (int k = threadIdx.x; k < cfg.d; k += blockDim.x) theta[p * cfg.d + k] = __ldcv(row + k);
+    if (threadIdx.x == 0) {
+        const double rw = __ldcv(row + cfg.d), rid = __ldcv(row + cfg.d + 1), ra = __ldcv(row + cfg.d + 2);
+        w[p] = rw; id[p] = (int32_t)rid; acc[p] = (uint8_t)ra;
+        if (pos) pos[(int32_t)rid - cfg.group_begin * cfg.Np] = (int32_t)p;
+    }
+}
+
+// rows produced here and consumed on another rank: store them into the consumer's mailbox, then publish the tag
+__global__ void __launch_bounds__(128) k_mig_push(ConfigDev cfg, MigArgs a, const double *stage, PeerTable peers, Mbox geom,
+                                                  int rank, int slot, unsigned long long tag)
+{
+    const int i = blockIdx.x;
+    if (a.src_rank[i] != rank || a.dst_rank[i] == rank) return;
+    const int r = (i + a.n - 1) % a.n, dst = a.dst_rank[i];
+    const size_t cell = (size_t)slot * geom.max_rows + r;
+    const double *row = stage + (size_t)r * (cfg.d + 3);
+    double *out = peers.rows[dst] + cell * geom.row_len;
+    for (int k = threadIdx.x; k < cfg.d + 3; k += blockDim.x) out[k] = row[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(peers.flags[dst] + cell), "l"(tag) : "memory");
 }
 
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks)
@@ -1879,10 +1928,63 @@ int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *pic
     return 0;
 }
 int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta,
-                       double *w, int32_t *id, uint8_t *acc, int32_t *pos)
+                       double *w, int32_t *id, uint8_t *acc, int32_t *pos, const Mbox *mbox, int rank, int slot, unsigned long long tag)
 {
-    k_mig_scatter<<<a.n, 128, 0, stream()>>>(cfg, a, picks, stage, theta, w, id, acc, pos);
+    Mbox none = { nullptr, nullptr, 0, 0, 0 };
+    k_mig_scatter<<<a.n, 128, 0, stream()>>>(cfg, a, picks, stage, theta, w, id, acc, pos, mbox ? *mbox : none, rank, slot, tag);
     LAUNCHED("k_mig_scatter");
+    return 0;
+}
+int launch_mig_push(const ConfigDev &cfg, const MigArgs &a, const double *stage, const PeerTable &peers, const Mbox &geom,
+                    int rank, int slot, unsigned long long tag)
+{
+    k_mig_push<<<a.n, 128, 0, stream()>>>(cfg, a, stage, peers, geom, rank, slot, tag);
+    LAUNCHED("k_mig_push");
+    return 0;
+}
+// The mailbox is plain cudaMalloc memory: stream-ordered pool memory cannot be exported with cudaIpcGetMemHandle
+int mbox_create(int depth, int max_rows, int row_len, Mbox *out)
+{
+    out->depth = depth; out->max_rows = max_rows; out->row_len = row_len; out->rows = nullptr; out->flags = nullptr;
+    const size_t cells = (size_t)depth * max_rows;
+    CU(cudaMalloc(&out->rows, sizeof(double) * cells * row_len));
+    CU(cudaMalloc(&out->flags, sizeof(unsigned long long) * cells));
+    CU(cudaMemset(out->flags, 0, sizeof(unsigned long long) * cells));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+void mbox_destroy(Mbox *m) { if (m->rows) cudaFree(m->rows); if (m->flags) cudaFree(m->flags); m->rows = nullptr; m->flags = nullptr; }
+int mbox_export(const Mbox &m, uint8_t handle[128])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two IPC handles fill the 128-byte blob");
+    cudaIpcMemHandle_t hr, hf;
+    CU(cudaIpcGetMemHandle(&hr, m.rows));
+    CU(cudaIpcGetMemHandle(&hf, m.flags));
+    memcpy(handle, &hr, 64); memcpy(handle + 64, &hf, 64);
+    return 0;
+}
+int mbox_open(const uint8_t handle[128], Mbox *peer)
+{
+    cudaIpcMemHandle_t hr, hf;
+    memcpy(&hr, handle, 64); memcpy(&hf, handle + 64, 64);
+    CU(cudaIpcOpenMemHandle((void **)&peer->rows, hr, cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle((void **)&peer->flags, hf, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+void mbox_close(Mbox *peer) { if (peer->rows) cudaIpcCloseMemHandle(peer->rows); if (peer->flags) cudaIpcCloseMemHandle(peer->flags); peer->rows = nullptr; peer->flags = nullptr; }
+int enable_peer_access(int dev, int peer_dev)
+{
+    if (dev == peer_dev) return 0;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, dev, peer_dev));
+    if (!can) { g_be_err = "no peer access between the two devices"; return -1; }
+    int keep = 0;
+    CU(cudaGetDevice(&keep));
+    CU(cudaSetDevice(dev));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(keep);
+    if (e != cudaSuccess) return cu_fail(e, "cudaDeviceEnablePeerAccess");
     return 0;
 }
 
@@ -1893,13 +1995,13 @@ int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *pi
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_history(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid,
                                                  int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int P, int d, int id_base,
-                                                 double *samples, double *lp, uint8_t *accept)
+                                                 double *samples, double *lp, uint8_t *accept, int P_ids)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int slot = blockIdx.y;
     if (r >= n_rows_dev) return;
     const int id = rid[r * P + slot] - id_base;
-    if (id < 0 || id >= P) return;
+    if (id < 0 || id >= P_ids) return;
     const int64_t ro = row0 + r;
     if (samples) for (int k = 0; k < d; ++k) samples[((int64_t)id * d + k) * n_rows_out + ro] = rt[(r * P + slot) * d + k];
     if (lp) lp[(int64_t)id * n_rows_out + ro] = rw[r * P + slot];
@@ -1908,10 +2010,10 @@ __global__ void __launch_bounds__(256) k_history(const double *rt, const double 
 
 int launch_history_by_id(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
                          int64_t n_rows_dev, int64_t row0, int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base,
-                         double *samples, double *lp, uint8_t *accept)
+                         double *samples, double *lp, uint8_t *accept, int32_t P_ids)
 {
     dim3 grid((unsigned)((n_rows_dev + 255) / 256), (unsigned)P);
-    k_history<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, n_rows_dev, row0, n_rows_out, P, d, id_base, samples, lp, accept);
+    k_history<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, n_rows_dev, row0, n_rows_out, P, d, id_base, samples, lp, accept, P_ids > 0 ? P_ids : P);
     LAUNCHED("k_history");
     return 0;
 }
@@ -1919,22 +2021,22 @@ int launch_history_by_id(const double *rows_theta, const double *rows_w, const u
 // bundle_samples (main.jl:222-250) on the device: chains[c][k][row] for rows [row0, row0+n_rows) of
 // the history; parameter columns k < d of chain c are the draws of particle id c, the columns
 // "acceptance" (d) and "lp" (d+1) belong to the particle sitting at final position c
-__global__ void __launch_bounds__(256) k_chain_pos(const int32_t *final_id, int P, int id_base, int32_t *pos_of_id)
+__global__ void __launch_bounds__(256) k_chain_pos(const int32_t *final_id, int P, int id_base, int32_t *pos_of_id, int P_ids, int pos_base)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P) return;
     const int id = final_id[c] - id_base;
-    if (id >= 0 && id < P) pos_of_id[id] = c;
+    if (id >= 0 && id < P_ids) pos_of_id[id] = pos_base + c;
 }
 __global__ void __launch_bounds__(256) k_chains(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid,
-                                                const int32_t *pos_of_id, int64_t row0, int64_t n_rows, int P, int d, int id_base, double *out)
+                                                const int32_t *pos_of_id, int64_t row0, int64_t n_rows, int P, int d, int id_base, double *out, int P_ids)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int slot = blockIdx.y;
     if (r >= n_rows) return;
     const int64_t row = row0 + r;
     const int id = rid[row * P + slot] - id_base;
-    if (id < 0 || id >= P) return;
+    if (id < 0 || id >= P_ids) return;
     const double *src = rt + (row * P + slot) * d;
     double *dst = out + (int64_t)id * (d + 2) * n_rows + r;
     for (int k = 0; k < d; ++k) dst[(int64_t)k * n_rows] = src[k];
@@ -1944,13 +2046,17 @@ __global__ void __launch_bounds__(256) k_chains(const double *rt, const double *
 }
 
 int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t *rows_acc, const int32_t *rows_id,
-                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out)
+                  const int32_t *final_id, int32_t *pos_scratch, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out,
+                  int32_t P_ids, int32_t pos_base, int phase)
 {
-    k_chain_pos<<<(P + 255) / 256, 256, 0, stream()>>>(final_id, P, id_base, pos_scratch);
-    LAUNCHED("k_chain_pos");
-    if (n_rows <= 0) return 0;
+    if (P_ids <= 0) P_ids = P;
+    if (phase & 1) {
+        k_chain_pos<<<(P + 255) / 256, 256, 0, stream()>>>(final_id, P, id_base, pos_scratch, P_ids, pos_base);
+        LAUNCHED("k_chain_pos");
+    }
+    if (n_rows <= 0 || !(phase & 2)) return 0;
     dim3 grid((unsigned)((n_rows + 255) / 256), (unsigned)P);
-    k_chains<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, pos_scratch, row0, n_rows, P, d, id_base, out);
+    k_chains<<<grid, 256, 0, stream()>>>(rows_theta, rows_w, rows_acc, rows_id, pos_scratch, row0, n_rows, P, d, id_base, out, P_ids);
     LAUNCHED("k_chains");
     return 0;
 }
@@ -2184,12 +2290,14 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
 
 static int nccl_load()
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     if (g_nccl.lib) return 0;
     const char *names[] = { "libnccl.so.2", "libnccl.so" };
     for (const char *n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
@@ -2197,7 +2305,7 @@ static int nccl_load()
 #define SYM(field, sym) do { *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, sym); if (!g_nccl.field) { g_be_err = std::string("libnccl misses ") + sym; g_nccl.lib = nullptr; return -1; } } while (0)
     SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
     SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
-    SYM(AllGather, "ncclAllGather");
+    SYM(AllGather, "ncclAllGather"); SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return 0;
@@ -2255,6 +2363,13 @@ int comm_destroy(void *comm)
 int comm_allgather(void *comm, const void *send, void *recv, size_t bytes_per_rank)
 {
     NC(g_nccl.AllGather(send, recv, bytes_per_rank, 0 /* ncclInt8 */, (nccl_comm)comm, stream()));
+    return 0;
+}
+int comm_barrier(void *comm)
+{
+    static int32_t *buf[64] = { nullptr };
+    if (!buf[g_dev]) { CU(cudaMalloc(&buf[g_dev], 2 * sizeof(int32_t))); CU(cudaMemset(buf[g_dev], 0, 2 * sizeof(int32_t))); }
+    NC(g_nccl.AllReduce(buf[g_dev], buf[g_dev] + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, (nccl_comm)comm, stream()));
     return 0;
 }
 __global__ void __launch_bounds__(256) k_pos_from_ids(const int32_t *ids, int n, int32_t *pos)

@@ -21,8 +21,12 @@ class Handle:
     def __init__(self, n_groups, Np, d, lo, hi, burnin=1000, n_initial=0, alpha=0.1, beta=0.1, eps=0.001,
                  sigma=0.05, kappa=1.0, theta_snooker=0.0, proposal="random_gamma", blocks=None, seed=0,
                  device=0, group_begin=0, group_count=0, trace=False, store_every=1, resample=False, update="mh", fitness="posterior",
-                 blocking_schedule=None):
+                 blocking_schedule=None, devices=None):
+        """devices=[0, 1, ...]: ONE handle over several GPUs of the box from this one process (cfg.n_devices)."""
         self._h = C.c_void_p()
+        self.devices = None if devices is None or len(devices) <= 1 else np.ascontiguousarray(devices, dtype=np.int32)
+        if devices is not None and len(devices) == 1:
+            device = int(devices[0])
         self.lo, self.hi = f8(lo), f8(hi)
         if self.lo.shape != (d,) or self.hi.shape != (d,):
             raise ValueError("bounds must be expanded to one (lo, hi) per flattened parameter")
@@ -32,13 +36,14 @@ class Handle:
         self.cfg = _ffi.Config(_ffi.ABI_VERSION, n_groups, Np, d, burnin, n_initial, alpha, beta, eps, sigma, kappa,
                                theta_snooker, prop, nb, ptr(self.blocks, _bp), ptr(self.lo, _dp), ptr(self.hi, _dp),
                                int(seed) & (2**64 - 1), device, group_begin, group_count, int(bool(resample)), int(bool(trace)), store_every,
-                               UPDATES[update], FITNESS[fitness])
+                               UPDATES[update], FITNESS[fitness], 0 if self.devices is None else self.devices.size, ptr(self.devices, _ip))
         self.n_groups, self.Np, self.d = n_groups, Np, d
         self.G_local = group_count if group_count > 0 else n_groups
         self.P = self.G_local * Np
         self.P_total = n_groups * Np
         self.B = max(1, nb)
         self.n_initial = n_initial
+        self.store_every = max(1, int(store_every))
         self.iterations = 0
         self._last_iters = 0
         self._keep = []
@@ -158,7 +163,12 @@ class Handle:
     # ---- results -------------------------------------------------------------------------------
     @property
     def n_rows(self):
-        return self.iterations + self.n_initial
+        """rows of de.samples held: the n_initial prior rows + every store_every-th iteration"""
+        return self.iterations // self.store_every + self.n_initial
+
+    @property
+    def stored_iterations(self):
+        return self.iterations // self.store_every
 
     def samples(self):
         """de.samples in Julia memory order: returned as a numpy array of shape (P, d, n_rows),
@@ -180,7 +190,7 @@ class Handle:
     def chains(self, row0=0, n_rows=None):
         """bundle_samples on the device: array of shape (P, d+2, n_rows) in Julia memory order, i.e.
         out[c, k, r] == Julia Array(n_rows, d+2, P)[r+1, k+1, c+1] of iterations row0+r."""
-        n = self.iterations - row0 if n_rows is None else n_rows
+        n = self.stored_iterations - row0 if n_rows is None else n_rows
         out = np.empty((self.P, self.d + 2, max(n, 0)))
         if n > 0:
             check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
@@ -203,14 +213,14 @@ class Handle:
     def moments(self, row0=0, n_rows=None):
         """Pooled posterior summary computed on the device (no download of the draws): (count, mean[d],
         var[d] with ddof=1) over history rows [row0, row0+n_rows) and all local particles."""
-        n = self.iterations - row0 if n_rows is None else n_rows
+        n = self.stored_iterations - row0 if n_rows is None else n_rows
         cnt = C.c_int64(0)
         mean, m2 = np.zeros(self.d), np.zeros(self.d)
         check(_ffi.lib().demcmc_get_moments(self._h, int(row0), int(n), C.byref(cnt), ptr(mean, _dp), ptr(m2, _dp)))
         return cnt.value, mean, m2 / max(cnt.value - 1, 1)
 
     def history_by_slot(self, row0=0, n_rows=None):
-        n = self.iterations - row0 if n_rows is None else n_rows
+        n = self.stored_iterations - row0 if n_rows is None else n_rows
         th = np.zeros((n, self.P, self.d))
         w = np.zeros((n, self.P))
         ids = np.zeros((n, self.P), dtype=np.int32)

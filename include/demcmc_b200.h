@@ -107,11 +107,23 @@ typedef struct {
                                 iteration and after each migration) */
     int32_t trace;           /* 1: keep per-sweep proposals / proposal weights / log_adj for
                                 demcmc_get_trace (parity tests) */
-    int32_t store_every;     /* 1 = keep every iteration (reference behaviour, utilities.jl:161-180) */
+    int32_t store_every;     /* 1 (or 0) = keep every iteration (reference behaviour, utilities.jl:161-180); k > 1 = thinning:
+                                only iterations k, 2k, 3k, ... get a row of de.samples (configs[4] writes
+                                26.5 MB per iteration per GPU).  Every row count of this header (n_rows, row0) then counts
+                                STORED rows: n_initial + iterations / k.  sample = resample draws its donors from the
+                                stored rows. */
     int32_t update;          /* DEMCMC_UPDATE_*; maximize!/minimize! need theta_snooker == 0 (they take no log_adj:
                                 the reference's snooker branch would throw a MethodError, crossover.jl:38) and
                                 leave accept / lp untouched (false / 0.0) */
     int32_t fitness;         /* DEMCMC_FITNESS_* */
+    int32_t n_devices;       /* 0 / 1: the handle lives on `device`.  N > 1: ONE handle over the N GPUs devices[0..N) of this
+                                box, from ONE process: the groups shard over the devices in order (n_groups % N == 0), one
+                                host thread of the library drives each device, migration crosses NVLink through peer-mapped
+                                mailboxes, and every demcmc_get_* call returns the whole job exactly as a single-device
+                                handle would (same chains bit for bit).  This is what replaces the ThreadsX.map over groups
+                                of p_update! (src/main.jl:135-148) for a Julia caller: no MPI, no torchrun.  group_begin /
+                                group_count must be 0; sample = resample is not available in this mode. */
+    const int32_t *devices;  /* [n_devices] CUDA ordinals, all different, with P2P access to each other */
 } demcmc_config;
 
 /* Structured replay tape: the reference's own random draws, recorded

@@ -9,15 +9,21 @@
 # What it adds to the package:
 #   * `GPULoglike(kind; data...)`  -- binds a model to a registered hand-written likelihood kernel
 #   * `GPUPrior(specs...)`         -- registered prior specs (one per named parameter)
+#   * `GPUDEModel(; prior_loglike, loglike, names, sample_prior)` = `DEModel(loglike::GPULoglike; ...)`:
+#     its OWN entry points -- the package's keyword constructor `DEModel(args...; ...)`
+#     (src/structs.jl:176-189) is NOT redefined (Julia does not dispatch on keyword types: a method
+#     with the same positional signature would replace it and break every CPU model)
 #   * `sample(model::DEModel{<:GPULoglike}, de::DE, n_iter)` and the `MCMCThreads()` method:
-#     `sample_init` (src/main.jl:263-271) runs unchanged on the host, the state is uploaded, ONE
+#     `gpu_sample_init` draws the initial particles exactly as `sample_init` + `init_particle`
+#     (src/main.jl:263-271, src/utilities.jl:13-41) but leaves the initial weights to the device
+#     (`evaluate_fitness!` would call the plugin object on the host), the state is uploaded, ONE
 #     ccall runs all n_iter iterations of step!/pstep! (src/main.jl:84-107) on the device, and the
 #     unchanged `bundle_samples` (src/main.jl:222-250) builds the Chains.
 # A DEModel whose loglike is any other callable keeps using the package's CPU path; asking for the
 # GPU path with a closure throws an ArgumentError -- there is no silent CPU fallback.
 
 const LIBDEMCMC = get(ENV, "LIBDEMCMC_B200", "libdemcmc_b200.so")
-const DEMCMC_ABI_VERSION = Int32(3)
+const DEMCMC_ABI_VERSION = Int32(4)
 
 const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5, rastrigin = 6)
 const GPU_PRIORS = (flat = 0, normal = 1, halfcauchy = 2, uniform = 3, beta = 4, normal_ref = 5)
@@ -62,10 +68,40 @@ struct GPUPrior
 end
 GPUPrior(specs::Tuple...) = GPUPrior(collect(Tuple, specs))
 
-# DEModel(; ...) wraps loglike/prior_loglike in closures (src/structs.jl:184-188), which would hide
-# the plugin object: keep it unwrapped when it is a GPULoglike.
-function DEModel(args...; prior_loglike::GPUPrior, loglike::GPULoglike, names, sample_prior, data = nothing, kwargs...)
-    return DEModel(prior_loglike, loglike, sample_prior, names)   # positional inner constructor, src/structs.jl:169-174
+# The package's keyword constructor DEModel(args...; prior_loglike, loglike, names, sample_prior, data, kwargs...)
+# (src/structs.jl:176-189) wraps loglike / prior_loglike in closures, which would hide the plugin object -- and it
+# must stay as it is for every CPU model.  A GPU model therefore has its OWN constructors, which store the plugin
+# unwrapped through the positional inner constructor DEModel(prior_loglike, loglike, sample_prior, names)
+# (src/structs.jl:169-174):
+#   GPUDEModel(; prior_loglike = GPUPrior(...), loglike = GPULoglike(...), names, sample_prior)
+#   DEModel(GPULoglike(...); prior_loglike = GPUPrior(...), names, sample_prior)     # one POSITIONAL plugin argument
+# (the second is a distinct, more specific method than DEModel(args...; ...): it does not replace it).
+# prior_loglike may be `nothing` for optimize with evaluate_fun! (src/utilities.jl:113-120 never calls it).
+function GPUDEModel(; prior_loglike::Union{GPUPrior, Nothing} = nothing, loglike::GPULoglike, names, sample_prior)
+    return DEModel(prior_loglike, loglike, sample_prior, names)
+end
+function DEModel(loglike::GPULoglike; prior_loglike::Union{GPUPrior, Nothing} = nothing, names, sample_prior)
+    return GPUDEModel(; prior_loglike, loglike, names, sample_prior)
+end
+
+# sample_init (src/main.jl:263-271) + init_particle (src/utilities.jl:13-22) for a GPU model: the same
+# de.samples array (initialize_samples, src/utilities.jl:29-41, unchanged: it only calls model.sample_prior()), the
+# same sample_prior() call per particle in id order, the same zeroed accept / lp vectors -- but NOT
+# de.evaluate_fitness!(de, model, p): that would call the GPULoglike / GPUPrior objects on the host.  The initial
+# weights are computed by demcmc_set_state on the device.
+function gpu_sample_init(model::DEModel, de::DE, n_iter)
+    de.samples = initialize_samples(de, model, n_iter)
+    N = n_iter + de.n_initial
+    id = 0
+    groups = [[begin
+                   id += 1
+                   Θ = de.n_initial > 0 ? de.samples[1, :, id] : model.sample_prior()
+                   p = Particle(; Θ, id)
+                   p.accept = fill(false, N)
+                   p.lp = fill(0.0, N)
+                   p
+               end for _ = 1:(de.Np)] for _ = 1:(de.n_groups)]
+    return groups
 end
 
 # ---- C structs (include/demcmc_b200.h) -----------------------------------------------------------
@@ -89,6 +125,7 @@ struct CModel
     prior::Ptr{CPrior}
     data_on_device::Int32
     reserved::Int32
+    center::Ptr{Float64}   # C_NULL: centre the data on their column means (the product default)
 end
 
 struct CConfig
@@ -156,6 +193,7 @@ function prior_table(model, Θ)
         pos += n_elems(θ)
     end
     table = CPrior[]
+    model.prior_loglike === nothing && return fill(CPrior(GPU_PRIORS[:flat], 0, 0.0, 0.0), pos)   # evaluate_fun! never calls it
     for (spec, θ) in zip(model.prior_loglike.specs, Θ)
         kind = GPU_PRIORS[spec[1]]
         a = length(spec) > 1 ? Float64(spec[2]) : 0.0
@@ -192,8 +230,8 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
         throw(ArgumentError("de.sample must be `sample` or `resample`: a custom donor function cannot run on the device"))
     donors = de.sample === resample ? Int32(1) : Int32(0)
     ll = model.loglike
-    # sample_init (src/main.jl:263-271) unchanged: initial Θ and ids are the reference's own
-    groups = sample_init(model, de, n_iter)
+    # initial Θ and ids drawn exactly as sample_init does (src/main.jl:263-271), weights left to the device
+    groups = gpu_sample_init(model, de, n_iter)
     particles = vcat(groups...)
     Θ1 = particles[1].Θ
     d = sum(n_elems, Θ1)
@@ -241,7 +279,7 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
-                isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0)
+                isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0, C_NULL)
             demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
             if n_blocks > 0 && !all(!iszero, block_on)         # block updating in some iterations only
                 GC.@preserve block_on demcmc_check(ccall((:demcmc_set_blocking_schedule, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], block_on, length(block_on)))

@@ -8,6 +8,7 @@
 // oracle on a machine without a GPU.  "Device" memory is plain malloc; each "kernel" is a loop
 // that honours the same contract as the CUDA kernel of the same name.
 #include <math.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -19,8 +20,8 @@
 namespace de {
 namespace be {
 
-static std::string g_err;
-static int64_t g_launches = 0;
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
 // exchange hook so a CPU test can stand in for NCCL (tests/test_multirank_gloo.py)
 typedef int (*exchange_fn)(int rank, int n, const int *src_rank, const int *dst_rank, double *send, double *recv, int row_len, void *user);
 static exchange_fn g_exchange = nullptr;
@@ -304,14 +305,23 @@ int launch_mig_gather(const ConfigDev &cfg, const MigArgs &a, const int32_t *pic
     return 0;
 }
 
-int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos)
+// The migration mailbox of the double: host memory shared by the threads of one process (a multi-device handle runs
+// one thread per "device"); same protocol as k_mig_push / k_mig_scatter -- rows, then a release store of the tag.
+int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *picks, const double *stage, double *theta, double *w, int32_t *id, uint8_t *acc, int32_t *pos,
+                       const Mbox *mbox, int rank, int slot, unsigned long long tag)
 {
     ++g_launches;
     for (int i = 0; i < a.n; ++i) {
         const int gl = a.groups[i] - cfg.group_begin;
         if (gl < 0 || gl >= cfg.G_local) continue;
         const size_t p = (size_t)gl * cfg.Np + picks[i];
-        const double *row = stage + (size_t)((i + a.n - 1) % a.n) * (cfg.d + 3);
+        const int r = (i + a.n - 1) % a.n;
+        const double *row = stage + (size_t)r * (cfg.d + 3);
+        if (mbox && mbox->rows && a.src_rank[i] != rank) {
+            const size_t cell = (size_t)slot * mbox->max_rows + r;
+            while (__atomic_load_n(mbox->flags + cell, __ATOMIC_ACQUIRE) != tag) sched_yield();
+            row = mbox->rows + cell * mbox->row_len;
+        }
         memcpy(theta + p * cfg.d, row, sizeof(double) * cfg.d);
         w[p] = row[cfg.d]; id[p] = (int32_t)row[cfg.d + 1]; acc[p] = (uint8_t)row[cfg.d + 2];
         if (pos) pos[id[p] - cfg.group_begin * cfg.Np] = (int32_t)p;
@@ -320,13 +330,14 @@ int launch_mig_scatter(const ConfigDev &cfg, const MigArgs &a, const int32_t *pi
 }
 
 int launch_history_by_id(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid, int64_t n_rows_dev, int64_t row0,
-                         int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base, double *samples, double *lp, uint8_t *accept)
+                         int64_t n_rows_out, int32_t P, int32_t d, int32_t id_base, double *samples, double *lp, uint8_t *accept, int32_t P_ids)
 {
     ++g_launches;
+    if (P_ids <= 0) P_ids = P;
     for (int64_t r = 0; r < n_rows_dev; ++r)
         for (int slot = 0; slot < P; ++slot) {
             const int id = rid[r * P + slot] - id_base;
-            if (id < 0 || id >= P) continue;
+            if (id < 0 || id >= P_ids) continue;
             const int64_t ro = row0 + r;
             if (samples) for (int k = 0; k < d; ++k) samples[((int64_t)id * d + k) * n_rows_out + ro] = rt[(r * P + slot) * d + k];
             if (lp) lp[(int64_t)id * n_rows_out + ro] = rw[r * P + slot];
@@ -336,15 +347,17 @@ int launch_history_by_id(const double *rt, const double *rw, const uint8_t *ra, 
 }
 
 int launch_chains(const double *rt, const double *rw, const uint8_t *ra, const int32_t *rid, const int32_t *final_id, int32_t *pos,
-                  int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out)
+                  int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t id_base, double *out, int32_t P_ids, int32_t pos_base, int phase)
 {
     ++g_launches;
-    for (int c = 0; c < P; ++c) { const int id = final_id[c] - id_base; if (id >= 0 && id < P) pos[id] = c; }
+    if (P_ids <= 0) P_ids = P;
+    if (phase & 1) for (int c = 0; c < P; ++c) { const int id = final_id[c] - id_base; if (id >= 0 && id < P_ids) pos[id] = pos_base + c; }
+    if (!(phase & 2)) return 0;
     for (int64_t r = 0; r < n_rows; ++r)
         for (int slot = 0; slot < P; ++slot) {
             const int64_t row = row0 + r;
             const int id = rid[row * P + slot] - id_base;
-            if (id < 0 || id >= P) continue;
+            if (id < 0 || id >= P_ids) continue;
             for (int k = 0; k < d; ++k) out[((int64_t)id * (d + 2) + k) * n_rows + r] = rt[(row * P + slot) * d + k];
             out[((int64_t)pos[id] * (d + 2) + d) * n_rows + r] = (double)ra[row * P + slot];
             out[((int64_t)pos[id] * (d + 2) + d + 1) * n_rows + r] = rw[row * P + slot];
@@ -396,6 +409,31 @@ int fp64_peak(double *t) { *t = 0.0; return 0; }
 int fp64_peaks(double *a, double *b) { if (a) *a = 0.0; if (b) *b = 0.0; return 0; }
 int copy_peak(double *g) { *g = 0.0; return 0; }
 
+int launch_mig_push(const ConfigDev &cfg, const MigArgs &a, const double *stage, const PeerTable &peers, const Mbox &geom, int rank, int slot, unsigned long long tag)
+{
+    ++g_launches;
+    for (int i = 0; i < a.n; ++i) {
+        if (a.src_rank[i] != rank || a.dst_rank[i] == rank) continue;
+        const int r = (i + a.n - 1) % a.n, dst = a.dst_rank[i];
+        const size_t cell = (size_t)slot * geom.max_rows + r;
+        memcpy(peers.rows[dst] + cell * geom.row_len, stage + (size_t)r * (cfg.d + 3), sizeof(double) * (cfg.d + 3));
+        __atomic_store_n(peers.flags[dst] + cell, tag, __ATOMIC_RELEASE);
+    }
+    return 0;
+}
+int mbox_create(int depth, int max_rows, int row_len, Mbox *out)
+{
+    out->depth = depth; out->max_rows = max_rows; out->row_len = row_len;
+    out->rows = (double *)calloc((size_t)depth * max_rows * row_len, sizeof(double));
+    out->flags = (unsigned long long *)calloc((size_t)depth * max_rows, sizeof(unsigned long long));
+    return (out->rows && out->flags) ? 0 : -1;
+}
+void mbox_destroy(Mbox *m) { free(m->rows); free(m->flags); m->rows = nullptr; m->flags = nullptr; }
+int mbox_export(const Mbox &, uint8_t *) { g_err = "the test double has no inter-process mailbox"; return -1; }
+int mbox_open(const uint8_t *, Mbox *) { g_err = "the test double has no inter-process mailbox"; return -1; }
+void mbox_close(Mbox *) {}
+int enable_peer_access(int, int) { return 0; }
+int comm_barrier(void *) { return 0; }
 int comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return 0; }
 int comm_init(const uint8_t *, int, int, void **comm) { *comm = malloc(8); return 0; }
 int comm_destroy(void *comm) { free(comm); return 0; }

@@ -548,3 +548,72 @@ def test_optimize_updates(mode, model, update):
 
 def test_optimize_api():                            # test/optimization_tests.jl at its own size
     common.optimize_checks()
+
+
+# ---- thinning and the multi-device handle: the bodies of the CPU tests, on the device ---------------------------------
+import test_host_logic_emu as E  # noqa: E402
+
+
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.4)), ("gaussian", dict(kappa=0.8)),
+                                      ("hier_normal", dict(blocks=True, alpha=0.3))])
+def test_thinned_run_keeps_every_kth_row_of_the_full_run(model, kw):
+    E.test_thinned_run_keeps_every_kth_row_of_the_full_run(None, model, kw)
+
+
+def test_thinned_resample_runs_on_the_stored_rows():
+    E.test_thinned_resample_runs_on_the_stored_rows(None)
+
+
+def test_thinned_run_through_the_persistent_kernel():
+    """configs[1]-like shape: chunks of 16 overlapped sweeps write 15 scratch rows + 1 history row each"""
+    rng = np.random.default_rng(6)
+    case = make_case("mvnormal", rng, n_obs=3000)
+    G, Np, n_iter = 4, 64, 48
+    th0 = case.theta0(rng, G * Np)
+    outs = []
+    for every in (1, 16, 5):
+        with case.handle(G, Np, seed=3, burnin=5, alpha=0.05, theta_snooker=0.1, store_every=every) as h:
+            h.set_state(th0)
+            h.run(n_iter)
+            outs.append((h.samples(), h.get_state(), h.counters()))
+    assert outs[0][2]["persistent_chunks"] > 0 and outs[1][2]["persistent_chunks"] > 0
+    assert np.array_equal(outs[1][0], outs[0][0][:, :, 15::16]) and np.array_equal(outs[2][0], outs[0][0][:, :, 4::5])
+    assert all(np.array_equal(a, b) for a, b in zip(outs[1][1], outs[0][1]))
+
+
+def _n_gpus():
+    return D._ffi.lib().demcmc_device_count()
+
+
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.6)), ("lnr", dict(alpha=0.5)),
+                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2))])
+def test_multi_device_handle_is_the_single_device_chain(model, kw):
+    if _n_gpus() < 2:
+        pytest.skip("a multi-device handle needs two GPUs (gpurun --gpus 2)")
+    E.test_multi_device_handle_is_the_single_device_chain(None, model, kw, 2)
+    if _n_gpus() >= 4:
+        E.test_multi_device_handle_is_the_single_device_chain(None, model, kw, 4)
+
+
+def test_multi_device_handle_replays_the_oracle():
+    if _n_gpus() < 2:
+        pytest.skip("a multi-device handle needs two GPUs (gpurun --gpus 2)")
+    E.test_multi_device_handle_replays_the_oracle_and_checks_its_arguments(None)
+
+
+def test_multi_device_sample_api_at_configs1_shape():
+    """sample(model, de, n_iter, devices=[...]) from ONE process: the single-GPU chains bit for bit (persistent kernel on
+    every device, migration through the peer-mapped mailboxes)"""
+    if _n_gpus() < 2:
+        pytest.skip("a multi-device handle needs two GPUs (gpurun --gpus 2)")
+    rng = np.random.default_rng(50514)
+    n, dm, G, Np, n_iter = 20_000, 50, 8, 64, 60
+    x = rng.normal(rng.normal(size=dm), 1.0, size=(n, dm))
+    outs = []
+    for devices in (None, list(range(min(_n_gpus(), 4)))):
+        r2 = np.random.default_rng(1)
+        model = D.DEModel(sample_prior=lambda: [r2.normal(size=dm), abs(r2.standard_cauchy()) + 0.2], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                          loglike=D.GPULoglike("mvnormal", x), names=("μ", "σ"))
+        de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=Np, burnin=10, θsnooker=0.1, α=0.3, seed=5)
+        outs.append(D.sample(model, de, n_iter, devices=devices).value)
+    assert np.array_equal(outs[0], outs[1])

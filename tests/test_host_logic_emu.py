@@ -455,3 +455,109 @@ def test_cross_term_mutation_is_caught_by_the_cpu_suite(emu):
     assert subprocess.run([sys.executable, script, common.EMU_LIB], env=env, capture_output=True).returncode == 0
     env["DEMCMC_TEST_CORRUPT"] = "1"
     assert subprocess.run([sys.executable, script, common.EMU_LIB], env=env, capture_output=True).returncode == 3
+
+
+# ---- thinning (demcmc_config.store_every) and the multi-device handle (demcmc_config.n_devices) ---------------
+def _full_outputs(h):
+    return dict(samples=h.samples(), accept=h.accept(), lp=h.lp(), chains=h.chains(), state=h.get_state(), mom=h.moments(),
+                slot=h.history_by_slot(), mig=h.migration_slots(), updates=h.counters()["particle_updates"])
+
+
+def _same(a, b):
+    if isinstance(a, (tuple, list)):
+        return all(_same(x, y) for x, y in zip(a, b))
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.4)), ("gaussian", dict(kappa=0.8)),
+                                      ("hier_normal", dict(blocks=True, alpha=0.3))])
+def test_thinned_run_keeps_every_kth_row_of_the_full_run(emu, model, kw):
+    """store_every = k: the chain is the same chain; de.samples holds iterations k, 2k, ... only"""
+    rng = np.random.default_rng(11)
+    case = make_case(model, rng)
+    kw = dict(kw)
+    if kw.pop("blocks", False):
+        kw["blocks"] = hier_blocks(9)
+    G, Np, n_iter, k = 4, 7, 23, 3
+    th0 = case.theta0(rng, G * Np)
+    outs = []
+    for every in (1, k):
+        with case.handle(G, Np, seed=3, burnin=5, store_every=every, **kw) as h:
+            h.set_state(th0)
+            h.run(10)
+            h.run(n_iter - 10)                     # two calls: the history grows in place
+            assert h.n_rows == n_iter // every
+            outs.append(_full_outputs(h))
+    full, thin = outs
+    keep = np.arange(k - 1, n_iter, k)
+    assert np.array_equal(thin["samples"], full["samples"][:, :, keep])
+    assert np.array_equal(thin["accept"], full["accept"][:, keep]) and np.array_equal(thin["lp"], full["lp"][:, keep])
+    assert _same(thin["state"], full["state"]) and thin["updates"] == full["updates"]
+    assert np.array_equal(thin["slot"][0], full["slot"][0][keep]) and np.array_equal(thin["slot"][2], full["slot"][2][keep])
+    # bundle_samples of the kept rows: parameter columns are the kept draws of each id
+    d = case.d
+    assert np.array_equal(thin["chains"][:, :d, :], full["chains"][:, :d, :][:, :, keep])
+
+
+def test_thinned_resample_runs_on_the_stored_rows(emu):
+    rng = np.random.default_rng(4)
+    case = make_case("mvnormal", rng)
+    G, Np, n0 = 2, 5, 6
+    rows = np.stack([case.theta0(rng, G * Np) for _ in range(n0)])
+    with case.handle(G, Np, seed=2, burnin=4, n_initial=n0, resample=True, store_every=4, theta_snooker=0.2) as h:
+        h.set_history(rows)
+        h.set_state(None)
+        h.run(17)
+        assert h.n_rows == n0 + 4
+        s = h.samples()
+        assert np.array_equal(s[:, :, :n0], rows.transpose(1, 2, 0)) and np.isfinite(s).all()
+
+
+@pytest.mark.parametrize("n_dev", [2, 4])
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.6)), ("lnr", dict(alpha=0.5)),
+                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2))])
+def test_multi_device_handle_is_the_single_device_chain(emu, model, kw, n_dev):
+    """cfg.n_devices = N: one handle, one process, N devices (host threads of the test double here), migration through
+    the mailboxes -- every output identical to the single-device handle's, bit for bit"""
+    rng = np.random.default_rng(21)
+    case = make_case(model, rng)
+    kw = dict(kw)
+    if kw.pop("blocks", False):
+        kw["blocks"] = hier_blocks(9)
+    G, Np, n_iter = 4, 6, 25
+    th0 = case.theta0(rng, G * Np)
+    outs = []
+    for devices in (None, list(range(n_dev))):
+        with case.handle(G, Np, seed=8, burnin=6, trace=True, devices=devices, **kw) as h:
+            h.set_state(th0)
+            h.run(n_iter)
+            o = _full_outputs(h)
+            o["trace"] = h.trace()
+            o["eval"] = h.eval(th0[:5])
+            outs.append(o)
+    one, many = outs
+    assert (one["mig"] >= 0).any(), "no migration happened: the test would not cross devices"
+    for key in ("samples", "accept", "lp", "chains", "state", "slot", "mig", "updates", "eval"):
+        assert _same(one[key], many[key]), key
+    for key in one["trace"]:
+        assert np.array_equal(one["trace"][key], many["trace"][key], equal_nan=True), key
+    assert one["mom"][0] == many["mom"][0] and rel_err(many["mom"][1], one["mom"][1]) < 1e-13 and rel_err(many["mom"][2], one["mom"][2]) < 1e-12
+
+
+def test_multi_device_handle_replays_the_oracle_and_checks_its_arguments(emu):
+    rng = np.random.default_rng(2)
+    case = make_case("mvnormal", rng)
+    G, Np, n_iter = 4, 5, 8
+    th0 = case.theta0(rng, G * Np)
+    cfg = case.oracle_config(G, Np, seed=5, burnin=3, alpha=0.5, theta_snooker=0.2)
+    r = O.run(cfg, case.oracle_model(), th0, n_iter)
+    with case.handle(G, Np, seed=5, burnin=3, alpha=0.5, theta_snooker=0.2, devices=[0, 1]) as h:
+        h.set_state(th0)
+        h.replay(r["tape"], n_iter)
+        assert np.array_equal(h.accept(), r["accept"])
+        assert rel_err(h.samples(), r["samples"]) < 1e-12
+        with pytest.raises(D._ffi.DemcmcError):
+            h.comm_init(bytes(128), 0, 2)
+    for bad in (dict(devices=[0, 0]), dict(devices=[0, 1, 2]), dict(devices=[0, 1], resample=True, n_initial=4)):
+        with pytest.raises(D._ffi.DemcmcError):
+            case.handle(G, Np, **bad)
