@@ -58,7 +58,8 @@ class Tape(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("sweeps", C.c_int64), ("particle_updates", C.c_int64),
                 ("loglike_evals", C.c_int64), ("kernel_launches", C.c_int64), ("levels", C.c_int64),
-                ("device_ms", C.c_double), ("loglike_ms", C.c_double), ("persistent_chunks", C.c_int64)]
+                ("device_ms", C.c_double), ("loglike_ms", C.c_double), ("persistent_chunks", C.c_int64),
+                ("mailbox_events", C.c_int64), ("cross_migrations", C.c_int64)]
 
 
 # every symbol include/demcmc_b200.h declares (tests check the library exports all of them)

@@ -853,6 +853,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     if (n_iter > 0) {
         h->d_mig_log = (int32_t *)be::dmalloc(sizeof(int32_t) * n_iter * MAX_MIG);
         if (!h->d_mig_log) { cleanup(); return fail(DEMCMC_ENOMEM, "migration log"); }
+        BE(be::dfill(h->d_mig_log, 0xFF, sizeof(int32_t) * n_iter * MAX_MIG));   // -1: a cycle this rank took no part in
     }
 
     const int64_t launches0 = be::launch_count();
@@ -1086,6 +1087,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             // a cycle that spans ranks is one mailbox EVENT on every rank (the schedule is the same everywhere): slot
             // seq % depth, published under the tag seq + 1; before a slot is used again every rank must have consumed it
             const bool use_mbox = cross && h->mbox_on;
+            if (cross) ++h->ctr.cross_migrations;
+            if (use_mbox) ++h->ctr.mailbox_events;
             int mb_slot = 0;
             unsigned long long mb_tag = 0;
             if (use_mbox) {
@@ -1428,7 +1431,7 @@ int demcmc_get_counters(demcmc_handle *h, demcmc_counters *out)
         for (size_t i = 1; i < h->kids.size(); ++i) {
             const demcmc_counters &k = h->kids[i]->ctr;
             c.particle_updates += k.particle_updates; c.loglike_evals += k.loglike_evals; c.kernel_launches += k.kernel_launches;
-            c.levels += k.levels; c.persistent_chunks += k.persistent_chunks;
+            c.levels += k.levels; c.persistent_chunks += k.persistent_chunks;   // (mailbox_events / cross_migrations: the same on every device)
             c.device_ms = std::max(c.device_ms, k.device_ms); c.loglike_ms = std::max(c.loglike_ms, k.loglike_ms);
         }
         *out = c;

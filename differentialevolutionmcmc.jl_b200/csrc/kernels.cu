@@ -1985,6 +1985,13 @@ int enable_peer_access(int dev, int peer_dev)
     if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); e = cudaSuccess; }
     cudaSetDevice(keep);
     if (e != cudaSuccess) return cu_fail(e, "cudaDeviceEnablePeerAccess");
+    // device memory here comes from the stream-ordered pool (dmalloc), which peer access does not cover by itself:
+    // `dev` must be granted access to peer_dev's pool as well
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, peer_dev));
+    cudaMemAccessDesc desc = {};
+    desc.location.type = cudaMemLocationTypeDevice; desc.location.id = dev; desc.flags = cudaMemAccessFlagsProtReadWrite;
+    CU(cudaMemPoolSetAccess(pool, &desc, 1));
     return 0;
 }
 

@@ -14,6 +14,9 @@ from .api import DE, DEModel, MCMCThreads, _flatten, build_handle, bundle_sample
 from .handle import comm_unique_id
 
 
+last_counters = None
+
+
 def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
     """sample(model, de, n_iter) / sample(model, de, MCMCThreads(), n_iter) on all ranks of the default
     process group.  Returns the Chains on rank 0 and None elsewhere.  `unique_id`: a communicator id
@@ -68,6 +71,8 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
             h.set_state(box[0][rank * P_local:(rank + 1) * P_local])
         h.run(n_iter)
         de.iter = n_iter + de.n_initial
+        global last_counters
+        last_counters = h.counters()                         # of this rank's shard (which migration transport ran, launches, ...)
         part = h.history_by_slot()                           # theta[n][P_local][d], w, ids, acc -- by position
         parts = [None] * world if rank == 0 else None
         dist.gather_object(part, parts, dst=0)

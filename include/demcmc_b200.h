@@ -150,6 +150,9 @@ typedef struct {
     double device_ms;        /* CUDA-event time of the last run/replay call */
     double loglike_ms;       /* of which: likelihood kernels (0 unless timing was requested) */
     int64_t persistent_chunks; /* chunks (<= 16 overlapped sweeps) that ran as ONE persistent launch */
+    int64_t mailbox_events;    /* migrations whose cycle crossed ranks / devices and went through the peer-mapped mailboxes
+                                  (0 with the NCCL send/recv exchange, DEMCMC_MIG=nccl) */
+    int64_t cross_migrations;  /* migrations whose cycle crossed ranks / devices, whatever the transport */
 } demcmc_counters;
 
 typedef struct demcmc_handle demcmc_handle;

@@ -39,5 +39,8 @@ if rank == 0:
     print(f"distributed.sample{' (sample = resample)' if RESAMPLE else ''} on {world} GPUs: chains {chains.value.shape}, identical to the single-GPU sample(): {same}; "
           f"{G * Np * n_iter / dt:.0f} particle-updates/s end to end", flush=True)
     assert same
+    c = distributed.last_counters
+    print(f"migration transport: DEMCMC_MIG={os.environ.get('DEMCMC_MIG', 'mailbox (default)')}: {c['cross_migrations']} cross-rank migrations, "
+          f"{c['mailbox_events']} through the peer-mapped mailboxes, {c['persistent_chunks']} persistent chunks", flush=True)
 dist.barrier()
 dist.destroy_process_group()
