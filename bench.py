@@ -36,6 +36,12 @@ CONFIG_NAME = "BASELINE configs[1]"
 L2_FLUSH_BYTES = 256 << 20
 
 
+def workload_string():
+    """config.workload: the same string on both arms (the driver compares them)"""
+    return (f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, "
+            f"crossover+snooker {THETA_SNOOKER} ({CONFIG_NAME})")
+
+
 def workload(n_groups, seed=50514):
     rng = np.random.default_rng(seed)
     mu = rng.normal(size=N_DIM)
@@ -185,7 +191,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles, crossover+snooker {THETA_SNOOKER} (BASELINE configs[1])"},
+            "config": {"workload": workload_string(), "groups_total": GROUPS_PER_GPU, "particles_total": GROUPS_PER_GPU * NP,
+                       "note": "the CPU arm always runs ONE GPU's share of the job (4 groups): at --gpus N > 1 the B200 arm runs N times as many groups, so only the N = 1 ratio compares like with like"},
             "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "C restatement of the reference's algorithm (oracle/), one thread per group; the reference itself is Julia and cannot run in this image"},
             "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -290,7 +297,24 @@ def run_b200(args):
     h.run(args.steps)
     barrier()
     windows.append((tw, time.time(), "steady pass"))
-    ms_steady = h.counters()["device_ms"]
+    ms_steady = torch.tensor([h.counters()["device_ms"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms_steady, op=dist.ReduceOp.MAX)
+    ms_steady = float(ms_steady.item())
+    c3 = h.counters()
+    # SURVEY hard part 7, reported separately: with the data centred on their column means the streamed cross term is
+    # analytically zero, so the same chain follows from O(d) sufficient statistics -- the O(N d) stream skipped
+    ms_suff = None
+    if world == 1:
+        h.set_sufficient_stat(True)
+        h.run(args.warmup)
+        barrier()
+        tw = time.time()
+        h.run(args.steps)
+        barrier()
+        windows.append((tw, time.time(), "sufficient-statistic pass"))
+        ms_suff = h.counters()["device_ms"]
+        h.set_sufficient_stat(False)
     ck = clocks.stop(windows)
     h.close()
 
@@ -314,7 +338,7 @@ def run_b200(args):
                 "measured_in": measured_in,
                 "peak_source": "measured in this run (MEASURED_PEAKS.json has no fp64 entry): the larger of a DFMA loop and a DMMA m8n8k4 loop, 8 warps x 8 CTAs/SM; the two fp64 paths share one pipe on B200",
                 "peak_dfma": dfma_peak, "peak_dmma": dmma_peak,
-                "note": "bound = the fp64 tensor path (DMMA m8n8k4; peak = this run's fp64 microbenchmarks, not the bf16 figure of MEASURED_PEAKS.json): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work; for the persistent kernel the duration includes the proposals and accepts it runs (6 of the 148 SMs do only those)",
+                "note": "bound = the fp64 tensor path (DMMA m8n8k4; peak = this run's fp64 microbenchmarks, not the bf16 figure of MEASURED_PEAKS.json): ~400 flop/B against the L2-resident data set; algorithmic work = 2*N*d flop per particle update (one multiply-add per observation x dimension x particle, contraction form of the sum of squares); padding of d to whole k-steps of 4 and of levels to whole octets of particles is NOT counted as work; for the persistent kernel the duration includes the proposals and accepts it runs (the scalar SMs do only those). WHAT THE STREAM COMPUTES: the kernel centres the data on their exact column means, so the streamed cross term B = sum_i sum_k x'_ik m'_k is analytically ZERO and the log-likelihood rests on the O(d) terms sum x'^2 and n sum m'^2; every observation is streamed for every particle only because the metric counts 'loglike evals incl.' (SURVEY hard part 7) -- value_sufficient_stat is the same chain with the stream skipped. The kernel's arithmetic is pinned on operands whose answer is not zero by tests/test_gpu_xdot.py (caller-supplied centre, B against an extended-precision reference to 2^-40 of its Cauchy-Schwarz bound, both launch paths, mutation tests)",
                 "hbm_gbs_measured": peaks.get("hbm_gbs")}
 
     # ---- end to end through the public API with HOST buffers -------------------------------------
@@ -358,37 +382,74 @@ def run_b200(args):
             e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "call": "sample(model, de, n_iter) with host (pageable numpy) data: handle creation, data upload + packing, P sample_prior() calls, all iterations, device-side bundle_samples and the download of the chains; timed on the second call of the process",
                    "seconds": t_e2e, "seconds_by_part": {k: round(v, 4) for k, v in parts.items()}}
-            # ESS/s (the second half of BASELINE.json's metric): min over parameters of the bulk ESS of the
-            # second half of that same run (all chains pooled) / the wall time of the whole call
-            if args.steps >= 100 and not args.no_ess:
-                from demcmc_b200.diagnostics import bulk_ess
-                half = chains.value[args.steps // 2:, :d, :]
-                ess = [bulk_ess(half[:, k, :]) for k in range(d)]
-                e2e["ess"] = {"min_bulk_ess": float(np.nanmin(ess)), "median_bulk_ess": float(np.nanmedian(ess)),
-                              "ess_per_s": float(np.nanmin(ess)) / t_e2e, "draws": int(half.shape[0]), "chains": int(half.shape[2]),
-                              "note": "started from prior draws with burnin=0; draws of the second half of the run, "
-                                      "rank-normalised split bulk ESS (Vehtari et al. 2021), min over the 51 parameters"}
     if world > 1:
-        # sharded e2e: every rank builds its handle from host buffers, runs, and downloads its by-slot history
+        # sharded e2e through the user-facing call: every rank calls distributed.sample(model, de, n_iter) with HOST data;
+        # rank 0 gets the Chains (per-rank by-slot histories gathered and merged by id on the host)
+        from demcmc_b200 import distributed
+
+        def make():
+            r = np.random.default_rng(7)
+            m = D.DEModel(sample_prior=lambda: [r.normal(size=N_DIM), abs(r.standard_cauchy())],
+                          prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)), loglike=D.GPULoglike("mvnormal", x), names=("μ", "σ"))
+            return m, D.DE(sample_prior=m.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=NP, burnin=0, θsnooker=THETA_SNOOKER, seed=11)
+        m_, de_ = make()
+        distributed.sample(m_, de_, min(args.steps, 16), device=local)      # untimed: contexts, pools, host pages
+        m_, de_ = make()
         barrier()
         t0 = time.perf_counter()
-        h2 = D.Handle(G, NP, d, lo, hi, **kw)
-        h2.set_model("mvnormal", prior, x=x)
-        uid2 =[D.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid2, src=0)
-        h2.comm_init(uid2[0], rank, world)
-        h2.set_state(theta0[rank * P_local:(rank + 1) * P_local])
-        h2.run(args.steps)
-        hist = h2.history_by_slot()
-        h2.close()
+        chains = distributed.sample(m_, de_, args.steps, device=local)
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_e2e = float(t_e2e.item())
+        if rank == 0:
+            assert len(chains) == args.steps and chains.value.shape[2] == G * NP
         e2e = {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (x.nbytes + P_local * d * 8) / args.steps,
                "d2h_bytes_per_step": P_local * (d * 8 + 8 + 4 + 1), "seconds": t_e2e,
-               "call": "per rank: Handle + set_model(host data) + set_state + run + history_by_slot (host buffers in and out)"}
-        del hist
+               "call": "distributed.sample(model, de, n_iter) on every rank with host (numpy) data: handle creation, data upload + packing, the P sample_prior() draws "
+                       "on rank 0 and their broadcast, all iterations (migration across ranks included), the download of every rank's history, the gather on rank 0 and the "
+                       "by-id merge into the Chains; max over ranks of the wall time between two barriers, second call of the process",
+               "migration": distributed.last_counters and {k: distributed.last_counters[k] for k in ("cross_migrations", "mailbox_events")}}
+
+    # ---- ESS/s, the second half of BASELINE.json's metric: a fixed-length leg, whatever --steps is -----------------------
+    if rank == 0 and world == 1 and not args.no_ess:
+        from demcmc_b200.diagnostics import bulk_ess
+        n_ess, burn_ess = 1000, 400
+        xbar = x.mean(axis=0)
+        s_pool = float(np.sqrt(((x - xbar) ** 2).sum() / x.size))
+        r3 = np.random.default_rng(13)
+        # chains started around the posterior mode (xbar +- a posterior sd): from N(0,1) prior draws this model needs
+        # thousands of iterations before any draw is usable (d = 51, posterior sd 0.003); the ESS of unconverged chains says nothing
+        m3 = D.DEModel(sample_prior=lambda: [xbar + r3.normal(0, s_pool / np.sqrt(N_OBS), N_DIM), s_pool * (1 + r3.normal(0, 5e-4))],
+                       prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)), loglike=D.GPULoglike("mvnormal", x), names=("μ", "σ"))
+        de3 = D.DE(sample_prior=m3.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=NP, burnin=burn_ess, θsnooker=THETA_SNOOKER, seed=17)
+        t0 = time.perf_counter()
+        ch3 = D.sample(m3, de3, n_ess, device=local)
+        t_ess = time.perf_counter() - t0
+        ess = np.array([bulk_ess(ch3.value[:, k, :]) for k in range(d)])
+        from demcmc_b200.diagnostics import split_rhat
+        rhat = np.array([split_rhat(ch3.value[:, k, :]) for k in range(0, d, 10)])
+        if e2e is None:
+            e2e = {}
+        e2e["ess"] = {"min_bulk_ess": float(np.nanmin(ess)), "median_bulk_ess": float(np.nanmedian(ess)), "ess_per_s": float(np.nanmin(ess)) / t_ess,
+                      "seconds": t_ess, "iterations": n_ess, "burnin_discarded": burn_ess, "draws": int(ch3.value.shape[0]), "chains": int(ch3.value.shape[2]),
+                      "max_split_rhat_sampled": float(np.nanmax(rhat)),
+                      "note": "ESS/s = min over the 51 parameters of the rank-normalised split bulk ESS (Vehtari et al. 2021) of the kept draws, all chains pooled, "
+                              "divided by the wall time of the WHOLE sample() call (host data in, burn-in iterations included, chains out); 1000 iterations of which the "
+                              "first 400 are discarded; chains started around the posterior mode (a cold start from the N(0,1) prior needs thousands of iterations "
+                              "at d = 51 with posterior sd 0.003)"}
+
+    # ---- the other BASELINE shapes, one GPU (scripts/bench_configs.py): driver-observed companion numbers -----------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_configs
+        configs = []
+        for name in ("c1", "c3", "c4", "c5"):
+            try:
+                configs.append(bench_configs.run(name, peaks=(dfma_peak, dmma_peak), hbm_gbs=peaks.get("hbm_gbs")))
+            except Exception as e:                                   # a companion number must never cost the headline line
+                configs.append({"config": name, "error": repr(e)})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -399,11 +460,14 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"isotropic MVN d={N_DIM}, {N_OBS} obs, {GROUPS_PER_GPU} groups x {NP} particles per GPU, crossover+snooker {THETA_SNOOKER} ({CONFIG_NAME})",
+                "config": {"workload": workload_string(),
                            "groups_total": G, "particles_total": G * NP, "parallelism": f"groups sharded over {world} GPU(s); NCCL send/recv migration",
                            "l2": f"flushed: {L2_FLUSH_BYTES >> 20} MiB overwritten before every segment = a migration (with its NCCL exchange) plus the chunk of overlapped steps that follows it (a chunk ends at the next migration, at most 16 steps; steps inside a chunk share launches so there is no per-step boundary); per-segment CUDA events, flush excluded",
                            "timing": "CUDA events on the library's launching stream (demcmc_counters.device_ms), max over ranks"},
-                "value_steady_no_flush": updates / (ms_steady * 1e-3) if world == 1 else None,
+                "value_steady_no_flush": updates / (ms_steady * 1e-3),
+                "value_sufficient_stat": (c3["particle_updates"] - c2["particle_updates"]) / (ms_suff * 1e-3) if ms_suff else None,
+                "value_sufficient_stat_note": "the same chain with the O(N d) stream skipped (demcmc_set_sufficient_stat; exact: the cross term is analytically zero with mean-centred data); NOT the headline: the metric counts log-likelihood evaluations that stream every observation" if ms_suff else None,
+                "configs": configs,
                 "gpu_launches": int(launches), "clocks": ck, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall_timed}
         sys.stdout.flush()
@@ -421,7 +485,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s estimate of the e2e leg")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the companion numbers of the other BASELINE shapes")
     # the same step on another BASELINE shape (the contract's line is the default, configs[1]); configs[4] is
     # --dim 100 --particles 4096 --groups-per-gpu 8 on 8 GPUs
     ap.add_argument("--dim", type=int, default=None, help="dimensions of the multivariate normal (default 50)")

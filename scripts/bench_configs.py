@@ -81,7 +81,13 @@ def config(name):
     raise KeyError(name)
 
 
-def run(name, iters=None):
+# fp64 warp-instructions the LBA kernel executes per (trial x particle) density, from the committed ncu capture
+# (profiles/: smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on / 32 / densities); the fp64 pipe issues
+# 64 lanes per SM per clock = 2 warp-instructions, i.e. peak_dfma_tflops / 2 / 32 warp-instructions per second
+LBA_FP64_WARP_INST_PER_DENSITY = None      # filled in from the r02 capture (see profiles/README.md)
+
+
+def run(name, iters=None, peaks=None, hbm_gbs=None):
     c = config(name)
     n_iter = iters or c["iters"]
     P = c["G"] * c["Np"]
@@ -105,7 +111,7 @@ def run(name, iters=None):
         h.run(n_iter)
         c2 = h.counters()
         if c2["loglike_ms"] > 0:
-            dfma, dmma = D.fp64_peaks(0)
+            dfma, dmma = peaks if peaks else D.fp64_peaks(0)
             tf = c["flops"] * (c2["particle_updates"] - c1["particle_updates"]) / (c2["loglike_ms"] * 1e-3) / 1e12
             persistent = c2["persistent_chunks"] > c1["persistent_chunks"]
             ll = {"kernel": "k_chunk_persist (whole chunk: proposals and accepts included)" if persistent else "k_xdot",
@@ -119,6 +125,24 @@ def run(name, iters=None):
     if c["flops"]:
         line["likelihood_tflops_whole_step"] = c["flops"] * updates / (ms * 1e-3) / 1e12
         line["likelihood_kernel"] = ll
+    ups = line["particle_updates_per_s"]
+    # roofline of each shape: what bounds it, achieved / peak
+    if name == "c1":
+        line["roofline"] = {"bound": "latency", "note": "24 particles x 50 observations: one fused launch per dependency level; nothing to saturate"}
+    elif name == "c3":
+        dens = ups * 100_000
+        line["roofline"] = {"bound": "fp64 pipe (transcendental)", "trial_densities_per_s": dens, "unit": "fp64 warp-instructions/s"}
+        if LBA_FP64_WARP_INST_PER_DENSITY and peaks:
+            peak_wi = max(peaks) * 1e12 / 2.0 / 32.0
+            line["roofline"].update(achieved=dens * LBA_FP64_WARP_INST_PER_DENSITY / 32.0, peak=peak_wi,
+                                    frac=dens * LBA_FP64_WARP_INST_PER_DENSITY / 32.0 / peak_wi)
+    elif name == "c4" and hbm_gbs:
+        gbs = ups * 64.0 * c["d"] / 1e9              # propose (4 reads + 1 write) + accept (1 read + 2 writes) of d doubles
+        line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                            "note": "algorithmic bytes = 64 d per particle update (SURVEY 8d) over the whole step; the likelihood (k_xdot) share is in likelihood_kernel"}
+    elif name == "c5" and ll:
+        line["roofline"] = {"bound": "tensor", "achieved": ll["tflops_event_bracketed"], "peak": ll["peak_dmma_tflops"], "unit": "TFLOP/s",
+                            "frac": ll["of_measured_dmma_peak"], "whole_step_frac": line["likelihood_tflops_whole_step"] / ll["peak_dmma_tflops"]}
     return line
 
 
