@@ -155,6 +155,8 @@ struct CConfig
     store_every::Int32
     update::Int32          # 0 mh_update!, 1 maximize!, 2 minimize!
     fitness::Int32         # 0 compute_posterior!, 1 evaluate_fun!
+    n_devices::Int32       # > 1: ONE handle over several GPUs of the box, driven from this one Julia process
+    devices::Ptr{Int32}    # [n_devices] CUDA ordinals
 end
 
 function demcmc_check(rc)
@@ -212,14 +214,21 @@ proposal_id(de) = de.generate_proposal === random_gamma ? 0 : de.generate_propos
                   throw(ArgumentError("generate_proposal must be random_gamma, fixed_gamma or variable_gamma on the B200 path"))
 
 # ---- the sampler ---------------------------------------------------------------------------------
-function sample(model::DEModel{<:GPULoglike}, de::DE, n_iter::Int; progress = false, device = 0, seed = rand(UInt64), kwargs...)
-    return _sample_gpu(model, de, n_iter; device, seed)
+# `devices = [0, 1, ..., 7]`: the groups shard over several GPUs of the box from THIS process (demcmc_config.n_devices:
+# one host thread of the library per GPU, migration over NVLink through peer-mapped mailboxes) -- what replaces the
+# ThreadsX.map over groups of p_update! (src/main.jl:135-148); no MPI, no second process.  `store_every = k` keeps
+# iterations k, 2k, ... only (the Chains then hold (n_iter - burnin) ÷ k draws).
+function sample(model::DEModel{<:GPULoglike}, de::DE, n_iter::Int; progress = false, device = 0, devices = Int32[], store_every = 1, seed = rand(UInt64), kwargs...)
+    return _sample_gpu(model, de, n_iter; device, devices, store_every, seed)
 end
-function sample(model::DEModel{<:GPULoglike}, de::DE, ::MCMCThreads, n_iter::Int; progress = false, device = 0, seed = rand(UInt64), kwargs...)
-    return _sample_gpu(model, de, n_iter; device, seed)    # every group is always updated concurrently on the device
+function sample(model::DEModel{<:GPULoglike}, de::DE, ::MCMCThreads, n_iter::Int; progress = false, device = 0, devices = Int32[], store_every = 1, seed = rand(UInt64), kwargs...)
+    return _sample_gpu(model, de, n_iter; device, devices, store_every, seed)    # every group is always updated concurrently on the device(s)
 end
 
-function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
+function _sample_gpu(model, de, n_iter; device, seed, devices = Int32[], store_every = 1, return_particles = false)
+    store_every == 1 || return_particles === false || throw(ArgumentError("optimize keeps every row"))
+    store_every == 1 || return _sample_gpu_thinned(model, de, n_iter; device, devices, store_every, seed)
+    devs = Vector{Int32}(devices)
     model.prior_loglike isa GPUPrior || de.evaluate_fitness! === evaluate_fun! ||
         throw(ArgumentError("prior_loglike must be a GPUPrior: a Julia closure would need a host round trip per particle"))
     update = de.update_particle! === mh_update! ? Int32(0) : de.update_particle! === maximize! ? Int32(1) :
@@ -272,10 +281,10 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
     init_rows = de.n_initial > 0 ?
         Float64[flatten_theta(de.samples[i, :, p])[k] for k = 1:d, p = 1:P, i = 1:(de.n_initial)] : Float64[]
     sig = ll.sigma === nothing ? Float64[] : ll.sigma
-    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids final_theta final_weight init_rows begin
+    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids final_theta final_weight init_rows devs begin
         cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, de.n_initial, de.α, de.β, de.ϵ, de.σ, de.κ,
             de.θsnooker, proposal_id(de), n_blocks, isempty(blocks) ? C_NULL : pointer(blocks), pointer(lo), pointer(hi),
-            seed, device, 0, 0, donors, 0, 1, update, fitness)
+            seed, device, 0, 0, donors, 0, 1, update, fitness, length(devs), isempty(devs) ? C_NULL : pointer(devs))
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
@@ -319,6 +328,46 @@ function _sample_gpu(model, de, n_iter; device, seed, return_particles = false)
     end
     groups = [particles[((g - 1) * de.Np + 1):(g * de.Np)] for g = 1:(de.n_groups)]
     return bundle_samples(model, de, groups, n_iter)
+end
+
+# Thinned run (store_every = k > 1): de.samples would have holes, so the Chains are built from the device-side
+# bundle_samples (demcmc_get_chains) of the kept rows instead of from de.samples.
+function _sample_gpu_thinned(model, de, n_iter; device, devices, store_every, seed)
+    groups = gpu_sample_init(model, de, 0)               # initial draws only; no n_iter-long host arrays
+    particles = vcat(groups...)
+    Θ1 = particles[1].Θ
+    d = sum(n_elems, Θ1); P = length(particles)
+    theta0 = reduce(hcat, (flatten_theta(p.Θ) for p in particles))
+    lo, hi = expand_bounds(de.bounds, Θ1)
+    priors = prior_table(model, Θ1)
+    ll = model.loglike
+    ll.kind in (:gaussian, :mvnormal, :hier_normal) || throw(ArgumentError("thinned runs are wired for the matrix / vector data kinds in this wrapper"))
+    de.n_initial == 0 || throw(ArgumentError("store_every > 1 with n_initial > 0: use the full-history path"))
+    de.blocking_on(de) && throw(ArgumentError("store_every > 1 with blocks: use the full-history path"))
+    x = ll.data.x
+    n_dim, n_per, n_obs = ll.kind == :mvnormal ? (size(x, 1), 0, size(x, 2)) : ll.kind == :hier_normal ? (size(x, 2), size(x, 1), length(x)) : (0, 0, length(x))
+    devs = Vector{Int32}(devices)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    local v
+    GC.@preserve theta0 lo hi priors x devs begin
+        cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, 0, de.α, de.β, de.ϵ, de.σ, de.κ, de.θsnooker, proposal_id(de), 0, C_NULL,
+            pointer(lo), pointer(hi), seed, device, 0, 0, 0, 0, store_every, 0, 0, length(devs), isempty(devs) ? C_NULL : pointer(devs))
+        demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        try
+            m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), C_NULL, C_NULL, ll.lba_floor, pointer(priors), 0, 0, C_NULL)
+            demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
+            demcmc_check(ccall((:demcmc_set_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), h[], theta0, C_NULL))
+            demcmc_check(ccall((:demcmc_run, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64), h[], n_iter))
+            offset = de.discard_burnin ? de.burnin ÷ store_every : 0
+            Ns = n_iter ÷ store_every - offset
+            v = zeros(Float64, Ns, d + 2, P)
+            GC.@preserve v demcmc_check(ccall((:demcmc_get_chains, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), h[], offset, Ns, v))
+        finally
+            ccall((:demcmc_destroy, LIBDEMCMC), Cint, (Ptr{Cvoid},), h[])
+        end
+    end
+    de.iter = n_iter
+    return Chains(v, get_names(model, particles[1]), (parameters = [model.names...], internals = ["acceptance", "lp"]))
 end
 
 # Faster exit when only the Chains are wanted: bundle_samples (src/main.jl:222-250) runs on the device

@@ -561,3 +561,28 @@ def test_multi_device_handle_replays_the_oracle_and_checks_its_arguments(emu):
     for bad in (dict(devices=[0, 0]), dict(devices=[0, 1, 2]), dict(devices=[0, 1], resample=True, n_initial=4)):
         with pytest.raises(D._ffi.DemcmcError):
             case.handle(G, Np, **bad)
+
+
+def test_julia_tape_format_round_trip(emu, tmp_path):
+    """the on-disk tape julia/record_tape.jl writes (never produced here: no Julia), written from an oracle run by
+    tests/tape_io.py and replayed through the library after a round trip through the files"""
+    import tape_io
+    rng = np.random.default_rng(31)
+    case = make_case("gaussian", rng)
+    G, Np, n_iter = 4, 6, 12
+    th0 = case.theta0(rng, G * Np)
+    kw = dict(burnin=5, theta_snooker=0.2, kappa=0.8)
+    r = O.run(case.oracle_config(G, Np, seed=5, **kw), case.oracle_model(), th0, n_iter)
+    arrays = dict(r["tape"])
+    arrays.update(theta0=th0, accepted=r["trace"]["accepted"] if "accepted" in r["trace"] else None)
+    tape_io.save_tape(str(tmp_path), dict(G=G, Np=Np, d=case.d, B=1, n_iter=n_iter, n_initial=0, burnin=5, alpha=0.1, beta=0.1, eps=0.001,
+                                          sigma=0.05, kappa=0.8, theta_snooker=0.2), arrays)
+    meta, tape, extra = tape_io.load_tape(str(tmp_path))
+    assert meta["G"] == G and meta["kappa"] == 0.8
+    for k in tape_io.TAPE_FIELDS:
+        if r["tape"].get(k) is not None and tape.get(k) is not None:
+            assert np.array_equal(np.asarray(r["tape"][k]).reshape(-1), np.asarray(tape[k]).reshape(-1)), k
+    with case.handle(G, Np, seed=5, **kw) as h:
+        h.set_state(extra["theta0"])
+        h.replay(tape, n_iter)
+        assert np.array_equal(h.accept(), r["accept"])
