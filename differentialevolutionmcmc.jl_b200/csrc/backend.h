@@ -28,7 +28,7 @@ int sync();
 // lanes: independent kernel chains on separate streams (lane 0 = the engine stream).  set_lane
 // selects where the launchers below enqueue; lane_fork makes lanes 1..n-1 wait for everything
 // enqueued on lane 0 so far, lane_join makes lane 0 wait for the other lanes.
-constexpr int MAX_LANES = 2;
+constexpr int MAX_LANES = 4;          // the persistent chunk kernel interleaves the levels of up to 4 lanes; kernel-chain lanes use 2
 void set_lane(int lane);
 int lane_fork(int n_lanes);
 int lane_join(int n_lanes);
@@ -73,8 +73,9 @@ int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 // level dep[l] (< l, or -1); the scalar warps run their accepts `lag` levels behind their proposals.
 // Returns 1 when the chunk does not fit that kernel (launch it level by level instead), -1 on error.
 int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m);   // lanes that kernel wants for this job; 0 = use the level-by-level path
+// n_buf: staging copies of the means (= lanes): level l stages into copy l % n_buf once level l - n_buf has been accepted
 int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
-                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc);
+                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc, int n_buf = 2);
 // migration (migration.jl:11-116): picks, then gather to / scatter from a staging buffer laid out
 // [position][d+3] = {theta..., weight, id, accept flag}
 int launch_mig_pick(const ConfigDev &cfg, const MigArgs &a, const double *w, int32_t *picks /*[MAX_MIG]*/);
@@ -110,6 +111,16 @@ int launch_chains(const double *rows_theta, const double *rows_w, const uint8_t 
 // phase 1 on every shard, then phase 2 on every shard, all on one pos_scratch[P_ids] and one output.)
 // pooled per-parameter mean and sum of squared deviations of n vectors x[n][d] (fixed reduction order)
 int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *m2 /* device [d] each */);
+// Convergence diagnostics on the device (no download of the draws): every particle id is a chain over
+// history rows [row0, row0 + n_rows); each chain is split in two halves of nh = n_rows / 2 draws (the middle one is
+// dropped when n_rows is odd).  launch_diag_pos fills pos[r][id] = pos_base + slot for the ids a shard holds at row r
+// (ids migrate between shards: every shard writes into the same map); launch_diag_aggregates then gathers every chain
+// through that map from the shards' rows.  Output agg[d][3 + n_lag] (device), per flattened parameter k, summed over
+// the 2 P_ids split chains in a fixed order: [0] sum of the chain variances (ddof 1), [1] sum of the chain means,
+// [2] sum of their squares, [3 + t] sum of the biased autocovariances at lag t < n_lag.  The host turns them into
+// split-R-hat and ESS (engine.cpp: diag_finish).
+int launch_diag_pos(const int32_t *rows_id, int64_t row0, int64_t n_rows, int32_t P_local, int32_t id_base, int32_t P_ids, int32_t pos_base, int32_t *pos);
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t n_lag, double *agg);
 // particle algebra known-answer ops (single warp each)
 int launch_op_project(const double *p1, const double *p2, int d, double *out);
 int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,

@@ -143,6 +143,9 @@ struct MigArgs {
 // scope and publishes the event's tag in the flag; the receiver's scatter kernel acquires the flag.  No host call and no
 // collective sits between a rank's chunks, and only the ranks of the cycle ever wait for each other.
 struct Mbox { double *rows; unsigned long long *flags; int32_t depth, max_rows, row_len; };
+// history rows of every shard of a job (one entry for a single-device handle): global position q lives at slot q % P_local
+// of shard q / P_local
+struct DiagShards { const double *theta[MAX_RANKS]; int32_t n, P_local; };
 struct PeerTable { double *rows[MAX_RANKS]; unsigned long long *flags[MAX_RANKS]; };
 
 } // namespace de

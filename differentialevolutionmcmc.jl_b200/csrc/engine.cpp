@@ -484,7 +484,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->n0 = cfg->n_initial;
     h->k_store = std::max(1, cfg->store_every);
     h->n_scratch = h->k_store > 1 ? MAX_CHUNK + 2 : 3;
-    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), be::MAX_LANES));   // A/B measurements
+    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), 2));   // A/B measurements
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
     h->P = h->G_local * cfg->Np;
@@ -957,7 +957,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
         std::vector<uint8_t> mut((size_t)n_sw * G, 0);
         for (int ln = 0; ln < n_lanes; ++ln) {
-            const int g0 = ln == 0 ? 0 : (G + 1) / 2, g1 = (n_lanes == 1 || ln == 1) ? G : (G + 1) / 2;
+            const int g0 = (ln * G + n_lanes - 1) / n_lanes, g1 = ((ln + 1) * G + n_lanes - 1) / n_lanes;   // contiguous sets of groups
             PlanInput pin;
             pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
             pin.pos_offset = g0 * Np; pin.P_stride = blocked ? P : P * B;   // consecutive sweeps of an unblocked chunk are consecutive iterations
@@ -994,7 +994,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // levels of the lanes alternate; a level's proposals wait for the previous level of its lane
         if (persist_lanes) {
             std::vector<int32_t> off, cnt, dep;
-            int last[be::MAX_LANES] = { -1, -1 };
+            int last[be::MAX_LANES];
+            for (int &v : last) v = -1;
             for (int l = 0; l < max_levels; ++l)
                 for (int ln = 0; ln < n_lanes; ++ln) {
                     const ChunkPlan &pl = plans[ln];
@@ -1007,7 +1008,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const bool tl = h->time_loglik && tev_ll0 + 2 * tev_ll + 1 < h->tev.size();
             if (tl) BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll]));
             const int rc = off.empty() ? 1 : be::launch_chunk_persist(h->dcfg, h->dmodel, u.d_order, u.d_ctx, off.data(), cnt.data(), dep.data(),
-                                                                      (int)off.size(), n_lanes > 1 ? 1 : 0, h->ll_acc);
+                                                                      (int)off.size(), n_lanes > 1 ? 1 : 0, h->ll_acc, std::max(2, n_lanes));
             if (rc < 0) return fail(DEMCMC_ECUDA, "chunk launch: %s", be::last_error());
             if (rc == 0) {
                 if (tl) { BE(be::event_record(h->tev[tev_ll0 + 2 * tev_ll + 1])); ++tev_ll; }
@@ -1245,6 +1246,69 @@ int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *
     return rc;
 }
 
+// split-R-hat and ESS from the aggregates of launch_diag_aggregates, summed over the shards (m = split chains in all)
+static void diag_finish(const double *agg, int d, int n_lag, int64_t nh, int64_t m, double *rhat, double *ess)
+{
+    const double n = (double)nh, M = (double)m;
+    for (int k = 0; k < d; ++k) {
+        const double *a = agg + (size_t)k * (3 + n_lag);
+        const double W = a[0] / M;                                        // mean within-chain variance
+        const double var_means = M > 1 ? (a[2] - a[1] * a[1] / M) / (M - 1.0) : 0.0;
+        const double var_plus = W * (n - 1.0) / n + var_means;           // B / n = var of the chain means
+        if (rhat) rhat[k] = W > 0.0 ? sqrt(var_plus / W) : NAN;
+        if (!ess) continue;
+        if (!(var_plus > 0.0)) { ess[k] = NAN; continue; }
+        auto rho = [&](int t) { return t == 0 ? 1.0 : 1.0 - (W - a[3 + t] / M) / var_plus; };
+        double tau = -1.0, prev = INFINITY;
+        for (int t = 0; t + 1 < n_lag; t += 2) {                          // Geyer's initial positive, monotone sequence
+            double pair = rho(t) + rho(t + 1);
+            if (pair < 0.0) break;
+            pair = std::min(pair, prev);
+            prev = pair;
+            tau += 2.0 * pair;
+        }
+        tau = std::max(tau, 1.0 / log10(std::max(n * M, 10.0)));
+        ess[k] = n * M / tau;
+    }
+}
+
+int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, double *rhat, double *ess)
+{
+    if (!h || (!rhat && !ess)) return fail(DEMCMC_EINVAL, "null argument");
+    demcmc_handle *h0 = h->multi ? h->kids[0] : h;
+    if (row0 < 0 || n_rows < 4 || row0 + n_rows > stored_rows(h0)) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows (at least 4 rows)", (long long)row0, (long long)(row0 + n_rows), (long long)stored_rows(h0));
+    const int64_t nh = n_rows / 2;
+    if (nh > 4096) return fail(DEMCMC_EUNSUPPORTED, "diagnostics over more than 8192 stored rows per call: thin the run or pass a sub-range");
+    const int d = h->d, n_lag = (int)nh;
+    const size_t na = (size_t)d * (3 + n_lag);
+    std::vector<demcmc_handle *> leaves = h->multi ? h->kids : std::vector<demcmc_handle *>{ h };
+    const int32_t Pt = (int32_t)h->P, id_base = h->multi ? 0 : h->cfg.group_begin * h->cfg.Np;
+    // ids migrate between the shards of a job: every shard marks, in ONE map on the first device, where the ids it holds
+    // sit at every row; the first device then gathers every chain through the map (peer access) and reduces
+    BE(be::set_device(h0->cfg.device));
+    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * (size_t)n_rows * Pt);
+    double *agg = (double *)be::dmalloc(sizeof(double) * na);
+    std::vector<double> total(na);
+    int rc = (!pos || !agg) ? fail(DEMCMC_ENOMEM, "diagnostics staging") : 0;
+    DiagShards sh;
+    memset(&sh, 0, sizeof sh);
+    sh.n = (int32_t)leaves.size(); sh.P_local = (int32_t)h0->P;
+    for (size_t i = 0; i < leaves.size() && !rc; ++i) {
+        demcmc_handle *k = leaves[i];
+        sh.theta[i] = k->hist_theta;
+        if (be::set_device(k->cfg.device) ||
+            be::launch_diag_pos(k->hist_id, row0, n_rows, (int32_t)k->P, id_base, Pt, h->multi ? k->cfg.group_begin * k->cfg.Np : 0, pos) || be::sync())
+            rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error());
+    }
+    if (!rc && (be::set_device(h0->cfg.device) || be::launch_diag_aggregates(sh, pos, row0, n_rows, Pt, d, n_lag, agg) ||
+                be::d2h(total.data(), agg, sizeof(double) * na))) rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error());
+    be::set_device(h0->cfg.device);
+    be::dfree(pos); be::dfree(agg);
+    if (rc) return rc;
+    diag_finish(total.data(), d, n_lag, nh, 2 * (int64_t)Pt, rhat, ess);
+    return 0;
+}
+
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)
 {
     if (!h || !out) return fail(DEMCMC_EINVAL, "null argument");
@@ -1419,7 +1483,7 @@ int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
 {
     if (!h || n_lanes < 1) return fail(DEMCMC_EINVAL, "bad argument");
     if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_lanes(k, n_lanes); }, false);
-    h->n_lanes = std::min<int32_t>(n_lanes, be::MAX_LANES);
+    h->n_lanes = std::min<int32_t>(n_lanes, 2);
     return 0;
 }
 

@@ -1147,7 +1147,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
 // wait for proposals of that level, those for accepts of earlier levels), and the launch is one CTA
 // per SM, so all CTAs are resident.  A wait that lasts 20 s traps instead of hanging the device.
 // ------------------------------------------------------------------------------------------------
-constexpr int PK_MAX_LEVELS = 192;
+constexpr int PK_MAX_LEVELS = 448;             // levels of all lanes of one chunk (kernel parameter block: 48 bytes each)
 constexpr int PK_MAX_TILES = 8192;
 constexpr int PK_WARPS = 16;                    // per CTA: 4 per SM sub-partition, 128 registers each at launch
 constexpr int PK_THREADS = PK_WARPS * 32;
@@ -1156,11 +1156,11 @@ constexpr int PK_SCALAR_CTAS = 6;               // CTAs (SMs) given to the scala
 
 struct PLevel { int32_t order_off, n, n_items, dep, tile_base, pad; XdGrid g; };
 struct PChunk {
-    int32_t n_levels, lag, n_scalar_ctas;
+    int32_t n_levels, lag, n_scalar_ctas, n_buf;      // n_buf: staging copies of the means (level l uses copy pl.pad = l % n_buf)
     const int32_t *order;
     const SweepCtx *ctxs;
     int32_t *acc_done, *prop_done, *xdot_done;       // zeroed before the launch
-    double *bfrag[2], *magic[2];
+    double *bfrag[MAX_LANES], *magic[MAX_LANES];
     long long *ll_acc;
     unsigned long long *tl;                          // debug timeline [level][PT_WORDS] or nullptr
     PLevel lv[PK_MAX_LEVELS];
@@ -1340,8 +1340,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
                 int32_t *ctr = ck.xdot_done + pl.tile_base + it.tile;
                 if (it.T1 <= it.T0) { publish(ctr); continue; }  // (k_xdot's grids never deal an empty range)
                 const int32_t *flag = ck.prop_done + pl.tile_base + it.tile;
-                const double *bsrc = ck.bfrag[L & 1] + (((size_t)it.oct0 * m.n_ksplit + it.ks) * nj) * 32;
-                const double *msrc = ck.magic[L & 1] + (size_t)it.oct0 * SSD_OCT;
+                const double *bsrc = ck.bfrag[pl.pad] + (((size_t)it.oct0 * m.n_ksplit + it.ks) * nj) * 32;
+                const double *msrc = ck.magic[pl.pad] + (size_t)it.oct0 * SSD_OCT;
                 const size_t bstride = (size_t)m.n_ksplit * nj * 32;
                 bool filled = false;
                 const unsigned long long t0 = gtime();
@@ -1446,18 +1446,18 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
         const PLevel &pl = ck.lv[L];
         // the accepts this level's proposals (or its staging buffer) wait for: inside the first
         // proposal's dependency wait when this warp has one, else here
-        const int must = max(pl.dep, L - 2);
+        const int must = max(pl.dep, L - ck.n_buf);
         auto pending = [&]() { while (next_acc <= must) accept_level(next_acc++); };
         for (int wi = sw; wi < pl.n; wi += NS) {
             const uint32_t e = (uint32_t)ck.order[pl.order_off + wi];
             const SweepCtx ctx = ck.ctxs[e >> LV_SLOT_SHIFT];
             const int p = (int)(e & LV_POS_MASK);
-            double *bfrag = ck.bfrag[L & 1], *magic = ck.magic[L & 1];
+            double *bfrag = ck.bfrag[pl.pad], *magic = ck.magic[pl.pad];
             unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
             const unsigned long long tp0 = (TL && tl) ? gtime() : 0ull;
             if (tl && lane == 0) atomicMax(tl + PT_P0, ~tp0);
             const FlagWait fw = { pl.dep >= 0 ? ck.acc_done + pl.dep : nullptr, pl.dep >= 0 ? ck.lv[pl.dep].n : 0,
-                                  L >= 2 ? ck.acc_done + (L - 2) : nullptr, L >= 2 ? ck.lv[L - 2].n : 0, tl, PT_PW, -1, 0ull };
+                                  L >= ck.n_buf ? ck.acc_done + (L - ck.n_buf) : nullptr, L >= ck.n_buf ? ck.lv[L - ck.n_buf].n : 0, tl, PT_PW, -1, 0ull };
             const ProposeLanes<decltype(pending)> co(pending, fw);
             StageSink sink = { m, bfrag, wi, m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
             propose_particle(co, cfg, m, ctx, p, sink);
@@ -1538,7 +1538,12 @@ int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m)
     if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER)) return 0;
     if (cfg.G_local < 2) return 0;
     if ((int64_t)cfg.G_local * cfg.Np / 8 > (int64_t)4 * PK_WARPS * persist_scalar_ctas()) return 0;   // ~ a level per lane
-    return 2;
+    // Two lanes.  More (DEMCMC_PK_LANES = 3, 4: one lane per group) give a lane's accept -> propose chain more DMMA time
+    // to hide in, but halve the levels: measured on configs[1] 2 / 3 / 4 lanes = 2.76 / 2.65 / 2.52 M updates/s -- smaller
+    // particle tiles (fewer octets per streamed A fragment) and twice the items cost more than the waits they remove.
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("DEMCMC_PK_LANES"); want = e ? std::max(2, std::min(atoi(e), (int)MAX_LANES)) : 2; }
+    return std::min(cfg.G_local, want);
 }
 
 // Runs the levels [level_off[l], level_off[l] + level_n[l]) of a chunk (entries in d_order) in one persistent
@@ -1546,8 +1551,9 @@ int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m)
 // many levels the accepts trail the proposals in the scalar warps' program (0 or 1).
 // Returns 1 when the chunk does not fit this kernel (the caller launches the levels one by one).
 int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx,
-                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc)
+                         const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc, int n_buf)
 {
+    n_buf = std::max(2, std::min(n_buf, (int)MAX_LANES));
     if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
     static thread_local PChunk ck;                           // 9 KB: not on the stack of every call
     const int n_scalar = persist_scalar_ctas();
@@ -1555,7 +1561,7 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
     int tiles = 0, n_max = 0;
     for (int l = 0; l < n_levels; ++l) {
         PLevel &pl = ck.lv[l];
-        pl.order_off = level_off[l]; pl.n = level_n[l]; pl.dep = dep[l]; pl.tile_base = tiles; pl.pad = 0;
+        pl.order_off = level_off[l]; pl.n = level_n[l]; pl.dep = dep[l]; pl.tile_base = tiles; pl.pad = l % n_buf;
         if (pl.n <= 0 || pl.dep >= l) return 1;
         pl.g = xdot_grid(m, pl.n, slots);
         pl.n_items = pl.g.n_hi * pl.g.c_hi + pl.g.n_lo * pl.g.c_lo;
@@ -1568,14 +1574,13 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
     if (n_max > 8 * PK_WARPS * n_scalar) return 1;
     static int32_t *ctr[64] = { nullptr };
     if (!ctr[g_dev]) CU(cudaMalloc(&ctr[g_dev], sizeof(int32_t) * (PK_MAX_LEVELS + 2 * PK_MAX_TILES)));
-    XdStage *xs[2];
+    XdStage *xs[MAX_LANES];
     const int keep = g_lane;
-    for (int b = 0; b < 2; ++b) { g_lane = b; xs[b] = xd_stage(m, std::max(n_max, cfg.G_local * cfg.Np)); }
+    for (int b = 0; b < n_buf; ++b) { g_lane = b; xs[b] = xd_stage(m, std::max(n_max, cfg.G_local * cfg.Np)); if (!xs[b]) { g_lane = keep; return -1; } }
     g_lane = keep;
-    if (!xs[0] || !xs[1]) return -1;
-    ck.n_levels = n_levels; ck.lag = lag; ck.n_scalar_ctas = n_scalar; ck.order = d_order; ck.ctxs = d_ctx;
+    ck.n_levels = n_levels; ck.lag = lag; ck.n_scalar_ctas = n_scalar; ck.n_buf = n_buf; ck.order = d_order; ck.ctxs = d_ctx;
     ck.acc_done = ctr[g_dev]; ck.prop_done = ctr[g_dev] + PK_MAX_LEVELS; ck.xdot_done = ck.prop_done + PK_MAX_TILES;
-    for (int b = 0; b < 2; ++b) { ck.bfrag[b] = xs[b]->bfrag; ck.magic[b] = xs[b]->magic; }
+    for (int b = 0; b < n_buf; ++b) { ck.bfrag[b] = xs[b]->bfrag; ck.magic[b] = xs[b]->magic; }
     ck.ll_acc = ll_acc;
     if (g_ptl_cap < 0) {
         const char *e = getenv("DEMCMC_PK_TIMELINE");
@@ -2113,6 +2118,102 @@ int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *
     LAUNCHED("k_moments_partial");
     k_moments_merge<<<(d + MOM_THREADS - 1) / MOM_THREADS, MOM_THREADS, 0, stream()>>>(part, part + (size_t)MOM_BLOCKS * d, n, d, mean, m2);
     LAUNCHED("k_moments_merge");
+    dfree(part);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// convergence diagnostics of the stored history, on the device (backend.h: launch_diag_aggregates)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag_pos(const int32_t *rid, int64_t row0, int64_t n_rows, int P, int id_base, int P_ids, int pos_base, int32_t *pos)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows * P) return;
+    const int64_t r = i / P;
+    const int id = rid[(row0 + r) * P + (i - r * P)] - id_base;
+    if (id >= 0 && id < P_ids) pos[r * P_ids + id] = pos_base + (int32_t)(i - r * P);
+}
+// one block per (parameter k, group of chains): each split chain is gathered into shared memory (its draws sit at a
+// different position of every stored row: ids migrate), then thread t accumulates the lags t, t + 256, ...; the
+// block's chains are summed in order, the groups by k_diag_merge in order: deterministic
+constexpr int DG_THREADS = 256, DG_GROUPS = 32, DG_MAX_NH = 4096;
+__global__ void __launch_bounds__(DG_THREADS) k_diag_partial(DiagShards sh, const int32_t *pos, int64_t row0, int64_t n_rows, int P, int d,
+                                                             int n_lag, double *part /* [d][DG_GROUPS][3 + n_lag] */)
+{
+    extern __shared__ double xs[];                                // nh draws of one split chain
+    __shared__ double red[DG_THREADS / 32 + 1];
+    const int k = blockIdx.x, grp = blockIdx.y, tid = threadIdx.x;
+    const int nh = (int)(n_rows / 2);
+    const int n_chain = 2 * P;
+    const int c0 = (int)((int64_t)grp * n_chain / DG_GROUPS), c1 = (int)((int64_t)(grp + 1) * n_chain / DG_GROUPS);
+    double *out = part + ((size_t)k * DG_GROUPS + grp) * (3 + n_lag);
+    double s_cv = 0.0, s_m = 0.0, s_m2 = 0.0;
+    constexpr int LPT = (DG_MAX_NH + DG_THREADS - 1) / DG_THREADS;  // lags per thread
+    double acov[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) acov[j] = 0.0;
+    for (int c = c0; c < c1; ++c) {
+        const int id = c >> 1;
+        const int64_t r0 = (c & 1) ? n_rows - nh : 0;             // second half: the LAST nh draws
+        double s = 0.0;
+        for (int i = tid; i < nh; i += DG_THREADS) {
+            const int64_t r = r0 + i;
+            const int q = pos[r * P + id], shard = q / sh.P_local;
+            const double v = sh.theta[shard][((row0 + r) * sh.P_local + (q - shard * sh.P_local)) * d + k];
+            xs[i] = v; s += v;
+        }
+        s = warp_sum(s);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        double mean = 0.0;
+        for (int w = 0; w < DG_THREADS / 32; ++w) mean += red[w];
+        mean /= (double)nh;
+        __syncthreads();
+        for (int i = tid; i < nh; i += DG_THREADS) xs[i] -= mean;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            const int t = tid + j * DG_THREADS;
+            if (t < n_lag) {
+                double a = 0.0;
+                for (int i = 0; i + t < nh; ++i) a += xs[i] * xs[i + t];
+                a /= (double)nh;
+                acov[j] += a;
+                if (t == 0) { s_cv += a * (double)nh / (double)(nh - 1); s_m += mean; s_m2 += mean * mean; }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) { const int t = tid + j * DG_THREADS; if (t < n_lag) out[3 + t] = acov[j]; }
+    if (tid == 0) { out[0] = s_cv; out[1] = s_m; out[2] = s_m2; }
+}
+__global__ void __launch_bounds__(256) k_diag_merge(const double *part, int d, int n_lag, double *agg)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)d * (3 + n_lag)) return;
+    const int k = (int)(i / (3 + n_lag)), j = (int)(i - (int64_t)k * (3 + n_lag));
+    double s = 0.0;
+    for (int g = 0; g < DG_GROUPS; ++g) s += part[((size_t)k * DG_GROUPS + g) * (3 + n_lag) + j];
+    agg[i] = s;
+}
+int launch_diag_pos(const int32_t *rows_id, int64_t row0, int64_t n_rows, int32_t P_local, int32_t id_base, int32_t P_ids, int32_t pos_base, int32_t *pos)
+{
+    k_diag_pos<<<(unsigned)((n_rows * P_local + 255) / 256), 256, 0, stream()>>>(rows_id, row0, n_rows, P_local, id_base, P_ids, pos_base, pos);
+    LAUNCHED("k_diag_pos");
+    return 0;
+}
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t n_lag, double *agg)
+{
+    const int64_t nh = n_rows / 2;
+    if (nh < 2 || nh > DG_MAX_NH || n_lag > nh || n_lag < 1) { g_be_err = "diagnostics need 4 <= n_rows <= 8192 stored rows per call"; return -1; }
+    double *part = (double *)dmalloc(sizeof(double) * (size_t)d * DG_GROUPS * (3 + n_lag));
+    if (!part) return -1;
+    k_diag_partial<<<dim3(d, DG_GROUPS), DG_THREADS, sizeof(double) * nh, stream()>>>(sh, pos, row0, n_rows, P_ids, d, n_lag, part);
+    LAUNCHED("k_diag_partial");
+    k_diag_merge<<<(unsigned)(((int64_t)d * (3 + n_lag) + 255) / 256), 256, 0, stream()>>>(part, d, n_lag, agg);
+    LAUNCHED("k_diag_merge");
     dfree(part);
     return 0;
 }

@@ -219,6 +219,14 @@ class Handle:
         check(_ffi.lib().demcmc_get_moments(self._h, int(row0), int(n), C.byref(cnt), ptr(mean, _dp), ptr(m2, _dp)))
         return cnt.value, mean, m2 / max(cnt.value - 1, 1)
 
+    def diagnostics(self, row0=0, n_rows=None):
+        """(split-R-hat[d], ESS[d]) of history rows [row0, row0+n_rows) computed on the device, every particle id one
+        chain (demcmc_get_diagnostics): no download of the draws."""
+        n = self.n_rows - row0 if n_rows is None else n_rows
+        rhat, ess = np.zeros(self.d), np.zeros(self.d)
+        check(_ffi.lib().demcmc_get_diagnostics(self._h, int(row0), int(n), ptr(rhat, _dp), ptr(ess, _dp)))
+        return rhat, ess
+
     def history_by_slot(self, row0=0, n_rows=None):
         n = self.stored_iterations - row0 if n_rows is None else n_rows
         th = np.zeros((n, self.P, self.d))

@@ -220,6 +220,14 @@ int demcmc_set_weights(demcmc_handle *h, const double *w);
  * n_rows * P_local draws, i.e. what MCMCChains' mean / std of the pooled chains reduce to
  * (var = m2 / (count - 1)).  Shards of a multi-GPU job merge (count, mean, m2) with Chan's update. */
 int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *count, double *mean, double *m2);
+/* Convergence diagnostics computed on the device from the stored rows [row0, row0+n_rows) (no download of the draws):
+ * per flattened parameter, split-R-hat and effective sample size with every particle id as one chain, each chain split
+ * in two halves (Gelman et al., BDA3 11.4-11.5; Stan's estimators: between / within variances of the split chains,
+ * autocorrelations from the chain-averaged autocovariances, Geyer's initial monotone sequence) -- what the reference's
+ * tests read off MCMCChains.describe (test/gaussian_tests.jl:42-59), minus the rank normalisation of the newer
+ * "bulk" variants (that one needs a global sort of all draws; demcmc_b200.diagnostics computes it on the host).
+ * 4 <= n_rows <= 8192 per call.  Works on a multi-device handle (the shards' aggregates are merged). */
+int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, double *rhat, double *ess);
 /* the same history as the device keeps it, rows [row0, row0+n_rows) of the iterations run, by
  * POSITION: theta[n_rows][P_local][d], w[n_rows][P_local] (= lp), ids[n_rows][P_local] (particle id
  * sitting at each position after that iteration), acc[n_rows][P_local]; any pointer may be NULL.

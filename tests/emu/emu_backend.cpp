@@ -230,10 +230,48 @@ int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *
     return 0;
 }
 
+int launch_diag_pos(const int32_t *rid, int64_t row0, int64_t n_rows, int32_t P, int32_t id_base, int32_t P_ids, int32_t pos_base, int32_t *pos)
+{
+    ++g_launches;
+    for (int64_t r = 0; r < n_rows; ++r)
+        for (int s = 0; s < P; ++s) { const int id = rid[(row0 + r) * P + s] - id_base; if (id >= 0 && id < P_ids) pos[(size_t)r * P_ids + id] = pos_base + s; }
+    return 0;
+}
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t n_lag, double *agg)
+{
+    ++g_launches;
+    const int64_t nh = n_rows / 2;
+    std::vector<double> x(nh);
+    for (int k = 0; k < d; ++k) {
+        double *a = agg + (size_t)k * (3 + n_lag);
+        for (int j = 0; j < 3 + n_lag; ++j) a[j] = 0.0;
+        for (int c = 0; c < 2 * P; ++c) {
+            const int id = c >> 1;
+            const int64_t r0 = (c & 1) ? n_rows - nh : 0;
+            double mean = 0.0;
+            for (int64_t i = 0; i < nh; ++i) {
+                const int q = pos[(size_t)(r0 + i) * P + id], shard = q / sh.P_local;
+                x[i] = sh.theta[shard][((row0 + r0 + i) * sh.P_local + (q - shard * sh.P_local)) * d + k];
+                mean += x[i];
+            }
+            mean /= (double)nh;
+            for (int64_t i = 0; i < nh; ++i) x[i] -= mean;
+            for (int t = 0; t < n_lag; ++t) {
+                double s = 0.0;
+                for (int64_t i = 0; i + t < nh; ++i) s += x[i] * x[i + t];
+                s /= (double)nh;
+                a[3 + t] += s;
+                if (t == 0) { a[0] += s * (double)nh / (double)(nh - 1); a[1] += mean; a[2] += mean * mean; }
+            }
+        }
+    }
+    return 0;
+}
+
 int launch_level_fused(const ConfigDev &, const ModelDev &, const Level &) { return 1; }
 int chunk_persist_lanes(const ConfigDev &, const ModelDev &) { return 0; }
 int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
-                         const int32_t *, int, int, long long *) { return 1; }
+                         const int32_t *, int, int, long long *, int) { return 1; }
 
 int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {

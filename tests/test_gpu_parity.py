@@ -617,3 +617,12 @@ def test_multi_device_sample_api_at_configs1_shape():
         de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=Np, burnin=10, θsnooker=0.1, α=0.3, seed=5)
         outs.append(D.sample(model, de, n_iter, devices=devices).value)
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_device_diagnostics_match_the_host_estimators():
+    E._check_device_diagnostics()
+    E._check_device_diagnostics(n_iter=91)
+    E._check_device_diagnostics(store_every=2, n_iter=120)
+    E._check_device_diagnostics(G=4, Np=64, n_iter=400)
+    if _n_gpus() >= 2:
+        E._check_device_diagnostics(devices=[0, 1])

@@ -586,3 +586,29 @@ def test_julia_tape_format_round_trip(emu, tmp_path):
         h.set_state(extra["theta0"])
         h.replay(tape, n_iter)
         assert np.array_equal(h.accept(), r["accept"])
+
+
+def _check_device_diagnostics(devices=None, G=4, Np=6, n_iter=90, store_every=1):
+    """demcmc_get_diagnostics against the host estimators (diagnostics.py without the rank normalisation)"""
+    from demcmc_b200 import diagnostics as Dg
+    rng = np.random.default_rng(12)
+    case = make_case("gaussian", rng)
+    th0 = case.theta0(rng, G * Np)
+    with case.handle(G, Np, seed=4, burnin=0, alpha=0.4, devices=devices, store_every=store_every) as h:
+        h.set_state(th0)
+        h.run(n_iter)
+        row0 = 7
+        n = h.n_rows - row0
+        rhat, ess = h.diagnostics(row0, n)
+        s = h.samples()[:, :, row0:]                       # [P][d][n]: chain = particle id
+    for k in range(case.d):
+        x = Dg._split(s[:, k, :].T)                        # (draws, chains) -> split halves
+        assert abs(rhat[k] - Dg._rhat(x)) < 1e-9 * max(1.0, abs(rhat[k])), (k, rhat[k], Dg._rhat(x))
+        assert abs(ess[k] - Dg._ess(x)) < 1e-6 * ess[k], (k, ess[k], Dg._ess(x))
+
+
+def test_device_diagnostics_match_the_host_estimators(emu):
+    _check_device_diagnostics()
+    _check_device_diagnostics(n_iter=91)                   # odd number of rows: the middle draw is dropped
+    _check_device_diagnostics(devices=[0, 1])              # shards merged
+    _check_device_diagnostics(store_every=2, n_iter=120)
