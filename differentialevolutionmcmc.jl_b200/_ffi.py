@@ -34,7 +34,7 @@ class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("d", C.c_int32), ("n_obs", C.c_int64), ("n_dim", C.c_int32),
                 ("n_per", C.c_int32), ("x", C.c_void_p), ("choice", C.c_void_p), ("sigma", _dp),
                 ("lba_floor", C.c_double), ("prior", C.POINTER(Prior)), ("data_on_device", C.c_int32),
-                ("reserved", C.c_int32), ("center", _dp)]
+                ("reserved", C.c_int32), ("cov", _dp), ("center", _dp)]
 
 
 class Config(C.Structure):

@@ -91,10 +91,12 @@ class GPULoglike:
     GPULoglike("lnr", choice=c, rt=t)            sum(logpdf(LNR(;ν,τ), data)), σ = 1 unless sigma=...
     GPULoglike("lba", choice=c, rt=t)            sum(logpdf.(LBA(;ν,A,k,τ), c, t))
     GPULoglike("hier_normal", Y)                 Y is n_subj × n_per (Examples/Hierarchical_Example.jl)
+    GPULoglike("mvnormal_full", X, cov=Σ)        sum(logpdf(MvNormal(μ, σ²Σ), X')) with a known covariance Σ
+    (Examples/Guassian_Example_Vector.jl is the "gaussian" kernel: its loglike(data, θ...) destructures μ, σ)
     """
-    KINDS = ("gaussian", "mvnormal", "binomial", "lnr", "lba", "hier_normal", "rastrigin")
+    KINDS = ("gaussian", "mvnormal", "binomial", "lnr", "lba", "hier_normal", "rastrigin", "mvnormal_full")
 
-    def __init__(self, kind, x=None, *, choice=None, rt=None, N=None, k=None, sigma=None, lba_floor=1e-10):
+    def __init__(self, kind, x=None, *, choice=None, rt=None, N=None, k=None, sigma=None, lba_floor=1e-10, cov=None):
         kind = str(kind).lstrip(":")
         if kind not in self.KINDS:
             raise ValueError(f"no registered kernel for {kind!r}; registered: {self.KINDS}")
@@ -102,6 +104,7 @@ class GPULoglike:
         self.choice = None
         self.sigma = sigma
         self.lba_floor = lba_floor
+        self.cov = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)   # mvnormal_full: the known covariance
         if kind == "rastrigin":              # the objective of test/optimization_tests.jl:15-23: no data
             self.x = np.zeros(0)
         elif kind == "binomial":
@@ -119,7 +122,7 @@ class GPULoglike:
             if x is None:
                 raise ValueError(f"{kind} needs data")
             self.x = np.ascontiguousarray(x, dtype=np.float64)
-            if kind in ("mvnormal", "hier_normal") and self.x.ndim != 2:
+            if kind in ("mvnormal", "hier_normal", "mvnormal_full") and self.x.ndim != 2:
                 raise ValueError(f"{kind} data must be a matrix")
 
     def __call__(self, *a, **k):
@@ -396,7 +399,7 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
                resample=de.sample is resample, update={mh_update: "mh", maximize: "maximize", minimize: "minimize"}[de.update_particle],
                fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior", blocking_schedule=schedule, devices=devices,
                store_every=store_every)
-    h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor)
+    h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor, cov=ll.cov)
     return h, shapes, d
 
 

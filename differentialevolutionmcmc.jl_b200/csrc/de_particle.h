@@ -34,6 +34,12 @@ constexpr int PROP_PRE = 2;   // elements per lane whose state-independent input
 // mean of dimension k of the MVN / hierarchical likelihood, relative to the data centre
 DE_HD double centred_mean(const ModelDev &m, const double *theta, int k)
 {
+    if (m.kind == M_MVN_FULL) {                                // whitened mean nu_k = sum_{j <= k} Linv[k][j] mu_j
+        const double *row = m.linv + (size_t)k * m.n_dim;
+        double nu = 0.0;
+        for (int j = 0; j <= k; ++j) nu += row[j] * theta[j];
+        return nu - m.center[k];
+    }
     return (m.kind == M_HIER ? theta[0] + theta[2 + k] : theta[k]) - m.center[k];
 }
 
@@ -41,7 +47,7 @@ DE_HD double centred_mean(const ModelDev &m, const double *theta, int k)
 template <class C>
 DE_HD double mean_sq(const C &co, const ModelDev &m, const double *theta)
 {
-    if (m.kind != M_MVNORMAL && m.kind != M_HIER) return 0.0;
+    if (!is_ssd(m.kind)) return 0.0;
     double s = 0.0;
     for (int k = co.lane(); k < m.ssd_k; k += co.width()) { const double v = centred_mean(m, theta, k); s += v * v; }
     return co.sum(s);
@@ -58,6 +64,14 @@ DE_HD double finalize_ll(const ModelDev &m, const double *theta, double total, d
         const double ssd = (m.ssd_xx - 2.0 * total) + (double)m.ssd_n * msq;
         const double sig = theta[m.n_dim], s2 = sig * sig, dm = (double)m.n_dim;
         const double c0 = -(dm * DE_LOG2PI + dm * log(s2)) / 2.0;
+        return (double)m.n_obs * c0 - (ssd / s2) / 2.0;
+    }
+    case M_MVN_FULL: {
+        // sum(logpdf(MvNormal(mu, sigma^2 * Sigma), data)), Sigma known: per column
+        // -(k log2pi + logdet(sigma^2 Sigma)) / 2 - sqmahal / 2, sqmahal = |Linv (x - mu)|^2 / sigma^2
+        const double ssd = (m.ssd_xx - 2.0 * total) + (double)m.ssd_n * msq;
+        const double sig = theta[m.n_dim], s2 = sig * sig, dm = (double)m.n_dim;
+        const double c0 = -(dm * DE_LOG2PI + (dm * log(s2) + m.logdet)) / 2.0;
         return (double)m.n_obs * c0 - (ssd / s2) / 2.0;
     }
     case M_HIER: {
@@ -255,14 +269,14 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const double u = ctx.replay ? ctx.t_uacc[p] : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
     co.dependency_wait();
     double total;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];
+    if (is_ssd(m.kind)) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];
     else {
         double part = 0.0;
         if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN)
             for (int s = co.lane(); s < n_split; s += co.width()) part += ctx.ll_part[(size_t)p * n_split + s];
         total = co.sum(part);
     }
-    const double msq = (m.kind == M_MVNORMAL || m.kind == M_HIER) ? ctx.prop_msq[p] : 0.0;
+    const double msq = is_ssd(m.kind) ? ctx.prop_msq[p] : 0.0;
     const double ll = finalize_ll(m, prop, total, msq);
     const bool inb = ctx.prop_inb[p] != 0;
     // compute_posterior! (utilities.jl:92-99), or evaluate_fun! (utilities.jl:113-120): the kernel

@@ -14,7 +14,9 @@ constexpr int SSD_KS = 4 * SSD_NJ; // max dimensions per dimension split
 constexpr int PW_TP = 8;          // particles per tile of the pointwise kernels
 constexpr int PW_THREADS = 256;
 
-enum ModelKind { M_GAUSSIAN = 0, M_MVNORMAL = 1, M_BINOMIAL = 2, M_LNR = 3, M_LBA = 4, M_HIER = 5, M_RASTRIGIN = 6 };
+enum ModelKind { M_GAUSSIAN = 0, M_MVNORMAL = 1, M_BINOMIAL = 2, M_LNR = 3, M_LBA = 4, M_HIER = 5, M_RASTRIGIN = 6, M_MVN_FULL = 7 };
+// the likelihoods that are a sum of squared deviations from per-dimension means (the streamed DMMA kernels k_xdot / k_chunk_persist)
+DE_HD bool is_ssd(int kind) { return kind == M_MVNORMAL || kind == M_HIER || kind == M_MVN_FULL; }
 enum { UPDATE_MH = 0, UPDATE_MAXIMIZE = 1, UPDATE_MINIMIZE = 2 };
 enum { FITNESS_POSTERIOR = 0, FITNESS_FUN = 1 };
 
@@ -28,6 +30,9 @@ struct ModelDev {
     const double *xT;         // MVN/hier kernel: CENTRED data x' = x - center[k], zero padded, packed as DMMA
                               // A fragments (ssd_pack_index below); the host test double keeps xT[ssd_k][ssd_ld]
     const double *center;     // [ssd_k] column means removed from the data
+    const double *linv;       // M_MVN_FULL: inverse of the Cholesky factor of the covariance, lower triangular [n_dim][n_dim]: the
+                              // kernel streams the WHITENED data y = Linv x against the whitened means nu = Linv mu
+    double logdet;            // M_MVN_FULL: log det of the covariance
     double ssd_xx;            // sum of the squared centred data
     double ssd_rowmax;        // 2 max_i |x'_i|: bounds every chain of k_xdot (the cross terms of two observation rows)
     int64_t ssd_n, ssd_ld;    // observations per dimension and padded leading dimension

@@ -602,6 +602,7 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
     case DEMCMC_LBA: want_d = m->n_dim + 3; break;
     case DEMCMC_HIER_NORMAL: want_d = m->n_dim + 3; break;
     case DEMCMC_RASTRIGIN: want_d = m->d; break;
+    case DEMCMC_MVNORMAL_FULL: want_d = m->n_dim + 1; break;
     default: return fail(DEMCMC_EUNSUPPORTED, "no registered kernel for model kind %d: arbitrary closures are not supported and there is no CPU fallback", m->kind);
     }
     if (m->d != want_d) return fail(DEMCMC_EINVAL, "model kind %d expects d = %d, got %d", m->kind, want_d, m->d);
@@ -628,10 +629,10 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         double nk[2];
         if (dev) { BE(be::d2h(nk, m->x, sizeof nk)); } else memcpy(nk, m->x, sizeof nk);
         D.binom_N = nk[0]; D.binom_k = nk[1]; D.n_obs = 1;
-    } else if (m->kind == DEMCMC_MVNORMAL || m->kind == DEMCMC_HIER_NORMAL) {
+    } else if (m->kind == DEMCMC_MVNORMAL || m->kind == DEMCMC_HIER_NORMAL || m->kind == DEMCMC_MVNORMAL_FULL) {
         // SSD layout: xT[k][ld]; MVN: k = dimension, obs = n_obs; hierarchical: k = subject, obs = n_per
         D.ssd_k = m->n_dim;
-        D.ssd_n = m->kind == DEMCMC_MVNORMAL ? m->n_obs : m->n_per;
+        D.ssd_n = m->kind == DEMCMC_HIER_NORMAL ? m->n_per : m->n_obs;
         if (m->kind == DEMCMC_HIER_NORMAL) D.n_obs = (int64_t)m->n_dim * m->n_per;
         D.ssd_ld = (D.ssd_n + SSD_TN - 1) / SSD_TN * SSD_TN;
         if (D.ssd_ld == 0) D.ssd_ld = SSD_TN;
@@ -657,6 +658,48 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         h->model_allocs.push_back(center);
         D.xT = xT;
         D.center = center;
+        if (m->kind == DEMCMC_MVNORMAL_FULL) {
+            // MvNormal(mu, sigma^2 Sigma), Sigma known: Cholesky Sigma = L L', the data whitened once (y = L^-1 x), and the
+            // device keeps L^-1 to whiten every proposal's mean when it is staged (de_particle.h: centred_mean)
+            const int k = m->n_dim;
+            if (!m->cov) return fail(DEMCMC_EINVAL, "MVNORMAL_FULL needs model.cov");
+            if (dev) return fail(DEMCMC_EUNSUPPORTED, "MVNORMAL_FULL whitens the data on the host: pass host data");
+            if (k < 1 || k > 1024) return fail(DEMCMC_EUNSUPPORTED, "MVNORMAL_FULL supports 1..1024 dimensions");
+            std::vector<double> L((size_t)k * k, 0.0), Li((size_t)k * k, 0.0);
+            double logdet = 0.0;
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    if (fabs(m->cov[(size_t)i * k + j] - m->cov[(size_t)j * k + i]) > 1e-12 * (fabs(m->cov[(size_t)i * k + i]) + fabs(m->cov[(size_t)j * k + j])))
+                        return fail(DEMCMC_EINVAL, "model.cov is not symmetric at (%d, %d)", i, j);
+                    long double sacc = m->cov[(size_t)i * k + j];
+                    for (int q = 0; q < j; ++q) sacc -= (long double)L[(size_t)i * k + q] * L[(size_t)j * k + q];
+                    if (i == j) {
+                        if (!(sacc > 0)) return fail(DEMCMC_EINVAL, "model.cov is not positive definite (pivot %d)", i);
+                        L[(size_t)i * k + i] = sqrt((double)sacc);
+                        logdet += 2.0 * log(L[(size_t)i * k + i]);
+                    } else L[(size_t)i * k + j] = (double)(sacc / L[(size_t)j * k + j]);
+                }
+            for (int c = 0; c < k; ++c)                          // L^-1 column by column: L z = e_c
+                for (int r = c; r < k; ++r) {
+                    long double t = r == c ? 1.0L : 0.0L;
+                    for (int q = c; q < r; ++q) t -= (long double)L[(size_t)r * k + q] * Li[(size_t)q * k + c];
+                    Li[(size_t)r * k + c] = (double)(t / L[(size_t)r * k + r]);
+                }
+            std::vector<double> y((size_t)m->n_obs * k);
+            for (int64_t i = 0; i < m->n_obs; ++i) {
+                const double *xi = m->x + (size_t)i * k;
+                double *yi = y.data() + (size_t)i * k;
+                for (int r = 0; r < k; ++r) {                    // forward substitution: the same arithmetic as whitening through L
+                    long double t = xi[r];
+                    for (int q = 0; q < r; ++q) t -= (long double)L[(size_t)r * k + q] * yi[q];
+                    yi[r] = (double)(t / L[(size_t)r * k + r]);
+                }
+            }
+            D.linv = (const double *)upload(Li.data(), sizeof(double) * Li.size(), false);
+            if (!D.linv) return fail(DEMCMC_ENOMEM, "covariance factor upload failed");
+            D.logdet = logdet;
+            BE(be::launch_pack_ssd(y.data(), 0, m->center, &D));
+        } else
         BE(be::launch_pack_ssd(m->x, dev, m->center, &D));       // centres and packs the data, fills D.ssd_xx / D.ssd_rowmax
     } else {
         D.x = (const double *)upload(m->x, sizeof(double) * m->n_obs, dev);
@@ -832,7 +875,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     // ---- trace and migration log of this call ------------------------------------------------------
     be::dfree(h->tr_theta); be::dfree(h->tr_w); be::dfree(h->tr_adj); be::dfree(h->tr_acc); be::dfree(h->tr_xdot);
     h->tr_theta = h->tr_w = h->tr_adj = h->tr_xdot = nullptr; h->tr_acc = nullptr; h->tr_sweeps = 0;
-    const bool ssd_model = h->dmodel.kind == M_MVNORMAL || h->dmodel.kind == M_HIER;
+    const bool ssd_model = is_ssd(h->dmodel.kind);
     if (cfg.trace && S > 0) {
         h->tr_theta = (double *)be::dmalloc(sizeof(double) * S * P * d);
         h->tr_w = (double *)be::dmalloc(sizeof(double) * S * P);
@@ -965,7 +1008,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             {
                 const char *e = getenv("DEMCMC_SHAPE");       // 0 = off, else the modulus (A/B runs)
                 const int mod = e ? atoi(e) : 8;
-                pin.shape_octets = (h->dmodel.kind == M_MVNORMAL || h->dmodel.kind == M_HIER) ? std::max(0, mod) : 0;
+                pin.shape_octets = (is_ssd(h->dmodel.kind)) ? std::max(0, mod) : 0;
             }
             pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
             const int64_t s_first = it0 * B + b;
@@ -1510,7 +1553,7 @@ int demcmc_eval(demcmc_handle *h, const double *theta, int64_t n, double *loglik
 int demcmc_eval_xdot(demcmc_handle *h, const double *theta, int64_t n, double *xdot)
 {
     if (!xdot) return fail(DEMCMC_EINVAL, "null out");
-    if (h && h->has_model && h->dmodel.kind != M_MVNORMAL && h->dmodel.kind != M_HIER) return fail(DEMCMC_EINVAL, "only MVNORMAL / HIER_NORMAL have a cross term");
+    if (h && h->has_model && !is_ssd(h->dmodel.kind)) return fail(DEMCMC_EINVAL, "only MVNORMAL / HIER_NORMAL have a cross term");
     return eval_impl(h, theta, n, nullptr, nullptr, xdot);
 }
 static int eval_impl(demcmc_handle *h, const double *theta, int64_t n, double *loglike, double *prior, double *xdot)

@@ -378,7 +378,7 @@ constexpr int PA_THREADS = 128;
 // per-device staging for k_xdot: the proposals' centred means as DMMA B fragments,
 // bfrag[octet of the level][dimension split][k-step j][lane], and the fixed-point magic constant of
 // every particle of the level, magic[level order]
-struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; };
+struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; bool fresh = false; };   // fresh: cleared on its lane's stream just now
 static XdStage g_xs[64][MAX_LANES];
 static XdStage *xd_stage(const ModelDev &m, int n);
 
@@ -562,7 +562,7 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
     XdStage *xs = nullptr;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+    if (is_ssd(m.kind)) {
         // sized once for the handle's whole population so it never grows inside a run
         xs = xd_stage(m, std::max(lv.n, cfg.G_local * cfg.Np));
         if (!xs) return -1;
@@ -688,7 +688,7 @@ int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const char *env = getenv("DEMCMC_NO_FUSED");
     if (env && env[0] == '1') return 1;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER || !lv.ctxs || cfg.d > 64) return 1;
+    if (is_ssd(m.kind) || !lv.ctxs || cfg.d > 64) return 1;
     if ((m.kind == M_GAUSSIAN || m.kind == M_LNR || m.kind == M_LBA) && (m.n_obs > FUSED_MAX_OBS || m.n_osplit * m.n_ksplit != 1)) return 1;
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
     switch (m.kind) {
@@ -864,6 +864,7 @@ static XdStage *xd_stage(const ModelDev &m, int n)
     if (magic != x.magic) {
         if (cudaMemsetAsync(x.bfrag, 0, sizeof(double) * x.cap, stream()) != cudaSuccess) { g_be_err = "cudaMemset(mean staging)"; return nullptr; }
         x.magic = magic;
+        x.fresh = true;
     }
     return &x;
 }
@@ -1535,7 +1536,7 @@ static int persist_scalar_ctas()
 // fewer warps than k_propose has), or levels far larger than the scalar warps.
 int chunk_persist_lanes(const ConfigDev &cfg, const ModelDev &m)
 {
-    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER)) return 0;
+    if (!persist_enabled() || !is_ssd(m.kind)) return 0;
     if (cfg.G_local < 2) return 0;
     if ((int64_t)cfg.G_local * cfg.Np / 8 > (int64_t)4 * PK_WARPS * persist_scalar_ctas()) return 0;   // ~ a level per lane
     // Two lanes.  More (DEMCMC_PK_LANES = 3, 4: one lane per group) give a lane's accept -> propose chain more DMMA time
@@ -1554,7 +1555,7 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
                          const int32_t *level_off, const int32_t *level_n, const int32_t *dep, int n_levels, int lag, long long *ll_acc, int n_buf)
 {
     n_buf = std::max(2, std::min(n_buf, (int)MAX_LANES));
-    if (!persist_enabled() || (m.kind != M_MVNORMAL && m.kind != M_HIER) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
+    if (!persist_enabled() || !is_ssd(m.kind) || n_levels <= 0 || n_levels > PK_MAX_LEVELS) return 1;
     static thread_local PChunk ck;                           // 9 KB: not on the stack of every call
     const int n_scalar = persist_scalar_ctas();
     const int sms = n_sms(), slots = XD_CTAS_PER_SM * (sms - n_scalar);
@@ -1576,7 +1577,14 @@ int launch_chunk_persist(const ConfigDev &cfg, const ModelDev &m, const int32_t 
     if (!ctr[g_dev]) CU(cudaMalloc(&ctr[g_dev], sizeof(int32_t) * (PK_MAX_LEVELS + 2 * PK_MAX_TILES)));
     XdStage *xs[MAX_LANES];
     const int keep = g_lane;
-    for (int b = 0; b < n_buf; ++b) { g_lane = b; xs[b] = xd_stage(m, std::max(n_max, cfg.G_local * cfg.Np)); if (!xs[b]) { g_lane = keep; return -1; } }
+    for (int b = 0; b < n_buf; ++b) {
+        g_lane = b;
+        xs[b] = xd_stage(m, std::max(n_max, cfg.G_local * cfg.Np));
+        if (!xs[b]) { g_lane = keep; return -1; }
+        // the copy was cleared on lane b's stream; this kernel runs on the launching lane's: order them
+        if (xs[b]->fresh && b != keep) { cudaStreamSynchronize(stream()); }
+        xs[b]->fresh = false;
+    }
     g_lane = keep;
     ck.n_levels = n_levels; ck.lag = lag; ck.n_scalar_ctas = n_scalar; ck.n_buf = n_buf; ck.order = d_order; ck.ctxs = d_ctx;
     ck.acc_done = ctr[g_dev]; ck.prop_done = ctr[g_dev] + PK_MAX_LEVELS; ck.xdot_done = ck.prop_done + PK_MAX_TILES;
@@ -1622,7 +1630,7 @@ int launch_loglik(const ConfigDev &cfg, const ModelDev &m, const double *theta, 
 {
     (void)cfg;
     if (lv.n <= 0 || m.kind == M_BINOMIAL || m.kind == M_RASTRIGIN) return 0;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+    if (is_ssd(m.kind)) {
         // the proposal kernel of this level has staged the centred means and cleared the accumulators
         const XdStage &xs = g_xs[g_dev][g_lane];
         if (!xs.bfrag || !xs.magic) { g_be_err = "mean staging buffer missing"; return -1; }
@@ -1710,7 +1718,7 @@ int launch_pack_ssd(const double *x_in, int in_on_device, const double *center_h
         if (h2d(tmp, x_in, bytes)) { dfree(tmp); dfree(blk); return -1; }
         src = tmp;
     }
-    const int obs_major = m->kind == M_MVNORMAL ? 1 : 0;
+    const int obs_major = m->kind == M_HIER ? 0 : 1;
     cudaError_t e = cudaMemsetAsync(const_cast<double *>(m->xT), 0, sizeof(double) * pack_ssd_doubles(*m), stream());
     if (e == cudaSuccess) e = cudaMemsetAsync(blk, 0, sizeof(double) * 2 * n_blk, stream());
     if (e == cudaSuccess && center_host) e = cudaMemcpyAsync(const_cast<double *>(m->center), center_host, sizeof(double) * m->ssd_k, cudaMemcpyHostToDevice, stream());
@@ -1748,7 +1756,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_eval_finish(ConfigDev cfg, Model
     bounds_and_prior(co, cfg, m, th, inb, pr);
     const int n_split = m.n_osplit * m.n_ksplit;
     double s = 0.0;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) s = (double)acc[wi] * q[wi];
+    if (is_ssd(m.kind)) s = (double)acc[wi] * q[wi];
     else {
         if (m.kind != M_BINOMIAL && m.kind != M_RASTRIGIN) for (int c = co.lane(); c < n_split; c += 32) s += part[(size_t)wi * n_split + c];
         s = co.sum(s);
@@ -1770,7 +1778,7 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
     const int blocks = (int)((n * 32 + PA_THREADS - 1) / PA_THREADS);
     long long *acc = nullptr;
     double *q = nullptr;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+    if (is_ssd(m.kind)) {
         XdStage *xs = xd_stage(m, (int)n);
         if (!xs) return -1;
         acc = (long long *)dmalloc(sizeof(long long) * n);

@@ -8,7 +8,7 @@ import numpy as np
 from . import _ffi
 from ._ffi import _bp, _dp, _ip, check, f8, ptr
 
-KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6}
+KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6, "mvnormal_full": 7}
 UPDATES = {"mh": 0, "maximize": 1, "minimize": 2}
 FITNESS = {"posterior": 0, "fun": 1}
 PRIORS = {"flat": 0, "normal": 1, "halfcauchy": 2, "uniform": 3, "beta": 4, "normal_ref": 5}
@@ -70,7 +70,7 @@ class Handle:
 
     # ---- model ---------------------------------------------------------------------------------
     def set_model(self, kind, prior, x=None, choice=None, sigma=None, lba_floor=1e-10, device_ptrs=None, n_obs=None,
-                  n_dim=0, n_per=0, center=None):
+                  n_dim=0, n_per=0, center=None, cov=None):
         """Bind a registered likelihood kernel.  `prior` is a list of (name, a, b, ref) per
         flattened parameter.  `device_ptrs=(x_ptr, choice_ptr)` passes data already in HBM.
         `center` (mvnormal / hier_normal, test hook): centre the data on this vector instead of on their
@@ -95,7 +95,7 @@ class Handle:
             cs = None if choice is None else np.ascontiguousarray(choice, dtype=np.int32)
             xp = xs.ctypes.data
             cp = cs.ctypes.data if cs is not None else None
-            if kind == "mvnormal":
+            if kind in ("mvnormal", "mvnormal_full"):
                 n_obs, n_dim = xs.shape
             elif kind == "hier_normal":
                 n_dim, n_per = xs.shape
@@ -112,8 +112,11 @@ class Handle:
         cen = None if center is None else f8(center).reshape(-1)
         if cen is not None and cen.size != int(n_dim):
             raise ValueError(f"center needs {n_dim} entries")
-        m = _ffi.Model(kind_id, d, int(n_obs), int(n_dim), int(n_per), xp, cp, ptr(sg, _dp), float(lba_floor), pr, on_dev, 0, ptr(cen, _dp))
-        self._keep = [xs, cs, sg, pr, cen]
+        cv = None if cov is None else f8(cov)
+        if kind == "mvnormal_full" and (cv is None or cv.shape != (int(n_dim), int(n_dim))):
+            raise ValueError("mvnormal_full needs cov of shape (n_dim, n_dim)")
+        m = _ffi.Model(kind_id, d, int(n_obs), int(n_dim), int(n_per), xp, cp, ptr(sg, _dp), float(lba_floor), pr, on_dev, 0, ptr(cv, _dp), ptr(cen, _dp))
+        self._keep = [xs, cs, sg, pr, cen, cv]
         check(_ffi.lib().demcmc_set_model(self._h, C.byref(m)))
 
     # ---- state ---------------------------------------------------------------------------------

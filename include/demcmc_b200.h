@@ -33,7 +33,13 @@ enum { DEMCMC_OK = 0, DEMCMC_EINVAL = -1, DEMCMC_ENODEVICE = -2, DEMCMC_ECUDA = 
  * `loglike(data, theta...)`, e.g. Examples/Gaussian_Example.jl:26-28) */
 enum { DEMCMC_GAUSSIAN = 0, DEMCMC_MVNORMAL = 1, DEMCMC_BINOMIAL = 2, DEMCMC_LNR = 3, DEMCMC_LBA = 4,
        DEMCMC_HIER_NORMAL = 5,
-       DEMCMC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23 (optimize path; no data) */ };
+       DEMCMC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23 (optimize path; no data) */,
+       DEMCMC_MVNORMAL_FULL = 7 /* sum(logpdf(MvNormal(mu, sigma^2 * Sigma), data)) with a KNOWN full covariance Sigma
+                                   (demcmc_model.cov); parameters mu[n_dim], sigma: d = n_dim + 1.  The data are
+                                   whitened once through the Cholesky factor (y = L^-1 x), every proposal's mean is whitened
+                                   when it is staged (nu = L^-1 mu), and the isotropic kernels stream y against nu */ };
+/* (Examples/Guassian_Example_Vector.jl is the Gaussian model with `loglike(data, theta...)` destructuring its arguments:
+ * DEMCMC_GAUSSIAN is its kernel, d = 2 whether the two parameters are named separately or as one 2-vector.) */
 /* de.update_particle! (src/utilities.jl:201-226): mh_update!, or the greedy maximize! / minimize! of
  * optimize (src/optimize.jl); de.evaluate_fitness! (src/utilities.jl:92-120): compute_posterior!, or
  * evaluate_fun! = the registered kernel alone, no prior, out of bounds = -/+Inf */
@@ -73,6 +79,7 @@ typedef struct {
     const demcmc_prior *prior; /* [d], host memory */
     int32_t data_on_device; /* 1: x / choice are device pointers on the handle's device */
     int32_t reserved;
+    const double *cov;      /* MVNORMAL_FULL: covariance [n_dim][n_dim] (host memory), symmetric positive definite */
     const double *center;   /* MVNORMAL / HIER_NORMAL: NULL (the default) = the kernel centres the data on their column
                                means, x' = x - mean: the sum of squares is then  sum x'^2 - 2 B + n sum m'^2  with the
                                streamed cross term B = sum_i sum_k x'_ik m'_k ANALYTICALLY ZERO (sum_i x'_ik = 0) -- the

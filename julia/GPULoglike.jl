@@ -25,7 +25,7 @@
 const LIBDEMCMC = get(ENV, "LIBDEMCMC_B200", "libdemcmc_b200.so")
 const DEMCMC_ABI_VERSION = Int32(4)
 
-const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5, rastrigin = 6)
+const GPU_KINDS = (gaussian = 0, mvnormal = 1, binomial = 2, lnr = 3, lba = 4, hier_normal = 5, rastrigin = 6, mvnormal_full = 7)
 const GPU_PRIORS = (flat = 0, normal = 1, halfcauchy = 2, uniform = 3, beta = 4, normal_ref = 5)
 
 """
@@ -41,10 +41,11 @@ struct GPULoglike{D}
     data::D
     sigma::Union{Nothing, Vector{Float64}}
     lba_floor::Float64
+    cov::Matrix{Float64}   # :mvnormal_full: the known covariance Σ of MvNormal(μ, σ²Σ); empty otherwise
 end
 
 function GPULoglike(kind::Symbol; x = nothing, choice = nothing, rt = nothing, N = nothing, k = nothing,
-    sigma = nothing, lba_floor = 1e-10)
+    sigma = nothing, lba_floor = 1e-10, cov = zeros(0, 0))
     haskey(GPU_KINDS, kind) || throw(ArgumentError("no registered kernel for :$kind; registered: $(keys(GPU_KINDS))"))
     data = if kind == :binomial
         (x = Float64[N, k], choice = nothing)
@@ -55,7 +56,8 @@ function GPULoglike(kind::Symbol; x = nothing, choice = nothing, rt = nothing, N
     else
         (x = Array{Float64}(x), choice = nothing)
     end
-    return GPULoglike(kind, data, sigma === nothing ? nothing : Vector{Float64}(sigma), Float64(lba_floor))
+    kind == :mvnormal_full && size(cov) != (size(data.x, 1), size(data.x, 1)) && throw(ArgumentError(":mvnormal_full needs cov, n_dim × n_dim"))
+    return GPULoglike(kind, data, sigma === nothing ? nothing : Vector{Float64}(sigma), Float64(lba_floor), Matrix{Float64}(cov))
 end
 
 # the device evaluates it; calling it on the host is an error, never a fallback
@@ -125,6 +127,7 @@ struct CModel
     prior::Ptr{CPrior}
     data_on_device::Int32
     reserved::Int32
+    cov::Ptr{Float64}      # :mvnormal_full: the known covariance, n_dim × n_dim
     center::Ptr{Float64}   # C_NULL: centre the data on their column means (the product default)
 end
 
@@ -257,7 +260,8 @@ function _sample_gpu(model, de, n_iter; device, seed, devices = Int32[], store_e
     x = ll.data.x
     choice = ll.data.choice
     n_dim, n_per, n_obs = 0, 0, length(x)
-    if ll.kind == :mvnormal
+    covm = ll.cov
+    if ll.kind == :mvnormal || ll.kind == :mvnormal_full
         n_dim, n_obs = size(x)
     elseif ll.kind == :hier_normal
         n_per, n_dim = size(x); n_obs = n_dim * n_per
@@ -281,14 +285,14 @@ function _sample_gpu(model, de, n_iter; device, seed, devices = Int32[], store_e
     init_rows = de.n_initial > 0 ?
         Float64[flatten_theta(de.samples[i, :, p])[k] for k = 1:d, p = 1:P, i = 1:(de.n_initial)] : Float64[]
     sig = ll.sigma === nothing ? Float64[] : ll.sigma
-    GC.@preserve theta0 lo hi blocks priors x choice sig samples accept lp final_ids final_theta final_weight init_rows devs begin
+    GC.@preserve theta0 lo hi blocks priors x choice sig covm samples accept lp final_ids final_theta final_weight init_rows devs begin
         cfg = CConfig(DEMCMC_ABI_VERSION, de.n_groups, de.Np, d, de.burnin, de.n_initial, de.α, de.β, de.ϵ, de.σ, de.κ,
             de.θsnooker, proposal_id(de), n_blocks, isempty(blocks) ? C_NULL : pointer(blocks), pointer(lo), pointer(hi),
             seed, device, 0, 0, donors, 0, 1, update, fitness, length(devs), isempty(devs) ? C_NULL : pointer(devs))
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
             m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), choice === nothing ? C_NULL : pointer(choice),
-                isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0, C_NULL)
+                isempty(sig) ? C_NULL : pointer(sig), ll.lba_floor, pointer(priors), 0, 0, isempty(covm) ? C_NULL : pointer(covm), C_NULL)
             demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
             if n_blocks > 0 && !all(!iszero, block_on)         # block updating in some iterations only
                 GC.@preserve block_on demcmc_check(ccall((:demcmc_set_blocking_schedule, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), h[], block_on, length(block_on)))
@@ -354,7 +358,7 @@ function _sample_gpu_thinned(model, de, n_iter; device, devices, store_every, se
             pointer(lo), pointer(hi), seed, device, 0, 0, 0, 0, store_every, 0, 0, length(devs), isempty(devs) ? C_NULL : pointer(devs))
         demcmc_check(ccall((:demcmc_create, LIBDEMCMC), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         try
-            m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), C_NULL, C_NULL, ll.lba_floor, pointer(priors), 0, 0, C_NULL)
+            m = CModel(GPU_KINDS[ll.kind], d, n_obs, n_dim, n_per, pointer(x), C_NULL, C_NULL, ll.lba_floor, pointer(priors), 0, 0, C_NULL, C_NULL)
             demcmc_check(ccall((:demcmc_set_model, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ref{CModel}), h[], m))
             demcmc_check(ccall((:demcmc_set_state, LIBDEMCMC), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), h[], theta0, C_NULL))
             demcmc_check(ccall((:demcmc_run, LIBDEMCMC), Cint, (Ptr{Cvoid}, Int64), h[], n_iter))

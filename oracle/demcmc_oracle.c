@@ -137,6 +137,39 @@ static double ll_mvnormal(const orc_model *m, const double *th)
     return kval(&s);
 }
 
+/* sum(logpdf(MvNormal(mu, sigma^2 Sigma), data)), Sigma known: per column -(k log2pi + logdet(sigma^2 Sigma))/2 -
+ * sqmahal/2 with sqmahal = z'z, L z = x - mu, sigma^2 Sigma = (sigma L)(sigma L)' (PDMats: whiten through the Cholesky
+ * factor).  O(n k^2) per evaluation: the Cholesky factor is rebuilt per call like MvNormal's constructor does. */
+static double ll_mvn_full(const orc_model *m, const double *th)
+{
+    int k = m->n_dim;
+    double sig = th[k], s2 = sig * sig;
+    double *L = (double *)calloc((size_t)k * k, sizeof(double)), *z = (double *)malloc(sizeof(double) * k);
+    double logdet = 0.0;
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j <= i; ++j) {
+            long double s = m->cov[(size_t)i * k + j];
+            for (int q = 0; q < j; ++q) s -= (long double)L[(size_t)i * k + q] * L[(size_t)j * k + q];
+            if (i == j) { L[(size_t)i * k + i] = sqrt((double)s); logdet += 2.0 * log(L[(size_t)i * k + i]); }
+            else L[(size_t)i * k + j] = (double)(s / L[(size_t)j * k + j]);
+        }
+    double c0 = -((double)k * LOG2PI + ((double)k * log(s2) + logdet)) / 2.0;
+    ksum s = { 0, 0 };
+    for (int64_t i = 0; i < m->n_obs; ++i) {
+        const double *x = m->x + i * k;
+        ksum q = { 0, 0 };
+        for (int r = 0; r < k; ++r) {
+            long double t = x[r] - th[r];
+            for (int c = 0; c < r; ++c) t -= (long double)L[(size_t)r * k + c] * z[c];
+            z[r] = (double)(t / L[(size_t)r * k + r]);
+            kadd(&q, z[r] * z[r]);
+        }
+        kadd(&s, c0 - (kval(&q) / s2) / 2.0);
+    }
+    free(L); free(z);
+    return kval(&s);
+}
+
 /* test/binomial_tests.jl:15-17: logpdf(Binomial(N,theta),k) */
 static double ll_binomial(const orc_model *m, const double *th)
 {
@@ -232,6 +265,7 @@ double orc_loglike(const orc_model *m, const double *theta)
     case ORC_LNR: return ll_lnr(m, theta);
     case ORC_LBA: return ll_lba(m, theta);
     case ORC_HIER_NORMAL: return ll_hier(m, theta);
+    case ORC_MVN_FULL: return ll_mvn_full(m, theta);
     case ORC_RASTRIGIN: {       /* test/optimization_tests.jl:15-23 */
         const double A = 10.0;
         double y = A * (double)m->d;

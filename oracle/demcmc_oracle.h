@@ -26,7 +26,9 @@ extern "C" {
 
 /* registered likelihood kernels */
 enum { ORC_GAUSSIAN = 0, ORC_MVNORMAL = 1, ORC_BINOMIAL = 2, ORC_LNR = 3, ORC_LBA = 4, ORC_HIER_NORMAL = 5,
-       ORC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23; no data */ };
+       ORC_RASTRIGIN = 6 /* the objective of test/optimization_tests.jl:15-23; no data */,
+       ORC_MVN_FULL = 7  /* MvNormal(mu, sigma^2 * Sigma) with a known covariance Sigma (not a model of the reference's
+                            examples: Distributions.logpdf(MvNormal(mu, Sigma), data) by its published definition) */ };
 /* de.update_particle! (utilities.jl:201-226) and de.evaluate_fitness! (utilities.jl:92-120) */
 enum { ORC_UPDATE_MH = 0, ORC_UPDATE_MAXIMIZE = 1, ORC_UPDATE_MINIMIZE = 2 };
 enum { ORC_FITNESS_POSTERIOR = 0, ORC_FITNESS_FUN = 1 };
@@ -57,6 +59,7 @@ typedef struct {
     const double *sigma;   /* LNR: sd per accumulator [n_dim] (NULL => 1) */
     double lba_floor;      /* LBA: density floor (SequentialSamplingModels uses 1e-10); 0 disables */
     const orc_prior *prior;/* [d] */
+    const double *cov;     /* MVN_FULL: covariance [n_dim][n_dim], symmetric positive definite */
 } orc_model;
 
 typedef struct {

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6}
+KINDS = {"gaussian": 0, "mvnormal": 1, "binomial": 2, "lnr": 3, "lba": 4, "hier_normal": 5, "rastrigin": 6, "mvnormal_full": 7}
 UPDATES = {"mh": 0, "maximize": 1, "minimize": 2}
 FITNESS = {"posterior": 0, "fun": 1}
 PRIORS = {"flat": 0, "normal": 1, "halfcauchy": 2, "uniform": 3, "beta": 4, "normal_ref": 5}
@@ -33,7 +33,7 @@ class _Prior(C.Structure):
 class _Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("d", C.c_int32), ("n_obs", C.c_int64), ("n_dim", C.c_int32),
                 ("n_per", C.c_int32), ("x", _dp), ("choice", _ip), ("sigma", _dp),
-                ("lba_floor", C.c_double), ("prior", C.POINTER(_Prior))]
+                ("lba_floor", C.c_double), ("prior", C.POINTER(_Prior)), ("cov", _dp)]
 
 
 class _Config(C.Structure):
@@ -102,7 +102,7 @@ def _f8(a):
 class Model:
     """Keeps the numpy buffers alive behind an orc_model."""
 
-    def __init__(self, kind, d, prior, x=None, choice=None, n_dim=0, n_per=0, sigma=None, lba_floor=1e-10):
+    def __init__(self, kind, d, prior, x=None, choice=None, n_dim=0, n_per=0, sigma=None, lba_floor=1e-10, cov=None):
         self.kind, self.d = kind, int(d)
         self.x = _f8(x if x is not None else [])
         self.choice = None if choice is None else np.ascontiguousarray(choice, dtype=np.int32)
@@ -115,7 +115,8 @@ class Model:
             b = float(p[2]) if len(p) > 2 else 0.0
             ref = int(p[3]) if len(p) > 3 else 0
             self._prior[k] = _Prior(PRIORS[name], ref, a, b)
-        if kind == "mvnormal":
+        self.cov = None if cov is None else _f8(cov)
+        if kind in ("mvnormal", "mvnormal_full"):
             n_obs = self.x.shape[0]
             n_dim = self.x.shape[1]
         elif kind == "hier_normal":
@@ -126,7 +127,7 @@ class Model:
         else:
             n_obs = self.x.shape[0]
         self.c = _Model(KINDS[kind], self.d, n_obs, int(n_dim), int(n_per), _ptr(self.x, _dp),
-                        _ptr(self.choice, _ip), _ptr(self.sigma, _dp), float(lba_floor), self._prior)
+                        _ptr(self.choice, _ip), _ptr(self.sigma, _dp), float(lba_floor), self._prior, _ptr(self.cov, _dp))
 
 
 class Config:

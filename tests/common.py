@@ -95,6 +95,15 @@ def make_case(name, rng, n_obs=None, n_subjects=9):
         x = rng.normal(mu, 1.0, size=(n, dm))
         return Case(name, "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-INF] * dm + [0],
                     [INF] * (dm + 1), lambda r: list(r.normal(size=dm)) + [halfcauchy(r) + 0.3], dict(x=x))
+    if name == "mvnormal_full":  # MvNormal(mu, sigma^2 Sigma) with a known, strongly correlated covariance
+        n = n_obs or 150
+        dm = 6
+        A = rng.normal(size=(dm, dm))
+        cov = A @ A.T + 0.5 * np.eye(dm)
+        mu = rng.normal(size=dm)
+        x = rng.multivariate_normal(mu, 1.3 ** 2 * cov, size=n)
+        return Case(name, "mvnormal_full", dm + 1, [("normal", 0, 2)] * dm + [("halfcauchy", 0, 1)], [-INF] * dm + [0],
+                    [INF] * (dm + 1), lambda r: list(r.normal(mu, 0.3)) + [halfcauchy(r) + 0.5], dict(x=x, cov=cov))
     if name == "rastrigin":      # test/optimization_tests.jl:8-23: x in [-5, 5]^2, no data, no prior
         return Case(name, "rastrigin", 2, [("flat",), ("flat",)], [-5.0, -5.0], [5.0, 5.0], lambda r: list(r.uniform(-5, 5, 2)), dict())
     if name == "binomial":

@@ -73,7 +73,7 @@ int launch_pack_ssd(const double *x, int, const double *center_host, ModelDev *m
     double *xT = const_cast<double *>(m->xT), *center = const_cast<double *>(m->center);
     double xx = 0.0;
     for (int k = 0; k < m->ssd_k; ++k) {
-        auto at = [&](int64_t i) { return m->kind == M_MVNORMAL ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i]; };
+        auto at = [&](int64_t i) { return m->kind != M_HIER ? x[i * m->ssd_k + k] : x[(int64_t)k * m->ssd_n + i]; };
         double s = 0.0;
         for (int64_t i = 0; i < m->ssd_n; ++i) s += at(i);
         const double c = center_host ? center_host[k] : (m->ssd_n > 0 ? s / (double)m->ssd_n : 0.0);
@@ -101,7 +101,7 @@ static int loglik_impl(const ModelDev &m, const double *theta, const Level &lv, 
     for (int q = 0; q < lv.n; ++q) {
         const int p = lv.order ? (int)((uint32_t)lv.order[q] & LV_POS_MASK) : q;
         const double *th = theta + (size_t)p * m.d;
-        if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+        if (is_ssd(m.kind)) {
             for (int os = 0; os < m.n_osplit; ++os)
                 for (int ks = 0; ks < m.n_ksplit; ++ks) {
                     const int k0 = ks * m.ksplit_len, k1 = std::min(m.ssd_k, k0 + m.ksplit_len);
@@ -144,7 +144,7 @@ static int loglik_impl(const ModelDev &m, const double *theta, const Level &lv, 
 int launch_loglik(const ConfigDev &, const ModelDev &m, const double *theta, const Level &lv, double *part, long long *)
 {
     if (loglik_impl(m, theta, lv, part)) return -1;
-    if (m.kind == M_MVNORMAL || m.kind == M_HIER) {
+    if (is_ssd(m.kind)) {
         const int n_split = m.n_osplit * m.n_ksplit;
         for (int q = 0; q < lv.n; ++q) {
             const uint32_t e = (uint32_t)lv.order[q];

@@ -626,3 +626,24 @@ def test_device_diagnostics_match_the_host_estimators():
     E._check_device_diagnostics(G=4, Np=64, n_iter=400)
     if _n_gpus() >= 2:
         E._check_device_diagnostics(devices=[0, 1])
+
+
+def test_full_covariance_mvn_kernel():
+    E._check_mvn_full()
+    # a larger, strongly correlated case through the persistent kernel against the oracle's per-observation whitening
+    rng = np.random.default_rng(17)
+    n, dm = 4000, 50
+    A = rng.normal(size=(dm, dm))
+    cov = A @ A.T / dm + 0.2 * np.eye(dm)
+    mu = rng.normal(size=dm)
+    x = rng.multivariate_normal(mu, cov, size=n)
+    prior = [("normal", 0, 2)] * dm + [("halfcauchy", 0, 1)]
+    case = common.Case("mvn_full50", "mvnormal_full", dm + 1, prior, [-np.inf] * dm + [0], [np.inf] * (dm + 1),
+                       lambda r: list(r.normal(mu, 0.05)) + [abs(r.normal(1, 0.05))], dict(x=x, cov=cov))
+    r, out = forced_run(case, 4, 16, 3, "replay", burnin=1, theta_snooker=0.1)
+    assert out["counters"]["persistent_chunks"] > 0
+    check(r, out)
+
+
+def test_vector_parameter_gaussian_example():   # Examples/Guassian_Example_Vector.jl
+    E._check_vector_gaussian_example()

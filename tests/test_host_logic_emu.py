@@ -612,3 +612,65 @@ def test_device_diagnostics_match_the_host_estimators(emu):
     _check_device_diagnostics(n_iter=91)                   # odd number of rows: the middle draw is dropped
     _check_device_diagnostics(devices=[0, 1])              # shards merged
     _check_device_diagnostics(store_every=2, n_iter=120)
+
+
+# ---- the full-covariance MVN kernel and the vector-parameter Gaussian example --------------------------
+def _check_mvn_full():
+    from scipy import stats
+    rng = np.random.default_rng(8)
+    case = make_case("mvnormal_full", rng)
+    th = case.theta0(rng, 9)
+    # the oracle's restatement against scipy's multivariate normal
+    m = case.oracle_model()
+    for t in th:
+        ref = stats.multivariate_normal(mean=t[:6], cov=t[6] ** 2 * case.data["cov"]).logpdf(case.data["x"]).sum()
+        assert abs(O.loglike(m, t) - ref) <= 1e-11 * abs(ref)
+    with case.handle(1, 9) as h:
+        ll, pr = h.eval(th)
+    assert rel_err(ll, np.array([O.loglike(m, t) for t in th])) <= 1e-12
+    for mode in ("replay", "native"):
+        r, out = forced_run(case, 2, 7, 6, mode, burnin=2, theta_snooker=0.2, alpha=0.4)
+        assert np.array_equal(out["accept"], r["accept"])
+        assert rel_err(out["samples"], r["samples"]) <= 1e-12 and rel_err(out["lp"], r["lp"]) <= 1e-12
+
+
+def test_full_covariance_mvn_kernel(emu):
+    _check_mvn_full()
+    rng = np.random.default_rng(3)
+    case = make_case("mvnormal_full", rng)
+    bad = dict(case.data)
+    bad["cov"] = -np.eye(6)
+    with pytest.raises(D._ffi.DemcmcError):
+        D.Handle(1, 4, 7, case.lo, case.hi).set_model("mvnormal_full", case.prior, **bad)
+
+
+def _check_vector_gaussian_example():
+    """Examples/Guassian_Example_Vector.jl: the Gaussian model whose loglike(data, θ...) destructures μ, σ -- whether the
+    two parameters are named separately or come as ONE 2-vector parameter, the registered "gaussian" kernel is its
+    kernel and the chains are the same chains"""
+    x = np.random.default_rng(50514).normal(0, 1, 50)
+    outs = []
+    for vector in (False, True):
+        rng = np.random.default_rng(9)
+        draw = lambda: [rng.normal(0, 1), abs(rng.standard_cauchy())]      # noqa: E731
+        if vector:
+            model = D.DEModel(sample_prior=lambda: [np.array(draw())], prior_loglike=D.GPUPrior(D.Flat()), loglike=D.GPULoglike("gaussian", x), names=("θ",))
+            de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf),), burnin=100, Np=6, seed=3)
+        else:
+            model = D.DEModel(sample_prior=draw, prior_loglike=D.GPUPrior(D.Flat(), D.Flat()), loglike=D.GPULoglike("gaussian", x), names=("μ", "σ"))
+            de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (-np.inf, np.inf)), burnin=100, Np=6, seed=3)
+        ch = D.sample(model, de, D.MCMCThreads(), 300)
+        outs.append(ch)
+    assert outs[1].names[:2] == ["θ[1]", "θ[2]"] and outs[0].names[:2] == ["μ", "σ"]
+    assert np.array_equal(outs[0].value, outs[1].value, equal_nan=True)
+    # and with the example's own priors and bounds it recovers the posterior (mean of μ near the sample mean)
+    rng = np.random.default_rng(1)
+    model = D.GPUDEModel(sample_prior=lambda: [rng.normal(0, 1), abs(rng.standard_cauchy())], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                         loglike=D.GPULoglike("gaussian", x), names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), burnin=1000, Np=6, seed=4)
+    ch = D.sample(model, de, D.MCMCThreads(), 2000)
+    assert abs(ch.mean()[0] - x.mean() * 50 / 51) < 0.05 and abs(ch.mean()[1] - x.std()) < 0.1
+
+
+def test_vector_parameter_gaussian_example(emu):
+    _check_vector_gaussian_example()
