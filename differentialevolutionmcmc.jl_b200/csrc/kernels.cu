@@ -378,7 +378,7 @@ constexpr int PA_THREADS = 128;
 // per-device staging for k_xdot: the proposals' centred means as DMMA B fragments,
 // bfrag[octet of the level][dimension split][k-step j][lane], and the fixed-point magic constant of
 // every particle of the level, magic[level order]
-struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; bool fresh = false; };   // fresh: cleared on its lane's stream just now
+struct XdStage { double *bfrag = nullptr; double *magic = nullptr; size_t cap = 0; bool fresh = false; long long geom = -1; };   // fresh: cleared on its lane's stream just now
 static XdStage g_xs[64][MAX_LANES];
 static XdStage *xd_stage(const ModelDev &m, int n);
 
@@ -861,7 +861,10 @@ static XdStage *xd_stage(const ModelDev &m, int n)
     // the dimension slots that pad a split to whole k-steps must read as zero, and the geometry may
     // change with the model: clear whenever the split between the two arrays moves
     double *magic = x.bfrag + (x.cap - (size_t)((n + SSD_OCT - 1) / SSD_OCT) * SSD_OCT);
-    if (magic != x.magic) {
+    // (the staging buffers outlive the handles: another model's layout leaves its means where this one's padding is)
+    const long long geom = ((long long)m.ssd_k << 40) ^ ((long long)m.ksplit_len << 24) ^ ((long long)m.n_ksplit << 12) ^ ((long long)m.ssd_nj << 4) ^ (long long)m.ssd_half;
+    if (magic != x.magic || geom != x.geom) {
+        x.geom = geom;
         if (cudaMemsetAsync(x.bfrag, 0, sizeof(double) * x.cap, stream()) != cudaSuccess) { g_be_err = "cudaMemset(mean staging)"; return nullptr; }
         x.magic = magic;
         x.fresh = true;
