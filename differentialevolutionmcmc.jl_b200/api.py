@@ -298,6 +298,31 @@ def _flatten(theta):
     return out
 
 
+def _fill_flat(theta, out):
+    """_flatten straight into a row of the state matrix (the P sample_prior() calls of sample_init are the host-side
+    cost of a short run: no lists in between)"""
+    k = 0
+    for v in theta:
+        if isinstance(v, np.ndarray) and v.ndim:
+            n = v.size
+            out[k:k + n] = v if v.ndim == 1 else v.reshape(-1, order="F")
+            k += n
+        elif np.ndim(v):
+            a = np.asarray(v, dtype=np.float64)
+            out[k:k + a.size] = a.reshape(-1, order="F")
+            k += a.size
+        else:
+            out[k] = v
+            k += 1
+
+
+def _draw_states(sample_prior, n, d):
+    out = np.empty((n, d))
+    for p in range(n):
+        _fill_flat(sample_prior(), out[p])
+    return out
+
+
 def _flat_names(names, shapes):
     out = []
     for n, sh in zip(names, shapes):
@@ -423,13 +448,12 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, devices=None
             rows = np.empty((de.n_initial, P, d))
             for p in range(P):
                 for i in range(de.n_initial):
-                    rows[i, p] = _flatten(model.sample_prior())
+                    _fill_flat(model.sample_prior(), rows[i, p])
             h.set_history(rows)
             h.set_state(None)
         else:
             # sample_init (src/main.jl:263-271): one sample_prior() per particle, id order
-            theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)
-            h.set_state(theta0)
+            h.set_state(_draw_states(model.sample_prior, P, d))
         h.run(n_iter)
         de.iter = n_iter + de.n_initial
         # bundle_samples (src/main.jl:222-250) runs on the device: one gather, one download, and the
@@ -464,8 +488,7 @@ def optimize(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
     h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter)
     try:
         P = de.n_groups * de.Np
-        theta0 = np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64)
-        h.set_state(theta0)
+        h.set_state(_draw_states(model.sample_prior, P, d))
         h.run(n_iter)
         de.iter = n_iter
         th, w, ids = h.get_state()

@@ -372,6 +372,57 @@ DE_HD double prior_elem(const Prior &p, double x, double sd_ref)
     return qnan();
 }
 
+#if defined(__CUDACC__)
+// ---- device exp / erfcx for the LBA kernel --------------------------------------------------------------------------
+// CUDA's exp() and erfcx() materialise every polynomial coefficient with two UMOVs: in the LBA trial loop a quarter of the
+// executed instructions were constant moves and the kernel was ISSUE-bound with the fp64 pipe 65 % busy
+// (profiles/r01_v20_k_ll_pointwise_lba_ncu_full_summary.csv).  These two take their coefficients from constant memory as
+// operands of the DFMAs.  de_exp_nonpos: exp(x) for x <= 0 (the kernel's arguments are -n^2/2): 2^k * Taylor_13(r),
+// |r| <= ln2/2, remainder < 4e-18; below -708 it returns 0 (CUDA returns denormals there: < 1e-307 absolute, far under
+// the density floor).  de_erfcx_nonneg: (1 + 2x) erfcx(x) = sum_j c_j t^j, t = (x - 3.75)/(x + 3.75) in [-1, 1)
+// (Shepherd & Laframboise 1981; the Chebyshev series of degree 26 fitted with mpmath at 60 digits and converted to the
+// monomial basis: max coefficient 1.24, so Horner is well conditioned), one reciprocal for both divisions.  Measured
+// against mpmath on [0, 1e8]: <= 2.4 ulp (scipy.special.erfcx: 3.4 ulp); tests/test_device_math.py parses the two tables
+// below and repeats that check with the same arithmetic in numpy.
+__constant__ double DE_ERFCX_C[27] = {
+    1.23751263083782748e+00, -1.40240598585547022e-01, 3.58541548546368986e-03,
+    8.22767384901510190e-02, -1.08803930141707458e-01, 9.23043211601983354e-02,
+    -5.86933985905476185e-02, 2.83622774215155984e-02, -9.74657954761962327e-03,
+    1.75562583242175286e-03, 2.93713594805707372e-04, -2.90153979289867647e-04,
+    5.16494077754639890e-05, 2.23839120365506783e-05, -1.14450491258313085e-05,
+    -9.72849582211122008e-07, 1.75344342511063340e-06, -5.82628107880077700e-08,
+    -2.61147023599009557e-07, 2.42897629254887070e-08, 4.09712231527030054e-08,
+    -4.38928415998632824e-09, -6.54556021248026694e-09, 5.45715730470468752e-10,
+    9.02214970034058998e-10, -3.75315827795962019e-11, -7.33950500852953997e-11
+};
+__constant__ double DE_EXP_C[14] = {
+    1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0,
+    1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0
+};
+__device__ __forceinline__ double de_exp_nonpos(double x)
+{
+    const double kd = __dadd_rn(__fma_rn(x, 1.4426950408889634074, 6755399441055744.0), -6755399441055744.0);   // rint(x log2 e)
+    double r = __fma_rn(kd, -6.93147180369123816490e-01, x);
+    r = __fma_rn(kd, -1.90821492927058770002e-10, r);
+    double p = DE_EXP_C[13];
+#pragma unroll
+    for (int j = 12; j >= 0; --j) p = __fma_rn(p, r, DE_EXP_C[j]);
+    const int k = (int)kd;
+    const double scale = __hiloint2double((k + 1023) << 20, 0);                      // 2^k, k >= -1022
+    return x < -708.0 ? 0.0 : p * scale;                                             // NaN compares false: propagates through p
+}
+__device__ __forceinline__ double de_erfcx_nonneg(double x)
+{
+    const double a = x + 3.75, b = __fma_rn(2.0, x, 1.0);
+    const double r = 1.0 / (a * b);
+    const double t = (x - 3.75) * b * r;
+    double p = DE_ERFCX_C[26];
+#pragma unroll
+    for (int j = 25; j >= 0; --j) p = __fma_rn(p, t, DE_ERFCX_C[j]);
+    return x < 4.0e15 ? p * (a * r) : 0.56418958354775628695 / x;                    // beyond: 1 / (x sqrt(pi)); inf -> 0
+}
+#endif
+
 // ---- per-observation log densities of the "pointwise" kernels ---------------------------------
 // Gaussian (Examples/Gaussian_Example.jl:26-28): logpdf(Normal(mu,sigma), x); par = {mu, sigma, log(sigma)}
 DE_HD double gaussian_obs(const double *par, double x)
@@ -415,8 +466,8 @@ DE_HD double lba_obs(const double *par, int na, double inv_1mpneg, double floor_
     for (int r = 0; r < na; ++r) {
         const double v = par[r];
         const double n1 = q1 - v, n2 = q2 - v;
-        const double e1 = exp(-0.5 * n1 * n1), e2 = exp(-0.5 * n2 * n2);
-        const double t1 = 0.5 * erfcx(fabs(n1) * DE_SQRT1_2) * e1, t2 = 0.5 * erfcx(fabs(n2) * DE_SQRT1_2) * e2;
+        const double e1 = de_exp_nonpos(-0.5 * n1 * n1), e2 = de_exp_nonpos(-0.5 * n2 * n2);
+        const double t1 = 0.5 * de_erfcx_nonneg(fabs(n1) * DE_SQRT1_2) * e1, t2 = 0.5 * de_erfcx_nonneg(fabs(n2) * DE_SQRT1_2) * e2;
         const double c1 = n1 < 0.0 ? t1 : 1.0 - t1, c2 = n2 < 0.0 ? t2 : 1.0 - t2;
         const double p1 = e1 * DE_INV_SQRT2PI, p2 = e2 * DE_INV_SQRT2PI;
         if (r == choice) {
