@@ -478,6 +478,53 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """The same workload, N GPUs, ONE process: what a Julia caller of sample(model, de, n_iter; devices = 0:N-1) gets."""
+    import torch
+
+    import demcmc_b200 as D
+    D._ffi.use_library(D._ffi.DEFAULT_LIB)
+    N = args.gpus
+    G = GROUPS_PER_GPU * N
+    x, prior, lo, hi, theta0 = workload(G)
+    d = N_DIM + 1
+    h = D.Handle(G, NP, d, lo, hi, burnin=0, theta_snooker=THETA_SNOOKER, seed=20261017, devices=list(range(N)))
+    h.set_model("mvnormal", prior, x=x)
+    h.set_state(theta0)
+    h.set_timing(L2_FLUSH_BYTES, False)
+    h.run(args.warmup)
+    c0 = h.counters()
+    t0 = time.perf_counter()
+    h.run(args.steps)
+    wall = time.perf_counter() - t0
+    c1 = h.counters()
+    h.set_timing(0, False)
+    h.run(args.steps)
+    c2 = h.counters()
+    h.close()
+    updates = c1["particle_updates"] - c0["particle_updates"]
+    rng = np.random.default_rng(7)
+    model = D.DEModel(sample_prior=lambda: [rng.normal(size=N_DIM), abs(rng.standard_cauchy())], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                      loglike=D.GPULoglike("mvnormal", x), names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=G, Np=NP, burnin=0, θsnooker=THETA_SNOOKER, seed=11)
+    D.sample(model, de, min(args.steps, 16), devices=list(range(N)))
+    t0 = time.perf_counter()
+    chains = D.sample(model, de, args.steps, devices=list(range(N)))
+    t_e2e = time.perf_counter() - t0
+    assert chains.value.shape == (args.steps, d + 2, G * NP)
+    line = {"metric": METRIC, "value": updates / (c1["device_ms"] * 1e-3), "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": c1["device_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(), "groups_total": G, "particles_total": G * NP,
+                       "parallelism": f"ONE process, one multi-device handle over {N} GPU(s): a host thread per GPU, migration through peer-mapped mailboxes",
+                       "timing": "device_ms = the slowest device's CUDA-event time (L2 flushed between segments)"},
+            "value_wall": updates / wall, "value_steady_no_flush": (c2["particle_updates"] - c1["particle_updates"]) / (c2["device_ms"] * 1e-3),
+            "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+            "migration": {"cross_device": int(c1["cross_migrations"] - c0["cross_migrations"]), "through_mailboxes": int(c1["mailbox_events"] - c0["mailbox_events"])},
+            "e2e": {"value": G * NP * args.steps / t_e2e, "unit": UNIT, "seconds": t_e2e, "h2d_bytes_per_step": (N * x.nbytes + G * NP * d * 8) / args.steps,
+                    "d2h_bytes_per_step": G * NP * (d + 2) * 8, "call": "sample(model, de, n_iter, devices=[0..N-1]) from one process, host data in, Chains out"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -487,6 +534,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the companion numbers of the other BASELINE shapes")
+    ap.add_argument("--single-process", action="store_true",
+                    help="python bench.py --gpus N --single-process: ONE process drives the N GPUs through a multi-device handle (demcmc_config.n_devices) instead of one torchrun rank per GPU")
     # the same step on another BASELINE shape (the contract's line is the default, configs[1]); configs[4] is
     # --dim 100 --particles 4096 --groups-per-gpu 8 on 8 GPUs
     ap.add_argument("--dim", type=int, default=None, help="dimensions of the multivariate normal (default 50)")
@@ -504,6 +553,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_b200(args)
 
