@@ -407,7 +407,7 @@ static int multi_get_chains(demcmc_handle *p, int64_t row0, int64_t n_rows, doub
     double *dout = (double *)be::dmalloc(sizeof(double) * n);
     int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * Pt);
     int rc = 0;
-    if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging does not fit on device %d", k0->cfg.device);
+    if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging (%zu MB) does not fit on device %d: %s", sizeof(double) * n >> 20, k0->cfg.device, be::last_error());
     if (!rc && (be::dzero(dout, sizeof(double) * n) || be::sync())) rc = DEMCMC_ECUDA;
     for (int phase = 1; phase <= 2 && !rc; ++phase)           // every device's final positions first, then the rows
         for (demcmc_handle *k : p->kids) {

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .api import DE, DEModel, MCMCThreads, _flatten, build_handle, bundle_samples, resample
+from .api import DE, DEModel, MCMCThreads, _draw_states, _flatten, build_handle, bundle_samples, resample
 from .handle import comm_unique_id
 
 
@@ -18,24 +18,50 @@ last_counters = None
 
 
 def _gather_arrays(dist, part, rank, world, device):
-    """Every rank's tuple of equally shaped numpy arrays -> list of tuples on rank 0.  With the NCCL backend the arrays
-    travel as device tensors over NVLink (pickling 80 MB per rank through gather_object took longer than the run);
-    the gloo backend of the CPU tests gathers the objects."""
+    """Every rank's tuple of equally shaped numpy arrays -> on rank 0, a tuple of arrays concatenated along axis 1 (the
+    particle positions, in rank order).  With the NCCL backend they travel as device tensors over NVLink and STAY on
+    rank 0's GPU as torch tensors (pickling 80 MB per rank through gather_object took longer than the run); the gloo
+    backend of the CPU tests gathers the objects."""
     if dist.get_backend() != "nccl":
         parts = [None] * world if rank == 0 else None
         dist.gather_object(part, parts, dst=0)
-        return parts
+        if rank != 0:
+            return None
+        return tuple(np.concatenate([p[i] for p in parts], axis=1) for i in range(len(part)))
     import torch
     dev = torch.device("cuda", device)
-    out = [[] for _ in range(world)]
+    out = []
     for a in part:
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
         dist.gather(t, bufs, dst=0)
         if rank == 0:
-            for r in range(world):
-                out[r].append(bufs[r].cpu().numpy())
-    return [tuple(o) for o in out] if rank == 0 else None
+            out.append(torch.cat(bufs, dim=1))
+    return tuple(out) if rank == 0 else None
+
+
+def _merge_by_id(th, w, ids, acc, n_iter, P, d):
+    """de.samples[row, :, id] (utilities.jl:161-180): ids travel with the particles through migration.  numpy on the
+    host, or -- when the gathered history is still on rank 0's GPU -- torch index_put there and one download."""
+    if isinstance(th, np.ndarray):
+        rows = np.arange(n_iter)[:, None]
+        samples = np.empty((P, d, n_iter))
+        lp = np.empty((P, n_iter))
+        accept = np.empty((P, n_iter), dtype=np.uint8)
+        samples[ids, :, rows] = th
+        lp[ids, rows] = w
+        accept[ids, rows] = acc
+        return samples, lp, accept, ids[-1]
+    import torch
+    idl = ids.long()
+    rows = torch.arange(n_iter, device=th.device)[:, None].expand_as(idl)
+    samples = torch.empty((P, d, n_iter), dtype=th.dtype, device=th.device)
+    samples[idl, :, rows] = th
+    lp = torch.empty((P, n_iter), dtype=w.dtype, device=th.device)
+    lp[idl, rows] = w
+    accept = torch.empty((P, n_iter), dtype=acc.dtype, device=th.device)
+    accept[idl, rows] = acc
+    return samples.cpu().numpy(), lp.cpu().numpy(), accept.cpu().numpy(), ids[-1].cpu().numpy()
 
 
 def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
@@ -87,7 +113,7 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
             h.set_state(None)
         else:
             # sample_init (src/main.jl:263-271): one sample_prior() per particle in id order -- drawn once, on rank 0
-            box = [np.array([_flatten(model.sample_prior()) for _ in range(P)], dtype=np.float64) if rank == 0 else None]
+            box = [_draw_states(model.sample_prior, P, d) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             h.set_state(box[0][rank * P_local:(rank + 1) * P_local])
         h.run(n_iter)
@@ -100,18 +126,10 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
         h.close()
     if rank != 0:
         return None
-    th = np.concatenate([p[0] for p in parts], axis=1)       # [n][P][d]
-    w = np.concatenate([p[1] for p in parts], axis=1)
-    ids = np.concatenate([p[2] for p in parts], axis=1)
-    acc = np.concatenate([p[3] for p in parts], axis=1)
-    # de.samples[row, :, id] (utilities.jl:161-180): ids travel with the particles through migration
-    rows = np.arange(n_iter)[:, None]
-    samples = np.empty((P, d, n_iter))
-    lp = np.empty((P, n_iter))
-    accept = np.empty((P, n_iter), dtype=np.uint8)
-    samples[ids, :, rows] = th
-    lp[ids, rows] = w
-    accept[ids, rows] = acc
+    th, w, ids, acc = parts                                  # [n][P][d], [n][P] x 3 -- by position, ranks side by side
+    if not isinstance(th, np.ndarray):
+        return _bundle_on_gpu(model, de, th, w, ids, acc, init_rows, shapes, n_iter, P, d)
+    samples, lp, accept, final_ids = _merge_by_id(th, w, ids, acc, n_iter, P, d)
     if init_rows is not None:
         # rows 1..n_initial of de.samples are the prior draws (utilities.jl:35-39); bundle_samples then keeps
         # rows burnin+1..n_iter of the n_iter + n_initial array -- not shifted by n_initial (main.jl:226-234)
@@ -120,4 +138,37 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
         lp = np.concatenate([np.zeros((P, n0)), lp], axis=1)
         accept = np.concatenate([np.zeros((P, n0), dtype=np.uint8), accept], axis=1)
     de.samples = samples
-    return bundle_samples(model, de, samples, accept, lp, ids[-1], shapes, n_iter)
+    return bundle_samples(model, de, samples, accept, lp, final_ids, shapes, n_iter)
+
+
+def _bundle_on_gpu(model, de, th, w, ids, acc, init_rows, shapes, n_iter, P, d):
+    """The by-id merge and bundle_samples (src/main.jl:222-250, by-position quirk of "acceptance" / "lp" included) as
+    index operations on rank 0's GPU, where the gathered history already is; ONE download of the array the Chains wrap,
+    in the memory order the single-GPU sample() returns (chain, column, draw) so no host-side transpose is needed."""
+    import torch
+    from .api import Chains, _flat_names
+    dev = th.device
+    idl = ids.long()
+    rows = torch.arange(n_iter, device=dev)[:, None].expand_as(idl)
+    n0 = de.n_initial if init_rows is not None else 0
+    samples = torch.empty((P, d, n0 + n_iter), dtype=th.dtype, device=dev)
+    lp = torch.zeros((P, n0 + n_iter), dtype=w.dtype, device=dev)
+    accept = torch.zeros((P, n0 + n_iter), dtype=torch.float64, device=dev)
+    samples[idl, :, rows + n0] = th
+    lp[idl, rows + n0] = w
+    accept[idl, rows + n0] = acc.double()
+    if n0:
+        samples[:, :, :n0] = torch.from_numpy(np.ascontiguousarray(init_rows.transpose(1, 2, 0))).to(dev)
+    Ns = n_iter - de.burnin if de.discard_burnin else n_iter
+    offset = de.burnin if de.discard_burnin else 0
+    Ns = max(Ns, 0)
+    arr = torch.empty((P, d + 2, Ns), dtype=th.dtype, device=dev)
+    if Ns > 0:
+        final_ids = idl[-1]
+        arr[:, :d, :] = samples[:, :, offset:offset + Ns]
+        arr[:, d, :] = accept[final_ids, offset:offset + Ns]
+        arr[:, d + 1, :] = lp[final_ids, offset:offset + Ns]
+    host = arr.cpu().numpy()
+    de.samples = host[:, :d, :]
+    names = _flat_names(model.names, shapes) + ["acceptance", "lp"]
+    return Chains(host.transpose(2, 1, 0), names, [str(n) for n in model.names])
