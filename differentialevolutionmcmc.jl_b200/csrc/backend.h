@@ -15,7 +15,9 @@ int device_count();
 int set_device(int dev);                  // 0 or error
 const char *last_error();
 
-void *dmalloc(size_t bytes);              // nullptr on failure
+void *dmalloc(size_t bytes);              // nullptr on failure (stream-ordered pool)
+void *dmalloc_shared(size_t bytes);       // plain device memory that peers write into (the outputs a multi-device handle assembles on one GPU)
+void dfree_shared(void *p);
 void dfree(void *p);
 void *hmalloc_pinned(size_t bytes);
 void hfree_pinned(void *p);

@@ -371,9 +371,9 @@ static int multi_history_out(demcmc_handle *p, double *samples, double *lp, uint
     const size_t Pt = p->P, d = p->d;
     double *ds = nullptr, *dl = nullptr; uint8_t *da = nullptr;
     int rc = 0;
-    if (samples) ds = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * Pt * d));
-    if (lp) dl = (double *)be::dmalloc(sizeof(double) * std::max<size_t>(1, n_rows * Pt));
-    if (accept) da = (uint8_t *)be::dmalloc(std::max<size_t>(1, n_rows * Pt));
+    if (samples) ds = (double *)be::dmalloc_shared(sizeof(double) * std::max<size_t>(1, n_rows * Pt * d));
+    if (lp) dl = (double *)be::dmalloc_shared(sizeof(double) * std::max<size_t>(1, n_rows * Pt));
+    if (accept) da = (uint8_t *)be::dmalloc_shared(std::max<size_t>(1, n_rows * Pt));
     const bool lp_written = p->cfg.update == DEMCMC_UPDATE_MH;
     if ((samples && !ds) || (lp && !dl) || (accept && !da)) rc = fail(DEMCMC_ENOMEM, "output staging does not fit on device %d", k0->cfg.device);
     if (!rc && n_rows > 0) {
@@ -392,7 +392,7 @@ static int multi_history_out(demcmc_handle *p, double *samples, double *lp, uint
         if (rc == DEMCMC_ECUDA) fail(rc, "history gather: %s", be::last_error());
     }
     be::set_device(k0->cfg.device);
-    be::dfree(ds); be::dfree(dl); be::dfree(da);
+    be::dfree_shared(ds); be::dfree_shared(dl); be::dfree_shared(da);
     return rc;
 }
 
@@ -404,8 +404,8 @@ static int multi_get_chains(demcmc_handle *p, int64_t row0, int64_t n_rows, doub
     if (n_rows == 0) return 0;
     BE(be::set_device(k0->cfg.device));
     const size_t Pt = p->P, d = p->d, n = (size_t)n_rows * Pt * (d + 2);
-    double *dout = (double *)be::dmalloc(sizeof(double) * n);
-    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * Pt);
+    double *dout = (double *)be::dmalloc_shared(sizeof(double) * n);
+    int32_t *pos = (int32_t *)be::dmalloc_shared(sizeof(int32_t) * Pt);
     int rc = 0;
     if (!dout || !pos) rc = fail(DEMCMC_ENOMEM, "chain staging (%zu MB) does not fit on device %d: %s", sizeof(double) * n >> 20, k0->cfg.device, be::last_error());
     if (!rc && (be::dzero(dout, sizeof(double) * n) || be::sync())) rc = DEMCMC_ECUDA;
@@ -419,7 +419,7 @@ static int multi_get_chains(demcmc_handle *p, int64_t row0, int64_t n_rows, doub
     if (!rc && (be::set_device(k0->cfg.device) || be::d2h(out, dout, sizeof(double) * n))) rc = DEMCMC_ECUDA;
     if (rc == DEMCMC_ECUDA) fail(rc, "chain gather: %s", be::last_error());
     be::set_device(k0->cfg.device);
-    be::dfree(dout); be::dfree(pos);
+    be::dfree_shared(dout); be::dfree_shared(pos);
     return rc;
 }
 
@@ -1329,7 +1329,7 @@ int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, doubl
     // ids migrate between the shards of a job: every shard marks, in ONE map on the first device, where the ids it holds
     // sit at every row; the first device then gathers every chain through the map (peer access) and reduces
     BE(be::set_device(h0->cfg.device));
-    int32_t *pos = (int32_t *)be::dmalloc(sizeof(int32_t) * (size_t)n_rows * Pt);
+    int32_t *pos = (int32_t *)be::dmalloc_shared(sizeof(int32_t) * (size_t)n_rows * Pt);
     double *agg = (double *)be::dmalloc(sizeof(double) * na);
     std::vector<double> total(na);
     int rc = (!pos || !agg) ? fail(DEMCMC_ENOMEM, "diagnostics staging") : 0;
@@ -1346,7 +1346,7 @@ int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, doubl
     if (!rc && (be::set_device(h0->cfg.device) || be::launch_diag_aggregates(sh, pos, row0, n_rows, Pt, d, n_lag, agg) ||
                 be::d2h(total.data(), agg, sizeof(double) * na))) rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error());
     be::set_device(h0->cfg.device);
-    be::dfree(pos); be::dfree(agg);
+    be::dfree_shared(pos); be::dfree(agg);
     if (rc) return rc;
     diag_finish(total.data(), d, n_lag, nh, 2 * (int64_t)Pt, rhat, ess);
     return 0;

@@ -224,6 +224,16 @@ void *dmalloc(size_t bytes)
     return p;
 }
 void dfree(void *p) { if (p) cudaFreeAsync(p, stream()); }
+// outside the pool: cudaDeviceEnablePeerAccess covers it directly (a 662 MB pool allocation that seven peers must map
+// failed with "out of memory" on an 8-GPU box)
+void *dmalloc_shared(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) { cu_fail(e, "cudaMalloc"); return nullptr; }
+    return p;
+}
+void dfree_shared(void *p) { if (p) { cudaStreamSynchronize(stream()); cudaFree(p); } }
 // pinned blocks are recycled through a small free list for the same reason
 struct PinnedBlock { void *p; size_t bytes; bool busy; };
 static std::vector<PinnedBlock> g_pinned;

@@ -33,6 +33,8 @@ int device_count() { return 1; }
 int set_device(int) { return 0; }
 void *dmalloc(size_t b) { return calloc(1, b ? b : 8); }
 void dfree(void *p) { free(p); }
+void *dmalloc_shared(size_t b) { return calloc(1, b ? b : 8); }
+void dfree_shared(void *p) { free(p); }
 void *hmalloc_pinned(size_t b) { return calloc(1, b ? b : 8); }
 void hfree_pinned(void *p) { free(p); }
 int h2d(void *d, const void *s, size_t b) { if (b) memcpy(d, s, b); return 0; }
