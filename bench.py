@@ -136,7 +136,7 @@ class ClockSampler:
 def ncu_traffic(persistent=False):
     """dram bytes read + written per launch of the dominant kernel from the committed `ncu --set full` capture."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_k_chunk_persist_traffic.json" if persistent else "r01_k_xdot_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_k_chunk_persist_traffic.json" if persistent else "r01_k_xdot_traffic.json")))
         return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
     except (OSError, KeyError, ValueError):
         return None

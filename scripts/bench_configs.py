@@ -81,10 +81,11 @@ def config(name):
     raise KeyError(name)
 
 
-# fp64 warp-instructions the LBA kernel executes per (trial x particle) density, from the committed ncu capture
-# (profiles/: smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on / 32 / densities); the fp64 pipe issues
-# 64 lanes per SM per clock = 2 warp-instructions, i.e. peak_dfma_tflops / 2 / 32 warp-instructions per second
-LBA_FP64_WARP_INST_PER_DENSITY = None      # filled in from the r02 capture (see profiles/README.md)
+# fp64 instructions (DFMA + DMUL + DADD, thread level) the LBA kernel executes per (trial x particle) density, from the
+# committed ncu capture profiles/r02_v8_k_ll_pointwise_lba_ncu_full_summary.csv: 742.9 M warp instructions for a level of
+# 344 particles x 1e5 trials, 48.6 % of them fp64 => 336 per density.  The fp64 CUDA-core pipe retires peak_dfma / 2
+# of them per second (one DFMA = 2 flop), which is the denominator of the instruction roofline below.
+LBA_FP64_INST_PER_DENSITY = 336.0
 
 
 def run(name, iters=None, peaks=None, hbm_gbs=None):
@@ -131,11 +132,12 @@ def run(name, iters=None, peaks=None, hbm_gbs=None):
         line["roofline"] = {"bound": "latency", "note": "24 particles x 50 observations: one fused launch per dependency level; nothing to saturate"}
     elif name == "c3":
         dens = ups * 100_000
-        line["roofline"] = {"bound": "fp64 pipe (transcendental)", "trial_densities_per_s": dens, "unit": "fp64 warp-instructions/s"}
-        if LBA_FP64_WARP_INST_PER_DENSITY and peaks:
-            peak_wi = max(peaks) * 1e12 / 2.0 / 32.0
-            line["roofline"].update(achieved=dens * LBA_FP64_WARP_INST_PER_DENSITY / 32.0, peak=peak_wi,
-                                    frac=dens * LBA_FP64_WARP_INST_PER_DENSITY / 32.0 / peak_wi)
+        line["roofline"] = {"bound": "fp64 pipe (transcendental)", "trial_densities_per_s": dens, "unit": "fp64 instructions/s",
+                            "fp64_instructions_per_density": LBA_FP64_INST_PER_DENSITY}
+        if peaks:
+            peak_i = peaks[0] * 1e12 / 2.0
+            line["roofline"].update(achieved=dens * LBA_FP64_INST_PER_DENSITY, peak=peak_i, frac=dens * LBA_FP64_INST_PER_DENSITY / peak_i,
+                                    note="instruction roofline of the fp64 CUDA-core pipe (DFMA-loop peak / 2 instructions per second); ncu of the same kernel: sm__pipe_fp64_cycles_active 75.8 %")
     elif name == "c4" and hbm_gbs:
         gbs = ups * 64.0 * c["d"] / 1e9              # propose (4 reads + 1 write) + accept (1 read + 2 writes) of d doubles
         line["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
