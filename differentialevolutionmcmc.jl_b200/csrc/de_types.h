@@ -20,13 +20,6 @@ DE_HD bool is_ssd(int kind) { return kind == M_MVNORMAL || kind == M_HIER || kin
 enum { UPDATE_MH = 0, UPDATE_MAXIMIZE = 1, UPDATE_MINIMIZE = 2 };
 enum { FITNESS_POSTERIOR = 0, FITNESS_FUN = 1 };
 
-// A run of consecutive flattened parameters with the same bounds and the same prior spec -- in practice one NAMED
-// parameter (bounds and priors are per named parameter: src/utilities.jl:70-78).  The per-element tables cost 56 bytes of
-// loads per element per proposal (d = 1003: 56 KB per particle update, seven times the parameter vector itself); a
-// handful of segments sit in a few cache lines.
-struct Seg { int32_t begin, end; double lo, hi; Prior pr; };
-constexpr int MAX_SEG = 16;
-
 // The registered likelihood a handle is bound to (GPULoglike), device-resident.
 struct ModelDev {
     int32_t kind, d;
@@ -60,8 +53,6 @@ struct ModelDev {
     double lba_floor;
     double binom_N, binom_k;
     const Prior *prior;       // [d]
-    const Seg *segs;          // [n_seg] the same bounds + priors as runs of equal elements, or n_seg = 0 (more than MAX_SEG runs)
-    int32_t n_seg;
     int32_t prior_has_ref;    // some prior reads another parameter (NORMAL_REF): priors need the whole proposal
     // partition of the likelihood sum: slice s covers observations [s*split_len, ...) x dimension
     // split; fixed by the model alone so the summation order never depends on the GPU count or on

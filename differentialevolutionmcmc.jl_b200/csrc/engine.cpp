@@ -621,24 +621,6 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
     }
     D.prior = (const Prior *)upload(pr.data(), sizeof(Prior) * pr.size(), false);
     if (!D.prior) return fail(DEMCMC_ENOMEM, "prior upload failed");
-    {   // runs of equal (bounds, prior spec): one per named parameter in practice (de_types.h: Seg)
-        std::vector<Seg> segs;
-        auto same = [&](int a, int b) {
-            return ((h->lo[a] == h->lo[b]) || (h->lo[a] != h->lo[a] && h->lo[b] != h->lo[b])) && ((h->hi[a] == h->hi[b]) || (h->hi[a] != h->hi[a] && h->hi[b] != h->hi[b])) &&
-                   pr[a].kind == pr[b].kind && pr[a].ref == pr[b].ref && pr[a].a == pr[b].a && pr[a].b == pr[b].b;
-        };
-        for (int k = 0; k < m->d; ++k) {
-            if (!segs.empty() && same(segs.back().begin, k)) { segs.back().end = k + 1; continue; }
-            Seg sg; sg.begin = k; sg.end = k + 1; sg.lo = h->lo[k]; sg.hi = h->hi[k]; sg.pr = pr[k];
-            segs.push_back(sg);
-        }
-        const char *e = getenv("DEMCMC_NO_SEGMENTS");             // A/B runs and the equivalence test
-        if ((int)segs.size() <= MAX_SEG && !(e && e[0] == '1')) {
-            D.segs = (const Seg *)upload(segs.data(), sizeof(Seg) * segs.size(), false);
-            if (!D.segs) return fail(DEMCMC_ENOMEM, "segment table upload failed");
-            D.n_seg = (int32_t)segs.size();
-        }
-    }
     const bool dev = m->data_on_device != 0;
     D.n_osplit = 1; D.n_ksplit = 1; D.split_len = 0; D.ksplit_len = 0;
     if (m->kind == DEMCMC_RASTRIGIN) {
