@@ -255,8 +255,11 @@ def run_b200(args):
         uuid = str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
         uuid = None
-    clocks = ClockSampler(local, uuid)
-    clocks.start()
+    # rank 0 samples its GPU (the line reports rank 0's clocks); NVML queries take a driver-wide lock, and eight
+    # processes polling at 500 Hz each get in the way of each other's kernel launches
+    clocks = ClockSampler(local, uuid) if rank == 0 else None
+    if clocks:
+        clocks.start()
     barrier()
     t0 = time.time()
     h.run(args.steps)
@@ -315,7 +318,7 @@ def run_b200(args):
         windows.append((tw, time.time(), "sufficient-statistic pass"))
         ms_suff = h.counters()["device_ms"]
         h.set_sufficient_stat(False)
-    ck = clocks.stop(windows)
+    ck = clocks.stop(windows) if clocks else None
     h.close()
 
     # ---- roofline of the dominant kernel (k_ssd, the likelihood) ----------------------------------
