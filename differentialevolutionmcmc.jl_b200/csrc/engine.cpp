@@ -483,7 +483,7 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->d = cfg->d;
     h->n0 = cfg->n_initial;
     h->k_store = std::max(1, cfg->store_every);
-    h->n_scratch = h->k_store > 1 ? MAX_CHUNK + 2 : 3;
+    h->n_scratch = (h->k_store > 1 || cfg->n_blocks > 0) ? MAX_CHUNK + 2 : 3;      // chunks of overlapped block sweeps write scratch rows too
     if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), 2));   // A/B measurements
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
@@ -932,7 +932,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         return a >= (int64_t)h->block_on.size() || h->block_on[(size_t)a] != 0;
     };
     int64_t sweeps_run = 0;
-    auto run_chunk = [&](int64_t it0, int b, int n_sw, bool blocked) -> int {
+    auto run_chunk = [&](int64_t it0, int b0, int n_sw, bool blocked) -> int {
         sweeps_run += n_sw;
         const int64_t itg0 = h->iters_done + it0;
         Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
@@ -941,7 +941,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         bool basedep[MAX_CHUNK];
         Row cur = cur_row(h);
         for (int s = 0; s < n_sw; ++s) {
-            const int64_t it = it0 + (blocked ? 0 : s), itg = itg0 + (blocked ? 0 : s);
+            // a chunk of blocked sweeps walks the blocks of consecutive iterations: sweep s is block (b0 + s) % B of
+            // iteration it0 + (b0 + s) / B; an unblocked chunk holds one sweep per iteration
+            const int b = blocked ? (b0 + s) % B : 0;
+            const int64_t it = it0 + (blocked ? (b0 + s) / B : s), itg = itg0 + (blocked ? (b0 + s) / B : s);
             const bool last = !blocked || b == B - 1;             // this sweep completes its iteration
             const int64_t s_local = it * B + b;
             const bool inb = in_burnin_at(it);
@@ -1003,7 +1006,8 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const int g0 = (ln * G + n_lanes - 1) / n_lanes, g1 = ((ln + 1) * G + n_lanes - 1) / n_lanes;   // contiguous sets of groups
             PlanInput pin;
             pin.seed = cfg.seed; pin.Np = Np; pin.G_local = g1 - g0; pin.group_begin = cfg.group_begin + g0; pin.G_total = Gt;
-            pin.pos_offset = g0 * Np; pin.P_stride = blocked ? P : P * B;   // consecutive sweeps of an unblocked chunk are consecutive iterations
+            pin.pos_offset = g0 * Np; pin.P_stride = blocked ? P : P * B;   // consecutive sweeps of an unblocked chunk are consecutive iterations;
+                                                                            // those of a blocked one are consecutive blocks (adjacent in the tape)
             pin.sweep_stride = blocked ? 1 : B;
             {
                 const char *e = getenv("DEMCMC_SHAPE");       // 0 = off, else the modulus (A/B runs)
@@ -1011,10 +1015,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 pin.shape_octets = (is_ssd(h->dmodel.kind)) ? std::max(0, mod) : 0;
             }
             pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
-            const int64_t s_first = it0 * B + b;
+            const int64_t s_first = it0 * B + (blocked ? b0 : 0);
             pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // a chunk of several sweeps is unblocked: its sweeps are P_stride apart in the tape
             pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
-            plan_chunk(pin, (uint32_t)((h->iter_offset + itg0) * B + b), n_sw, basedep, plans[ln]);
+            plan_chunk(pin, (uint32_t)((h->iter_offset + itg0) * B + (blocked ? b0 : 0)), n_sw, basedep, plans[ln]);
             const ChunkPlan &pl = plans[ln];
             memcpy(u.h_order + lane_off[ln], pl.order.data(), sizeof(int32_t) * pl.order.size());
             lane_off[ln + 1] = lane_off[ln] + (int32_t)pl.order.size();
@@ -1167,11 +1171,34 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         }
 
         // ---- update! (main.jl:161-167) -------------------------------------------------------------
-        if (blocking_at(it)) {                        // blocking: every block is one sweep, one chunk each
-            for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1, true)) { cleanup(); return rc; }
-            if (ghist && h->cur_hist >= 0) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
+        if (blocking_at(it)) {
+            // blocking (main.jl:174-179): every block is one sweep.  Consecutive block sweeps -- the blocks of this
+            // iteration and of the blocked iterations that follow it without a migration in between -- overlap on the
+            // device like the sweeps of unblocked iterations do (the tail levels of one sweep share launches with the
+            // head levels of the next).  A sweep whose select_base needs the sweep-start weights, and DE-MCz donors
+            // (rows of earlier sweeps), keep one sweep per chunk.
+            if (needs_snapshot(it) || cfg.donors || h->max_chunk <= 1) {
+                for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1, true)) { cleanup(); return rc; }
+                if (ghist && h->cur_hist >= 0) if (int rc = gather_row(h, h->cur_hist)) { cleanup(); return rc; }
+                if (int rc = seg_end()) { cleanup(); return rc; }
+                ++it;
+                continue;
+            }
+            const int cap_sweeps = (int)std::min<int64_t>(h->max_chunk, (int64_t)2 << std::min<int64_t>(chunks_this_call, 8));
+            ++chunks_this_call;
+            int n_it = 1;
+            MigSchedule m2;
+            while (it + n_it < n_iter && (n_it + 1) * B <= std::max(cap_sweeps, B)) {
+                get_mig(it + n_it, m2);
+                if (m2.migrate || needs_snapshot(it + n_it) || !blocking_at(it + n_it)) break;
+                ++n_it;
+            }
+            if (n_it * B > MAX_CHUNK) {                          // more blocks than a chunk holds: one sweep per chunk
+                for (int b = 0; b < B; ++b) if (int rc = run_chunk(it, b, 1, true)) { cleanup(); return rc; }
+                n_it = 1;
+            } else if (int rc = run_chunk(it, 0, n_it * B, true)) { cleanup(); return rc; }
             if (int rc = seg_end()) { cleanup(); return rc; }
-            ++it;
+            it += n_it;
             continue;
         }
         // consecutive iterations without a migration and without a sweep-start snapshot overlap on

@@ -647,3 +647,23 @@ def test_full_covariance_mvn_kernel():
 
 def test_vector_parameter_gaussian_example():   # Examples/Guassian_Example_Vector.jl
     E._check_vector_gaussian_example()
+
+
+@pytest.mark.parametrize("kw", [dict(alpha=0.3), dict(alpha=0.0, proposal="fixed_gamma", kappa=0.8), dict(alpha=0.2, store_every=3)])
+def test_overlapped_block_sweeps_are_a_schedule_only(kw):
+    E.test_overlapped_block_sweeps_are_a_schedule_only(None, kw)
+
+
+def test_overlapped_block_sweeps_wide_kernels():
+    """the configs[3] shape in small: 300 subjects (d = 303: the one-CTA-per-particle kernels), two blocks"""
+    rng = np.random.default_rng(2)
+    case = make_case("hier_normal", rng, n_subjects=300)
+    th0 = case.theta0(rng, 4 * 24)
+    outs = []
+    for chunk in (1, 16):
+        with case.handle(4, 24, seed=6, burnin=0, blocks=hier_blocks(300), alpha=0.2) as h:
+            h.set_max_chunk(chunk)
+            h.set_state(th0)
+            h.run(12)
+            outs.append((h.samples(), h.accept(), h.counters()["levels"]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[1][2] < outs[0][2]

@@ -674,3 +674,29 @@ def _check_vector_gaussian_example():
 
 def test_vector_parameter_gaussian_example(emu):
     _check_vector_gaussian_example()
+
+
+@pytest.mark.parametrize("kw", [dict(alpha=0.3), dict(alpha=0.0, proposal="fixed_gamma", kappa=0.8), dict(alpha=0.2, store_every=3)])
+def test_overlapped_block_sweeps_are_a_schedule_only(emu, kw):
+    """blocking_on: the block sweeps of consecutive iterations share a chunk (their dependency levels overlap); one sweep
+    per chunk (max_chunk = 1) must give the same chain bit for bit -- native draws and replayed ones"""
+    rng = np.random.default_rng(14)
+    case = make_case("hier_normal", rng)
+    G, Np, n_iter = 3, 8, 21
+    th0 = case.theta0(rng, G * Np)
+    outs = []
+    for chunk in (1, 16, 5):
+        with case.handle(G, Np, seed=6, burnin=4, blocks=hier_blocks(9), proposal=kw.get("proposal", "random_gamma"),
+                         **{k: v for k, v in kw.items() if k != "proposal"}) as h:
+            h.set_max_chunk(chunk)
+            h.set_state(th0)
+            h.run(9)
+            h.run(n_iter - 9)
+            outs.append((h.samples(), h.accept(), h.lp(), h.get_state(), h.counters()["levels"]))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+        assert all(np.array_equal(a, b) for a, b in zip(o[3], outs[0][3]))
+    assert outs[1][4] < outs[0][4]                         # fewer, fuller levels
+    # replay through overlapped block sweeps against the oracle
+    r, out = compare_run(case, 2, 6, 7, "replay", seed=3, burnin=3, blocks=hier_blocks(9), proposal="fixed_gamma")
+    assert np.array_equal(out["accept"], r["accept"])
