@@ -155,6 +155,7 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 def cpu_updates_per_s(steps, warmup, budget_s=100.0):
     from oracle import oracle as O
+    O.set_plain_sums(True)     # the timing variant of the restatement: plain fp64 sums, not the compensated ones of the parity oracle
     x, prior, lo, hi, _ = workload(GROUPS_PER_GPU)
     model = O.Model("mvnormal", N_DIM + 1, prior, x=x)
     cores = min(GROUPS_PER_GPU, os.cpu_count() or 1)
@@ -194,7 +195,7 @@ def run_reference(args):
             "config": {"workload": workload_string(), "groups_total": GROUPS_PER_GPU, "particles_total": GROUPS_PER_GPU * NP,
                        "note": "the CPU arm always runs ONE GPU's share of the job (4 groups): at --gpus N > 1 the B200 arm runs N times as many groups, so only the N = 1 ratio compares like with like"},
             "cpu_baseline": {"value": ups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "note": "C restatement of the reference's algorithm (oracle/), one thread per group; the reference itself is Julia and cannot run in this image"},
+                             "note": "C restatement of the reference's algorithm (oracle/) with plain fp64 sums, one thread per group = the reference's own parallel width (ThreadsX.map over groups, src/main.jl:135-148); the reference itself is Julia and cannot run in this image (julia/cpu_baseline.jl is the script for where it can)"},
             "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

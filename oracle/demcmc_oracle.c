@@ -122,8 +122,34 @@ static double ll_gaussian(const orc_model *m, const double *th)
 
 /* Examples/Multivariate_Guassian_Example.jl:31-33: sum(logpdf(MvNormal(mu, sigma^2 I), data));
  * per column -(d*log2pi + d*log(sigma^2))/2 - sqmahal/2, sqmahal = sum((x-mu)^2)/sigma^2 */
+/* The timing variant (orc_set_plain_sums(1), bench.py's CPU arm only): plain fp64 accumulation in four independent
+ * partial sums per row -- what Distributions' sqmahal + Julia's sum compile to -- instead of the compensated sums the
+ * parity oracle uses to sit within 1e-12 of both Julia and the device.  Same formula, ~3x the speed. */
+static int g_plain_sums = 0;
+void orc_set_plain_sums(int on) { g_plain_sums = on; }
+static double ll_mvnormal_plain(const orc_model *m, const double *th)
+{
+    int dm = m->n_dim;
+    double sig = th[dm], s2 = sig * sig;
+    double c0 = -((double)dm * LOG2PI + (double)dm * log(s2)) / 2.0;
+    double total = 0.0;
+    for (int64_t i = 0; i < m->n_obs; ++i) {
+        const double *x = m->x + i * dm;
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        int k = 0;
+        for (; k + 3 < dm; k += 4) {
+            double t0 = x[k] - th[k], t1 = x[k + 1] - th[k + 1], t2 = x[k + 2] - th[k + 2], t3 = x[k + 3] - th[k + 3];
+            q0 += t0 * t0; q1 += t1 * t1; q2 += t2 * t2; q3 += t3 * t3;
+        }
+        for (; k < dm; ++k) { double t = x[k] - th[k]; q0 += t * t; }
+        total += c0 - (((q0 + q1) + (q2 + q3)) / s2) / 2.0;
+    }
+    return total;
+}
+
 static double ll_mvnormal(const orc_model *m, const double *th)
 {
+    if (g_plain_sums) return ll_mvnormal_plain(m, th);
     int dm = m->n_dim;
     double sig = th[dm], s2 = sig * sig;
     double c0 = -((double)dm * LOG2PI + (double)dm * log(s2)) / 2.0;

@@ -145,6 +145,8 @@ int orc_run(const orc_config *cfg, const orc_model *model, const double *theta0,
 
 /* log posterior pieces, exposed for density tests */
 double orc_loglike(const orc_model *m, const double *theta);
+/* bench.py's CPU arm: plain (uncompensated) sums in the MVN likelihood, the speed a straightforward CPU code has */
+void orc_set_plain_sums(int on);
 double orc_prior_loglike(const orc_model *m, const double *theta);
 /* compute_posterior! (utilities.jl:92-99) */
 double orc_posterior(const orc_config *cfg, const orc_model *m, const double *theta);

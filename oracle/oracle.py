@@ -223,6 +223,11 @@ def run(cfg: Config, model: Model, theta0, n_iter, tape_in=None, record=True, tr
     return out
 
 
+def set_plain_sums(on: bool):
+    """bench.py's CPU arm only: uncompensated sums in the MVN likelihood (the speed of a straightforward CPU code)"""
+    lib().orc_set_plain_sums(int(bool(on)))
+
+
 def loglike(model: Model, theta):
     th = _f8(theta)
     return lib().orc_loglike(C.byref(model.c), _ptr(th, _dp))
