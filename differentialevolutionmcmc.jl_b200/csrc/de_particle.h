@@ -145,7 +145,7 @@ DE_PRAGMA_UNROLL
     for (int q = 0; q < PROP_PRE; ++q) {
         const int k = co.lane() + q * co.width();
         pre_nz[q] = 0.0; pre_lo[q] = 0.0; pre_hi[q] = 0.0; pre_pr[q].kind = PRIOR_FLAT;
-        if (k < d) { pre_nz[q] = noise_at(k); pre_lo[q] = cfg.lo[k]; pre_hi[q] = cfg.hi[k]; pre_pr[q] = m.prior[k]; sink.prefetch(q, k); }
+        if (k < d) { pre_nz[q] = (ctx.block >= 0 && !is_mut && !cfg.blocks[(size_t)ctx.block * d + k]) ? 0.0 : noise_at(k); pre_lo[q] = cfg.lo[k]; pre_hi[q] = cfg.hi[k]; pre_pr[q] = m.prior[k]; sink.prefetch(q, k); }
     }
     co.dependency_wait();
     // a donor that sits before the target in the sweep already holds this sweep's value; with
@@ -200,18 +200,23 @@ DE_PRAGMA_UNROLL
     bool ok = true;
     double sq1 = 0.0, sq2 = 0.0, ps = 0.0;
     const bool one_pass = m.prior_has_ref == 0;                            // no prior reads another parameter
+    // An element outside the sweep's block is reset to theta_t,k whatever was proposed for it (reset!,
+    // crossover.jl:336-352; a mutation sweep ignores the block, main.jl:205): its noise draw, its donors and the proposal
+    // arithmetic are skipped -- the draws are counter-based, so skipping one does not move the others.  With two blocks of
+    // 3 and 1000 parameters (Hierarchical_Example.jl:88-92) every other sweep proposes 3 elements instead of 1003.
+    auto live = [&](int k) { return !mask || mask[k] != 0; };
     auto body = [&](int q, int k, double nz, double lo, double hi, const Prior &pr) {
         const double t = tcur[k];
         double v;
-        if (is_mut) v = add(t, nz);                                            // utilities.jl:291-298
+        if (!live(k)) v = t;
+        else if (is_mut) v = add(t, nz);                                       // utilities.jl:291-298
         else if (kind == KIND_DE) v = de_elem(t, pm[k], pn[k], has_base ? pb[k] : t, g1, g2, has_base, nz);
         else v = snooker_elem(t, pz[k], r1, r2, g1, nz);
-        if (!is_mut) {
+        if (!is_mut && live(k)) {
             if (cfg.kappa != 1.0) {                                            // recombination! (crossover.jl:301-321)
                 const bool keep = ctx.replay ? ctx.t_keep[(size_t)p * d + k] != 0 : keep_elem(cfg.seed, ctx.sweep, unit, k, cfg.kappa);
                 if (keep) v = t;
             }
-            if (mask && !mask[k]) v = t;                                       // reset! (crossover.jl:336-352)
         }
         if (kind == KIND_SNOOKER) {                                            // adjust_loglike (crossover.jl:268-273)
             const double a = sub(v, pz[k]), b = sub(t, pz[k]);
@@ -231,7 +236,7 @@ DE_PRAGMA_UNROLL
     // (tried: bounds and prior specs from a table of per-named-parameter segments instead of the per-element arrays, which
     // cost 56 bytes of loads per element; the arrays are L1-resident and the segment lookup cost more than it saved:
     // configs[3] 14.2 vs 14.7 M updates/s)
-    for (int k = co.lane() + PROP_PRE * co.width(); k < d; k += co.width()) body(PROP_PRE, k, noise_at(k), cfg.lo[k], cfg.hi[k], m.prior[k]);
+    for (int k = co.lane() + PROP_PRE * co.width(); k < d; k += co.width()) body(PROP_PRE, k, live(k) ? noise_at(k) : 0.0, cfg.lo[k], cfg.hi[k], m.prior[k]);
     if (!one_pass) {
         co.sync();
         // hierarchical priors: a thousand elements share one sd parameter, so its logarithm is kept
