@@ -1241,7 +1241,11 @@ __device__ __forceinline__ int ld_acquire(const int32_t *p)
 // every lane has fenced its own writes before lane 0 publishes
 __device__ __forceinline__ void arrive(int32_t *ctr)
 {
+    // DEMCMC_ARRIVE_FENCE (compile-time A/B): the release below is cumulative over what lane 0 has observed, and the
+    // other lanes' stores are ordered before it by the warp barrier; the explicit fence in front of it is belt and braces
+#ifdef DEMCMC_ARRIVE_FENCE
     __threadfence();
+#endif
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(ctr) : "memory");
 }
