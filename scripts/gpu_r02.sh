@@ -8,6 +8,7 @@ echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu > gpurun_
 echo "== bench (driver arguments)"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_steps20.json 2> gpurun_out/${TAG}_bench_steps20.err; echo "rc=$?"
 echo "== bench (defaults)"; timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "rc=$?"
 echo "== bench reference arm"; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "rc=$?"
+[ -n "$NO_NCU" ] && { ls -la gpurun_out/ | tail -12; exit 0; }
 echo "== launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 40 --warmup 3 --no-cpu --no-ess --no-configs > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "rc=$?"
 echo "== ncu full k_chunk_persist"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_chunk_persist -s 4 -c 2 -o gpurun_out/${TAG}_pk -f python bench.py --steps 40 --warmup 3 --no-cpu --no-ess --no-configs > gpurun_out/${TAG}_ncu_pk.log 2>&1; echo "rc=$?"
 echo "== ncu full LBA"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ll_pointwise -s 10 -c 3 -o gpurun_out/${TAG}_lba -f python scripts/bench_configs.py c3 --iters 6 > gpurun_out/${TAG}_ncu_lba.log 2>&1; echo "rc=$?"
