@@ -485,7 +485,8 @@ def optimize(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
         n_iter = int(args[0])
     else:
         raise TypeError("optimize(model, de, n_iter) or optimize(model, de, MCMCThreads(), n_iter)")
-    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter)
+    # optimize returns the final particles only (src/optimize.jl:38): no history row is needed, so none but the last is kept
+    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter, store_every=max(1, n_iter))
     try:
         P = de.n_groups * de.Np
         h.set_state(_draw_states(model.sample_prior, P, d))
