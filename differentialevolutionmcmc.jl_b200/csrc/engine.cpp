@@ -1013,6 +1013,10 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 const char *e = getenv("DEMCMC_SHAPE");       // 0 = off, else the modulus (A/B runs)
                 const int mod = e ? atoi(e) : 8;
                 pin.shape_octets = (is_ssd(h->dmodel.kind)) ? std::max(0, mod) : 0;
+                const char *ec = getenv("DEMCMC_LEVEL_CAP");
+                // levels of at most 112 updates (14 octets) for the persistent chunk kernel: measured on configs[1] against
+                // no cap / 64 / 96 / 104 / 120 / 128: 2.86 M updates/s against 2.83 / 2.64 / 2.75 / 2.82 / 2.80 / 2.83
+                pin.level_cap = persist_lanes ? (ec ? std::max(0, atoi(ec)) : 112) : 0;
             }
             pin.proposal = cfg.proposal; pin.beta = cfg.beta; pin.theta_snooker = cfg.theta_snooker; pin.resample = cfg.donors != 0;
             const int64_t s_first = it0 * B + (blocked ? b0 : 0);

@@ -61,6 +61,22 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
         }
         prev = cur;
     }
+    // Capacity: levels of at most level_cap updates.  (sweep, slot) order is a topological order of the dependencies
+    // (own previous update, donors with a smaller slot of this sweep, donors with a larger slot of the previous one),
+    // so every update can simply take the first level after its dependencies that still has room.
+    if (in.level_cap > 0) {
+        std::vector<int32_t> cnt;
+        max_level = 0;
+        for (size_t u = 0; u < level.size(); ++u) {
+            int e = 0;
+            for (int q = 0; q < 4; ++q) { const int32_t v = deps[u * 4 + q]; if (v >= 0) e = std::max(e, level[v] + 1); }
+            while (e < (int)cnt.size() && cnt[e] >= in.level_cap) ++e;
+            if (e >= (int)cnt.size()) cnt.resize(e + 1, 0);
+            ++cnt[e];
+            level[u] = e;
+            max_level = std::max(max_level, e);
+        }
+    }
     // Shaping: the likelihood kernel pads every level to whole octets of particles (DMMA n = 8), on
     // average 3.5 idle columns per level.  An update whose dependents all sit two or more levels
     // later may run one level later at no cost, so each level hands its remainder (n mod 8) to the

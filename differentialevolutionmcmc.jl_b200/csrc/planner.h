@@ -36,6 +36,10 @@ struct PlanInput {
     int32_t shape_octets = 0;  // > 0: hand each level's remainder modulo this many updates to the next level where the
                                // dependencies allow (the DMMA likelihood kernel pads levels to whole octets of particles,
                                // and its particle tiles are most efficient with four octets: 8 or 32)
+    int32_t level_cap = 0;     // > 0: at most this many updates per level (list scheduling in (sweep, slot) order: an update
+                               // goes to the first level after its dependencies that still has room).  The persistent chunk
+                               // kernel wants levels of one size: its lanes hide each other's accept -> propose chain only
+                               // when their levels take about as long as that chain
     bool resample;             // donors come from stored rows (crossover.jl:113-124): no donor dependencies inside a sweep
     // replay: tape slices [sweep][P_local] of the chunk's FIRST sweep onwards, else nullptr
     const uint8_t *t_kind;     // [n_sweeps][P_local]

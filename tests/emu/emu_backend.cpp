@@ -516,14 +516,23 @@ extern "C" void demcmc_emu_set_exchange(de::be::exchange_fn fn, void *user)
 // the same sweep, donors with a larger slot in the previous sweep (crossover.jl:12-17) -- sits in a strictly
 // earlier level, with or without the octet shaping.  Returns 0, or a negative code naming the violation.
 #include "planner.h"
+extern "C" int demcmc_emu_plan_check_cap(uint64_t seed, int Np, int G, int n_sweeps, double beta, double theta_snooker, int shape,
+                                          int sweep_stride, int cap, int *n_levels_out, int *padded_out);
 extern "C" int demcmc_emu_plan_check(uint64_t seed, int Np, int G, int n_sweeps, double beta, double theta_snooker, int shape,
                                       int sweep_stride, int *n_levels_out, int *padded_out)
+{
+    return demcmc_emu_plan_check_cap(seed, Np, G, n_sweeps, beta, theta_snooker, shape, sweep_stride, 0, n_levels_out, padded_out);
+}
+// ... with a level capacity (PlanInput::level_cap): also checks that no level exceeds it; *padded_out = the largest level
+extern "C" int demcmc_emu_plan_check_cap(uint64_t seed, int Np, int G, int n_sweeps, double beta, double theta_snooker, int shape,
+                                          int sweep_stride, int cap, int *n_levels_out, int *padded_out)
 {
     using namespace de;
     PlanInput in{};
     in.seed = seed; in.Np = Np; in.G_local = G; in.group_begin = 0; in.G_total = G; in.proposal = 0; in.beta = beta;
     in.theta_snooker = theta_snooker; in.resample = false; in.t_kind = nullptr; in.t_idx = nullptr; in.shape_octets = shape;
     in.sweep_stride = sweep_stride;
+    in.level_cap = cap;
     bool bd[MAX_CHUNK] = { false };
     ChunkPlan pl;
     const uint32_t sweep0 = 7;
@@ -535,6 +544,7 @@ extern "C" int demcmc_emu_plan_check(uint64_t seed, int Np, int G, int n_sweeps,
     for (int l = 0; l < pl.n_levels; ++l) {
         const int n = pl.level_off[l + 1] - pl.level_off[l];
         if (n < 0) return -2;
+        if (cap > 0 && n > cap + (shape > 0 ? shape : 0)) return -7;       // (the octet shaping may hand a remainder of < shape updates down)
         padded += (n + 7) / 8 * 8;
         for (int q = pl.level_off[l]; q < pl.level_off[l + 1]; ++q) {
             const uint32_t e = (uint32_t)pl.order[q];

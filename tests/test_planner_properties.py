@@ -44,3 +44,20 @@ def test_shaping_removes_most_padding_at_the_bench_shape(plan_check):
         assert plan_check(20261017, 256, 2, 16, 0.1, 0.1, shape, 1, C.byref(nl), C.byref(padded)) == 0
         res[shape] = padded.value - 16 * 512
     assert res[8] < 0.4 * res[0], res
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 2**63 - 1), Np=st.integers(3, 300), G=st.integers(1, 4), n_sweeps=st.integers(1, 16),
+       beta=st.sampled_from([0.0, 0.1]), snooker=st.sampled_from([0.0, 0.1, 0.6]), cap=st.sampled_from([8, 40, 112, 200]), shape=st.sampled_from([0, 8]))
+def test_level_capacity_keeps_every_dependency(emu, seed, Np, G, n_sweeps, beta, snooker, cap, shape):
+    """PlanInput::level_cap (list scheduling in (sweep, slot) order): every dependency still sits in a strictly earlier
+    level, no level holds more than the cap (+ one shaping remainder), and there are never fewer levels than without it"""
+    L = C.CDLL(common.EMU_LIB)
+    f = L.demcmc_emu_plan_check_cap
+    f.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    f.restype = C.c_int
+    nl0, nl1, pad = C.c_int(0), C.c_int(0), C.c_int(0)
+    assert f(seed, Np, G, n_sweeps, beta, snooker, shape, 1, 0, C.byref(nl0), C.byref(pad)) == 0
+    assert f(seed, Np, G, n_sweeps, beta, snooker, shape, 1, cap, C.byref(nl1), C.byref(pad)) == 0
+    assert nl1.value >= nl0.value
+    assert nl1.value >= -(-n_sweeps * Np * G // (cap + shape))
