@@ -1325,7 +1325,7 @@ template <bool TL>
 struct VctaHooks {
     uint64_t *b_full, *b_empty, *item_done;
     uint32_t parity;
-    unsigned long long *tl; mutable unsigned long long t_done;   // debug timeline (TL) only
+    unsigned long long *tl; mutable unsigned long long t_done, t_first;   // debug timeline (TL) only
     __device__ __forceinline__ void operator()() const
     {
         mbar_wait(b_full, parity);
@@ -1334,7 +1334,7 @@ struct VctaHooks {
             if ((threadIdx.x & 31) == 0) { atomicMax(tl + PT_XW0, ~t_done); atomicMax(tl + PT_XW1, t_done); }
         }
     }
-    __device__ __forceinline__ void after_loads() const { if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }   // called right after a __syncwarp
+    __device__ __forceinline__ void after_loads() const { if (TL && tl) t_first = gtime(); if ((threadIdx.x & 31) == 0) mbar_arrive(b_empty); }   // called right after a __syncwarp
     __device__ __forceinline__ void item_end() const { __syncwarp(); if ((threadIdx.x & 31) == 0) mbar_arrive(item_done); }
 };
 
@@ -1455,7 +1455,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
                 const PkItem it = pk_item(pl, n_tiles, q);
                 if (it.T1 <= it.T0) continue;
                 unsigned long long *tl = (TL && ck.tl) ? ck.tl + (size_t)L * PT_WORDS : nullptr;
-                const VctaHooks<TL> hooks = { &vbars[vc * 3 + 0], &vbars[vc * 3 + 1], &vbars[vc * 3 + 2], n & 1u, tl, 0ull };
+                const VctaHooks<TL> hooks = { &vbars[vc * 3 + 0], &vbars[vc * 3 + 1], &vbars[vc * 3 + 2], n & 1u, tl, 0ull, 0ull };
                 const unsigned long long t_a = (TL && tl) ? gtime() : 0ull;
                 xw.ks = it.ks;
                 const int oct0 = it.oct0, T0 = it.T0, T1 = it.T1;
@@ -1474,6 +1474,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
                     const unsigned long long t_b = gtime();
                     atomicMax(tl + PT_X1, t_b);
                     atomicAdd(tl + PT_SUM_WAIT, hooks.t_done - t_a); atomicAdd(tl + PT_SUM_ITEM, t_b - hooks.t_done);
+                    atomicAdd(tl + PT_SUM_ARRIVE, hooks.t_first - hooks.t_done);      // B fragments + first observation tile (of T1 - T0)
                     atomicAdd(tl + PT_ITEMS, 1ull);
                 }
             }

@@ -39,7 +39,7 @@ for ch in sorted(set(r["chunk"] for r in R)):
     for a, b in zip(rows[:-1], rows[1:]):
         per.append(b["xdot_last_end"] - a["xdot_last_end"])
 print("level period (last item end to last item end) %.2f us" % float(np.mean(per)))
-print("per DMMA warp and item: wait for proposals %.2f us, item (B fragments + DMMA loop + flush) %.2f us, arrive %.2f us" % (
+print("per DMMA warp and item: wait for proposals %.2f us, item (B fragments + DMMA loop + flush) %.2f us, of which B fragments + FIRST observation tile %.2f us" % (
     mean(lambda r: r["wait_us_per_item"]), mean(lambda r: r["work_us_per_item"]), mean(lambda r: r["arrive_us_per_item"])))
 print("per proposal: prologue + pending accepts + dependency wait %.2f us, body %.2f us, staging %.2f us, arrive %.2f us; per accept: body %.2f us, arrive %.2f us" % (
     mean(lambda r: r["prop_pre_us"]), mean(lambda r: r["prop_body_us"]), mean(lambda r: r["prop_stage_us"]), mean(lambda r: r["prop_arrive_us"]),
