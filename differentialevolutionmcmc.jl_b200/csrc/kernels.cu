@@ -256,50 +256,9 @@ void hfree_pinned(void *p)
     for (auto &b : g_pinned) if (b.p == p) { b.busy = false; return; }
     cudaFreeHost(p);
 }
-// Large uploads (the data set of a sample() call: tens of MB of pageable numpy / Julia memory) go through two pinned
-// staging blocks: four host threads copy chunk c + 1 into pinned memory while chunk c crosses PCIe, instead of the
-// driver's single-threaded pageable path (measured: 40 MB in 3.8 ms = 10.5 GB/s that way).
-static int h2d_staged(void *dst, const void *src, size_t bytes)
-{
-    constexpr size_t CHUNK = (size_t)8 << 20;
-    constexpr int NT = 4;
-    static void *stage[64][2] = { { nullptr } };
-    static cudaEvent_t done[64][2] = { { nullptr } };
-    for (int b = 0; b < 2; ++b) {
-        if (!stage[g_dev][b]) CU(cudaMallocHost(&stage[g_dev][b], CHUNK));
-        if (!done[g_dev][b]) CU(cudaEventCreateWithFlags(&done[g_dev][b], cudaEventDisableTiming));
-    }
-    const size_t n_chunks = (bytes + CHUNK - 1) / CHUNK;
-    for (size_t c = 0; c < n_chunks; ++c) {
-        const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
-        if (c >= 2) CU(cudaEventSynchronize(done[g_dev][c & 1]));          // the block's previous copy has left it
-        char *to = (char *)stage[g_dev][c & 1];
-        const char *from = (const char *)src + off;
-        std::thread th[NT];
-        const size_t part = ((len / NT) + 4095) & ~(size_t)4095;
-        for (int t = 0; t < NT; ++t) {
-            const size_t o = std::min(len, (size_t)t * part), l = std::min(part, len - o);
-            th[t] = std::thread([=]() { if (l) memcpy(to + o, from + o, l); });
-        }
-        for (int t = 0; t < NT; ++t) th[t].join();
-        CU(cudaMemcpyAsync((char *)dst + off, to, len, cudaMemcpyHostToDevice, stream()));
-        CU(cudaEventRecord(done[g_dev][c & 1], stream()));
-    }
-    for (int b = 0; b < 2; ++b) CU(cudaEventSynchronize(done[g_dev][b]));      // the staging blocks are free again (and reusable by the next call)
-    return 0;
-}
-int h2d(void *dst, const void *src, size_t bytes)
-{
-    if (!bytes) return 0;
-    if (bytes >= ((size_t)16 << 20)) {
-        cudaPointerAttributes at;
-        const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
-        (void)cudaGetLastError();
-        if (!pinned) return h2d_staged(dst, src, bytes);
-    }
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
-    return 0;
-}
+// (Uploads stay on the driver's pageable path: 40 MB of numpy memory arrive in 2-3 ms either way -- a pipelined pinned staging
+// like d2h_staged below was measured and made no difference.)
+int h2d(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream())); return 0; }
 // Large downloads (the chains of a run: hundreds of MB into a freshly allocated, never-touched
 // caller buffer) do not go through the driver's pageable path -- measured on the B200 box it takes
 // anything from 57 ms to 2.2 s for the same 217 MB, depending on how the destination pages fault.
@@ -341,7 +300,9 @@ static int d2h_staged(void *dst, const void *src, size_t bytes)
 int d2h(void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return 0;
-    if (bytes >= ((size_t)32 << 20)) return d2h_staged(dst, src, bytes);
+    static long long staged_min = -1;
+    if (staged_min < 0) { const char *e = getenv("DEMCMC_D2H_STAGED_MIN_MB"); staged_min = (long long)(e ? atoi(e) : 4) << 20; }   // 8.7 MB of chains: 3.3 ms through the driver's pageable path, 1.2-1.8 ms staged
+    if ((long long)bytes >= staged_min) return d2h_staged(dst, src, bytes);
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
     CU(cudaStreamSynchronize(stream()));
     return 0;
