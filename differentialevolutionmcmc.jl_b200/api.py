@@ -303,7 +303,10 @@ def _fill_flat(theta, out):
     cost of a short run: no lists in between)"""
     k = 0
     for v in theta:
-        if isinstance(v, np.ndarray) and v.ndim:
+        if isinstance(v, float):
+            out[k] = v
+            k += 1
+        elif isinstance(v, np.ndarray) and v.ndim:
             n = v.size
             out[k:k + n] = v if v.ndim == 1 else v.reshape(-1, order="F")
             k += n
