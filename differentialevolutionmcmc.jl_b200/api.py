@@ -402,7 +402,33 @@ def _blocking_schedule(de: DE, n_iter):
     return on
 
 
-def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0, n_iter=None, devices=None, store_every=1):
+class _Background:
+    """Runs one library call on a host thread (ctypes releases the GIL for its duration) while the caller goes on in
+    Python: sample() uploads and packs the data set (demcmc_set_model, a few ms for tens of MB) while the P sample_prior()
+    calls of sample_init run.  join() re-raises what the call raised."""
+
+    def __init__(self, fn):
+        import threading
+        self.err = None
+
+        def run():
+            try:
+                fn()
+            except BaseException as e:      # noqa: BLE001  (re-raised by join)
+                self.err = e
+        self.t = threading.Thread(target=run)
+        self.t.start()
+
+    def join(self):
+        self.t.join()
+        if self.err is not None:
+            raise self.err
+
+
+def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, group_count=0, n_iter=None, devices=None, store_every=1,
+                 background_model=False):
+    """background_model=True: demcmc_set_model runs on a host thread; the fourth return value must be join()ed before the
+    handle is used."""
     """Everything `sample` does before the iteration loop; also used by bench.py and the tests."""
     ll = model.loglike
     if not isinstance(ll, GPULoglike):
@@ -427,7 +453,13 @@ def build_handle(model: DEModel, de: DE, device=0, trace=False, group_begin=0, g
                resample=de.sample is resample, update={mh_update: "mh", maximize: "maximize", minimize: "minimize"}[de.update_particle],
                fitness="fun" if de.evaluate_fitness is evaluate_fun else "posterior", blocking_schedule=schedule, devices=devices,
                store_every=store_every)
-    h.set_model(ll.kind, _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun), x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor, cov=ll.cov)
+    table = _prior_table(model, shapes, needed=de.evaluate_fitness is not evaluate_fun)
+
+    def bind():
+        h.set_model(ll.kind, table, x=ll.x, choice=ll.choice, sigma=ll.sigma, lba_floor=ll.lba_floor, cov=ll.cov)
+    if background_model:
+        return h, shapes, d, _Background(bind)
+    bind()
     return h, shapes, d
 
 
@@ -442,7 +474,7 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, devices=None
         n_iter = int(args[0])
     else:
         raise TypeError("sample(model, de, n_iter) or sample(model, de, MCMCThreads(), n_iter)")
-    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter, devices=devices, store_every=store_every)
+    h, shapes, d, binding = build_handle(model, de, device=device, n_iter=n_iter, devices=devices, store_every=store_every, background_model=True)
     try:
         P = de.n_groups * de.Np
         if de.n_initial > 0:
@@ -452,11 +484,14 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, devices=None
             for p in range(P):
                 for i in range(de.n_initial):
                     _fill_flat(model.sample_prior(), rows[i, p])
+            binding.join()                                   # the data set is on the device and packed
             h.set_history(rows)
             h.set_state(None)
         else:
-            # sample_init (src/main.jl:263-271): one sample_prior() per particle, id order
-            h.set_state(_draw_states(model.sample_prior, P, d))
+            # sample_init (src/main.jl:263-271): one sample_prior() per particle, id order -- drawn while the data upload runs
+            theta0 = _draw_states(model.sample_prior, P, d)
+            binding.join()
+            h.set_state(theta0)
         h.run(n_iter)
         de.iter = n_iter + de.n_initial
         # bundle_samples (src/main.jl:222-250) runs on the device: one gather, one download, and the
@@ -467,6 +502,10 @@ def sample(model: DEModel, de: DE, *args, progress=False, device=0, devices=None
         names = _flat_names(model.names, shapes) + ["acceptance", "lp"]
         return Chains(arr.transpose(2, 1, 0), names, [str(n) for n in model.names])
     finally:
+        try:
+            binding.join()                                   # (an exception above: let the upload finish before the handle goes)
+        except BaseException:                                # noqa: BLE001
+            pass
         h.close()
 
 
