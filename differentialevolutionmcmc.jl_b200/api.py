@@ -528,14 +528,20 @@ def optimize(model: DEModel, de: DE, *args, progress=False, device=0, **kwargs):
     else:
         raise TypeError("optimize(model, de, n_iter) or optimize(model, de, MCMCThreads(), n_iter)")
     # optimize returns the final particles only (src/optimize.jl:38): no history row is needed, so none but the last is kept
-    h, shapes, d = build_handle(model, de, device=device, n_iter=n_iter, store_every=max(1, n_iter))
+    h, shapes, d, binding = build_handle(model, de, device=device, n_iter=n_iter, store_every=max(1, n_iter), background_model=True)
     try:
         P = de.n_groups * de.Np
-        h.set_state(_draw_states(model.sample_prior, P, d))
+        theta0 = _draw_states(model.sample_prior, P, d)
+        binding.join()
+        h.set_state(theta0)
         h.run(n_iter)
         de.iter = n_iter
         th, w, ids = h.get_state()
     finally:
+        try:
+            binding.join()
+        except BaseException:                                # noqa: BLE001
+            pass
         h.close()
     out = []
     for c in range(P):

@@ -700,3 +700,18 @@ def test_overlapped_block_sweeps_are_a_schedule_only(emu, kw):
     # replay through overlapped block sweeps against the oracle
     r, out = compare_run(case, 2, 6, 7, "replay", seed=3, burnin=3, blocks=hier_blocks(9), proposal="fixed_gamma")
     assert np.array_equal(out["accept"], r["accept"])
+
+
+def test_background_model_binding_reports_its_errors(emu):
+    """sample() binds the model on a host thread while the initial particles are drawn: an error of that call must
+    surface in the caller, and the handle must still be released"""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(30, 4))
+    bad = D.GPULoglike("mvnormal_full", x, cov=-np.eye(4))          # not positive definite: demcmc_set_model fails
+    model = D.DEModel(sample_prior=lambda: [rng.normal(size=4), 1.0], prior_loglike=D.GPUPrior(D.Normal(0, 1), D.HalfCauchy(0, 1)),
+                      loglike=bad, names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), n_groups=2, Np=4, burnin=0, seed=1)
+    with pytest.raises(D._ffi.DemcmcError, match="positive definite"):
+        D.sample(model, de, 5)
+    good = D.DEModel(sample_prior=model.sample_prior, prior_loglike=model.prior_loglike, loglike=D.GPULoglike("mvnormal_full", x, cov=np.eye(4)), names=("μ", "σ"))
+    assert len(D.sample(good, de, 5)) == 5
