@@ -61,6 +61,8 @@ int launch_eval(const ConfigDev &cfg, const ModelDev &m, const double *theta, in
                 double *w, double *scratch_part, double *xdot = nullptr);
 // select_base preparation on the sweep-start weights: cw[P] running sums, tot[G]; th[P] is scratch
 int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *cw, double *tot);
+// fills ctxs[s].plan[0..P_local) for the n_sw sweeps of a chunk (contexts with plan == NULL are skipped)
+int launch_plan(const ConfigDev &cfg, const SweepCtx *d_ctxs, int n_sw);
 // propose -> loglik -> accept for one level of one sweep
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // MVN / hierarchical: adds the cross term into ll_acc (fixed point, see de_math.h: xd_scale; launch_propose

@@ -106,6 +106,49 @@ DE_HD void bounds_and_prior(const C &co, const ConfigDev &cfg, const ModelDev &m
     prior = co.sum(ps);
 }
 
+// the state-independent draws of the update of local position p in this sweep (native mode)
+DE_HD PlanRec make_plan(const ConfigDev &cfg, const SweepCtx &ctx, int p)
+{
+    const int Np = cfg.Np;
+    const int g = p / Np, j = p - g * Np;
+    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
+    const bool mutate = ctx.mutate[g] != 0;
+    PlanRec r;
+    r.i0 = r.i1 = r.i2 = r.hr0 = r.hr1 = r.hr2 = -1; r.pad = 0; r.g1 = 0.0; r.g2 = 0.0;
+    if (cfg.resample) {
+        const PlanHist pl = plan_particle_hist(cfg.seed, ctx.sweep, unit, mutate, cfg.theta_snooker, ctx.donor_rows, (int64_t)cfg.P_hist);
+        r.kind = pl.kind; r.i0 = pl.id[0]; r.i1 = pl.id[1]; r.i2 = pl.id[2]; r.hr0 = pl.row[0]; r.hr1 = pl.row[1]; r.hr2 = pl.row[2]; r.u_base = pl.u_base;
+    } else {
+        const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
+        r.kind = pl.kind; r.i0 = pl.i0; r.i1 = pl.i1; r.i2 = pl.i2; r.u_base = pl.u_base;
+    }
+    if (r.kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, r.kind, cfg.proposal, ctx.in_burnin != 0, cfg.d); r.g1 = gg.a; r.g2 = gg.b; }
+    r.u_acc = uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
+    return r;
+}
+
+// a record drawn by an earlier launch: read past the (non-coherent) L1, four 16-byte loads
+DE_HD PlanRec load_plan(const PlanRec *r)
+{
+#if defined(__CUDA_ARCH__)
+    union { PlanRec rec; int4 q[4]; } u;
+    const int4 *src = reinterpret_cast<const int4 *>(r);
+    u.q[0] = __ldcg(src); u.q[1] = __ldcg(src + 1); u.q[2] = __ldcg(src + 2); u.q[3] = __ldcg(src + 3);
+    return u.rec;
+#else
+    return *r;
+#endif
+}
+
+DE_HD double load_plan_uacc(const PlanRec *r)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcg(&r->u_acc);
+#else
+    return r->u_acc;
+#endif
+}
+
 // crossover!(model,de,group,pt[,block]) / mutation! up to evaluate_fitness!: writes the proposal,
 // its prior, bounds flag and snooker adjustment (crossover.jl:30-99,154-273,301-352; mutation.jl:13-25)
 template <class C, class S>
@@ -114,7 +157,6 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
     const int Np = cfg.Np, d = cfg.d;
     const int g = p / Np, j = p - g * Np;
     const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
-    const bool mutate = ctx.mutate[g] != 0;
     const double *tcur = ctx.cur_theta + (size_t)p * d;
     double *prop = ctx.prop_theta + (size_t)p * d;
 
@@ -126,14 +168,8 @@ DE_HD void propose_particle(const C &co, const ConfigDev &cfg, const ModelDev &m
         if (cfg.resample) { hr0 = ctx.t_idx_row[p * 3]; hr1 = ctx.t_idx_row[p * 3 + 1]; hr2 = ctx.t_idx_row[p * 3 + 2]; }
         g1 = ctx.t_g1[p]; g2 = ctx.t_g2[p];
     } else {
-        if (cfg.resample) {
-            const PlanHist pl = plan_particle_hist(cfg.seed, ctx.sweep, unit, mutate, cfg.theta_snooker, ctx.donor_rows, (int64_t)cfg.P_hist);
-            kind = pl.kind; i0 = pl.id[0]; i1 = pl.id[1]; i2 = pl.id[2]; hr0 = pl.row[0]; hr1 = pl.row[1]; hr2 = pl.row[2]; u_base = pl.u_base;
-        } else {
-            const Plan pl = plan_particle(cfg.seed, ctx.sweep, unit, j, Np, mutate, cfg.theta_snooker);
-            kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; u_base = pl.u_base;
-        }
-        if (kind != KIND_MUTATION) { const dbl2 gg = gamma_draw(cfg.seed, ctx.sweep, unit, kind, cfg.proposal, ctx.in_burnin != 0, d); g1 = gg.a; g2 = gg.b; }
+        const PlanRec pl = ctx.plan ? load_plan(ctx.plan + p) : make_plan(cfg, ctx, p);
+        kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; hr0 = pl.hr0; hr1 = pl.hr1; hr2 = pl.hr2; u_base = pl.u_base; g1 = pl.g1; g2 = pl.g2;
     }
     // everything an element needs that does not depend on the state -- its noise draw, bounds, prior
     // spec -- is fetched for the first PROP_PRE elements of the lane before the dependency wait
@@ -274,7 +310,7 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const double *tcur = ctx.cur_theta + (size_t)p * d;
     const int g = p / Np, j = p - g * Np;
     const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
-    const double u = ctx.replay ? ctx.t_uacc[p] : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
+    const double u = ctx.replay ? ctx.t_uacc[p] : ctx.plan ? load_plan_uacc(ctx.plan + p) : uniform2(cfg.seed, ST_ACC, ctx.sweep, unit, 0).a;
     co.dependency_wait();
     double total;
     if (is_ssd(m.kind)) total = (double)ctx.ll_acc[p] * ctx.ll_q[p];

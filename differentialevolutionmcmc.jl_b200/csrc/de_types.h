@@ -58,6 +58,7 @@ struct ModelDev {
     // split; fixed by the model alone so the summation order never depends on the GPU count or on
     // how many slices one CTA happens to process
     int32_t n_osplit, n_ksplit, split_len, ksplit_len;
+    uint32_t ksplit_magic;    // ceil(2^32 / ksplit_len): k / ksplit_len = umulhi(k, magic) for every dimension index k < 2^32 / ksplit_len
 };
 
 // Packed layout of the centred data for k_xdot: element (observation i, dimension k) lives in the
@@ -87,6 +88,11 @@ struct ConfigDev {
     uint64_t seed;
 };
 
+// The state-independent draws of one particle update (kind, donor slots, gammas, the select_base and accept uniforms):
+// functions of (seed, sweep, unit) alone, so a whole chunk's worth is drawn by ONE launch before the chunk's levels run
+// (k_plan) and the per-level kernels start from a 64-byte record instead of a ~600-instruction Philox chain per warp.
+struct alignas(16) PlanRec { int32_t kind, i0, i1, i2, hr0, hr1, hr2, pad; double g1, g2, u_base, u_acc; };
+
 // One sweep (one pass of mutate_or_crossover! over every local group).  State is kept in ROWS:
 // the sweep reads row `cur` (immutable while the sweep runs) and writes row `next`; a donor with
 // a smaller slot than the target is read from `next`, reproducing the reference's sequential,
@@ -100,6 +106,7 @@ struct SweepCtx {
     const double *cur_theta; const double *cur_w; const int32_t *cur_id;
     double *next_theta; double *next_w; int32_t *next_id; uint8_t *next_acc;
     const uint8_t *mutate;    // [G_local] this sweep's rand() <= beta (main.jl:200)
+    PlanRec *plan;            // [P_local] this sweep's pre-drawn plans (native mode), or NULL: drawn in place
     // select_base on the sweep-start weights (native mode, burn-in, random_gamma): running sums of
     // the sampling weights per group and their totals (crossover.jl:282-289)
     const double *base_cw;    // [P_local]

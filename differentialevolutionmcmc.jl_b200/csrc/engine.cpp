@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -88,6 +89,7 @@ struct demcmc_handle {
     int64_t cur_hist = -1;                              // in history row cur_hist (>= 0)
     // proposal scratch
     double *prop_theta = nullptr, *prop_prior = nullptr, *prop_adj = nullptr, *prop_msq = nullptr, *ll_part = nullptr, *ll_q = nullptr;
+    PlanRec *plan_recs = nullptr;                      // [MAX_CHUNK][P_local] the pre-drawn plans of the chunk in flight (native mode)
     long long *ll_acc = nullptr;
     uint8_t *prop_inb = nullptr;
     double *base_th = nullptr, *base_cw = nullptr, *base_tot = nullptr;
@@ -510,6 +512,10 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->prop_adj = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_msq = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_inb = (uint8_t *)be::dmalloc(P);
+    {
+        const char *e = getenv("DEMCMC_NO_PLAN");             // A/B runs: draw the plans inside the level kernels
+        if (!(e && e[0] == '1')) h->plan_recs = (PlanRec *)be::dmalloc(sizeof(PlanRec) * (size_t)MAX_CHUNK * P);
+    }
     h->ll_acc = (long long *)be::dmalloc(sizeof(long long) * P);
     h->ll_q = (double *)be::dmalloc(sizeof(double) * P);
     h->base_th = (double *)be::dmalloc(sizeof(double) * P);
@@ -561,7 +567,7 @@ int demcmc_destroy(demcmc_handle *h)
     for (void *p : h->model_allocs) be::dfree(p);
     void *ptrs[] = { h->hist_theta, h->hist_w, h->hist_id, h->hist_acc, h->hist_pos, h->scr_theta, h->scr_w, h->scr_id, h->scr_acc,
                      h->prop_theta, h->prop_prior, h->prop_adj, h->prop_msq, h->prop_inb, h->ll_acc, h->ll_q, h->base_th, h->base_cw, h->base_tot, h->ll_part, h->d_lo, h->d_hi, h->d_blocks,
-                     h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_xdot, h->tr_acc, h->flush_buf };
+                     h->plan_recs, h->d_picks, h->d_stage, h->d_stage_recv, h->d_mig_log, h->tr_theta, h->tr_w, h->tr_adj, h->tr_xdot, h->tr_acc, h->flush_buf };
     for (void *e : h->tev) be::tevent_destroy(e);
     for (void *p : ptrs) be::dfree(p);
     for (auto &u : h->ring) { be::hfree_pinned(u.h_blk); be::dfree(u.d_blk); be::event_destroy(u.copied); }
@@ -640,6 +646,7 @@ int demcmc_set_model(demcmc_handle *h, const demcmc_model *m)
         D.n_ksplit = (D.ssd_k + SSD_KS - 1) / SSD_KS;
         D.ksplit_len = (D.ssd_k + D.n_ksplit - 1) / D.n_ksplit;
         D.ssd_nj = (D.ksplit_len + 3) / 4;
+        D.ksplit_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)D.ksplit_len - 1) / (uint64_t)D.ksplit_len);
         { const char *e = getenv("DEMCMC_NO_HALF_STEP"); D.ssd_half = (D.ksplit_len % 4 == 2 && !(e && e[0] == '1')) ? 1 : 0; }
         { const char *e = getenv("DEMCMC_TEST_CORRUPT"); D.debug_corrupt = e ? atoi(e) : 0; }     // mutation tests (de_types.h)
         D.center_given = m->center ? 1 : 0;
@@ -932,8 +939,14 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         return a >= (int64_t)h->block_on.size() || h->block_on[(size_t)a] != 0;
     };
     int64_t sweeps_run = 0;
+    // DEMCMC_HOST_PROFILE=1: host seconds spent planning and launching, printed per call (stderr)
+    static const bool host_prof = [] { const char *e = getenv("DEMCMC_HOST_PROFILE"); return e && e[0] == '1'; }();
+    double host_plan_s = 0.0, host_chunk_s = 0.0;
+    auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto run_chunk = [&](int64_t it0, int b0, int n_sw, bool blocked) -> int {
         sweeps_run += n_sw;
+        const double t_chunk0 = host_prof ? now_s() : 0.0;
+        struct ChunkTimer { double &acc; double t0; bool on; std::function<double()> now; ~ChunkTimer() { if (on) acc += now() - t0; } } chunk_timer{ host_chunk_s, t_chunk0, host_prof, now_s };
         const int64_t itg0 = h->iters_done + it0;
         Upload &u = h->ring[h->ring_use % demcmc_handle::RING];
         if (u.armed) BE(be::event_wait(u.copied));             // the pinned slot is free once its copies ran
@@ -971,6 +984,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             ctx.cur_theta = cur.theta; ctx.cur_w = cur.w; ctx.cur_id = cur.id;
             ctx.next_theta = next.theta; ctx.next_w = next.w; ctx.next_id = next.id; ctx.next_acc = next.acc;
             ctx.mutate = u.d_mut + (size_t)s * G;
+            ctx.plan = (tape || !h->plan_recs) ? nullptr : h->plan_recs + (size_t)s * P;
             if (tape) {
                 ctx.t_kind = t_kind + (size_t)s_local * P; ctx.t_idx = t_idx + (size_t)s_local * P * 3;
                 ctx.t_g1 = t_g1 + (size_t)s_local * P; ctx.t_g2 = t_g2 + (size_t)s_local * P; ctx.t_uacc = t_uacc + (size_t)s_local * P;
@@ -1022,7 +1036,9 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
             const int64_t s_first = it0 * B + (blocked ? b0 : 0);
             pin.t_kind = tape ? hk.data() + (size_t)s_first * P : nullptr;       // a chunk of several sweeps is unblocked: its sweeps are P_stride apart in the tape
             pin.t_idx = tape ? hi.data() + (size_t)s_first * P * 3 : nullptr;
+            const double t_plan0 = host_prof ? now_s() : 0.0;
             plan_chunk(pin, (uint32_t)((h->iter_offset + itg0) * B + (blocked ? b0 : 0)), n_sw, basedep, plans[ln]);
+            if (host_prof) host_plan_s += now_s() - t_plan0;
             const ChunkPlan &pl = plans[ln];
             memcpy(u.h_order + lane_off[ln], pl.order.data(), sizeof(int32_t) * pl.order.size());
             lane_off[ln + 1] = lane_off[ln] + (int32_t)pl.order.size();
@@ -1033,6 +1049,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         BE(be::h2d(u.d_blk, u.h_blk, u.off_order + sizeof(int32_t) * (size_t)n_sw * P));   // contexts, flags and entries in one copy
         BE(be::event_record(u.copied));
         u.armed = true;
+        if (!tape && h->plan_recs) BE(be::launch_plan(h->dcfg, u.d_ctx, n_sw));     // every state-independent draw of the chunk, one launch
 
         if (needs_snapshot(it0)) {                               // n_sw == 1 here
             bool any_cross = false;
@@ -1246,6 +1263,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
     }
     cleanup();
     h->iters_done += n_iter;
+    if (host_prof) fprintf(stderr, "[demcmc host] %lld iterations: chunks %.3f ms on the host (planner %.3f ms), %lld levels\n", (long long)n_iter, host_chunk_s * 1e3, host_plan_s * 1e3, (long long)n_levels);
     h->ctr.iterations += n_iter; h->ctr.sweeps += sweeps_run; h->ctr.particle_updates += sweeps_run * P; h->ctr.loglike_evals += sweeps_run * P;
     h->ctr.kernel_launches += be::launch_count() - launches0; h->ctr.levels += n_levels; h->ctr.device_ms = ms_dev;
     return 0;

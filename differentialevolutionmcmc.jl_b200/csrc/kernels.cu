@@ -71,6 +71,9 @@ static bool use_pdl()
     if (v < 0) { const char *e = getenv("DEMCMC_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
+// set by launch_plan: the next kernel on lane 0 reads the plan records BEFORE its griddepcontrol.wait, so it must not be
+// chained to k_plan programmatically (the other lanes start behind an event recorded after k_plan)
+static thread_local bool g_break_chain = false;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
 {
@@ -78,7 +81,8 @@ static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream();
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = (use_pdl() && !(g_break_chain && g_lane == 0)) ? 1 : 0;
+    if (g_lane == 0) g_break_chain = false;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
@@ -86,7 +90,7 @@ static cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // ---- debug timeline (DEMCMC_TIMELINE=<levels> DEMCMC_TIMELINE_FILE=<csv>): every kernel of a level
 // stamps %globaltimer into one 16-word slot, so the gaps between the kernels of a PDL chain can be
 // read without events (which would break the chain) and without a profiler (which serialises it)
-enum { TL_P0 = 0, TL_P1, TL_X0, TL_X0MAX, TL_XWAIT, TL_XFIRST, TL_XLOOP0, TL_XLOOP1, TL_X1, TL_A0, TL_A1, TL_N, TL_WORDS = 16 };
+enum { TL_P0 = 0, TL_P1, TL_X0, TL_X0MAX, TL_XWAIT, TL_XFIRST, TL_XLOOP0, TL_XLOOP1, TL_X1, TL_A0, TL_A1, TL_N, TL_PW, TL_AW, TL_Q0, TL_Q1, TL_Q2, TL_Q3, TL_WORDS = 24 };
 static unsigned long long *g_tl = nullptr;
 static int g_tl_cap = -1, g_tl_level = 0, g_tl_cta_level = -1;
 constexpr int TL_CTA_WORDS = 4, TL_CTA_MAX = 4096;
@@ -119,13 +123,13 @@ void timeline_dump()
     if (n <= 0 || cudaMemcpy(h.data(), g_tl, sizeof(unsigned long long) * TL_WORDS * n, cudaMemcpyDeviceToHost) != cudaSuccess) return;
     FILE *f = fopen(path, "w");
     if (!f) return;
-    fprintf(f, "level,n,propose_start,propose_end,xdot_start,xdot_last_start,xdot_wait_done,xdot_first_data,xdot_loop_end_min,xdot_loop_end_max,xdot_end,accept_start,accept_end\n");
+    fprintf(f, "level,n,propose_start,propose_end,xdot_start,xdot_last_start,xdot_wait_done,xdot_first_data,xdot_loop_end_min,xdot_loop_end_max,xdot_end,accept_start,accept_end,propose_wait_done,accept_wait_done,q0,q1,q2,q3\n");
     const unsigned long long t0 = ~h[TL_P0];
     for (int i = 0; i < n; ++i) {
         const unsigned long long *w = h.data() + (size_t)TL_WORDS * i;
         auto rel = [&](unsigned long long v) { return (double)((long long)(v - t0)) * 1e-3; };
-        fprintf(f, "%d,%llu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, w[TL_N], rel(~w[TL_P0]), rel(w[TL_P1]), rel(~w[TL_X0]), rel(w[TL_X0MAX]),
-                rel(w[TL_XWAIT]), rel(w[TL_XFIRST]), rel(~w[TL_XLOOP0]), rel(w[TL_XLOOP1]), rel(w[TL_X1]), rel(~w[TL_A0]), rel(w[TL_A1]));
+        fprintf(f, "%d,%llu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, w[TL_N], rel(~w[TL_P0]), rel(w[TL_P1]), rel(~w[TL_X0]), rel(w[TL_X0MAX]),
+                rel(w[TL_XWAIT]), rel(w[TL_XFIRST]), rel(~w[TL_XLOOP0]), rel(w[TL_XLOOP1]), rel(w[TL_X1]), rel(~w[TL_A0]), rel(w[TL_A1]), rel(~w[TL_PW]), rel(~w[TL_AW]), rel(w[TL_Q0]), rel(w[TL_Q1]), rel(w[TL_Q2]), rel(w[TL_Q3]));
     }
     fclose(f);
     if (g_tl_cta_level >= 0) {
@@ -408,17 +412,26 @@ __device__ __forceinline__ void stage_scale(const ModelDev &m, double msq, int64
         if (msq_out) *msq_out = msq;
     }
 }
-__device__ __forceinline__ size_t bfrag_index(const ModelDev &m, int64_t wi, int k)
+// where dimension k of the wi-th particle of a launch goes: base (per particle) + offset (per dimension), the latter in
+// 32-bit arithmetic with the division by the split length done by multiplication (ModelDev::ksplit_magic) -- the plain
+// 64-bit form with a hardware-less integer division cost 57 instructions per element, a tenth of the wide proposal kernel
+__device__ __forceinline__ size_t bfrag_base(const ModelDev &m, int64_t wi)
 {
-    const int64_t oct = wi / SSD_OCT;
-    const int n = (int)(wi % SSD_OCT);
-    const int ks = k / m.ksplit_len, kl = k - ks * m.ksplit_len;
-    const size_t frag = (((size_t)oct * m.n_ksplit + ks) * m.ssd_nj + (kl >> 2)) * 32;
+    return (size_t)(wi / SSD_OCT) * (size_t)(m.n_ksplit * m.ssd_nj * 32);
+}
+__device__ __forceinline__ uint32_t bfrag_offset(const ModelDev &m, int n, int k)
+{
+    const int ks = m.n_ksplit == 1 ? 0 : (int)__umulhi((uint32_t)k, m.ksplit_magic), kl = k - ks * m.ksplit_len;
+    const uint32_t frag = (uint32_t)(ks * m.ssd_nj + (kl >> 2)) * 32u;
     if (m.debug_corrupt) {                                   // mutation tests only (de_types.h: debug_corrupt)
         if (m.debug_corrupt == 1) return frag + (kl & 3) * 8 + n;
         if (m.debug_corrupt == 3 && m.ssd_nj > 1 && (kl >> 2) == m.ssd_nj - 1) return frag - 32 + n * 4 + (kl & 3);
     }
     return frag + n * 4 + (kl & 3);
+}
+__device__ __forceinline__ size_t bfrag_index(const ModelDev &m, int64_t wi, int k)
+{
+    return bfrag_base(m, wi) + bfrag_offset(m, (int)(wi % SSD_OCT), k);
 }
 __device__ __forceinline__ void stage_bfrag(const ModelDev &m, const double *theta, int64_t wi, double *bfrag, double *magic,
                                             long long *acc, double *q, double *msq_out)
@@ -496,6 +509,8 @@ template <int PAW_THREADS>
 struct BlockLanes {
     double *red;                          // shared scratch: PAW_THREADS / 32 doubles
     int *ired;
+    unsigned long long *tl;               // debug timeline slot or NULL
+    int tl_wait;
     __device__ __forceinline__ int lane() const { return threadIdx.x; }
     __device__ __forceinline__ int width() const { return PAW_THREADS; }
     __device__ __forceinline__ double sum(double x) const
@@ -522,23 +537,28 @@ struct BlockLanes {
         return r;
     }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
-    __device__ __forceinline__ void dependency_wait() const { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+    __device__ __forceinline__ void dependency_wait() const
+    {
+        asm volatile("griddepcontrol.wait;\n" ::: "memory");
+        if (tl && threadIdx.x == 0) tl_min(tl, tl_wait);
+    }
 };
 
 template <int PAW_THREADS, int MINB>
-__global__ void __launch_bounds__(PAW_THREADS, MINB) k_propose_wide(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic)
+__global__ void __launch_bounds__(PAW_THREADS, MINB) k_propose_wide(ConfigDev cfg, ModelDev m, Level lv, double *bfrag, double *magic, unsigned long long *tl)
 {
     __shared__ double red[PAW_THREADS / 32];
     __shared__ int ired[PAW_THREADS / 32];
     pdl_launch_dependents();
+    if (threadIdx.x == 0) tl_min(tl, TL_P0);
     const int wi = blockIdx.x;
     const uint32_t e = (uint32_t)lv.order[wi];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
     const int p = (int)(e & LV_POS_MASK);
-    const BlockLanes<PAW_THREADS> co = { red, ired };
+    const BlockLanes<PAW_THREADS> co = { red, ired, tl, TL_PW };
     StageSink sink = { m, bfrag, wi, bfrag != nullptr && m.kind == M_MVNORMAL, { 0.0 }, 0.0 };
     propose_particle(co, cfg, m, ctx, p, sink);
-    if (!bfrag) return;
+    if (!bfrag) { if (threadIdx.x == 0) tl_max(tl, TL_P1); return; }
     double msq = sink.msq;
     if (!sink.on) {
         __syncthreads();                                          // the proposal is complete in global memory
@@ -552,20 +572,295 @@ __global__ void __launch_bounds__(PAW_THREADS, MINB) k_propose_wide(ConfigDev cf
     }
     msq = co.sum(msq);
     if (threadIdx.x < 32) stage_scale(m, msq, wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
+    if (threadIdx.x == 0) { tl_max(tl, TL_P1); if (tl && wi == 0) tl[TL_N] = (unsigned long long)lv.n; }
 }
 
-template <int PAW_THREADS>
-__global__ void __launch_bounds__(PAW_THREADS) k_accept_wide(ConfigDev cfg, ModelDev m, Level lv)
+template <int PAW_THREADS, int MINB>
+__global__ void __launch_bounds__(PAW_THREADS, MINB) k_accept_wide(ConfigDev cfg, ModelDev m, Level lv, unsigned long long *tl)
 {
     __shared__ double red[PAW_THREADS / 32];
     __shared__ int ired[PAW_THREADS / 32];
     pdl_launch_dependents();
+    if (threadIdx.x == 0) tl_min(tl, TL_A0);
     const uint32_t e = (uint32_t)lv.order[blockIdx.x];
     const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
-    const BlockLanes<PAW_THREADS> co = { red, ired };
+    const BlockLanes<PAW_THREADS> co = { red, ired, tl, TL_AW };
     accept_particle(co, cfg, m, ctx, (int)(e & LV_POS_MASK));
+    if (threadIdx.x == 0) tl_max(tl, TL_A1);
 }
 
+// ---- the one-pass wide proposal (d <= 4 x 256) ---------------------------------------------------------------------------
+// k_propose_wide walks the parameter vector three times (proposal, priors that read another parameter, staging of the
+// likelihood kernel's operands), re-reading its own stores from L2 between block-wide barriers, one element per thread and
+// trip: on configs[3] a CTA alone on its SM spends 12.6 us behind the dependency wait (profiles/r02_c4_timeline*.txt), and
+// that latency x 4 resident CTAs per SM is the throughput of the level.  Here every thread owns FOUR elements
+// (k = tid + 256 i) for the whole kernel: all their loads are issued together, the proposal values stay in registers for
+// the prior and the staging, the first four elements of the vector (where the hyper-parameters a NORMAL_REF prior or the
+// hierarchical mean refer to live) are broadcast through shared memory, and ONE combined reduction ends the kernel.  Two
+// neighbouring threads share each Philox call of the noise and kappa draws (two uniforms per call) through a shuffle.
+// Same per-element arithmetic as de_particle.h; only the order of the block-wide sums differs.
+constexpr int PW1_T = 256, PW1_E = 4;
+
+__device__ __forceinline__ double shfl_xor1(double v)
+{
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), 1), __shfl_xor_sync(0xffffffffu, __double2loint(v), 1));
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(PW1_T, MINB) k_propose_wide1(ConfigDev cfg, ModelDev m, Level lv, double *__restrict__ bfrag, double *magic, unsigned long long *tl)
+{
+    constexpr int T = PW1_T, E = PW1_E, NW = T / 32;
+    __shared__ double red[NW];
+    __shared__ int ired[NW];
+    __shared__ double red4[NW][4];
+    __shared__ double s_head[4], s_headlog[4];
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    if (tid == 0) tl_min(tl, TL_P0);
+    const int wi = blockIdx.x;
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    const int p = (int)(e & LV_POS_MASK);
+    const BlockLanes<T> co = { red, ired, tl, TL_PW };
+    const int Np = cfg.Np, d = cfg.d;
+    const int g = p / Np, j = p - g * Np;
+    const uint32_t unit = (uint32_t)((cfg.group_begin + g) * Np + j);
+    const bool replay = ctx.replay != 0;
+    const uint32_t sweep = ctx.sweep;
+
+    int kind, i0 = -1, i1 = -1, i2 = -1, hr0 = -1, hr1 = -1, hr2 = -1;
+    double g1 = 0.0, g2 = 0.0, u_base = 0.0;
+    if (replay) {
+        kind = ctx.t_kind[p];
+        i0 = ctx.t_idx[p * 3]; i1 = ctx.t_idx[p * 3 + 1]; i2 = ctx.t_idx[p * 3 + 2];
+        if (cfg.resample) { hr0 = ctx.t_idx_row[p * 3]; hr1 = ctx.t_idx_row[p * 3 + 1]; hr2 = ctx.t_idx_row[p * 3 + 2]; }
+        g1 = ctx.t_g1[p]; g2 = ctx.t_g2[p];
+    } else {
+        const PlanRec pl = ctx.plan ? load_plan(ctx.plan + p) : make_plan(cfg, ctx, p);
+        kind = pl.kind; i0 = pl.i0; i1 = pl.i1; i2 = pl.i2; hr0 = pl.hr0; hr1 = pl.hr1; hr2 = pl.hr2; u_base = pl.u_base; g1 = pl.g1; g2 = pl.g2;
+    }
+    const bool is_mut = kind == KIND_MUTATION;
+    const int block = ctx.block;
+    const uint8_t *mask = (block >= 0 && !is_mut) ? cfg.blocks + (size_t)block * d : nullptr;
+    const bool use_kappa = !is_mut && cfg.kappa != 1.0;
+
+    // state-independent inputs of the four elements: live flags, noise, kappa draws.  Element k = tid + T i belongs to the
+    // Philox pair k >> 1, which this thread shares with thread tid ^ 1: the even thread draws the pairs of i = 0, 2, the odd
+    // one those of i = 1, 3, and each hands the other its half.
+    unsigned live = 0;
+    double nz[E];
+    unsigned keep = 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int k = tid + T * i;
+        nz[i] = 0.0;
+        if (k < d && (!mask || mask[k] != 0)) live |= 1u << i;
+    }
+    if (replay) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int k = tid + T * i;
+            if ((live >> i) & 1u) {
+                nz[i] = ctx.t_noise[(size_t)p * d + k];
+                if (use_kappa && ctx.t_keep[(size_t)p * d + k] != 0) keep |= 1u << i;
+            }
+        }
+    } else {
+        const unsigned live_pair = live | __shfl_xor_sync(0xffffffffu, live, 1);
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int k = tid + T * i;
+            const bool mine = ((tid ^ i) & 1) == 0;                       // this thread draws the pair of trip i
+            dbl2 z; z.a = 0.0; z.b = 0.0;
+            unsigned kp = 0;
+            if (mine && ((live_pair >> i) & 1u)) {
+                const dbl2 u = uniform2(cfg.seed, ST_NOISE, sweep, unit, (uint32_t)(k >> 1));
+                if (is_mut) z = normal2(u, cfg.sigma);
+                else { z.a = -cfg.eps + (cfg.eps - (-cfg.eps)) * u.a; z.b = -cfg.eps + (cfg.eps - (-cfg.eps)) * u.b; }
+                if (use_kappa) {
+                    const dbl2 uk = uniform2(cfg.seed, ST_KAPPA, sweep, unit, (uint32_t)(k >> 1));
+                    kp = (uk.a <= (1.0 - cfg.kappa) ? 1u : 0u) | (uk.b <= (1.0 - cfg.kappa) ? 2u : 0u);
+                }
+            }
+            // the drawer keeps the half of its own parity and sends the other one
+            const double give = (tid & 1) ? z.a : z.b, got = shfl_xor1(give);
+            const unsigned kgot = __shfl_xor_sync(0xffffffffu, kp, 1);
+            const double own = (tid & 1) ? z.b : z.a;
+            const unsigned kbit = ((mine ? kp : kgot) >> (tid & 1)) & 1u;
+            if ((live >> i) & 1u) { nz[i] = mine ? own : got; if (kbit) keep |= 1u << i; }
+        }
+    }
+    co.dependency_wait();
+
+    const double *__restrict__ tcur = ctx.cur_theta + (size_t)p * d;
+    double *__restrict__ prop = ctx.prop_theta + (size_t)p * d;
+    const size_t gbase = (size_t)g * Np;
+    const size_t P_all = (size_t)cfg.P_hist;
+#define DE_SLOT(k) (((k) < j ? ctx.next_theta : ctx.cur_theta) + (gbase + (size_t)(k)) * d)
+#define DE_HIST(r, id) (ctx.hist_theta + ((size_t)(r) * P_all + (size_t)ctx.hist_pos[(size_t)(r) * P_all + (size_t)(id)]) * d)
+#define DE_DONOR(k, r) (cfg.resample ? DE_HIST(r, k) : DE_SLOT(k))
+    double r1 = 0.0, r2 = 0.0;
+    const double *__restrict__ pm = nullptr, *__restrict__ pn = nullptr, *__restrict__ px = nullptr;     // px: the base (DE) or z (snooker)
+    bool has_base = false;
+    double t[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const int k = tid + T * i; t[i] = k < d ? tcur[k] : 0.0; }
+    if (kind == KIND_DE) {
+        pm = DE_DONOR(i1, hr1); pn = DE_DONOR(i2, hr2);
+        has_base = cfg.proposal == 0 && ctx.in_burnin != 0;
+        if (has_base) {
+            if (ctx.exact_base) px = DE_SLOT(i0);
+            else {
+                const double *cw = ctx.base_cw + gbase;
+                const double tt = u_base * ctx.base_tot[g];
+                int found = Np - 1;
+                for (int q0 = 0; q0 < Np - 1; q0 += T) {
+                    const int q = q0 + tid;
+                    const bool hit = q < Np - 1 && !(cw[q] < tt);
+                    const int best = co.min_int(hit ? q : 0x7fffffff);
+                    if (best != 0x7fffffff) { found = best; break; }
+                }
+                px = ctx.cur_theta + (gbase + (size_t)found) * d;
+            }
+        }
+    } else if (kind == KIND_SNOOKER) {
+        px = DE_DONOR(i0, hr0); pm = DE_DONOR(i1, hr1); pn = DE_DONOR(i2, hr2);
+        double v1m = 0.0, v1n = 0.0, v2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int k = tid + T * i;
+            if (k < d) {
+                const double pd = sub(t[i], px[k]);
+                v1m = add(v1m, mul(pm[k], pd));
+                v1n = add(v1n, mul(pn[k], pd));
+                v2 = add(v2, mul(pd, pd));
+            }
+        }
+        v1m = co.sum(v1m); v1n = co.sum(v1n); v2 = co.sum(v2);
+        r1 = v1m / v2; r2 = v1n / v2;
+    }
+#undef DE_DONOR
+#undef DE_HIST
+#undef DE_SLOT
+
+    if (tid == 0) tl_max(tl, TL_Q0);
+    // the proposal: every load first, then the arithmetic and the stores
+    double a[E], b[E], c[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int k = tid + T * i;
+        a[i] = 0.0; b[i] = 0.0; c[i] = 0.0;
+        if (k < d && !is_mut) {
+            if ((live >> i) & 1u) { a[i] = pm[k]; b[i] = pn[k]; }
+            if (kind == KIND_SNOOKER || (has_base && ((live >> i) & 1u))) c[i] = px[k];
+        }
+    }
+    double v[E];
+    double sq1 = 0.0, sq2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int k = tid + T * i;
+        v[i] = 0.0;
+        if (k >= d) continue;
+        const bool lv_ = (live >> i) & 1u;
+        double x;
+        if (!lv_) x = t[i];
+        else if (is_mut) x = add(t[i], nz[i]);
+        else if (kind == KIND_DE) x = de_elem(t[i], a[i], b[i], has_base ? c[i] : t[i], g1, g2, has_base, nz[i]);
+        else x = snooker_elem(t[i], c[i], r1, r2, g1, nz[i]);
+        if (lv_ && ((keep >> i) & 1u)) x = t[i];                              // recombination! (crossover.jl:301-321)
+        if (kind == KIND_SNOOKER) {                                            // adjust_loglike (crossover.jl:268-273)
+            const double aa = sub(x, c[i]), bb = sub(t[i], c[i]);
+            sq1 = add(sq1, mul(aa, aa)); sq2 = add(sq2, mul(bb, bb));
+        }
+        v[i] = x;
+        prop[k] = x;
+        if (ctx.tr_theta) ctx.tr_theta[(size_t)p * d + k] = x;
+    }
+    // (the logarithm a NORMAL_REF prior needs of its sd parameter: once, by the thread that owns the parameter, not by
+    // every warp after the barrier; only when some prior refers to another parameter)
+    if (tid < 4) { s_head[tid] = v[0]; s_headlog[tid] = m.prior_has_ref ? log(v[0]) : 0.0; }
+    __syncthreads();
+    if (tid == 0) tl_max(tl, TL_Q1);
+
+    // bounds, priors and the staging of the likelihood kernel's operands, from the registers
+    const bool stage_hier = bfrag != nullptr && m.kind == M_HIER, stage_mvn = bfrag != nullptr && m.kind == M_MVNORMAL;
+    const double head0 = s_head[0];
+    bool ok = true;
+    double ps = 0.0, msq = 0.0;
+    double ref_sd = qnan(), ref_log = 0.0;
+    // every element's bounds, prior kind and first parameter are fetched before any of them is used (a loop that branches
+    // on the kind it has just loaded runs its four L2 round trips one after the other: 4.4 us of the 8.9 a lone CTA spent
+    // behind the dependency wait); the remaining parameters are only read for the kinds that need them
+    {
+        double lo[E], hi[E], pa[E];
+        int2 kr[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int k = min(tid + T * i, d - 1);
+            lo[i] = cfg.lo[k]; hi[i] = cfg.hi[k];
+            kr[i] = *reinterpret_cast<const int2 *>(&m.prior[k].kind);          // kind, ref
+            pa[i] = m.prior[k].a;
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int k = tid + T * i;
+            if (k >= d) continue;
+            const double x = v[i];
+            ok = ok && (x >= lo[i] && x <= hi[i]);
+            if (kr[i].x == PRIOR_NORMAL_REF) {
+                const double sd = kr[i].y < 4 ? s_head[kr[i].y] : prop[kr[i].y];
+                if (!(sd == ref_sd)) { ref_sd = sd; ref_log = kr[i].y < 4 ? s_headlog[kr[i].y] : log(sd); }
+                const double z = (x - pa[i]) / sd;
+                ps += -(z * z + DE_LOG2PI) / 2.0 - ref_log;
+            } else if (kr[i].x != PRIOR_FLAT) ps += prior_elem(m.prior[k], x, 0.0);
+            else ps += 0.0;
+        }
+    }
+    if (tid == 0) tl_max(tl, TL_Q2);
+    if (stage_hier || stage_mvn) {
+        const int shift = stage_hier ? 2 : 0;                                 // dimension kk of the likelihood is element kk + shift
+        double *__restrict__ bf_row = bfrag + bfrag_base(m, wi);
+        double cen[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) { const int kk = tid + T * i - shift; cen[i] = (kk >= 0 && kk < m.ssd_k) ? m.center[kk] : 0.0; }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const int kk = tid + T * i - shift;
+            if (kk < 0 || kk >= m.ssd_k) continue;
+            const double cm = stage_hier ? (head0 + v[i]) - cen[i] : v[i] - cen[i];
+            msq += cm * cm;
+            bf_row[bfrag_offset(m, wi % SSD_OCT, kk)] = cm;
+        }
+    }
+    const bool inb = __syncthreads_and(ok ? 1 : 0) != 0;
+    if (tid == 0) tl_max(tl, TL_Q3);
+    ps = warp_sum(ps); msq = warp_sum(msq);
+    if (kind == KIND_SNOOKER) { sq1 = warp_sum(sq1); sq2 = warp_sum(sq2); }
+    if ((tid & 31) == 0) { red4[tid >> 5][0] = ps; red4[tid >> 5][1] = msq; red4[tid >> 5][2] = sq1; red4[tid >> 5][3] = sq2; }
+    __syncthreads();
+    if (tid == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { s0 += red4[w][0]; s1 += red4[w][1]; s2 += red4[w][2]; s3 += red4[w][3]; }
+        ctx.prop_prior[p] = s0;
+        ctx.prop_inb[p] = inb ? 1 : 0;
+        ctx.prop_adj[p] = kind == KIND_SNOOKER ? adjust_loglike(s2, s3, d) : 0.0;
+        if (bfrag) stage_scale(m, s1, wi, magic, ctx.ll_acc + p, ctx.ll_q + p, ctx.prop_msq + p);
+        tl_max(tl, TL_P1);
+        if (tl && wi == 0) tl[TL_N] = (unsigned long long)lv.n;
+    }
+}
+
+// DEMCMC_WIDE_SHAPE=<accept digit><propose digit> (A/B runs, tests).  Accept: 0 = 256 threads x 4 CTAs per SM, else 128 x 12 (40 registers, no spills).
+// Propose: 0 = the three-pass kernel at 256 x 4, 2 = at 128 x 8, 5 = the one-pass kernel (also tried: 256 x 6, 128 x 12, 64 x 16: slower)
+// Measured on configs[3] (M updates/s, 60 iterations):
+// 00: 16.6, 22: 17.5, 32: 17.9 (19.3 with the threaded planner), 35: 20.9 -> 21.7 (prior loads hoisted, cheap staging index); the one-pass kernel at 3 / 2 CTAs per SM (80 / 116 registers): 19.9 / 17.1
+static int wide_shape()
+{
+    const char *e = getenv("DEMCMC_WIDE_SHAPE");
+    return e ? atoi(e) : 35;
+}
 static bool wide_enabled(const ConfigDev &cfg)
 {
     const char *e = getenv("DEMCMC_NO_WIDE");
@@ -584,7 +879,16 @@ int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
     if (wide_enabled(cfg) && lv.ctxs) {
         // 256 threads, 4 CTAs per SM (64 registers, a few spills): measured on configs[3] against
         // 2 / 3 CTAs per SM and 512 threads x 1 / 2: 14.9 vs 12.7 / 14.0 / 10.8 / 13.5 M updates/s
-        CU(launch_chained(k_propose_wide<256, 4>, dim3(lv.n), dim3(256), 0, cfg, m, lv, xs ? xs->bfrag : nullptr, xs ? xs->magic : nullptr));
+        double *bf = xs ? xs->bfrag : nullptr, *mg = xs ? xs->magic : nullptr;
+        if (cfg.d <= PW1_T * PW1_E && m.kind != M_MVN_FULL && wide_shape() % 10 >= 5) {
+            CU(launch_chained(k_propose_wide1<4>, dim3(lv.n), dim3(PW1_T), 0, cfg, m, lv, bf, mg, tl_slot()));
+            LAUNCHED("k_propose_wide1");
+            return 0;
+        }
+        switch (wide_shape() % 10) {
+        case 2: CU(launch_chained(k_propose_wide<128, 8>, dim3(lv.n), dim3(128), 0, cfg, m, lv, bf, mg, tl_slot())); break;
+        default: CU(launch_chained(k_propose_wide<256, 4>, dim3(lv.n), dim3(256), 0, cfg, m, lv, bf, mg, tl_slot())); break;
+        }
         LAUNCHED("k_propose_wide");
         return 0;
     }
@@ -597,7 +901,10 @@ int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     const int blocks = (lv.n * 32 + PA_THREADS - 1) / PA_THREADS;
     if (wide_enabled(cfg) && lv.ctxs) {
-        CU(launch_chained(k_accept_wide<256>, dim3(lv.n), dim3(256), 0, cfg, m, lv));
+        switch (wide_shape() / 10) {
+        case 0: CU(launch_chained(k_accept_wide<256, 4>, dim3(lv.n), dim3(256), 0, cfg, m, lv, tl_slot())); break;
+        default: CU(launch_chained(k_accept_wide<128, 12>, dim3(lv.n), dim3(128), 0, cfg, m, lv, tl_slot())); break;
+        }
         LAUNCHED("k_accept_wide");
         if (g_tl_cap > 0) ++g_tl_level;
         return 0;
@@ -640,6 +947,27 @@ int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *
 {
     k_base_prep<<<cfg.G_local, 128, 0, stream()>>>(cfg, w, th, cw, tot);
     LAUNCHED("k_base_prep");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the state-independent draws of a whole chunk (de_types.h: PlanRec), one thread per (sweep, particle)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_plan(ConfigDev cfg, const SweepCtx *ctxs, int n_sw, int P)
+{
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n_sw * P) return;
+    const int s = t / P, p = t - s * P;
+    const SweepCtx &ctx = ctxs[s];
+    if (ctx.plan) ctx.plan[p] = make_plan(cfg, ctx, p);
+}
+
+int launch_plan(const ConfigDev &cfg, const SweepCtx *d_ctxs, int n_sw)
+{
+    const int P = cfg.G_local * cfg.Np;
+    k_plan<<<(n_sw * P + 127) / 128, 128, 0, stream()>>>(cfg, d_ctxs, n_sw, P);
+    LAUNCHED("k_plan");
+    g_break_chain = true;
     return 0;
 }
 
@@ -818,6 +1146,7 @@ __global__ void __launch_bounds__(PW_THREADS) k_ll_pointwise(ModelDev m, const d
 constexpr int XD_THREADS = 128;
 constexpr int XD_STAGES = 4;
 constexpr int XD_CTAS_PER_SM = 2;
+constexpr int XD_KPC_MAX_TILES = 8;   // observation streams this short take several dimension splits per CTA (XdGrid::kpc)
 constexpr int XD_MIN_TILES = 4;          // observation tiles a CTA should at least stream (amortises its prologue)
 constexpr int XD_WAVE_TILES = 48;        // observation tiles per CTA when a level needs several waves
 
@@ -888,7 +1217,10 @@ static XdStage *xd_stage(const ModelDev &m, int n)
 
 // how the CTAs of one launch are dealt to the particle tiles of a level
 // n_hi tiles of oct_hi octets with c_hi CTAs each, then n_lo tiles of oct_lo octets with c_lo CTAs each
-struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo; };
+// kpc: dimension splits one CTA walks (1 unless the observation stream is a few tiles long: the hierarchical model with 50
+// observations per subject has ONE tile and 20 splits of 52 subjects -- a CTA per (particle tile, split) is all launch
+// latency, 1160 CTAs in four waves for a level of 1834 updates; its CTAs take several splits each so the level fits one wave)
+struct XdGrid { int32_t n_hi, oct_hi, c_hi, n_lo, oct_lo, c_lo, kpc; };
 
 // Where one warp of k_xdot / k_chunk_persist keeps its operand ring: the warp's index inside its
 // 4-warp CTA (= the row pair it owns), the dimension split, the ring and its `full` barriers, and the
@@ -1057,7 +1389,7 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int warp = threadIdx.x >> 5;
     const uint32_t stage_doubles = (uint32_t)m.ssd_nj * 64;
     XdWarp xw;
-    xw.warp = warp; xw.ks = blockIdx.y; xw.it_base = 0;
+    xw.warp = warp; xw.ks = 0; xw.it_base = 0;
     xw.ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
     xw.full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
     if ((threadIdx.x & 31) == 0) {
@@ -1066,17 +1398,22 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const PdlWait wait;
-    const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + blockIdx.y) * m.ssd_nj) * 32, *msrc = magic + (size_t)oct0 * SSD_OCT;
+    const double *msrc = magic + (size_t)oct0 * SSD_OCT;
     const size_t bstride = (size_t)m.n_ksplit * m.ssd_nj * 32;
+    const int ks_end = min(m.n_ksplit, ((int)blockIdx.y + 1) * g.kpc);
+    for (int ks = blockIdx.y * g.kpc; ks < ks_end; ++ks) {                 // (the operand ring carries over: xw.it_base)
+        xw.ks = ks;
+        const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + ks) * m.ssd_nj) * 32;
 #define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
-    if (m.ssd_nj == SSD_NJ && m.ssd_half) {
-        switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
-    } else if (m.ssd_nj == SSD_NJ) {
-        switch (noct) { case 4: XD_CALL(4, SSD_NJ, false); break; case 3: XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
-    } else {
-        switch (noct) { case 4: XD_CALL(4, 0, false); break; case 3: XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
-    }
+        if (m.ssd_nj == SSD_NJ && m.ssd_half) {
+            switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
+        } else if (m.ssd_nj == SSD_NJ) {
+            switch (noct) { case 4: XD_CALL(4, SSD_NJ, false); break; case 3: XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
+        } else {
+            switch (noct) { case 4: XD_CALL(4, 0, false); break; case 3: XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
+        }
 #undef XD_CALL
+    }
 }
 
 // centred means of arbitrary parameter vectors in the k_xdot layout (demcmc_eval, initial weights)
@@ -1125,6 +1462,12 @@ static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
         // several waves: many short CTAs, the hardware scheduler balances them as slots free up
         g.c_hi = g.c_lo = std::min(c_max, std::max(1, n_tiles / XD_WAVE_TILES));
     }
+    g.kpc = 1;
+    if (n_tiles <= XD_KPC_MAX_TILES && m.n_ksplit > 1) {
+        static const int kpc_env = [] { const char *e = getenv("DEMCMC_XD_KPC"); return e ? atoi(e) : 0; }();     // A/B runs: 1 = off
+        const int64_t ctas = (int64_t)(g.n_hi * g.c_hi + g.n_lo * g.c_lo) * m.n_ksplit;
+        g.kpc = kpc_env > 0 ? std::min(kpc_env, (int)m.n_ksplit) : (int)std::min<int64_t>(m.n_ksplit, std::max<int64_t>(1, (ctas + slots - 1) / slots));
+    }
     return g;
 }
 
@@ -1137,7 +1480,7 @@ static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, lo
         attr_set[g_dev] = true;
     }
     const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
-    dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)m.n_ksplit);
+    dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)((m.n_ksplit + g.kpc - 1) / g.kpc));
     CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, lv.ctxs ? tl_slot() : (unsigned long long *)nullptr, lv.ctxs ? tl_cta() : (unsigned long long *)nullptr));
     LAUNCHED("k_xdot");
     return 0;

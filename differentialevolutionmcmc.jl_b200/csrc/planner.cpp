@@ -1,6 +1,8 @@
 // planner.cpp -- see planner.h
 #include "planner.h"
 #include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include "de_math.h"
 
 namespace de {
@@ -15,12 +17,22 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
     std::vector<int32_t> level((size_t)n_sweeps * P, 0), prev(P, -1), cur(P, 0);
     // dependencies of every update as update indices (sweep * P + position), for the shaping pass below
     std::vector<int32_t> deps((size_t)n_sweeps * P * 4, -1);
+    // Groups never read each other inside a chunk, so their level assignments are independent: large plans (the Philox
+    // draws of plan_particle dominate: ~40 ns per update, 5 ms for 16 sweeps of 8192 particles) are split over a few host
+    // threads by group range.  The result does not depend on the split.
+    int n_thr = 1;
+    if ((size_t)n_sweeps * P >= 16384 && G >= 2) {
+        static const int hw = [] { const char *e = getenv("DEMCMC_PLAN_THREADS"); const int v = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2; return std::max(1, std::min(v, 8)); }();
+        n_thr = std::min(hw, G);
+    }
+    std::vector<int> max_level_thr(n_thr, 0);
+    auto plan_groups = [&](int tix, int g_lo, int g_hi) {
     int max_level = 0;
     for (int s = 0; s < n_sweeps; ++s) {
         const uint32_t sweep = sweep0 + (uint32_t)s * (uint32_t)in.sweep_stride;
         const uint8_t *tk = in.t_kind ? in.t_kind + (size_t)s * stride + in.pos_offset : nullptr;
         const int32_t *ti = in.t_idx ? in.t_idx + ((size_t)s * stride + in.pos_offset) * 3 : nullptr;
-        for (int g = 0; g < G; ++g) {
+        for (int g = g_lo; g < g_hi; ++g) {
             const int gg = in.group_begin + g;
             bool mutate;
             if (tk) mutate = tk[g * Np] == KIND_MUTATION;
@@ -59,8 +71,17 @@ void plan_chunk(const PlanInput &in, uint32_t sweep0, int32_t n_sweeps, const bo
                 max_level = std::max(max_level, l);
             }
         }
-        prev = cur;
+        std::copy(cur.begin() + (size_t)g_lo * Np, cur.begin() + (size_t)g_hi * Np, prev.begin() + (size_t)g_lo * Np);
     }
+    max_level_thr[tix] = max_level;
+    };
+    if (n_thr == 1) plan_groups(0, 0, G);
+    else {
+        std::vector<std::thread> thr;
+        for (int t = 0; t < n_thr; ++t) thr.emplace_back(plan_groups, t, (int)((int64_t)t * G / n_thr), (int)((int64_t)(t + 1) * G / n_thr));
+        for (auto &t : thr) t.join();
+    }
+    int max_level = *std::max_element(max_level_thr.begin(), max_level_thr.end());
     // Capacity: levels of at most level_cap updates.  (sweep, slot) order is a topological order of the dependencies
     // (own previous update, donors with a smaller slot of this sweep, donors with a larger slot of the previous one),
     // so every update can simply take the first level after its dependencies that still has room.

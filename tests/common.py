@@ -82,7 +82,7 @@ def halfcauchy(rng):
     return abs(rng.standard_cauchy())
 
 
-def make_case(name, rng, n_obs=None, n_subjects=9):
+def make_case(name, rng, n_obs=None, n_subjects=9, n_dim=None):
     if name == "gaussian":
         n = n_obs or 50
         x = rng.normal(0.0, 1.0, n)
@@ -90,7 +90,7 @@ def make_case(name, rng, n_obs=None, n_subjects=9):
                     lambda r: [r.normal(), halfcauchy(r)], dict(x=x))
     if name == "mvnormal":
         n = n_obs or 200
-        dm = 7
+        dm = n_dim or 7
         mu = rng.normal(size=dm)
         x = rng.normal(mu, 1.0, size=(n, dm))
         return Case(name, "mvnormal", dm + 1, [("normal", 0, 1)] * dm + [("halfcauchy", 0, 1)], [-INF] * dm + [0],

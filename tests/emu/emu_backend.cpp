@@ -206,6 +206,16 @@ int launch_base_prep(const ConfigDev &cfg, const double *w, double *th, double *
     return 0;
 }
 
+int launch_plan(const ConfigDev &cfg, const SweepCtx *ctxs, int n_sw)
+{
+    ++g_launches;
+    const int P = cfg.G_local * cfg.Np;
+    for (int s = 0; s < n_sw; ++s)
+        if (ctxs[s].plan)
+            for (int p = 0; p < P; ++p) ctxs[s].plan[p] = make_plan(cfg, ctxs[s], p);
+    return 0;
+}
+
 int launch_propose(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
 {
     ++g_launches;

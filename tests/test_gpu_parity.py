@@ -536,6 +536,44 @@ def test_wide_kernels_long_parameter_vectors(mode, monkeypatch):
     assert np.allclose(outs[0][2][fin], outs[1][2][fin], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("mode", ["replay", "native"])
+@pytest.mark.parametrize("model,kw", [
+    ("hier_normal", dict(blocks=True, theta_snooker=0.2, alpha=0.3)),            # blocks + snooker + the NORMAL_REF prior
+    ("hier_normal", dict(theta_snooker=0.15, kappa=0.7, burnin=6)),              # recombination + the burn-in base term
+    ("mvnormal", dict(theta_snooker=0.1, alpha=0.3, kappa=0.9)),                 # d = 301: the means staged from registers
+])
+def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
+    """k_propose_wide1 (four elements per thread, one pass, d <= 1024): the oracle's accept decisions and values, and
+    the chain of the three-pass kernel k_propose_wide (same per-element arithmetic, other summation order for the mean
+    square only)."""
+    kw = dict(kw)
+    rng = np.random.default_rng(67)
+    if model == "hier_normal":
+        case = make_case("hier_normal", rng, n_obs=12, n_subjects=297)           # d = 300: last pair of elements incomplete
+        if kw.pop("blocks", False):
+            kw["blocks"] = hier_blocks(case.d - 3)
+    else:
+        case = make_case("mvnormal", rng, n_obs=300, n_dim=300)
+    kw.setdefault("burnin", 4)
+    monkeypatch.setenv("DEMCMC_WIDE_SHAPE", "5")
+    r, out = forced_run(case, 2, 9, 8, mode, **kw)
+    check(r, out)
+    theta0 = case.theta0(np.random.default_rng(3), 2 * 9)
+    outs, names = [], []
+    for shape in ("0", "32", "35"):
+        monkeypatch.setenv("DEMCMC_WIDE_SHAPE", shape)
+        h = case.handle(2, 9, seed=4, **kw)
+        h.set_state(theta0)
+        h.run(12)
+        outs.append((h.samples(), h.accept(), h.lp()))
+        h.close()
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][1], other[1])
+        assert np.allclose(outs[0][0], other[0], rtol=1e-9, atol=1e-12)
+        fin = np.isfinite(outs[0][2])
+        assert np.allclose(outs[0][2][fin], other[2][fin], rtol=1e-9, atol=1e-9)
+
+
 # ---- the optimize path (optimize.jl; maximize! / minimize! + evaluate_fun!) -------------------------
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
