@@ -306,7 +306,12 @@ int d2h(void *dst, const void *src, size_t bytes)
     if (!bytes) return 0;
     static long long staged_min = -1;
     if (staged_min < 0) { const char *e = getenv("DEMCMC_D2H_STAGED_MIN_MB"); staged_min = (long long)(e ? atoi(e) : 4) << 20; }   // 8.7 MB of chains: 3.3 ms through the driver's pageable path, 1.2-1.8 ms staged
-    if ((long long)bytes >= staged_min) return d2h_staged(dst, src, bytes);
+    if ((long long)bytes >= staged_min) {
+        // a page-locked destination (Handle.chains() allocates one when it can) takes the copy engine directly
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) { (void)cudaGetLastError(); return d2h_staged(dst, src, bytes); }
+    }
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
     CU(cudaStreamSynchronize(stream()));
     return 0;
@@ -1238,7 +1243,7 @@ struct XdWarp { int warp, ks; double *ring; uint64_t *full; uint32_t it_base; };
 template <int NOCT, int NJC, bool HALF, int STAGES, class HOOKS>
 __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc, size_t b_oct_stride, const double *msrc, const Level &lv,
                                           long long *ll_acc, int oct0, int T0, int T1, XdWarp &xw, const HOOKS &dependency_wait,
-                                          unsigned long long *tl, unsigned long long *tlc)
+                                          unsigned long long *tl, unsigned long long *tlc, int pre_issued = 0)
 {
     const int tid = threadIdx.x, warp = xw.warp, lane = tid & 31, ks = xw.ks;
     const int nj = NJC ? NJC : m.ssd_nj;
@@ -1252,7 +1257,7 @@ __device__ __forceinline__ void xdot_body(const ModelDev &m, const double *bsrc,
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s)
+        for (int s = pre_issued; s < STAGES; ++s)            // (pre_issued: the caller has requested the first tiles already)
             if (T0 + s < T1) {
                 const uint32_t st = (it_base + (uint32_t)s) % STAGES;
                 mbar_expect_tx(&full[st], stage_bytes);
@@ -1401,10 +1406,20 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const double *msrc = magic + (size_t)oct0 * SSD_OCT;
     const size_t bstride = (size_t)m.n_ksplit * m.ssd_nj * 32;
     const int ks_end = min(m.n_ksplit, ((int)blockIdx.y + 1) * g.kpc);
+    // one observation tile per split (<= 64 observations per dimension) and no more splits than ring stages: every split's
+    // tile is requested up front, so the later ones arrive while the earlier ones are multiplied
+    const bool ahead = n_tiles == 1 && g.kpc > 1 && g.kpc <= XD_STAGES;
+    if (ahead && (threadIdx.x & 31) == 0) {
+        int i = 0;
+        for (int ks = blockIdx.y * g.kpc; ks < ks_end; ++ks, ++i) {
+            mbar_expect_tx(&xw.full[i], stage_doubles * (uint32_t)sizeof(double));
+            bulk_g2s(xw.ring + (size_t)i * stage_doubles, m.xT + ((size_t)(ks * 4 + warp) * m.ssd_nj) * 64, stage_doubles * (uint32_t)sizeof(double), &xw.full[i]);
+        }
+    }
     for (int ks = blockIdx.y * g.kpc; ks < ks_end; ++ks) {                 // (the operand ring carries over: xw.it_base)
         xw.ks = ks;
         const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + ks) * m.ssd_nj) * 32;
-#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc)
+#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc, ahead ? 1 : 0)
         if (m.ssd_nj == SSD_NJ && m.ssd_half) {
             switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
         } else if (m.ssd_nj == SSD_NJ) {

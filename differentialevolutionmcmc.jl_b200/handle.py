@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _ffi
@@ -13,6 +15,22 @@ UPDATES = {"mh": 0, "maximize": 1, "minimize": 2}
 FITNESS = {"posterior": 0, "fun": 1}
 PRIORS = {"flat": 0, "normal": 1, "halfcauchy": 2, "uniform": 3, "beta": 4, "normal_ref": 5}
 PROPOSALS = {"random_gamma": 0, "fixed_gamma": 1, "variable_gamma": 2}
+
+
+def _out_empty(shape):
+    """The array a large download lands in.  DEMCMC_PINNED_OUT=1: page-locked memory from torch's caching host allocator, which
+    the copy engine writes directly -- worth it only for callers that drop each result before the next call (the allocator
+    can then reuse the block; pinning a fresh 222 MB block costs 115 ms, five times the pageable download).  Default: numpy
+    memory through the library's pipelined staging copy."""
+    n = int(np.prod(shape))
+    if n * 8 >= (1 << 20) and os.environ.get("DEMCMC_PINNED_OUT", "0") == "1":
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy().reshape(shape)
+        except Exception:                                    # noqa: BLE001 -- no torch, no CUDA runtime in torch: pageable
+            pass
+    return np.empty(shape)
 
 
 class Handle:
@@ -194,7 +212,7 @@ class Handle:
         """bundle_samples on the device: array of shape (P, d+2, n_rows) in Julia memory order, i.e.
         out[c, k, r] == Julia Array(n_rows, d+2, P)[r+1, k+1, c+1] of iterations row0+r."""
         n = self.stored_iterations - row0 if n_rows is None else n_rows
-        out = np.empty((self.P, self.d + 2, max(n, 0)))
+        out = _out_empty((self.P, self.d + 2, max(n, 0)))
         if n > 0:
             check(_ffi.lib().demcmc_get_chains(self._h, int(row0), int(n), ptr(out, _dp)))
         return out
