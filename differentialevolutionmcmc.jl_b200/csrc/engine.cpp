@@ -486,7 +486,11 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->n0 = cfg->n_initial;
     h->k_store = std::max(1, cfg->store_every);
     h->n_scratch = (h->k_store > 1 || cfg->n_blocks > 0) ? MAX_CHUNK + 2 : 3;      // chunks of overlapped block sweeps write scratch rows too
-    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), 2));   // A/B measurements
+    // long parameter vectors (the wide kernels, one CTA per particle): two chains of kernels over two halves of the groups
+    // overlap one half's latency-bound likelihood launch with the other's issue-bound proposals (configs[3]: 21.7 -> 23.7 M
+    // updates/s; 3 / 4 lanes: 19.3 / 18.4; configs[4]'s shard, d = 101: no gain)
+    if (cfg->d >= 256) h->n_lanes = 2;
+    if (const char *e = getenv("DEMCMC_LANES")) h->n_lanes = std::max(1, std::min<int>(atoi(e), be::MAX_LANES));   // A/B measurements
     h->G_local = cfg->group_count > 0 ? cfg->group_count : cfg->n_groups;
     if (cfg->group_begin < 0 || cfg->group_begin + h->G_local > cfg->n_groups) { delete h; return fail(DEMCMC_EINVAL, "group shard out of range"); }
     h->P = h->G_local * cfg->Np;
@@ -513,8 +517,11 @@ int demcmc_create(const demcmc_config *cfg, demcmc_handle **out)
     h->prop_msq = (double *)be::dmalloc(sizeof(double) * P);
     h->prop_inb = (uint8_t *)be::dmalloc(P);
     {
-        const char *e = getenv("DEMCMC_NO_PLAN");             // A/B runs: draw the plans inside the level kernels
-        if (!(e && e[0] == '1')) h->plan_recs = (PlanRec *)be::dmalloc(sizeof(PlanRec) * (size_t)MAX_CHUNK * P);
+        // only where one CTA per particle repeats the draws in every warp (the wide kernels, d >= 256: +1 % on configs[3]);
+        // with one warp per particle the launch costs more than it saves (configs[0]: -6 %).  DEMCMC_PLAN=1 / 0 forces it.
+        const char *e = getenv("DEMCMC_PLAN");
+        const bool on = e ? e[0] == '1' : d >= 256;
+        if (on) h->plan_recs = (PlanRec *)be::dmalloc(sizeof(PlanRec) * (size_t)MAX_CHUNK * P);
     }
     h->ll_acc = (long long *)be::dmalloc(sizeof(long long) * P);
     h->ll_q = (double *)be::dmalloc(sizeof(double) * P);
@@ -1013,7 +1020,7 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // runs the handle's lanes (default 1) as concurrent kernel chains
         const bool skip_stream = h->suffstat && ssd_model;       // B == 0 analytically: propose -> accept, nothing streamed
         const int persist_lanes = skip_stream ? 0 : be::chunk_persist_lanes(h->dcfg, h->dmodel);
-        const int n_lanes = persist_lanes ? persist_lanes : ((h->n_lanes > 1 && G >= 2) ? 2 : 1);
+        const int n_lanes = persist_lanes ? persist_lanes : std::max(1, std::min(h->n_lanes, G));
         int32_t lane_off[be::MAX_LANES + 1] = { 0 };              // entries of each lane in u.d_order
         std::vector<uint8_t> mut((size_t)n_sw * G, 0);
         for (int ln = 0; ln < n_lanes; ++ln) {
@@ -1577,7 +1584,7 @@ int demcmc_set_lanes(demcmc_handle *h, int32_t n_lanes)
 {
     if (!h || n_lanes < 1) return fail(DEMCMC_EINVAL, "bad argument");
     if (h->multi) return for_kids(h, [&](demcmc_handle *k, int) { return demcmc_set_lanes(k, n_lanes); }, false);
-    h->n_lanes = std::min<int32_t>(n_lanes, 2);
+    h->n_lanes = std::min<int32_t>(n_lanes, be::MAX_LANES);
     return 0;
 }
 

@@ -602,6 +602,12 @@ def test_thinned_resample_runs_on_the_stored_rows():
     E.test_thinned_resample_runs_on_the_stored_rows(None)
 
 
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.25, alpha=0.4, burnin=6)), ("gaussian", dict(kappa=0.8)),
+                                      ("mvnormal", dict(resample=True, theta_snooker=0.2, burnin=3))])
+def test_plan_records_equal_the_draws_made_in_place(model, kw, monkeypatch):
+    E.test_plan_records_equal_the_draws_made_in_place(None, model, kw, monkeypatch)
+
+
 def test_thinned_run_through_the_persistent_kernel():
     """configs[1]-like shape: chunks of 16 overlapped sweeps write 15 scratch rows + 1 history row each"""
     rng = np.random.default_rng(6)

@@ -715,3 +715,32 @@ def test_background_model_binding_reports_its_errors(emu):
         D.sample(model, de, 5)
     good = D.DEModel(sample_prior=model.sample_prior, prior_loglike=model.prior_loglike, loglike=D.GPULoglike("mvnormal_full", x, cov=np.eye(4)), names=("μ", "σ"))
     assert len(D.sample(good, de, 5)) == 5
+
+
+@pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.25, alpha=0.4, burnin=6)), ("gaussian", dict(kappa=0.8)),
+                                      ("mvnormal", dict(resample=True, theta_snooker=0.2, burnin=3))])
+def test_plan_records_equal_the_draws_made_in_place(emu, model, kw, monkeypatch):
+    """DEMCMC_PLAN=1: kind, donors, gammas and the accept uniform of a whole chunk are drawn by one launch (PlanRec) and
+    read back by the level kernels; the chain is the one of the in-place draws, bit for bit"""
+    rng = np.random.default_rng(31)
+    case = make_case(model, rng)
+    kw = dict(kw)
+    G, Np, n0 = 3, 6, 5
+    rows = np.stack([case.theta0(rng, G * Np) for _ in range(n0)]) if kw.get("resample") else None
+    if rows is not None:
+        kw["n_initial"] = n0
+    th0 = case.theta0(rng, G * Np)
+    outs = []
+    for plan in ("0", "1"):
+        monkeypatch.setenv("DEMCMC_PLAN", plan)
+        with case.handle(G, Np, seed=9, **kw) as h:
+            if rows is not None:
+                h.set_history(rows)
+                h.set_state(None)
+            else:
+                h.set_state(th0)
+            h.run(23)
+            outs.append((h.samples(), h.accept(), h.lp(), h.counters()["kernel_launches"]))
+    assert outs[1][3] > outs[0][3]                            # the plan launches happened
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert np.array_equal(a, b, equal_nan=True)
