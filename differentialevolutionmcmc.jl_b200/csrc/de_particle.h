@@ -241,13 +241,30 @@ DE_PRAGMA_UNROLL
     // arithmetic are skipped -- the draws are counter-based, so skipping one does not move the others.  With two blocks of
     // 3 and 1000 parameters (Hierarchical_Example.jl:88-92) every other sweep proposes 3 elements instead of 1003.
     auto live = [&](int k) { return !mask || mask[k] != 0; };
+    // the lane's first PROP_PRE elements: every operand is requested before any element is computed (a store sits between
+    // two elements, so the compiler cannot move the next element's loads above it: the elements' L2 round trips ran one
+    // after the other -- with d <= 64 on a warp that is the whole proposal)
+    double pre_t[PROP_PRE], pre_m[PROP_PRE], pre_n[PROP_PRE], pre_x[PROP_PRE];
+DE_PRAGMA_UNROLL
+    for (int q = 0; q < PROP_PRE; ++q) {
+        const int k = co.lane() + q * co.width();
+        pre_t[q] = 0.0; pre_m[q] = 0.0; pre_n[q] = 0.0; pre_x[q] = 0.0;
+        if (k < d) {
+            pre_t[q] = tcur[k];
+            if (!is_mut && live(k)) {
+                if (kind == KIND_DE) { pre_m[q] = pm[k]; pre_n[q] = pn[k]; if (has_base) pre_x[q] = pb[k]; }
+            }
+            if (kind == KIND_SNOOKER) pre_x[q] = pz[k];
+        }
+    }
     auto body = [&](int q, int k, double nz, double lo, double hi, const Prior &pr) {
-        const double t = tcur[k];
+        const bool pre = q < PROP_PRE;
+        const double t = pre ? pre_t[q] : tcur[k];
         double v;
         if (!live(k)) v = t;
         else if (is_mut) v = add(t, nz);                                       // utilities.jl:291-298
-        else if (kind == KIND_DE) v = de_elem(t, pm[k], pn[k], has_base ? pb[k] : t, g1, g2, has_base, nz);
-        else v = snooker_elem(t, pz[k], r1, r2, g1, nz);
+        else if (kind == KIND_DE) v = de_elem(t, pre ? pre_m[q] : pm[k], pre ? pre_n[q] : pn[k], has_base ? (pre ? pre_x[q] : pb[k]) : t, g1, g2, has_base, nz);
+        else v = snooker_elem(t, pre ? pre_x[q] : pz[k], r1, r2, g1, nz);
         if (!is_mut && live(k)) {
             if (cfg.kappa != 1.0) {                                            // recombination! (crossover.jl:301-321)
                 const bool keep = ctx.replay ? ctx.t_keep[(size_t)p * d + k] != 0 : keep_elem(cfg.seed, ctx.sweep, unit, k, cfg.kappa);
@@ -255,7 +272,8 @@ DE_PRAGMA_UNROLL
             }
         }
         if (kind == KIND_SNOOKER) {                                            // adjust_loglike (crossover.jl:268-273)
-            const double a = sub(v, pz[k]), b = sub(t, pz[k]);
+            const double z = pre ? pre_x[q] : pz[k];
+            const double a = sub(v, z), b = sub(t, z);
             sq1 = add(sq1, mul(a, a)); sq2 = add(sq2, mul(b, b));
         }
         ok = ok && (v >= lo && v <= hi);
@@ -333,7 +351,14 @@ DE_HD void accept_particle(const C &co, const ConfigDev &cfg, const ModelDev &m,
     const bool acc = cfg.update == UPDATE_MAXIMIZE ? wprop > wcur : cfg.update == UPDATE_MINIMIZE ? wprop < wcur : accept(wprop, wcur, adj, u);
     double *dst = ctx.next_theta + (size_t)p * d;
     const double *src = acc ? prop : tcur;                     // (uniform over the lanes: only the row that is kept is read)
-    for (int k = co.lane(); k < d; k += co.width()) dst[k] = src[k];
+    {
+        double r[PROP_PRE];                                    // (both loads before the first store: one round trip for d <= 2 lanes' widths)
+DE_PRAGMA_UNROLL
+        for (int q = 0; q < PROP_PRE; ++q) { const int k = co.lane() + q * co.width(); r[q] = k < d ? src[k] : 0.0; }
+DE_PRAGMA_UNROLL
+        for (int q = 0; q < PROP_PRE; ++q) { const int k = co.lane() + q * co.width(); if (k < d) dst[k] = r[q]; }
+    }
+    for (int k = co.lane() + PROP_PRE * co.width(); k < d; k += co.width()) dst[k] = src[k];
     if (co.lane() == 0) {
         ctx.next_w[p] = acc ? wprop : wcur;
         ctx.next_id[p] = ctx.cur_id[p];
