@@ -1528,7 +1528,8 @@ constexpr int PK_MAX_TILES = 8192;
 constexpr int PK_WARPS = 16;                    // per CTA: 4 per SM sub-partition, 128 registers each at launch
 constexpr int PK_THREADS = PK_WARPS * 32;
 constexpr int PK_REGS_DMMA = 216, PK_REGS_HELPER = 56, PK_REGS_IDLE = 24;   // per sub-partition 2 * 216 + 56 + 24 = 512 = 4 * 128, the launch allocation
-constexpr int PK_SCALAR_CTAS = 6;               // CTAs (SMs) given to the scalar warps: 96 warps, one update each per level of ~100
+constexpr int PK_SCALAR_CTAS = 6;               // CTAs (SMs) given to the scalar warps: 96 warps, one update each per level of ~100 (7 / 8 CTAs, so that no warp has two
+                                                // proposals in a level of 112: the proposal phase 16 -> 9 us, but 2.73 against 2.83 M updates/s -- the DMMA items deal worse over 141 SMs)
 
 struct PLevel { int32_t order_off, n, n_items, dep, tile_base, pad; XdGrid g; };
 struct PChunk {
