@@ -141,6 +141,38 @@ def sample(model: DEModel, de: DE, *args, device=None, unique_id=None):
     return bundle_samples(model, de, samples, accept, lp, final_ids, shapes, n_iter)
 
 
+_stage = [None]                                              # page-locked staging tensor, kept for the life of the process
+
+
+def _download(t):
+    """GPU tensor -> fresh numpy array through a cached page-locked staging block (torch's .cpu() into pageable memory
+    ran at 2 GB/s: 8 ms for the 17 MB bundle of a 20-iteration, 2-GPU run); 16 MB chunks, the copy of chunk c into the
+    array overlapping the transfer of chunk c + 1."""
+    import torch
+    flat = t.contiguous().view(-1)
+    out = np.empty(tuple(t.shape), dtype=np.float64)
+    n = flat.numel()
+    if n == 0:
+        return out
+    chunk = 2 << 20                                         # doubles per staging half: 16 MB
+    if _stage[0] is None:
+        _stage[0] = torch.empty(2 * chunk, dtype=torch.float64, pin_memory=True)
+    st, dst = _stage[0], out.reshape(-1)
+    ev = [torch.cuda.Event(), torch.cuda.Event()]
+    spans = [(o, min(chunk, n - o)) for o in range(0, n, chunk)]
+    for c, (o, m) in enumerate(spans[:1]):
+        st[:m].copy_(flat[o:o + m], non_blocking=True); ev[0].record()
+    for c, (o, m) in enumerate(spans):
+        if c + 1 < len(spans):
+            o2, m2 = spans[c + 1]
+            h2 = ((c + 1) & 1) * chunk
+            st[h2:h2 + m2].copy_(flat[o2:o2 + m2], non_blocking=True); ev[(c + 1) & 1].record()
+        ev[c & 1].synchronize()
+        h = (c & 1) * chunk
+        dst[o:o + m] = st[h:h + m].numpy()
+    return out
+
+
 def _bundle_on_gpu(model, de, th, w, ids, acc, init_rows, shapes, n_iter, P, d):
     """The by-id merge and bundle_samples (src/main.jl:222-250, by-position quirk of "acceptance" / "lp" included) as
     index operations on rank 0's GPU, where the gathered history already is; ONE download of the array the Chains wrap,
@@ -168,7 +200,7 @@ def _bundle_on_gpu(model, de, th, w, ids, acc, init_rows, shapes, n_iter, P, d):
         arr[:, :d, :] = samples[:, :, offset:offset + Ns]
         arr[:, d, :] = accept[final_ids, offset:offset + Ns]
         arr[:, d + 1, :] = lp[final_ids, offset:offset + Ns]
-    host = arr.cpu().numpy()
+    host = _download(arr)
     de.samples = host[:, :d, :]
     names = _flat_names(model.names, shapes) + ["acceptance", "lp"]
     return Chains(host.transpose(2, 1, 0), names, [str(n) for n in model.names])
