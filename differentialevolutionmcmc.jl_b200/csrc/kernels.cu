@@ -1189,9 +1189,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-static size_t xdot_smem_bytes(int nj)
+static size_t xdot_smem_bytes(int nj, int stages = XD_STAGES)
 {
-    return (size_t)4 * XD_STAGES * nj * 64 * sizeof(double) + sizeof(uint64_t) * 4 * XD_STAGES;
+    return (size_t)4 * stages * nj * 64 * sizeof(double) + sizeof(uint64_t) * 4 * stages;
 }
 
 static size_t xd_bfrag_doubles(const ModelDev &m, int n) { return (size_t)((n + SSD_OCT - 1) / SSD_OCT) * m.n_ksplit * m.ssd_nj * 32; }
@@ -1378,8 +1378,14 @@ struct PdlWait {
     __device__ __forceinline__ void item_end() const {}
 };
 
-__global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m, const double *bfrag, const double *magic, Level lv,
-                                                                     long long *ll_acc, XdGrid g, unsigned long long *tl, unsigned long long *tlc)
+// STAGES / MAXOCT / MINB: <XD_STAGES, 4, XD_CTAS_PER_SM> is the streaming kernel (long observation streams: four-octet tiles, a
+// four-stage ring, 252 registers, two CTAs per SM).  <2, 2, 4> serves streams of a few tiles (the hierarchical model's 50
+// observations per subject are ONE tile): an item there is all latency -- B-fragment loads, 104 DMMAs, the flush -- so tiles of
+// at most two octets at <= 128 registers and a two-stage ring put four CTAs on an SM instead of two.  The DMMA chains (octet,
+// row pair, observation tile, dimension split) are the same in both, hence the same fixed-point totals.
+template <int STAGES, int MAXOCT, int MINB>
+__global__ void __launch_bounds__(XD_THREADS, MINB) k_xdot_t(ModelDev m, const double *bfrag, const double *magic, Level lv,
+                                                             long long *ll_acc, XdGrid g, unsigned long long *tl, unsigned long long *tlc)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_launch_dependents();
@@ -1395,11 +1401,11 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const uint32_t stage_doubles = (uint32_t)m.ssd_nj * 64;
     XdWarp xw;
     xw.warp = warp; xw.ks = 0; xw.it_base = 0;
-    xw.ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * XD_STAGES * stage_doubles;
-    xw.full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * XD_STAGES * stage_doubles) + warp * XD_STAGES;
+    xw.ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * STAGES * stage_doubles;
+    xw.full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)4 * STAGES * stage_doubles) + warp * STAGES;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int s = 0; s < XD_STAGES; ++s) mbar_init(&xw.full[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&xw.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const PdlWait wait;
@@ -1408,7 +1414,7 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     const int ks_end = min(m.n_ksplit, ((int)blockIdx.y + 1) * g.kpc);
     // one observation tile per split (<= 64 observations per dimension) and no more splits than ring stages: every split's
     // tile is requested up front, so the later ones arrive while the earlier ones are multiplied
-    const bool ahead = n_tiles == 1 && g.kpc > 1 && g.kpc <= XD_STAGES;
+    const bool ahead = n_tiles == 1 && g.kpc > 1 && g.kpc <= STAGES;
     if (ahead && (threadIdx.x & 31) == 0) {
         int i = 0;
         for (int ks = blockIdx.y * g.kpc; ks < ks_end; ++ks, ++i) {
@@ -1419,13 +1425,13 @@ __global__ void __launch_bounds__(XD_THREADS, XD_CTAS_PER_SM) k_xdot(ModelDev m,
     for (int ks = blockIdx.y * g.kpc; ks < ks_end; ++ks) {                 // (the operand ring carries over: xw.it_base)
         xw.ks = ks;
         const double *bsrc = bfrag + (((size_t)oct0 * m.n_ksplit + ks) * m.ssd_nj) * 32;
-#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, XD_STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc, ahead ? 1 : 0)
+#define XD_CALL(NO, NJC, HF) xdot_body<NO, NJC, HF, STAGES>(m, bsrc, bstride, msrc, lv, ll_acc, oct0, T0, T1, xw, wait, tl, tlc, ahead ? 1 : 0)
         if (m.ssd_nj == SSD_NJ && m.ssd_half) {
-            switch (noct) { case 4: XD_CALL(4, SSD_NJ, true); break; case 3: XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
+            switch (noct) { case 4: if constexpr (MAXOCT >= 4) XD_CALL(4, SSD_NJ, true); break; case 3: if constexpr (MAXOCT >= 3) XD_CALL(3, SSD_NJ, true); break; case 2: XD_CALL(2, SSD_NJ, true); break; default: XD_CALL(1, SSD_NJ, true); break; }
         } else if (m.ssd_nj == SSD_NJ) {
-            switch (noct) { case 4: XD_CALL(4, SSD_NJ, false); break; case 3: XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
+            switch (noct) { case 4: if constexpr (MAXOCT >= 4) XD_CALL(4, SSD_NJ, false); break; case 3: if constexpr (MAXOCT >= 3) XD_CALL(3, SSD_NJ, false); break; case 2: XD_CALL(2, SSD_NJ, false); break; default: XD_CALL(1, SSD_NJ, false); break; }
         } else {
-            switch (noct) { case 4: XD_CALL(4, 0, false); break; case 3: XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
+            switch (noct) { case 4: if constexpr (MAXOCT >= 4) XD_CALL(4, 0, false); break; case 3: if constexpr (MAXOCT >= 3) XD_CALL(3, 0, false); break; case 2: XD_CALL(2, 0, false); break; default: XD_CALL(1, 0, false); break; }
         }
 #undef XD_CALL
     }
@@ -1451,11 +1457,11 @@ static int n_sms()
 // than 4,4,..,1: a one-octet CTA has two DMMA chains and starves next to eight-chain warps), and
 // the resident CTA slots of one wave are dealt to the tiles in proportion to their octets; a level
 // too large for that is cut into many short CTAs instead.
-static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
+static XdGrid xdot_grid(const ModelDev &m, int n, int slots, int max_oct, int max_kpc)
 {
     XdGrid g;
     const int octets = (n + SSD_OCT - 1) / SSD_OCT;
-    const int nt = (octets + 3) / 4;
+    const int nt = (octets + max_oct - 1) / max_oct;
     g.oct_lo = octets / nt; g.oct_hi = g.oct_lo + 1;
     g.n_hi = octets - g.oct_lo * nt; g.n_lo = nt - g.n_hi;
     const int n_tiles = (int)(m.ssd_ld / SSD_TN);
@@ -1482,21 +1488,33 @@ static XdGrid xdot_grid(const ModelDev &m, int n, int slots)
         static const int kpc_env = [] { const char *e = getenv("DEMCMC_XD_KPC"); return e ? atoi(e) : 0; }();     // A/B runs: 1 = off
         const int64_t ctas = (int64_t)(g.n_hi * g.c_hi + g.n_lo * g.c_lo) * m.n_ksplit;
         g.kpc = kpc_env > 0 ? std::min(kpc_env, (int)m.n_ksplit) : (int)std::min<int64_t>(m.n_ksplit, std::max<int64_t>(1, (ctas + slots - 1) / slots));
+        g.kpc = std::min(g.kpc, max_kpc);
     }
     return g;
 }
 
+constexpr int XDS_STAGES = 2, XDS_MAXOCT = 2, XDS_CTAS_PER_SM = 4;      // the short-stream instantiation
 static int launch_xdot(const ModelDev &m, const XdStage &xs, const Level &lv, long long *ll_acc)
 {
     static bool attr_set[64] = { false };
-    const size_t smem = xdot_smem_bytes(m.ssd_nj);
     if (!attr_set[g_dev]) {
-        CU(cudaFuncSetAttribute(k_xdot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_NJ)));
+        CU(cudaFuncSetAttribute(k_xdot_t<XD_STAGES, 4, XD_CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_NJ)));
+        CU(cudaFuncSetAttribute(k_xdot_t<XDS_STAGES, XDS_MAXOCT, XDS_CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xdot_smem_bytes(SSD_NJ, XDS_STAGES)));
         attr_set[g_dev] = true;
     }
-    const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms());
+    unsigned long long *tls = lv.ctxs ? tl_slot() : nullptr, *tlc = lv.ctxs ? tl_cta() : nullptr;
+    static const bool short_on = [] { const char *e = getenv("DEMCMC_XD_SHORT"); return !(e && e[0] == '0'); }();       // A/B runs
+    if (short_on && m.ssd_ld / SSD_TN <= XD_KPC_MAX_TILES && m.n_ksplit > 1) {
+        const XdGrid g = xdot_grid(m, lv.n, XDS_CTAS_PER_SM * n_sms(), XDS_MAXOCT, XDS_STAGES);
+        dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)((m.n_ksplit + g.kpc - 1) / g.kpc));
+        CU(launch_chained(k_xdot_t<XDS_STAGES, XDS_MAXOCT, XDS_CTAS_PER_SM>, grid, dim3(XD_THREADS), xdot_smem_bytes(m.ssd_nj, XDS_STAGES), m, (const double *)xs.bfrag,
+                          (const double *)xs.magic, lv, ll_acc, g, tls, tlc));
+        LAUNCHED("k_xdot");
+        return 0;
+    }
+    const XdGrid g = xdot_grid(m, lv.n, XD_CTAS_PER_SM * n_sms(), 4, XD_STAGES);
     dim3 grid((unsigned)(g.n_hi * g.c_hi + g.n_lo * g.c_lo), (unsigned)((m.n_ksplit + g.kpc - 1) / g.kpc));
-    CU(launch_chained(k_xdot, grid, dim3(XD_THREADS), smem, m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, lv.ctxs ? tl_slot() : (unsigned long long *)nullptr, lv.ctxs ? tl_cta() : (unsigned long long *)nullptr));
+    CU(launch_chained(k_xdot_t<XD_STAGES, 4, XD_CTAS_PER_SM>, grid, dim3(XD_THREADS), xdot_smem_bytes(m.ssd_nj), m, (const double *)xs.bfrag, (const double *)xs.magic, lv, ll_acc, g, tls, tlc));
     LAUNCHED("k_xdot");
     return 0;
 }
@@ -1867,7 +1885,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_chunk_persist(const __grid_co
     while (next_acc < ck.n_levels) accept_level(next_acc++);
 }
 
-static XdGrid xdot_grid(const ModelDev &m, int n, int slots);
+static XdGrid xdot_grid(const ModelDev &m, int n, int slots, int max_oct = 4, int max_kpc = XD_STAGES);
 
 // debug timeline of the persistent kernel (DEMCMC_PK_TIMELINE=<levels> DEMCMC_PK_TIMELINE_FILE=<csv>)
 static unsigned long long *g_ptl = nullptr;
