@@ -72,6 +72,9 @@ int launch_accept(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
 // small pointwise problems: propose + likelihood + accept of a level in one launch, one warp per
 // particle; returns 1 when the model / size does not qualify (launch the three kernels instead)
 int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv);
+// every level of a chunk of a SMALL pointwise problem (population of at most a few warps) in one single-CTA launch;
+// level l = entries [level_off[l], level_off[l + 1]) of d_order.  Returns 1 when the chunk does not qualify.
+int launch_chunk_small(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx, const int32_t *level_off, int n_levels);
 // all levels of a chunk in ONE persistent, warp-specialised launch (MVN / hierarchical): level l
 // holds the entries d_order[level_off[l] .. + level_n[l]); its proposals wait for the accepts of
 // level dep[l] (< l, or -1); the scalar warps run their accepts `lag` levels behind their proposals.

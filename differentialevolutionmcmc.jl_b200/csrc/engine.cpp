@@ -1092,6 +1092,13 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 return 0;
             }
         }
+        // ---- a population of a few warps (the reference's own examples): every level of the chunk in one single-CTA launch
+        if (n_lanes == 1 && !h->time_loglik && !skip_stream) {
+            const ChunkPlan &pl = plans[0];
+            const int rc = be::launch_chunk_small(h->dcfg, h->dmodel, u.d_order, u.d_ctx, pl.level_off.data(), pl.n_levels);
+            if (rc < 0) return fail(DEMCMC_ECUDA, "chunk launch: %s", be::last_error());
+            if (rc == 0) { n_levels += pl.n_levels; return 0; }
+        }
         BE(be::lane_fork(n_lanes));
         int rc_launch = 0;
         for (int l = 0; l < max_levels && !rc_launch; ++l)

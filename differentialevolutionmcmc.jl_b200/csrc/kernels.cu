@@ -999,17 +999,14 @@ __device__ __forceinline__ void pointwise_par(const ModelDev &m, const double *t
 // observations, accept -- by ONE warp in ONE launch per level.  The three-kernel chain of a level
 // costs ~13 us of launches and hand-offs, which is all there is to do on configs[0].
 struct NoWaitLanes : WarpLanes { __device__ __forceinline__ void dependency_wait() const {} };
-template <int KIND>
-__global__ void __launch_bounds__(PA_THREADS) k_level_fused(ConfigDev cfg, ModelDev m, Level lv)
+// the whole update of one particle by one warp (small pointwise problems, n_split == 1): C = WarpLanes inside a PDL chain,
+// NoWaitLanes where the caller has done the waiting
+template <int KIND, class C>
+__device__ __forceinline__ void fused_update(const C &co, const ConfigDev &cfg, const ModelDev &m, const SweepCtx &ctx, int p)
 {
-    pdl_launch_dependents();
-    const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
-    if (wi >= lv.n) { pdl_wait(); return; }
-    const uint32_t e = (uint32_t)lv.order[wi];
-    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
-    const int p = (int)(e & LV_POS_MASK), lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     NullSink sink;
-    propose_particle(WarpLanes(), cfg, m, ctx, p, sink);
+    propose_particle(co, cfg, m, ctx, p, sink);
     __syncwarp();
     if (KIND == M_GAUSSIAN || KIND == M_LNR || KIND == M_LBA) {
         double par[MAX_ACC + 5];
@@ -1027,6 +1024,39 @@ __global__ void __launch_bounds__(PA_THREADS) k_level_fused(ConfigDev cfg, Model
         __syncwarp();
     }
     accept_particle(NoWaitLanes(), cfg, m, ctx, p);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PA_THREADS) k_level_fused(ConfigDev cfg, ModelDev m, Level lv)
+{
+    pdl_launch_dependents();
+    const int wi = (blockIdx.x * PA_THREADS + threadIdx.x) >> 5;
+    if (wi >= lv.n) { pdl_wait(); return; }
+    const uint32_t e = (uint32_t)lv.order[wi];
+    const SweepCtx ctx = lv.ctxs[e >> LV_SLOT_SHIFT];
+    fused_update<KIND>(WarpLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
+}
+
+// The reference's own examples (Gaussian_Example.jl: 4 groups x 6 particles, 50 observations) are a handful of warps: a
+// launch per dependency level -- ~8 us each, 3.7 per sweep -- is all there is to their step.  When the whole population
+// fits one CTA, ONE launch runs every level of a chunk (up to 16 sweeps): a warp per update, a block-wide barrier between
+// levels (the state rows are global memory written and read by the same SM).
+constexpr int SC_MAX_LEVELS = 640, SC_MAX_WARPS = 12;       // 12 warps x 168 registers fit one SM
+constexpr int SC_MAX_P = 96;                                // beyond, a level is several rounds of the 12 warps and the level-by-level path (all SMs) wins
+struct SmallChunk { int32_t n_levels; int32_t off[SC_MAX_LEVELS + 1]; };
+template <int KIND>
+__global__ void __launch_bounds__(SC_MAX_WARPS * 32, 1) k_chunk_small(const __grid_constant__ ConfigDev cfg, const __grid_constant__ ModelDev m,
+                                                                       const int32_t *order, const SweepCtx *ctxs, const __grid_constant__ SmallChunk sc)
+{
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int L = 0; L < sc.n_levels; ++L) {
+        for (int wi = sc.off[L] + warp; wi < sc.off[L + 1]; wi += nw) {
+            const uint32_t e = (uint32_t)order[wi];
+            const SweepCtx ctx = ctxs[e >> LV_SLOT_SHIFT];
+            fused_update<KIND>(NoWaitLanes(), cfg, m, ctx, (int)(e & LV_POS_MASK));
+        }
+        __syncthreads();
+    }
 }
 constexpr int64_t FUSED_MAX_OBS = 256;
 
@@ -1048,6 +1078,39 @@ int launch_level_fused(const ConfigDev &cfg, const ModelDev &m, const Level &lv)
     }
     LAUNCHED("k_level_fused");
     if (g_tl_cap > 0) ++g_tl_level;
+    return 0;
+}
+
+static bool fused_eligible(const ConfigDev &cfg, const ModelDev &m)
+{
+    const char *env = getenv("DEMCMC_NO_FUSED");
+    if (env && env[0] == '1') return false;
+    if (is_ssd(m.kind) || cfg.d > 64) return false;
+    if ((m.kind == M_GAUSSIAN || m.kind == M_LNR || m.kind == M_LBA) && (m.n_obs > FUSED_MAX_OBS || m.n_osplit * m.n_ksplit != 1)) return false;
+    return m.kind == M_GAUSSIAN || m.kind == M_LNR || m.kind == M_LBA || m.kind == M_BINOMIAL || m.kind == M_RASTRIGIN;
+}
+
+// returns 1 when the chunk is not a small pointwise one (the caller launches level by level)
+int launch_chunk_small(const ConfigDev &cfg, const ModelDev &m, const int32_t *d_order, const SweepCtx *d_ctx, const int32_t *level_off, int n_levels)
+{
+    const char *env = getenv("DEMCMC_NO_SMALL");
+    if ((env && env[0] == '1') || !fused_eligible(cfg, m)) return 1;
+    if (n_levels <= 0 || n_levels > SC_MAX_LEVELS || cfg.G_local * cfg.Np > SC_MAX_P) return 1;
+    SmallChunk sc;
+    sc.n_levels = n_levels;
+    int widest = 1;
+    for (int l = 0; l <= n_levels; ++l) sc.off[l] = level_off[l];
+    for (int l = 0; l < n_levels; ++l) widest = std::max(widest, level_off[l + 1] - level_off[l]);
+    const int threads = 32 * std::min(widest, SC_MAX_WARPS);
+    switch (m.kind) {
+    case M_GAUSSIAN: k_chunk_small<M_GAUSSIAN><<<1, threads, 0, stream()>>>(cfg, m, d_order, d_ctx, sc); break;
+    case M_LNR: k_chunk_small<M_LNR><<<1, threads, 0, stream()>>>(cfg, m, d_order, d_ctx, sc); break;
+    case M_LBA: k_chunk_small<M_LBA><<<1, threads, 0, stream()>>>(cfg, m, d_order, d_ctx, sc); break;
+    case M_BINOMIAL: k_chunk_small<M_BINOMIAL><<<1, threads, 0, stream()>>>(cfg, m, d_order, d_ctx, sc); break;
+    default: k_chunk_small<M_RASTRIGIN><<<1, threads, 0, stream()>>>(cfg, m, d_order, d_ctx, sc); break;
+    }
+    LAUNCHED("k_chunk_small");
+    if (g_tl_cap > 0) g_tl_level += n_levels;
     return 0;
 }
 

@@ -1,9 +1,9 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-for sh in 0 1; do
-  echo -n "xd_short $sh: "
-  DEMCMC_XD_SHORT=$sh python scripts/bench_configs.py c4 --iters 60 2>/dev/null | python -c "
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for ns in 1 0; do
+echo -n "NO_SMALL=$ns: "
+DEMCMC_NO_SMALL=$ns python scripts/bench_configs.py c1 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
-    d=json.loads(l); print(d['config'], round(d['particle_updates_per_s']), d['ms_per_iteration'])"
+    d=json.loads(l); print(d['config'], round(d['particle_updates_per_s']), d['ms_per_iteration'], d['kernel_launches'])"
 done
-DEMCMC_LANES=1 python scripts/c4_timeline.py gpurun_out/c4_timeline_xs.csv 2>&1 | tail -10
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

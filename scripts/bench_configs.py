@@ -115,7 +115,7 @@ def run(name, iters=None, peaks=None, hbm_gbs=None):
             dfma, dmma = peaks if peaks else D.fp64_peaks(0)
             tf = c["flops"] * (c2["particle_updates"] - c1["particle_updates"]) / (c2["loglike_ms"] * 1e-3) / 1e12
             persistent = c2["persistent_chunks"] > c1["persistent_chunks"]
-            ll = {"kernel": "k_chunk_persist (whole chunk: proposals and accepts included)" if persistent else "k_xdot",
+            ll = {"kernel": "k_chunk_persist (whole chunk: proposals and accepts included)" if persistent else ("k_xdot" if c["kind"] in ("mvnormal", "hier_normal", "mvnormal_full") else "k_ll_pointwise"),
                   "tflops_event_bracketed": tf, "of_measured_dmma_peak": tf / max(dfma, dmma), "peak_dmma_tflops": dmma,
                   "share_of_step": c2["loglike_ms"] / c2["device_ms"]}
     h.close()
@@ -129,7 +129,7 @@ def run(name, iters=None, peaks=None, hbm_gbs=None):
     ups = line["particle_updates_per_s"]
     # roofline of each shape: what bounds it, achieved / peak
     if name == "c1":
-        line["roofline"] = {"bound": "latency", "note": "24 particles x 50 observations: one fused launch per dependency level; nothing to saturate"}
+        line["roofline"] = {"bound": "latency", "note": "24 particles x 50 observations: every level of a chunk in one single-CTA launch (k_chunk_small); during burn-in a chunk is one sweep (select_base reads the sweep-start weights) and the step is the host's per-chunk work; nothing to saturate"}
     elif name == "c3":
         dens = ups * 100_000
         line["roofline"] = {"bound": "fp64 pipe (transcendental)", "trial_densities_per_s": dens, "unit": "fp64 instructions/s",

@@ -281,6 +281,7 @@ int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row
 }
 
 int launch_level_fused(const ConfigDev &, const ModelDev &, const Level &) { return 1; }
+int launch_chunk_small(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, int) { return 1; }
 int chunk_persist_lanes(const ConfigDev &, const ModelDev &) { return 0; }
 int launch_chunk_persist(const ConfigDev &, const ModelDev &, const int32_t *, const SweepCtx *, const int32_t *, const int32_t *,
                          const int32_t *, int, int, long long *, int) { return 1; }

@@ -131,6 +131,34 @@ def test_fused_level_kernel_against_the_three_kernel_chain(model, monkeypatch):
     assert np.allclose(outs[0][2][fin], outs[1][2][fin], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("model,kw", [("gaussian", dict(burnin=8, theta_snooker=0.2, alpha=0.3)), ("lnr", dict(burnin=0, kappa=0.8)),
+                                      ("lba", dict(burnin=30, alpha=0.5)), ("binomial", dict(burnin=5)), ("gaussian", dict(burnin=4, resample=True, n_initial=5))])
+def test_single_cta_chunk_kernel_is_the_level_by_level_chain(model, kw, monkeypatch):
+    """A population of a few warps (the reference's own examples) runs every level of a chunk in ONE single-CTA launch
+    (k_chunk_small): bit for bit the chain of one k_level_fused launch per level, in a fraction of the launches."""
+    rng = np.random.default_rng(79)
+    case = make_case(model, rng)
+    kw = dict(kw)
+    rows = np.stack([case.theta0(rng, 4 * 6) for _ in range(kw["n_initial"])]) if kw.get("resample") else None
+    theta0 = case.theta0(np.random.default_rng(9), 4 * 6)
+    outs = []
+    for no_small in ("1", "0"):
+        monkeypatch.setenv("DEMCMC_NO_SMALL", no_small)
+        h = case.handle(4, 6, seed=12, **kw)
+        if rows is not None:
+            h.set_history(rows)
+            h.set_state(None)
+        else:
+            h.set_state(theta0)
+        h.run(60)
+        outs.append((h.samples(), h.accept(), h.lp(), h.counters()["kernel_launches"]))
+        h.close()
+    if rows is None:                                          # (DE-MCz donors come from the history: one level per sweep either way)
+        assert outs[1][3] < outs[0][3] * 0.6
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
 @pytest.mark.parametrize("model", ["gaussian", "mvnormal", "binomial"])
 def test_unforced_short_replay(model):
     """Without teacher forcing, over a run short enough that rounding differences are not yet
