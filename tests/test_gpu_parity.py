@@ -569,6 +569,7 @@ def test_wide_kernels_long_parameter_vectors(mode, monkeypatch):
     ("hier_normal", dict(blocks=True, theta_snooker=0.2, alpha=0.3)),            # blocks + snooker + the NORMAL_REF prior
     ("hier_normal", dict(theta_snooker=0.15, kappa=0.7, burnin=6)),              # recombination + the burn-in base term
     ("mvnormal", dict(theta_snooker=0.1, alpha=0.3, kappa=0.9)),                 # d = 301: the means staged from registers
+    ("hier_normal", dict(resample=True, n_initial=4, theta_snooker=0.2)),        # DE-MCz: donors are cells of the history
 ])
 def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
     """k_propose_wide1 (four elements per thread, one pass, d <= 1024): the oracle's accept decisions and values, and
@@ -587,11 +588,16 @@ def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
     r, out = forced_run(case, 2, 9, 8, mode, **kw)
     check(r, out)
     theta0 = case.theta0(np.random.default_rng(3), 2 * 9)
+    rows = np.stack([case.theta0(np.random.default_rng(40 + i), 2 * 9) for i in range(kw["n_initial"])]) if kw.get("resample") else None
     outs, names = [], []
     for shape in ("0", "32", "35"):
         monkeypatch.setenv("DEMCMC_WIDE_SHAPE", shape)
         h = case.handle(2, 9, seed=4, **kw)
-        h.set_state(theta0)
+        if rows is not None:
+            h.set_history(rows)
+            h.set_state(None)
+        else:
+            h.set_state(theta0)
         h.run(12)
         outs.append((h.samples(), h.accept(), h.lp()))
         h.close()
