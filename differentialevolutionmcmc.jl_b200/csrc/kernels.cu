@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(PW1_T, MINB) k_propose_wide1(ConfigDev cfg, Mo
 // DEMCMC_WIDE_SHAPE=<accept digit><propose digit> (A/B runs, tests).  Accept: 0 = 256 threads x 4 CTAs per SM, else 128 x 12 (40 registers, no spills).
 // Propose: 0 = the three-pass kernel at 256 x 4, 2 = at 128 x 8, 5 = the one-pass kernel (also tried: 256 x 6, 128 x 12, 64 x 16: slower)
 // Measured on configs[3] (M updates/s, 60 iterations):
-// 00: 16.6, 22: 17.5, 32: 17.9 (19.3 with the threaded planner), 35: 20.9 -> 21.7 (prior loads hoisted, cheap staging index); the one-pass kernel at 3 / 2 CTAs per SM (80 / 116 registers): 19.9 / 17.1
+// 00: 16.6, 22: 17.5, 32: 17.9 (19.3 with the threaded planner), 35: 20.9 -> 21.7 (prior loads hoisted, cheap staging index); the one-pass kernel at 3 / 2 CTAs per SM (80 / 116 registers): 19.9 / 17.1, at 5 / 6 CTAs per SM (48 / 40 registers, 470 / 850 B of spills): 23.8 / 21.3 against 25.0
 static int wide_shape()
 {
     const char *e = getenv("DEMCMC_WIDE_SHAPE");
