@@ -545,6 +545,7 @@ def test_wide_kernels_long_parameter_vectors(mode, monkeypatch):
     """d >= 256 (hierarchical normal with 300 subjects, d = 303, parameter blocks): the proposal and the
     accept run as one CTA of 256 threads per particle (k_propose_wide / k_accept_wide) -- same
     accept decisions as the oracle, values within 1e-12; and the same chain as the one-warp kernels."""
+    monkeypatch.setenv("DEMCMC_PERSIST", "0")                 # (a population this small would otherwise run in the persistent kernel)
     case = make_case("hier_normal", np.random.default_rng(61), n_obs=20, n_subjects=300)
     S = case.d - 3
     r, out = forced_run(case, 2, 10, 8, mode, burnin=4, blocks=hier_blocks(S), alpha=0.3)
@@ -556,6 +557,7 @@ def test_wide_kernels_long_parameter_vectors(mode, monkeypatch):
         h = case.handle(2, 10, seed=4, burnin=3, blocks=hier_blocks(S), alpha=0.3)
         h.set_state(theta0)
         h.run(12)
+        assert h.counters()["persistent_chunks"] == 0
         outs.append((h.samples(), h.accept(), h.lp()))
         h.close()
     assert np.array_equal(outs[0][1], outs[1][1])                       # accept decisions
@@ -584,6 +586,7 @@ def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
     else:
         case = make_case("mvnormal", rng, n_obs=300, n_dim=300)
     kw.setdefault("burnin", 4)
+    monkeypatch.setenv("DEMCMC_PERSIST", "0")                 # the level-by-level path: that is where the wide kernels are
     monkeypatch.setenv("DEMCMC_WIDE_SHAPE", "5")
     r, out = forced_run(case, 2, 9, 8, mode, **kw)
     check(r, out)
@@ -599,6 +602,7 @@ def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
         else:
             h.set_state(theta0)
         h.run(12)
+        assert h.counters()["persistent_chunks"] == 0
         outs.append((h.samples(), h.accept(), h.lp()))
         h.close()
     for other in outs[1:]:
@@ -732,8 +736,9 @@ def test_overlapped_block_sweeps_are_a_schedule_only(kw):
     E.test_overlapped_block_sweeps_are_a_schedule_only(None, kw)
 
 
-def test_overlapped_block_sweeps_wide_kernels():
+def test_overlapped_block_sweeps_wide_kernels(monkeypatch):
     """the configs[3] shape in small: 300 subjects (d = 303: the one-CTA-per-particle kernels), two blocks"""
+    monkeypatch.setenv("DEMCMC_PERSIST", "0")
     rng = np.random.default_rng(2)
     case = make_case("hier_normal", rng, n_subjects=300)
     th0 = case.theta0(rng, 4 * 24)
