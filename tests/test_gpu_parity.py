@@ -612,6 +612,16 @@ def test_one_pass_wide_proposal(mode, model, kw, monkeypatch):
         assert np.allclose(outs[0][2][fin], other[2][fin], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("mode", ["replay", "native"])
+def test_one_pass_wide_proposal_at_the_configs3_length(mode, monkeypatch):
+    """d = 1003 (1000 subjects, two parameter blocks): all four elements of every thread in use, the last trip partial;
+    20 dimension splits of the short-stream k_xdot; two lanes.  Oracle parity, teacher-forced."""
+    monkeypatch.setenv("DEMCMC_PERSIST", "0")
+    case = make_case("hier_normal", np.random.default_rng(83), n_obs=50, n_subjects=1000)
+    r, out = forced_run(case, 2, 7, 5, mode, burnin=2, blocks=hier_blocks(1000), theta_snooker=0.2, alpha=0.3)
+    check(r, out)
+
+
 # ---- the optimize path (optimize.jl; maximize! / minimize! + evaluate_fun!) -------------------------
 @pytest.mark.parametrize("mode", ["replay", "native"])
 @pytest.mark.parametrize("model,update", [("rastrigin", "minimize"), ("gaussian", "maximize"), ("mvnormal", "maximize")])
