@@ -1,7 +1,8 @@
-for sh in 35 36 37; do
-  echo -n "shape $sh: "
-  DEMCMC_WIDE_SHAPE=$sh python scripts/bench_configs.py c4 --iters 60 2>/dev/null | python -c "
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+for sp in 0 1; do
+echo -n "PK_SPLIT=$sp: "
+DEMCMC_PK_SPLIT=$sp python bench.py --steps 300 --warmup 5 --no-ess --no-configs 2>/dev/null | python -c "
 import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print(d['config'], round(d['particle_updates_per_s']), d['ms_per_iteration'])"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c2', d['value'], d['roofline']['frac'], d['e2e']['value'])"
 done
+python scripts/pk_timeline.py gpurun_out/pk_tl_split.csv 2>&1 | tail -9
