@@ -470,15 +470,13 @@ DE_HD double lba_obs(const double *par, int na, double inv_1mpneg, double floor_
         const double t1 = 0.5 * de_erfcx_nonneg(fabs(n1) * DE_SQRT1_2) * e1, t2 = 0.5 * de_erfcx_nonneg(fabs(n2) * DE_SQRT1_2) * e2;
         const double c1 = n1 < 0.0 ? t1 : 1.0 - t1, c2 = n2 < 0.0 ? t2 : 1.0 - t2;
         const double p1 = e1 * DE_INV_SQRT2PI, p2 = e2 * DE_INV_SQRT2PI;
-        if (r == choice) {
-            const double f = (-v * c1 + p1 + v * c2 - p2) * inv_A;
-            den *= (f > 0.0 ? f : (f != f ? f : 0.0));
-        } else {
-            const double dA = dt * inv_A;
-            double F = 1.0 + (n1 * dA) * c1 - (n2 * dA) * c2 + dA * p1 - dA * p2;
-            F = F > 0.0 ? F : (F != F ? F : 0.0);
-            den *= (1.0 - F);
-        }
+        // both forms, then a select: the winner differs from trial to trial, so a warp took both branches anyway (with the
+        // divergence bookkeeping on top); the selected value is the one the branch computed
+        const double f = (-v * c1 + p1 + v * c2 - p2) * inv_A;
+        const double dA = dt * inv_A;
+        double F = 1.0 + (n1 * dA) * c1 - (n2 * dA) * c2 + dA * p1 - dA * p2;
+        F = F > 0.0 ? F : (F != F ? F : 0.0);
+        den *= (r == choice) ? (f > 0.0 ? f : (f != f ? f : 0.0)) : (1.0 - F);
     }
 #else
     for (int r = 0; r < na; ++r) {
