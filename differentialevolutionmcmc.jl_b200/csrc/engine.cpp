@@ -1244,7 +1244,14 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
         // ones are planned while the device is busy with their predecessors
         static int first_chunk = -1;
         if (first_chunk < 0) { const char *e = getenv("DEMCMC_FIRST_CHUNK"); first_chunk = e ? std::max(1, atoi(e)) : 4; }     // 4, 8, 16 sweeps: measured against 2, 4, 8, 16 at 20 steps: +1.4 %
-        const int chunk_cap = (int)std::min<int64_t>(h->max_chunk, (int64_t)first_chunk << std::min<int64_t>(chunks_this_call, 8));
+        // ... doubling from chunk to chunk; four-fold where a sweep is heavy on the device next to its planning (>= 2e6
+        // observation x dimension products per particle: planning 16 sweeps of configs[1] takes 0.6 ms, the 4 sweeps it hides
+        // behind 1.5 ms), so that a 20-iteration call is 4 + 16 sweeps instead of 4 + 8 + 8
+        static int growth_env = -1;
+        if (growth_env < 0) { const char *e = getenv("DEMCMC_CHUNK_GROWTH"); growth_env = e ? std::max(0, atoi(e)) : 0; }
+        const bool heavy = (double)h->dmodel.n_obs * (double)std::max(1, (int)h->dmodel.n_dim) >= 2e6;
+        const int shift = growth_env ? growth_env : (heavy ? 2 : 1);
+        const int chunk_cap = (int)std::min<int64_t>(h->max_chunk, (int64_t)first_chunk << std::min<int64_t>(shift * chunks_this_call, 8));
         ++chunks_this_call;
         if (!needs_snapshot(it) && h->max_chunk > 1 && !cfg.donors) {   // resample reads rows of earlier sweeps: one sweep per chunk
             MigSchedule m2;
