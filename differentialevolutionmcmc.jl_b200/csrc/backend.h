@@ -127,7 +127,9 @@ int launch_moments(const double *x, int64_t n, int32_t d, double *mean, double *
 // [2] sum of their squares, [3 + t] sum of the biased autocovariances at lag t < n_lag.  The host turns them into
 // split-R-hat and ESS (engine.cpp: diag_finish).
 int launch_diag_pos(const int32_t *rows_id, int64_t row0, int64_t n_rows, int32_t P_local, int32_t id_base, int32_t P_ids, int32_t pos_base, int32_t *pos);
-int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t n_lag, double *agg);
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t lag0, int32_t n_lag, double *agg);   // lags [lag0, lag0 + n_lag)
+int diag_max_half();   // longest split chain (stored rows / 2) one call can hold, and
+int diag_max_lags();   // the most lags one call computes
 // particle algebra known-answer ops (single warp each)
 int launch_op_project(const double *p1, const double *p2, int d, double *out);
 int launch_op_snooker(const double *pt, const double *pz, const double *pm, const double *pn, double g, const double *b,

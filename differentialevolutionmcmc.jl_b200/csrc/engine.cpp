@@ -13,6 +13,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <array>
 #include <vector>
 
 #include "../../include/demcmc_b200.h"
@@ -1361,30 +1362,37 @@ int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *
     return rc;
 }
 
-// split-R-hat and ESS from the aggregates of launch_diag_aggregates, summed over the shards (m = split chains in all)
-static void diag_finish(const double *agg, int d, int n_lag, int64_t nh, int64_t m, double *rhat, double *ess)
+// split-R-hat and ESS from the aggregates of launch_diag_aggregates, summed over the shards (m = split chains in all).
+// head[k] = the three variance sums, acov[k] = the chain-summed autocovariances of the lags computed so far; returns
+// false when some parameter's Geyer sequence is still positive at the last lag available and lags remain (< nh)
+static bool diag_finish(const std::vector<std::array<double, 3>> &head, const std::vector<std::vector<double>> &acov, int64_t nh, int64_t m, double *rhat, double *ess)
 {
     const double n = (double)nh, M = (double)m;
-    for (int k = 0; k < d; ++k) {
-        const double *a = agg + (size_t)k * (3 + n_lag);
-        const double W = a[0] / M;                                        // mean within-chain variance
-        const double var_means = M > 1 ? (a[2] - a[1] * a[1] / M) / (M - 1.0) : 0.0;
+    bool done = true;
+    for (size_t k = 0; k < head.size(); ++k) {
+        const double *a = acov[k].data();
+        const int64_t n_lag = (int64_t)acov[k].size();
+        const double W = head[k][0] / M;                                  // mean within-chain variance
+        const double var_means = M > 1 ? (head[k][2] - head[k][1] * head[k][1] / M) / (M - 1.0) : 0.0;
         const double var_plus = W * (n - 1.0) / n + var_means;           // B / n = var of the chain means
         if (rhat) rhat[k] = W > 0.0 ? sqrt(var_plus / W) : NAN;
         if (!ess) continue;
         if (!(var_plus > 0.0)) { ess[k] = NAN; continue; }
-        auto rho = [&](int t) { return t == 0 ? 1.0 : 1.0 - (W - a[3 + t] / M) / var_plus; };
+        auto rho = [&](int64_t t) { return t == 0 ? 1.0 : 1.0 - (W - a[t] / M) / var_plus; };
         double tau = -1.0, prev = INFINITY;
-        for (int t = 0; t + 1 < n_lag; t += 2) {                          // Geyer's initial positive, monotone sequence
+        bool ended = false;
+        for (int64_t t = 0; t + 1 < n_lag; t += 2) {                      // Geyer's initial positive, monotone sequence
             double pair = rho(t) + rho(t + 1);
-            if (pair < 0.0) break;
+            if (pair < 0.0) { ended = true; break; }
             pair = std::min(pair, prev);
             prev = pair;
             tau += 2.0 * pair;
         }
+        if (!ended && n_lag < nh) done = false;
         tau = std::max(tau, 1.0 / log10(std::max(n * M, 10.0)));
         ess[k] = n * M / tau;
     }
+    return done;
 }
 
 int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, double *rhat, double *ess)
@@ -1393,8 +1401,12 @@ int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, doubl
     demcmc_handle *h0 = h->multi ? h->kids[0] : h;
     if (row0 < 0 || n_rows < 4 || row0 + n_rows > stored_rows(h0)) return fail(DEMCMC_EINVAL, "row range [%lld, %lld) outside the %lld stored rows (at least 4 rows)", (long long)row0, (long long)(row0 + n_rows), (long long)stored_rows(h0));
     const int64_t nh = n_rows / 2;
-    if (nh > 4096) return fail(DEMCMC_EUNSUPPORTED, "diagnostics over more than 8192 stored rows per call: thin the run or pass a sub-range");
-    const int d = h->d, n_lag = (int)nh;
+    if (nh > be::diag_max_half()) return fail(DEMCMC_EUNSUPPORTED, "diagnostics over more than %d stored rows per call: thin the run or pass a sub-range", 2 * be::diag_max_half());
+    // the autocovariances come in batches of lags (an even number: Geyer's sequence sums pairs); a batch is computed only
+    // while some parameter's sequence is still positive at the last lag of the one before it
+    // (DEMCMC_DIAG_LAGS: test switch, a smaller batch so that short chains walk through several of them)
+    const char *lag_env = getenv("DEMCMC_DIAG_LAGS");
+    const int d = h->d, lag_step = std::max(2, std::min(be::diag_max_lags(), lag_env ? atoi(lag_env) : be::diag_max_lags()) & ~1), n_lag = (int)std::min<int64_t>(nh, lag_step);
     const size_t na = (size_t)d * (3 + n_lag);
     std::vector<demcmc_handle *> leaves = h->multi ? h->kids : std::vector<demcmc_handle *>{ h };
     const int32_t Pt = (int32_t)h->P, id_base = h->multi ? 0 : h->cfg.group_begin * h->cfg.Np;
@@ -1415,13 +1427,22 @@ int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, doubl
             be::launch_diag_pos(k->hist_id, row0, n_rows, (int32_t)k->P, id_base, Pt, h->multi ? k->cfg.group_begin * k->cfg.Np : 0, pos) || be::sync())
             rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error());
     }
-    if (!rc && (be::set_device(h0->cfg.device) || be::launch_diag_aggregates(sh, pos, row0, n_rows, Pt, d, n_lag, agg) ||
-                be::d2h(total.data(), agg, sizeof(double) * na))) rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error());
+    std::vector<std::array<double, 3>> head(d);
+    std::vector<std::vector<double>> acov(d);
+    for (int64_t lag0 = 0; lag0 < nh && !rc; lag0 += lag_step) {
+        const int nl = (int)std::min<int64_t>(lag_step, nh - lag0);
+        if (be::set_device(h0->cfg.device) || be::launch_diag_aggregates(sh, pos, row0, n_rows, Pt, d, (int32_t)lag0, nl, agg) ||
+            be::d2h(total.data(), agg, sizeof(double) * (size_t)d * (3 + nl))) { rc = fail(DEMCMC_ECUDA, "diagnostics: %s", be::last_error()); break; }
+        for (int k = 0; k < d; ++k) {
+            const double *a = total.data() + (size_t)k * (3 + nl);
+            if (lag0 == 0) head[k] = { a[0], a[1], a[2] };
+            acov[k].insert(acov[k].end(), a + 3, a + 3 + nl);
+        }
+        if (diag_finish(head, acov, nh, 2 * (int64_t)Pt, rhat, ess) || !ess) break;
+    }
     be::set_device(h0->cfg.device);
     be::dfree_shared(pos); be::dfree(agg);
-    if (rc) return rc;
-    diag_finish(total.data(), d, n_lag, nh, 2 * (int64_t)Pt, rhat, ess);
-    return 0;
+    return rc;
 }
 
 int demcmc_get_chains(demcmc_handle *h, int64_t row0, int64_t n_rows, double *out)

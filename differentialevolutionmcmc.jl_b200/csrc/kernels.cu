@@ -2606,9 +2606,9 @@ __global__ void __launch_bounds__(256) k_diag_pos(const int32_t *rid, int64_t ro
 // one block per (parameter k, group of chains): each split chain is gathered into shared memory (its draws sit at a
 // different position of every stored row: ids migrate), then thread t accumulates the lags t, t + 256, ...; the
 // block's chains are summed in order, the groups by k_diag_merge in order: deterministic
-constexpr int DG_THREADS = 256, DG_GROUPS = 32, DG_MAX_NH = 4096;
+constexpr int DG_THREADS = 256, DG_GROUPS = 32, DG_MAX_LAG = 4096 /* lags per launch: 16 accumulators per thread */, DG_MAX_NH = 24576 /* 192 KB of shared memory */;
 __global__ void __launch_bounds__(DG_THREADS) k_diag_partial(DiagShards sh, const int32_t *pos, int64_t row0, int64_t n_rows, int P, int d,
-                                                             int n_lag, double *part /* [d][DG_GROUPS][3 + n_lag] */)
+                                                             int lag0, int n_lag, double *part /* [d][DG_GROUPS][3 + n_lag]: lags lag0 .. lag0 + n_lag - 1 */)
 {
     extern __shared__ double xs[];                                // nh draws of one split chain
     __shared__ double red[DG_THREADS / 32 + 1];
@@ -2618,7 +2618,7 @@ __global__ void __launch_bounds__(DG_THREADS) k_diag_partial(DiagShards sh, cons
     const int c0 = (int)((int64_t)grp * n_chain / DG_GROUPS), c1 = (int)((int64_t)(grp + 1) * n_chain / DG_GROUPS);
     double *out = part + ((size_t)k * DG_GROUPS + grp) * (3 + n_lag);
     double s_cv = 0.0, s_m = 0.0, s_m2 = 0.0;
-    constexpr int LPT = (DG_MAX_NH + DG_THREADS - 1) / DG_THREADS;  // lags per thread
+    constexpr int LPT = (DG_MAX_LAG + DG_THREADS - 1) / DG_THREADS; // lags per thread
     double acov[LPT];
 #pragma unroll
     for (int j = 0; j < LPT; ++j) acov[j] = 0.0;
@@ -2644,8 +2644,8 @@ __global__ void __launch_bounds__(DG_THREADS) k_diag_partial(DiagShards sh, cons
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < LPT; ++j) {
-            const int t = tid + j * DG_THREADS;
-            if (t < n_lag) {
+            const int tl = tid + j * DG_THREADS, t = lag0 + tl;
+            if (tl < n_lag) {
                 double a = 0.0;
                 for (int i = 0; i + t < nh; ++i) a += xs[i] * xs[i + t];
                 a /= (double)nh;
@@ -2674,13 +2674,22 @@ int launch_diag_pos(const int32_t *rows_id, int64_t row0, int64_t n_rows, int32_
     LAUNCHED("k_diag_pos");
     return 0;
 }
-int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t n_lag, double *agg)
+int diag_max_half() { return DG_MAX_NH; }
+int diag_max_lags() { return DG_MAX_LAG; }
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P_ids, int32_t d, int32_t lag0, int32_t n_lag, double *agg)
 {
     const int64_t nh = n_rows / 2;
-    if (nh < 2 || nh > DG_MAX_NH || n_lag > nh || n_lag < 1) { g_be_err = "diagnostics need 4 <= n_rows <= 8192 stored rows per call"; return -1; }
+    if (nh < 2 || nh > DG_MAX_NH || lag0 < 0 || n_lag < 1 || n_lag > DG_MAX_LAG || lag0 + n_lag > nh) { g_be_err = "diagnostics need 4 <= n_rows <= 49152 stored rows and at most 4096 lags per launch"; return -1; }
+    if (sizeof(double) * nh > 48 * 1024) {
+        static bool attr_set[64] = {};
+        if (!attr_set[g_dev & 63]) {
+            if (cudaFuncSetAttribute(k_diag_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * DG_MAX_NH)) != cudaSuccess) { g_be_err = "k_diag_partial: shared-memory opt-in refused"; return -1; }
+            attr_set[g_dev & 63] = true;
+        }
+    }
     double *part = (double *)dmalloc(sizeof(double) * (size_t)d * DG_GROUPS * (3 + n_lag));
     if (!part) return -1;
-    k_diag_partial<<<dim3(d, DG_GROUPS), DG_THREADS, sizeof(double) * nh, stream()>>>(sh, pos, row0, n_rows, P_ids, d, n_lag, part);
+    k_diag_partial<<<dim3(d, DG_GROUPS), DG_THREADS, sizeof(double) * nh, stream()>>>(sh, pos, row0, n_rows, P_ids, d, lag0, n_lag, part);
     LAUNCHED("k_diag_partial");
     k_diag_merge<<<(unsigned)(((int64_t)d * (3 + n_lag) + 255) / 256), 256, 0, stream()>>>(part, d, n_lag, agg);
     LAUNCHED("k_diag_merge");

@@ -233,7 +233,9 @@ int demcmc_get_moments(demcmc_handle *h, int64_t row0, int64_t n_rows, int64_t *
  * autocorrelations from the chain-averaged autocovariances, Geyer's initial monotone sequence) -- what the reference's
  * tests read off MCMCChains.describe (test/gaussian_tests.jl:42-59), minus the rank normalisation of the newer
  * "bulk" variants (that one needs a global sort of all draws; demcmc_b200.diagnostics computes it on the host).
- * 4 <= n_rows <= 8192 per call.  Works on a multi-device handle (the shards' aggregates are merged). */
+ * 4 <= n_rows <= 49152 per call (a split chain is held in 192 KB of shared memory; the autocovariances are computed in
+ * batches of 4096 lags, and a further batch only while some parameter's Geyer sequence is still positive).  Works on a
+ * multi-device handle (the shards' aggregates are merged). */
 int demcmc_get_diagnostics(demcmc_handle *h, int64_t row0, int64_t n_rows, double *rhat, double *ess);
 /* the same history as the device keeps it, rows [row0, row0+n_rows) of the iterations run, by
  * POSITION: theta[n_rows][P_local][d], w[n_rows][P_local] (= lp), ids[n_rows][P_local] (particle id

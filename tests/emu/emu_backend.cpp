@@ -249,7 +249,9 @@ int launch_diag_pos(const int32_t *rid, int64_t row0, int64_t n_rows, int32_t P,
         for (int s = 0; s < P; ++s) { const int id = rid[(row0 + r) * P + s] - id_base; if (id >= 0 && id < P_ids) pos[(size_t)r * P_ids + id] = pos_base + s; }
     return 0;
 }
-int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t n_lag, double *agg)
+int diag_max_half() { return 24576; }
+int diag_max_lags() { return 4096; }
+int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row0, int64_t n_rows, int32_t P, int32_t d, int32_t lag0, int32_t n_lag, double *agg)
 {
     ++g_launches;
     const int64_t nh = n_rows / 2;
@@ -268,11 +270,12 @@ int launch_diag_aggregates(const DiagShards &sh, const int32_t *pos, int64_t row
             }
             mean /= (double)nh;
             for (int64_t i = 0; i < nh; ++i) x[i] -= mean;
-            for (int t = 0; t < n_lag; ++t) {
+            for (int tl = 0; tl < n_lag; ++tl) {
+                const int t = lag0 + tl;
                 double s = 0.0;
                 for (int64_t i = 0; i + t < nh; ++i) s += x[i] * x[i + t];
                 s /= (double)nh;
-                a[3 + t] += s;
+                a[3 + tl] += s;
                 if (t == 0) { a[0] += s * (double)nh / (double)(nh - 1); a[1] += mean; a[2] += mean * mean; }
             }
         }

@@ -720,6 +720,16 @@ def test_device_diagnostics_match_the_host_estimators():
         E._check_device_diagnostics(devices=[0, 1])
 
 
+def test_device_diagnostics_of_long_chains(monkeypatch):
+    """more than 8192 stored rows (the split chain in opted-in shared memory), and the lags in several batches
+    (k_diag_partial with lag0 > 0) against the one-batch result and the host estimators"""
+    E._check_device_diagnostics(G=2, Np=4, n_iter=12000)
+    monkeypatch.setenv("DEMCMC_DIAG_LAGS", "8")
+    E._check_device_diagnostics(G=2, Np=5, n_iter=300)
+    monkeypatch.setenv("DEMCMC_DIAG_LAGS", "512")
+    E._check_device_diagnostics(G=2, Np=4, n_iter=12000)
+
+
 def test_full_covariance_mvn_kernel():          # SURVEY 8f-4
     E._check_mvn_full()
     # a larger, strongly correlated case through the persistent kernel against the oracle's per-observation whitening

@@ -614,6 +614,15 @@ def test_device_diagnostics_match_the_host_estimators(emu):
     _check_device_diagnostics(store_every=2, n_iter=120)
 
 
+def test_device_diagnostics_in_batches_of_lags(emu, monkeypatch):
+    """the autocovariances arrive in batches of lags, a further batch only while a Geyer sequence is still positive: batches
+    of 2, 6 and 16 lags on chains of 41-60 draws give what one batch of all lags gives"""
+    for step in ("2", "6", "16", "3"):                     # an odd step is rounded down to whole pairs
+        monkeypatch.setenv("DEMCMC_DIAG_LAGS", step)
+        _check_device_diagnostics()
+        _check_device_diagnostics(n_iter=127, G=2, Np=5)
+
+
 # ---- SURVEY 8f-4: the full-covariance MVN kernel and the vector-parameter Gaussian example --------------------------
 def _check_mvn_full():
     from scipy import stats
