@@ -77,7 +77,8 @@ struct demcmc_handle {
     // (positions in rank order) and its id -> global position map, gathered after each iteration
     double *ghist_theta = nullptr;                      // [row][P_total][d]
     int32_t *ghist_pos = nullptr;                       // [row][P_total]
-    int32_t *gid_tmp = nullptr;                         // [P_total] gathered ids of one row
+    int32_t *gid_tmp = nullptr;                         // [2][P_total] gathered ids of one row (two copies: a multi-device handle alternates them)
+    uint64_t n_gathers = 0;
     int64_t k_store = 1;                                // store_every: iteration it (1-based, counted on this handle) is kept iff it % k_store == 0
     int n_scratch = 3;                                  // scratch state rows (write-once within a chunk): 3, or MAX_CHUNK + 2 when thinning
     int64_t n0 = 0;                                     // de.n_initial: history rows before iteration 1
@@ -179,7 +180,7 @@ static int grow_history(demcmc_handle *h, int64_t need)
         const size_t Pt = (size_t)h->cfg.n_groups * h->cfg.Np;
         double *gt = (double *)be::dmalloc(sizeof(double) * cap * Pt * d);
         int32_t *gp = (int32_t *)be::dmalloc(sizeof(int32_t) * cap * Pt);
-        if (!h->gid_tmp) h->gid_tmp = (int32_t *)be::dmalloc(sizeof(int32_t) * Pt);
+        if (!h->gid_tmp) h->gid_tmp = (int32_t *)be::dmalloc(sizeof(int32_t) * 2 * Pt);
         if (!gt || !gp || !h->gid_tmp) return fail(DEMCMC_ENOMEM, "replicated history of %lld rows does not fit on the device", (long long)cap);
         if (have > 0 && h->ghist_theta) {
             BE(be::d2d(gt, h->ghist_theta, sizeof(double) * have * Pt * d));
@@ -196,8 +197,10 @@ static int grow_history(demcmc_handle *h, int64_t need)
 
 // resample on a sharded job: the replicated copy of history row `row` (theta and the id -> position
 // map) from every rank's slice, in rank order = global position order
+static int gather_row_local(demcmc_handle *h, int64_t row);
 static int gather_row(demcmc_handle *h, int64_t row)
 {
+    if (h->parent) return gather_row_local(h, row);
     const size_t P = h->P, d = h->d, Pt = (size_t)h->cfg.n_groups * h->cfg.Np;
     if (be::comm_allgather(h->comm, h->hist_theta + (size_t)row * P * d, h->ghist_theta + (size_t)row * Pt * d, sizeof(double) * P * d) ||
         be::comm_allgather(h->comm, h->hist_id + (size_t)row * P, h->gid_tmp, sizeof(int32_t) * P) ||
@@ -270,6 +273,26 @@ struct HostBarrier {
 }
 struct MultiState { HostBarrier barrier; };
 
+// the same gather between the devices of a multi-device handle (one host thread per device, peer access enabled by
+// multi_create): every device stores its slice of the row into every device's replicated copy, then all meet at a host
+// barrier.  The gathered ids alternate between two buffers: a device may start the stores of gather n + 1 while a slower
+// peer's position kernel of gather n is still queued; it cannot reach gather n + 2 before that peer has synchronised.
+static int gather_row_local(demcmc_handle *h, int64_t row)
+{
+    demcmc_handle *p = h->parent;
+    const size_t P = h->P, d = h->d, Pt = (size_t)h->cfg.n_groups * h->cfg.Np, par = (size_t)(h->n_gathers++ & 1);
+    for (demcmc_handle *k : p->kids) {
+        if (!k->ghist_theta || !k->gid_tmp) return fail(DEMCMC_ESTATE, "history gather: device %d has no replicated history", k->cfg.device);
+        if (be::d2d(k->ghist_theta + ((size_t)row * Pt + (size_t)h->rank * P) * d, h->hist_theta + (size_t)row * P * d, sizeof(double) * P * d) ||
+            be::d2d(k->gid_tmp + par * Pt + (size_t)h->rank * P, h->hist_id + (size_t)row * P, sizeof(int32_t) * P))
+            return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
+    }
+    if (be::sync()) return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
+    p->multi->barrier.wait();
+    if (be::launch_pos_from_ids(h->gid_tmp + par * Pt, (int32_t)Pt, h->ghist_pos + (size_t)row * Pt)) return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
+    return 0;
+}
+
 template <class F>
 static int for_kids(demcmc_handle *h, F f, bool parallel = true)
 {
@@ -297,7 +320,6 @@ static int multi_create(const demcmc_config *cfg, demcmc_handle **out)
     if (N > MAX_RANKS) return fail(DEMCMC_EUNSUPPORTED, "n_devices > %d", (int)MAX_RANKS);
     if (cfg->n_groups % N) return fail(DEMCMC_EINVAL, "n_groups %d is not a multiple of the %d devices", cfg->n_groups, N);
     if (cfg->group_begin != 0 || (cfg->group_count != 0 && cfg->group_count != cfg->n_groups)) return fail(DEMCMC_EINVAL, "a multi-device handle holds every group: group_begin / group_count must be 0");
-    if (cfg->donors) return fail(DEMCMC_EUNSUPPORTED, "sample = resample on a multi-device handle (its replicated history is gathered with NCCL: shard the job over processes instead, demcmc_comm_init)");
     for (int i = 0; i < N; ++i) for (int j = 0; j < i; ++j) if (cfg->devices[i] == cfg->devices[j]) return fail(DEMCMC_EINVAL, "device %d listed twice", cfg->devices[i]);
     if (be::device_count() <= 0) return fail(DEMCMC_ENODEVICE, "no CUDA device: libdemcmc_b200 has no CPU fallback (%s)", be::last_error());
     demcmc_handle *p = new demcmc_handle();
@@ -743,6 +765,7 @@ int demcmc_set_history(demcmc_handle *h, const double *rows)
     if (h->multi) {                                          // rows[n_initial][P_total][d] -> every device its own ids
         const size_t Pt = h->P, dd = h->d;
         const int rc = for_kids(h, [&](demcmc_handle *k, int) {
+            if (h->cfg.donors) return demcmc_set_history(k, rows);    // sample = resample: every device keeps the rows of ALL ids
             const size_t Pl = k->P, pb = (size_t)k->cfg.group_begin * k->cfg.Np;
             std::vector<double> part((size_t)h->n0 * Pl * dd);
             for (int64_t r = 0; r < h->n0; ++r) memcpy(part.data() + (size_t)r * Pl * dd, rows + ((size_t)r * Pt + pb) * dd, sizeof(double) * Pl * dd);
@@ -1296,6 +1319,14 @@ static int run_impl(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 static int multi_run(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
 {
     if (n_iter < 0) return fail(DEMCMC_EINVAL, "bad argument");
+    // sample = resample: the devices store into each other's replicated history, so every copy has its final address
+    // before any device starts (run_impl then finds the capacity in place)
+    if (h->cfg.donors)
+        if (const int rc = for_kids(h, [&](demcmc_handle *k, int) {
+                if (be::set_device(k->cfg.device)) return fail(DEMCMC_ECUDA, "%s", be::last_error());
+                if (int r = grow_history(k, stored_rows(k, k->iters_done + n_iter))) return r;
+                return be::sync() ? fail(DEMCMC_ECUDA, "%s", be::last_error()) : 0;
+            }, false)) return rc;
     const int rc = for_kids(h, [&](demcmc_handle *k, int) { return run_impl(k, tape, n_iter); });
     if (!rc) h->iters_done += n_iter;
     return rc;

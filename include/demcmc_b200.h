@@ -129,7 +129,9 @@ typedef struct {
                                 mailboxes, and every demcmc_get_* call returns the whole job exactly as a single-device
                                 handle would (same chains bit for bit).  This is what replaces the ThreadsX.map over groups
                                 of p_update! (src/main.jl:135-148) for a Julia caller: no MPI, no torchrun.  group_begin /
-                                group_count must be 0; sample = resample is not available in this mode. */
+                                group_count must be 0.  With sample = resample every device keeps a replicated copy of the stored rows: after
+                                each iteration (and each migration that edits a stored row) the devices store their slice of the
+                                row into each other's copy through peer access and meet at a host barrier. */
     const int32_t *devices;  /* [n_devices] CUDA ordinals, all different, with P2P access to each other */
 } demcmc_config;
 

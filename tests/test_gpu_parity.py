@@ -678,7 +678,9 @@ def _n_gpus():
 
 
 @pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.6)), ("lnr", dict(alpha=0.5)),
-                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2))])
+                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2)),
+                                      ("mvnormal", dict(resample=True, n_initial=5, theta_snooker=0.2, alpha=0.6)),
+                                      ("hier_normal", dict(blocks=True, resample=True, n_initial=4, alpha=0.5))])
 def test_multi_device_handle_is_the_single_device_chain(model, kw):
     if _n_gpus() < 2:
         pytest.skip("a multi-device handle needs two GPUs (gpurun --gpus 2)")

@@ -515,7 +515,9 @@ def test_thinned_resample_runs_on_the_stored_rows(emu):
 
 @pytest.mark.parametrize("n_dev", [2, 4])
 @pytest.mark.parametrize("model,kw", [("mvnormal", dict(theta_snooker=0.2, alpha=0.6)), ("lnr", dict(alpha=0.5)),
-                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2))])
+                                      ("hier_normal", dict(blocks=True, alpha=0.5, store_every=2)),
+                                      ("mvnormal", dict(resample=True, n_initial=5, theta_snooker=0.2, alpha=0.6)),
+                                      ("hier_normal", dict(blocks=True, resample=True, n_initial=4, alpha=0.5))])
 def test_multi_device_handle_is_the_single_device_chain(emu, model, kw, n_dev):
     """cfg.n_devices = N: one handle, one process, N devices (host threads of the test double here), migration through
     the mailboxes -- every output identical to the single-device handle's, bit for bit"""
@@ -526,9 +528,12 @@ def test_multi_device_handle_is_the_single_device_chain(emu, model, kw, n_dev):
         kw["blocks"] = hier_blocks(9)
     G, Np, n_iter = 4, 6, 25
     th0 = case.theta0(rng, G * Np)
+    rows = np.stack([case.theta0(rng, G * Np) for _ in range(kw["n_initial"])]) if kw.get("resample") else None
     outs = []
     for devices in (None, list(range(n_dev))):
         with case.handle(G, Np, seed=8, burnin=6, trace=True, devices=devices, **kw) as h:
+            if rows is not None:                           # sample = resample: every device keeps a replicated history
+                h.set_history(rows)
             h.set_state(th0)
             h.run(n_iter)
             o = _full_outputs(h)
@@ -558,7 +563,7 @@ def test_multi_device_handle_replays_the_oracle_and_checks_its_arguments(emu):
         assert rel_err(h.samples(), r["samples"]) < 1e-12
         with pytest.raises(D._ffi.DemcmcError):
             h.comm_init(bytes(128), 0, 2)
-    for bad in (dict(devices=[0, 0]), dict(devices=[0, 1, 2]), dict(devices=[0, 1], resample=True, n_initial=4)):
+    for bad in (dict(devices=[0, 0]), dict(devices=[0, 1, 2])):
         with pytest.raises(D._ffi.DemcmcError):
             case.handle(G, Np, **bad)
 
