@@ -261,14 +261,19 @@ static int mbox_alloc(demcmc_handle *h)
 // ---- multi-device handle: fan a call out over the children, one host thread per device -------------------------
 namespace {
 struct HostBarrier {
-    std::mutex m; std::condition_variable cv; int n = 0, waiting = 0; uint64_t gen = 0;
-    void wait()
+    std::mutex m; std::condition_variable cv; int n = 0, waiting = 0; uint64_t gen = 0; bool aborted = false;
+    // false: a peer thread has left its run with an error (abort()) -- nobody would ever complete this barrier
+    bool wait()
     {
         std::unique_lock<std::mutex> lk(m);
+        if (aborted) return false;
         const uint64_t g = gen;
-        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return gen != g || aborted; });
+        return gen != g;
     }
+    void abort() { std::lock_guard<std::mutex> lk(m); aborted = true; cv.notify_all(); }
+    void reset() { std::lock_guard<std::mutex> lk(m); aborted = false; waiting = 0; }
 };
 }
 struct MultiState { HostBarrier barrier; };
@@ -288,7 +293,7 @@ static int gather_row_local(demcmc_handle *h, int64_t row)
             return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
     }
     if (be::sync()) return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
-    p->multi->barrier.wait();
+    if (!p->multi->barrier.wait()) return fail(DEMCMC_ECOMM, "history gather: another device of the handle failed");
     if (be::launch_pos_from_ids(h->gid_tmp + par * Pt, (int32_t)Pt, h->ghist_pos + (size_t)row * Pt)) return fail(DEMCMC_ECOMM, "history gather: %s", be::last_error());
     return 0;
 }
@@ -356,7 +361,7 @@ static int multi_create(const demcmc_config *cfg, demcmc_handle **out)
         for (int j = 0; j < N; ++j) { k->peers.rows[j] = p->kids[j]->mbox.rows; k->peers.flags[j] = p->kids[j]->mbox.flags; }
         k->mbox_on = true;
         MultiState *ms = p->multi;
-        k->mbox_barrier = [ms]() { if (be::sync()) return -1; ms->barrier.wait(); return 0; };
+        k->mbox_barrier = [ms]() { if (be::sync()) return -1; return ms->barrier.wait() ? 0 : -1; };
     }
     *out = p;
     return 0;
@@ -1327,7 +1332,12 @@ static int multi_run(demcmc_handle *h, const demcmc_tape *tape, int64_t n_iter)
                 if (int r = grow_history(k, stored_rows(k, k->iters_done + n_iter))) return r;
                 return be::sync() ? fail(DEMCMC_ECUDA, "%s", be::last_error()) : 0;
             }, false)) return rc;
-    const int rc = for_kids(h, [&](demcmc_handle *k, int) { return run_impl(k, tape, n_iter); });
+    h->multi->barrier.reset();
+    const int rc = for_kids(h, [&](demcmc_handle *k, int) {
+        const int r = run_impl(k, tape, n_iter);
+        if (r) h->multi->barrier.abort();                  // the peers must not wait for this device at a host barrier
+        return r;
+    });
     if (!rc) h->iters_done += n_iter;
     return rc;
 }
