@@ -247,6 +247,49 @@ def mvn_resample_check(n_iter, burnin, sd_atol, seed=505514):
     assert np.corrcoef(data.mean(axis=0), means)[0, 1] > 0.98
 
 
+def lnr_posterior_check():
+    """test/lognormal_race_tests.jl restated at its own size on the bound library: LNR(nu = [-2,-2,-3,-3], sigma = 1, tau = 0.5),
+    100 trials, DE(burnin = 2000, Np = 24, n_groups = 4), 5000 iterations through sample(..., MCMCThreads(), ...); the
+    assertions are the reference's (rhat within 0.05 of 1, posterior means and sds within 5 % of an independent sampler's).  The
+    independent sampler is NUTS there; here it is the random-walk Metropolis run of tests/golden/make_lnr_posterior.py
+    (scipy densities, no code of this repo), whose moments and Monte-Carlo errors are in tests/golden/lnr_posterior.json."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lnr_posterior.json")) as f:
+        gold = json.load(f)
+    assert max(gold["split_rhat"]) < 1.01 and np.all(np.array(gold["mcse_mean"]) < 0.01 * np.array(gold["sd"]) * 5)
+    choice, rt, min_rt = np.array(gold["choice"], np.int32), np.array(gold["rt"]), gold["min_rt"]
+    rng = np.random.default_rng(9918)
+    model = D.DEModel(sample_prior=lambda: [rng.normal(0, 3, 4), rng.uniform(0, min_rt)],
+                      prior_loglike=D.GPUPrior(D.Normal(0, 3), D.Uniform(0.0, min_rt)),
+                      loglike=D.GPULoglike("lnr", choice=choice, rt=rt), names=("ν", "τ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, min_rt)), burnin=2000, Np=24, n_groups=4, seed=3)
+    chains = D.sample(model, de, D.MCMCThreads(), 5000)
+    assert len(chains) == 3000 and chains.value.shape[2] == 96
+    mean, sd, rhat = chains.mean()[:5], chains.std()[:5], chains.rhat()[:5]
+    assert np.all(np.abs(rhat - 1.0) < 0.05), rhat                                     # lognormal_race_tests.jl:64
+    assert np.allclose(mean, gold["mean"], rtol=0.05), (mean, gold["mean"])            # :65
+    assert np.allclose(sd, gold["sd"], rtol=0.05), (sd, gold["sd"])                    # :66
+
+
+def blocking_posterior_check(seed=58122):
+    """test/blocking_tests.jl restated at its own size on the bound library: Normal(mu, sigma), 1000 observations,
+    blocks [[true, false], [false, true]] with blocking_on = x -> true, DE(burnin = 1000, Np = 6), 2000 iterations, through
+    both sample(model, de, n_iter) and sample(model, de, MCMCThreads(), n_iter); the reference's assertions (:59-62, :69-72)."""
+    rng = np.random.default_rng(seed)
+    data = rng.normal(0.0, 1.0, 1000)
+    model = D.DEModel(sample_prior=lambda: [rng.normal(0, 10), abs(rng.standard_cauchy())],
+                      prior_loglike=D.GPUPrior(D.Normal(0, 10), D.HalfCauchy(0, 1)),
+                      loglike=D.GPULoglike("gaussian", data), names=("μ", "σ"))
+    de = D.DE(sample_prior=model.sample_prior, bounds=((-np.inf, np.inf), (0.0, np.inf)), burnin=1000, Np=6, seed=seed,
+              blocking_on=lambda de_: True, blocks=[[True, False], [False, True]])
+    for args in ((2000,), (D.MCMCThreads(), 2000)):
+        chains = D.sample(model, de, *args)
+        assert len(chains) == 1000
+        mean, rhat = chains.mean()[:2], chains.rhat()[:2]
+        assert abs(mean[0] - 0.0) < 0.1 and abs(mean[1] - 1.0) < 0.1, mean
+        assert np.all(np.abs(rhat - 1.0) < 0.01), rhat
+
+
 def optimize_checks():
     """test/optimization_tests.jl restated on the bound library: Rastrigin minimum and Gaussian MLE."""
     # Rastrigin has a lattice of local minima and a greedy 6-particle population settles in one basin:

@@ -480,6 +480,14 @@ def test_resample_blocking_hierarchical(mode):      # Examples/Hierarchical_Exam
     check(r, out)
 
 
+def test_sample_api_lnr_posterior():                 # test/lognormal_race_tests.jl at its own size
+    common.lnr_posterior_check()
+
+
+def test_sample_api_blocking_posterior():            # test/blocking_tests.jl at its own size
+    common.blocking_posterior_check()
+
+
 def test_sample_api_mvn_resample():                 # test/multivariate_normal_tests.jl at its own size
     common.mvn_resample_check(n_iter=50_000, burnin=5000, sd_atol=0.01)
 

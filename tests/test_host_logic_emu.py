@@ -185,6 +185,14 @@ def test_sample_api_gaussian_posterior():
     assert len(D.sample(model, de2, D.MCMCThreads(), 250)) == 250
 
 
+def test_sample_api_lnr_posterior(emu):                 # test/lognormal_race_tests.jl at its own size
+    common.lnr_posterior_check()
+
+
+def test_sample_api_blocking_posterior():               # test/blocking_tests.jl at its own size
+    common.blocking_posterior_check()
+
+
 def test_sample_api_blocking_on_function():
     """DE(blocking_on = de -> ..., blocks = ...): the wrapper evaluates the function for every iteration with
     de.iter = iter + n_initial (src/main.jl:34,137,162) and hands the schedule to the library -- the chains
